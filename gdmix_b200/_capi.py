@@ -1,0 +1,309 @@
+"""ctypes binding of include/gdmix_b200.h.
+
+The library is the product: if ``lib/libgdmix_b200.so`` is missing or does not load, importing
+this module raises -- there is no CPU fallback anywhere in the package.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgdmix_b200.so")
+
+GDMIX_OK = 0
+GDMIX_ERR_INVALID = -1
+GDMIX_ERR_CUDA = -2
+GDMIX_ERR_WORKSPACE = -3
+GDMIX_ERR_TOO_LARGE = -4
+GDMIX_ERR_NO_DEVICE = -5
+GDMIX_MAX_M = 32
+
+VARIANCE_NONE, VARIANCE_SIMPLE, VARIANCE_FULL = 0, 1, 2
+EPS = float(np.finfo(np.float64).eps)
+
+# every symbol include/gdmix_b200.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_workspace_size",
+           "gdmix_re_loss_grad", "gdmix_re_fit", "gdmix_re_score", "gdmix_fe_loss_grad", "gdmix_fe_score",
+           "gdmix_re_fit_host", "gdmix_re_score_host", "gdmix_host_release", "gdmix_partition_ids",
+           "gdmix_launch_count"]
+
+
+class GdmixError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"gdmix_b200 error {code}: {msg}")
+        self.code = code
+
+
+class ReBatch(C.Structure):
+    _fields_ = [("n_entities", C.c_int64), ("n_rows", C.c_int64), ("nnz", C.c_int64),
+                ("ent_rowptr", C.c_void_p), ("rowptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p),
+                ("label", C.c_void_p), ("weight", C.c_void_p), ("offset", C.c_void_p), ("theta_ptr", C.c_void_p),
+                ("max_rows", C.c_int32), ("max_nnz", C.c_int32), ("max_coef", C.c_int32), ("reserved", C.c_int32)]
+
+
+class LrOpts(C.Structure):
+    _fields_ = [("l2", C.c_double), ("factr", C.c_double), ("pgtol", C.c_double),
+                ("sparsity_threshold", C.c_double), ("regularize_bias", C.c_int32), ("has_intercept", C.c_int32),
+                ("m", C.c_int32), ("max_iter", C.c_int32), ("max_ls", C.c_int32), ("max_fun", C.c_int32),
+                ("variance_mode", C.c_int32), ("threads_per_entity", C.c_int32)]
+
+
+class FeRows(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("nnz", C.c_int64), ("n_features", C.c_int64), ("rowptr", C.c_void_p),
+                ("col", C.c_void_p), ("val", C.c_void_p), ("label", C.c_void_p), ("weight", C.c_void_p),
+                ("offset", C.c_void_p), ("linear_regression", C.c_int32), ("num_workers", C.c_int32)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a).  gdmix_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.gdmix_last_error.restype = C.c_char_p
+    lib.gdmix_version.restype = C.c_char_p
+    lib.gdmix_launch_count.restype = C.c_int64
+    lib.gdmix_host_release.restype = None
+    for name in SYMBOLS:
+        getattr(lib, name)  # AttributeError if the build is stale
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc != GDMIX_OK:
+        raise GdmixError(rc, lib.gdmix_last_error().decode())
+
+
+def make_opts(l2=1.0, regularize_bias=False, has_intercept=True, m=10, max_iter=100, tol=1e-12, factr=None,
+              pgtol=1e-5, max_ls=20, max_fun=15000, sparsity_threshold=0.0, variance_mode=VARIANCE_NONE,
+              threads_per_entity=0):
+    """Defaults are what the reference hands to scipy (random_effect_lr_lbfgs_model.py:142-146); pgtol,
+    maxls and maxfun are scipy's own defaults because the reference never sets them."""
+    if factr is None:
+        factr = tol / EPS
+    return LrOpts(float(l2), float(factr), float(pgtol), float(sparsity_threshold), int(bool(regularize_bias)),
+                  int(bool(has_intercept)), int(m), int(max_iter), int(max_ls), int(max_fun), int(variance_mode),
+                  int(threads_per_entity))
+
+
+def device_info():
+    sm, smem, cc = C.c_int32(), C.c_int32(), C.c_int32()
+    check(lib.gdmix_device_info(C.byref(sm), C.byref(smem), C.byref(cc)))
+    return {"sm_count": sm.value, "smem_per_block_optin": smem.value, "cc": cc.value}
+
+
+def launch_count():
+    return int(lib.gdmix_launch_count())
+
+
+def _np_ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class HostBatch:
+    """A batch of entities in host memory (numpy), entity-local CSR -- gdmix_re_batch with host pointers."""
+
+    def __init__(self, ent_rowptr, rowptr, col, val, label, weight=None, offset=None, theta_ptr=None,
+                 has_intercept=True):
+        self.ent_rowptr = np.ascontiguousarray(ent_rowptr, dtype=np.int64)
+        self.rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+        self.col = np.ascontiguousarray(col, dtype=np.int32)
+        self.val = np.ascontiguousarray(val, dtype=np.float32)
+        self.label = np.ascontiguousarray(label, dtype=np.float32)
+        self.weight = None if weight is None else np.ascontiguousarray(weight, dtype=np.float32)
+        self.offset = None if offset is None else np.ascontiguousarray(offset, dtype=np.float32)
+        self.n_entities = len(self.ent_rowptr) - 1
+        self.n_rows = int(self.ent_rowptr[-1]) if self.n_entities >= 0 else 0
+        self.nnz = int(self.rowptr[self.n_rows])
+        assert self.rowptr.shape[0] == self.n_rows + 1 and self.col.shape[0] >= self.nnz
+        self.theta_ptr = np.ascontiguousarray(theta_ptr, dtype=np.int64)
+        assert self.theta_ptr.shape[0] == self.n_entities + 1
+        rows = np.diff(self.ent_rowptr)
+        nnz_e = self.rowptr[self.ent_rowptr[1:]] - self.rowptr[self.ent_rowptr[:-1]]
+        coef = np.diff(self.theta_ptr)
+        self.max_rows = int(rows.max()) if self.n_entities else 0
+        self.max_nnz = int(nnz_e.max()) if self.n_entities else 0
+        self.max_coef = int(coef.max()) if self.n_entities else 0
+        self.n_coef = int(self.theta_ptr[-1])
+
+    def c_struct(self):
+        return ReBatch(self.n_entities, self.n_rows, self.nnz, _np_ptr(self.ent_rowptr), _np_ptr(self.rowptr),
+                       _np_ptr(self.col), _np_ptr(self.val), _np_ptr(self.label), _np_ptr(self.weight),
+                       _np_ptr(self.offset), _np_ptr(self.theta_ptr), self.max_rows, self.max_nnz, self.max_coef, 0)
+
+    def algorithmic_bytes(self, warm=False):
+        """8 B/nnz + 16 B/sample + 8 B/coef out (+8 in when warm) + 4 B/feature index map."""
+        hi_total = self.n_coef
+        return 8 * self.nnz + 16 * self.n_rows + 8 * hi_total * (2 if warm else 1) + 4 * hi_total
+
+
+def re_fit_host(batch, opts, theta0=None, want_variance=False, chunk_entities=0):
+    """gdmix_re_fit_host: numpy in, numpy out (theta, f, nit, nfev, status[, variance])."""
+    E, T = batch.n_entities, batch.n_coef
+    theta = np.zeros(T, np.float64)
+    f = np.zeros(E, np.float64)
+    nit = np.zeros(E, np.int32)
+    nfev = np.zeros(E, np.int32)
+    status = np.zeros(E, np.int32)
+    var = np.zeros(T, np.float64) if want_variance else None
+    t0 = None if theta0 is None else np.ascontiguousarray(theta0, dtype=np.float64)
+    cb = batch.c_struct()
+    check(lib.gdmix_re_fit_host(C.byref(cb), C.byref(opts), _np_ptr(t0), _np_ptr(theta), _np_ptr(f), _np_ptr(nit),
+                                _np_ptr(nfev), _np_ptr(status), _np_ptr(var), C.c_int64(chunk_entities)))
+    out = {"theta": theta, "f": f, "nit": nit, "nfev": nfev, "status": status}
+    if want_variance:
+        out["variance"] = var
+    return out
+
+
+def re_score_host(batch, opts, theta, has_model=None):
+    logit = np.zeros(batch.n_rows, np.float32)
+    per = np.zeros(batch.n_rows, np.float32)
+    th = None if theta is None else np.ascontiguousarray(theta, dtype=np.float64)
+    hm = None if has_model is None else np.ascontiguousarray(has_model, dtype=np.uint8)
+    cb = batch.c_struct()
+    check(lib.gdmix_re_score_host(C.byref(cb), C.byref(opts), _np_ptr(th), _np_ptr(hm), _np_ptr(logit),
+                                  _np_ptr(per)))
+    return logit, per
+
+
+def partition_ids(ids, num_partitions):
+    """abs(String.hashCode(id)) % num_partitions for a list of str ids -> (hash int32[], partition int32[])."""
+    enc = [np.frombuffer(s.encode("utf-16-le"), dtype=np.uint16) for s in ids]
+    ptr = np.zeros(len(ids) + 1, np.int64)
+    if ids:
+        ptr[1:] = np.cumsum([len(u) for u in enc])
+    units = np.ascontiguousarray(np.concatenate(enc)) if ids and ptr[-1] > 0 else np.zeros(1, np.uint16)
+    h = np.zeros(len(ids), np.int32)
+    p = np.zeros(len(ids), np.int32)
+    check(lib.gdmix_partition_ids(_np_ptr(units), _np_ptr(ptr), C.c_int64(len(ids)), C.c_int32(num_partitions),
+                                  _np_ptr(h), _np_ptr(p)))
+    return h, p
+
+
+# ---- device-pointer entry points (torch tensors supply memory and the stream; plumbing only) ------
+
+def _tptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class DeviceBatch:
+    """gdmix_re_batch over torch CUDA tensors."""
+
+    def __init__(self, host: HostBatch, device="cuda"):
+        import torch
+        self.host = host
+        to = lambda a, pin=False: None if a is None else torch.from_numpy(a).to(device, non_blocking=False)
+        self.ent_rowptr, self.rowptr, self.theta_ptr = to(host.ent_rowptr), to(host.rowptr), to(host.theta_ptr)
+        self.col, self.val, self.label = to(host.col), to(host.val), to(host.label)
+        self.weight, self.offset = to(host.weight), to(host.offset)
+
+    def c_struct(self):
+        h = self.host
+        return ReBatch(h.n_entities, h.n_rows, h.nnz, _tptr(self.ent_rowptr), _tptr(self.rowptr), _tptr(self.col),
+                       _tptr(self.val), _tptr(self.label), _tptr(self.weight), _tptr(self.offset),
+                       _tptr(self.theta_ptr), h.max_rows, h.max_nnz, h.max_coef, 0)
+
+
+def re_workspace_size(cb, opts):
+    n = C.c_size_t()
+    check(lib.gdmix_re_workspace_size(C.byref(cb), C.byref(opts), C.byref(n)))
+    return n.value
+
+
+def _stream_ptr(stream):
+    import torch
+    s = torch.cuda.current_stream() if stream is None else stream
+    return C.c_void_p(s.cuda_stream)
+
+
+def re_fit_device(dbatch, opts, theta0=None, want_variance=False, workspace=None, out=None, stream=None):
+    """gdmix_re_fit on device tensors; asynchronous on the (current) torch stream."""
+    import torch
+    h = dbatch.host
+    dev = dbatch.val.device
+    cb = dbatch.c_struct()
+    need = re_workspace_size(cb, opts)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+    if out is None:
+        out = {"theta": torch.empty(h.n_coef, dtype=torch.float64, device=dev),
+               "f": torch.empty(h.n_entities, dtype=torch.float64, device=dev),
+               "nit": torch.empty(h.n_entities, dtype=torch.int32, device=dev),
+               "nfev": torch.empty(h.n_entities, dtype=torch.int32, device=dev),
+               "status": torch.empty(h.n_entities, dtype=torch.int32, device=dev)}
+        if want_variance:
+            out["variance"] = torch.empty(h.n_coef, dtype=torch.float64, device=dev)
+    check(lib.gdmix_re_fit(C.byref(cb), C.byref(opts), _tptr(theta0), _tptr(out["theta"]), _tptr(out["f"]),
+                           _tptr(out["nit"]), _tptr(out["nfev"]), _tptr(out["status"]),
+                           _tptr(out.get("variance")), _tptr(workspace), C.c_size_t(workspace.numel()),
+                           _stream_ptr(stream)))
+    out["workspace"] = workspace
+    return out
+
+
+def re_loss_grad_device(dbatch, opts, theta, stream=None):
+    import torch
+    h = dbatch.host
+    dev = dbatch.val.device
+    cb = dbatch.c_struct()
+    need = re_workspace_size(cb, opts)
+    ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+    f = torch.empty(h.n_entities, dtype=torch.float64, device=dev)
+    g = torch.empty(h.n_coef, dtype=torch.float64, device=dev)
+    check(lib.gdmix_re_loss_grad(C.byref(cb), C.byref(opts), _tptr(theta), _tptr(f), _tptr(g), _tptr(ws),
+                                 C.c_size_t(ws.numel()), _stream_ptr(stream)))
+    return f, g
+
+
+def re_score_device(dbatch, opts, theta, has_model=None, stream=None):
+    import torch
+    h = dbatch.host
+    dev = dbatch.val.device
+    logit = torch.empty(h.n_rows, dtype=torch.float32, device=dev)
+    per = torch.empty(h.n_rows, dtype=torch.float32, device=dev)
+    cb = dbatch.c_struct()
+    check(lib.gdmix_re_score(C.byref(cb), C.byref(opts), _tptr(theta), _tptr(has_model), _tptr(logit), _tptr(per),
+                             _stream_ptr(stream)))
+    return logit, per
+
+
+class DeviceFeRows:
+    def __init__(self, rowptr, col, val, label, weight, offset, n_features, linear_regression=False, num_workers=1,
+                 device="cuda"):
+        import torch
+        to = lambda a, dt: None if a is None else torch.as_tensor(np.ascontiguousarray(a, dtype=dt)).to(device)
+        self.rowptr, self.col, self.val = to(rowptr, np.int64), to(col, np.int32), to(val, np.float32)
+        self.label, self.weight, self.offset = to(label, np.float32), to(weight, np.float32), to(offset, np.float32)
+        self.n_rows = int(self.rowptr.numel() - 1)
+        self.nnz = int(self.col.numel())
+        self.n_features = int(n_features)
+        self.linear_regression, self.num_workers = bool(linear_regression), int(num_workers)
+
+    def c_struct(self):
+        return FeRows(self.n_rows, self.nnz, self.n_features, _tptr(self.rowptr), _tptr(self.col), _tptr(self.val),
+                      _tptr(self.label), _tptr(self.weight), _tptr(self.offset), int(self.linear_regression),
+                      self.num_workers)
+
+
+def fe_loss_grad_device(rows, opts, x, fg=None, stream=None):
+    """-> fg tensor [1 + D + has_intercept]: value then gradient (this rank's partial)."""
+    import torch
+    n = 1 + rows.n_features + (1 if opts.has_intercept else 0)
+    if fg is None:
+        fg = torch.empty(n, dtype=torch.float64, device=x.device)
+    cs = rows.c_struct()
+    check(lib.gdmix_fe_loss_grad(C.byref(cs), C.byref(opts), _tptr(x), _tptr(fg), _stream_ptr(stream)))
+    return fg
+
+
+def fe_score_device(rows, opts, x, stream=None):
+    import torch
+    logit = torch.empty(rows.n_rows, dtype=torch.float32, device=x.device)
+    per = torch.empty(rows.n_rows, dtype=torch.float32, device=x.device)
+    cs = rows.c_struct()
+    check(lib.gdmix_fe_score(C.byref(cs), C.byref(opts), _tptr(x), _tptr(logit), _tptr(per), _stream_ptr(stream)))
+    return logit, per

@@ -1,0 +1,553 @@
+// api.cu -- the extern "C" boundary declared in include/gdmix_b200.h: argument checks, launch
+// planning (threads per entity, shared memory per CTA, persistent grid), the host-buffer
+// pipeline (pinned staging, chunked H2D -> solve -> D2H on two streams) and the partition map.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/gdmix_b200.h"
+#include "aux_kernels.cuh"
+#include "re_solver.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                               \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return fail(GDMIX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                        __LINE__);                                                                   \
+    } while (0)
+
+struct DeviceInfo {
+    int sm_count = 0, smem_optin = 0, cc = 0;
+    bool ok = false;
+};
+
+int device_info(DeviceInfo &d)
+{
+    static std::mutex mu;
+    static DeviceInfo cached[64];
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 64 && cached[dev].ok) { d = cached[dev]; return GDMIX_OK; }
+    int major = 0, minor = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    d.cc = major * 10 + minor;
+    d.ok = true;
+    if (dev < 64) cached[dev] = d;
+    return GDMIX_OK;
+}
+
+// Launch plan for one batch shape.
+struct RePlan {
+    int G = 128;                 // threads per entity (= CTA size)
+    uint32_t smem = 0;           // dynamic shared memory per CTA
+    int ctas_per_sm = 1;
+    int grid = 1;
+    unsigned long long arena_stride = 0;  // per-CTA history spill in global memory
+    size_t workspace = 0;
+};
+
+constexpr size_t kQueueBytes = 256;
+constexpr uint32_t kStaticSmem = 2 * gdmix::kMaxWarps * gdmix::kRedK * 8 + 2 * GDMIX_MAX_M * 8 + 64;
+
+int choose_group(const gdmix_re_batch *b, const gdmix_lr_opts *o)
+{
+    if (o->threads_per_entity == 32 || o->threads_per_entity == 64 || o->threads_per_entity == 128 ||
+        o->threads_per_entity == 256)
+        return o->threads_per_entity;
+    // Rows and coefficients are the two thread-parallel axes; one thread per unit of the larger
+    // one, clamped to [32, 256].
+    const int span = std::max(b->max_rows, b->max_coef);
+    if (span <= 40) return 32;
+    if (span <= 96) return 64;
+    if (span <= 512) return 128;
+    return 256;
+}
+
+int plan_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &dev, RePlan &pl)
+{
+    if (b->max_rows <= 0 || b->max_coef <= 0 || b->max_nnz < 0)
+        return fail(GDMIX_ERR_INVALID, "gdmix_re_batch.max_rows/max_nnz/max_coef must be set (got %d/%d/%d)",
+                    b->max_rows, b->max_nnz, b->max_coef);
+    if (b->max_rows >= 65535 || b->max_coef >= 65535)
+        return fail(GDMIX_ERR_TOO_LARGE, "an entity has %d rows / %d coefficients; the on-chip index is 16 bit",
+                    b->max_rows, b->max_coef);
+    if (o->m < 0 || o->m > GDMIX_MAX_M) return fail(GDMIX_ERR_INVALID, "m = %d outside [0, %d]", o->m, GDMIX_MAX_M);
+    const uint32_t hi = o->has_intercept ? 1u : 0u;
+    if ((uint32_t)b->max_coef < hi) return fail(GDMIX_ERR_INVALID, "max_coef < has_intercept");
+    const gdmix::ReLayout L = gdmix::re_layout((uint32_t)b->max_rows, (uint32_t)b->max_nnz,
+                                               (uint32_t)b->max_coef - hi, (uint32_t)b->max_coef, (uint32_t)o->m);
+    const uint32_t budget = (uint32_t)dev.smem_optin - kStaticSmem;
+    if (L.fixed_bytes > budget)
+        return fail(GDMIX_ERR_TOO_LARGE,
+                    "largest entity (%d rows, %d nnz, %d coef) needs %u B of shared memory, device offers %u B",
+                    b->max_rows, b->max_nnz, b->max_coef, L.fixed_bytes, budget);
+    pl.G = choose_group(b, o);
+    const bool hist_on_chip = L.total_bytes <= budget;
+    pl.smem = hist_on_chip ? L.total_bytes : L.fixed_bytes;
+    pl.arena_stride = hist_on_chip ? 0ull : (unsigned long long)gdmix::align16(16u * o->m * b->max_coef);
+    // CTAs per SM: shared memory (228 KB per SM, 1 KB reserved per CTA), 2048 threads, 32 CTAs
+    const int by_smem = (int)((228u * 1024u) / (pl.smem + kStaticSmem + 1024u));
+    pl.ctas_per_sm = std::max(1, std::min({by_smem, 2048 / pl.G, 32}));
+    const int64_t want = (int64_t)dev.sm_count * pl.ctas_per_sm;
+    pl.grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, b->n_entities));
+    pl.workspace = kQueueBytes + (size_t)pl.arena_stride * (size_t)want;
+    return GDMIX_OK;
+}
+
+template <int G>
+int launch_re_t(const gdmix::ReArgs &args, const RePlan &pl, cudaStream_t st)
+{
+    static std::atomic<uint32_t> configured{0};
+    if (configured.load() < pl.smem) {
+        CUDA_TRY(cudaFuncSetAttribute(gdmix::re_solver_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024 - (int)kStaticSmem));
+        configured.store(227 * 1024);
+    }
+    gdmix::re_solver_kernel<G><<<pl.grid, G, pl.smem, st>>>(args);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
+int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const double *theta_in, double *theta_out,
+              double *f_out, int32_t *nit, int32_t *nfev, int32_t *status, double *var_out, double *g_out,
+              void *workspace, size_t workspace_bytes, cudaStream_t st)
+{
+    if (!b || !o) return fail(GDMIX_ERR_INVALID, "null batch/opts");
+    if (b->n_entities < 0) return fail(GDMIX_ERR_INVALID, "n_entities < 0");
+    if (b->n_entities == 0) return GDMIX_OK;
+    if (!b->ent_rowptr || !b->rowptr || !b->label || !b->theta_ptr || (b->nnz > 0 && (!b->col || !b->val)))
+        return fail(GDMIX_ERR_INVALID, "null array in gdmix_re_batch");
+    if (o->variance_mode == GDMIX_VARIANCE_FULL)
+        return fail(GDMIX_ERR_INVALID, "variance_mode FULL is not implemented on the device path");
+    DeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc) return rc;
+    if (dev.cc < 100) return fail(GDMIX_ERR_NO_DEVICE, "device compute capability %d < 100 (sm_100a build)", dev.cc);
+    RePlan pl;
+    rc = plan_re(b, o, dev, pl);
+    if (rc) return rc;
+    if (!workspace || workspace_bytes < pl.workspace)
+        return fail(GDMIX_ERR_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, pl.workspace);
+
+    gdmix::ReArgs a;
+    memset(&a, 0, sizeof(a));
+    a.b = *b; a.o = *o;
+    a.theta_in = theta_in; a.theta_out = theta_out; a.f_out = f_out; a.nit = nit; a.nfev = nfev; a.status = status;
+    a.var_out = var_out; a.g_out = g_out;
+    a.queue = (int32_t *)workspace;
+    a.arena = (unsigned char *)workspace + kQueueBytes;
+    a.arena_stride = pl.arena_stride;
+    a.mode = mode;
+    a.smem_bytes = pl.smem;
+    CUDA_TRY(cudaMemsetAsync(workspace, 0, kQueueBytes, st));
+    switch (pl.G) {
+    case 32: return launch_re_t<32>(a, pl, st);
+    case 64: return launch_re_t<64>(a, pl, st);
+    case 128: return launch_re_t<128>(a, pl, st);
+    default: return launch_re_t<256>(a, pl, st);
+    }
+}
+
+// ---- host-buffer pipeline ----------------------------------------------------------------------
+struct Slot {
+    cudaStream_t st = nullptr;
+    void *dev = nullptr; size_t dev_bytes = 0;
+    void *pin = nullptr; size_t pin_bytes = 0;
+    void *ws = nullptr; size_t ws_bytes = 0;
+};
+struct HostCtx {
+    std::mutex mu;
+    Slot slot[2];
+    int device = -1;
+} g_host;
+
+int ensure(Slot &s, size_t dev_bytes, size_t pin_bytes, size_t ws_bytes)
+{
+    if (!s.st) CUDA_TRY(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    if (s.dev_bytes < dev_bytes) {
+        if (s.dev) cudaFree(s.dev);
+        s.dev = nullptr; s.dev_bytes = 0;
+        CUDA_TRY(cudaMalloc(&s.dev, dev_bytes + dev_bytes / 4));
+        s.dev_bytes = dev_bytes + dev_bytes / 4;
+    }
+    if (s.pin_bytes < pin_bytes) {
+        if (s.pin) cudaFreeHost(s.pin);
+        s.pin = nullptr; s.pin_bytes = 0;
+        CUDA_TRY(cudaMallocHost(&s.pin, pin_bytes + pin_bytes / 4));
+        s.pin_bytes = pin_bytes + pin_bytes / 4;
+    }
+    if (s.ws_bytes < ws_bytes) {
+        if (s.ws) cudaFree(s.ws);
+        s.ws = nullptr; s.ws_bytes = 0;
+        CUDA_TRY(cudaMalloc(&s.ws, ws_bytes));
+        s.ws_bytes = ws_bytes;
+    }
+    return GDMIX_OK;
+}
+
+inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Carves a chunk's device image: inputs first, outputs after.  Returns total bytes.
+struct ChunkImage {
+    size_t ent_rowptr, rowptr, col, val, label, weight, offset, theta_ptr, theta0;  // inputs
+    size_t in_bytes;
+    size_t theta, f, nit, nfev, status, var;  // outputs
+    size_t total;
+};
+
+ChunkImage chunk_image(int64_t ne, int64_t nr, int64_t nz, int64_t nt, bool has_w, bool has_off, bool warm,
+                       bool want_var)
+{
+    ChunkImage c;
+    size_t o = 0;
+    c.ent_rowptr = o; o += up256(8 * (ne + 1));
+    c.rowptr = o; o += up256(8 * (nr + 1));
+    c.theta_ptr = o; o += up256(8 * (ne + 1));
+    c.col = o; o += up256(4 * nz);
+    c.val = o; o += up256(4 * nz);
+    c.label = o; o += up256(4 * nr);
+    c.weight = o; o += has_w ? up256(4 * nr) : 0;
+    c.offset = o; o += has_off ? up256(4 * nr) : 0;
+    c.theta0 = o; o += warm ? up256(8 * nt) : 0;
+    c.in_bytes = o;
+    c.theta = o; o += up256(8 * nt);
+    c.f = o; o += up256(8 * ne);
+    c.nit = o; o += up256(4 * ne);
+    c.nfev = o; o += up256(4 * ne);
+    c.status = o; o += up256(4 * ne);
+    c.var = o; o += want_var ? up256(8 * nt) : 0;
+    c.total = o;
+    return c;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *gdmix_last_error(void) { return g_err; }
+const char *gdmix_version(void) { return "gdmix_b200 0.1 (sm_100a)"; }
+int64_t gdmix_launch_count(void) { return g_launches.load(); }
+
+int gdmix_device_info(int32_t *sm_count, int32_t *smem_per_block_optin, int32_t *cc)
+{
+    DeviceInfo d;
+    int rc = device_info(d);
+    if (rc) return rc;
+    if (sm_count) *sm_count = d.sm_count;
+    if (smem_per_block_optin) *smem_per_block_optin = d.smem_optin;
+    if (cc) *cc = d.cc;
+    return GDMIX_OK;
+}
+
+int gdmix_re_workspace_size(const gdmix_re_batch *batch, const gdmix_lr_opts *opts, size_t *bytes)
+{
+    if (!batch || !opts || !bytes) return fail(GDMIX_ERR_INVALID, "null argument");
+    DeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc) return rc;
+    RePlan pl;
+    rc = plan_re(batch, opts, dev, pl);
+    if (rc) return rc;
+    *bytes = pl.workspace;
+    return GDMIX_OK;
+}
+
+int gdmix_re_loss_grad(const gdmix_re_batch *batch, const gdmix_lr_opts *opts, const double *theta, double *f,
+                       double *g, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!theta || !f || !g) return fail(GDMIX_ERR_INVALID, "null theta/f/g");
+    return launch_re(batch, opts, gdmix::kModeLossGrad, theta, nullptr, f, nullptr, nullptr, nullptr, nullptr, g,
+                     workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gdmix_re_fit(const gdmix_re_batch *batch, const gdmix_lr_opts *opts, const double *theta0, double *theta_out,
+                 double *f_out, int32_t *nit, int32_t *nfev, int32_t *status, double *var_out, void *workspace,
+                 size_t workspace_bytes, void *stream)
+{
+    if (!theta_out) return fail(GDMIX_ERR_INVALID, "null theta_out");
+    if (var_out && opts && opts->variance_mode == GDMIX_VARIANCE_NONE)
+        return fail(GDMIX_ERR_INVALID, "var_out given but variance_mode is NONE");
+    return launch_re(batch, opts, gdmix::kModeFit, theta0, theta_out, f_out, nit, nfev, status, var_out, nullptr,
+                     workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gdmix_re_score(const gdmix_re_batch *b, const gdmix_lr_opts *o, const double *theta, const uint8_t *has_model,
+                   float *logit, float *logit_pc, void *stream)
+{
+    if (!b || !o || !logit || !logit_pc) return fail(GDMIX_ERR_INVALID, "null argument");
+    if (b->n_entities <= 0) return GDMIX_OK;
+    DeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc) return rc;
+    const int64_t warps = b->n_entities;
+    const int grid = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)dev.sm_count * 8);
+    gdmix::re_score_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*b, o->has_intercept ? 1 : 0, theta, has_model,
+                                                                  logit, logit_pc);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
+int gdmix_fe_loss_grad(const gdmix_fe_rows *rows, const gdmix_lr_opts *o, const double *x, double *fg, void *stream)
+{
+    if (!rows || !o || !x || !fg) return fail(GDMIX_ERR_INVALID, "null argument");
+    DeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc) return rc;
+    const size_t len = (size_t)rows->n_features + (o->has_intercept ? 1 : 0) + 1;
+    CUDA_TRY(cudaMemsetAsync(fg, 0, 8 * len, (cudaStream_t)stream));
+    const int64_t work = std::max<int64_t>(rows->n_rows, rows->n_features + 1);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)dev.sm_count * 8));
+    gdmix::fe_loss_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*rows, *o, x, fg);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
+int gdmix_fe_score(const gdmix_fe_rows *rows, const gdmix_lr_opts *o, const double *x, float *logit, float *logit_pc,
+                   void *stream)
+{
+    if (!rows || !o || !x || !logit || !logit_pc) return fail(GDMIX_ERR_INVALID, "null argument");
+    if (rows->n_rows <= 0) return GDMIX_OK;
+    DeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc) return rc;
+    const int grid = (int)std::min<int64_t>((rows->n_rows + 255) / 256, (int64_t)dev.sm_count * 8);
+    gdmix::fe_score_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*rows, o->has_intercept ? 1 : 0, x, logit,
+                                                                  logit_pc);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
+// ---- host-buffer entry points --------------------------------------------------------------------
+
+int gdmix_re_fit_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const double *theta0, double *theta_out,
+                      double *f_out, int32_t *nit, int32_t *nfev, int32_t *status, double *var_out,
+                      int64_t chunk_entities)
+{
+    if (!hb || !o || !theta_out) return fail(GDMIX_ERR_INVALID, "null argument");
+    const int64_t E = hb->n_entities;
+    if (E <= 0) return GDMIX_OK;
+    if (!hb->ent_rowptr || !hb->rowptr || !hb->label || !hb->theta_ptr)
+        return fail(GDMIX_ERR_INVALID, "null array in gdmix_re_batch");
+    const bool want_var = var_out != nullptr;
+    if (want_var && o->variance_mode != GDMIX_VARIANCE_SIMPLE)
+        return fail(GDMIX_ERR_INVALID, "var_out needs variance_mode SIMPLE");
+    std::lock_guard<std::mutex> lk(g_host.mu);
+
+    // chunk boundaries: ~chunk_entities entities, or ~256 MB of input, whichever is smaller
+    if (chunk_entities <= 0) chunk_entities = 32768;
+    std::vector<int64_t> cuts;
+    cuts.push_back(0);
+    {
+        const size_t cap = (size_t)256 << 20;
+        int64_t e = 0;
+        while (e < E) {
+            int64_t e1 = std::min(E, e + chunk_entities);
+            auto bytes = [&](int64_t a, int64_t b2) {
+                const int64_t r0 = hb->ent_rowptr[a], r1 = hb->ent_rowptr[b2];
+                return (size_t)(8 * (hb->rowptr[r1] - hb->rowptr[r0]) + 20 * (r1 - r0));
+            };
+            while (e1 > e + 1 && bytes(e, e1) > cap) e1 = e + (e1 - e) / 2;
+            cuts.push_back(e1);
+            e = e1;
+        }
+    }
+    const size_t nchunks = cuts.size() - 1;
+    struct Pending { bool active = false; int64_t e0, e1, t0, nt; ChunkImage img; } pend[2];
+
+    auto drain = [&](int si) -> int {
+        Pending &p = pend[si];
+        if (!p.active) return GDMIX_OK;
+        Slot &s = g_host.slot[si];
+        CUDA_TRY(cudaStreamSynchronize(s.st));
+        const char *pin = (const char *)s.pin;
+        const int64_t ne = p.e1 - p.e0;
+        memcpy(theta_out + p.t0, pin + p.img.theta, 8 * p.nt);
+        if (f_out) memcpy(f_out + p.e0, pin + p.img.f, 8 * ne);
+        if (nit) memcpy(nit + p.e0, pin + p.img.nit, 4 * ne);
+        if (nfev) memcpy(nfev + p.e0, pin + p.img.nfev, 4 * ne);
+        if (status) memcpy(status + p.e0, pin + p.img.status, 4 * ne);
+        if (want_var) memcpy(var_out + p.t0, pin + p.img.var, 8 * p.nt);
+        p.active = false;
+        return GDMIX_OK;
+    };
+
+    for (size_t ci = 0; ci < nchunks; ci++) {
+        const int si = (int)(ci & 1);
+        int rc = drain(si);
+        if (rc) return rc;
+        const int64_t e0 = cuts[ci], e1 = cuts[ci + 1], ne = e1 - e0;
+        const int64_t r0 = hb->ent_rowptr[e0], r1 = hb->ent_rowptr[e1], nr = r1 - r0;
+        const int64_t q0 = hb->rowptr[r0], q1 = hb->rowptr[r1], nz = q1 - q0;
+        const int64_t t0 = hb->theta_ptr[e0], t1 = hb->theta_ptr[e1], nt = t1 - t0;
+        gdmix_re_batch db = *hb;
+        db.n_entities = ne; db.n_rows = nr; db.nnz = nz;
+        int32_t mr = 0, mz = 0, mc = 0;
+        for (int64_t e = e0; e < e1; e++) {
+            const int64_t a = hb->ent_rowptr[e], b2 = hb->ent_rowptr[e + 1];
+            mr = std::max<int64_t>(mr, b2 - a);
+            mz = (int32_t)std::max<int64_t>(mz, hb->rowptr[b2] - hb->rowptr[a]);
+            mc = (int32_t)std::max<int64_t>(mc, hb->theta_ptr[e + 1] - hb->theta_ptr[e]);
+        }
+        db.max_rows = mr; db.max_nnz = mz; db.max_coef = mc;
+        size_t ws_bytes = 0;
+        rc = gdmix_re_workspace_size(&db, o, &ws_bytes);
+        if (rc) return rc;
+        const ChunkImage img = chunk_image(ne, nr, nz, nt, hb->weight != nullptr, hb->offset != nullptr,
+                                           theta0 != nullptr, want_var);
+        Slot &s = g_host.slot[si];
+        rc = ensure(s, img.total, img.total, ws_bytes);
+        if (rc) return rc;
+        // pack inputs into pinned memory (pointer tables are rebased to the chunk)
+        char *pin = (char *)s.pin;
+        {
+            int64_t *p = (int64_t *)(pin + img.ent_rowptr);
+            for (int64_t i = 0; i <= ne; i++) p[i] = hb->ent_rowptr[e0 + i] - r0;
+            p = (int64_t *)(pin + img.rowptr);
+            for (int64_t i = 0; i <= nr; i++) p[i] = hb->rowptr[r0 + i] - q0;
+            p = (int64_t *)(pin + img.theta_ptr);
+            for (int64_t i = 0; i <= ne; i++) p[i] = hb->theta_ptr[e0 + i] - t0;
+        }
+        if (nz) {
+            memcpy(pin + img.col, hb->col + q0, 4 * nz);
+            memcpy(pin + img.val, hb->val + q0, 4 * nz);
+        }
+        memcpy(pin + img.label, hb->label + r0, 4 * nr);
+        if (hb->weight) memcpy(pin + img.weight, hb->weight + r0, 4 * nr);
+        if (hb->offset) memcpy(pin + img.offset, hb->offset + r0, 4 * nr);
+        if (theta0) memcpy(pin + img.theta0, theta0 + t0, 8 * nt);
+        CUDA_TRY(cudaMemcpyAsync(s.dev, pin, img.in_bytes, cudaMemcpyHostToDevice, s.st));
+        char *dv = (char *)s.dev;
+        db.ent_rowptr = (const int64_t *)(dv + img.ent_rowptr);
+        db.rowptr = (const int64_t *)(dv + img.rowptr);
+        db.theta_ptr = (const int64_t *)(dv + img.theta_ptr);
+        db.col = (const int32_t *)(dv + img.col);
+        db.val = (const float *)(dv + img.val);
+        db.label = (const float *)(dv + img.label);
+        db.weight = hb->weight ? (const float *)(dv + img.weight) : nullptr;
+        db.offset = hb->offset ? (const float *)(dv + img.offset) : nullptr;
+        rc = gdmix_re_fit(&db, o, theta0 ? (const double *)(dv + img.theta0) : nullptr, (double *)(dv + img.theta),
+                          (double *)(dv + img.f), (int32_t *)(dv + img.nit), (int32_t *)(dv + img.nfev),
+                          (int32_t *)(dv + img.status), want_var ? (double *)(dv + img.var) : nullptr, s.ws,
+                          s.ws_bytes, s.st);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(pin + img.theta, dv + img.theta, img.total - img.in_bytes, cudaMemcpyDeviceToHost,
+                                 s.st));
+        pend[si].active = true; pend[si].e0 = e0; pend[si].e1 = e1; pend[si].t0 = t0; pend[si].nt = nt;
+        pend[si].img = img;
+    }
+    int rc = drain(0);
+    if (rc) return rc;
+    rc = drain(1);
+    if (rc) return rc;
+    if (status) {
+        for (int64_t e = 0; e < E; e++)
+            if (status[e] < 0)
+                return fail(status[e], "entity %lld rejected by the device path (status %d)", (long long)e, status[e]);
+    }
+    return GDMIX_OK;
+}
+
+int gdmix_re_score_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const double *theta,
+                        const uint8_t *has_model, float *logit, float *logit_pc)
+{
+    if (!hb || !o || !logit || !logit_pc) return fail(GDMIX_ERR_INVALID, "null argument");
+    const int64_t E = hb->n_entities;
+    if (E <= 0) return GDMIX_OK;
+    std::lock_guard<std::mutex> lk(g_host.mu);
+    const int64_t nr = hb->ent_rowptr[E], nz = hb->rowptr[nr], nt = hb->theta_ptr[E];
+    size_t o_ent = 0, o_row = up256(8 * (E + 1)), o_tp = o_row + up256(8 * (nr + 1));
+    size_t o_col = o_tp + up256(8 * (E + 1)), o_val = o_col + up256(4 * nz), o_off = o_val + up256(4 * nz);
+    size_t o_th = o_off + up256(4 * nr), o_hm = o_th + up256(8 * nt), o_in = o_hm + up256(E);
+    size_t o_lg = o_in, o_pc = o_lg + up256(4 * nr), total = o_pc + up256(4 * nr);
+    Slot &s = g_host.slot[0];
+    int rc = ensure(s, total, 0, 0);
+    if (rc) return rc;
+    char *dv = (char *)s.dev;
+    CUDA_TRY(cudaMemcpyAsync(dv + o_ent, hb->ent_rowptr, 8 * (E + 1), cudaMemcpyHostToDevice, s.st));
+    CUDA_TRY(cudaMemcpyAsync(dv + o_row, hb->rowptr, 8 * (nr + 1), cudaMemcpyHostToDevice, s.st));
+    CUDA_TRY(cudaMemcpyAsync(dv + o_tp, hb->theta_ptr, 8 * (E + 1), cudaMemcpyHostToDevice, s.st));
+    if (nz) {
+        CUDA_TRY(cudaMemcpyAsync(dv + o_col, hb->col, 4 * nz, cudaMemcpyHostToDevice, s.st));
+        CUDA_TRY(cudaMemcpyAsync(dv + o_val, hb->val, 4 * nz, cudaMemcpyHostToDevice, s.st));
+    }
+    if (hb->offset) CUDA_TRY(cudaMemcpyAsync(dv + o_off, hb->offset, 4 * nr, cudaMemcpyHostToDevice, s.st));
+    if (theta) CUDA_TRY(cudaMemcpyAsync(dv + o_th, theta, 8 * nt, cudaMemcpyHostToDevice, s.st));
+    if (has_model) CUDA_TRY(cudaMemcpyAsync(dv + o_hm, has_model, E, cudaMemcpyHostToDevice, s.st));
+    gdmix_re_batch db = *hb;
+    db.ent_rowptr = (const int64_t *)(dv + o_ent);
+    db.rowptr = (const int64_t *)(dv + o_row);
+    db.theta_ptr = (const int64_t *)(dv + o_tp);
+    db.col = (const int32_t *)(dv + o_col);
+    db.val = (const float *)(dv + o_val);
+    db.label = nullptr; db.weight = nullptr;
+    db.offset = hb->offset ? (const float *)(dv + o_off) : nullptr;
+    rc = gdmix_re_score(&db, o, theta ? (const double *)(dv + o_th) : nullptr,
+                        has_model ? (const uint8_t *)(dv + o_hm) : nullptr, (float *)(dv + o_lg),
+                        (float *)(dv + o_pc), s.st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(logit, dv + o_lg, 4 * nr, cudaMemcpyDeviceToHost, s.st));
+    CUDA_TRY(cudaMemcpyAsync(logit_pc, dv + o_pc, 4 * nr, cudaMemcpyDeviceToHost, s.st));
+    CUDA_TRY(cudaStreamSynchronize(s.st));
+    return GDMIX_OK;
+}
+
+void gdmix_host_release(void)
+{
+    std::lock_guard<std::mutex> lk(g_host.mu);
+    for (Slot &s : g_host.slot) {
+        if (s.dev) cudaFree(s.dev);
+        if (s.pin) cudaFreeHost(s.pin);
+        if (s.ws) cudaFree(s.ws);
+        if (s.st) cudaStreamDestroy(s.st);
+        s = Slot();
+    }
+}
+
+int gdmix_partition_ids(const uint16_t *units, const int64_t *id_ptr, int64_t n_ids, int32_t num_partitions,
+                        int32_t *hash_out, int32_t *partition_out)
+{
+    if (!id_ptr || n_ids < 0 || num_partitions <= 0 || (!hash_out && !partition_out))
+        return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_partition_ids");
+    for (int64_t e = 0; e < n_ids; e++) {
+        uint32_t h = 0;
+        for (int64_t k = id_ptr[e]; k < id_ptr[e + 1]; k++) h = 31u * h + (uint32_t)units[k];
+        const int32_t hs = (int32_t)h;
+        if (hash_out) hash_out[e] = hs;
+        if (partition_out) {
+            const int32_t a = (hs == INT32_MIN) ? hs : (hs < 0 ? -hs : hs);  // Math.abs(Int.MinValue) < 0
+            partition_out[e] = a % num_partitions;                          // sign of the dividend, like the JVM
+        }
+    }
+    return GDMIX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,124 @@
+// aux_kernels.cuh -- scoring and fixed-effect streaming kernels (single pass, HBM bound).
+//
+// Reference semantics (gdmix-trainer/src/gdmix/):
+//   re_score_kernel     models/custom/scipy/job_consumers.py:138-152 (InferenceJobConsumer) +
+//                       models/custom/binary_logistic_regression.py:241-262 (predict_proba, logits)
+//   fe_loss_grad_kernel models/custom/fixed_effect_lr_lbfgs_model.py:309-381 (_train_model_fn, one worker's
+//                       partial sum before the all-reduce; intercept LAST; no 1/n)
+//   fe_score_kernel     fixed_effect_lr_lbfgs_model.py:214-270 (_scoring_fn logits)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gdmix_b200.h"
+
+namespace gdmix {
+
+// One warp per entity, lanes over the entity's samples.  theta is read through L2 (each entity's
+// coefficients are touched by one warp only), X once from HBM.
+__global__ void __launch_bounds__(256) re_score_kernel(const gdmix_re_batch b, const int hi, const double *theta,
+                                                       const uint8_t *has_model, float *logit, float *logit_pc)
+{
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int64_t e = warp; e < b.n_entities; e += nwarps) {
+        const int64_t r0 = b.ent_rowptr[e], r1 = b.ent_rowptr[e + 1];
+        const bool model = theta != nullptr && (has_model == nullptr || has_model[e] != 0);
+        const double *th = model ? theta + b.theta_ptr[e] : nullptr;
+        for (int64_t i = r0 + lane; i < r1; i += 32) {
+            const double offs = b.offset ? (double)b.offset[i] : 0.0;
+            double z;
+            if (model) {
+                z = hi ? th[0] : 0.0;
+                const int64_t qs = b.rowptr[i], qe = b.rowptr[i + 1];
+                for (int64_t q = qs; q < qe; q++) z = fma((double)b.val[q], th[hi + b.col[q]], z);
+                z = z + offs;
+            } else {
+                z = offs;
+            }
+            logit[i] = (float)z;
+            logit_pc[i] = (float)(z - offs);
+        }
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Fixed-effect partial objective and gradient over this rank's rows.  fg[0] = value,
+// fg[1 + j] = gradient of coefficient j (intercept at j = D).  Thread per row; the scatter
+// into the (L2-resident, 8*(D+2) byte) accumulator uses fp64 RED atomics.
+__global__ void __launch_bounds__(256) fe_loss_grad_kernel(const gdmix_fe_rows R, const gdmix_lr_opts o,
+                                                           const double *x, double *fg)
+{
+    const int hi = o.has_intercept ? 1 : 0;
+    const int64_t D = R.n_features;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    const double b0 = hi ? x[D] : 0.0;
+    double value = 0.0, dz_sum = 0.0;
+    for (int64_t i = tid; i < R.n_rows; i += nth) {
+        const int64_t qs = R.rowptr[i], qe = R.rowptr[i + 1];
+        double z = 0.0;
+        for (int64_t q = qs; q < qe; q++) z = fma((double)R.val[q], x[R.col[q]], z);
+        z += R.offset ? (double)R.offset[i] : 0.0;
+        z += b0;
+        const double yi = (double)R.label[i], wi = R.weight ? (double)R.weight[i] : 1.0;
+        double dz;
+        if (R.linear_regression) {
+            const double e = yi - z;
+            value = fma(wi * e, e, value);
+            dz = -2.0 * wi * e;
+        } else {
+            const double ex = exp(-fabs(z));
+            value = fma(wi, fmax(z, 0.0) - z * yi + log1p(ex), value);
+            const double inv = 1.0 / (1.0 + ex);
+            dz = wi * ((z >= 0.0 ? inv : ex * inv) - yi);
+        }
+        for (int64_t q = qs; q < qe; q++) atomicAdd(&fg[1 + R.col[q]], (double)R.val[q] * dz);
+        dz_sum += dz;
+    }
+    // L2 term (the reference adds l2 * l2_loss(x_reg) / num_workers on every worker)
+    const int64_t preg = (hi && !o.regularize_bias) ? D : D + hi;
+    const double nw = (double)(R.num_workers > 0 ? R.num_workers : 1);
+    for (int64_t j = tid; j < preg; j += nth) {
+        const double xj = x[j];
+        value = fma(0.5 * o.l2 / nw * xj, xj, value);
+        atomicAdd(&fg[1 + j], o.l2 * xj / nw);
+    }
+    value = warp_sum(value);
+    dz_sum = warp_sum(dz_sum);
+    __shared__ double sv[8], sd[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sv[warp] = value; sd[warp] = dz_sum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0, dsum = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { v += sv[w]; dsum += sd[w]; }
+        atomicAdd(&fg[0], v);
+        if (hi) atomicAdd(&fg[1 + D], dsum);
+    }
+}
+
+__global__ void __launch_bounds__(256) fe_score_kernel(const gdmix_fe_rows R, const int hi, const double *x,
+                                                       float *logit, float *logit_pc)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    const double b0 = hi ? x[R.n_features] : 0.0;
+    for (int64_t i = tid; i < R.n_rows; i += nth) {
+        double z = 0.0;
+        for (int64_t q = R.rowptr[i]; q < R.rowptr[i + 1]; q++) z = fma((double)R.val[q], x[R.col[q]], z);
+        z += b0;
+        const double offs = R.offset ? (double)R.offset[i] : 0.0;
+        logit_pc[i] = (float)z;
+        logit[i] = (float)(z + offs);
+    }
+}
+
+}  // namespace gdmix

@@ -1,0 +1,200 @@
+/*
+ * gdmix_b200.h -- C ABI of the B200-native random-effect / fixed-effect LR trainer.
+ *
+ * This is the drop-in boundary for ONE hot path of linkedin/gdmix: the per-entity
+ * L2-regularised logistic-regression solves of the random-effect trainer, the
+ * fixed-effect objective/gradient that feeds the global L-BFGS step, and the
+ * scoring pass that follows both.  The reference has no FFI on this path -- its
+ * numerical seam is Python calling scipy once per entity -- so every entry point
+ * below names the reference call it replaces (paths relative to
+ * gdmix-trainer/src/gdmix/ in the reference tree):
+ *
+ *   gdmix_re_fit         TrainingJobConsumer.__call__            models/custom/scipy/job_consumers.py:36-63
+ *                        -> BinaryLogisticRegressionTrainer.fit  models/custom/binary_logistic_regression.py:191-239
+ *                        -> scipy.optimize.fmin_l_bfgs_b         (L-BFGS-B 3.0, un-vendored dependency)
+ *                        + threshold_coefficients                util/model_utils.py:4-12
+ *                        + _compute_variance (SIMPLE)            binary_logistic_regression.py:144-189
+ *   gdmix_re_loss_grad   _loss / _gradient                       binary_logistic_regression.py:84-131
+ *   gdmix_re_score       InferenceJobConsumer.__call__           job_consumers.py:138-152
+ *                        -> predict_proba(return_logits=True)    binary_logistic_regression.py:241-262
+ *   gdmix_fe_loss_grad   _train_model_fn (per-worker partial)    models/custom/fixed_effect_lr_lbfgs_model.py:309-381
+ *                        (the all-reduce at :382-390 stays with the caller: NCCL on the same stream)
+ *   gdmix_fe_score       _scoring_fn                             fixed_effect_lr_lbfgs_model.py:214-307
+ *   gdmix_partition_ids  getPartitionIdUDF                       gdmix-data/.../utils/PartitionUtils.scala:31-37
+ *
+ * Conventions
+ *   - All array pointers in gdmix_re_batch / gdmix_fe_rows are DEVICE pointers owned by
+ *     the caller, except in the *_host entry points which take host pointers and do
+ *     their own pinned staging, H2D/D2H copies and chunking.
+ *   - Functions enqueue work on `stream` (a cudaStream_t passed as void*) and return
+ *     without synchronising unless stated.  They are re-entrant per stream as long as
+ *     each stream uses its own workspace.
+ *   - Return value: 0 (GDMIX_OK) or a negative gdmix_status.  gdmix_last_error() gives a
+ *     thread-local message.  No exceptions cross this boundary; nothing is allocated
+ *     behind the caller's back by the device-pointer entry points.
+ *   - Coefficient vectors: random effect = intercept FIRST (if has_intercept), then the
+ *     entity's local features in ascending local index; fixed effect = intercept LAST
+ *     (the reference's conventions, binary_logistic_regression.py:133-142 vs
+ *     fixed_effect_lr_lbfgs_model.py:345-351).
+ *   - Arithmetic: objective, gradient and all solver state are fp64 (trajectory parity
+ *     with scipy requires it); feature values / labels / weights / offsets are fp32 in
+ *     HBM, exactly what the TFRecords hold.
+ */
+#ifndef GDMIX_B200_H
+#define GDMIX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define GDMIX_API
+#else
+#define GDMIX_API __attribute__((visibility("default")))
+#endif
+
+typedef enum gdmix_status {
+    GDMIX_OK = 0,
+    GDMIX_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, m > GDMIX_MAX_M ...) */
+    GDMIX_ERR_CUDA = -2,        /* a CUDA runtime call failed; message has cudaGetErrorString */
+    GDMIX_ERR_WORKSPACE = -3,   /* workspace too small */
+    GDMIX_ERR_TOO_LARGE = -4,   /* an entity exceeds what the kernels index (rows/features >= 65535) */
+    GDMIX_ERR_NO_DEVICE = -5    /* no sm_100 device */
+} gdmix_status;
+
+#define GDMIX_MAX_M 32          /* largest supported number of L-BFGS curvature pairs */
+
+/* Per-entity solver status, mirrors scipy's warnflag (fmin_l_bfgs_b). */
+#define GDMIX_SOLVE_CONVERGED 0 /* pgtol or factr test passed */
+#define GDMIX_SOLVE_MAXITER 1   /* maxiter / maxfun reached */
+#define GDMIX_SOLVE_ABNORMAL 2  /* line search failed with empty memory */
+
+#define GDMIX_VARIANCE_NONE 0
+#define GDMIX_VARIANCE_SIMPLE 1
+#define GDMIX_VARIANCE_FULL 2   /* not implemented by the device path yet: returns GDMIX_ERR_INVALID */
+
+/* A batch of entities in entity-local CSR form: what prepare_jobs
+ * (job_consumers.py:161-296) hands to the consumers, flattened.  Entity e owns samples
+ * [ent_rowptr[e], ent_rowptr[e+1]); sample i owns non-zeros [rowptr[i], rowptr[i+1]);
+ * col holds the entity-LOCAL feature index (rank of the global id among the entity's
+ * sorted unique ids, job_consumers.py:243); coefficients of entity e live at
+ * theta[theta_ptr[e] .. theta_ptr[e+1]) with length d_e + has_intercept. */
+typedef struct gdmix_re_batch {
+    int64_t n_entities;
+    int64_t n_rows;
+    int64_t nnz;
+    const int64_t *ent_rowptr; /* [n_entities + 1] */
+    const int64_t *rowptr;     /* [n_rows + 1] */
+    const int32_t *col;        /* [nnz] */
+    const float *val;          /* [nnz] */
+    const float *label;        /* [n_rows] 0/1 */
+    const float *weight;       /* [n_rows] or NULL (= 1) */
+    const float *offset;       /* [n_rows] or NULL (= 0) */
+    const int64_t *theta_ptr;  /* [n_entities + 1] */
+    /* Upper bounds over the batch, known to the host from ingest.  They size shared
+     * memory and the launch geometry; the kernels re-check each entity against them. */
+    int32_t max_rows;          /* max samples of one entity */
+    int32_t max_nnz;           /* max non-zeros of one entity */
+    int32_t max_coef;          /* max coefficients (d_e + has_intercept) of one entity */
+    int32_t reserved;
+} gdmix_re_batch;
+
+/* LRParams / scipy knobs (base_lr_params.py:5-42; scipy defaults for the rest). */
+typedef struct gdmix_lr_opts {
+    double l2;                  /* l2_reg_weight */
+    double factr;               /* lbfgs_tolerance / eps */
+    double pgtol;               /* 1e-5: scipy default, the reference never overrides it */
+    double sparsity_threshold;  /* |theta| <= thr -> 0 on output; 0 disables */
+    int32_t regularize_bias;
+    int32_t has_intercept;
+    int32_t m;                  /* num_of_lbfgs_curvature_pairs */
+    int32_t max_iter;           /* num_of_lbfgs_iterations */
+    int32_t max_ls;             /* 20 */
+    int32_t max_fun;            /* 15000 */
+    int32_t variance_mode;      /* GDMIX_VARIANCE_* */
+    int32_t threads_per_entity; /* 0 = choose; else 32/64/128/256 */
+} gdmix_lr_opts;
+
+/* Rows of the fixed-effect shard this rank owns (per_record_input_fn output, flattened). */
+typedef struct gdmix_fe_rows {
+    int64_t n_rows;
+    int64_t nnz;
+    int64_t n_features;       /* D: x has D + has_intercept entries, intercept LAST */
+    const int64_t *rowptr;    /* [n_rows + 1] */
+    const int32_t *col;       /* [nnz] global feature index < D */
+    const float *val;         /* [nnz] */
+    const float *label;       /* [n_rows] */
+    const float *weight;      /* [n_rows] or NULL */
+    const float *offset;      /* [n_rows] or NULL */
+    int32_t linear_regression; /* 0: logistic loss, 1: squared error (fixed_effect_lr_lbfgs_model.py:356-358) */
+    int32_t num_workers;       /* the reference adds l2/num_workers per worker before the all-reduce (:375-381) */
+} gdmix_fe_rows;
+
+GDMIX_API const char *gdmix_last_error(void);
+GDMIX_API const char *gdmix_version(void);
+
+/* Device facts the host side needs for its own planning: SM count, max opt-in shared
+ * memory per block, compute capability major*10+minor.  Any pointer may be NULL. */
+GDMIX_API int gdmix_device_info(int32_t *sm_count, int32_t *smem_per_block_optin, int32_t *cc);
+
+/* Bytes of device scratch gdmix_re_fit / gdmix_re_loss_grad need for this batch shape
+ * (only n_entities, max_rows, max_nnz, max_coef and opts are read). */
+GDMIX_API int gdmix_re_workspace_size(const gdmix_re_batch *batch, const gdmix_lr_opts *opts, size_t *bytes);
+
+/* K1 test seam: f[e], g[theta_ptr[e]..] at a caller-supplied theta for every entity. */
+GDMIX_API int gdmix_re_loss_grad(const gdmix_re_batch *batch, const gdmix_lr_opts *opts, const double *theta,
+                                 double *f, double *g, void *workspace, size_t workspace_bytes, void *stream);
+
+/* The hot path: stage each entity's block once into shared memory and run L-BFGS-B
+ * (as scipy.fmin_l_bfgs_b runs it without bounds) to completion on chip.
+ *   theta0      NULL = cold start (zeros), else warm-start coefficients (same layout as theta_out)
+ *   theta_out   [theta_ptr[E]] coefficients (thresholded if opts->sparsity_threshold > 0)
+ *   f_out,nit,nfev,status   [E], any may be NULL
+ *   var_out     [theta_ptr[E]] or NULL; needs opts->variance_mode == GDMIX_VARIANCE_SIMPLE */
+GDMIX_API int gdmix_re_fit(const gdmix_re_batch *batch, const gdmix_lr_opts *opts, const double *theta0,
+                           double *theta_out, double *f_out, int32_t *nit, int32_t *nfev, int32_t *status,
+                           double *var_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Scoring: logit = x.theta (+ intercept) + offset, per_coordinate = logit - offset, both
+ * rounded to fp32 as the reference's Avro `float` fields are.  has_model[e] == 0 (or
+ * theta == NULL) means "no model for this entity": logit = offset (job_consumers.py:145-146). */
+GDMIX_API int gdmix_re_score(const gdmix_re_batch *batch, const gdmix_lr_opts *opts, const double *theta,
+                             const uint8_t *has_model, float *logit, float *logit_per_coordinate, void *stream);
+
+/* Fixed effect: fg[0] = sum_rows w*loss + l2/2*|x_reg|^2/num_workers, fg[1..D+has_intercept] =
+ * gradient (same partial the reference all-reduces).  fg is zeroed by the call.  The caller
+ * all-reduces fg (NCCL, same stream) and feeds it to the replicated L-BFGS step. */
+GDMIX_API int gdmix_fe_loss_grad(const gdmix_fe_rows *rows, const gdmix_lr_opts *opts, const double *x, double *fg,
+                                 void *stream);
+GDMIX_API int gdmix_fe_score(const gdmix_fe_rows *rows, const gdmix_lr_opts *opts, const double *x, float *logit,
+                             float *logit_per_coordinate, void *stream);
+
+/* Host-buffer form of gdmix_re_fit: every pointer (batch arrays, theta0, outputs) is HOST
+ * memory.  The library owns device buffers and pinned staging, splits the batch into
+ * chunks of about `chunk_entities` entities (0 = choose) and overlaps H2D copy, solve and
+ * D2H copy on its own streams.  Synchronous: returns when the outputs are in host memory.
+ * This is the call the Python plugin classes make. */
+GDMIX_API int gdmix_re_fit_host(const gdmix_re_batch *host_batch, const gdmix_lr_opts *opts, const double *theta0,
+                                double *theta_out, double *f_out, int32_t *nit, int32_t *nfev, int32_t *status,
+                                double *var_out, int64_t chunk_entities);
+GDMIX_API int gdmix_re_score_host(const gdmix_re_batch *host_batch, const gdmix_lr_opts *opts, const double *theta,
+                                  const uint8_t *has_model, float *logit, float *logit_per_coordinate);
+/* Releases the cached device/pinned buffers of the *_host entry points. */
+GDMIX_API void gdmix_host_release(void);
+
+/* Entity -> partition map, bit-exact with the JVM: abs(String.hashCode(id)) % num_partitions
+ * (Math.abs(Int.MinValue) stays negative and % keeps the dividend's sign).  ids are UTF-16
+ * code units, entity e owning units[id_ptr[e] .. id_ptr[e+1]).  Host function. */
+GDMIX_API int gdmix_partition_ids(const uint16_t *units, const int64_t *id_ptr, int64_t n_ids,
+                                  int32_t num_partitions, int32_t *hash_out, int32_t *partition_out);
+
+/* Number of kernel launches issued by this library since load (for bench accounting). */
+GDMIX_API int64_t gdmix_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDMIX_B200_H */

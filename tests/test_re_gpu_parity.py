@@ -1,0 +1,188 @@
+"""GPU parity: the CUDA random-effect path (through the C ABI) against the CPU oracle and against the
+golden vectors the reference itself produced.  Tolerance per BASELINE.json north_star: coefficients within
+1e-5 relative of the reference solver (we assert much tighter where the reference pins its own answer)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():  # pragma: no cover
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from gdmix_b200 import _capi as capi  # noqa: E402
+from gdmix_b200.synthetic import make_batch  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from tests.golden_util import is_pinned, load_re  # noqa: E402
+
+REL_TOL = 1e-5  # north_star tolerance
+
+
+def _oracle_opts(o):
+    return O.Opts(o.l2, o.regularize_bias, o.has_intercept, o.m, o.max_iter, o.max_ls, o.max_fun, o.factr, o.pgtol)
+
+
+def _oracle_batch(hb):
+    return {"ent_rowptr": hb.ent_rowptr, "rowptr": hb.rowptr, "col": hb.col, "val": hb.val, "y": hb.label,
+            "w": hb.weight if hb.weight is not None else np.ones(hb.n_rows, np.float32),
+            "off": hb.offset if hb.offset is not None else np.zeros(hb.n_rows, np.float32),
+            "theta_ptr": hb.theta_ptr}
+
+
+def _rel_per_entity(a, b, ptr):
+    out = np.zeros(len(ptr) - 1)
+    for e in range(len(ptr) - 1):
+        x, y = a[ptr[e]:ptr[e + 1]], b[ptr[e]:ptr[e + 1]]
+        out[e] = np.linalg.norm(x - y) / max(np.linalg.norm(y), 1e-300)
+    return out
+
+
+def _golden_batch(cases, arr):
+    """Packs golden cases that share solver options into one HostBatch."""
+    ent, rowptr, cols, vals, ys, ws, offs, tptr = [0], [0], [], [], [], [], [], [0]
+    for c in cases:
+        k = c["key"]
+        rp = arr[k + "_rowptr"]
+        rowptr.extend((rp[1:] + rowptr[-1]).tolist())
+        ent.append(ent[-1] + c["n"])
+        cols.append(arr[k + "_col"]); vals.append(arr[k + "_val"]); ys.append(arr[k + "_y"])
+        ws.append(arr[k + "_w"]); offs.append(arr[k + "_off"])
+        tptr.append(tptr[-1] + c["d"] + (1 if c["has_intercept"] else 0))
+    return capi.HostBatch(np.array(ent), np.array(rowptr), np.concatenate(cols), np.concatenate(vals),
+                          np.concatenate(ys), np.concatenate(ws), np.concatenate(offs), np.array(tptr))
+
+
+def _group_key(c):
+    return (c["l2"], c["regularize_bias"], c["has_intercept"], c["m"], c["max_iter"], c["tol"])
+
+
+ARR, CASES = load_re()
+GROUPS = {}
+for _c in CASES:
+    GROUPS.setdefault(_group_key(_c), []).append(_c)
+
+
+@pytest.mark.parametrize("threads", [0, 32, 64, 128, 256])
+def test_golden_fit_matches_reference(threads):
+    """Every golden case (reference fixtures + synthetic + edge cases + warm starts) through gdmix_re_fit_host."""
+    worst = 0.0
+    for key, cases in GROUPS.items():
+        l2, rb, hi, m, maxit, tol = key
+        hb = _golden_batch(cases, ARR)
+        theta0 = np.concatenate([ARR[c["key"] + "_theta0"] if c["warm"] else
+                                 np.zeros(c["d"] + (1 if hi else 0)) for c in cases])
+        opts = capi.make_opts(l2=l2, regularize_bias=rb, has_intercept=hi, m=m, max_iter=maxit, tol=tol,
+                              threads_per_entity=threads)
+        out = capi.re_fit_host(hb, opts, theta0=theta0)
+        for i, c in enumerate(cases):
+            th = out["theta"][hb.theta_ptr[i]:hb.theta_ptr[i + 1]]
+            ref = ARR[c["key"] + "_theta"]
+            if is_pinned(c):
+                rel = np.linalg.norm(th - ref) / max(np.linalg.norm(ref), 1e-300)
+                worst = max(worst, rel)
+                assert rel <= 1e-7, (c["name"], rel)
+                assert (out["nit"][i], out["nfev"][i], out["status"][i]) == (c["nit"], c["nfev"], c["warnflag"]), c["name"]
+                assert abs(out["f"][i] - c["f"]) <= 1e-11 * max(1.0, abs(c["f"])), c["name"]
+            else:
+                assert out["status"][i] == 0 and abs(out["f"][i] - c["f"]) <= 1e-5, c["name"]
+    print("worst relative coefficient error vs reference:", worst)
+
+
+def test_golden_loss_grad_matches_reference():
+    """K1 seam: f and g at the reference's probe points (binary_logistic_regression.py:84-131)."""
+    for key, cases in GROUPS.items():
+        l2, rb, hi, m, maxit, tol = key
+        hb = _golden_batch(cases, ARR)
+        probe = np.concatenate([ARR[c["key"] + "_probe"] for c in cases])
+        opts = capi.make_opts(l2=l2, regularize_bias=rb, has_intercept=hi, m=m, max_iter=maxit, tol=tol)
+        db = capi.DeviceBatch(hb)
+        f, g = capi.re_loss_grad_device(db, opts, torch.from_numpy(probe).cuda())
+        torch.cuda.synchronize()
+        f, g = f.cpu().numpy(), g.cpu().numpy()
+        for i, c in enumerate(cases):
+            assert abs(f[i] - c["probe_f"]) <= 1e-13 * max(1.0, abs(c["probe_f"])), c["name"]
+            np.testing.assert_allclose(g[hb.theta_ptr[i]:hb.theta_ptr[i + 1]], ARR[c["key"] + "_probe_g"],
+                                       rtol=1e-11, atol=1e-13, err_msg=c["name"])
+
+
+@pytest.mark.parametrize("shape", [(128, 256, 32, False), (32, 64, 8, False), (64, 64, 16, True),
+                                   (106, 20, 6, True), (16, 24, 4, False)])
+def test_synthetic_batch_matches_oracle(shape):
+    """Seeded synthetic entities (C1 / C3 / C4 / MovieLens-like shapes): CUDA vs oracle on the same bytes."""
+    n, d, k, ragged = shape
+    E = 400
+    hb = make_batch(E, n, d, k, seed=7 + n, ragged=ragged, weights=ragged)
+    opts = capi.make_opts(l2=1.0, regularize_bias=False, has_intercept=True)
+    out = capi.re_fit_host(hb, opts, chunk_entities=150)  # exercises the chunked pipeline too
+    th_o, f_o, nit_o, nfev_o, st_o = O.re_fit_batch(_oracle_batch(hb), _oracle_opts(opts))
+    rel = _rel_per_entity(out["theta"], th_o, hb.theta_ptr)
+    frac = float((rel <= REL_TOL).mean())
+    print(f"shape {shape}: max rel {rel.max():.3e}, frac<=1e-5 {frac:.4f}, nit equal {(out['nit'] == nit_o).mean():.4f}")
+    assert rel.max() <= REL_TOL
+    assert (out["nit"] == nit_o).all() and (out["nfev"] == nfev_o).all() and (out["status"] == st_o).all()
+    np.testing.assert_allclose(out["f"], f_o, rtol=1e-11)
+
+
+def test_device_api_matches_host_api():
+    hb = make_batch(300, 64, 64, 16, seed=3)
+    opts = capi.make_opts(l2=0.5)
+    host = capi.re_fit_host(hb, opts)
+    dev = capi.re_fit_device(capi.DeviceBatch(hb), opts)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(dev["theta"].cpu().numpy(), host["theta"])
+    np.testing.assert_array_equal(dev["nit"].cpu().numpy(), host["nit"])
+
+
+def test_run_to_run_bitwise_reproducible():
+    hb = make_batch(500, 128, 256, 32, seed=11)
+    opts = capi.make_opts()
+    a = capi.re_fit_host(hb, opts)
+    b = capi.re_fit_host(hb, opts, chunk_entities=97)
+    np.testing.assert_array_equal(a["theta"], b["theta"])
+    np.testing.assert_array_equal(a["f"], b["f"])
+
+
+def test_threshold_and_variance_simple():
+    """threshold_coefficients (model_utils.py:4-12) and SIMPLE variance (binary_logistic_regression.py:171-177)."""
+    hb = make_batch(64, 40, 24, 6, seed=5, weights=True)
+    raw = capi.re_fit_host(hb, capi.make_opts(l2=1.0))
+    thr = capi.re_fit_host(hb, capi.make_opts(l2=1.0, sparsity_threshold=1e-4, variance_mode=capi.VARIANCE_SIMPLE),
+                           want_variance=True)
+    expect = np.where(np.abs(raw["theta"]) <= 1e-4, 0.0, raw["theta"])
+    np.testing.assert_array_equal(thr["theta"], expect)
+    ob = _oracle_batch(hb)
+    oo = _oracle_opts(capi.make_opts(l2=1.0))
+    for e in range(0, 64, 7):
+        r0, r1 = hb.ent_rowptr[e], hb.ent_rowptr[e + 1]
+        q0, q1 = hb.rowptr[r0], hb.rowptr[r1]
+        blk = O.EntityBlock(r1 - r0, 24, hb.rowptr[r0:r1 + 1] - q0, hb.col[q0:q1], hb.val[q0:q1], hb.label[r0:r1],
+                            ob["w"][r0:r1], ob["off"][r0:r1])
+        th = raw["theta"][hb.theta_ptr[e]:hb.theta_ptr[e + 1]]
+        np.testing.assert_allclose(thr["variance"][hb.theta_ptr[e]:hb.theta_ptr[e + 1]],
+                                   O.re_variance(blk, oo, th, "simple"), rtol=1e-10)
+
+
+def test_scoring_matches_oracle():
+    """InferenceJobConsumer (job_consumers.py:138-152): logits incl. offset, per-coordinate, entities w/o model."""
+    hb = make_batch(200, 32, 64, 8, seed=9)
+    opts = capi.make_opts()
+    fit = capi.re_fit_host(hb, opts)
+    has_model = (np.arange(200) % 5 != 0).astype(np.uint8)
+    logit, per = capi.re_score_host(hb, opts, fit["theta"], has_model)
+    ob, oo = _oracle_batch(hb), _oracle_opts(opts)
+    for e in range(0, 200, 9):
+        r0, r1 = hb.ent_rowptr[e], hb.ent_rowptr[e + 1]
+        q0, q1 = hb.rowptr[r0], hb.rowptr[r1]
+        blk = O.EntityBlock(r1 - r0, 64, hb.rowptr[r0:r1 + 1] - q0, hb.col[q0:q1], hb.val[q0:q1], hb.label[r0:r1],
+                            ob["w"][r0:r1], ob["off"][r0:r1])
+        th = fit["theta"][hb.theta_ptr[e]:hb.theta_ptr[e + 1]] if has_model[e] else None
+        lo, po = O.re_score(blk, oo, th)
+        np.testing.assert_allclose(logit[r0:r1], lo.astype(np.float32), rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(per[r0:r1], po.astype(np.float32), rtol=1e-6, atol=1e-7)
+
+
+def test_bad_column_index_is_rejected():
+    hb = make_batch(8, 16, 24, 4, seed=1)
+    hb.col[5] = 9999
+    with pytest.raises(capi.GdmixError):
+        capi.re_fit_host(hb, capi.make_opts())
