@@ -25,7 +25,8 @@ EPS = float(np.finfo(np.float64).eps)
 # every symbol include/gdmix_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_workspace_size",
            "gdmix_re_loss_grad", "gdmix_re_fit", "gdmix_re_score", "gdmix_fe_loss_grad", "gdmix_fe_score",
-           "gdmix_re_fit_host", "gdmix_re_score_host", "gdmix_host_release", "gdmix_partition_ids",
+           "gdmix_re_fit_host", "gdmix_re_score_host", "gdmix_host_register", "gdmix_host_unregister",
+           "gdmix_host_release", "gdmix_partition_ids",
            "gdmix_launch_count"]
 
 

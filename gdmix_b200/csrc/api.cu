@@ -360,14 +360,16 @@ int gdmix_re_fit_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const do
     const bool want_var = var_out != nullptr;
     if (want_var && o->variance_mode != GDMIX_VARIANCE_SIMPLE)
         return fail(GDMIX_ERR_INVALID, "var_out needs variance_mode SIMPLE");
+    std::vector<int32_t> own_status;
+    if (!status) { own_status.resize((size_t)E); status = own_status.data(); }
     std::lock_guard<std::mutex> lk(g_host.mu);
 
-    // chunk boundaries: ~chunk_entities entities, or ~256 MB of input, whichever is smaller
-    if (chunk_entities <= 0) chunk_entities = 32768;
+    // chunk boundaries: ~chunk_entities entities, or ~512 MB of input, whichever is smaller
+    if (chunk_entities <= 0) chunk_entities = 16384;
     std::vector<int64_t> cuts;
     cuts.push_back(0);
     {
-        const size_t cap = (size_t)256 << 20;
+        const size_t cap = (size_t)512 << 20;
         int64_t e = 0;
         while (e < E) {
             int64_t e1 = std::min(E, e + chunk_entities);
@@ -381,98 +383,89 @@ int gdmix_re_fit_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const do
         }
     }
     const size_t nchunks = cuts.size() - 1;
-    struct Pending { bool active = false; int64_t e0, e1, t0, nt; ChunkImage img; } pend[2];
 
-    auto drain = [&](int si) -> int {
-        Pending &p = pend[si];
-        if (!p.active) return GDMIX_OK;
-        Slot &s = g_host.slot[si];
-        CUDA_TRY(cudaStreamSynchronize(s.st));
-        const char *pin = (const char *)s.pin;
-        const int64_t ne = p.e1 - p.e0;
-        memcpy(theta_out + p.t0, pin + p.img.theta, 8 * p.nt);
-        if (f_out) memcpy(f_out + p.e0, pin + p.img.f, 8 * ne);
-        if (nit) memcpy(nit + p.e0, pin + p.img.nit, 4 * ne);
-        if (nfev) memcpy(nfev + p.e0, pin + p.img.nfev, 4 * ne);
-        if (status) memcpy(status + p.e0, pin + p.img.status, 4 * ne);
-        if (want_var) memcpy(var_out + p.t0, pin + p.img.var, 8 * p.nt);
-        p.active = false;
-        return GDMIX_OK;
-    };
-
+    // Each chunk is copied straight out of the caller's arrays (pinned memory makes these copies truly
+    // asynchronous; pageable memory still works, staged by the driver).  The pointer tables keep their
+    // absolute values: the device-side array pointers are shifted instead, so nothing is rewritten.
     for (size_t ci = 0; ci < nchunks; ci++) {
-        const int si = (int)(ci & 1);
-        int rc = drain(si);
-        if (rc) return rc;
+        Slot &s = g_host.slot[ci & 1];
+        if (s.st) CUDA_TRY(cudaStreamSynchronize(s.st));  // the slot's previous chunk is fully drained
         const int64_t e0 = cuts[ci], e1 = cuts[ci + 1], ne = e1 - e0;
         const int64_t r0 = hb->ent_rowptr[e0], r1 = hb->ent_rowptr[e1], nr = r1 - r0;
         const int64_t q0 = hb->rowptr[r0], q1 = hb->rowptr[r1], nz = q1 - q0;
         const int64_t t0 = hb->theta_ptr[e0], t1 = hb->theta_ptr[e1], nt = t1 - t0;
         gdmix_re_batch db = *hb;
         db.n_entities = ne; db.n_rows = nr; db.nnz = nz;
-        int32_t mr = 0, mz = 0, mc = 0;
+        int64_t mr = 0, mz = 0, mc = 0;
         for (int64_t e = e0; e < e1; e++) {
             const int64_t a = hb->ent_rowptr[e], b2 = hb->ent_rowptr[e + 1];
             mr = std::max<int64_t>(mr, b2 - a);
-            mz = (int32_t)std::max<int64_t>(mz, hb->rowptr[b2] - hb->rowptr[a]);
-            mc = (int32_t)std::max<int64_t>(mc, hb->theta_ptr[e + 1] - hb->theta_ptr[e]);
+            mz = std::max<int64_t>(mz, hb->rowptr[b2] - hb->rowptr[a]);
+            mc = std::max<int64_t>(mc, hb->theta_ptr[e + 1] - hb->theta_ptr[e]);
         }
-        db.max_rows = mr; db.max_nnz = mz; db.max_coef = mc;
+        if (mr >= 65535 || mc >= 65535 || mz >= (1ll << 30))
+            return fail(GDMIX_ERR_TOO_LARGE, "an entity has %lld rows / %lld nnz / %lld coefficients",
+                        (long long)mr, (long long)mz, (long long)mc);
+        db.max_rows = (int32_t)mr; db.max_nnz = (int32_t)mz; db.max_coef = (int32_t)mc;
         size_t ws_bytes = 0;
-        rc = gdmix_re_workspace_size(&db, o, &ws_bytes);
+        int rc = gdmix_re_workspace_size(&db, o, &ws_bytes);
         if (rc) return rc;
         const ChunkImage img = chunk_image(ne, nr, nz, nt, hb->weight != nullptr, hb->offset != nullptr,
                                            theta0 != nullptr, want_var);
-        Slot &s = g_host.slot[si];
-        rc = ensure(s, img.total, img.total, ws_bytes);
+        rc = ensure(s, img.total, 0, ws_bytes);
         if (rc) return rc;
-        // pack inputs into pinned memory (pointer tables are rebased to the chunk)
-        char *pin = (char *)s.pin;
-        {
-            int64_t *p = (int64_t *)(pin + img.ent_rowptr);
-            for (int64_t i = 0; i <= ne; i++) p[i] = hb->ent_rowptr[e0 + i] - r0;
-            p = (int64_t *)(pin + img.rowptr);
-            for (int64_t i = 0; i <= nr; i++) p[i] = hb->rowptr[r0 + i] - q0;
-            p = (int64_t *)(pin + img.theta_ptr);
-            for (int64_t i = 0; i <= ne; i++) p[i] = hb->theta_ptr[e0 + i] - t0;
-        }
-        if (nz) {
-            memcpy(pin + img.col, hb->col + q0, 4 * nz);
-            memcpy(pin + img.val, hb->val + q0, 4 * nz);
-        }
-        memcpy(pin + img.label, hb->label + r0, 4 * nr);
-        if (hb->weight) memcpy(pin + img.weight, hb->weight + r0, 4 * nr);
-        if (hb->offset) memcpy(pin + img.offset, hb->offset + r0, 4 * nr);
-        if (theta0) memcpy(pin + img.theta0, theta0 + t0, 8 * nt);
-        CUDA_TRY(cudaMemcpyAsync(s.dev, pin, img.in_bytes, cudaMemcpyHostToDevice, s.st));
         char *dv = (char *)s.dev;
-        db.ent_rowptr = (const int64_t *)(dv + img.ent_rowptr);
-        db.rowptr = (const int64_t *)(dv + img.rowptr);
+        const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
+        CUDA_TRY(cudaMemcpyAsync(dv + img.ent_rowptr, hb->ent_rowptr + e0, 8 * (ne + 1), H2D, s.st));
+        CUDA_TRY(cudaMemcpyAsync(dv + img.rowptr, hb->rowptr + r0, 8 * (nr + 1), H2D, s.st));
+        CUDA_TRY(cudaMemcpyAsync(dv + img.theta_ptr, hb->theta_ptr + e0, 8 * (ne + 1), H2D, s.st));
+        if (nz) {
+            CUDA_TRY(cudaMemcpyAsync(dv + img.col, hb->col + q0, 4 * nz, H2D, s.st));
+            CUDA_TRY(cudaMemcpyAsync(dv + img.val, hb->val + q0, 4 * nz, H2D, s.st));
+        }
+        CUDA_TRY(cudaMemcpyAsync(dv + img.label, hb->label + r0, 4 * nr, H2D, s.st));
+        if (hb->weight) CUDA_TRY(cudaMemcpyAsync(dv + img.weight, hb->weight + r0, 4 * nr, H2D, s.st));
+        if (hb->offset) CUDA_TRY(cudaMemcpyAsync(dv + img.offset, hb->offset + r0, 4 * nr, H2D, s.st));
+        if (theta0) CUDA_TRY(cudaMemcpyAsync(dv + img.theta0, theta0 + t0, 8 * nt, H2D, s.st));
+        db.ent_rowptr = (const int64_t *)(dv + img.ent_rowptr);            // indexed by local entity
         db.theta_ptr = (const int64_t *)(dv + img.theta_ptr);
-        db.col = (const int32_t *)(dv + img.col);
-        db.val = (const float *)(dv + img.val);
-        db.label = (const float *)(dv + img.label);
-        db.weight = hb->weight ? (const float *)(dv + img.weight) : nullptr;
-        db.offset = hb->offset ? (const float *)(dv + img.offset) : nullptr;
-        rc = gdmix_re_fit(&db, o, theta0 ? (const double *)(dv + img.theta0) : nullptr, (double *)(dv + img.theta),
-                          (double *)(dv + img.f), (int32_t *)(dv + img.nit), (int32_t *)(dv + img.nfev),
-                          (int32_t *)(dv + img.status), want_var ? (double *)(dv + img.var) : nullptr, s.ws,
-                          s.ws_bytes, s.st);
+        db.rowptr = (const int64_t *)(dv + img.rowptr) - r0;               // indexed by absolute row
+        db.label = (const float *)(dv + img.label) - r0;
+        db.weight = hb->weight ? (const float *)(dv + img.weight) - r0 : nullptr;
+        db.offset = hb->offset ? (const float *)(dv + img.offset) - r0 : nullptr;
+        db.col = (const int32_t *)(dv + img.col) - q0;                     // indexed by absolute non-zero
+        db.val = (const float *)(dv + img.val) - q0;
+        rc = gdmix_re_fit(&db, o, theta0 ? (const double *)(dv + img.theta0) - t0 : nullptr,
+                          (double *)(dv + img.theta) - t0, (double *)(dv + img.f), (int32_t *)(dv + img.nit),
+                          (int32_t *)(dv + img.nfev), (int32_t *)(dv + img.status),
+                          want_var ? (double *)(dv + img.var) - t0 : nullptr, s.ws, s.ws_bytes, s.st);
         if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(pin + img.theta, dv + img.theta, img.total - img.in_bytes, cudaMemcpyDeviceToHost,
-                                 s.st));
-        pend[si].active = true; pend[si].e0 = e0; pend[si].e1 = e1; pend[si].t0 = t0; pend[si].nt = nt;
-        pend[si].img = img;
+        CUDA_TRY(cudaMemcpyAsync(theta_out + t0, dv + img.theta, 8 * nt, D2H, s.st));
+        if (f_out) CUDA_TRY(cudaMemcpyAsync(f_out + e0, dv + img.f, 8 * ne, D2H, s.st));
+        if (nit) CUDA_TRY(cudaMemcpyAsync(nit + e0, dv + img.nit, 4 * ne, D2H, s.st));
+        if (nfev) CUDA_TRY(cudaMemcpyAsync(nfev + e0, dv + img.nfev, 4 * ne, D2H, s.st));
+        CUDA_TRY(cudaMemcpyAsync(status + e0, dv + img.status, 4 * ne, D2H, s.st));
+        if (want_var) CUDA_TRY(cudaMemcpyAsync(var_out + t0, dv + img.var, 8 * nt, D2H, s.st));
     }
-    int rc = drain(0);
-    if (rc) return rc;
-    rc = drain(1);
-    if (rc) return rc;
-    if (status) {
-        for (int64_t e = 0; e < E; e++)
-            if (status[e] < 0)
-                return fail(status[e], "entity %lld rejected by the device path (status %d)", (long long)e, status[e]);
-    }
+    for (Slot &s : g_host.slot)
+        if (s.st) CUDA_TRY(cudaStreamSynchronize(s.st));
+    for (int64_t e = 0; e < E; e++)
+        if (status[e] < 0)
+            return fail(status[e], "entity %lld rejected by the device path (status %d)", (long long)e, status[e]);
+    return GDMIX_OK;
+}
+
+int gdmix_host_register(void *ptr, size_t bytes)
+{
+    if (!ptr || !bytes) return fail(GDMIX_ERR_INVALID, "null buffer");
+    CUDA_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return GDMIX_OK;
+}
+
+int gdmix_host_unregister(void *ptr)
+{
+    if (!ptr) return fail(GDMIX_ERR_INVALID, "null buffer");
+    CUDA_TRY(cudaHostUnregister(ptr));
     return GDMIX_OK;
 }
 

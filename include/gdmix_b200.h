@@ -173,16 +173,20 @@ GDMIX_API int gdmix_fe_score(const gdmix_fe_rows *rows, const gdmix_lr_opts *opt
                              float *logit_per_coordinate, void *stream);
 
 /* Host-buffer form of gdmix_re_fit: every pointer (batch arrays, theta0, outputs) is HOST
- * memory.  The library owns device buffers and pinned staging, splits the batch into
- * chunks of about `chunk_entities` entities (0 = choose) and overlaps H2D copy, solve and
- * D2H copy on its own streams.  Synchronous: returns when the outputs are in host memory.
+ * memory.  The library owns the device buffers, splits the batch into chunks of about
+ * `chunk_entities` entities (0 = choose), copies each chunk straight out of / into the caller's
+ * arrays and overlaps H2D copy, solve and D2H copy of alternating chunks on two streams.  Synchronous: returns when the outputs are in host memory.
  * This is the call the Python plugin classes make. */
 GDMIX_API int gdmix_re_fit_host(const gdmix_re_batch *host_batch, const gdmix_lr_opts *opts, const double *theta0,
                                 double *theta_out, double *f_out, int32_t *nit, int32_t *nfev, int32_t *status,
                                 double *var_out, int64_t chunk_entities);
 GDMIX_API int gdmix_re_score_host(const gdmix_re_batch *host_batch, const gdmix_lr_opts *opts, const double *theta,
                                   const uint8_t *has_model, float *logit, float *logit_per_coordinate);
-/* Releases the cached device/pinned buffers of the *_host entry points. */
+/* Page-locks / unlocks a caller buffer (cudaHostRegister) so that the *_host entry points can copy from
+ * and to it asynchronously.  Optional: pageable buffers work, pinned ones overlap copy and compute. */
+GDMIX_API int gdmix_host_register(void *ptr, size_t bytes);
+GDMIX_API int gdmix_host_unregister(void *ptr);
+/* Releases the cached device buffers and streams of the *_host entry points. */
 GDMIX_API void gdmix_host_release(void);
 
 /* Entity -> partition map, bit-exact with the JVM: abs(String.hashCode(id)) % num_partitions

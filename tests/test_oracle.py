@@ -133,3 +133,19 @@ def test_partition_map_bit_exact():
     # the Int.MinValue quirk: abs() stays negative, % keeps the sign
     assert O.partition_id("polygenelubricants", 3) == -2
     assert O.partition_id("polygenelubricants", 10) == -8
+
+
+@pytest.mark.parametrize("c", CASES[::3], ids=[c["name"] for c in CASES[::3]])
+def test_scipy_port_is_the_reference(c):
+    """oracle/scipy_port.py (the CPU-baseline arm of bench.py) repeats the reference's library calls in the
+    reference's order, so on pinned cases it must reproduce the reference's coefficients to the last bits."""
+    from oracle import scipy_port as SP
+    k = c["key"]
+    th0 = ARR[k + "_theta0"] if c["warm"] else None
+    theta, f, nit, nfev, wf = SP.fit_entity(c["n"], c["d"], ARR[k + "_rowptr"], ARR[k + "_col"], ARR[k + "_val"],
+                                            ARR[k + "_y"], ARR[k + "_w"], ARR[k + "_off"], l2=c["l2"],
+                                            regularize_bias=c["regularize_bias"], has_intercept=c["has_intercept"],
+                                            m=c["m"], max_iter=c["max_iter"], tol=c["tol"], theta0=th0)
+    if is_pinned(c):
+        assert (nit, nfev, wf) == (c["nit"], c["nfev"], c["warnflag"])
+        np.testing.assert_allclose(theta, ARR[k + "_theta"], rtol=1e-12, atol=1e-15)
