@@ -64,6 +64,7 @@ int device_info(DeviceInfo &d)
 // Launch plan for one batch shape.
 struct RePlan {
     int G = 128;                 // threads per entity (= CTA size)
+    int MT = 10;                 // compile-time bound on the number of curvature pairs (10 or 32)
     uint32_t smem = 0;           // dynamic shared memory per CTA
     int ctas_per_sm = 1;
     int grid = 1;
@@ -72,7 +73,7 @@ struct RePlan {
 };
 
 constexpr size_t kQueueBytes = 256;
-constexpr uint32_t kStaticSmem = 2 * gdmix::kMaxWarps * gdmix::kRedK * 8 + 2 * GDMIX_MAX_M * 8 + 64;
+constexpr uint32_t kStaticSmem = 2 * gdmix::kMaxWarps * gdmix::kRedK * 8 + 64;
 
 int choose_group(const gdmix_re_batch *b, const gdmix_lr_opts *o)
 {
@@ -99,8 +100,10 @@ int plan_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &d
     if (o->m < 0 || o->m > GDMIX_MAX_M) return fail(GDMIX_ERR_INVALID, "m = %d outside [0, %d]", o->m, GDMIX_MAX_M);
     const uint32_t hi = o->has_intercept ? 1u : 0u;
     if ((uint32_t)b->max_coef < hi) return fail(GDMIX_ERR_INVALID, "max_coef < has_intercept");
+    pl.MT = (o->m <= 10) ? 10 : 32;
     const gdmix::ReLayout L = gdmix::re_layout((uint32_t)b->max_rows, (uint32_t)b->max_nnz,
-                                               (uint32_t)b->max_coef - hi, (uint32_t)b->max_coef, (uint32_t)o->m);
+                                               (uint32_t)b->max_coef - hi, (uint32_t)b->max_coef, (uint32_t)o->m,
+                                               (uint32_t)pl.MT);
     const uint32_t budget = (uint32_t)dev.smem_optin - kStaticSmem;
     if (L.fixed_bytes > budget)
         return fail(GDMIX_ERR_TOO_LARGE,
@@ -119,16 +122,16 @@ int plan_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &d
     return GDMIX_OK;
 }
 
-template <int G>
+template <int G, int MT>
 int launch_re_t(const gdmix::ReArgs &args, const RePlan &pl, cudaStream_t st)
 {
     static std::atomic<uint32_t> configured{0};
     if (configured.load() < pl.smem) {
-        CUDA_TRY(cudaFuncSetAttribute(gdmix::re_solver_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(gdmix::re_solver_kernel<G, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       227 * 1024 - (int)kStaticSmem));
         configured.store(227 * 1024);
     }
-    gdmix::re_solver_kernel<G><<<pl.grid, G, pl.smem, st>>>(args);
+    gdmix::re_solver_kernel<G, MT><<<pl.grid, G, pl.smem, st>>>(args);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return GDMIX_OK;
@@ -166,11 +169,19 @@ int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const d
     a.mode = mode;
     a.smem_bytes = pl.smem;
     CUDA_TRY(cudaMemsetAsync(workspace, 0, kQueueBytes, st));
+    if (pl.MT == 10) {
+        switch (pl.G) {
+        case 32: return launch_re_t<32, 10>(a, pl, st);
+        case 64: return launch_re_t<64, 10>(a, pl, st);
+        case 128: return launch_re_t<128, 10>(a, pl, st);
+        default: return launch_re_t<256, 10>(a, pl, st);
+        }
+    }
     switch (pl.G) {
-    case 32: return launch_re_t<32>(a, pl, st);
-    case 64: return launch_re_t<64>(a, pl, st);
-    case 128: return launch_re_t<128>(a, pl, st);
-    default: return launch_re_t<256>(a, pl, st);
+    case 32: return launch_re_t<32, 32>(a, pl, st);
+    case 64: return launch_re_t<64, 32>(a, pl, st);
+    case 128: return launch_re_t<128, 32>(a, pl, st);
+    default: return launch_re_t<256, 32>(a, pl, st);
     }
 }
 

@@ -5,12 +5,16 @@
 //              label/weight/offset) is read from HBM exactly once and laid out in shared
 //              memory as a bank-skewed CSR (u16 columns) plus a bank-skewed CSC built on
 //              chip by a deterministic counting sort (row-ascending inside each column);
-//   2. solve   L-BFGS-B as scipy.optimize.fmin_l_bfgs_b runs it without bounds
-//              (two-loop direction with H0 = I/theta, MINPACK-2 dcsrch line search,
-//              skip / restart rules, pgtol + factr + maxiter stop tests) entirely out of
-//              shared memory: z = X1.theta by row-threads from the CSR, g = X1^T r by
-//              coefficient-threads from the CSC -- no atomics, fixed summation order,
-//              fp64 throughout;
+//   2. solve   L-BFGS-B as scipy.optimize.fmin_l_bfgs_b runs it without bounds (MINPACK-2
+//              dcsrch line search, skip / restart rules, pgtol + factr + maxiter stop tests)
+//              entirely out of shared memory: z = X1.theta by row-threads from the CSR,
+//              g = X1^T r by coefficient-threads from the CSC -- no atomics, fixed summation
+//              order, fp64 throughout.  The search direction d = -H g uses the compact
+//              (Byrd-Nocedal-Schnabel) form of the L-BFGS inverse Hessian with an explicitly
+//              maintained R^-1: per iteration ONE batched reduction of the 2m+2 inner
+//              products [S;Y]^T g, y.y, y.g, a warp-sized m x m update, and one axpy pass --
+//              instead of the two-loop recursion's 2m dependent block reductions.  It is
+//              the same direction algebraically (H0 = I/theta);
 //   3. emit    theta (optionally thresholded), f, nit, nfev, status, SIMPLE variance.
 // CTAs are persistent and pull entities from a global atomic queue, so divergent iteration
 // counts between entities never idle an SM.
@@ -59,14 +63,26 @@ struct ReLayout {
     uint32_t rowst, colst;            // u32[n+1], u32[d+1] skewed segment starts
     uint32_t csr_val, csc_val;        // fp32[nnz+n], fp32[nnz+d]
     uint32_t csr_col, csc_row;        // u16[nnz+n], u16[nnz+d]
+    uint32_t dense;                   // fp64 small matrices / vectors of the compact L-BFGS form
+    uint32_t part;                    // fp64[kMaxWarps * (2*MT+2)] per-warp partial inner products
     uint32_t fixed_bytes;             // everything above
     uint32_t hist;                    // fp64[2*m*p]: S rows then Y rows
     uint32_t total_bytes;             // fixed + history
 };
 
+// Offsets (in doubles) inside the dense block, MT = compile-time bound on m.
+template <int MT>
+struct Dense {
+    static constexpr int rinv = 0, yy = MT * MT, d = 2 * MT * MT, p1old = d + MT, p2old = p1old + MT,
+                         cu = p2old + MT, cw = cu + MT, ta = cw + MT, tb = ta + MT, tot = tb + MT,
+                         count = tot + 2 * MT + 2;
+};
+__host__ __device__ inline uint32_t dense_doubles(uint32_t mt) { return 2 * mt * mt + 9 * mt + 2; }
+
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
-__host__ __device__ inline ReLayout re_layout(uint32_t n, uint32_t nnz, uint32_t d, uint32_t p, uint32_t m)
+__host__ __device__ inline ReLayout re_layout(uint32_t n, uint32_t nnz, uint32_t d, uint32_t p, uint32_t m,
+                                              uint32_t mt)
 {
     ReLayout L;
     uint32_t o = 0;
@@ -85,6 +101,8 @@ __host__ __device__ inline ReLayout re_layout(uint32_t n, uint32_t nnz, uint32_t
     L.csc_val = o; o += align16(4 * (nnz + d));
     L.csr_col = o; o += align16(2 * (nnz + n));
     L.csc_row = o; o += align16(2 * (nnz + d));
+    L.dense = o; o += align16(8 * dense_doubles(mt));
+    L.part = o; o += align16(8 * kMaxWarps * (2 * mt + 2));
     L.fixed_bytes = o;
     L.hist = o; o += align16(16 * m * p);
     L.total_bytes = o;
@@ -383,14 +401,203 @@ __device__ __forceinline__ void evaluate(const Staged &S, const double *xt, cons
 }
 
 // ---------------------------------------------------------------------------------------
+// Compact L-BFGS direction.  Ring of m physical slots (MT = compile-time bound on m); all small
+// matrices are indexed by PHYSICAL slot and hold zeros in rows/columns of empty slots, so the
+// m x m products need no masks.  With R_ij = s_i.y_j (i not newer than j), D = diag(s_i.y_i),
+// gamma = 1/theta:
+//     H g = gamma g + S u - gamma Y w,   w = R^-1 S^T g,   u = R^-T ((D + gamma Y^T Y) w - gamma Y^T g)
+// R^-1 is kept explicitly: appending a pair adds the column -R^-1 (S^T y_new) / (s_new.y_new) and the
+// diagonal entry 1/(s_new.y_new); dropping the oldest pair deletes its row and column (a trailing
+// principal block of an upper-triangular inverse is the inverse of the trailing block).
+// S^T y_new and Y^T y_new follow from the inner products with the new and the previous gradient.
+// ---------------------------------------------------------------------------------------
+struct Lbfgs {
+    int col, head;        // pairs stored, physical slot of the oldest
+    uint32_t valid;       // bit s set: physical slot s holds a pair
+    double theta;
+};
+
+template <int G, int MT>
+__device__ __forceinline__ void lbfgs_reset(Lbfgs &L, double *dense)
+{
+    L.col = 0; L.head = 0; L.valid = 0; L.theta = 1.0;
+    for (int k = threadIdx.x; k < Dense<MT>::tot; k += G) dense[k] = 0.0;
+}
+
+// After an accepted step: g = new gradient, gold = previous gradient, dv = the direction just used.
+// Optionally stores the new pair (s = stp*dv, y = g - gold), then writes the next direction into dv and
+// returns gd = g.dv and dtd = dv.dv (identical in all threads).
+template <int G, int MT>
+__device__ __forceinline__ void lbfgs_direction(Lbfgs &L, const int m, const bool update, const double stp,
+                                                const double dr, const double gd_new, const uint32_t p,
+                                                const double *g, const double *gold, double *dv, double *Sh,
+                                                double *Yh, double *dense, double *part, double *red, int &flip,
+                                                double &gd, double &dtd)
+{
+    using DN = Dense<MT>;
+    constexpr int W = G / 32;
+    constexpr int K = 2 * MT + 2;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    int newslot = -1;
+    if (update) newslot = (L.col < m) ? (L.head + L.col) % m : L.head;
+    const uint32_t dotmask = update ? (L.valid & ~(1u << newslot)) : L.valid;  // surviving old pairs
+
+    // ---- pass H1: inner products of every stored pair with g, plus y.y and y.g ------------------------
+    double a1[MT], a2[MT], yy = 0.0, yg = 0.0;
+#pragma unroll
+    for (int s = 0; s < MT; s++) { a1[s] = 0.0; a2[s] = 0.0; }
+    for (uint32_t j = tid; j < p; j += G) {
+        const double gj = g[j], yj = gj - gold[j];
+        yy = fma(yj, yj, yy);
+        yg = fma(yj, gj, yg);
+#pragma unroll
+        for (int s = 0; s < MT; s++) {
+            if ((dotmask >> s) & 1u) {
+                a1[s] = fma(Sh[(size_t)s * p + j], gj, a1[s]);
+                a2[s] = fma(Yh[(size_t)s * p + j], gj, a2[s]);
+            }
+        }
+        if (update) {
+            Sh[(size_t)newslot * p + j] = stp * dv[j];
+            Yh[(size_t)newslot * p + j] = yj;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < MT; s++) {
+        if ((dotmask >> s) & 1u) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a1[s] += __shfl_xor_sync(kFull, a1[s], o);
+                a2[s] += __shfl_xor_sync(kFull, a2[s], o);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        yy += __shfl_xor_sync(kFull, yy, o);
+        yg += __shfl_xor_sync(kFull, yg, o);
+    }
+    if (lane == 0) {
+        double *row = part + warp * K;
+#pragma unroll
+        for (int s = 0; s < MT; s++) { row[s] = a1[s]; row[MT + s] = a2[s]; }
+        row[2 * MT] = yy; row[2 * MT + 1] = yg;
+    }
+    group_sync<G>();
+
+    // ---- warp 0: totals, pair update, the three m x m products ---------------------------------------
+    if (warp == 0) {
+        double *tot = dense + DN::tot;
+        for (int k = lane; k < K; k += 32) {
+            double t = part[k];
+#pragma unroll
+            for (int w2 = 1; w2 < W; w2++) t += part[w2 * K + k];
+            tot[k] = t;
+        }
+        __syncwarp();
+        const int i = lane;
+        const bool in = i < MT;
+        const bool old_i = in && ((dotmask >> i) & 1u);
+        double p1i = old_i ? tot[i] : 0.0, p2i = old_i ? tot[MT + i] : 0.0;
+        const double yyt = tot[2 * MT], ygt = tot[2 * MT + 1];
+        double *Rinv = dense + DN::rinv, *YY = dense + DN::yy, *Dg = dense + DN::d;
+        double *p1old = dense + DN::p1old, *p2old = dense + DN::p2old;
+        double *ta = dense + DN::ta, *tb = dense + DN::tb;
+        double theta = L.theta;
+        if (update) {
+            theta = yyt / dr;
+            const double rc = old_i ? p1i - p1old[i] : 0.0;  // s_i . y_new
+            const double yc = old_i ? p2i - p2old[i] : 0.0;  // y_i . y_new
+            if (in) ta[i] = rc;
+            __syncwarp();
+            double acc = 0.0;
+            if (in) {
+#pragma unroll
+                for (int j = 0; j < MT; j++) acc = fma(Rinv[i * MT + j], ta[j], acc);
+            }
+            __syncwarp();
+            if (in) {
+                Rinv[i * MT + newslot] = old_i ? -acc / dr : 0.0;
+                YY[i * MT + newslot] = yc;
+            }
+            __syncwarp();
+            if (in) {
+                Rinv[newslot * MT + i] = (i == newslot) ? 1.0 / dr : 0.0;
+                YY[newslot * MT + i] = (i == newslot) ? yyt : yc;
+            }
+            if (i == newslot) { Dg[i] = dr; p1i = stp * gd_new; p2i = ygt; }
+            __syncwarp();
+        }
+        const uint32_t valid = update ? (L.valid | (1u << newslot)) : L.valid;
+        const bool val_i = in && ((valid >> i) & 1u);
+        const double gamma = 1.0 / theta;
+        if (in) { p1old[i] = p1i; p2old[i] = p2i; ta[i] = val_i ? p1i : 0.0; }
+        __syncwarp();
+        double wv = 0.0;
+        if (in) {
+#pragma unroll
+            for (int j = 0; j < MT; j++) wv = fma(Rinv[i * MT + j], ta[j], wv);
+        }
+        if (in) tb[i] = wv;
+        __syncwarp();
+        double yw = 0.0;
+        if (in) {
+#pragma unroll
+            for (int j = 0; j < MT; j++) yw = fma(YY[i * MT + j], tb[j], yw);
+        }
+        const double tv = val_i ? fma(Dg[i], wv, gamma * (yw - p2i)) : 0.0;
+        __syncwarp();
+        if (in) ta[i] = tv;
+        __syncwarp();
+        double uv = 0.0;
+        if (in) {
+#pragma unroll
+            for (int j = 0; j < MT; j++) uv = fma(Rinv[j * MT + i], ta[j], uv);
+        }
+        if (in) { dense[DN::cu + i] = uv; dense[DN::cw + i] = wv; }
+    }
+    group_sync<G>();
+    if (update) {
+        L.theta = dense[DN::tot + 2 * MT] / dr;
+        L.valid |= (1u << newslot);
+        if (L.col < m) L.col++; else L.head = (L.head + 1) % m;
+    }
+
+    // ---- pass H2: dv = -gamma g - S u + gamma Y w ------------------------------------------------------
+    const double gamma = 1.0 / L.theta;
+    double cu[MT], cw[MT];
+#pragma unroll
+    for (int s = 0; s < MT; s++) { cu[s] = dense[DN::cu + s]; cw[s] = gamma * dense[DN::cw + s]; }
+    double v2[2] = {0.0, 0.0};
+    const uint32_t valid = L.valid;
+    for (uint32_t j = tid; j < p; j += G) {
+        const double gj = g[j];
+        double acc = -gamma * gj;
+#pragma unroll
+        for (int s = 0; s < MT; s++) {
+            if ((valid >> s) & 1u) {
+                acc = fma(-cu[s], Sh[(size_t)s * p + j], acc);
+                acc = fma(cw[s], Yh[(size_t)s * p + j], acc);
+            }
+        }
+        dv[j] = acc;
+        v2[0] = fma(gj, acc, v2[0]);
+        v2[1] = fma(acc, acc, v2[1]);
+    }
+    group_sum<G, 2>(v2, red, flip);
+    gd = v2[0];
+    dtd = v2[1];
+}
+
+// ---------------------------------------------------------------------------------------
 // The kernel.
 // ---------------------------------------------------------------------------------------
-template <int G>
+template <int G, int MT>
 __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double red[2 * kMaxWarps * kRedK];
-    __shared__ double s_rho[GDMIX_MAX_M], s_alpha[GDMIX_MAX_M];
     __shared__ int s_entity;
     __shared__ unsigned s_bad;
 
@@ -413,7 +620,7 @@ __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
         const int64_t n64 = r1 - r0, nnz64 = q1 - q0, p64 = a.b.theta_ptr[e + 1] - t0;
         const uint32_t n = (uint32_t)n64, nnz = (uint32_t)nnz64, p = (uint32_t)p64, d = p - hi;
 
-        const ReLayout L = re_layout(n, nnz, d, p, (uint32_t)m);
+        const ReLayout L = re_layout(n, nnz, d, p, (uint32_t)m, (uint32_t)MT);
         const bool ok = n64 >= 1 && n64 < 65535 && p64 >= 1 && p64 >= (int64_t)hi && (p64 - hi) < 65535 &&
                         nnz64 >= 0 && nnz64 < (1ll << 30) && L.fixed_bytes <= a.smem_bytes;
         if (!ok) {
@@ -428,6 +635,7 @@ __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
         uint32_t *rowst = (uint32_t *)(smem + L.rowst), *colst = (uint32_t *)(smem + L.colst);
         float *csr_val = (float *)(smem + L.csr_val), *csc_val = (float *)(smem + L.csc_val);
         uint16_t *csr_col = (uint16_t *)(smem + L.csr_col), *csc_row = (uint16_t *)(smem + L.csc_row);
+        double *dense = (double *)(smem + L.dense), *part = (double *)(smem + L.part);
         double *hist = (L.total_bytes <= a.smem_bytes)
                            ? (double *)(smem + L.hist)
                            : (double *)(a.arena + (unsigned long long)blockIdx.x * a.arena_stride);
@@ -537,6 +745,8 @@ __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
             x[j] = a.theta_in ? a.theta_in[t0 + j] : 0.0;
             dv[j] = 0.0;
         }
+        Lbfgs lb;
+        lbfgs_reset<G, MT>(lb, dense);
         group_sync<G>();
 
         double f, gd, gmax;
@@ -552,47 +762,24 @@ __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
         // ---- L-BFGS-B, unbounded ---------------------------------------------------------
         const double epsmch = 2.220446049250313e-16;
         const double ftol = 1e-3, gtol = 0.9, xtol = 0.1, stpmx = 1e10;
-        int col = 0, head = 0;
-        double theta = 1.0;
+        double dtd;
         bool done = gmax <= a.o.pgtol;
+        if (!done) {
+            // steepest descent start: dv = -g
+            double v1[1] = {0.0};
+            for (uint32_t j = tid; j < p; j += G) {
+                const double gj = g[j];
+                dv[j] = -gj;
+                v1[0] = fma(gj, gj, v1[0]);
+            }
+            group_sum<G, 1>(v1, red, flip);
+            dtd = v1[0];
+            gd = -v1[0];
+        }
 
         while (!done) {
-            // direction: two-loop recursion in dv
-            for (uint32_t j = tid; j < p; j += G) dv[j] = g[j];
-            for (int k = col - 1; k >= 0; k--) {
-                const int s = (head + k) % m;
-                const double *Ss = Sh + (size_t)s * p, *Ys = Yh + (size_t)s * p;
-                double v[1] = {0.0};
-                for (uint32_t j = tid; j < p; j += G) v[0] = fma(Ss[j], dv[j], v[0]);
-                group_sum<G, 1>(v, red, flip);
-                const double al = s_rho[s] * v[0];
-                if (tid == 0) s_alpha[s] = al;
-                for (uint32_t j = tid; j < p; j += G) dv[j] = fma(-al, Ys[j], dv[j]);
-            }
-            for (uint32_t j = tid; j < p; j += G) dv[j] = dv[j] / theta;
-            group_sync<G>();  // s_alpha visible
-            for (int k = 0; k < col; k++) {
-                const int s = (head + k) % m;
-                const double *Ss = Sh + (size_t)s * p, *Ys = Yh + (size_t)s * p;
-                double v[1] = {0.0};
-                for (uint32_t j = tid; j < p; j += G) v[0] = fma(Ys[j], dv[j], v[0]);
-                group_sum<G, 1>(v, red, flip);
-                const double c2 = s_alpha[s] - s_rho[s] * v[0];
-                for (uint32_t j = tid; j < p; j += G) dv[j] = fma(Ss[j], c2, dv[j]);
-            }
-            double v2[2] = {0.0, 0.0};
-            for (uint32_t j = tid; j < p; j += G) {
-                const double dj = -dv[j];
-                dv[j] = dj;
-                v2[0] = fma(dj, dj, v2[0]);
-                v2[1] = fma(g[j], dj, v2[1]);
-            }
-            group_sum<G, 2>(v2, red, flip);
-            const double dnorm = sqrt(v2[0]);
-            gd = v2[1];
-
-            // line search (lnsrlb + dcsrch)
-            double stp = (iter == 0) ? fmin(1.0 / dnorm, stpmx) : 1.0;
+            // line search (lnsrlb + dcsrch) along dv; gd = g.dv, dtd = dv.dv on entry
+            double stp = (iter == 0) ? fmin(1.0 / sqrt(dtd), stpmx) : 1.0;
             const double fold = f, gdold = gd;
             int ifun = 0, iback = 0, info = 0, task = LS_START;
             LineSearch ls;
@@ -611,12 +798,23 @@ __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
             }
             if (info != 0 || iback >= a.o.max_ls) {
                 f = fold;  // x, g still hold the previous iterate
-                if (col == 0) { status = GDMIX_SOLVE_ABNORMAL; iter++; break; }
-                col = 0; head = 0; theta = 1.0;
+                if (lb.col == 0) { status = GDMIX_SOLVE_ABNORMAL; iter++; break; }
+                // refresh the memory and restart from steepest descent
+                group_sync<G>();
+                lbfgs_reset<G, MT>(lb, dense);
+                double v2[1] = {0.0};
+                for (uint32_t j = tid; j < p; j += G) {
+                    const double gj = g[j];
+                    dv[j] = -gj;
+                    v2[0] = fma(gj, gj, v2[0]);
+                }
+                group_sum<G, 1>(v2, red, flip);
+                dtd = v2[0];
+                gd = -v2[0];
                 continue;
             }
             iter++;
-            // accept: (x, g) <-> (xt, gt); the old iterate stays reachable for y = g - g_old
+            // accept: (x, g) <-> (xt, gt); gt now holds the previous gradient
             { double *t = x; x = xt; xt = t; t = g; g = gt; gt = t; }
             gmax = gmax_t;
 
@@ -624,30 +822,13 @@ __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
             if (gmax <= a.o.pgtol) break;
             if ((fold - f) <= epsmch * a.o.factr * max3(fabs(fold), fabs(f), 1.0)) break;
 
-            // curvature pair
-            double vr[1] = {0.0};
-            for (uint32_t j = tid; j < p; j += G) {
-                const double yj = g[j] - gt[j];
-                gt[j] = yj;
-                vr[0] = fma(yj, yj, vr[0]);
-            }
-            group_sum<G, 1>(vr, red, flip);
-            const double rr = vr[0];
+            // curvature pair (L-BFGS-B's skip rule) and the next direction
             double dr, ddum;
             if (stp == 1.0) { dr = gd - gdold; ddum = -gdold; }
             else { dr = (gd - gdold) * stp; ddum = -gdold * stp; }
-            if (dr <= epsmch * ddum || m == 0) continue;  // skip the update
-            int slot;
-            if (col < m) { slot = (head + col) % m; col++; }
-            else { slot = head; head = (head + 1) % m; }
-            double *Ss = Sh + (size_t)slot * p, *Ys = Yh + (size_t)slot * p;
-            for (uint32_t j = tid; j < p; j += G) {
-                Ss[j] = stp * dv[j];
-                Ys[j] = gt[j];
-            }
-            if (tid == 0) s_rho[slot] = 1.0 / dr;
-            theta = rr / dr;
-            group_sync<G>();  // s_rho visible
+            const bool update = (m > 0) && !(dr <= epsmch * ddum);
+            lbfgs_direction<G, MT>(lb, m, update, stp, dr, gd, p, g, gt, dv, Sh, Yh, dense, part, red, flip, gd,
+                                   dtd);
         }
 
         // ---- emit ------------------------------------------------------------------------

@@ -186,3 +186,15 @@ def test_bad_column_index_is_rejected():
     hb.col[5] = 9999
     with pytest.raises(capi.GdmixError):
         capi.re_fit_host(hb, capi.make_opts())
+
+
+@pytest.mark.parametrize("m", [1, 4, 15, 32])
+def test_history_sizes_match_oracle(m):
+    """Curvature-pair counts other than the default 10 (m > 10 runs the MT=32 kernel instantiation)."""
+    hb = make_batch(120, 48, 40, 8, seed=21 + m, weights=True)
+    opts = capi.make_opts(l2=0.3, m=m)
+    out = capi.re_fit_host(hb, opts)
+    th_o, f_o, nit_o, nfev_o, st_o = O.re_fit_batch(_oracle_batch(hb), _oracle_opts(opts))
+    rel = _rel_per_entity(out["theta"], th_o, hb.theta_ptr)
+    assert rel.max() <= REL_TOL, rel.max()
+    assert (out["nit"] == nit_o).all() and (out["nfev"] == nfev_o).all()
