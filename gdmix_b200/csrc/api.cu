@@ -7,13 +7,14 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
 
 #include "../../include/gdmix_b200.h"
 #include "aux_kernels.cuh"
-#include "re_solver.cuh"
+#include "re_kernel.cuh"
 
 namespace {
 
@@ -68,6 +69,7 @@ struct RePlan {
     uint32_t smem = 0;           // dynamic shared memory per CTA
     int ctas_per_sm = 1;
     int grid = 1;
+    int hist_global = 0;         // history lives in the global arena (L2) instead of shared memory
     unsigned long long arena_stride = 0;  // per-CTA history spill in global memory
     size_t workspace = 0;
 };
@@ -110,12 +112,21 @@ int plan_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &d
                     "largest entity (%d rows, %d nnz, %d coef) needs %u B of shared memory, device offers %u B",
                     b->max_rows, b->max_nnz, b->max_coef, L.fixed_bytes, budget);
     pl.G = choose_group(b, o);
-    const bool hist_on_chip = L.total_bytes <= budget;
+    // Where the (S, Y) history lives: on chip when that does not cost residency, else in a per-CTA global
+    // arena that stays L2-resident (444 CTAs x 41 KB at the C1 shape).  GDMIX_HIST_GLOBAL=0/1 overrides.
+    static const char *env_hist = getenv("GDMIX_HIST_GLOBAL");
+    auto ctas_for = [&](uint32_t smem) {
+        const int by_smem = (int)((228u * 1024u) / (smem + kStaticSmem + 1024u));
+        return std::max(1, std::min({by_smem, 2048 / pl.G, 32, 65536 / (pl.G * 168)}));
+    };
+    pl.G = choose_group(b, o);
+    bool hist_on_chip = L.total_bytes <= budget;
+    if (hist_on_chip && ctas_for(L.fixed_bytes) > ctas_for(L.total_bytes)) hist_on_chip = false;
+    if (env_hist) hist_on_chip = (L.total_bytes <= budget) && atoi(env_hist) == 0;
+    pl.hist_global = hist_on_chip ? 0 : 1;
     pl.smem = hist_on_chip ? L.total_bytes : L.fixed_bytes;
     pl.arena_stride = hist_on_chip ? 0ull : (unsigned long long)gdmix::align16(16u * o->m * b->max_coef);
-    // CTAs per SM: shared memory (228 KB per SM, 1 KB reserved per CTA), 2048 threads, 32 CTAs
-    const int by_smem = (int)((228u * 1024u) / (pl.smem + kStaticSmem + 1024u));
-    pl.ctas_per_sm = std::max(1, std::min({by_smem, 2048 / pl.G, 32}));
+    pl.ctas_per_sm = ctas_for(pl.smem);
     const int64_t want = (int64_t)dev.sm_count * pl.ctas_per_sm;
     pl.grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, b->n_entities));
     pl.workspace = kQueueBytes + (size_t)pl.arena_stride * (size_t)want;
@@ -167,6 +178,7 @@ int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const d
     a.arena = (unsigned char *)workspace + kQueueBytes;
     a.arena_stride = pl.arena_stride;
     a.mode = mode;
+    a.hist_global = pl.hist_global;
     a.smem_bytes = pl.smem;
     CUDA_TRY(cudaMemsetAsync(workspace, 0, kQueueBytes, st));
     if (pl.MT == 10) {
