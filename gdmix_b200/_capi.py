@@ -26,8 +26,8 @@ EPS = float(np.finfo(np.float64).eps)
 SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_workspace_size",
            "gdmix_re_loss_grad", "gdmix_re_fit", "gdmix_re_score", "gdmix_fe_loss_grad", "gdmix_fe_score",
            "gdmix_re_fit_host", "gdmix_re_score_host", "gdmix_host_register", "gdmix_host_unregister",
-           "gdmix_host_release", "gdmix_partition_ids",
-           "gdmix_launch_count"]
+           "gdmix_host_release", "gdmix_partition_ids", "gdmix_lbfgs_create", "gdmix_lbfgs_iterate",
+           "gdmix_lbfgs_info", "gdmix_lbfgs_destroy", "gdmix_launch_count"]
 
 
 class GdmixError(RuntimeError):
@@ -65,6 +65,12 @@ def _load():
     lib.gdmix_version.restype = C.c_char_p
     lib.gdmix_launch_count.restype = C.c_int64
     lib.gdmix_host_release.restype = None
+    lib.gdmix_lbfgs_create.restype = C.c_void_p
+    lib.gdmix_lbfgs_create.argtypes = [C.c_int64, C.c_void_p]
+    lib.gdmix_lbfgs_iterate.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    lib.gdmix_lbfgs_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gdmix_lbfgs_destroy.argtypes = [C.c_void_p]
+    lib.gdmix_lbfgs_destroy.restype = None
     for name in SYMBOLS:
         getattr(lib, name)  # AttributeError if the build is stale
     return lib
@@ -308,3 +314,38 @@ def fe_score_device(rows, opts, x, stream=None):
     cs = rows.c_struct()
     check(lib.gdmix_fe_score(C.byref(cs), C.byref(opts), _tptr(x), _tptr(logit), _tptr(per), _stream_ptr(stream)))
     return logit, per
+
+
+class HostLbfgs:
+    """gdmix_lbfgs_*: the replicated L-BFGS-B state of the fixed-effect solve (host side, reverse communication)."""
+
+    NEED_FG, DONE = 1, 0
+
+    def __init__(self, n, opts):
+        self._h = lib.gdmix_lbfgs_create(C.c_int64(n), C.cast(C.pointer(opts), C.c_void_p))
+        if not self._h:
+            raise GdmixError(GDMIX_ERR_INVALID, lib.gdmix_last_error().decode())
+
+    def iterate(self, x, f, g):
+        """x: float64 numpy array, updated in place; g: float64 numpy array.  -> NEED_FG or DONE."""
+        assert x.dtype == np.float64 and g.dtype == np.float64 and x.flags.c_contiguous and g.flags.c_contiguous
+        rc = lib.gdmix_lbfgs_iterate(self._h, _np_ptr(x), C.c_double(f), _np_ptr(g))
+        if rc < 0:
+            check(rc)
+        return rc
+
+    def info(self):
+        nit, nfev, st, f = C.c_int32(), C.c_int32(), C.c_int32(), C.c_double()
+        check(lib.gdmix_lbfgs_info(self._h, C.byref(nit), C.byref(nfev), C.byref(st), C.byref(f)))
+        return {"nit": nit.value, "nfev": nfev.value, "status": st.value, "f": f.value}
+
+    def close(self):
+        if self._h:
+            lib.gdmix_lbfgs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -14,6 +14,7 @@
 
 #include "../../include/gdmix_b200.h"
 #include "aux_kernels.cuh"
+#include "host_lbfgs.h"
 #include "re_kernel.cuh"
 
 namespace {
@@ -547,6 +548,41 @@ void gdmix_host_release(void)
         s = Slot();
     }
 }
+
+struct gdmix_lbfgs {
+    gdmix_host::Lbfgs impl;
+    gdmix_lbfgs(int64_t n, const gdmix_lr_opts *o)
+        : impl(n, o->m, o->max_iter, o->max_ls, o->max_fun, o->factr, o->pgtol) {}
+};
+
+gdmix_lbfgs *gdmix_lbfgs_create(int64_t n, const gdmix_lr_opts *opts)
+{
+    if (n <= 0 || !opts || opts->m < 0) { fail(GDMIX_ERR_INVALID, "bad argument to gdmix_lbfgs_create"); return nullptr; }
+    try {
+        return new gdmix_lbfgs(n, opts);
+    } catch (...) {
+        fail(GDMIX_ERR_INVALID, "out of host memory in gdmix_lbfgs_create");
+        return nullptr;
+    }
+}
+
+int gdmix_lbfgs_iterate(gdmix_lbfgs *h, double *x, double f, const double *g)
+{
+    if (!h || !x || !g) return fail(GDMIX_ERR_INVALID, "null argument to gdmix_lbfgs_iterate");
+    return h->impl.iterate(x, f, g);
+}
+
+int gdmix_lbfgs_info(const gdmix_lbfgs *h, int32_t *nit, int32_t *nfev, int32_t *status, double *f)
+{
+    if (!h) return fail(GDMIX_ERR_INVALID, "null handle");
+    if (nit) *nit = h->impl.nit();
+    if (nfev) *nfev = h->impl.nfev();
+    if (status) *status = h->impl.status();
+    if (f) *f = h->impl.f();
+    return GDMIX_OK;
+}
+
+void gdmix_lbfgs_destroy(gdmix_lbfgs *h) { delete h; }
 
 int gdmix_partition_ids(const uint16_t *units, const int64_t *id_ptr, int64_t n_ids, int32_t num_partitions,
                         int32_t *hash_out, int32_t *partition_out)

@@ -195,6 +195,18 @@ GDMIX_API void gdmix_host_release(void);
 GDMIX_API int gdmix_partition_ids(const uint16_t *units, const int64_t *id_ptr, int64_t n_ids,
                                   int32_t num_partitions, int32_t *hash_out, int32_t *partition_out);
 
+/* Replicated host-side solver state of the fixed-effect solve: L-BFGS-B without bounds, reverse
+ * communication, the role scipy.optimize.fmin_l_bfgs_b plays at fixed_effect_lr_lbfgs_model.py:635-643.
+ *   h = gdmix_lbfgs_create(n, opts)            (uses opts->m, max_iter, max_ls, max_fun, factr, pgtol)
+ *   task = gdmix_lbfgs_iterate(h, x, f, g)     f, g = all-reduced objective / gradient at x (host memory)
+ *       1: evaluate at the x just written and call again;  0: finished;  < 0: gdmix_status
+ *   gdmix_lbfgs_info(h, &nit, &nfev, &status, &f)   scipy's nit / funcalls / warnflag / final f */
+typedef struct gdmix_lbfgs gdmix_lbfgs;
+GDMIX_API gdmix_lbfgs *gdmix_lbfgs_create(int64_t n, const gdmix_lr_opts *opts);
+GDMIX_API int gdmix_lbfgs_iterate(gdmix_lbfgs *h, double *x, double f, const double *g);
+GDMIX_API int gdmix_lbfgs_info(const gdmix_lbfgs *h, int32_t *nit, int32_t *nfev, int32_t *status, double *f);
+GDMIX_API void gdmix_lbfgs_destroy(gdmix_lbfgs *h);
+
 /* Number of kernel launches issued by this library since load (for bench accounting). */
 GDMIX_API int64_t gdmix_launch_count(void);
 

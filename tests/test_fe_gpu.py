@@ -1,0 +1,78 @@
+"""GPU parity of the fixed-effect path: gdmix_fe_loss_grad / gdmix_fe_score against the oracle and the
+reference test's own restatement (test_fixed_effect_lr_lbfgs_model.py:480-528) recorded in tests/golden/."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():  # pragma: no cover
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from gdmix_b200 import _capi as capi  # noqa: E402
+from gdmix_b200.fe_solver import FixedEffectSolver  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from tests.golden_util import load_fe  # noqa: E402
+
+FE_ARR, FE_CASES = load_fe()
+
+
+def _rows(c, num_workers=1):
+    k = c["key"]
+    return capi.DeviceFeRows(FE_ARR[k + "_rowptr"], FE_ARR[k + "_col"], FE_ARR[k + "_val"], FE_ARR[k + "_y"],
+                             FE_ARR[k + "_w"], FE_ARR[k + "_off"], c["D"],
+                             linear_regression=c["linear_regression"], num_workers=num_workers)
+
+
+def _opts(c, mod):
+    return mod.make_opts(l2=c["l2"], regularize_bias=True, has_intercept=c["has_intercept"], m=c["m"],
+                         max_iter=c["max_iter"], factr=c["factr"])
+
+
+@pytest.mark.parametrize("c", FE_CASES, ids=[c["name"] for c in FE_CASES])
+def test_fe_fit_matches_reference_restatement(c):
+    solver = FixedEffectSolver(_rows(c), _opts(c, capi))
+    x, info = solver.fit(FE_ARR[c["key"] + "_x0"])
+    assert (info["nit"], info["nfev"], info["status"]) == (c["nit"], c["nfev"], c["warnflag"])
+    # the reference asserts in fp32 with assertAllClose's default 1e-6 (test_fixed_effect...:449-464)
+    np.testing.assert_allclose(x, FE_ARR[c["key"] + "_theta"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(x, FE_ARR[c["key"] + "_theta"], rtol=1e-9, atol=1e-11)
+
+
+def test_fe_loss_grad_large_random_matches_oracle():
+    rng = np.random.default_rng(5)
+    n, D, k = 20000, 3000, 12
+    rowptr = np.arange(n + 1, dtype=np.int64) * k
+    col = rng.integers(0, D, size=n * k).astype(np.int32)      # duplicates and hot columns included
+    col[: n * k // 4] = rng.integers(0, 8, size=n * k // 4)     # contended scatter targets
+    val = rng.standard_normal(n * k).astype(np.float32)
+    y = (rng.random(n) < 0.4).astype(np.float32)
+    w = rng.uniform(0.5, 2, n).astype(np.float32)
+    off = rng.standard_normal(n).astype(np.float32)
+    x = rng.standard_normal(D + 1) * 0.3
+    for lin in (False, True):
+        for nw in (1, 8):
+            rows = capi.DeviceFeRows(rowptr, col, val, y, w, off, D, linear_regression=lin, num_workers=nw)
+            po = capi.make_opts(l2=0.7, regularize_bias=False, has_intercept=True)
+            fg = capi.fe_loss_grad_device(rows, po, torch.from_numpy(x).cuda())
+            torch.cuda.synchronize()
+            fg = fg.cpu().numpy()
+            ob = O.FeBlock(n, D, rowptr, col, val, y, w, off, linear_regression=lin, num_workers=nw)
+            f, g = O.fe_loss_grad(ob, O.make_opts(l2=0.7, regularize_bias=False, has_intercept=True), x)
+            assert abs(fg[0] - f) <= 1e-11 * abs(f)
+            np.testing.assert_allclose(fg[1:], g, rtol=1e-9, atol=1e-9)
+
+
+def test_fe_score_matches_definition():
+    c = FE_CASES[0]
+    rows = _rows(c)
+    x = FE_ARR[c["key"] + "_theta"]
+    solver = FixedEffectSolver(rows, _opts(c, capi))
+    logit, per = solver.score(x)
+    k = c["key"]
+    dense = np.zeros((c["n"], c["D"]))
+    rp, col, val = FE_ARR[k + "_rowptr"], FE_ARR[k + "_col"], FE_ARR[k + "_val"]
+    for i in range(c["n"]):
+        dense[i, col[rp[i]:rp[i + 1]]] = val[rp[i]:rp[i + 1]]
+    z = dense @ x[:-1] + x[-1]
+    np.testing.assert_allclose(per, z.astype(np.float32), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(logit, (z + FE_ARR[k + "_off"]).astype(np.float32), rtol=1e-6, atol=1e-6)
