@@ -99,9 +99,16 @@ def cpu_baseline(sample_entities):
     from gdmix_b200.synthetic import make_batch
     from oracle import oracle as O
     from oracle import scipy_port as SP
+    kw = dict(l2=WORKLOAD["l2"], regularize_bias=False, has_intercept=True)
+    if sample_entities <= 0:
+        # size the sample for ~15 s of CPU work on this box: probe the rate on a small slice first
+        probe = make_batch(64 * (os.cpu_count() or 1), WORKLOAD["n"], WORKLOAD["d"], WORKLOAD["k"],
+                           seed=WORKLOAD["seed"])
+        rate = SP.timed_fit(_oracle_batch_dict(probe), probe.n_entities, **kw)["entities_per_sec"]
+        sample_entities = int(min(max(rate * 15.0, 2048), 400000))
     hb = make_batch(sample_entities, WORKLOAD["n"], WORKLOAD["d"], WORKLOAD["k"], seed=WORKLOAD["seed"])
     b = _oracle_batch_dict(hb)
-    r = SP.timed_fit(b, sample_entities, l2=WORKLOAD["l2"], regularize_bias=False, has_intercept=True)
+    r = SP.timed_fit(b, sample_entities, **kw)
     nc = min(sample_entities, 2000)
     t0 = time.perf_counter()
     O.re_fit_batch(b, O.make_opts(l2=WORKLOAD["l2"]), e0=0, e1=nc)
@@ -122,10 +129,12 @@ def run_reference(args):
     from gdmix_b200.synthetic import make_batch
     from oracle import scipy_port as SP
     cores = os.cpu_count() or 1
-    per_step = max(256, 96 * cores)  # ~5 s of work per step at ~170 entities/s/core
+    kw = dict(l2=WORKLOAD["l2"], regularize_bias=False, has_intercept=True)
+    probe = make_batch(64 * cores, WORKLOAD["n"], WORKLOAD["d"], WORKLOAD["k"], seed=WORKLOAD["seed"])
+    rate = SP.timed_fit(_oracle_batch_dict(probe), probe.n_entities, **kw)["entities_per_sec"]
+    per_step = int(min(max(rate * 6.0, 1024), 200000))  # ~6 s of CPU work per step
     hb = make_batch(per_step, WORKLOAD["n"], WORKLOAD["d"], WORKLOAD["k"], seed=WORKLOAD["seed"])
     b = _oracle_batch_dict(hb)
-    kw = dict(l2=WORKLOAD["l2"], regularize_bias=False, has_intercept=True)
     for _ in range(args.warmup):
         SP.timed_fit(b, min(per_step, 4 * cores), **kw)
     secs, done = 0.0, 0
@@ -136,7 +145,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(per_step), "sample_entities_per_step": per_step},
+            "config": {"workload": workload_name(args.entities), "entities_per_gpu": args.entities,
+                       "sample_entities_per_step": per_step,
+                       "note": "each step solves a bounded sample of the same workload (same generator and seed)"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{per_step} c1 entities per step through oracle/scipy_port.py "
                                        "(reference call sequence on scipy/numpy), all host cores"},
@@ -321,12 +332,10 @@ def main():
     ap.add_argument("--entities", type=int, default=1_000_000, help="entities per GPU")
     ap.add_argument("--e2e-entities", type=int, default=131072)
     ap.add_argument("--e2e-chunk", type=int, default=0)
-    ap.add_argument("--cpu-sample", type=int, default=0, help="entities for the cpu_baseline leg (0 = ~100/core)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="entities for the cpu_baseline leg (0 = ~15 s of work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--threads-per-entity", type=int, default=0)
     args = ap.parse_args()
-    if args.cpu_sample <= 0:
-        args.cpu_sample = max(512, 128 * (os.cpu_count() or 1))
     if args.impl == "reference":
         run_reference(args)
     else:
