@@ -1,0 +1,255 @@
+"""TFRecords -> the flat CSR batches the C ABI takes (the reference's producer side).
+
+Random effect: one ``SequenceExample`` per entity (context = entity id + per-sample dense columns as
+variable-length lists; feature_lists = ``<bag>_indices`` / ``<bag>_values`` with one Feature per sample) as read by
+``per_entity_grouped_input_fn`` (gdmix-trainer/src/gdmix/io/input_data_pipeline.py:223-332) and sliced per entity
+by ``prepare_jobs`` (models/custom/scipy/job_consumers.py:161-296):
+
+  * entity id -> ``str`` (bytes decoded as utf-8, integers through ``str()``)            :235-239
+  * global feature ids -> entity-local columns = rank among the entity's sorted unique ids  :243
+  * intercept-only model (no feature bag): X is an n x 1 zero column                        :213-218
+  * warm start: prior intercept + prior coefficients of the features present now            :262-288
+
+Fixed effect: one ``Example`` per row (``per_record_input_fn``, :129-220).
+
+Files: a directory is globbed for ``*.tfrecord``, then ``*.tfrecord.deflate``, then ``*.tfrecord.gz``
+(:88-126); the sorted list is sharded ``files[shard_index::num_shards]`` (util/distribution_utils.py:36-47).
+"""
+import glob
+import os
+
+import numpy as np
+
+from . import constants
+from ._capi import HostBatch
+from .io import tfrecord
+from .io.dataset_metadata import DatasetMetadata
+
+INDICES_SUFFIX = "_indices"
+VALUES_SUFFIX = "_values"
+
+
+def list_tfrecord_files(input_path, num_shards=1, shard_index=0):
+    if isinstance(input_path, (list, tuple)):
+        files = sorted(input_path)
+    elif os.path.isdir(input_path):
+        files = []
+        for suffix in ("", ".deflate", ".gz"):
+            files = sorted(glob.glob(os.path.join(input_path, constants.TFRECORD_GLOB_PATTERN + suffix)))
+            if files:
+                break
+        if not files:
+            files = sorted(f for f in glob.glob(os.path.join(input_path, "*"))
+                           if os.path.isfile(f) and not os.path.basename(f).startswith((".", "_")))
+    else:
+        files = sorted(glob.glob(input_path)) or ([input_path] if os.path.exists(input_path) else [])
+    return files[shard_index::num_shards]
+
+
+def is_empty_directory(path):
+    return not os.path.isdir(path) or not any(not n.startswith((".", "_")) for n in os.listdir(path))
+
+
+class EntityGroupedData:
+    """All entities of one partition, flattened.  Columns are GLOBAL feature ids here."""
+
+    def __init__(self):
+        self.entity_ids = []
+        self.ent_rowptr = np.zeros(1, np.int64)
+        self.rowptr = np.zeros(1, np.int64)
+        self.gcol = np.zeros(0, np.int64)
+        self.val = np.zeros(0, np.float32)
+        self.label = None
+        self.weight = None
+        self.offset = None
+        self.uid = None
+        self.has_weight_column = False
+        self.num_features = 1
+
+    @property
+    def n_entities(self):
+        return len(self.entity_ids)
+
+    @property
+    def n_rows(self):
+        return int(self.ent_rowptr[-1])
+
+
+def _entity_id_to_str(kind, values):
+    v = values[0]
+    if kind == "bytes":
+        return v.decode("utf-8")
+    return str(int(v)) if kind == "int64" else str(v)
+
+
+def read_entity_grouped(input_path, metadata, entity_name, feature_bag, label_column, offset_column, weight_column,
+                        uid_column, num_features, num_shards=1, shard_index=0):
+    """-> EntityGroupedData.  `metadata` is a DatasetMetadata (used to check that the entity column exists, as the
+    reference does) ."""
+    if isinstance(metadata, str):
+        metadata = DatasetMetadata(metadata)
+    if entity_name not in metadata.get_feature_names():
+        raise ValueError(f"entity name {entity_name} is not found among the features")
+    files = list_tfrecord_files(input_path, num_shards, shard_index)
+    ids, n_per_entity = [], []
+    row_len, gcols, vals, labels, weights, offsets, uids = [], [], [], [], [], [], []
+    saw_weight = False
+    for fn in files:
+        for payload in tfrecord.read_records(fn):
+            ctx, lists = tfrecord.parse_sequence_example(payload)
+            if entity_name not in ctx or ctx[entity_name][0] is None:
+                raise ValueError(f"record without entity column {entity_name!r} in {fn}")
+            ids.append(_entity_id_to_str(*ctx[entity_name]))
+            uid = np.asarray(ctx[uid_column][1], dtype=np.int64)
+            n = uid.shape[0]
+            n_per_entity.append(n)
+            uids.append(uid)
+            if feature_bag is None:
+                # intercept-only: one explicit zero in column 0 per sample
+                row_len.append(np.ones(n, np.int64))
+                gcols.append(np.zeros(n, np.int64))
+                vals.append(np.zeros(n, np.float32))
+            else:
+                fi = lists.get(feature_bag + INDICES_SUFFIX, [])
+                fv = lists.get(feature_bag + VALUES_SUFFIX, [])
+                if len(fi) != n or len(fv) != n:
+                    raise ValueError(f"entity {ids[-1]}: {len(fi)} index lists / {len(fv)} value lists for {n} samples")
+                for (_, ci), (_, vi) in zip(fi, fv):
+                    ci = np.zeros(0, np.int64) if ci is None else np.asarray(ci, np.int64)
+                    vi = np.zeros(0, np.float32) if vi is None else np.asarray(vi, np.float32)
+                    if ci.shape[0] != vi.shape[0]:
+                        raise ValueError(f"entity {ids[-1]}: indices / values length mismatch")
+                    gcols.append(ci)
+                    vals.append(vi)
+                row_len.append(np.array([len(c[1]) if c[1] is not None else 0 for c in fi], np.int64))
+            if label_column is not None and label_column in ctx:
+                labels.append(np.asarray(ctx[label_column][1], dtype=np.float32))
+            offsets.append(np.asarray(ctx[offset_column][1], dtype=np.float32) if offset_column in ctx
+                           else np.zeros(n, np.float32))
+            if weight_column is not None and weight_column in ctx:
+                saw_weight = True
+                weights.append(np.asarray(ctx[weight_column][1], dtype=np.float32))
+            else:
+                weights.append(np.ones(n, np.float32))
+    d = EntityGroupedData()
+    d.entity_ids = ids
+    d.num_features = int(num_features)
+    d.has_weight_column = saw_weight
+    d.ent_rowptr = np.concatenate([[0], np.cumsum(n_per_entity)]).astype(np.int64)
+    rl = np.concatenate(row_len) if row_len else np.zeros(0, np.int64)
+    d.rowptr = np.concatenate([[0], np.cumsum(rl)]).astype(np.int64)
+    d.gcol = np.concatenate(gcols).astype(np.int64) if gcols else np.zeros(0, np.int64)
+    d.val = np.concatenate(vals).astype(np.float32) if vals else np.zeros(0, np.float32)
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
+    d.uid = cat(uids, np.int64)
+    d.offset = cat(offsets, np.float32)
+    d.weight = cat(weights, np.float32)
+    d.label = cat(labels, np.float32) if labels and len(labels) == len(ids) else None
+    if d.gcol.size and (d.gcol.min() < 0 or d.gcol.max() >= d.num_features):
+        raise ValueError(f"feature index outside [0, {d.num_features}) in {input_path}")
+    return d
+
+
+def to_local_batch(data, has_intercept=True):
+    """np.unique per entity, vectorised over the whole partition.
+    -> (HostBatch with entity-local columns, uniq_ptr int64[E+1], uniq_global int64[sum d_e])"""
+    E = data.n_entities
+    ent_of_row = np.repeat(np.arange(E, dtype=np.int64), np.diff(data.ent_rowptr))
+    ent_of_nnz = np.repeat(ent_of_row, np.diff(data.rowptr))
+    key = ent_of_nnz * np.int64(data.num_features) + data.gcol
+    uk, inv = np.unique(key, return_inverse=True)
+    ent_of_uk = uk // np.int64(data.num_features)
+    d_e = np.bincount(ent_of_uk, minlength=E).astype(np.int64)
+    uniq_ptr = np.concatenate([[0], np.cumsum(d_e)]).astype(np.int64)
+    local = (inv - uniq_ptr[ent_of_nnz]).astype(np.int32)
+    uniq_global = (uk % np.int64(data.num_features)).astype(np.int64)
+    hi = 1 if has_intercept else 0
+    theta_ptr = np.concatenate([[0], np.cumsum(d_e + hi)]).astype(np.int64)
+    label = data.label if data.label is not None else np.zeros(data.n_rows, np.float32)
+    hb = HostBatch(data.ent_rowptr, data.rowptr, local, data.val, label, data.weight, data.offset, theta_ptr,
+                   has_intercept)
+    return hb, uniq_ptr, uniq_global
+
+
+def warm_start_theta(hb, uniq_ptr, uniq_global, entity_ids, model_weights, has_intercept=True):
+    """theta0 for every entity of the batch plus a has_model flag (job_consumers.py:262-288: the prior's
+    intercept and the prior coefficients of features that occur in the current data; everything else 0)."""
+    hi = 1 if has_intercept else 0
+    theta0 = np.zeros(hb.n_coef, np.float64)
+    has_model = np.zeros(len(entity_ids), np.uint8)
+    if not model_weights:
+        return theta0, has_model
+    for e, eid in enumerate(entity_ids):
+        prior = model_weights.get(eid)
+        if prior is None:
+            continue
+        has_model[e] = 1
+        t0 = hb.theta_ptr[e]
+        ptheta = np.asarray(prior.theta, np.float64)
+        if has_intercept:
+            theta0[t0] = ptheta[0]
+        pidx = np.asarray(prior.unique_global_indices, np.int64)
+        pcoef = ptheta[hi:]
+        cur = uniq_global[uniq_ptr[e]:uniq_ptr[e + 1]]
+        if pidx.size and cur.size:
+            order = np.argsort(pidx, kind="stable")
+            ps, pc = pidx[order], pcoef[order]
+            pos = np.searchsorted(ps, cur)
+            pos_c = np.minimum(pos, ps.size - 1)
+            hit = ps[pos_c] == cur
+            theta0[t0 + hi + np.flatnonzero(hit)] = pc[pos_c[hit]]
+    return theta0, has_model
+
+
+class RecordData:
+    """Rows of a per-record (fixed-effect) dataset as CSR with GLOBAL feature ids."""
+
+    def __init__(self):
+        self.rowptr = np.zeros(1, np.int64)
+        self.col = np.zeros(0, np.int32)
+        self.val = np.zeros(0, np.float32)
+        self.label = None
+        self.weight = None
+        self.offset = None
+        self.uid = None
+        self.has_weight_column = False
+
+    @property
+    def n_rows(self):
+        return len(self.rowptr) - 1
+
+
+def read_per_record(input_path_or_files, feature_bag, label_column, offset_column, weight_column, uid_column,
+                    num_shards=1, shard_index=0):
+    files = list_tfrecord_files(input_path_or_files, num_shards, shard_index)
+    row_len, cols, vals, labels, weights, offsets, uids = [], [], [], [], [], [], []
+    saw_weight = False
+    for fn in files:
+        for payload in tfrecord.read_records(fn):
+            ex = tfrecord.parse_example(payload)
+            if feature_bag is not None:
+                ci = ex.get(feature_bag + INDICES_SUFFIX, (None, None))[1]
+                vi = ex.get(feature_bag + VALUES_SUFFIX, (None, None))[1]
+                ci = np.zeros(0, np.int64) if ci is None else np.asarray(ci, np.int64)
+                vi = np.zeros(0, np.float32) if vi is None else np.asarray(vi, np.float32)
+                cols.append(ci); vals.append(vi); row_len.append(ci.shape[0])
+            else:
+                row_len.append(0)
+            one = lambda name, default: ex[name][1][0] if name is not None and name in ex and len(ex[name][1]) \
+                else default
+            uids.append(one(uid_column, 0))
+            labels.append(one(label_column, np.nan))
+            offsets.append(one(offset_column, 0.0))
+            if weight_column is not None and weight_column in ex:
+                saw_weight = True
+            weights.append(one(weight_column, 1.0))
+    d = RecordData()
+    d.rowptr = np.concatenate([[0], np.cumsum(row_len)]).astype(np.int64)
+    d.col = np.concatenate(cols).astype(np.int32) if cols else np.zeros(0, np.int32)
+    d.val = np.concatenate(vals).astype(np.float32) if vals else np.zeros(0, np.float32)
+    d.uid = np.asarray(uids, np.int64)
+    d.label = np.asarray(labels, np.float32)
+    d.offset = np.asarray(offsets, np.float32)
+    d.weight = np.asarray(weights, np.float32)
+    d.has_weight_column = saw_weight
+    return d

@@ -1,0 +1,158 @@
+"""Photon-ML Avro model files and score files -- the outputs of the path.
+
+Mirrors gdmix-trainer/src/gdmix/util/io_utils.py of the reference:
+  gen_one_avro_model              :102-160   (intercept always first, coefficients with abs(w) <= 1e-4 dropped)
+  export_linear_model_to_avro     :163-212
+  load_linear_models_from_avro    :45-83     (fixed effect: intercept moved to the END)
+  read_feature_list / get_feature_map :215-239
+  get_inference_output_avro_schema    :367-375
+  batched_write_avro              :299-334
+and the schema at models/schemas.py:3-51.
+"""
+import csv
+import json
+
+import numpy as np
+
+from ..constants import INTERCEPT
+from . import avro
+
+BAYESIAN_LINEAR_MODEL_SCHEMA = {
+    "type": "record",
+    "name": "BayesianLinearModelAvro",
+    "namespace": "com.linkedin.photon.avro.generated",
+    "doc": "a generic schema to describe a Bayesian linear model with means and variances",
+    "fields": [
+        {"name": "modelId", "type": "string"},
+        {"name": "modelClass", "type": ["null", "string"], "default": None,
+         "doc": "The fully-qualified class name of enclosing GLM model class. E.g.: "
+                "com.linkedin.photon.ml.supervised.classification.LogisticRegressionModel"},
+        {"name": "means", "type": {"type": "array", "items": {
+            "type": "record", "name": "NameTermValueAvro",
+            "doc": "A tuple of name, term and value. Used as feature or model coefficient",
+            "fields": [{"name": "name", "type": "string"}, {"name": "term", "type": "string"},
+                       {"name": "value", "type": "double"}]}}},
+        {"name": "variances", "type": ["null", {"type": "array", "items": "NameTermValueAvro"}], "default": None},
+        {"name": "lossFunction", "type": ["null", "string"], "default": None,
+         "doc": "The loss function used for training as the class name. E.g.: "
+                "com.linkedin.photon.ml.function.LogisticLossFunction"},
+    ],
+}
+LOGISTIC_MODEL_CLASS = "com.linkedin.photon.ml.supervised.classification.LogisticRegressionModel"
+
+
+def read_feature_list(feature_file):
+    """CSV rows ``name,term``; the row number is the global feature index (intercept not included)."""
+    result = []
+    with open(feature_file, newline="") as f:
+        for row in csv.reader(f):
+            assert len(row) == 2, f"Each feature name should have exactly name and term only, but I got {row}."
+            result.append(tuple(row))
+    return result
+
+
+def get_feature_map(feature_file):
+    return {feature: index for index, feature in enumerate(read_feature_list(feature_file))}
+
+
+def gen_one_avro_model(model_id, model_class, weight_indices, weight_values, bias, feature_list, sparsity_threshold):
+    """One model record.  `weight_values` / `bias` are plain values, or (mean, variance) tuples."""
+    has_bias = bias is not None
+    if isinstance(bias, tuple) and len(bias) == 2 and bias[1] is not None:
+        has_variance = True
+    elif weight_values is not None and isinstance(weight_values, tuple) and len(weight_values) == 2 \
+            and weight_values[1] is not None:
+        has_variance = True
+    else:
+        has_variance = False
+    record = {"modelId": model_id, "modelClass": model_class, "means": [], "lossFunction": ""}
+    if has_bias:
+        record["means"].append({"name": INTERCEPT, "term": "", "value": float(bias[0] if has_variance else bias)})
+    if has_variance:
+        record["variances"] = []
+        if has_bias:
+            record["variances"].append({"name": INTERCEPT, "term": "", "value": float(bias[1])})
+    if weight_indices is not None and weight_values is not None:
+        if has_variance:
+            mean, variance = weight_values
+            variance = np.asarray(variance).flatten()
+        else:
+            mean, variance = weight_values, None
+        for i, (w_i, w_v) in enumerate(zip(np.asarray(weight_indices).flatten(), np.asarray(mean).flatten())):
+            if abs(w_v) > sparsity_threshold:
+                name, term = feature_list[int(w_i)][0], feature_list[int(w_i)][1]
+                record["means"].append({"name": name, "term": term, "value": float(w_v)})
+                if has_variance:
+                    record["variances"].append({"name": name, "term": term, "value": float(variance[i])})
+    return record
+
+
+def export_linear_model_to_avro(model_ids, list_of_weight_indices, list_of_weight_values, biases, feature_file,
+                                output_file, model_log_interval=1000, model_class=LOGISTIC_MODEL_CLASS,
+                                sparsity_threshold=1.0e-4):
+    feature_list = read_feature_list(feature_file) if feature_file else None
+    num_models = len(list_of_weight_indices) if biases is None else len(biases)
+
+    def gen_records():
+        no_weights = list_of_weight_indices is None or list_of_weight_values is None or feature_list is None
+        for i in range(num_models):
+            current_bias = None if biases is None else biases[i]
+            if no_weights:
+                yield gen_one_avro_model(str(model_ids[i]), model_class, None, None, current_bias, feature_list,
+                                         sparsity_threshold)
+            else:
+                yield gen_one_avro_model(str(model_ids[i]), model_class, list_of_weight_indices[i],
+                                         list_of_weight_values[i], current_bias, feature_list, sparsity_threshold)
+
+    avro.write_records(output_file, BAYESIAN_LINEAR_MODEL_SCHEMA, gen_records())
+
+
+def load_linear_models_from_avro(model_file, feature_file):
+    """Fixed-effect loader: dense coefficient arrays with the intercept moved to the end."""
+    feature_map = None if feature_file is None else get_feature_map(feature_file)
+
+    def one(model_record):
+        num_features = 0 if feature_map is None else len(feature_map)
+        coef = np.zeros(num_features + 1, dtype=np.float64)
+        has_bias = 0
+        for ntv in model_record["means"]:
+            name, term, value = ntv["name"], ntv["term"], np.float64(ntv["value"])
+            if name == INTERCEPT and term == "":
+                coef[num_features] = value
+                has_bias = 1
+            elif feature_map is not None:
+                idx = feature_map.get((name, term))
+                if idx is not None:
+                    coef[idx] = value
+        return coef[:num_features + has_bias]
+
+    return tuple(one(r) for r in avro.read_records(model_file))
+
+
+def add_dummy_weight(models):
+    """Intercept-only models get a zero first weight (io_utils.py:86-99)."""
+    out = []
+    for m in models:
+        c = np.zeros(2, dtype=np.float64)
+        c[1] = m[0]
+        out.append(c)
+    return tuple(out)
+
+
+def get_inference_output_avro_schema(metadata, has_logits_per_coordinate, schema_params, has_weight=False):
+    fields = [{"name": schema_params.uid_column_name, "type": "long"},
+              {"name": schema_params.prediction_score_column_name, "type": "float"},
+              {"name": schema_params.label_column_name, "type": ["null", "float"], "default": None}]
+    if has_weight or metadata.get(schema_params.weight_column_name) is not None:
+        fields.append({"name": schema_params.weight_column_name, "type": "float"})
+    if has_logits_per_coordinate:
+        fields.append({"name": schema_params.prediction_score_per_coordinate_column_name, "type": "float"})
+    return {"name": "validation_result", "type": "record", "fields": fields}
+
+
+def batched_write_avro(records, output_file, schema, write_frequency=1000, batch_size=1024):
+    return avro.write_records(output_file, schema, records, batch_size=batch_size)
+
+
+def dumps_schema(schema):
+    return json.dumps(schema)
