@@ -27,7 +27,7 @@ SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_w
            "gdmix_re_loss_grad", "gdmix_re_fit", "gdmix_re_score", "gdmix_fe_loss_grad", "gdmix_fe_score",
            "gdmix_re_fit_host", "gdmix_re_score_host", "gdmix_host_register", "gdmix_host_unregister",
            "gdmix_host_release", "gdmix_partition_ids", "gdmix_lbfgs_create", "gdmix_lbfgs_iterate",
-           "gdmix_lbfgs_info", "gdmix_lbfgs_destroy", "gdmix_launch_count"]
+           "gdmix_lbfgs_info", "gdmix_lbfgs_destroy", "gdmix_launch_count", "gdmix_re_last_plan"]
 
 
 class GdmixError(RuntimeError):
@@ -65,6 +65,7 @@ def _load():
     lib.gdmix_version.restype = C.c_char_p
     lib.gdmix_launch_count.restype = C.c_int64
     lib.gdmix_host_release.restype = None
+    lib.gdmix_re_last_plan.restype = None
     lib.gdmix_lbfgs_create.restype = C.c_void_p
     lib.gdmix_lbfgs_create.argtypes = [C.c_int64, C.c_void_p]
     lib.gdmix_lbfgs_iterate.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
@@ -100,6 +101,14 @@ def device_info():
     sm, smem, cc = C.c_int32(), C.c_int32(), C.c_int32()
     check(lib.gdmix_device_info(C.byref(sm), C.byref(smem), C.byref(cc)))
     return {"sm_count": sm.value, "smem_per_block_optin": smem.value, "cc": cc.value}
+
+
+def last_plan():
+    """Plan of this thread's latest random-effect launch (gdmix_re_last_plan)."""
+    a = (C.c_int32 * 8)()
+    lib.gdmix_re_last_plan(a)
+    keys = ["fast", "threads", "ept", "ctas_per_sm", "cap_steps", "smem", "grid", "hist_global"]
+    return dict(zip(keys, list(a)))
 
 
 def launch_count():

@@ -15,12 +15,14 @@
 #include "../../include/gdmix_b200.h"
 #include "aux_kernels.cuh"
 #include "host_lbfgs.h"
+#include "re_fast.cuh"
 #include "re_kernel.cuh"
 
 namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+thread_local int32_t g_last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
 int fail(int code, const char *fmt, ...)
 {
@@ -72,6 +74,14 @@ struct RePlan {
     int grid = 1;
     int hist_global = 0;         // history lives in the global arena (L2) instead of shared memory
     unsigned long long arena_stride = 0;  // per-CTA history spill in global memory
+    // fast kernel (re_fast.cuh): entities that fit its sliced-ELL staging; the rest is deferred to the
+    // general kernel above through a list in the workspace
+    int fast = 0;
+    int fG = 128, fEPT = 2;
+    int fctas_per_sm = 1;
+    int fgrid = 1;
+    gdmix::FastLayout fL;
+    size_t off_defer = 0, off_arena = 0;
     size_t workspace = 0;
 };
 
@@ -90,6 +100,87 @@ int choose_group(const gdmix_re_batch *b, const gdmix_lr_opts *o)
     if (span <= 96) return 64;
     if (span <= 512) return 128;
     return 256;
+}
+
+// ---- fast path planning ----------------------------------------------------------------------------
+template <int G, int EPT>
+int fast_regs(int &regs)
+{
+    cudaFuncAttributes at;
+    CUDA_TRY(cudaFuncGetAttributes(&at, gdmix::re_fast_kernel<G, EPT>));
+    regs = at.numRegs;
+    return GDMIX_OK;
+}
+
+int fast_regs_of(int G, int EPT, int &regs)
+{
+    switch (G * 4 + EPT) {
+    case 32 * 4 + 1: return fast_regs<32, 1>(regs);
+    case 32 * 4 + 2: return fast_regs<32, 2>(regs);
+    case 64 * 4 + 1: return fast_regs<64, 1>(regs);
+    case 64 * 4 + 2: return fast_regs<64, 2>(regs);
+    case 128 * 4 + 1: return fast_regs<128, 1>(regs);
+    case 128 * 4 + 2: return fast_regs<128, 2>(regs);
+    case 256 * 4 + 1: return fast_regs<256, 1>(regs);
+    default: return fast_regs<256, 2>(regs);
+    }
+}
+
+// Decides whether the batch goes through re_fast_kernel and with what geometry.  Shared memory per CTA is
+// whatever the chosen residency leaves, so the sliced-ELL capacity (cap_steps) is as large as it can be;
+// residency is the largest for which an entity of the batch's maximal shape with evenly spread non-zeros
+// fits.  Entities that still do not fit are deferred to the general kernel one by one.
+int plan_fast(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &dev, RePlan &pl)
+{
+    pl.fast = 0;
+    const char *env_path = getenv("GDMIX_RE_PATH");
+    const char *env_ctas = getenv("GDMIX_FAST_CTAS");
+    const char *env_cap = getenv("GDMIX_FAST_CAP_STEPS");  // test hook: shrink the sliced-ELL capacity to force deferrals
+    if (env_path && strcmp(env_path, "generic") == 0) return GDMIX_OK;
+    const uint32_t hi = o->has_intercept ? 1u : 0u;
+    const uint32_t D = (uint32_t)b->max_coef - hi, N = (uint32_t)b->max_rows;
+    if (o->m > gdmix::kFastMT || D > 512 || N > gdmix::kFastMaxRows) return GDMIX_OK;
+    int G;
+    if (o->threads_per_entity == 32 || o->threads_per_entity == 64 || o->threads_per_entity == 128 ||
+        o->threads_per_entity == 256) {
+        G = o->threads_per_entity;
+    } else {
+        const uint32_t want = std::max((D + 1) / 2, (N + 1) / 2);
+        G = 32;
+        while ((uint32_t)G < want && G < 256) G <<= 1;
+    }
+    if (D > 2u * (uint32_t)G) return GDMIX_OK;
+    const int EPT = (D > (uint32_t)G) ? 2 : 1;
+    int regs = 0;
+    int rc = fast_regs_of(G, EPT, regs);
+    if (rc) return rc;
+    const int regs_alloc = (regs + 7) & ~7;
+    const int k_hw = std::max(1, std::min({65536 / (G * regs_alloc), 2048 / G, 32}));
+    const uint32_t W = (uint32_t)G / 32;
+    const uint32_t fixed = gdmix::fast_fixed_bytes(N, D, W, nullptr);
+    const uint32_t nrslab = (N + 31) / 32, ncslab = (D + 31) / 32;
+    const uint32_t ar = (uint32_t)((b->max_nnz + (int64_t)N - 1) / N), ac = D ? (uint32_t)((b->max_nnz + (int64_t)D - 1) / D) : 0;
+    const uint32_t est = nrslab * ((ar + 3) / 4 + 1) + ncslab * ((ac + 3) / 4 + 1);
+    int k = env_ctas ? std::max(1, std::min(atoi(env_ctas), k_hw)) : k_hw;
+    for (; k >= 1; k--) {
+        const int64_t budget = (int64_t)(228 * 1024) / k - 1024 - (int64_t)kStaticSmem - 64;
+        int64_t cap = (std::min<int64_t>(budget, (int64_t)dev.smem_optin - kStaticSmem - 64) - (int64_t)fixed) /
+                            (int64_t)gdmix::kStepBytes;
+        if (cap >= (int64_t)est) {
+            if (env_cap) cap = std::max<int64_t>(1, std::min<int64_t>(cap, atoi(env_cap)));
+            pl.fast = 1;
+            pl.fG = G; pl.fEPT = EPT; pl.fctas_per_sm = k;
+            pl.fL = gdmix::fast_layout(N, D, W, (uint32_t)cap);
+            const int64_t want = (int64_t)dev.sm_count * k;
+            pl.fgrid = (int)std::max<int64_t>(1, std::min<int64_t>(want, b->n_entities));
+            return GDMIX_OK;
+        }
+        if (env_ctas) break;
+    }
+    if (env_path && strcmp(env_path, "fast") == 0)
+        return fail(GDMIX_ERR_TOO_LARGE, "GDMIX_RE_PATH=fast but the batch shape (%u rows, %d nnz, %u features) "
+                    "does not fit the fast kernel", N, b->max_nnz, D);
+    return GDMIX_OK;
 }
 
 int plan_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &dev, RePlan &pl)
@@ -130,7 +221,11 @@ int plan_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &d
     pl.ctas_per_sm = ctas_for(pl.smem);
     const int64_t want = (int64_t)dev.sm_count * pl.ctas_per_sm;
     pl.grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, b->n_entities));
-    pl.workspace = kQueueBytes + (size_t)pl.arena_stride * (size_t)want;
+    int rc = plan_fast(b, o, dev, pl);
+    if (rc) return rc;
+    pl.off_defer = kQueueBytes;
+    pl.off_arena = pl.off_defer + (pl.fast ? (((size_t)b->n_entities * 4 + 255) & ~(size_t)255) : 0);
+    pl.workspace = pl.off_arena + (size_t)pl.arena_stride * (size_t)want;
     return GDMIX_OK;
 }
 
@@ -147,6 +242,36 @@ int launch_re_t(const gdmix::ReArgs &args, const RePlan &pl, cudaStream_t st)
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return GDMIX_OK;
+}
+
+
+template <int G, int EPT>
+int launch_fast_t(const gdmix::FastArgs &fa, const RePlan &pl, cudaStream_t st)
+{
+    static std::atomic<int> configured{0};
+    if (!configured.load()) {
+        CUDA_TRY(cudaFuncSetAttribute(gdmix::re_fast_kernel<G, EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024 - (int)kStaticSmem));
+        configured.store(1);
+    }
+    gdmix::re_fast_kernel<G, EPT><<<pl.fgrid, G, pl.fL.total_bytes, st>>>(fa);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
+int launch_fast(const gdmix::FastArgs &fa, const RePlan &pl, cudaStream_t st)
+{
+    switch (pl.fG * 4 + pl.fEPT) {
+    case 32 * 4 + 1: return launch_fast_t<32, 1>(fa, pl, st);
+    case 32 * 4 + 2: return launch_fast_t<32, 2>(fa, pl, st);
+    case 64 * 4 + 1: return launch_fast_t<64, 1>(fa, pl, st);
+    case 64 * 4 + 2: return launch_fast_t<64, 2>(fa, pl, st);
+    case 128 * 4 + 1: return launch_fast_t<128, 1>(fa, pl, st);
+    case 128 * 4 + 2: return launch_fast_t<128, 2>(fa, pl, st);
+    case 256 * 4 + 1: return launch_fast_t<256, 1>(fa, pl, st);
+    default: return launch_fast_t<256, 2>(fa, pl, st);
+    }
 }
 
 int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const double *theta_in, double *theta_out,
@@ -176,12 +301,32 @@ int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const d
     a.theta_in = theta_in; a.theta_out = theta_out; a.f_out = f_out; a.nit = nit; a.nfev = nfev; a.status = status;
     a.var_out = var_out; a.g_out = g_out;
     a.queue = (int32_t *)workspace;
-    a.arena = (unsigned char *)workspace + kQueueBytes;
+    a.arena = (unsigned char *)workspace + pl.off_arena;
     a.arena_stride = pl.arena_stride;
     a.mode = mode;
     a.hist_global = pl.hist_global;
     a.smem_bytes = pl.smem;
     CUDA_TRY(cudaMemsetAsync(workspace, 0, kQueueBytes, st));
+    g_last_plan[0] = pl.fast; g_last_plan[1] = pl.fast ? pl.fG : pl.G; g_last_plan[2] = pl.fast ? pl.fEPT : 0;
+    g_last_plan[3] = pl.fast ? pl.fctas_per_sm : pl.ctas_per_sm;
+    g_last_plan[4] = pl.fast ? (int32_t)pl.fL.cap_steps : 0;
+    g_last_plan[5] = pl.fast ? (int32_t)pl.fL.total_bytes : (int32_t)pl.smem;
+    g_last_plan[6] = pl.fast ? pl.fgrid : pl.grid;
+    g_last_plan[7] = pl.hist_global;
+    if (pl.fast) {
+        // fast kernel first; what it defers (entities whose sliced form does not fit) is drained by the
+        // general kernel from the list, with its own work counter
+        gdmix::FastArgs fa;
+        fa.a = a;
+        fa.L = pl.fL;
+        fa.defer_list = (int32_t *)((unsigned char *)workspace + pl.off_defer);
+        fa.defer_count = (int32_t *)workspace + 2;
+        rc = launch_fast(fa, pl, st);
+        if (rc) return rc;
+        a.queue = (int32_t *)workspace + 1;
+        a.todo = fa.defer_list;
+        a.todo_count = fa.defer_count;
+    }
     if (pl.MT == 10) {
         switch (pl.G) {
         case 32: return launch_re_t<32, 10>(a, pl, st);
@@ -287,6 +432,11 @@ int gdmix_device_info(int32_t *sm_count, int32_t *smem_per_block_optin, int32_t 
     if (smem_per_block_optin) *smem_per_block_optin = d.smem_optin;
     if (cc) *cc = d.cc;
     return GDMIX_OK;
+}
+
+void gdmix_re_last_plan(int32_t *out8)
+{
+    if (out8) memcpy(out8, g_last_plan, sizeof(g_last_plan));
 }
 
 int gdmix_re_workspace_size(const gdmix_re_batch *batch, const gdmix_lr_opts *opts, size_t *bytes)

@@ -1,0 +1,890 @@
+// re_fast.cuh -- the random-effect solver for the common case (m <= 10, at most 2 local features per thread).
+//
+// Same algorithm and the same per-entity semantics as re_kernel.cuh (see its banner for the reference
+// call sites); what differs is where things live and how the two sparse passes walk them:
+//
+//   * X on chip in sliced-ELL form.  Rows (for z = X1.theta) and columns (for g = X1^T r) are each sorted by
+//     length (stable counting sort on chip), cut into slabs of 32 segments, and a slab is stored step-major:
+//     step k holds, for each of its 32 lanes, four consecutive non-zeros of that lane's segment
+//     ([step][lane][4] values fp32, and the same shape of u16 byte offsets into the gathered vector).  One
+//     LDS.128 + one LDS.64 per lane fetch four non-zeros with no bank conflicts and no per-element index
+//     arithmetic; lanes of a warp run in lockstep for exactly the slab's step count, and sorting keeps the
+//     padding to the last partial quad of each segment.  A step is 33 lane-quads wide, not 32: the phantom
+//     quad skews consecutive steps by four banks so that staging's row-wise writes do not collide either.
+//   * L-BFGS history (S, Y: 2 m p doubles) in REGISTERS: feature c belongs to thread c mod G, slot c / G
+//     (EPT = 1 or 2 slots).  The two dense passes of the compact update (2m+2 inner products with the new
+//     gradient; the direction as a combination of S, Y columns) then touch no memory at all.  The intercept's
+//     component of every history vector lives in lane s of warp 0 (slot s) and joins in the warp-sized m x m step.
+//   * The 22 inner products are reduced across a warp by transposing butterflies, 12 values at a time
+//     (18 shuffles per dozen instead of 60).
+//   * Staging reads the entity's CSR slice from HBM with row-contiguous (coalesced) loads.
+//
+// Entities whose sliced form does not fit the shared memory planned for the batch are not solved here: their
+// index goes to a deferral list that the general kernel (re_kernel.cuh) drains right afterwards.
+#pragma once
+#include "linesearch.cuh"
+#include "re_common.cuh"
+#include "re_lbfgs.cuh"
+
+namespace gdmix {
+
+constexpr int kFastMT = 10;
+constexpr uint32_t kKeys = 64;                    // segment lengths are sorted exactly below this, clipped above
+constexpr uint32_t kStepQuads = 33;               // lane-quads per slab step (32 + 1 phantom for the bank skew)
+constexpr uint32_t kStepElems = 4 * kStepQuads;   // 132 non-zero slots per step
+constexpr uint32_t kStepBytes = 6 * kStepElems;   // fp32 value + u16 offset
+constexpr uint32_t kFastMaxRows = 8191;           // u16 byte offsets into fp64 vectors
+constexpr uint32_t kFastPartK = 24;
+
+using DNF = Dense<kFastMT>;
+constexpr uint32_t kFastDense = DNF::count + 2;   // + direction / trial value of the intercept
+
+// Byte offsets of one CTA's dynamic shared memory.  N = max rows, D = max local features of the batch.
+struct FastLayout {
+    uint32_t xt, gnew, r, dense, part;                       // solve block
+    uint32_t rowoff, ccnt, keys, rowpos, colpos, seglen;     // staging scratch, aliases the solve block
+    uint32_t rowperm, colperm, sy, sw, soff, rbase, cbase;   // live through the solve
+    uint32_t sell_val, sell_idx;
+    uint32_t cap_steps;
+    uint32_t total_bytes;
+};
+
+__host__ __device__ inline uint32_t fast_fixed_bytes(uint32_t N, uint32_t D, uint32_t W, FastLayout *out)
+{
+    FastLayout L;
+    uint32_t o = 0;
+    L.xt = o; o += align16(8 * D);
+    L.gnew = o; o += align16(8 * D);
+    L.r = o; o += align16(8 * N);
+    L.dense = o; o += align16(8 * kFastDense);
+    L.part = o; o += align16(8 * kMaxWarps * kFastPartK);
+    const uint32_t solve_end = o;
+    o = 0;
+    L.rowoff = o; o += align16(4 * (N + 1));
+    L.ccnt = o; o += align16(4 * W * D);
+    L.keys = o; o += align16(4 * 2 * kKeys);
+    L.rowpos = o; o += align16(2 * N);
+    L.colpos = o; o += align16(2 * D);
+    L.seglen = o; o += align16(2 * D);
+    o = o > solve_end ? o : solve_end;
+    const uint32_t N32 = (N + 31u) & ~31u, D32 = (D + 31u) & ~31u;
+    L.rowperm = o; o += align16(2 * N32);
+    L.colperm = o; o += align16(2 * D32);
+    L.sy = o; o += align16(4 * N32);
+    L.sw = o; o += align16(4 * N32);
+    L.soff = o; o += align16(4 * N32);
+    L.rbase = o; o += align16(4 * (N32 / 32 + 2));
+    L.cbase = o; o += align16(4 * (D32 / 32 + 2));
+    L.sell_val = o;
+    L.sell_idx = 0; L.cap_steps = 0; L.total_bytes = o;
+    if (out) *out = L;
+    return o;
+}
+
+__host__ __device__ inline FastLayout fast_layout(uint32_t N, uint32_t D, uint32_t W, uint32_t cap_steps)
+{
+    FastLayout L;
+    uint32_t o = fast_fixed_bytes(N, D, W, &L);
+    L.cap_steps = cap_steps;
+    L.sell_val = o; o += align16(4 * kStepElems * cap_steps);
+    L.sell_idx = o; o += align16(2 * kStepElems * cap_steps);
+    L.total_bytes = o;
+    return L;
+}
+
+struct FastArgs {
+    ReArgs a;
+    FastLayout L;
+    int32_t *defer_list;   // entities this kernel could not hold on chip
+    int32_t *defer_count;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// 12 per-lane partial sums -> totals.  Afterwards v[0..2] of a lane hold the totals of the values
+// 6*b4 + 3*b3 + {0,1,2} (b_k = bit k of the lane index).  Fixed order: bitwise reproducible.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_reduce12(double (&v)[12], const uint32_t lane)
+{
+    {
+        const bool up = lane & 16u;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            const double keep = up ? v[i + 6] : v[i], send = up ? v[i] : v[i + 6];
+            v[i] = keep + __shfl_xor_sync(kFull, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8u;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const double keep = up ? v[i + 3] : v[i], send = up ? v[i] : v[i + 3];
+            v[i] = keep + __shfl_xor_sync(kFull, send, 8);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        v[i] += __shfl_xor_sync(kFull, v[i], 4);
+        v[i] += __shfl_xor_sync(kFull, v[i], 2);
+        v[i] += __shfl_xor_sync(kFull, v[i], 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Slab sort: stable counting sort of `nseg` segments by descending clipped length (warp 0), then the step
+// count of every slab of 32 and their prefix sums.  pos[i] = sorted position of segment i, perm = inverse,
+// base[b] = first step of slab b (base[nslab] = end), starting at base0.  All threads call it.
+// ---------------------------------------------------------------------------------------------------------
+template <int G, class LenFn>
+__device__ __forceinline__ void slab_sort(const LenFn len, const uint32_t nseg, uint16_t *pos, uint16_t *perm,
+                                          uint32_t *base, const uint32_t base0, uint32_t *keys)
+{
+    constexpr uint32_t W = G / 32;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t k = tid; k < 2 * kKeys; k += G) keys[k] = 0;
+    group_sync<G>();
+    for (uint32_t i = tid; i < nseg; i += G) atomicAdd(&keys[min(len(i), kKeys - 1u)], 1u);
+    group_sync<G>();
+    if (warp == 0) {
+        // lane l owns keys kKeys-1-2l and kKeys-2-2l; starts are counted from the longest key down
+        const uint32_t k0 = kKeys - 1u - 2u * lane, k1 = k0 - 1u;
+        const uint32_t c0 = keys[k0], c1 = keys[k1];
+        uint32_t incl = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        const uint32_t excl = incl - (c0 + c1);
+        keys[kKeys + k0] = excl;
+        keys[kKeys + k1] = excl + c0;
+        __syncwarp();
+        for (uint32_t b0 = 0; b0 < nseg; b0 += 32) {
+            const uint32_t i = b0 + lane;
+            const bool act = i < nseg;
+            const uint32_t key = act ? min(len(i), kKeys - 1u) : (kKeys + lane);
+            const unsigned grp = __match_any_sync(kFull, key);
+            const uint32_t rank = __popc(grp & ((1u << lane) - 1u));
+            uint32_t cur = 0;
+            if (act) {
+                cur = keys[kKeys + key];
+                pos[i] = (uint16_t)(cur + rank);
+                perm[cur + rank] = (uint16_t)i;
+            }
+            __syncwarp();
+            if (act && rank == (uint32_t)__popc(grp) - 1u) keys[kKeys + key] = cur + rank + 1u;
+            __syncwarp();
+        }
+    }
+    group_sync<G>();
+    const uint32_t nslab = (nseg + 31u) >> 5;
+    for (uint32_t b = warp; b < nslab; b += W) {
+        const uint32_t i = b * 32u + lane;
+        uint32_t l = (i < nseg) ? len(perm[i]) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) l = max(l, __shfl_xor_sync(kFull, l, o));
+        if (lane == 0) base[b] = (l + 3u) >> 2;
+    }
+    group_sync<G>();
+    if (warp == 0) {
+        uint32_t carry = base0;
+        for (uint32_t b0 = 0; b0 < nslab; b0 += 32) {
+            const uint32_t b = b0 + lane;
+            const uint32_t mine = (b < nslab) ? base[b] : 0u;
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(kFull, incl, o);
+                if (lane >= (uint32_t)o) incl += t;
+            }
+            if (b < nslab) base[b] = carry + incl - mine;
+            carry += __shfl_sync(kFull, incl, 31);
+        }
+        if (lane == 0) base[nslab] = carry;
+    }
+    group_sync<G>();
+}
+
+// L2 prefetch hints for the CSR slice of a later entity (one warp; nobody waits for it).
+__device__ __forceinline__ void prefetch_entity_l2(const gdmix_re_batch &b, const int64_t e2, const uint32_t lane)
+{
+    if (e2 >= b.n_entities) return;
+    const int64_t r0 = b.ent_rowptr[e2], r1 = b.ent_rowptr[e2 + 1];
+    const int64_t q0 = b.rowptr[r0], q1 = b.rowptr[r1];
+    auto hint = [&](const char *p0, const char *p1) {
+        for (const char *p = (const char *)((uintptr_t)p0 & ~(uintptr_t)127) + 128 * (size_t)lane; p < p1; p += 128 * 32)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    };
+    hint((const char *)(b.col + q0), (const char *)(b.col + q1));
+    hint((const char *)(b.val + q0), (const char *)(b.val + q1));
+    hint((const char *)(b.rowptr + r0), (const char *)(b.rowptr + r1 + 1));
+    hint((const char *)(b.label + r0), (const char *)(b.label + r1));
+    if (b.offset) hint((const char *)(b.offset + r0), (const char *)(b.offset + r1));
+    if (b.weight) hint((const char *)(b.weight + r0), (const char *)(b.weight + r1));
+}
+
+// One lane's share of a slab: sum over `nsteps` quads of val * vec[offset].  val / idx point at this lane's
+// quad of the slab's first step; vec is the gathered fp64 vector (byte offsets).
+__device__ __forceinline__ double sell_dot(const float4 *pv, const uint2 *pi, const uint32_t nsteps, const char *vec)
+{
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    uint32_t k = 0;
+    for (; k + 2 <= nsteps; k += 2) {
+        const float4 va = pv[k * kStepQuads], vb = pv[(k + 1) * kStepQuads];
+        const uint2 ca = pi[k * kStepQuads], cb = pi[(k + 1) * kStepQuads];
+        const double x0 = *(const double *)(vec + (ca.x & 0xffffu)), x1 = *(const double *)(vec + (ca.x >> 16));
+        const double x2 = *(const double *)(vec + (ca.y & 0xffffu)), x3 = *(const double *)(vec + (ca.y >> 16));
+        const double x4 = *(const double *)(vec + (cb.x & 0xffffu)), x5 = *(const double *)(vec + (cb.x >> 16));
+        const double x6 = *(const double *)(vec + (cb.y & 0xffffu)), x7 = *(const double *)(vec + (cb.y >> 16));
+        s0 = fma((double)va.x, x0, s0);
+        s1 = fma((double)va.y, x1, s1);
+        s2 = fma((double)va.z, x2, s2);
+        s3 = fma((double)va.w, x3, s3);
+        s0 = fma((double)vb.x, x4, s0);
+        s1 = fma((double)vb.y, x5, s1);
+        s2 = fma((double)vb.z, x6, s2);
+        s3 = fma((double)vb.w, x7, s3);
+    }
+    if (k < nsteps) {
+        const float4 va = pv[k * kStepQuads];
+        const uint2 ca = pi[k * kStepQuads];
+        const double x0 = *(const double *)(vec + (ca.x & 0xffffu)), x1 = *(const double *)(vec + (ca.x >> 16));
+        const double x2 = *(const double *)(vec + (ca.y & 0xffffu)), x3 = *(const double *)(vec + (ca.y >> 16));
+        s0 = fma((double)va.x, x0, s0);
+        s1 = fma((double)va.y, x1, s1);
+        s2 = fma((double)va.z, x2, s2);
+        s3 = fma((double)va.w, x3, s3);
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+
+// The staged entity as the passes see it: five small integers; every array is addressed as smem + an offset
+// of the launch-constant FastLayout (kernel parameter space), so no pointer stays live across the solve.
+struct FastDims {
+    uint32_t n, d, hi, nrslab, ncslab;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Staging.  Returns 0 = staged, 1 = invalid input (column out of range), 2 = does not fit (defer).
+// ---------------------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ int fast_stage(const ReArgs &a, const FastLayout &L, unsigned char *smem,
+                                          const int64_t r0, const int64_t q0, const uint32_t n, const uint32_t d,
+                                          unsigned *s_flag, uint32_t &nrslab, uint32_t &ncslab)
+{
+    constexpr uint32_t W = G / 32;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *rowoff = (uint32_t *)(smem + L.rowoff), *ccnt = (uint32_t *)(smem + L.ccnt);
+    uint32_t *keys = (uint32_t *)(smem + L.keys);
+    uint16_t *rowpos = (uint16_t *)(smem + L.rowpos), *colpos = (uint16_t *)(smem + L.colpos);
+    uint16_t *seglen = (uint16_t *)(smem + L.seglen);
+    uint16_t *rowperm = (uint16_t *)(smem + L.rowperm), *colperm = (uint16_t *)(smem + L.colperm);
+    uint32_t *rbase = (uint32_t *)(smem + L.rbase), *cbase = (uint32_t *)(smem + L.cbase);
+    float *sval = (float *)(smem + L.sell_val);
+    uint16_t *sidx = (uint16_t *)(smem + L.sell_idx);
+    float *sy = (float *)(smem + L.sy), *sw = (float *)(smem + L.sw), *soff = (float *)(smem + L.soff);
+
+    for (uint32_t i = tid; i <= n; i += G) rowoff[i] = (uint32_t)(a.b.rowptr[r0 + i] - q0);
+    for (uint32_t k = tid; k < W * d; k += G) ccnt[k] = 0;
+    group_sync<G>();
+
+    // ---- rows: sort, slab bases, zero fill, fill (coalesced: a warp streams one row at a time) -------------
+    slab_sort<G>([&](uint32_t i) { return rowoff[i + 1] - rowoff[i]; }, n, rowpos, rowperm, rbase, 0u, keys);
+    nrslab = (n + 31u) >> 5;
+    const uint32_t total_r = rbase[nrslab];
+    if (total_r > L.cap_steps) return 2;
+    {
+        uint4 *zv = (uint4 *)sval;
+        const uint32_t nv = total_r * (kStepElems / 4);
+        for (uint32_t k = tid; k < nv; k += G) zv[k] = make_uint4(0, 0, 0, 0);
+        uint4 *zi = (uint4 *)sidx;
+        const uint32_t ni = (total_r * kStepElems * 2 + 15) / 16;
+        for (uint32_t k = tid; k < ni; k += G) zi[k] = make_uint4(0, 0, 0, 0);
+    }
+    for (uint32_t i = tid; i < n; i += G) {
+        const uint32_t sp = rowpos[i];
+        sy[sp] = a.b.label[r0 + i];
+        sw[sp] = a.b.weight ? a.b.weight[r0 + i] : 1.0f;
+        soff[sp] = a.b.offset ? a.b.offset[r0 + i] : 0.0f;
+    }
+    group_sync<G>();
+    const uint32_t chunk = (n + W - 1) / W;
+    const uint32_t rbeg = min(n, warp * chunk), rend = min(n, rbeg + chunk);
+    unsigned bad = 0;
+    auto put = [&](const uint32_t at, const uint32_t j, const uint32_t c, const float v) {
+        if (c < d) {
+            const uint32_t dst = at + (j >> 2) * kStepElems + (j & 3u);
+            sval[dst] = v;
+            sidx[dst] = (uint16_t)(c * 8u);
+            atomicAdd(&ccnt[warp * d + c], 1u);
+        } else {
+            bad = 1;
+        }
+    };
+    // eight rows per trip: all their loads are in flight before the first is consumed (one warp streams one
+    // row at a time, so without this every row would cost a full HBM round trip)
+    for (uint32_t i0 = rbeg; i0 < rend; i0 += 8) {
+        uint32_t cc[8], ss[8], ll[8];
+        float vv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t i = i0 + u;
+            ss[u] = 0; ll[u] = 0; cc[u] = 0; vv[u] = 0.0f;
+            if (i < rend) {
+                ss[u] = rowoff[i];
+                ll[u] = rowoff[i + 1] - ss[u];
+                if (lane < ll[u]) {
+                    cc[u] = (uint32_t)a.b.col[q0 + ss[u] + lane];
+                    vv[u] = a.b.val[q0 + ss[u] + lane];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (ll[u] == 0) continue;
+            const uint32_t sp = rowpos[i0 + u];
+            const uint32_t at = rbase[sp >> 5] * kStepElems + (sp & 31u) * 4u;
+            if (lane < ll[u]) put(at, lane, cc[u], vv[u]);
+            for (uint32_t j = lane + 32; j < ll[u]; j += 32)
+                put(at, j, (uint32_t)a.b.col[q0 + ss[u] + j], a.b.val[q0 + ss[u] + j]);
+        }
+    }
+    if (bad) atomicOr(s_flag, 1u);
+    group_sync<G>();
+    if (*s_flag) return 1;
+
+    // ---- columns: lengths and per-warp cursors, sort, slab bases, zero fill, row-ordered fill ------------
+    for (uint32_t c = tid; c < d; c += G) {
+        uint32_t run = 0;
+#pragma unroll
+        for (uint32_t w2 = 0; w2 < W; w2++) {
+            const uint32_t t = ccnt[w2 * d + c];
+            ccnt[w2 * d + c] = run;
+            run += t;
+        }
+        seglen[c] = (uint16_t)run;
+    }
+    group_sync<G>();
+    slab_sort<G>([&](uint32_t c) { return (uint32_t)seglen[c]; }, d, colpos, colperm, cbase, total_r, keys);
+    ncslab = (d + 31u) >> 5;
+    const uint32_t total = cbase[ncslab];
+    if (total > L.cap_steps) return 2;
+    {
+        uint4 *zv = (uint4 *)(sval + (size_t)total_r * kStepElems);
+        const uint32_t nv = (total - total_r) * (kStepElems / 4);
+        for (uint32_t k = tid; k < nv; k += G) zv[k] = make_uint4(0, 0, 0, 0);
+        // u16 region: kStepElems * 2 = 264 B per step, 8-byte granular
+        uint2 *zi = (uint2 *)(sidx + (size_t)total_r * kStepElems);
+        const uint32_t ni = (total - total_r) * (kStepElems / 4);
+        for (uint32_t k = tid; k < ni; k += G) zi[k] = make_uint2(0, 0);
+    }
+    group_sync<G>();
+    // second sweep out of the sliced rows just built (no global traffic): scatter every non-zero to its
+    // column's next free slot.  A warp walks its rows in ascending order, so a column's entries end up in row order.
+    for (uint32_t i = rbeg; i < rend; i++) {
+        const uint32_t len = rowoff[i + 1] - rowoff[i];
+        const uint32_t rp = rowpos[i];
+        const uint32_t rat = rbase[rp >> 5] * kStepElems + (rp & 31u) * 4u;
+        for (uint32_t j0 = 0; j0 < len; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            const bool act = j < len;
+            const uint32_t src = rat + (j >> 2) * kStepElems + (j & 3u);
+            const uint32_t c = act ? ((uint32_t)sidx[src] >> 3) : (0x10000u + lane);
+            const float v = act ? sval[src] : 0.0f;
+            // columns strictly ascending inside the chunk (the usual case) => no column occurs twice
+            const uint32_t prev = __shfl_up_sync(kFull, c, 1);
+            const bool uniq = __all_sync(kFull, lane == 0 || c > prev);
+            unsigned grp = 1u << lane;
+            if (!uniq) grp = __match_any_sync(kFull, c);
+            const uint32_t rank = __popc(grp & ((1u << lane) - 1u));
+            uint32_t cur = 0;
+            if (act) {
+                cur = ccnt[warp * d + c];
+                const uint32_t e = cur + rank, sp = colpos[c];
+                const uint32_t dst = (cbase[sp >> 5] + (e >> 2)) * kStepElems + (sp & 31u) * 4u + (e & 3u);
+                sval[dst] = v;
+                sidx[dst] = (uint16_t)(i * 8u);
+            }
+            __syncwarp();
+            if (act && rank == (uint32_t)__popc(grp) - 1u) ccnt[warp * d + c] = cur + rank + 1u;
+            __syncwarp();
+        }
+    }
+    group_sync<G>();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// f, g at the trial point held in smem xt (features) / xt0 (intercept).  sq_part = this thread's share of
+// sum xt_reg^2.  On return gn[] holds this thread's slots of the new gradient, gn0 the intercept's, and every
+// thread has identical f, gd (= g.d) and gmax (= max|g|).
+// ---------------------------------------------------------------------------------------------------------
+template <int G, int EPT>
+__device__ __forceinline__ void fast_evaluate(const FastArgs &fa, unsigned char *smem, const FastDims &E,
+                                              const double xt0, const double sq_part, const double (&dd)[EPT],
+                                              const double d0, double (&gn)[EPT], double &gn0, double *red,
+                                              int &flip, double &f, double &gd, double &gmax)
+{
+    constexpr uint32_t W = G / 32;
+    const FastLayout &L = fa.L;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double l2 = fa.a.o.l2;
+    const double inv_n = 1.0 / (double)E.n;
+    double part[3] = {0.0, 0.0, sq_part};
+    {
+        const uint32_t *rbase = (const uint32_t *)(smem + L.rbase);
+        const char *xt = (const char *)(smem + L.xt);
+        for (uint32_t b = warp; b < E.nrslab; b += W) {
+            const uint32_t st = rbase[b];
+            double z = sell_dot((const float4 *)(smem + L.sell_val) + st * kStepQuads + lane,
+                                (const uint2 *)(smem + L.sell_idx) + st * kStepQuads + lane, rbase[b + 1] - st, xt);
+            const uint32_t sp = b * 32u + lane;
+            if (sp < E.n) {
+                z = (z + (E.hi ? xt0 : 0.0)) + (double)((const float *)(smem + L.soff))[sp];
+                const double yi = (double)((const float *)(smem + L.sy))[sp];
+                const double wi = (double)((const float *)(smem + L.sw))[sp];
+                const double e = exp(-fabs(z));
+                const double ce = fmax(z, 0.0) - z * yi + log(1.0 + e);
+                part[0] = fma(wi, ce, part[0]);
+                const double inv = 1.0 / (1.0 + e);
+                const double sig = (z >= 0.0) ? inv : e * inv;
+                const double ri = wi * (sig - yi);
+                ((double *)(smem + L.r))[((const uint16_t *)(smem + L.rowperm))[sp]] = ri;
+                part[1] += ri;
+            }
+        }
+    }
+    group_sum<G, 3>(part, red, flip);  // its barrier also publishes r[]
+    if (G == 32) __syncwarp();
+    f = (part[0] + 0.5 * l2 * part[2]) * inv_n;
+    {
+        const uint32_t *cbase = (const uint32_t *)(smem + L.cbase);
+        const char *rv = (const char *)(smem + L.r);
+        for (uint32_t b = warp; b < E.ncslab; b += W) {
+            const uint32_t st = cbase[b];
+            const double acc = sell_dot((const float4 *)(smem + L.sell_val) + st * kStepQuads + lane,
+                                        (const uint2 *)(smem + L.sell_idx) + st * kStepQuads + lane,
+                                        cbase[b + 1] - st, rv);
+            const uint32_t sp = b * 32u + lane;
+            if (sp < E.d) {
+                const uint32_t c = ((const uint16_t *)(smem + L.colperm))[sp];
+                ((double *)(smem + L.gnew))[c] = (acc + l2 * ((const double *)(smem + L.xt))[c]) * inv_n;
+            }
+        }
+    }
+    group_sync<G>();
+    double gdp = 0.0, gmp = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPT; e++) {
+        const uint32_t c = tid + (uint32_t)e * G;
+        const double ge = (c < E.d) ? ((const double *)(smem + L.gnew))[c] : 0.0;
+        gn[e] = ge;
+        gdp = fma(ge, dd[e], gdp);
+        gmp = fmax(gmp, fabs(ge));
+    }
+    gn0 = 0.0;
+    if (E.hi) {
+        gn0 = (part[1] + (fa.a.o.regularize_bias ? l2 * xt0 : 0.0)) * inv_n;
+        if (tid == 0) gdp = fma(gn0, d0, gdp);
+        gmp = fmax(gmp, fabs(gn0));
+    }
+    group_sum_max<G>(gdp, gmp, red, flip);
+    gd = gdp;
+    gmax = gmp;
+}
+
+// Writes the trial point x + stp d into smem xt; returns the intercept's trial value and this thread's share
+// of sum xt_reg^2.
+template <int G, int EPT>
+__device__ __forceinline__ double fast_trial(const FastArgs &fa, unsigned char *smem, const FastDims &E,
+                                             const double stp, const double (&x)[EPT], const double (&dd)[EPT],
+                                             const double x0, const double d0, double &sq)
+{
+    double *xt = (double *)(smem + fa.L.xt);
+    sq = 0.0;
+#pragma unroll
+    for (int k = 0; k < EPT; k++) {
+        const uint32_t c = threadIdx.x + (uint32_t)k * G;
+        const double t = fma(stp, dd[k], x[k]);
+        if (c < E.d) { xt[c] = t; sq = fma(t, t, sq); }
+    }
+    const double xt0 = fma(stp, d0, x0);
+    if (E.hi && fa.a.o.regularize_bias && threadIdx.x == 0) sq = fma(xt0, xt0, sq);
+    return xt0;
+}
+
+template <int G, int EPT>
+__global__ void __launch_bounds__(G, (G <= 128) ? 384 / G : 1) re_fast_kernel(const FastArgs fa)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ double red[2 * kMaxWarps * kRedK];
+    __shared__ int s_entity;
+    __shared__ unsigned s_flag;
+
+    constexpr int MT = kFastMT;
+    constexpr uint32_t W = G / 32;
+    const ReArgs &a = fa.a;
+    const FastLayout &L = fa.L;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int flip = 0;
+
+    for (;;) {
+        group_sync<G>();  // previous entity fully emitted before its memory is reused
+        if (tid == 0) { s_entity = atomicAdd(a.queue, 1); s_flag = 0; }
+        group_sync<G>();
+        const int e = s_entity;
+        if ((int64_t)e >= a.b.n_entities) break;
+
+        FastDims E;
+        E.hi = a.o.has_intercept ? 1u : 0u;
+        int st = 2;
+        {
+            const int64_t r0 = a.b.ent_rowptr[e], r1 = a.b.ent_rowptr[e + 1];
+            const int64_t q0 = a.b.rowptr[r0], q1 = a.b.rowptr[r1];
+            const int64_t n64 = r1 - r0, nnz64 = q1 - q0, p64 = a.b.theta_ptr[e + 1] - a.b.theta_ptr[e];
+            E.n = (uint32_t)n64; E.d = (uint32_t)p64 - E.hi;
+            const bool shape_ok = n64 >= 1 && p64 >= 1 && p64 >= (int64_t)E.hi && nnz64 >= 0 && nnz64 < (1ll << 30);
+            if (!shape_ok) {
+                if (tid == 0 && a.status) a.status[e] = GDMIX_ERR_TOO_LARGE;
+                continue;
+            }
+            if (n64 <= (int64_t)kFastMaxRows && (int64_t)E.d <= (int64_t)G * EPT && a.o.m <= MT)
+                st = fast_stage<G>(a, L, smem, r0, q0, E.n, E.d, &s_flag, E.nrslab, E.ncslab);
+        }
+        if (st == 1) {
+            if (tid == 0 && a.status) a.status[e] = GDMIX_ERR_INVALID;
+            continue;
+        }
+        if (st == 2) {
+            if (tid == 0) fa.defer_list[atomicAdd(fa.defer_count, 1)] = (int32_t)e;
+            continue;
+        }
+        double *dense = (double *)(smem + L.dense);
+        if (W == 1) prefetch_entity_l2(a.b, (int64_t)e + gridDim.x, lane);
+
+        // ---- solver state: this thread's slots of x, g, direction and of every history vector -----------
+        double x[EPT], g[EPT], gn[EPT], dd[EPT], Sh[MT][EPT], Yh[MT][EPT];
+        double x0 = 0.0, g0 = 0.0, gn0 = 0.0, d0 = 0.0, S0 = 0.0, Y0 = 0.0;  // S0/Y0: lane s of warp 0 = slot s
+        {
+            const int64_t t0 = a.b.theta_ptr[e];
+#pragma unroll
+            for (int k = 0; k < EPT; k++) {
+                const uint32_t c = tid + (uint32_t)k * G;
+                x[k] = (c < E.d && a.theta_in) ? a.theta_in[t0 + E.hi + c] : 0.0;
+                g[k] = 0.0; dd[k] = 0.0;
+#pragma unroll
+                for (int s = 0; s < MT; s++) { Sh[s][k] = 0.0; Yh[s][k] = 0.0; }
+            }
+            if (E.hi && a.theta_in) x0 = a.theta_in[t0];
+        }
+        Lbfgs lb;
+        lbfgs_reset<G, MT>(lb, dense);
+        double f, gd, gmax;
+        {
+            double sq;
+            const double xt0 = fast_trial<G, EPT>(fa, smem, E, 0.0, x, dd, x0, d0, sq);
+            group_sync<G>();
+            fast_evaluate<G, EPT>(fa, smem, E, xt0, sq, dd, d0, gn, gn0, red, flip, f, gd, gmax);
+        }
+#pragma unroll
+        for (int k = 0; k < EPT; k++) g[k] = gn[k];
+        g0 = gn0;
+        int nfev = 1, iter = 0, status = GDMIX_SOLVE_CONVERGED;
+
+        if (a.mode == kModeLossGrad) {
+            const int64_t t0 = a.b.theta_ptr[e];
+#pragma unroll
+            for (int k = 0; k < EPT; k++) {
+                const uint32_t c = tid + (uint32_t)k * G;
+                if (c < E.d) a.g_out[t0 + E.hi + c] = g[k];
+            }
+            if (tid == 0) {
+                if (E.hi) a.g_out[t0] = g0;
+                a.f_out[e] = f;
+            }
+            continue;
+        }
+
+        // ---- L-BFGS-B, unbounded (same driver as re_kernel.cuh) ------------------------------------------
+        const double epsmch = 2.220446049250313e-16;
+        const double ftol = 1e-3, gtol = 0.9, xtol = 0.1, stpmx = 1e10;
+        double dtd = 0.0;
+        bool done = gmax <= a.o.pgtol;
+        auto steepest = [&]() {
+            double v1[1] = {0.0};
+#pragma unroll
+            for (int k = 0; k < EPT; k++) {
+                dd[k] = -g[k];
+                v1[0] = fma(g[k], g[k], v1[0]);
+            }
+            d0 = -g0;
+            if (tid == 0) v1[0] = fma(g0, g0, v1[0]);
+            group_sum<G, 1>(v1, red, flip);
+            dtd = v1[0];
+            gd = -v1[0];
+        };
+        if (!done) steepest();
+
+        while (!done) {
+            // ---- line search (lnsrlb + dcsrch) along d.  The first trial step is almost always accepted, so
+            // the More'-Thuente state is only materialised (re-derived from the values at step 0, which is
+            // exactly what dcsrch's START call computes) once a trial has been evaluated.
+            double stp = (iter == 0) ? fmin(1.0 / sqrt(dtd), stpmx) : 1.0;
+            const double fold = f, gdold = gd, stp_first = stp;
+            int iback = 0, info = 0;
+            double gmax_t = gmax;
+            if (gd >= 0.0 || stp < 0.0 || stp > stpmx) info = -4;  // dcsrch's START checks
+            if (info == 0 && a.o.max_ls > 0) {
+                {
+                    double sq;
+                    const double xt0 = fast_trial<G, EPT>(fa, smem, E, stp, x, dd, x0, d0, sq);
+                    group_sync<G>();
+                    fast_evaluate<G, EPT>(fa, smem, E, xt0, sq, dd, d0, gn, gn0, red, flip, f, gd, gmax_t);
+                    nfev++;
+                }
+                LineSearch ls;
+                {
+                    double s1 = stp_first;
+                    dcsrch(s1, fold, gdold, ftol, gtol, xtol, 0.0, stpmx, LS_START, ls);
+                }
+                int ifun = 1;
+                for (;;) {
+                    const int task = dcsrch(stp, f, gd, ftol, gtol, xtol, 0.0, stpmx, LS_FG, ls);
+                    if (task == LS_CONV || task == LS_WARN) break;
+                    if (task == LS_ERROR) { info = -4; break; }
+                    ifun++; iback = ifun - 1;
+                    if (iback >= a.o.max_ls) break;
+                    double sq;
+                    const double xt0 = fast_trial<G, EPT>(fa, smem, E, stp, x, dd, x0, d0, sq);
+                    group_sync<G>();
+                    fast_evaluate<G, EPT>(fa, smem, E, xt0, sq, dd, d0, gn, gn0, red, flip, f, gd, gmax_t);
+                    nfev++;
+                }
+            } else if (info == 0) {
+                iback = a.o.max_ls;  // max_ls == 0: no trial allowed
+            }
+            if (info != 0 || iback >= a.o.max_ls) {
+                f = fold;  // x, g still hold the previous iterate
+                if (lb.col == 0) { status = GDMIX_SOLVE_ABNORMAL; iter++; break; }
+                group_sync<G>();
+                lbfgs_reset<G, MT>(lb, dense);
+#pragma unroll
+                for (int k = 0; k < EPT; k++) {
+#pragma unroll
+                    for (int s = 0; s < MT; s++) { Sh[s][k] = 0.0; Yh[s][k] = 0.0; }
+                }
+                S0 = 0.0; Y0 = 0.0;
+                steepest();
+                continue;
+            }
+            iter++;
+            // accept the trial point (the same fma as fast_trial gives the same bits); g holds the old gradient
+#pragma unroll
+            for (int k = 0; k < EPT; k++) x[k] = fma(stp, dd[k], x[k]);
+            x0 = fma(stp, d0, x0);
+            gmax = gmax_t;
+
+            if (iter >= a.o.max_iter || nfev > a.o.max_fun) { status = GDMIX_SOLVE_MAXITER; break; }
+            if (gmax <= a.o.pgtol) break;
+            if ((fold - f) <= epsmch * a.o.factr * max3(fabs(fold), fabs(f), 1.0)) break;
+
+            // ---- curvature pair (L-BFGS-B's skip rule) and the next direction ---------------------------
+            double dr, ddum;
+            if (stp == 1.0) { dr = gd - gdold; ddum = -gdold; }
+            else { dr = (gd - gdold) * stp; ddum = -gdold * stp; }
+            const int m = a.o.m;
+            const bool update = (m > 0) && !(dr <= epsmch * ddum);
+            int newslot = -1;
+            if (update) newslot = (lb.col < m) ? (lb.head + lb.col) % m : lb.head;
+            const uint32_t dotmask = update ? (lb.valid & ~(1u << newslot)) : lb.valid;
+            double *part = (double *)(smem + L.part);
+
+            // H1: inner products of every stored pair with the new gradient, y.y, y.g -- a dozen at a time
+            {
+                double v[12];
+#pragma unroll
+                for (int s = 0; s < 12; s++) v[s] = 0.0;
+#pragma unroll
+                for (int k = 0; k < EPT; k++) {
+                    const double gj = gn[k], yj = gj - g[k];
+                    v[MT] = fma(yj, yj, v[MT]);
+                    v[MT + 1] = fma(yj, gj, v[MT + 1]);
+#pragma unroll
+                    for (int s = 0; s < MT; s++) v[s] = fma(Sh[s][k], gj, v[s]);
+                }
+                warp_reduce12(v, lane);
+                if ((lane & 7u) == 0) {
+                    const uint32_t at = warp * kFastPartK + 6u * ((lane >> 4) & 1u) + 3u * ((lane >> 3) & 1u);
+                    part[at] = v[0]; part[at + 1] = v[1]; part[at + 2] = v[2];
+                }
+            }
+            {
+                double v[12];
+#pragma unroll
+                for (int s = 0; s < 12; s++) v[s] = 0.0;
+#pragma unroll
+                for (int k = 0; k < EPT; k++) {
+                    const double gj = gn[k];
+#pragma unroll
+                    for (int s = 0; s < MT; s++) v[s] = fma(Yh[s][k], gj, v[s]);
+                }
+                warp_reduce12(v, lane);
+                if ((lane & 7u) == 0) {
+                    const uint32_t at = warp * kFastPartK + 12u + 6u * ((lane >> 4) & 1u) + 3u * ((lane >> 3) & 1u);
+                    part[at] = v[0]; part[at + 1] = v[1]; part[at + 2] = v[2];
+                }
+            }
+            // the new pair takes its slot: s = stp d, y = g_new - g_old
+            if (update) {
+#pragma unroll
+                for (int k = 0; k < EPT; k++) {
+                    const double sj = stp * dd[k], yj = gn[k] - g[k];
+#pragma unroll
+                    for (int s = 0; s < MT; s++) {
+                        if (s == newslot) { Sh[s][k] = sj; Yh[s][k] = yj; }
+                    }
+                }
+            }
+            group_sync<G>();
+            if (warp == 0) {
+                double *tot = dense + DNF::tot;
+                const double y0 = gn0 - g0;
+                if (lane < 2 * MT + 2) {
+                    // part row: [S^T g (10) | y.y | y.g | Y^T g (10) | 0 0]  ->  tot: [S^T g | Y^T g | y.y | y.g]
+                    const uint32_t src = (lane < (uint32_t)MT) ? lane : (lane < 2u * MT) ? lane + 2u : lane - MT;
+                    double t = part[src];
+#pragma unroll
+                    for (uint32_t w2 = 1; w2 < W; w2++) t += part[w2 * kFastPartK + src];
+                    tot[lane] = t;
+                }
+                __syncwarp();
+                if (E.hi) {
+                    // the intercept's share: slot s lives in lane s (S0, Y0)
+                    const double y0s = __shfl_sync(kFull, Y0, (lane >= (uint32_t)MT && lane < 2u * MT) ? lane - MT : lane);
+                    if (lane < (uint32_t)MT) tot[lane] = fma(S0, gn0, tot[lane]);
+                    else if (lane < 2u * MT) tot[lane] = fma(y0s, gn0, tot[lane]);
+                    else if (lane == 2u * MT) tot[lane] = fma(y0, y0, tot[lane]);
+                    else if (lane == 2u * MT + 1u) tot[lane] = fma(y0, gn0, tot[lane]);
+                }
+                __syncwarp();
+                double uv, wv;
+                lbfgs_small_update<MT>(lb, update, newslot, dotmask, stp, dr, gd, dense, uv, wv);
+                if (update && (int)lane == newslot) { S0 = stp * d0; Y0 = y0; }
+                // intercept component of the next direction
+                const double theta_n = update ? tot[2 * MT] / dr : lb.theta;
+                const double gamma = 1.0 / theta_n;
+                double t = (lane < (uint32_t)MT) ? fma(gamma * wv, Y0, -uv * S0) : 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+                if (lane == 0) dense[DNF::count] = E.hi ? fma(-gamma, gn0, t) : 0.0;
+            } else if (warp == 1 && iter == 1) {
+                // idle while warp 0 works: pull the entity a grid-width ahead in the queue towards L2
+                prefetch_entity_l2(a.b, (int64_t)e + gridDim.x, lane);
+            }
+            group_sync<G>();
+            if (update) {
+                lb.theta = dense[DNF::tot + 2 * MT] / dr;
+                lb.valid |= (1u << newslot);
+                if (lb.col < m) lb.col++; else lb.head = (lb.head + 1) % m;
+            }
+            // H2: d = -gamma g - S u + gamma Y w
+            {
+                const double gamma = 1.0 / lb.theta;
+                double acc[EPT];
+#pragma unroll
+                for (int k = 0; k < EPT; k++) acc[k] = -gamma * gn[k];
+#pragma unroll
+                for (int s = 0; s < MT; s++) {
+                    const double cu = dense[DNF::cu + s], cw = gamma * dense[DNF::cw + s];
+#pragma unroll
+                    for (int k = 0; k < EPT; k++) {
+                        acc[k] = fma(-cu, Sh[s][k], acc[k]);
+                        acc[k] = fma(cw, Yh[s][k], acc[k]);
+                    }
+                }
+                d0 = dense[DNF::count];
+                double v2[2] = {0.0, 0.0};
+#pragma unroll
+                for (int k = 0; k < EPT; k++) {
+                    dd[k] = acc[k];
+                    g[k] = gn[k];
+                    v2[0] = fma(gn[k], acc[k], v2[0]);
+                    v2[1] = fma(acc[k], acc[k], v2[1]);
+                }
+                g0 = gn0;
+                if (tid == 0) { v2[0] = fma(g0, d0, v2[0]); v2[1] = fma(d0, d0, v2[1]); }
+                group_sum<G, 2>(v2, red, flip);
+                gd = v2[0];
+                dtd = v2[1];
+            }
+        }
+
+        // ---- emit ---------------------------------------------------------------------------------------
+        const int64_t t0 = a.b.theta_ptr[e];
+        const double thr = a.o.sparsity_threshold;
+#pragma unroll
+        for (int k = 0; k < EPT; k++) {
+            const uint32_t c = tid + (uint32_t)k * G;
+            if (c < E.d) a.theta_out[t0 + E.hi + c] = (thr > 0.0 && fabs(x[k]) <= thr) ? 0.0 : x[k];
+        }
+        if (tid == 0) {
+            if (E.hi) a.theta_out[t0] = (thr > 0.0 && fabs(x0) <= thr) ? 0.0 : x0;
+            if (a.f_out) a.f_out[e] = f;
+            if (a.nit) a.nit[e] = iter;
+            if (a.nfev) a.nfev[e] = nfev;
+            if (a.status) a.status[e] = status;
+        }
+        if (a.var_out && a.o.variance_mode == GDMIX_VARIANCE_SIMPLE) {
+            // var_j = 1 / (sum_i x_ij^2 rho_i (1-rho_i) w_i + l2 [j regularised] + 1e-12)
+            // (binary_logistic_regression.py:171-177), at the un-thresholded optimum
+            group_sync<G>();
+            double *xt = (double *)(smem + L.xt), *rr = (double *)(smem + L.r);
+#pragma unroll
+            for (int k = 0; k < EPT; k++) {
+                const uint32_t c = tid + (uint32_t)k * G;
+                if (c < E.d) xt[c] = x[k];
+            }
+            group_sync<G>();
+            const uint32_t *rbase = (const uint32_t *)(smem + L.rbase), *cbase = (const uint32_t *)(smem + L.cbase);
+            double dsum[1] = {0.0};
+            for (uint32_t b = warp; b < E.nrslab; b += W) {
+                const uint32_t sb = rbase[b];
+                double z = sell_dot((const float4 *)(smem + L.sell_val) + sb * kStepQuads + lane,
+                                    (const uint2 *)(smem + L.sell_idx) + sb * kStepQuads + lane, rbase[b + 1] - sb,
+                                    (const char *)xt);
+                const uint32_t sp = b * 32u + lane;
+                if (sp < E.n) {
+                    z = (z + (E.hi ? x0 : 0.0)) + (double)((const float *)(smem + L.soff))[sp];
+                    const double rho = 1.0 / (1.0 + exp(-z));
+                    const double di = rho * (1.0 - rho) * (double)((const float *)(smem + L.sw))[sp];
+                    rr[((const uint16_t *)(smem + L.rowperm))[sp]] = di;
+                    dsum[0] += di;
+                }
+            }
+            group_sum<G, 1>(dsum, red, flip);
+            if (G == 32) __syncwarp();
+            for (uint32_t b = warp; b < E.ncslab; b += W) {
+                const uint32_t sb = cbase[b], ns = cbase[b + 1] - sb;
+                const float4 *pv = (const float4 *)(smem + L.sell_val) + sb * kStepQuads + lane;
+                const uint2 *pi = (const uint2 *)(smem + L.sell_idx) + sb * kStepQuads + lane;
+                const char *rv = (const char *)rr;
+                double h = 0.0;
+                for (uint32_t k = 0; k < ns; k++) {
+                    const float4 va = pv[k * kStepQuads];
+                    const uint2 ca = pi[k * kStepQuads];
+                    const double a0 = (double)va.x, a1 = (double)va.y, a2 = (double)va.z, a3 = (double)va.w;
+                    h = fma(a0, a0 * *(const double *)(rv + (ca.x & 0xffffu)), h);
+                    h = fma(a1, a1 * *(const double *)(rv + (ca.x >> 16)), h);
+                    h = fma(a2, a2 * *(const double *)(rv + (ca.y & 0xffffu)), h);
+                    h = fma(a3, a3 * *(const double *)(rv + (ca.y >> 16)), h);
+                }
+                const uint32_t sp = b * 32u + lane;
+                if (sp < E.d)
+                    a.var_out[t0 + E.hi + ((const uint16_t *)(smem + L.colperm))[sp]] = 1.0 / ((h + a.o.l2) + 1.0e-12);
+            }
+            if (E.hi && tid == 0)
+                a.var_out[t0] = 1.0 / ((dsum[0] + (a.o.regularize_bias ? a.o.l2 : 0.0)) + 1.0e-12);
+        }
+    }
+}
+
+}  // namespace gdmix

@@ -41,7 +41,11 @@ __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
         group_sync<G>();  // previous entity fully emitted before its memory is reused
         if (tid == 0) { s_entity = atomicAdd(a.queue, 1); s_bad = 0; }
         group_sync<G>();
-        const int64_t e = s_entity;
+        int64_t e = s_entity;
+        if (a.todo) {
+            if (e >= (int64_t)*a.todo_count) break;
+            e = a.todo[e];
+        }
         if (e >= a.b.n_entities) break;
 
         const int64_t r0 = a.b.ent_rowptr[e], r1 = a.b.ent_rowptr[e + 1];

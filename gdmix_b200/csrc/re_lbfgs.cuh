@@ -26,6 +26,82 @@ __device__ __forceinline__ void lbfgs_reset(Lbfgs &L, double *dense)
     for (int k = threadIdx.x; k < Dense<MT>::tot; k += G) dense[k] = 0.0;
 }
 
+// The warp-sized part of the update, run by ONE full warp after dense[tot..] holds the 2*MT+2 totals
+// [S^T g | Y^T g | y.y | y.g]: appends / replaces the pair, refreshes R^-1, Y^T Y, D and leaves the
+// coefficient vectors u (dense[cu..]) and w (dense[cw..]) of H g = gamma g + S u - gamma Y w.  Lane i < MT
+// returns its u_i, w_i (0 for empty slots).
+template <int MT>
+__device__ __forceinline__ void lbfgs_small_update(const Lbfgs &L, const bool update, const int newslot,
+                                                   const uint32_t dotmask, const double stp, const double dr,
+                                                   const double gd_new, double *dense, double &uv_out,
+                                                   double &wv_out)
+{
+    using DN = Dense<MT>;
+    const uint32_t lane = threadIdx.x & 31;
+    double *tot = dense + DN::tot;
+    const int i = lane;
+    const bool in = i < MT;
+    const bool old_i = in && ((dotmask >> i) & 1u);
+    double p1i = old_i ? tot[i] : 0.0, p2i = old_i ? tot[MT + i] : 0.0;
+    const double yyt = tot[2 * MT], ygt = tot[2 * MT + 1];
+    double *Rinv = dense + DN::rinv, *YY = dense + DN::yy, *Dg = dense + DN::d;
+    double *p1old = dense + DN::p1old, *p2old = dense + DN::p2old;
+    double *ta = dense + DN::ta, *tb = dense + DN::tb;
+    double theta = L.theta;
+    if (update) {
+        theta = yyt / dr;
+        const double rc = old_i ? p1i - p1old[i] : 0.0;  // s_i . y_new
+        const double yc = old_i ? p2i - p2old[i] : 0.0;  // y_i . y_new
+        if (in) ta[i] = rc;
+        __syncwarp();
+        double acc = 0.0;
+        if (in) {
+#pragma unroll
+            for (int j = 0; j < MT; j++) acc = fma(Rinv[i * MT + j], ta[j], acc);
+        }
+        __syncwarp();
+        if (in) {
+            Rinv[i * MT + newslot] = old_i ? -acc / dr : 0.0;
+            YY[i * MT + newslot] = yc;
+        }
+        __syncwarp();
+        if (in) {
+            Rinv[newslot * MT + i] = (i == newslot) ? 1.0 / dr : 0.0;
+            YY[newslot * MT + i] = (i == newslot) ? yyt : yc;
+        }
+        if (i == newslot) { Dg[i] = dr; p1i = stp * gd_new; p2i = ygt; }
+        __syncwarp();
+    }
+    const uint32_t valid = update ? (L.valid | (1u << newslot)) : L.valid;
+    const bool val_i = in && ((valid >> i) & 1u);
+    const double gamma = 1.0 / theta;
+    if (in) { p1old[i] = p1i; p2old[i] = p2i; ta[i] = val_i ? p1i : 0.0; }
+    __syncwarp();
+    double wv = 0.0;
+    if (in) {
+#pragma unroll
+        for (int j = 0; j < MT; j++) wv = fma(Rinv[i * MT + j], ta[j], wv);
+    }
+    if (in) tb[i] = wv;
+    __syncwarp();
+    double yw = 0.0;
+    if (in) {
+#pragma unroll
+        for (int j = 0; j < MT; j++) yw = fma(YY[i * MT + j], tb[j], yw);
+    }
+    const double tv = val_i ? fma(Dg[i], wv, gamma * (yw - p2i)) : 0.0;
+    __syncwarp();
+    if (in) ta[i] = tv;
+    __syncwarp();
+    double uv = 0.0;
+    if (in) {
+#pragma unroll
+        for (int j = 0; j < MT; j++) uv = fma(Rinv[j * MT + i], ta[j], uv);
+    }
+    if (in) { dense[DN::cu + i] = uv; dense[DN::cw + i] = wv; }
+    uv_out = uv; wv_out = wv;
+}
+
 // After an accepted step: g = new gradient, gold = previous gradient, dv = the direction just used.
 // Optionally stores the new pair (s = stp*dv, y = g - gold), then writes the next direction into dv and
 // returns gd = g.dv and dtd = dv.dv (identical in all threads).
@@ -98,66 +174,8 @@ __device__ __forceinline__ void lbfgs_direction(Lbfgs &L, const int m, const boo
             tot[k] = t;
         }
         __syncwarp();
-        const int i = lane;
-        const bool in = i < MT;
-        const bool old_i = in && ((dotmask >> i) & 1u);
-        double p1i = old_i ? tot[i] : 0.0, p2i = old_i ? tot[MT + i] : 0.0;
-        const double yyt = tot[2 * MT], ygt = tot[2 * MT + 1];
-        double *Rinv = dense + DN::rinv, *YY = dense + DN::yy, *Dg = dense + DN::d;
-        double *p1old = dense + DN::p1old, *p2old = dense + DN::p2old;
-        double *ta = dense + DN::ta, *tb = dense + DN::tb;
-        double theta = L.theta;
-        if (update) {
-            theta = yyt / dr;
-            const double rc = old_i ? p1i - p1old[i] : 0.0;  // s_i . y_new
-            const double yc = old_i ? p2i - p2old[i] : 0.0;  // y_i . y_new
-            if (in) ta[i] = rc;
-            __syncwarp();
-            double acc = 0.0;
-            if (in) {
-#pragma unroll
-                for (int j = 0; j < MT; j++) acc = fma(Rinv[i * MT + j], ta[j], acc);
-            }
-            __syncwarp();
-            if (in) {
-                Rinv[i * MT + newslot] = old_i ? -acc / dr : 0.0;
-                YY[i * MT + newslot] = yc;
-            }
-            __syncwarp();
-            if (in) {
-                Rinv[newslot * MT + i] = (i == newslot) ? 1.0 / dr : 0.0;
-                YY[newslot * MT + i] = (i == newslot) ? yyt : yc;
-            }
-            if (i == newslot) { Dg[i] = dr; p1i = stp * gd_new; p2i = ygt; }
-            __syncwarp();
-        }
-        const uint32_t valid = update ? (L.valid | (1u << newslot)) : L.valid;
-        const bool val_i = in && ((valid >> i) & 1u);
-        const double gamma = 1.0 / theta;
-        if (in) { p1old[i] = p1i; p2old[i] = p2i; ta[i] = val_i ? p1i : 0.0; }
-        __syncwarp();
-        double wv = 0.0;
-        if (in) {
-#pragma unroll
-            for (int j = 0; j < MT; j++) wv = fma(Rinv[i * MT + j], ta[j], wv);
-        }
-        if (in) tb[i] = wv;
-        __syncwarp();
-        double yw = 0.0;
-        if (in) {
-#pragma unroll
-            for (int j = 0; j < MT; j++) yw = fma(YY[i * MT + j], tb[j], yw);
-        }
-        const double tv = val_i ? fma(Dg[i], wv, gamma * (yw - p2i)) : 0.0;
-        __syncwarp();
-        if (in) ta[i] = tv;
-        __syncwarp();
-        double uv = 0.0;
-        if (in) {
-#pragma unroll
-            for (int j = 0; j < MT; j++) uv = fma(Rinv[j * MT + i], ta[j], uv);
-        }
-        if (in) { dense[DN::cu + i] = uv; dense[DN::cw + i] = wv; }
+        double uv, wv;
+        lbfgs_small_update<MT>(L, update, newslot, dotmask, stp, dr, gd_new, dense, uv, wv);
     }
     group_sync<G>();
     if (update) {

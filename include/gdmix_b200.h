@@ -207,6 +207,13 @@ GDMIX_API int gdmix_lbfgs_iterate(gdmix_lbfgs *h, double *x, double f, const dou
 GDMIX_API int gdmix_lbfgs_info(const gdmix_lbfgs *h, int32_t *nit, int32_t *nfev, int32_t *status, double *f);
 GDMIX_API void gdmix_lbfgs_destroy(gdmix_lbfgs *h);
 
+/* Launch plan of this thread's most recent gdmix_re_fit / gdmix_re_loss_grad (diagnostics, tests, bench):
+ * out8 = { fast kernel used, threads per entity, features per thread (fast) , CTAs per SM,
+ *          sliced-ELL capacity in steps (fast), dynamic shared memory per CTA, grid, history in global arena }.
+ * After a fast-path call the number of entities it deferred to the general kernel is the third int32 of the
+ * workspace. */
+GDMIX_API void gdmix_re_last_plan(int32_t *out8);
+
 /* Number of kernel launches issued by this library since load (for bench accounting). */
 GDMIX_API int64_t gdmix_launch_count(void);
 

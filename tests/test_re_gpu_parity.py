@@ -18,6 +18,17 @@ from tests.golden_util import is_pinned, load_re  # noqa: E402
 REL_TOL = 1e-5  # north_star tolerance
 
 
+@pytest.fixture(autouse=True, params=["auto", "generic"])
+def re_path(request, monkeypatch):
+    """Every test runs twice: through the planner's choice (the sliced-ELL fast kernel when the batch
+    qualifies) and through the general kernel alone."""
+    if request.param == "generic":
+        monkeypatch.setenv("GDMIX_RE_PATH", "generic")
+    else:
+        monkeypatch.delenv("GDMIX_RE_PATH", raising=False)
+    return request.param
+
+
 def _oracle_opts(o):
     return O.Opts(o.l2, o.regularize_bias, o.has_intercept, o.m, o.max_iter, o.max_ls, o.max_fun, o.factr, o.pgtol)
 
@@ -123,10 +134,11 @@ def test_synthetic_batch_matches_oracle(shape):
     np.testing.assert_allclose(out["f"], f_o, rtol=1e-11)
 
 
-def test_device_api_matches_host_api():
+def test_device_api_matches_host_api(re_path):
     hb = make_batch(300, 64, 64, 16, seed=3)
     opts = capi.make_opts(l2=0.5)
     host = capi.re_fit_host(hb, opts)
+    assert capi.last_plan()["fast"] == (1 if re_path == "auto" else 0)
     dev = capi.re_fit_device(capi.DeviceBatch(hb), opts)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(dev["theta"].cpu().numpy(), host["theta"])
@@ -198,3 +210,32 @@ def test_history_sizes_match_oracle(m):
     rel = _rel_per_entity(out["theta"], th_o, hb.theta_ptr)
     assert rel.max() <= REL_TOL, rel.max()
     assert (out["nit"] == nit_o).all() and (out["nfev"] == nfev_o).all()
+
+
+def test_deferred_entities_take_the_general_kernel(monkeypatch, re_path):
+    """Entities whose sliced form does not fit the fast kernel's shared memory are drained by the general
+    kernel from the deferral list: same answers either way."""
+    if re_path == "generic":
+        pytest.skip("fast path only")
+    hb = make_batch(300, 64, 64, 16, seed=31, ragged=True)
+    opts = capi.make_opts(l2=1.0)
+    ref = capi.re_fit_host(hb, opts)
+    assert capi.last_plan()["fast"] == 1
+    db = capi.DeviceBatch(hb)
+    monkeypatch.setenv("GDMIX_FAST_CAP_STEPS", "20")   # mean entity needs ~24 steps: most are deferred
+    dev = capi.re_fit_device(db, opts)
+    torch.cuda.synchronize()
+    deferred = int(dev["workspace"][:12].view(torch.int32)[2].item())
+    print("deferred", deferred, "of", hb.n_entities)
+    assert 0 < deferred < hb.n_entities
+    mixed = capi.re_fit_host(hb, opts)
+    monkeypatch.setenv("GDMIX_FAST_CAP_STEPS", "1")    # everything deferred
+    alld = capi.re_fit_host(hb, opts)
+    monkeypatch.setenv("GDMIX_RE_PATH", "generic")
+    gen = capi.re_fit_host(hb, opts)
+    np.testing.assert_array_equal(alld["theta"], gen["theta"])
+    for k in ("nit", "nfev", "status"):
+        np.testing.assert_array_equal(mixed[k], ref[k])
+        np.testing.assert_array_equal(alld[k], ref[k])
+    rel = _rel_per_entity(mixed["theta"], ref["theta"], hb.theta_ptr)
+    assert rel.max() <= 1e-9, rel.max()
