@@ -86,7 +86,7 @@ struct RePlan {
 };
 
 constexpr size_t kQueueBytes = 256;
-constexpr uint32_t kStaticSmem = 2 * gdmix::kMaxWarps * gdmix::kRedK * 8 + 64;
+constexpr uint32_t kStaticSmem = 1024;  // upper bound on the kernels' static shared memory
 
 int choose_group(const gdmix_re_batch *b, const gdmix_lr_opts *o)
 {
@@ -157,7 +157,10 @@ int plan_fast(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo 
     const int regs_alloc = (regs + 7) & ~7;
     const int k_hw = std::max(1, std::min({65536 / (G * regs_alloc), 2048 / G, 32}));
     const uint32_t W = (uint32_t)G / 32;
-    const uint32_t fixed = gdmix::fast_fixed_bytes(N, D, W, nullptr);
+    gdmix::FastLayout fl;
+    const uint32_t fixed = gdmix::fast_fixed_bytes(N, D, W, &fl);
+    // the sliced index stream holds 16-bit absolute shared addresses into xt[] and r[]
+    if (kStaticSmem + fl.r + 8u * N > 65536u) return GDMIX_OK;
     const uint32_t nrslab = (N + 31) / 32, ncslab = (D + 31) / 32;
     const uint32_t ar = (uint32_t)((b->max_nnz + (int64_t)N - 1) / N), ac = D ? (uint32_t)((b->max_nnz + (int64_t)D - 1) / D) : 0;
     const uint32_t est = nrslab * ((ar + 3) / 4 + 1) + ncslab * ((ac + 3) / 4 + 1);

@@ -41,7 +41,7 @@ constexpr uint32_t kFastDense = DNF::count + 2;   // + direction / trial value o
 
 // Byte offsets of one CTA's dynamic shared memory.  N = max rows, D = max local features of the batch.
 struct FastLayout {
-    uint32_t xt, gnew, r, dense, part;                       // solve block
+    uint32_t xt, gnew, r, xcur, gold, dense, icept, part;    // solve block
     uint32_t rowoff, ccnt, keys, rowpos, colpos, seglen;     // staging scratch, aliases the solve block
     uint32_t rowperm, colperm, sy, sw, soff, rbase, cbase;   // live through the solve
     uint32_t sell_val, sell_idx;
@@ -56,8 +56,11 @@ __host__ __device__ inline uint32_t fast_fixed_bytes(uint32_t N, uint32_t D, uin
     L.xt = o; o += align16(8 * D);
     L.gnew = o; o += align16(8 * D);
     L.r = o; o += align16(8 * N);
+    L.xcur = o; o += align16(8 * D);       // current iterate (features)
+    L.gold = o; o += align16(8 * D);       // its gradient
     L.dense = o; o += align16(8 * kFastDense);
-    L.part = o; o += align16(8 * kMaxWarps * kFastPartK);
+    L.icept = o; o += align16(8 * 2 * kFastMT);   // intercept components of the stored pairs: S0[m], Y0[m]
+    L.part = o; o += align16(8 * W * kFastPartK);
     const uint32_t solve_end = o;
     o = 0;
     L.rowoff = o; o += align16(4 * (N + 1));
@@ -222,19 +225,28 @@ __device__ __forceinline__ void prefetch_entity_l2(const gdmix_re_batch &b, cons
     if (b.weight) hint((const char *)(b.weight + r0), (const char *)(b.weight + r1));
 }
 
-// One lane's share of a slab: sum over `nsteps` quads of val * vec[offset].  val / idx point at this lane's
-// quad of the slab's first step; vec is the gathered fp64 vector (byte offsets).
-__device__ __forceinline__ double sell_dot(const float4 *pv, const uint2 *pi, const uint32_t nsteps, const char *vec)
+__device__ __forceinline__ double lds_f64(const uint32_t shared_addr)
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(shared_addr));
+    return v;
+}
+
+// One lane's share of a slab: sum over `nsteps` quads of val * vec[...].  pv / pi point at this lane's quad of
+// the slab's first step.  The index stream holds ABSOLUTE 16-bit shared-memory addresses of the gathered fp64
+// entries (the gathered vectors sit in the first 64 KB of the CTA's window), so a gather is one LDS with no
+// address arithmetic.
+__device__ __forceinline__ double sell_dot(const float4 *pv, const uint2 *pi, const uint32_t nsteps)
 {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     uint32_t k = 0;
     for (; k + 2 <= nsteps; k += 2) {
         const float4 va = pv[k * kStepQuads], vb = pv[(k + 1) * kStepQuads];
         const uint2 ca = pi[k * kStepQuads], cb = pi[(k + 1) * kStepQuads];
-        const double x0 = *(const double *)(vec + (ca.x & 0xffffu)), x1 = *(const double *)(vec + (ca.x >> 16));
-        const double x2 = *(const double *)(vec + (ca.y & 0xffffu)), x3 = *(const double *)(vec + (ca.y >> 16));
-        const double x4 = *(const double *)(vec + (cb.x & 0xffffu)), x5 = *(const double *)(vec + (cb.x >> 16));
-        const double x6 = *(const double *)(vec + (cb.y & 0xffffu)), x7 = *(const double *)(vec + (cb.y >> 16));
+        const double x0 = lds_f64(ca.x & 0xffffu), x1 = lds_f64(ca.x >> 16);
+        const double x2 = lds_f64(ca.y & 0xffffu), x3 = lds_f64(ca.y >> 16);
+        const double x4 = lds_f64(cb.x & 0xffffu), x5 = lds_f64(cb.x >> 16);
+        const double x6 = lds_f64(cb.y & 0xffffu), x7 = lds_f64(cb.y >> 16);
         s0 = fma((double)va.x, x0, s0);
         s1 = fma((double)va.y, x1, s1);
         s2 = fma((double)va.z, x2, s2);
@@ -247,8 +259,8 @@ __device__ __forceinline__ double sell_dot(const float4 *pv, const uint2 *pi, co
     if (k < nsteps) {
         const float4 va = pv[k * kStepQuads];
         const uint2 ca = pi[k * kStepQuads];
-        const double x0 = *(const double *)(vec + (ca.x & 0xffffu)), x1 = *(const double *)(vec + (ca.x >> 16));
-        const double x2 = *(const double *)(vec + (ca.y & 0xffffu)), x3 = *(const double *)(vec + (ca.y >> 16));
+        const double x0 = lds_f64(ca.x & 0xffffu), x1 = lds_f64(ca.x >> 16);
+        const double x2 = lds_f64(ca.y & 0xffffu), x3 = lds_f64(ca.y >> 16);
         s0 = fma((double)va.x, x0, s0);
         s1 = fma((double)va.y, x1, s1);
         s2 = fma((double)va.z, x2, s2);
@@ -260,7 +272,7 @@ __device__ __forceinline__ double sell_dot(const float4 *pv, const uint2 *pi, co
 // The staged entity as the passes see it: five small integers; every array is addressed as smem + an offset
 // of the launch-constant FastLayout (kernel parameter space), so no pointer stays live across the solve.
 struct FastDims {
-    uint32_t n, d, hi, nrslab, ncslab;
+    uint32_t n, d, hi;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -269,7 +281,7 @@ struct FastDims {
 template <int G>
 __device__ __forceinline__ int fast_stage(const ReArgs &a, const FastLayout &L, unsigned char *smem,
                                           const int64_t r0, const int64_t q0, const uint32_t n, const uint32_t d,
-                                          unsigned *s_flag, uint32_t &nrslab, uint32_t &ncslab)
+                                          unsigned *s_flag)
 {
     constexpr uint32_t W = G / 32;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -282,6 +294,9 @@ __device__ __forceinline__ int fast_stage(const ReArgs &a, const FastLayout &L, 
     float *sval = (float *)(smem + L.sell_val);
     uint16_t *sidx = (uint16_t *)(smem + L.sell_idx);
     float *sy = (float *)(smem + L.sy), *sw = (float *)(smem + L.sw), *soff = (float *)(smem + L.soff);
+    // 16-bit absolute shared addresses of xt[0] and r[0] (the planner keeps both vectors below 64 KB)
+    const uint32_t xt_abs = (uint32_t)__cvta_generic_to_shared(smem + L.xt);
+    const uint32_t r_abs = (uint32_t)__cvta_generic_to_shared(smem + L.r);
 
     for (uint32_t i = tid; i <= n; i += G) rowoff[i] = (uint32_t)(a.b.rowptr[r0 + i] - q0);
     for (uint32_t k = tid; k < W * d; k += G) ccnt[k] = 0;
@@ -289,7 +304,7 @@ __device__ __forceinline__ int fast_stage(const ReArgs &a, const FastLayout &L, 
 
     // ---- rows: sort, slab bases, zero fill, fill (coalesced: a warp streams one row at a time) -------------
     slab_sort<G>([&](uint32_t i) { return rowoff[i + 1] - rowoff[i]; }, n, rowpos, rowperm, rbase, 0u, keys);
-    nrslab = (n + 31u) >> 5;
+    const uint32_t nrslab = (n + 31u) >> 5;
     const uint32_t total_r = rbase[nrslab];
     if (total_r > L.cap_steps) return 2;
     {
@@ -298,7 +313,8 @@ __device__ __forceinline__ int fast_stage(const ReArgs &a, const FastLayout &L, 
         for (uint32_t k = tid; k < nv; k += G) zv[k] = make_uint4(0, 0, 0, 0);
         uint4 *zi = (uint4 *)sidx;
         const uint32_t ni = (total_r * kStepElems * 2 + 15) / 16;
-        for (uint32_t k = tid; k < ni; k += G) zi[k] = make_uint4(0, 0, 0, 0);
+        const uint32_t fill = xt_abs * 0x10001u;  // padding slots gather xt[0] (times a zero value)
+        for (uint32_t k = tid; k < ni; k += G) zi[k] = make_uint4(fill, fill, fill, fill);
     }
     for (uint32_t i = tid; i < n; i += G) {
         const uint32_t sp = rowpos[i];
@@ -314,7 +330,7 @@ __device__ __forceinline__ int fast_stage(const ReArgs &a, const FastLayout &L, 
         if (c < d) {
             const uint32_t dst = at + (j >> 2) * kStepElems + (j & 3u);
             sval[dst] = v;
-            sidx[dst] = (uint16_t)(c * 8u);
+            sidx[dst] = (uint16_t)(xt_abs + c * 8u);
             atomicAdd(&ccnt[warp * d + c], 1u);
         } else {
             bad = 1;
@@ -365,7 +381,7 @@ __device__ __forceinline__ int fast_stage(const ReArgs &a, const FastLayout &L, 
     }
     group_sync<G>();
     slab_sort<G>([&](uint32_t c) { return (uint32_t)seglen[c]; }, d, colpos, colperm, cbase, total_r, keys);
-    ncslab = (d + 31u) >> 5;
+    const uint32_t ncslab = (d + 31u) >> 5;
     const uint32_t total = cbase[ncslab];
     if (total > L.cap_steps) return 2;
     {
@@ -375,7 +391,8 @@ __device__ __forceinline__ int fast_stage(const ReArgs &a, const FastLayout &L, 
         // u16 region: kStepElems * 2 = 264 B per step, 8-byte granular
         uint2 *zi = (uint2 *)(sidx + (size_t)total_r * kStepElems);
         const uint32_t ni = (total - total_r) * (kStepElems / 4);
-        for (uint32_t k = tid; k < ni; k += G) zi[k] = make_uint2(0, 0);
+        const uint32_t fill = r_abs * 0x10001u;  // padding slots gather r[0] (times a zero value)
+        for (uint32_t k = tid; k < ni; k += G) zi[k] = make_uint2(fill, fill);
     }
     group_sync<G>();
     // second sweep out of the sliced rows just built (no global traffic): scatter every non-zero to its
@@ -388,7 +405,7 @@ __device__ __forceinline__ int fast_stage(const ReArgs &a, const FastLayout &L, 
             const uint32_t j = j0 + lane;
             const bool act = j < len;
             const uint32_t src = rat + (j >> 2) * kStepElems + (j & 3u);
-            const uint32_t c = act ? ((uint32_t)sidx[src] >> 3) : (0x10000u + lane);
+            const uint32_t c = act ? (((uint32_t)sidx[src] - xt_abs) >> 3) : (0x10000u + lane);
             const float v = act ? sval[src] : 0.0f;
             // columns strictly ascending inside the chunk (the usual case) => no column occurs twice
             const uint32_t prev = __shfl_up_sync(kFull, c, 1);
@@ -402,7 +419,7 @@ __device__ __forceinline__ int fast_stage(const ReArgs &a, const FastLayout &L, 
                 const uint32_t e = cur + rank, sp = colpos[c];
                 const uint32_t dst = (cbase[sp >> 5] + (e >> 2)) * kStepElems + (sp & 31u) * 4u + (e & 3u);
                 sval[dst] = v;
-                sidx[dst] = (uint16_t)(i * 8u);
+                sidx[dst] = (uint16_t)(r_abs + i * 8u);
             }
             __syncwarp();
             if (act && rank == (uint32_t)__popc(grp) - 1u) ccnt[warp * d + c] = cur + rank + 1u;
@@ -414,109 +431,67 @@ __device__ __forceinline__ int fast_stage(const ReArgs &a, const FastLayout &L, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// f, g at the trial point held in smem xt (features) / xt0 (intercept).  sq_part = this thread's share of
-// sum xt_reg^2.  On return gn[] holds this thread's slots of the new gradient, gn0 the intercept's, and every
-// thread has identical f, gd (= g.d) and gmax (= max|g|).
+// Cold half of the line search.  The first trial step is accepted almost always; only when it is not does the
+// More'-Thuente state exist at all, and then it lives in shared memory (two slots used alternately: every
+// thread computes and writes the same values into the slot nobody is reading).
 // ---------------------------------------------------------------------------------------------------------
-template <int G, int EPT>
-__device__ __forceinline__ void fast_evaluate(const FastArgs &fa, unsigned char *smem, const FastDims &E,
-                                              const double xt0, const double sq_part, const double (&dd)[EPT],
-                                              const double d0, double (&gn)[EPT], double &gn0, double *red,
-                                              int &flip, double &f, double &gd, double &gmax)
+struct LsOut {
+    double stp;
+    int task;
+};
+
+__device__ __noinline__ LsOut ls_continue(LineSearch *slots, const int read_slot, const bool first,
+                                          const double stp_first, const double fold, const double gdold,
+                                          const double stp_in, const double f, const double g)
 {
-    constexpr uint32_t W = G / 32;
-    const FastLayout &L = fa.L;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double l2 = fa.a.o.l2;
-    const double inv_n = 1.0 / (double)E.n;
-    double part[3] = {0.0, 0.0, sq_part};
-    {
-        const uint32_t *rbase = (const uint32_t *)(smem + L.rbase);
-        const char *xt = (const char *)(smem + L.xt);
-        for (uint32_t b = warp; b < E.nrslab; b += W) {
-            const uint32_t st = rbase[b];
-            double z = sell_dot((const float4 *)(smem + L.sell_val) + st * kStepQuads + lane,
-                                (const uint2 *)(smem + L.sell_idx) + st * kStepQuads + lane, rbase[b + 1] - st, xt);
-            const uint32_t sp = b * 32u + lane;
-            if (sp < E.n) {
-                z = (z + (E.hi ? xt0 : 0.0)) + (double)((const float *)(smem + L.soff))[sp];
-                const double yi = (double)((const float *)(smem + L.sy))[sp];
-                const double wi = (double)((const float *)(smem + L.sw))[sp];
-                const double e = exp(-fabs(z));
-                const double ce = fmax(z, 0.0) - z * yi + log(1.0 + e);
-                part[0] = fma(wi, ce, part[0]);
-                const double inv = 1.0 / (1.0 + e);
-                const double sig = (z >= 0.0) ? inv : e * inv;
-                const double ri = wi * (sig - yi);
-                ((double *)(smem + L.r))[((const uint16_t *)(smem + L.rowperm))[sp]] = ri;
-                part[1] += ri;
-            }
-        }
+    const double ftol = 1e-3, gtol = 0.9, xtol = 0.1, stpmx = 1e10;
+    LineSearch S;
+    if (first) {
+        double s1 = stp_first;  // dcsrch's START call: derives the state from the values at step 0
+        dcsrch(s1, fold, gdold, ftol, gtol, xtol, 0.0, stpmx, LS_START, S);
+    } else {
+        S = slots[read_slot];
     }
-    group_sum<G, 3>(part, red, flip);  // its barrier also publishes r[]
-    if (G == 32) __syncwarp();
-    f = (part[0] + 0.5 * l2 * part[2]) * inv_n;
-    {
-        const uint32_t *cbase = (const uint32_t *)(smem + L.cbase);
-        const char *rv = (const char *)(smem + L.r);
-        for (uint32_t b = warp; b < E.ncslab; b += W) {
-            const uint32_t st = cbase[b];
-            const double acc = sell_dot((const float4 *)(smem + L.sell_val) + st * kStepQuads + lane,
-                                        (const uint2 *)(smem + L.sell_idx) + st * kStepQuads + lane,
-                                        cbase[b + 1] - st, rv);
-            const uint32_t sp = b * 32u + lane;
-            if (sp < E.d) {
-                const uint32_t c = ((const uint16_t *)(smem + L.colperm))[sp];
-                ((double *)(smem + L.gnew))[c] = (acc + l2 * ((const double *)(smem + L.xt))[c]) * inv_n;
-            }
-        }
-    }
-    group_sync<G>();
-    double gdp = 0.0, gmp = 0.0;
-#pragma unroll
-    for (int e = 0; e < EPT; e++) {
-        const uint32_t c = tid + (uint32_t)e * G;
-        const double ge = (c < E.d) ? ((const double *)(smem + L.gnew))[c] : 0.0;
-        gn[e] = ge;
-        gdp = fma(ge, dd[e], gdp);
-        gmp = fmax(gmp, fabs(ge));
-    }
-    gn0 = 0.0;
-    if (E.hi) {
-        gn0 = (part[1] + (fa.a.o.regularize_bias ? l2 * xt0 : 0.0)) * inv_n;
-        if (tid == 0) gdp = fma(gn0, d0, gdp);
-        gmp = fmax(gmp, fabs(gn0));
-    }
-    group_sum_max<G>(gdp, gmp, red, flip);
-    gd = gdp;
-    gmax = gmp;
+    LsOut o;
+    o.stp = stp_in;
+    o.task = dcsrch(o.stp, f, g, ftol, gtol, xtol, 0.0, stpmx, LS_FG, S);
+    slots[read_slot ^ 1] = S;
+    return o;
 }
 
-// Writes the trial point x + stp d into smem xt; returns the intercept's trial value and this thread's share
-// of sum xt_reg^2.
+// Writes the features of the trial point x + stp d into smem xt (each thread its own slots).
 template <int G, int EPT>
-__device__ __forceinline__ double fast_trial(const FastArgs &fa, unsigned char *smem, const FastDims &E,
-                                             const double stp, const double (&x)[EPT], const double (&dd)[EPT],
-                                             const double x0, const double d0, double &sq)
+__device__ __forceinline__ void fast_trial(const FastArgs &fa, unsigned char *smem, const FastDims &E,
+                                           const double stp, const double (&dd)[EPT])
 {
     double *xt = (double *)(smem + fa.L.xt);
-    sq = 0.0;
+    const double *xcur = (const double *)(smem + fa.L.xcur);
 #pragma unroll
     for (int k = 0; k < EPT; k++) {
         const uint32_t c = threadIdx.x + (uint32_t)k * G;
-        const double t = fma(stp, dd[k], x[k]);
-        if (c < E.d) { xt[c] = t; sq = fma(t, t, sq); }
+        if (c < E.d) xt[c] = fma(stp, dd[k], xcur[c]);
     }
-    const double xt0 = fma(stp, d0, x0);
-    if (E.hi && fa.a.o.regularize_bias && threadIdx.x == 0) sq = fma(xt0, xt0, sq);
-    return xt0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The kernel.  Per L-BFGS iteration, in the common case (first trial step accepted), five block barriers:
+//   B1  trial point xt published (and the per-warp partials of g.d for the direction just built)
+//       rows: z = X1.xt + offset, cross entropy, residual r            -> B2 (r, and sums of cost / r / xt^2)
+//       cols: g_new = (X1^T r + l2 xt) / n into smem                   -> B3
+//       each thread takes its own slots of g_new back into registers and, SPECULATING that the step will be
+//       accepted, forms its share of the 2m+2 inner products of the compact update together with g_new.d and
+//       max|g_new|                                                     -> B4 (per-warp partials)
+//       all threads: Wolfe test on the totals; accept; stop tests; store the new pair in registers;
+//       warp 0: the m x m step (re_lbfgs.cuh)                          -> B5 (coefficients u, w)
+//       next direction d = -gamma g - S u + gamma Y w from registers, next trial point x + d -> B1
+// ---------------------------------------------------------------------------------------------------------
 template <int G, int EPT>
 __global__ void __launch_bounds__(G, (G <= 128) ? 384 / G : 1) re_fast_kernel(const FastArgs fa)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double red[2 * kMaxWarps * kRedK];
+    __shared__ double wred[2 * kMaxWarps];   // per-warp partials: [w] g.d after H2, [kMaxWarps + w] max|g_new|
+    __shared__ LineSearch ls_slots[2];
     __shared__ int s_entity;
     __shared__ unsigned s_flag;
 
@@ -548,7 +523,7 @@ __global__ void __launch_bounds__(G, (G <= 128) ? 384 / G : 1) re_fast_kernel(co
                 continue;
             }
             if (n64 <= (int64_t)kFastMaxRows && (int64_t)E.d <= (int64_t)G * EPT && a.o.m <= MT)
-                st = fast_stage<G>(a, L, smem, r0, q0, E.n, E.d, &s_flag, E.nrslab, E.ncslab);
+                st = fast_stage<G>(a, L, smem, r0, q0, E.n, E.d, &s_flag);
         }
         if (st == 1) {
             if (tid == 0 && a.status) a.status[e] = GDMIX_ERR_INVALID;
@@ -559,264 +534,360 @@ __global__ void __launch_bounds__(G, (G <= 128) ? 384 / G : 1) re_fast_kernel(co
             continue;
         }
         double *dense = (double *)(smem + L.dense);
+        double *part = (double *)(smem + L.part);
         if (W == 1) prefetch_entity_l2(a.b, (int64_t)e + gridDim.x, lane);
 
         // ---- solver state: this thread's slots of x, g, direction and of every history vector -----------
-        double x[EPT], g[EPT], gn[EPT], dd[EPT], Sh[MT][EPT], Yh[MT][EPT];
-        double x0 = 0.0, g0 = 0.0, gn0 = 0.0, d0 = 0.0, S0 = 0.0, Y0 = 0.0;  // S0/Y0: lane s of warp 0 = slot s
+        // (the iterate and its gradient live in smem xcur / gold, each thread touching only its own slots;
+        //  the intercept's components of the stored pairs in smem icept[], touched by warp 0 only)
+        double gn[EPT], dd[EPT], Sh[MT][EPT], Yh[MT][EPT];
+        double x0 = 0.0, g0 = 0.0, gn0 = 0.0, d0 = 0.0;
+        double *xcur = (double *)(smem + L.xcur), *gold = (double *)(smem + L.gold);
+        double *icept = (double *)(smem + L.icept);
         {
             const int64_t t0 = a.b.theta_ptr[e];
 #pragma unroll
             for (int k = 0; k < EPT; k++) {
                 const uint32_t c = tid + (uint32_t)k * G;
-                x[k] = (c < E.d && a.theta_in) ? a.theta_in[t0 + E.hi + c] : 0.0;
-                g[k] = 0.0; dd[k] = 0.0;
+                if (c < E.d) {
+                    xcur[c] = a.theta_in ? a.theta_in[t0 + E.hi + c] : 0.0;
+                    gold[c] = 0.0;
+                }
+                gn[k] = 0.0; dd[k] = 0.0;
 #pragma unroll
                 for (int s = 0; s < MT; s++) { Sh[s][k] = 0.0; Yh[s][k] = 0.0; }
             }
             if (E.hi && a.theta_in) x0 = a.theta_in[t0];
+            if (tid < 2u * MT) icept[tid] = 0.0;
         }
         Lbfgs lb;
         lbfgs_reset<G, MT>(lb, dense);
-        double f, gd, gmax;
-        {
-            double sq;
-            const double xt0 = fast_trial<G, EPT>(fa, smem, E, 0.0, x, dd, x0, d0, sq);
-            group_sync<G>();
-            fast_evaluate<G, EPT>(fa, smem, E, xt0, sq, dd, d0, gn, gn0, red, flip, f, gd, gmax);
-        }
-#pragma unroll
-        for (int k = 0; k < EPT; k++) g[k] = gn[k];
-        g0 = gn0;
-        int nfev = 1, iter = 0, status = GDMIX_SOLVE_CONVERGED;
 
-        if (a.mode == kModeLossGrad) {
-            const int64_t t0 = a.b.theta_ptr[e];
-#pragma unroll
-            for (int k = 0; k < EPT; k++) {
-                const uint32_t c = tid + (uint32_t)k * G;
-                if (c < E.d) a.g_out[t0 + E.hi + c] = g[k];
-            }
-            if (tid == 0) {
-                if (E.hi) a.g_out[t0] = g0;
-                a.f_out[e] = f;
-            }
-            continue;
-        }
-
-        // ---- L-BFGS-B, unbounded (same driver as re_kernel.cuh) ------------------------------------------
         const double epsmch = 2.220446049250313e-16;
-        const double ftol = 1e-3, gtol = 0.9, xtol = 0.1, stpmx = 1e10;
-        double dtd = 0.0;
-        bool done = gmax <= a.o.pgtol;
-        auto steepest = [&]() {
+        const double ftol = 1e-3, gtol = 0.9, stpmx = 1e10;
+        const double l2 = a.o.l2, inv_n = 1.0 / (double)E.n;
+        enum { PH_INIT = 0, PH_FIRST = 1, PH_MORE = 2 };
+        int phase = PH_INIT, nfev = 0, iter = 0, status = GDMIX_SOLVE_CONVERGED, ifun = 0, ls_slot = 0;
+        double f = 0.0, gd = 0.0, fold = 0.0, gdold = 0.0, stp = 0.0;
+        bool gd_pending = false, emitted = false;
+        fast_trial<G, EPT>(fa, smem, E, 0.0, dd);
+
+        // A search along the steepest-descent direction: the first iteration, or a restart after a failed search.
+        auto steepest_search = [&]() {
             double v1[1] = {0.0};
 #pragma unroll
             for (int k = 0; k < EPT; k++) {
-                dd[k] = -g[k];
-                v1[0] = fma(g[k], g[k], v1[0]);
+                const uint32_t c = tid + (uint32_t)k * G;
+                const double gk = (c < E.d) ? gold[c] : 0.0;
+                dd[k] = -gk;
+                v1[0] = fma(gk, gk, v1[0]);
             }
             d0 = -g0;
             if (tid == 0) v1[0] = fma(g0, g0, v1[0]);
             group_sum<G, 1>(v1, red, flip);
-            dtd = v1[0];
             gd = -v1[0];
+            gd_pending = false;
+            stp = (iter == 0) ? fmin(1.0 / sqrt(v1[0]), stpmx) : 1.0;
+            fast_trial<G, EPT>(fa, smem, E, stp, dd);
+            phase = PH_FIRST;
         };
-        if (!done) steepest();
 
-        while (!done) {
-            // ---- line search (lnsrlb + dcsrch) along d.  The first trial step is almost always accepted, so
-            // the More'-Thuente state is only materialised (re-derived from the values at step 0, which is
-            // exactly what dcsrch's START call computes) once a trial has been evaluated.
-            double stp = (iter == 0) ? fmin(1.0 / sqrt(dtd), stpmx) : 1.0;
-            const double fold = f, gdold = gd, stp_first = stp;
-            int iback = 0, info = 0;
-            double gmax_t = gmax;
-            if (gd >= 0.0 || stp < 0.0 || stp > stpmx) info = -4;  // dcsrch's START checks
-            if (info == 0 && a.o.max_ls > 0) {
+        for (;;) {
+            group_sync<G>();                                                    // ---- B1
+            if (gd_pending) {
+                double t = wred[0];
+#pragma unroll
+                for (uint32_t w2 = 1; w2 < W; w2++) t += wred[w2];
+                gd = t;
+                gd_pending = false;
+            }
+            bool failed = false;
+            if (phase == PH_FIRST) {
+                // a fresh search starts here: dcsrch's START checks
+                fold = f; gdold = gd; ifun = 1;
+                if (gd >= 0.0 || stp < 0.0 || stp > stpmx || a.o.max_ls <= 0) failed = true;
+            }
+            if (!failed) {
+                // ================= evaluate f, g at xt ====================================================
+                double ft, gdt, gmt;
                 {
-                    double sq;
-                    const double xt0 = fast_trial<G, EPT>(fa, smem, E, stp, x, dd, x0, d0, sq);
-                    group_sync<G>();
-                    fast_evaluate<G, EPT>(fa, smem, E, xt0, sq, dd, d0, gn, gn0, red, flip, f, gd, gmax_t);
-                    nfev++;
-                }
-                LineSearch ls;
-                {
-                    double s1 = stp_first;
-                    dcsrch(s1, fold, gdold, ftol, gtol, xtol, 0.0, stpmx, LS_START, ls);
-                }
-                int ifun = 1;
-                for (;;) {
-                    const int task = dcsrch(stp, f, gd, ftol, gtol, xtol, 0.0, stpmx, LS_FG, ls);
-                    if (task == LS_CONV || task == LS_WARN) break;
-                    if (task == LS_ERROR) { info = -4; break; }
-                    ifun++; iback = ifun - 1;
-                    if (iback >= a.o.max_ls) break;
-                    double sq;
-                    const double xt0 = fast_trial<G, EPT>(fa, smem, E, stp, x, dd, x0, d0, sq);
-                    group_sync<G>();
-                    fast_evaluate<G, EPT>(fa, smem, E, xt0, sq, dd, d0, gn, gn0, red, flip, f, gd, gmax_t);
-                    nfev++;
-                }
-            } else if (info == 0) {
-                iback = a.o.max_ls;  // max_ls == 0: no trial allowed
-            }
-            if (info != 0 || iback >= a.o.max_ls) {
-                f = fold;  // x, g still hold the previous iterate
-                if (lb.col == 0) { status = GDMIX_SOLVE_ABNORMAL; iter++; break; }
-                group_sync<G>();
-                lbfgs_reset<G, MT>(lb, dense);
-#pragma unroll
-                for (int k = 0; k < EPT; k++) {
-#pragma unroll
-                    for (int s = 0; s < MT; s++) { Sh[s][k] = 0.0; Yh[s][k] = 0.0; }
-                }
-                S0 = 0.0; Y0 = 0.0;
-                steepest();
-                continue;
-            }
-            iter++;
-            // accept the trial point (the same fma as fast_trial gives the same bits); g holds the old gradient
-#pragma unroll
-            for (int k = 0; k < EPT; k++) x[k] = fma(stp, dd[k], x[k]);
-            x0 = fma(stp, d0, x0);
-            gmax = gmax_t;
-
-            if (iter >= a.o.max_iter || nfev > a.o.max_fun) { status = GDMIX_SOLVE_MAXITER; break; }
-            if (gmax <= a.o.pgtol) break;
-            if ((fold - f) <= epsmch * a.o.factr * max3(fabs(fold), fabs(f), 1.0)) break;
-
-            // ---- curvature pair (L-BFGS-B's skip rule) and the next direction ---------------------------
-            double dr, ddum;
-            if (stp == 1.0) { dr = gd - gdold; ddum = -gdold; }
-            else { dr = (gd - gdold) * stp; ddum = -gdold * stp; }
-            const int m = a.o.m;
-            const bool update = (m > 0) && !(dr <= epsmch * ddum);
-            int newslot = -1;
-            if (update) newslot = (lb.col < m) ? (lb.head + lb.col) % m : lb.head;
-            const uint32_t dotmask = update ? (lb.valid & ~(1u << newslot)) : lb.valid;
-            double *part = (double *)(smem + L.part);
-
-            // H1: inner products of every stored pair with the new gradient, y.y, y.g -- a dozen at a time
-            {
-                double v[12];
-#pragma unroll
-                for (int s = 0; s < 12; s++) v[s] = 0.0;
-#pragma unroll
-                for (int k = 0; k < EPT; k++) {
-                    const double gj = gn[k], yj = gj - g[k];
-                    v[MT] = fma(yj, yj, v[MT]);
-                    v[MT + 1] = fma(yj, gj, v[MT + 1]);
-#pragma unroll
-                    for (int s = 0; s < MT; s++) v[s] = fma(Sh[s][k], gj, v[s]);
-                }
-                warp_reduce12(v, lane);
-                if ((lane & 7u) == 0) {
-                    const uint32_t at = warp * kFastPartK + 6u * ((lane >> 4) & 1u) + 3u * ((lane >> 3) & 1u);
-                    part[at] = v[0]; part[at + 1] = v[1]; part[at + 2] = v[2];
-                }
-            }
-            {
-                double v[12];
-#pragma unroll
-                for (int s = 0; s < 12; s++) v[s] = 0.0;
-#pragma unroll
-                for (int k = 0; k < EPT; k++) {
-                    const double gj = gn[k];
-#pragma unroll
-                    for (int s = 0; s < MT; s++) v[s] = fma(Yh[s][k], gj, v[s]);
-                }
-                warp_reduce12(v, lane);
-                if ((lane & 7u) == 0) {
-                    const uint32_t at = warp * kFastPartK + 12u + 6u * ((lane >> 4) & 1u) + 3u * ((lane >> 3) & 1u);
-                    part[at] = v[0]; part[at + 1] = v[1]; part[at + 2] = v[2];
-                }
-            }
-            // the new pair takes its slot: s = stp d, y = g_new - g_old
-            if (update) {
-#pragma unroll
-                for (int k = 0; k < EPT; k++) {
-                    const double sj = stp * dd[k], yj = gn[k] - g[k];
-#pragma unroll
-                    for (int s = 0; s < MT; s++) {
-                        if (s == newslot) { Sh[s][k] = sj; Yh[s][k] = yj; }
-                    }
-                }
-            }
-            group_sync<G>();
-            if (warp == 0) {
-                double *tot = dense + DNF::tot;
-                const double y0 = gn0 - g0;
-                if (lane < 2 * MT + 2) {
-                    // part row: [S^T g (10) | y.y | y.g | Y^T g (10) | 0 0]  ->  tot: [S^T g | Y^T g | y.y | y.g]
-                    const uint32_t src = (lane < (uint32_t)MT) ? lane : (lane < 2u * MT) ? lane + 2u : lane - MT;
-                    double t = part[src];
-#pragma unroll
-                    for (uint32_t w2 = 1; w2 < W; w2++) t += part[w2 * kFastPartK + src];
-                    tot[lane] = t;
-                }
-                __syncwarp();
-                if (E.hi) {
-                    // the intercept's share: slot s lives in lane s (S0, Y0)
-                    const double y0s = __shfl_sync(kFull, Y0, (lane >= (uint32_t)MT && lane < 2u * MT) ? lane - MT : lane);
-                    if (lane < (uint32_t)MT) tot[lane] = fma(S0, gn0, tot[lane]);
-                    else if (lane < 2u * MT) tot[lane] = fma(y0s, gn0, tot[lane]);
-                    else if (lane == 2u * MT) tot[lane] = fma(y0, y0, tot[lane]);
-                    else if (lane == 2u * MT + 1u) tot[lane] = fma(y0, gn0, tot[lane]);
-                }
-                __syncwarp();
-                double uv, wv;
-                lbfgs_small_update<MT>(lb, update, newslot, dotmask, stp, dr, gd, dense, uv, wv);
-                if (update && (int)lane == newslot) { S0 = stp * d0; Y0 = y0; }
-                // intercept component of the next direction
-                const double theta_n = update ? tot[2 * MT] / dr : lb.theta;
-                const double gamma = 1.0 / theta_n;
-                double t = (lane < (uint32_t)MT) ? fma(gamma * wv, Y0, -uv * S0) : 0.0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
-                if (lane == 0) dense[DNF::count] = E.hi ? fma(-gamma, gn0, t) : 0.0;
-            } else if (warp == 1 && iter == 1) {
-                // idle while warp 0 works: pull the entity a grid-width ahead in the queue towards L2
-                prefetch_entity_l2(a.b, (int64_t)e + gridDim.x, lane);
-            }
-            group_sync<G>();
-            if (update) {
-                lb.theta = dense[DNF::tot + 2 * MT] / dr;
-                lb.valid |= (1u << newslot);
-                if (lb.col < m) lb.col++; else lb.head = (lb.head + 1) % m;
-            }
-            // H2: d = -gamma g - S u + gamma Y w
-            {
-                const double gamma = 1.0 / lb.theta;
-                double acc[EPT];
-#pragma unroll
-                for (int k = 0; k < EPT; k++) acc[k] = -gamma * gn[k];
-#pragma unroll
-                for (int s = 0; s < MT; s++) {
-                    const double cu = dense[DNF::cu + s], cw = gamma * dense[DNF::cw + s];
+                    const double xt0 = fma(stp, d0, x0);
+                    double p3[3] = {0.0, 0.0, 0.0};   // sums of cost, r, xt_reg^2
 #pragma unroll
                     for (int k = 0; k < EPT; k++) {
-                        acc[k] = fma(-cu, Sh[s][k], acc[k]);
-                        acc[k] = fma(cw, Yh[s][k], acc[k]);
+                        const uint32_t c = tid + (uint32_t)k * G;
+                        if (c < E.d) { const double t = ((const double *)(smem + L.xt))[c]; p3[2] = fma(t, t, p3[2]); }
+                    }
+                    if (E.hi && a.o.regularize_bias && tid == 0) p3[2] = fma(xt0, xt0, p3[2]);
+                    const uint32_t *rbase = (const uint32_t *)(smem + L.rbase);
+                    for (uint32_t b = warp; b < ((E.n + 31u) >> 5); b += W) {
+                        const uint32_t sb = rbase[b];
+                        double z = sell_dot((const float4 *)(smem + L.sell_val) + sb * kStepQuads + lane,
+                                            (const uint2 *)(smem + L.sell_idx) + sb * kStepQuads + lane,
+                                            rbase[b + 1] - sb);
+                        const uint32_t sp = b * 32u + lane;
+                        if (sp < E.n) {
+                            z = (z + (E.hi ? xt0 : 0.0)) + (double)((const float *)(smem + L.soff))[sp];
+                            const double yi = (double)((const float *)(smem + L.sy))[sp];
+                            const double wi = (double)((const float *)(smem + L.sw))[sp];
+                            const double ez = exp(-fabs(z));
+                            const double ce = fmax(z, 0.0) - z * yi + log(1.0 + ez);
+                            p3[0] = fma(wi, ce, p3[0]);
+                            const double inv = 1.0 / (1.0 + ez);
+                            const double sig = (z >= 0.0) ? inv : ez * inv;
+                            const double ri = wi * (sig - yi);
+                            ((double *)(smem + L.r))[((const uint16_t *)(smem + L.rowperm))[sp]] = ri;
+                            p3[1] += ri;
+                        }
+                    }
+                    group_sum<G, 3>(p3, red, flip);                             // ---- B2 (publishes r[])
+                    if (G == 32) __syncwarp();
+                    ft = (p3[0] + 0.5 * l2 * p3[2]) * inv_n;
+                    gn0 = E.hi ? (p3[1] + (a.o.regularize_bias ? l2 * xt0 : 0.0)) * inv_n : 0.0;
+                }
+                {
+                    const uint32_t *cbase = (const uint32_t *)(smem + L.cbase);
+                    for (uint32_t b = warp; b < ((E.d + 31u) >> 5); b += W) {
+                        const uint32_t sb = cbase[b];
+                        const double acc = sell_dot((const float4 *)(smem + L.sell_val) + sb * kStepQuads + lane,
+                                                    (const uint2 *)(smem + L.sell_idx) + sb * kStepQuads + lane,
+                                                    cbase[b + 1] - sb);
+                        const uint32_t sp = b * 32u + lane;
+                        if (sp < E.d) {
+                            const uint32_t c = ((const uint16_t *)(smem + L.colperm))[sp];
+                            ((double *)(smem + L.gnew))[c] = (acc + l2 * ((const double *)(smem + L.xt))[c]) * inv_n;
+                        }
                     }
                 }
-                d0 = dense[DNF::count];
-                double v2[2] = {0.0, 0.0};
+                group_sync<G>();                                                // ---- B3 (publishes g_new)
+                // own slots of g_new; speculative inner products with the stored pairs (12 at a time)
+                double gm = fabs(gn0);
 #pragma unroll
                 for (int k = 0; k < EPT; k++) {
-                    dd[k] = acc[k];
-                    g[k] = gn[k];
-                    v2[0] = fma(gn[k], acc[k], v2[0]);
-                    v2[1] = fma(acc[k], acc[k], v2[1]);
+                    const uint32_t c = tid + (uint32_t)k * G;
+                    gn[k] = (c < E.d) ? ((const double *)(smem + L.gnew))[c] : 0.0;
+                    gm = fmax(gm, fabs(gn[k]));
                 }
-                g0 = gn0;
-                if (tid == 0) { v2[0] = fma(g0, d0, v2[0]); v2[1] = fma(d0, d0, v2[1]); }
-                group_sum<G, 2>(v2, red, flip);
-                gd = v2[0];
-                dtd = v2[1];
+                {
+                    double v[12];
+#pragma unroll
+                    for (int s = 0; s < 12; s++) v[s] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < EPT; k++) {
+                        const uint32_t c = tid + (uint32_t)k * G;
+                        const double gj = gn[k], yj = gj - ((c < E.d) ? gold[c] : 0.0);
+                        v[MT] = fma(yj, yj, v[MT]);
+                        v[MT + 1] = fma(yj, gj, v[MT + 1]);
+#pragma unroll
+                        for (int s = 0; s < MT; s++) v[s] = fma(Sh[s][k], gj, v[s]);
+                    }
+                    warp_reduce12(v, lane);
+                    if ((lane & 7u) == 0) {
+                        const uint32_t at = warp * kFastPartK + 6u * ((lane >> 4) & 1u) + 3u * ((lane >> 3) & 1u);
+                        part[at] = v[0]; part[at + 1] = v[1]; part[at + 2] = v[2];
+                    }
+                }
+                {
+                    double v[12];
+#pragma unroll
+                    for (int s = 0; s < 12; s++) v[s] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < EPT; k++) {
+                        const double gj = gn[k];
+                        v[MT] = fma(gj, dd[k], v[MT]);   // g_new . d
+#pragma unroll
+                        for (int s = 0; s < MT; s++) v[s] = fma(Yh[s][k], gj, v[s]);
+                    }
+                    if (tid == 0) v[MT] = fma(gn0, d0, v[MT]);
+                    warp_reduce12(v, lane);
+                    if ((lane & 7u) == 0) {
+                        const uint32_t at = warp * kFastPartK + 12u + 6u * ((lane >> 4) & 1u) + 3u * ((lane >> 3) & 1u);
+                        part[at] = v[0]; part[at + 1] = v[1]; part[at + 2] = v[2];
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) gm = fmax(gm, __shfl_xor_sync(kFull, gm, o));
+                if (lane == 0) wred[kMaxWarps + warp] = gm;
+                group_sync<G>();                                                // ---- B4
+                gdt = part[2 * MT + 2];
+                gmt = wred[kMaxWarps];
+#pragma unroll
+                for (uint32_t w2 = 1; w2 < W; w2++) {
+                    gdt += part[w2 * kFastPartK + 2 * MT + 2];
+                    gmt = fmax(gmt, wred[kMaxWarps + w2]);
+                }
+                nfev++;
+                // ================= what the evaluation was for ===========================================
+                if (phase == PH_INIT) {
+                    f = ft;
+#pragma unroll
+                    for (int k = 0; k < EPT; k++) {
+                        const uint32_t c = tid + (uint32_t)k * G;
+                        if (c < E.d) gold[c] = gn[k];
+                    }
+                    g0 = gn0;
+                    if (a.mode == kModeLossGrad) {
+                        const int64_t t0 = a.b.theta_ptr[e];
+#pragma unroll
+                        for (int k = 0; k < EPT; k++) {
+                            const uint32_t c = tid + (uint32_t)k * G;
+                            if (c < E.d) a.g_out[t0 + E.hi + c] = gn[k];
+                        }
+                        if (tid == 0) {
+                            if (E.hi) a.g_out[t0] = g0;
+                            a.f_out[e] = f;
+                        }
+                        emitted = true;
+                        break;
+                    }
+                    if (gmt <= a.o.pgtol) break;
+                    steepest_search();
+                    continue;
+                }
+                bool accept = false;
+                if (phase == PH_FIRST)   // dcsrch's convergence test, on the state its START call would have set
+                    accept = (ft <= fold + stp * (ftol * gdold)) && (fabs(gdt) <= gtol * (-gdold));
+                if (!accept) {
+                    const LsOut o = ls_continue(ls_slots, ls_slot, phase == PH_FIRST, stp, fold, gdold, stp, ft, gdt);
+                    ls_slot ^= 1;
+                    if (o.task == LS_CONV || o.task == LS_WARN) {
+                        accept = true;
+                    } else if (o.task == LS_ERROR || ifun >= a.o.max_ls) {
+                        failed = true;
+                    } else {
+                        ifun++;
+                        stp = o.stp;
+                        fast_trial<G, EPT>(fa, smem, E, stp, dd);
+                        phase = PH_MORE;
+                        continue;
+                    }
+                }
+                if (accept) {
+                    iter++;
+                    f = ft; gd = gdt;
+                    // the accepted point is the trial point; gold still holds the old gradient
+#pragma unroll
+                    for (int k = 0; k < EPT; k++) {
+                        const uint32_t c = tid + (uint32_t)k * G;
+                        if (c < E.d) xcur[c] = ((const double *)(smem + L.xt))[c];
+                    }
+                    x0 = fma(stp, d0, x0);
+                    if (iter >= a.o.max_iter || nfev > a.o.max_fun) { status = GDMIX_SOLVE_MAXITER; break; }
+                    if (gmt <= a.o.pgtol) break;
+                    if ((fold - f) <= epsmch * a.o.factr * max3(fabs(fold), fabs(f), 1.0)) break;
+
+                    // ---- curvature pair (L-BFGS-B's skip rule) and the next direction -----------------------
+                    double dr, ddum;
+                    if (stp == 1.0) { dr = gd - gdold; ddum = -gdold; }
+                    else { dr = (gd - gdold) * stp; ddum = -gdold * stp; }
+                    const int m = a.o.m;
+                    const bool update = (m > 0) && !(dr <= epsmch * ddum);
+                    int newslot = -1;
+                    if (update) newslot = (lb.col < m) ? (lb.head + lb.col) % m : lb.head;
+                    const uint32_t dotmask = update ? (lb.valid & ~(1u << newslot)) : lb.valid;
+                    // the new pair takes its slot: s = stp d, y = g_new - g_old
+                    if (update) {
+#pragma unroll
+                        for (int k = 0; k < EPT; k++) {
+                            const uint32_t c = tid + (uint32_t)k * G;
+                            const double sj = stp * dd[k], yj = gn[k] - ((c < E.d) ? gold[c] : 0.0);
+#pragma unroll
+                            for (int s = 0; s < MT; s++) {
+                                if (s == newslot) { Sh[s][k] = sj; Yh[s][k] = yj; }
+                            }
+                        }
+                    }
+                    if (warp == 0) {
+                        double *tot = dense + DNF::tot;
+                        const double y0 = gn0 - g0;
+                        if (lane < 2 * MT + 2) {
+                            // part row: [S^T g (10) | y.y | y.g | Y^T g (10) | g.d | -]  ->  tot: [S^T g | Y^T g | y.y | y.g]
+                            const uint32_t src = (lane < (uint32_t)MT) ? lane : (lane < 2u * MT) ? lane + 2u : lane - MT;
+                            double t = part[src];
+#pragma unroll
+                            for (uint32_t w2 = 1; w2 < W; w2++) t += part[w2 * kFastPartK + src];
+                            tot[lane] = t;
+                        }
+                        __syncwarp();
+                        if (E.hi) {
+                            // the intercept's share: icept[] = [S0 (m) | Y0 (m)], same order as tot[]
+                            if (lane < 2u * MT) tot[lane] = fma(icept[lane], gn0, tot[lane]);
+                            else if (lane == 2u * MT) tot[lane] = fma(y0, y0, tot[lane]);
+                            else if (lane == 2u * MT + 1u) tot[lane] = fma(y0, gn0, tot[lane]);
+                        }
+                        __syncwarp();
+                        double uv, wv;
+                        lbfgs_small_update<MT>(lb, update, newslot, dotmask, stp, dr, gd, dense, uv, wv);
+                        if (update && (int)lane == newslot) { icept[lane] = stp * d0; icept[MT + lane] = y0; }
+                        __syncwarp();
+                        // intercept component of the next direction
+                        const double theta_n = update ? tot[2 * MT] / dr : lb.theta;
+                        const double gamma = 1.0 / theta_n;
+                        double t = (lane < (uint32_t)MT) ? fma(gamma * wv, icept[MT + lane], -uv * icept[lane]) : 0.0;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+                        if (lane == 0) dense[DNF::count] = E.hi ? fma(-gamma, gn0, t) : 0.0;
+                    } else if (warp == 1 && iter == 1) {
+                        // idle while warp 0 works: pull the entity a grid-width ahead in the queue towards L2
+                        prefetch_entity_l2(a.b, (int64_t)e + gridDim.x, lane);
+                    }
+                    group_sync<G>();                                            // ---- B5
+                    if (update) {
+                        lb.theta = dense[DNF::tot + 2 * MT] / dr;
+                        lb.valid |= (1u << newslot);
+                        if (lb.col < m) lb.col++; else lb.head = (lb.head + 1) % m;
+                    }
+                    // H2: d = -gamma g - S u + gamma Y w, the next trial point x + d and the partials of g.d
+                    {
+                        const double gamma = 1.0 / lb.theta;
+                        double acc[EPT];
+#pragma unroll
+                        for (int k = 0; k < EPT; k++) acc[k] = -gamma * gn[k];
+#pragma unroll
+                        for (int s = 0; s < MT; s++) {
+                            const double cu = dense[DNF::cu + s], cw = gamma * dense[DNF::cw + s];
+#pragma unroll
+                            for (int k = 0; k < EPT; k++) {
+                                acc[k] = fma(-cu, Sh[s][k], acc[k]);
+                                acc[k] = fma(cw, Yh[s][k], acc[k]);
+                            }
+                        }
+                        d0 = dense[DNF::count];
+                        double gdp = 0.0;
+#pragma unroll
+                        for (int k = 0; k < EPT; k++) {
+                            const uint32_t c = tid + (uint32_t)k * G;
+                            dd[k] = acc[k];
+                            if (c < E.d) gold[c] = gn[k];
+                            gdp = fma(gn[k], acc[k], gdp);
+                        }
+                        g0 = gn0;
+                        if (tid == 0) gdp = fma(g0, d0, gdp);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) gdp += __shfl_xor_sync(kFull, gdp, o);
+                        if (lane == 0) wred[warp] = gdp;
+                        gd_pending = true;
+                        stp = 1.0;
+                        fast_trial<G, EPT>(fa, smem, E, stp, dd);
+                        phase = PH_FIRST;
+                    }
+                    continue;
+                }
             }
+            // ---- the search along d failed (or could not start): x, g, f are those of the last iterate -------
+            f = fold;
+            if (lb.col == 0) { status = GDMIX_SOLVE_ABNORMAL; iter++; break; }
+            group_sync<G>();
+            lbfgs_reset<G, MT>(lb, dense);
+#pragma unroll
+            for (int k = 0; k < EPT; k++) {
+#pragma unroll
+                for (int s = 0; s < MT; s++) { Sh[s][k] = 0.0; Yh[s][k] = 0.0; }
+            }
+            if (tid < 2u * MT) icept[tid] = 0.0;
+            steepest_search();
         }
+        if (emitted) continue;
 
         // ---- emit ---------------------------------------------------------------------------------------
         const int64_t t0 = a.b.theta_ptr[e];
@@ -824,7 +895,7 @@ __global__ void __launch_bounds__(G, (G <= 128) ? 384 / G : 1) re_fast_kernel(co
 #pragma unroll
         for (int k = 0; k < EPT; k++) {
             const uint32_t c = tid + (uint32_t)k * G;
-            if (c < E.d) a.theta_out[t0 + E.hi + c] = (thr > 0.0 && fabs(x[k]) <= thr) ? 0.0 : x[k];
+            if (c < E.d) { const double xv = xcur[c]; a.theta_out[t0 + E.hi + c] = (thr > 0.0 && fabs(xv) <= thr) ? 0.0 : xv; }
         }
         if (tid == 0) {
             if (E.hi) a.theta_out[t0] = (thr > 0.0 && fabs(x0) <= thr) ? 0.0 : x0;
@@ -841,16 +912,15 @@ __global__ void __launch_bounds__(G, (G <= 128) ? 384 / G : 1) re_fast_kernel(co
 #pragma unroll
             for (int k = 0; k < EPT; k++) {
                 const uint32_t c = tid + (uint32_t)k * G;
-                if (c < E.d) xt[c] = x[k];
+                if (c < E.d) xt[c] = xcur[c];
             }
             group_sync<G>();
             const uint32_t *rbase = (const uint32_t *)(smem + L.rbase), *cbase = (const uint32_t *)(smem + L.cbase);
             double dsum[1] = {0.0};
-            for (uint32_t b = warp; b < E.nrslab; b += W) {
+            for (uint32_t b = warp; b < ((E.n + 31u) >> 5); b += W) {
                 const uint32_t sb = rbase[b];
                 double z = sell_dot((const float4 *)(smem + L.sell_val) + sb * kStepQuads + lane,
-                                    (const uint2 *)(smem + L.sell_idx) + sb * kStepQuads + lane, rbase[b + 1] - sb,
-                                    (const char *)xt);
+                                    (const uint2 *)(smem + L.sell_idx) + sb * kStepQuads + lane, rbase[b + 1] - sb);
                 const uint32_t sp = b * 32u + lane;
                 if (sp < E.n) {
                     z = (z + (E.hi ? x0 : 0.0)) + (double)((const float *)(smem + L.soff))[sp];
@@ -862,20 +932,19 @@ __global__ void __launch_bounds__(G, (G <= 128) ? 384 / G : 1) re_fast_kernel(co
             }
             group_sum<G, 1>(dsum, red, flip);
             if (G == 32) __syncwarp();
-            for (uint32_t b = warp; b < E.ncslab; b += W) {
+            for (uint32_t b = warp; b < ((E.d + 31u) >> 5); b += W) {
                 const uint32_t sb = cbase[b], ns = cbase[b + 1] - sb;
                 const float4 *pv = (const float4 *)(smem + L.sell_val) + sb * kStepQuads + lane;
                 const uint2 *pi = (const uint2 *)(smem + L.sell_idx) + sb * kStepQuads + lane;
-                const char *rv = (const char *)rr;
                 double h = 0.0;
                 for (uint32_t k = 0; k < ns; k++) {
                     const float4 va = pv[k * kStepQuads];
                     const uint2 ca = pi[k * kStepQuads];
                     const double a0 = (double)va.x, a1 = (double)va.y, a2 = (double)va.z, a3 = (double)va.w;
-                    h = fma(a0, a0 * *(const double *)(rv + (ca.x & 0xffffu)), h);
-                    h = fma(a1, a1 * *(const double *)(rv + (ca.x >> 16)), h);
-                    h = fma(a2, a2 * *(const double *)(rv + (ca.y & 0xffffu)), h);
-                    h = fma(a3, a3 * *(const double *)(rv + (ca.y >> 16)), h);
+                    h = fma(a0, a0 * lds_f64(ca.x & 0xffffu), h);
+                    h = fma(a1, a1 * lds_f64(ca.x >> 16), h);
+                    h = fma(a2, a2 * lds_f64(ca.y & 0xffffu), h);
+                    h = fma(a3, a3 * lds_f64(ca.y >> 16), h);
                 }
                 const uint32_t sp = b * 32u + lane;
                 if (sp < E.d)
