@@ -6,3 +6,6 @@ There is no CPU fallback: a missing library is an ImportError.
 from . import _capi  # noqa: F401  (loads the native library or raises)
 
 __version__ = "0.1.0"
+
+from .fixed_effect import FixedEffectLRLBFGSModel, FixedEffectLRModelLBFGS  # noqa: E402,F401
+from .random_effect import RandomEffectLRLBFGSModel  # noqa: E402,F401

@@ -25,6 +25,7 @@ EPS = float(np.finfo(np.float64).eps)
 # every symbol include/gdmix_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_workspace_size",
            "gdmix_re_loss_grad", "gdmix_re_fit", "gdmix_re_score", "gdmix_fe_loss_grad", "gdmix_fe_score",
+           "gdmix_fe_hessian",
            "gdmix_re_fit_host", "gdmix_re_score_host", "gdmix_host_register", "gdmix_host_unregister",
            "gdmix_host_release", "gdmix_partition_ids", "gdmix_lbfgs_create", "gdmix_lbfgs_iterate",
            "gdmix_lbfgs_info", "gdmix_lbfgs_destroy", "gdmix_launch_count", "gdmix_re_last_plan"]
@@ -314,6 +315,16 @@ def fe_loss_grad_device(rows, opts, x, fg=None, stream=None):
     cs = rows.c_struct()
     check(lib.gdmix_fe_loss_grad(C.byref(cs), C.byref(opts), _tptr(x), _tptr(fg), _stream_ptr(stream)))
     return fg
+
+
+def fe_hessian_device(rows, opts, x, mode, stream=None):
+    """-> h tensor: [D+hi] (SIMPLE) or [(D+hi), (D+hi)] (FULL); this rank's partial sum."""
+    import torch
+    P = rows.n_features + (1 if opts.has_intercept else 0)
+    h = torch.empty(P * P if mode == VARIANCE_FULL else P, dtype=torch.float64, device=x.device)
+    cs = rows.c_struct()
+    check(lib.gdmix_fe_hessian(C.byref(cs), C.byref(opts), _tptr(x), C.c_int32(mode), _tptr(h), _stream_ptr(stream)))
+    return h.view(P, P) if mode == VARIANCE_FULL else h
 
 
 def fe_score_device(rows, opts, x, stream=None):

@@ -507,6 +507,29 @@ int gdmix_fe_loss_grad(const gdmix_fe_rows *rows, const gdmix_lr_opts *o, const 
     return GDMIX_OK;
 }
 
+int gdmix_fe_hessian(const gdmix_fe_rows *rows, const gdmix_lr_opts *o, const double *x, int32_t mode, double *h,
+                     void *stream)
+{
+    if (!rows || !o || !x || !h) return fail(GDMIX_ERR_INVALID, "null argument");
+    if (mode != GDMIX_VARIANCE_SIMPLE && mode != GDMIX_VARIANCE_FULL)
+        return fail(GDMIX_ERR_INVALID, "mode must be GDMIX_VARIANCE_SIMPLE or GDMIX_VARIANCE_FULL");
+    if (rows->linear_regression) return fail(GDMIX_ERR_INVALID, "variance is defined for logistic regression only");
+    DeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc) return rc;
+    const size_t P = (size_t)rows->n_features + (o->has_intercept ? 1 : 0);
+    const int full = mode == GDMIX_VARIANCE_FULL;
+    if (full && P > 16384) return fail(GDMIX_ERR_TOO_LARGE, "FULL variance needs a dense %zu x %zu matrix", P, P);
+    CUDA_TRY(cudaMemsetAsync(h, 0, 8 * (full ? P * P : P), (cudaStream_t)stream));
+    if (rows->n_rows > 0) {
+        const int grid = (int)std::min<int64_t>((rows->n_rows + 255) / 256, (int64_t)dev.sm_count * 8);
+        gdmix::fe_hessian_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*rows, o->has_intercept ? 1 : 0, x, full, h);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return GDMIX_OK;
+}
+
 int gdmix_fe_score(const gdmix_fe_rows *rows, const gdmix_lr_opts *o, const double *x, float *logit, float *logit_pc,
                    void *stream)
 {

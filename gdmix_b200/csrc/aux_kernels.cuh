@@ -105,6 +105,47 @@ __global__ void __launch_bounds__(256) fe_loss_grad_kernel(const gdmix_fe_rows R
     }
 }
 
+// Hessian of the fixed-effect logistic loss over this rank's rows, X1^T diag(w rho (1 - rho)) X1 with the
+// intercept column LAST (fixed_effect_lr_lbfgs_model.py:271-296).  full == 0: h[P] gets the diagonal;
+// full != 0: h[P*P] row-major gets the whole matrix (small P only: every row adds nnz^2 entries).
+__global__ void __launch_bounds__(256) fe_hessian_kernel(const gdmix_fe_rows R, const int hi, const double *x,
+                                                         const int full, double *h)
+{
+    const int64_t D = R.n_features, P = D + hi;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    const double b0 = hi ? x[D] : 0.0;
+    double dsum = 0.0;
+    for (int64_t i = tid; i < R.n_rows; i += nth) {
+        const int64_t qs = R.rowptr[i], qe = R.rowptr[i + 1];
+        double z = 0.0;
+        for (int64_t q = qs; q < qe; q++) z = fma((double)R.val[q], x[R.col[q]], z);
+        z += b0;
+        z += R.offset ? (double)R.offset[i] : 0.0;
+        const double rho = 1.0 / (1.0 + exp(-z));
+        const double di = rho * (1.0 - rho) * (R.weight ? (double)R.weight[i] : 1.0);
+        if (!full) {
+            for (int64_t q = qs; q < qe; q++) {
+                const double v = (double)R.val[q];
+                atomicAdd(&h[R.col[q]], v * v * di);
+            }
+            dsum += di;
+        } else {
+            for (int64_t q = qs; q < qe; q++) {
+                const double vd = (double)R.val[q] * di;
+                const int64_t r = R.col[q];
+                for (int64_t q2 = qs; q2 < qe; q2++) atomicAdd(&h[r * P + R.col[q2]], vd * (double)R.val[q2]);
+                if (hi) { atomicAdd(&h[r * P + D], vd); atomicAdd(&h[D * P + r], vd); }
+            }
+            if (hi) atomicAdd(&h[D * P + D], di);
+        }
+    }
+    if (!full && hi) {
+        dsum = warp_sum(dsum);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&h[D], dsum);
+    }
+}
+
 __global__ void __launch_bounds__(256) fe_score_kernel(const gdmix_fe_rows R, const int hi, const double *x,
                                                        float *logit, float *logit_pc)
 {

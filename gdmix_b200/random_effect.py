@@ -1,0 +1,269 @@
+"""RandomEffectLRLBFGSModel -- the reference's random-effect plugin with its per-entity scipy loop replaced by
+one batched CUDA solve per partition.
+
+Same constructor, attributes, ``train`` / ``predict`` / ``export`` signatures, files and error behaviour as
+gdmix-trainer/src/gdmix/models/custom/random_effect_lr_lbfgs_model.py:56-317; what changed underneath:
+
+  reference                                                      here
+  -------------------------------------------------------------  ---------------------------------------------
+  per_entity_grouped_input_fn (TF) + prepare_jobs: one Job per   ingest.read_entity_grouped + to_local_batch: the
+  entity through a Manager().Queue (job_consumers.py:161-296)    whole partition as one flat entity-local CSR batch
+  TrainingJobConsumer: BinaryLogisticRegressionTrainer.fit per   ONE gdmix_re_fit_host call (C ABI): every entity
+  entity in a process pool (job_consumers.py:36-63)              solved on the GPU, thresholded, SIMPLE variance
+  InferenceJobConsumer (job_consumers.py:138-152)                ONE gdmix_re_score_host call
+  fastavro model / score writers                                 io.model_io / io.avro (same schemas, same records)
+
+The reference always fits in the index space ``enable_local_indexing`` selects; both give the same
+coefficients (features an entity never sees keep a zero coefficient: SURVEY.md section 0), so the device always
+works entity-locally and ``enable_local_indexing`` is accepted and ignored.  ``num_of_consumers``,
+``max_training_queue_size`` and ``training_queue_timeout_in_seconds`` are accepted for CLI compatibility; there
+is no queue.  There is no CPU fallback: without the CUDA library the package does not import.
+"""
+import logging
+import os
+from collections import namedtuple
+
+import numpy as np
+
+from . import _capi as capi
+from . import constants, ingest
+from .api import Model
+from .io import model_io
+from .io.dataset_metadata import DatasetMetadata, read_json_file
+from .params import REParams
+
+logger = logging.getLogger(__name__)
+
+# job_consumers.py:19
+TrainingResult = namedtuple("TrainingResult", ("theta", "variance", "unique_global_indices"))
+
+
+class RandomEffectLRLBFGSModel(Model):
+    """Entity-based logistic regression: all entities of a partition are trained in one GPU batch."""
+
+    def __init__(self, raw_model_params):
+        super().__init__(raw_model_params)
+        self.model_params: REParams = self._parse_parameters(raw_model_params)
+        self.checkpoint_path = os.path.join(self.model_params.output_model_dir)
+        self.metadata_file = self.model_params.metadata_file
+        self.feature_bag_name = self.model_params.feature_bag
+        self.has_intercept = self.model_params.has_intercept
+        # an intercept-only model has no feature file
+        self.feature_file = None if self.feature_bag_name is None else self.model_params.feature_file
+        if self.model_params.training_data_dir is not None:
+            self.training_data_dir = os.path.join(self.model_params.training_data_dir, constants.ACTIVE)
+            self.passive_training_data_dir = os.path.join(self.model_params.training_data_dir, constants.PASSIVE)
+        else:
+            self.training_data_dir = None
+            self.passive_training_data_dir = None
+        self.validation_data_dir = self.model_params.validation_data_dir
+        self.disable_random_effect_scoring_after_training = \
+            self.model_params.disable_random_effect_scoring_after_training
+        self.last_fit_info = None  # nit / nfev / status arrays of the latest _train (diagnostics, tests)
+
+    # ---- Model API ------------------------------------------------------------------------------------
+    def train(self, training_data_dir, validation_data_dir, metadata_file, checkpoint_path, execution_context,
+              schema_params):
+        logger.info("Kicking off random effect custom LR training")
+        self._action(constants.ACTION_TRAIN, (training_data_dir, validation_data_dir), metadata_file,
+                     checkpoint_path, execution_context, schema_params)
+
+    def predict(self, output_dir, input_data_path, metadata_file, checkpoint_path, execution_context, schema_params):
+        logger.info(f"Running inference on dataset : {input_data_path}, results to be written to path : {output_dir}")
+        self._action(constants.ACTION_INFERENCE, (output_dir, input_data_path), metadata_file, checkpoint_path,
+                     execution_context, schema_params)
+
+    def export(self, output_model_dir):
+        logger.info("Model export is done as part of the training() API for random effect LR LBFGS training. "
+                    "Skipping.")
+
+    def _parse_parameters(self, raw_model_parameters) -> REParams:
+        params = REParams.__from_argv__(raw_model_parameters, error_on_unknown=False)
+        logger.info(params)
+        return params
+
+    # ---- orchestration (random_effect_lr_lbfgs_model.py:92-138) ------------------------------------------
+    def _action(self, action, action_context, metadata_file, checkpoint_path, execution_context, schema_params):
+        partition_index = execution_context[constants.PARTITION_INDEX]
+        metadata = read_json_file(metadata_file)
+        tensor_metadata = DatasetMetadata(metadata)
+        # an intercept-only model is padded with one dummy (all-zero) feature
+        num_features = 1 if self.feature_bag_name is None \
+            else tensor_metadata.get_feature_shape(self.feature_bag_name)[0]
+        logger.info(f"Found {num_features} features in feature bag {self.feature_bag_name}")
+        assert num_features > 0, "number of features must > 0"
+        avro_filename = f"part-{partition_index:05d}.avro"
+        common = dict(metadata=metadata, tensor_metadata=tensor_metadata, schema_params=schema_params,
+                      num_features=num_features)
+        if action == constants.ACTION_INFERENCE:
+            output_dir, input_data_path = action_context
+            model_weights = self._load_weights(os.path.join(checkpoint_path, avro_filename))
+            self._predict(input_path=input_data_path, output_file=os.path.join(output_dir, avro_filename),
+                          model_weights=model_weights, **common)
+        elif action == constants.ACTION_TRAIN:
+            training_data_dir, validation_data_dir = action_context
+            model_file = os.path.join(self.model_params.output_model_dir, avro_filename)
+            model_weights = self._load_weights(model_file, True)  # warm start when a model is already there
+            model_weights = self._train(training_data_dir, tensor_metadata, model_weights, num_features,
+                                        schema_params, model_file)
+            if validation_data_dir:
+                o = execution_context.get(constants.VALIDATION_OUTPUT_FILE, None)
+                o and self._predict(input_path=validation_data_dir, output_file=o, model_weights=model_weights,
+                                    **common)
+            if not self.disable_random_effect_scoring_after_training:
+                o = execution_context.get(constants.ACTIVE_TRAINING_OUTPUT_FILE, None)
+                o and self._predict(input_path=training_data_dir, output_file=o, model_weights=model_weights,
+                                    **common)
+                i = execution_context.get(constants.PASSIVE_TRAINING_DATA_DIR, None)
+                o = execution_context.get(constants.PASSIVE_TRAINING_OUTPUT_FILE, None)
+                i and o and self._predict(input_path=i, output_file=o, model_weights=model_weights, **common)
+        else:
+            raise ValueError(f"Invalid action {action!r}.")
+
+    def _read(self, input_path, tensor_metadata, schema_params, num_features, need_label):
+        assert self.model_params.data_format == constants.TFRECORD
+        data = ingest.read_entity_grouped(
+            input_path, tensor_metadata, entity_name=self.model_params.partition_entity,
+            feature_bag=self.feature_bag_name, label_column=schema_params.label_column_name,
+            offset_column=self.model_params.offset_column_name, weight_column=schema_params.weight_column_name,
+            uid_column=schema_params.uid_column_name, num_features=num_features)
+        if need_label and data.label is None:
+            raise ValueError(f"label column {schema_params.label_column_name!r} not found in {input_path}")
+        return data
+
+    def _opts(self, **kw):
+        mp = self.model_params
+        return capi.make_opts(l2=mp.l2_reg_weight, regularize_bias=mp.regularize_bias,
+                              has_intercept=self.has_intercept, m=mp.num_of_lbfgs_curvature_pairs,
+                              max_iter=mp.num_of_lbfgs_iterations, tol=mp.lbfgs_tolerance, **kw)
+
+    # ---- training (random_effect_lr_lbfgs_model.py:140-167 + job_consumers.py:36-99) -----------------------
+    def _train(self, input_path, tensor_metadata, model_weights: dict, num_features, schema_params,
+               output_model_file):
+        logger.info(f"Start training with "
+                    f"{f'loaded {len(model_weights)} previous models' if model_weights else 'zeros'} "
+                    f"as the model initial value.")
+        mp = self.model_params
+        data = self._read(input_path, tensor_metadata, schema_params, num_features, need_label=True)
+        if data.n_entities:
+            labels = data.label
+            if not np.all((labels == 0) | (labels == 1)):
+                raise ValueError("labels must be 0/1 for logistic regression")  # binary_logistic_regression.py:208
+            hb, uniq_ptr, uniq_global = ingest.to_local_batch(data, self.has_intercept)
+            theta0, has_model = ingest.warm_start_theta(hb, uniq_ptr, uniq_global, data.entity_ids, model_weights,
+                                                        self.has_intercept)
+            mode = mp.random_effect_variance_mode
+            if mode == constants.FULL:
+                vmode = capi.VARIANCE_FULL
+            elif mode == constants.SIMPLE:
+                vmode = capi.VARIANCE_SIMPLE
+            else:
+                vmode = capi.VARIANCE_NONE
+            opts = self._opts(sparsity_threshold=mp.sparsity_threshold, variance_mode=vmode)
+            out = capi.re_fit_host(hb, opts, theta0=theta0 if has_model.any() else None,
+                                   want_variance=vmode != capi.VARIANCE_NONE)
+            self.last_fit_info = {k: out[k] for k in ("nit", "nfev", "status", "f")}
+            results = {}
+            tp = hb.theta_ptr
+            for e, eid in enumerate(data.entity_ids):
+                var = out["variance"][tp[e]:tp[e + 1]].copy() if vmode != capi.VARIANCE_NONE else None
+                results[eid] = TrainingResult(theta=out["theta"][tp[e]:tp[e + 1]].copy(), variance=var,
+                                              unique_global_indices=uniq_global[uniq_ptr[e]:uniq_ptr[e + 1]].copy())
+            # prior-only entities survive; prior-only features of a retrained entity do not (:161)
+            model_weights.update(results)
+        logger.info(f"{len(model_weights)} models in total after training/refreshing.")
+        self._save_model(output_model_file, model_coefficients=model_weights, num_features=num_features,
+                         feature_file=self.feature_file)
+        return model_weights
+
+    # ---- inference (random_effect_lr_lbfgs_model.py:169-190 + job_consumers.py:102-152) --------------------
+    def _predict(self, input_path, metadata, tensor_metadata, output_file, schema_params, num_features,
+                 model_weights):
+        logger.info(f"Start inference for {input_path}.")
+        data = self._read(input_path, tensor_metadata, schema_params, num_features, need_label=False)
+        has_weight = any(schema_params.weight_column_name == f.name for f in tensor_metadata.get_features())
+        schema = model_io.get_inference_output_avro_schema(metadata, True, schema_params, has_weight=has_weight)
+        if data.n_entities:
+            hb, uniq_ptr, uniq_global = ingest.to_local_batch(data, self.has_intercept)
+            theta, has_model = ingest.warm_start_theta(hb, uniq_ptr, uniq_global, data.entity_ids, model_weights,
+                                                       self.has_intercept)
+            logit, per_coordinate = capi.re_score_host(hb, self._opts(), theta, has_model)
+        else:
+            logit = per_coordinate = np.zeros(0, np.float32)
+        sp = schema_params
+
+        def records():
+            lab = data.label
+            for i in range(data.n_rows):
+                rec = {sp.prediction_score_column_name: float(logit[i]), sp.weight_column_name: float(data.weight[i]),
+                       sp.uid_column_name: int(data.uid[i]),
+                       sp.prediction_score_per_coordinate_column_name: float(per_coordinate[i])}
+                if lab is not None:
+                    rec[sp.label_column_name] = float(lab[i])
+                yield rec
+
+        model_io.batched_write_avro(records(), output_file, schema)
+        logger.info(f"Inference complete: {input_path}.")
+
+    # ---- model files (random_effect_lr_lbfgs_model.py:219-309) ---------------------------------------------
+    def _save_model(self, output_file, model_coefficients, num_features, feature_file):
+        model_ids = list(model_coefficients.keys())
+        biases = [] if self.has_intercept else None
+        with_variance = self.model_params.random_effect_variance_mode is not None
+        if feature_file is None:
+            list_of_weight_indices = list_of_weight_values = None  # intercept-only model
+            assert num_features == 1
+        else:
+            list_of_weight_indices, list_of_weight_values = [], []
+        for entity_id, (mean, variance, unique_global_indices) in model_coefficients.items():
+            idx = 0
+            if self.has_intercept:
+                biases.append((mean[idx], variance[idx]) if with_variance else mean[idx])
+                idx = 1
+            if list_of_weight_indices is not None:
+                list_of_weight_values.append((mean[idx:], variance[idx:]) if with_variance else mean[idx:])
+                list_of_weight_indices.append(unique_global_indices)
+        os.makedirs(os.path.dirname(output_file) or ".", exist_ok=True)
+        model_io.export_linear_model_to_avro(model_ids, list_of_weight_indices, list_of_weight_values, biases,
+                                             feature_file, output_file,
+                                             sparsity_threshold=self.model_params.sparsity_threshold)
+
+    def _load_weights(self, model_file, catch_exception=False):
+        logger.info(f"Loading model from {model_file}")
+        if not os.path.exists(model_file):
+            if catch_exception:
+                logger.info(f"No model found at {model_file}.")
+                return {}
+            raise FileNotFoundError(f"Model file {model_file} does not exist")
+        feature2global_id = None if self.feature_file is None else model_io.get_feature_map(self.feature_file)
+        from .io import avro
+        return dict(self._convert_avro_model_record_to_sparse_coefficients(self.has_intercept, record,
+                                                                           feature2global_id)
+                    for record in avro.read_records(model_file))
+
+    @staticmethod
+    def _convert_avro_model_record_to_sparse_coefficients(has_intercept, model_record, feature2global_id):
+        model_id = model_record["modelId"]
+        coefficients, unique_global_indices, variances = [], [], []
+        for idx, ntv in enumerate(model_record["means"]):
+            coefficients.append(np.float64(ntv["value"]))
+            if has_intercept and idx == 0:
+                assert ntv["name"] == constants.INTERCEPT and ntv["term"] == ""
+            else:
+                unique_global_indices.append(feature2global_id[(ntv["name"], ntv["term"])])
+        if model_record.get("variances"):
+            for idx, ntv in enumerate(model_record["variances"]):
+                variances.append(np.float64(ntv["value"]))
+                if has_intercept and idx == 0:
+                    assert ntv["name"] == constants.INTERCEPT and ntv["term"] == ""
+                else:
+                    off = 1 if has_intercept else 0
+                    assert unique_global_indices[idx - off] == feature2global_id[(ntv["name"], ntv["term"])]
+        if feature2global_id is None:
+            # intercept-only model: one dummy feature
+            assert len(unique_global_indices) == 0
+            coefficients.append(np.float64(0.0))
+            unique_global_indices.append(0)
+        return model_id, TrainingResult(theta=np.array(coefficients),
+                                        variance=np.array(variances) if variances else None,
+                                        unique_global_indices=np.array(unique_global_indices, dtype=np.int64))

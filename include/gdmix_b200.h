@@ -169,6 +169,12 @@ GDMIX_API int gdmix_re_score(const gdmix_re_batch *batch, const gdmix_lr_opts *o
  * all-reduces fg (NCCL, same stream) and feeds it to the replicated L-BFGS step. */
 GDMIX_API int gdmix_fe_loss_grad(const gdmix_fe_rows *rows, const gdmix_lr_opts *opts, const double *x, double *fg,
                                  void *stream);
+/* Hessian of the logistic loss over this rank's rows at x, X1^T diag(w rho (1-rho)) X1 with the intercept column
+ * LAST -- the accumulator H of _scoring_fn (fixed_effect_lr_lbfgs_model.py:271-296; the reference keeps it in
+ * fp32, here fp64).  mode GDMIX_VARIANCE_SIMPLE: h[D+hi] = diagonal; GDMIX_VARIANCE_FULL: h[(D+hi)^2] row-major.
+ * h is zeroed by the call.  The caller all-reduces h, adds the L2 term and inverts (:451-463). */
+GDMIX_API int gdmix_fe_hessian(const gdmix_fe_rows *rows, const gdmix_lr_opts *opts, const double *x, int32_t mode,
+                               double *h, void *stream);
 GDMIX_API int gdmix_fe_score(const gdmix_fe_rows *rows, const gdmix_lr_opts *opts, const double *x, float *logit,
                              float *logit_per_coordinate, void *stream);
 
