@@ -17,6 +17,7 @@
 #include "host_lbfgs.h"
 #include "re_fast.cuh"
 #include "re_kernel.cuh"
+#include "re_variance.cuh"
 
 namespace {
 
@@ -82,6 +83,11 @@ struct RePlan {
     int fgrid = 1;
     gdmix::FastLayout fL;
     size_t off_defer = 0, off_arena = 0;
+    // FULL variance pass (re_variance.cuh)
+    int vgrid = 0;
+    uint32_t vsmem = 0, vsmem_matrix_doubles = 0;
+    unsigned long long vscratch_stride = 0;  // doubles per CTA in the workspace (0: the matrix fits on chip)
+    size_t off_vscratch = 0;
     size_t workspace = 0;
 };
 
@@ -229,6 +235,19 @@ int plan_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &d
     pl.off_defer = kQueueBytes;
     pl.off_arena = pl.off_defer + (pl.fast ? (((size_t)b->n_entities * 4 + 255) & ~(size_t)255) : 0);
     pl.workspace = pl.off_arena + (size_t)pl.arena_stride * (size_t)want;
+    if (o->variance_mode == GDMIX_VARIANCE_FULL) {
+        const size_t P = (size_t)b->max_coef;
+        const size_t vec_bytes = 2 * 8 * P;
+        const size_t avail = (size_t)dev.smem_optin - 1024;
+        if (vec_bytes > avail) return fail(GDMIX_ERR_TOO_LARGE, "%zu coefficients are too many for the variance pass", P);
+        pl.vsmem_matrix_doubles = (vec_bytes + 8 * P * P <= avail) ? (uint32_t)(P * P) : 0u;
+        pl.vsmem = (uint32_t)(vec_bytes + 8 * (size_t)pl.vsmem_matrix_doubles);
+        pl.vscratch_stride = pl.vsmem_matrix_doubles ? 0ull : (unsigned long long)(P * P);
+        const int per_sm = pl.vsmem_matrix_doubles ? std::max(1, (int)((228u * 1024u) / (pl.vsmem + 2048u))) : 2;
+        pl.vgrid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)dev.sm_count * std::min(per_sm, 8), b->n_entities));
+        pl.off_vscratch = (pl.workspace + 255) & ~(size_t)255;
+        pl.workspace = pl.off_vscratch + 8 * (size_t)pl.vscratch_stride * (size_t)pl.vgrid;
+    }
     return GDMIX_OK;
 }
 
@@ -286,8 +305,6 @@ int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const d
     if (b->n_entities == 0) return GDMIX_OK;
     if (!b->ent_rowptr || !b->rowptr || !b->label || !b->theta_ptr || (b->nnz > 0 && (!b->col || !b->val)))
         return fail(GDMIX_ERR_INVALID, "null array in gdmix_re_batch");
-    if (o->variance_mode == GDMIX_VARIANCE_FULL)
-        return fail(GDMIX_ERR_INVALID, "variance_mode FULL is not implemented on the device path");
     DeviceInfo dev;
     int rc = device_info(dev);
     if (rc) return rc;
@@ -298,9 +315,13 @@ int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const d
     if (!workspace || workspace_bytes < pl.workspace)
         return fail(GDMIX_ERR_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, pl.workspace);
 
+    const bool full_var = mode == gdmix::kModeFit && var_out && o->variance_mode == GDMIX_VARIANCE_FULL;
+    if (full_var && !status)
+        return fail(GDMIX_ERR_INVALID, "variance_mode FULL needs the status array (rejected entities are skipped)");
     gdmix::ReArgs a;
     memset(&a, 0, sizeof(a));
     a.b = *b; a.o = *o;
+    if (full_var) a.o.sparsity_threshold = 0.0;  // thresholded by the variance pass, after it has used theta
     a.theta_in = theta_in; a.theta_out = theta_out; a.f_out = f_out; a.nit = nit; a.nfev = nfev; a.status = status;
     a.var_out = var_out; a.g_out = g_out;
     a.queue = (int32_t *)workspace;
@@ -332,18 +353,40 @@ int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const d
     }
     if (pl.MT == 10) {
         switch (pl.G) {
-        case 32: return launch_re_t<32, 10>(a, pl, st);
-        case 64: return launch_re_t<64, 10>(a, pl, st);
-        case 128: return launch_re_t<128, 10>(a, pl, st);
-        default: return launch_re_t<256, 10>(a, pl, st);
+        case 32: rc = launch_re_t<32, 10>(a, pl, st); break;
+        case 64: rc = launch_re_t<64, 10>(a, pl, st); break;
+        case 128: rc = launch_re_t<128, 10>(a, pl, st); break;
+        default: rc = launch_re_t<256, 10>(a, pl, st); break;
+        }
+    } else {
+        switch (pl.G) {
+        case 32: rc = launch_re_t<32, 32>(a, pl, st); break;
+        case 64: rc = launch_re_t<64, 32>(a, pl, st); break;
+        case 128: rc = launch_re_t<128, 32>(a, pl, st); break;
+        default: rc = launch_re_t<256, 32>(a, pl, st); break;
         }
     }
-    switch (pl.G) {
-    case 32: return launch_re_t<32, 32>(a, pl, st);
-    case 64: return launch_re_t<64, 32>(a, pl, st);
-    case 128: return launch_re_t<128, 32>(a, pl, st);
-    default: return launch_re_t<256, 32>(a, pl, st);
+    if (rc || !full_var) return rc;
+    // FULL variance at the un-thresholded optimum, then the threshold (re_variance.cuh)
+    gdmix::VarArgs v;
+    memset(&v, 0, sizeof(v));
+    v.b = *b; v.o = *o;
+    v.theta = theta_out; v.var_out = var_out; v.status = status;
+    v.queue = (int32_t *)workspace + 3;
+    v.scratch = (double *)((unsigned char *)workspace + pl.off_vscratch);
+    v.scratch_stride = pl.vscratch_stride;
+    v.smem_matrix_doubles = pl.vsmem_matrix_doubles;
+    v.max_coef = (uint32_t)b->max_coef;
+    static std::atomic<int> vconfigured{0};
+    if (!vconfigured.load()) {
+        CUDA_TRY(cudaFuncSetAttribute(gdmix::re_variance_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024 - 1024));
+        vconfigured.store(1);
     }
+    gdmix::re_variance_full_kernel<<<pl.vgrid, 256, pl.vsmem, st>>>(v);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
 }
 
 // ---- host-buffer pipeline ----------------------------------------------------------------------
@@ -558,8 +601,8 @@ int gdmix_re_fit_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const do
     if (!hb->ent_rowptr || !hb->rowptr || !hb->label || !hb->theta_ptr)
         return fail(GDMIX_ERR_INVALID, "null array in gdmix_re_batch");
     const bool want_var = var_out != nullptr;
-    if (want_var && o->variance_mode != GDMIX_VARIANCE_SIMPLE)
-        return fail(GDMIX_ERR_INVALID, "var_out needs variance_mode SIMPLE");
+    if (want_var && o->variance_mode != GDMIX_VARIANCE_SIMPLE && o->variance_mode != GDMIX_VARIANCE_FULL)
+        return fail(GDMIX_ERR_INVALID, "var_out needs variance_mode SIMPLE or FULL");
     std::vector<int32_t> own_status;
     if (!status) { own_status.resize((size_t)E); status = own_status.data(); }
     std::lock_guard<std::mutex> lk(g_host.mu);

@@ -74,7 +74,7 @@ typedef enum gdmix_status {
 
 #define GDMIX_VARIANCE_NONE 0
 #define GDMIX_VARIANCE_SIMPLE 1
-#define GDMIX_VARIANCE_FULL 2   /* not implemented by the device path yet: returns GDMIX_ERR_INVALID */
+#define GDMIX_VARIANCE_FULL 2   /* diag(H^-1): a dense p x p inversion per entity after the solve */
 
 /* A batch of entities in entity-local CSR form: what prepare_jobs
  * (job_consumers.py:161-296) hands to the consumers, flattened.  Entity e owns samples
@@ -153,7 +153,8 @@ GDMIX_API int gdmix_re_loss_grad(const gdmix_re_batch *batch, const gdmix_lr_opt
  *   theta0      NULL = cold start (zeros), else warm-start coefficients (same layout as theta_out)
  *   theta_out   [theta_ptr[E]] coefficients (thresholded if opts->sparsity_threshold > 0)
  *   f_out,nit,nfev,status   [E], any may be NULL
- *   var_out     [theta_ptr[E]] or NULL; needs opts->variance_mode == GDMIX_VARIANCE_SIMPLE */
+ *   var_out     [theta_ptr[E]] or NULL; needs opts->variance_mode == GDMIX_VARIANCE_SIMPLE or _FULL
+ *               (binary_logistic_regression.py:144-189; taken at the un-thresholded optimum) */
 GDMIX_API int gdmix_re_fit(const gdmix_re_batch *batch, const gdmix_lr_opts *opts, const double *theta0,
                            double *theta_out, double *f_out, int32_t *nit, int32_t *nfev, int32_t *status,
                            double *var_out, void *workspace, size_t workspace_bytes, void *stream);

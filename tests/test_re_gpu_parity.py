@@ -239,3 +239,47 @@ def test_deferred_entities_take_the_general_kernel(monkeypatch, re_path):
         np.testing.assert_array_equal(alld[k], ref[k])
     rel = _rel_per_entity(mixed["theta"], ref["theta"], hb.theta_ptr)
     assert rel.max() <= 1e-9, rel.max()
+
+
+@pytest.mark.parametrize("shape", [(40, 24, 6), (128, 256, 32)])
+def test_variance_full_matches_oracle(shape):
+    """FULL variance = diag((X1^T D X1 + (l2 + 1e-12) I - l2 e0 e0^T)^-1) at the un-thresholded optimum
+    (binary_logistic_regression.py:178-186); the matrix lives on chip for the small shape, in the workspace for C1."""
+    n, d, k = shape
+    E = 48
+    hb = make_batch(E, n, d, k, seed=15, weights=True)
+    raw = capi.re_fit_host(hb, capi.make_opts(l2=1.0))
+    out = capi.re_fit_host(hb, capi.make_opts(l2=1.0, sparsity_threshold=1e-4, variance_mode=capi.VARIANCE_FULL),
+                           want_variance=True)
+    np.testing.assert_array_equal(out["theta"], np.where(np.abs(raw["theta"]) <= 1e-4, 0.0, raw["theta"]))
+    ob = _oracle_batch(hb)
+    oo = _oracle_opts(capi.make_opts(l2=1.0))
+    for e in range(0, E, 5):
+        r0, r1 = hb.ent_rowptr[e], hb.ent_rowptr[e + 1]
+        q0, q1 = hb.rowptr[r0], hb.rowptr[r1]
+        blk = O.EntityBlock(r1 - r0, d, hb.rowptr[r0:r1 + 1] - q0, hb.col[q0:q1], hb.val[q0:q1], hb.label[r0:r1],
+                            ob["w"][r0:r1], ob["off"][r0:r1])
+        th = raw["theta"][hb.theta_ptr[e]:hb.theta_ptr[e + 1]]
+        np.testing.assert_allclose(out["variance"][hb.theta_ptr[e]:hb.theta_ptr[e + 1]],
+                                   O.re_variance(blk, oo, th, "full"), rtol=1e-9)
+
+
+def test_golden_variances_match_reference():
+    """SIMPLE and FULL variances the reference itself computed for the golden cases (re_golden: *_var_simple,
+    *_var_full), cold-start cases with l2 > 0."""
+    checked = 0
+    for key, cases in GROUPS.items():
+        l2, rb, hi, m, maxit, tol = key
+        cases = [c for c in cases if not c["warm"] and is_pinned(c) and (c["key"] + "_var_full") in ARR]
+        if l2 <= 0 or not cases:
+            continue
+        hb = _golden_batch(cases, ARR)
+        for mode, suffix in ((capi.VARIANCE_SIMPLE, "_var_simple"), (capi.VARIANCE_FULL, "_var_full")):
+            opts = capi.make_opts(l2=l2, regularize_bias=rb, has_intercept=hi, m=m, max_iter=maxit, tol=tol,
+                                  variance_mode=mode)
+            out = capi.re_fit_host(hb, opts, want_variance=True)
+            for i, c in enumerate(cases):
+                np.testing.assert_allclose(out["variance"][hb.theta_ptr[i]:hb.theta_ptr[i + 1]],
+                                           ARR[c["key"] + suffix], rtol=2e-6, err_msg=c["name"] + suffix)
+                checked += 1
+    assert checked > 50
