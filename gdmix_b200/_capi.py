@@ -25,7 +25,7 @@ EPS = float(np.finfo(np.float64).eps)
 # every symbol include/gdmix_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_workspace_size",
            "gdmix_re_loss_grad", "gdmix_re_fit", "gdmix_re_score", "gdmix_fe_loss_grad", "gdmix_fe_score",
-           "gdmix_fe_hessian",
+           "gdmix_fe_hessian", "gdmix_fe_rows_grid", "gdmix_fe_loss_grad_planned",
            "gdmix_re_fit_host", "gdmix_re_score_host", "gdmix_host_register", "gdmix_host_unregister",
            "gdmix_host_release", "gdmix_partition_ids", "gdmix_lbfgs_create", "gdmix_lbfgs_iterate",
            "gdmix_lbfgs_info", "gdmix_lbfgs_destroy", "gdmix_launch_count", "gdmix_re_last_plan"]
@@ -55,6 +55,14 @@ class FeRows(C.Structure):
     _fields_ = [("n_rows", C.c_int64), ("nnz", C.c_int64), ("n_features", C.c_int64), ("rowptr", C.c_void_p),
                 ("col", C.c_void_p), ("val", C.c_void_p), ("label", C.c_void_p), ("weight", C.c_void_p),
                 ("offset", C.c_void_p), ("linear_regression", C.c_int32), ("num_workers", C.c_int32)]
+
+
+class FePlanStruct(C.Structure):
+    _fields_ = [("colptr", C.c_void_p), ("row", C.c_void_p), ("val", C.c_void_p), ("n_items", C.c_int64),
+                ("item_col", C.c_void_p), ("item_begin", C.c_void_p), ("item_end", C.c_void_p),
+                ("item_slot", C.c_void_p), ("n_split", C.c_int64), ("split_col", C.c_void_p),
+                ("split_slot_ptr", C.c_void_p), ("n_slots", C.c_int64), ("scratch", C.c_void_p),
+                ("scratch_doubles", C.c_int64)]
 
 
 def _load():
@@ -306,14 +314,74 @@ class DeviceFeRows:
                       self.num_workers)
 
 
-def fe_loss_grad_device(rows, opts, x, fg=None, stream=None):
-    """-> fg tensor [1 + D + has_intercept]: value then gradient (this rank's partial)."""
+FE_SLICE = 4096  # non-zeros of a column one warp sums; longer columns are sliced
+
+
+class DeviceFePlan:
+    """Column-major copy of a shard + work items + scratch for gdmix_fe_loss_grad_planned.  Built once per
+    training run (the shard does not change between the ~100 evaluations of an L-BFGS run).  The transpose is a
+    stable sort by column done with torch (device memory plumbing, outside any timed region)."""
+
+    def __init__(self, rows, slice_nnz=FE_SLICE):
+        import torch
+        dev = rows.val.device
+        D, n = rows.n_features, rows.n_rows
+        col64 = rows.col.to(torch.int64)
+        order = torch.sort(col64, stable=True).indices            # rows ascending inside a column
+        row_of_nnz = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int32),
+                                             (rows.rowptr[1:] - rows.rowptr[:-1]))
+        self.row = row_of_nnz[order].contiguous()
+        self.val = rows.val[order].contiguous()
+        counts = torch.bincount(col64, minlength=D)
+        self.colptr = torch.zeros(D + 1, dtype=torch.int64, device=dev)
+        self.colptr[1:] = torch.cumsum(counts, 0)
+        del order, row_of_nnz, col64
+        # work items (host side: D is small next to nnz)
+        cp = self.colptr.cpu().numpy()
+        ln = np.diff(cp)
+        pieces = np.maximum(1, -(-ln // slice_nnz)).astype(np.int64)
+        item_col = np.repeat(np.arange(D, dtype=np.int32), pieces)
+        first = np.concatenate([[0], np.cumsum(pieces)[:-1]])
+        k = np.arange(item_col.shape[0], dtype=np.int64) - np.repeat(first, pieces)
+        begin = cp[item_col] + k * slice_nnz
+        end = np.minimum(begin + slice_nnz, cp[item_col.astype(np.int64) + 1])
+        split = pieces > 1
+        item_split = np.repeat(split, pieces)
+        slot = np.full(item_col.shape[0], -1, np.int32)
+        slot[item_split] = np.arange(int(item_split.sum()), dtype=np.int32)
+        self.n_items, self.n_slots = int(item_col.shape[0]), int(item_split.sum())
+        split_col = np.flatnonzero(split).astype(np.int32)
+        ssp = np.concatenate([[0], np.cumsum(pieces[split])]).astype(np.int64)
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self.item_col, self.item_begin, self.item_end, self.item_slot = to(item_col), to(begin), to(end), to(slot)
+        self.n_split = int(split_col.shape[0])
+        self.split_col, self.split_slot_ptr = to(split_col), to(ssp)
+        g = C.c_int32()
+        cs = rows.c_struct()
+        check(lib.gdmix_fe_rows_grid(C.byref(cs), C.byref(g)))
+        self.scratch = torch.empty(n + self.n_slots + 2 * g.value, dtype=torch.float64, device=dev)
+
+    def c_struct(self):
+        return FePlanStruct(_tptr(self.colptr), _tptr(self.row), _tptr(self.val), self.n_items, _tptr(self.item_col),
+                            _tptr(self.item_begin), _tptr(self.item_end), _tptr(self.item_slot), self.n_split,
+                            _tptr(self.split_col), _tptr(self.split_slot_ptr), self.n_slots, _tptr(self.scratch),
+                            self.scratch.numel())
+
+
+def fe_loss_grad_device(rows, opts, x, fg=None, stream=None, plan=None):
+    """-> fg tensor [1 + D + has_intercept]: value then gradient (this rank's partial).  With a DeviceFePlan the
+    atomics-free three-kernel path runs; without, the single-pass kernel with fp64 atomics."""
     import torch
     n = 1 + rows.n_features + (1 if opts.has_intercept else 0)
     if fg is None:
         fg = torch.empty(n, dtype=torch.float64, device=x.device)
     cs = rows.c_struct()
-    check(lib.gdmix_fe_loss_grad(C.byref(cs), C.byref(opts), _tptr(x), _tptr(fg), _stream_ptr(stream)))
+    if plan is not None:
+        ps = plan.c_struct()
+        check(lib.gdmix_fe_loss_grad_planned(C.byref(cs), C.byref(ps), C.byref(opts), _tptr(x), _tptr(fg),
+                                             _stream_ptr(stream)))
+    else:
+        check(lib.gdmix_fe_loss_grad(C.byref(cs), C.byref(opts), _tptr(x), _tptr(fg), _stream_ptr(stream)))
     return fg
 
 

@@ -550,6 +550,64 @@ int gdmix_fe_loss_grad(const gdmix_fe_rows *rows, const gdmix_lr_opts *o, const 
     return GDMIX_OK;
 }
 
+namespace {
+void fe_rows_geometry(const gdmix_fe_rows *rows, const DeviceInfo &dev, int &grid, int &team_shift)
+{
+    const int64_t avg = rows->n_rows > 0 ? (rows->nnz + rows->n_rows - 1) / rows->n_rows : 1;
+    team_shift = 0;
+    while (team_shift < 5 && (1 << team_shift) < avg) team_shift++;
+    const int64_t teams_per_cta = 256 >> team_shift;
+    grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows->n_rows + teams_per_cta - 1) / teams_per_cta,
+                                                       (int64_t)dev.sm_count * 8));
+}
+}  // namespace
+
+int gdmix_fe_rows_grid(const gdmix_fe_rows *rows, int32_t *grid)
+{
+    if (!rows || !grid) return fail(GDMIX_ERR_INVALID, "null argument");
+    DeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc) return rc;
+    int g = 1, ts = 0;
+    fe_rows_geometry(rows, dev, g, ts);
+    *grid = g;
+    return GDMIX_OK;
+}
+
+int gdmix_fe_loss_grad_planned(const gdmix_fe_rows *rows, const gdmix_fe_plan *pl, const gdmix_lr_opts *o,
+                               const double *x, double *fg, void *stream)
+{
+    if (!rows || !pl || !o || !x || !fg) return fail(GDMIX_ERR_INVALID, "null argument");
+    if (!pl->colptr || !pl->item_col || !pl->item_begin || !pl->item_end || !pl->item_slot || !pl->scratch ||
+        (rows->nnz > 0 && (!pl->row || !pl->val)))
+        return fail(GDMIX_ERR_INVALID, "null array in gdmix_fe_plan");
+    DeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc) return rc;
+    int grid = 1, team_shift = 0;
+    fe_rows_geometry(rows, dev, grid, team_shift);
+    const int64_t need = rows->n_rows + pl->n_slots + 2 * (int64_t)grid;
+    if (pl->scratch_doubles < need)
+        return fail(GDMIX_ERR_WORKSPACE, "fe plan scratch %lld doubles < required %lld", (long long)pl->scratch_doubles,
+                    (long long)need);
+    gdmix::FePlan P;
+    P.colptr = pl->colptr; P.row = pl->row; P.val = pl->val;
+    P.n_items = pl->n_items; P.item_col = pl->item_col; P.item_begin = pl->item_begin; P.item_end = pl->item_end;
+    P.item_slot = pl->item_slot; P.n_split = pl->n_split; P.split_col = pl->split_col;
+    P.split_slot_ptr = pl->split_slot_ptr;
+    P.dz = pl->scratch; P.slots = pl->scratch + rows->n_rows; P.block_part = P.slots + pl->n_slots;
+    P.rows_grid = grid; P.team_shift = team_shift;
+    cudaStream_t st = (cudaStream_t)stream;
+    gdmix::fe_rows_kernel<<<grid, 256, 0, st>>>(*rows, *o, P, x);
+    const int cgrid = (int)std::max<int64_t>(1, std::min<int64_t>((pl->n_items + 7) / 8, (int64_t)dev.sm_count * 16));
+    gdmix::fe_cols_kernel<<<cgrid, 256, 0, st>>>(*rows, *o, P, x, fg);
+    const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((pl->n_split + 255) / 256, (int64_t)dev.sm_count));
+    gdmix::fe_finish_kernel<<<fgrid, 256, 0, st>>>(*rows, *o, P, x, fg);
+    g_launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
 int gdmix_fe_hessian(const gdmix_fe_rows *rows, const gdmix_lr_opts *o, const double *x, int32_t mode, double *h,
                      void *stream)
 {

@@ -146,6 +146,155 @@ __global__ void __launch_bounds__(256) fe_hessian_kernel(const gdmix_fe_rows R, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fixed-effect objective / gradient without atomics (gdmix_fe_loss_grad_planned).
+//
+//   fe_rows_kernel   a team of T lanes per row (T = 2^k ~ non-zeros per row, so loads coalesce): z, loss,
+//                    dz_i = d loss / d z_i -> dz[] (fp64), per-CTA partial sums of the loss and of dz.
+//   fe_cols_kernel   the gradient X^T dz from the column-major copy of the shard (built once per training by
+//                    the host): one warp per work item = a column, or a slice of at most kFeSlice non-zeros of
+//                    a long column; complete columns are stored straight into fg, slices go to a slot buffer.
+//   fe_finish_kernel sums the slices of every split column and the per-CTA partials in a fixed order, adds
+//                    the L2 term and the intercept's gradient.
+// Every sum has a fixed order: the objective is bitwise reproducible run to run, and popular features (one
+// feature can own 10 % of all non-zeros) cost no more per non-zero than rare ones -- with atomics they serialise.
+// ---------------------------------------------------------------------------------------------------------
+struct FePlan {
+    const int64_t *colptr;    // [D+1]
+    const int32_t *row;       // [nnz] ascending inside a column
+    const float *val;         // [nnz]
+    int64_t n_items;
+    const int32_t *item_col;  // [n_items]
+    const int64_t *item_begin, *item_end;
+    const int32_t *item_slot; // [n_items] -1: the item is a whole column
+    int64_t n_split;
+    const int32_t *split_col;       // [n_split]
+    const int64_t *split_slot_ptr;  // [n_split+1]
+    double *dz;               // [n_rows]
+    double *slots;            // [n_slots]
+    double *block_part;       // [2 * rows_grid]
+    int32_t rows_grid;
+    int32_t team_shift;       // log2 lanes per row
+};
+
+__global__ void __launch_bounds__(256) fe_rows_kernel(const gdmix_fe_rows R, const gdmix_lr_opts o, const FePlan P,
+                                                      const double *x)
+{
+    const int hi = o.has_intercept ? 1 : 0;
+    const int64_t D = R.n_features;
+    const uint32_t T = 1u << P.team_shift, lane = threadIdx.x & 31, t = lane & (T - 1);
+    const int64_t team = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> P.team_shift;
+    const int64_t nteams = ((int64_t)gridDim.x * blockDim.x) >> P.team_shift;
+    const double b0 = hi ? x[D] : 0.0;
+    double value = 0.0, dz_sum = 0.0;
+    const int64_t rounds = (R.n_rows + nteams - 1) / nteams;
+    for (int64_t rd = 0; rd < rounds; rd++) {
+        const int64_t i = rd * nteams + team;
+        const bool act = i < R.n_rows;
+        double z = 0.0;
+        if (act) {
+            const int64_t qs = R.rowptr[i], qe = R.rowptr[i + 1];
+            for (int64_t q = qs + t; q < qe; q += T) z = fma((double)R.val[q], x[R.col[q]], z);
+        }
+        for (uint32_t s = T >> 1; s > 0; s >>= 1) z += __shfl_xor_sync(0xffffffffu, z, s);
+        if (act && t == 0) {
+            z += R.offset ? (double)R.offset[i] : 0.0;
+            z += b0;
+            const double yi = (double)R.label[i], wi = R.weight ? (double)R.weight[i] : 1.0;
+            double dz;
+            if (R.linear_regression) {
+                const double e = yi - z;
+                value = fma(wi * e, e, value);
+                dz = -2.0 * wi * e;
+            } else {
+                const double ex = exp(-fabs(z));
+                value = fma(wi, fmax(z, 0.0) - z * yi + log1p(ex), value);
+                const double inv = 1.0 / (1.0 + ex);
+                dz = wi * ((z >= 0.0 ? inv : ex * inv) - yi);
+            }
+            P.dz[i] = dz;
+            dz_sum += dz;
+        }
+    }
+    value = warp_sum(value);
+    dz_sum = warp_sum(dz_sum);
+    __shared__ double sv[8], sd[8];
+    const int warp = threadIdx.x >> 5;
+    if (lane == 0) { sv[warp] = value; sd[warp] = dz_sum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0, dsum = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { v += sv[w]; dsum += sd[w]; }
+        P.block_part[2 * blockIdx.x] = v;
+        P.block_part[2 * blockIdx.x + 1] = dsum;
+    }
+}
+
+__global__ void __launch_bounds__(256) fe_cols_kernel(const gdmix_fe_rows R, const gdmix_lr_opts o, const FePlan P,
+                                                      const double *x, double *fg)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double l2w = o.l2 / (double)(R.num_workers > 0 ? R.num_workers : 1);
+    for (int64_t it = warp; it < P.n_items; it += nwarps) {
+        const int64_t b = P.item_begin[it], e = P.item_end[it];
+        double s0 = 0.0, s1 = 0.0;
+        int64_t q = b + lane;
+        for (; q + 32 < e; q += 64) {
+            const double a0 = (double)P.val[q] * P.dz[P.row[q]];
+            const double a1 = (double)P.val[q + 32] * P.dz[P.row[q + 32]];
+            s0 += a0; s1 += a1;
+        }
+        if (q < e) s0 = fma((double)P.val[q], P.dz[P.row[q]], s0);
+        const double s = warp_sum(s0 + s1);
+        if (lane == 0) {
+            const int32_t slot = P.item_slot[it];
+            if (slot < 0) {
+                const int32_t c = P.item_col[it];
+                fg[1 + c] = s + l2w * x[c];   // features are always regularised (the intercept is handled apart)
+            } else {
+                P.slots[slot] = s;
+            }
+        }
+    }
+}
+
+// Split columns (slices summed in slice order), then -- CTA 0 -- the objective value and the intercept's gradient
+// from the per-CTA partials of fe_rows_kernel and the L2 term, all in a fixed order.
+__global__ void __launch_bounds__(256) fe_finish_kernel(const gdmix_fe_rows R, const gdmix_lr_opts o, const FePlan P,
+                                                        const double *x, double *fg)
+{
+    const int hi = o.has_intercept ? 1 : 0;
+    const int64_t D = R.n_features;
+    const double l2w = o.l2 / (double)(R.num_workers > 0 ? R.num_workers : 1);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t sidx = tid; sidx < P.n_split; sidx += nth) {
+        double s = 0.0;
+        for (int64_t k = P.split_slot_ptr[sidx]; k < P.split_slot_ptr[sidx + 1]; k++) s += P.slots[k];
+        const int32_t c = P.split_col[sidx];
+        fg[1 + c] = s + l2w * x[c];
+    }
+    if (blockIdx.x != 0) return;
+    __shared__ double sh[3][256];
+    double v = 0.0, dsum = 0.0, sq = 0.0;
+    for (int32_t b = threadIdx.x; b < P.rows_grid; b += 256) { v += P.block_part[2 * b]; dsum += P.block_part[2 * b + 1]; }
+    const int64_t preg = (hi && !o.regularize_bias) ? D : D + hi;
+    for (int64_t j = threadIdx.x; j < preg; j += 256) sq = fma(x[j], x[j], sq);
+    sh[0][threadIdx.x] = v; sh[1][threadIdx.x] = dsum; sh[2][threadIdx.x] = sq;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s)
+            for (int k = 0; k < 3; k++) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        fg[0] = sh[0][0] + 0.5 * l2w * sh[2][0];
+        if (hi) fg[1 + D] = sh[1][0] + (o.regularize_bias ? l2w * x[D] : 0.0);
+    }
+}
+
 __global__ void __launch_bounds__(256) fe_score_kernel(const gdmix_fe_rows R, const int hi, const double *x,
                                                        float *logit, float *logit_pc)
 {

@@ -60,6 +60,7 @@ class FixedEffectSolver:
             self._x_dev = torch.empty(self.n_coef, dtype=torch.float64, device=self.device)
             self._fg_dev = torch.empty(1 + self.n_coef, dtype=torch.float64, device=self.device)
             self._fg_host = torch.empty(1 + self.n_coef, dtype=torch.float64).pin_memory()
+            self.plan = None  # column-major copy + work items, built on the first evaluation
         else:
             self.device = torch.device("cpu") if device is None else device
 
@@ -75,7 +76,9 @@ class FixedEffectSolver:
             fg = fg.cpu().numpy()
             return float(fg[0]), fg[1:].copy()
         self._x_dev.copy_(torch.from_numpy(x), non_blocking=False)
-        capi.fe_loss_grad_device(self.rows, self.opts, self._x_dev, fg=self._fg_dev)
+        if self.plan is None:
+            self.plan = capi.DeviceFePlan(self.rows)
+        capi.fe_loss_grad_device(self.rows, self.opts, self._x_dev, fg=self._fg_dev, plan=self.plan)
         if self.dist and self.world > 1:
             self.dist.all_reduce(self._fg_dev, group=self.group)  # value and gradient in one collective
         self._fg_host.copy_(self._fg_dev, non_blocking=True)

@@ -170,6 +170,35 @@ GDMIX_API int gdmix_re_score(const gdmix_re_batch *batch, const gdmix_lr_opts *o
  * all-reduces fg (NCCL, same stream) and feeds it to the replicated L-BFGS step. */
 GDMIX_API int gdmix_fe_loss_grad(const gdmix_fe_rows *rows, const gdmix_lr_opts *opts, const double *x, double *fg,
                                  void *stream);
+/* The same objective / gradient without atomics, for callers that evaluate many times over one shard (every
+ * L-BFGS run does): the caller supplies, once, the column-major copy of the shard and a list of work items, and
+ * the scratch the passes need.  Three kernels: rows (z, loss, dz), columns (X^T dz by segmented sums), finish.
+ * Every sum has a fixed order (bitwise reproducible), and a feature that owns a large share of the non-zeros
+ * costs no more per non-zero than a rare one.
+ *   colptr[D+1], row[nnz] (ascending inside a column), val[nnz]   the shard sorted by column
+ *   items: one per column that has at most `slice` non-zeros (slot = -1), else one per slice of it
+ *          (slot = index into the slot buffer); split_col / split_slot_ptr list the sliced columns
+ *   scratch: n_rows + n_slots + 2 * rows_grid doubles, rows_grid as returned by gdmix_fe_rows_grid */
+typedef struct gdmix_fe_plan {
+    const int64_t *colptr;
+    const int32_t *row;
+    const float *val;
+    int64_t n_items;
+    const int32_t *item_col;
+    const int64_t *item_begin;
+    const int64_t *item_end;
+    const int32_t *item_slot;
+    int64_t n_split;
+    const int32_t *split_col;
+    const int64_t *split_slot_ptr;
+    int64_t n_slots;
+    double *scratch;
+    int64_t scratch_doubles;
+} gdmix_fe_plan;
+GDMIX_API int gdmix_fe_rows_grid(const gdmix_fe_rows *rows, int32_t *grid);
+GDMIX_API int gdmix_fe_loss_grad_planned(const gdmix_fe_rows *rows, const gdmix_fe_plan *plan,
+                                         const gdmix_lr_opts *opts, const double *x, double *fg, void *stream);
+
 /* Hessian of the logistic loss over this rank's rows at x, X1^T diag(w rho (1-rho)) X1 with the intercept column
  * LAST -- the accumulator H of _scoring_fn (fixed_effect_lr_lbfgs_model.py:271-296; the reference keeps it in
  * fp32, here fp64).  mode GDMIX_VARIANCE_SIMPLE: h[D+hi] = diagonal; GDMIX_VARIANCE_FULL: h[(D+hi)^2] row-major.

@@ -76,3 +76,35 @@ def test_fe_score_matches_definition():
     z = dense @ x[:-1] + x[-1]
     np.testing.assert_allclose(per, z.astype(np.float32), rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(logit, (z + FE_ARR[k + "_off"]).astype(np.float32), rtol=1e-6, atol=1e-6)
+
+
+def test_planned_path_matches_atomic_path_and_is_reproducible():
+    """gdmix_fe_loss_grad_planned (column-major copy, no atomics) vs gdmix_fe_loss_grad on skewed columns, incl.
+    columns long enough to be sliced, empty columns, rows of different lengths, weights/offsets, no intercept."""
+    rng = np.random.default_rng(3)
+    n, D = 30000, 700
+    lens = rng.integers(0, 12, n)
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    nnz = int(rowptr[-1])
+    col = np.minimum((D ** rng.random(nnz) - 1).astype(np.int32), D - 1)
+    col[col == 5] = 6                                   # column 5 stays empty
+    val = rng.standard_normal(nnz).astype(np.float32)
+    y = (rng.random(n) < 0.4).astype(np.float32)
+    w = rng.uniform(0.5, 2.0, n).astype(np.float32)
+    off = rng.standard_normal(n).astype(np.float32)
+    for hi, rb, lin in ((True, True, False), (True, False, False), (False, False, False), (True, True, True)):
+        rows = capi.DeviceFeRows(rowptr, col, val, y, w, off, D, linear_regression=lin, num_workers=2)
+        opts = capi.make_opts(l2=0.7, regularize_bias=rb, has_intercept=hi)
+        x = torch.from_numpy(rng.standard_normal(D + (1 if hi else 0)) * 0.1).cuda()
+        plan = capi.DeviceFePlan(rows, slice_nnz=256)
+        assert plan.n_split > 0
+        a = capi.fe_loss_grad_device(rows, opts, x).cpu().numpy()
+        b = capi.fe_loss_grad_device(rows, opts, x, plan=plan).cpu().numpy()
+        c = capi.fe_loss_grad_device(rows, opts, x, plan=plan).cpu().numpy()
+        np.testing.assert_allclose(b, a, rtol=1e-11, atol=1e-9)
+        np.testing.assert_array_equal(b, c)
+        blk = O.FeBlock(n, D, rowptr, col, val, y, w, off, linear_regression=lin, num_workers=2)
+        oo = O.make_opts(l2=0.7, regularize_bias=rb, has_intercept=hi)
+        f_o, g_o = O.fe_loss_grad(blk, oo, x.cpu().numpy())
+        np.testing.assert_allclose(b[0], f_o, rtol=1e-12)
+        np.testing.assert_allclose(b[1:], g_o, rtol=1e-10, atol=1e-10)
