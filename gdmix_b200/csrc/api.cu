@@ -556,9 +556,8 @@ void fe_rows_geometry(const gdmix_fe_rows *rows, const DeviceInfo &dev, int &gri
     const int64_t avg = rows->n_rows > 0 ? (rows->nnz + rows->n_rows - 1) / rows->n_rows : 1;
     team_shift = 0;
     while (team_shift < 5 && (1 << team_shift) < avg) team_shift++;
-    const int64_t teams_per_cta = 256 >> team_shift;
-    grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows->n_rows + teams_per_cta - 1) / teams_per_cta,
-                                                       (int64_t)dev.sm_count * 8));
+    // a warp owns 32 rows at a time, 8 warps per CTA
+    grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows->n_rows + 255) / 256, (int64_t)dev.sm_count * 8));
 }
 }  // namespace
 
@@ -601,7 +600,7 @@ int gdmix_fe_loss_grad_planned(const gdmix_fe_rows *rows, const gdmix_fe_plan *p
     gdmix::fe_rows_kernel<<<grid, 256, 0, st>>>(*rows, *o, P, x);
     const int cgrid = (int)std::max<int64_t>(1, std::min<int64_t>((pl->n_items + 7) / 8, (int64_t)dev.sm_count * 16));
     gdmix::fe_cols_kernel<<<cgrid, 256, 0, st>>>(*rows, *o, P, x, fg);
-    const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((pl->n_split + 255) / 256, (int64_t)dev.sm_count));
+    const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((pl->n_split + 7) / 8, (int64_t)dev.sm_count * 4));
     gdmix::fe_finish_kernel<<<fgrid, 256, 0, st>>>(*rows, *o, P, x, fg);
     g_launches += 3;
     CUDA_TRY(cudaGetLastError());

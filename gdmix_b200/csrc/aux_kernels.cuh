@@ -180,25 +180,36 @@ struct FePlan {
 __global__ void __launch_bounds__(256) fe_rows_kernel(const gdmix_fe_rows R, const gdmix_lr_opts o, const FePlan P,
                                                       const double *x)
 {
+    // A warp owns 32 consecutive rows at a time.  Step s: each team of T lanes walks one row (coalesced loads,
+    // x gathered through L2), team sums by butterfly, and the row's z is handed to the lane whose index equals
+    // the row's position in the block -- so the loss / dz arithmetic (one exp, one log1p, one division per row)
+    // then runs on 32 rows in 32 lanes instead of on one lane per team.
     const int hi = o.has_intercept ? 1 : 0;
     const int64_t D = R.n_features;
-    const uint32_t T = 1u << P.team_shift, lane = threadIdx.x & 31, t = lane & (T - 1);
-    const int64_t team = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> P.team_shift;
-    const int64_t nteams = ((int64_t)gridDim.x * blockDim.x) >> P.team_shift;
+    const uint32_t ts = (uint32_t)P.team_shift, T = 1u << ts, RS = 32u >> ts;   // lanes per row, rows per step
+    const uint32_t lane = threadIdx.x & 31, t = lane & (T - 1), q = lane >> ts;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const double b0 = hi ? x[D] : 0.0;
     double value = 0.0, dz_sum = 0.0;
-    const int64_t rounds = (R.n_rows + nteams - 1) / nteams;
-    for (int64_t rd = 0; rd < rounds; rd++) {
-        const int64_t i = rd * nteams + team;
-        const bool act = i < R.n_rows;
-        double z = 0.0;
-        if (act) {
-            const int64_t qs = R.rowptr[i], qe = R.rowptr[i + 1];
-            for (int64_t q = qs + t; q < qe; q += T) z = fma((double)R.val[q], x[R.col[q]], z);
+    const int64_t nblocks = (R.n_rows + 31) >> 5;
+    for (int64_t blk = warp; blk < nblocks; blk += nwarps) {
+        const int64_t base = blk << 5;
+        double myz = 0.0;
+        for (uint32_t s = 0; s < T; s++) {
+            const int64_t i = base + s * RS + q;
+            double z = 0.0;
+            if (i < R.n_rows) {
+                const int64_t qs = R.rowptr[i], qe = R.rowptr[i + 1];
+                for (int64_t k = qs + t; k < qe; k += T) z = fma((double)R.val[k], x[R.col[k]], z);
+            }
+            for (uint32_t m = T >> 1; m > 0; m >>= 1) z += __shfl_xor_sync(0xffffffffu, z, m);
+            const double v = __shfl_sync(0xffffffffu, z, (lane & (RS - 1)) << ts);
+            if ((lane >> (5 - ts)) == s) myz = v;   // lane j takes row j = s * RS + (j mod RS)
         }
-        for (uint32_t s = T >> 1; s > 0; s >>= 1) z += __shfl_xor_sync(0xffffffffu, z, s);
-        if (act && t == 0) {
-            z += R.offset ? (double)R.offset[i] : 0.0;
+        const int64_t i = base + lane;
+        if (i < R.n_rows) {
+            double z = myz + (R.offset ? (double)R.offset[i] : 0.0);
             z += b0;
             const double yi = (double)R.label[i], wi = R.weight ? (double)R.weight[i] : 1.0;
             double dz;
@@ -219,8 +230,8 @@ __global__ void __launch_bounds__(256) fe_rows_kernel(const gdmix_fe_rows R, con
     value = warp_sum(value);
     dz_sum = warp_sum(dz_sum);
     __shared__ double sv[8], sd[8];
-    const int warp = threadIdx.x >> 5;
-    if (lane == 0) { sv[warp] = value; sd[warp] = dz_sum; }
+    const int wi_ = threadIdx.x >> 5;
+    if (lane == 0) { sv[wi_] = value; sd[wi_] = dz_sum; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double v = 0.0, dsum = 0.0;
@@ -270,11 +281,16 @@ __global__ void __launch_bounds__(256) fe_finish_kernel(const gdmix_fe_rows R, c
     const double l2w = o.l2 / (double)(R.num_workers > 0 ? R.num_workers : 1);
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t sidx = tid; sidx < P.n_split; sidx += nth) {
-        double s = 0.0;
-        for (int64_t k = P.split_slot_ptr[sidx]; k < P.split_slot_ptr[sidx + 1]; k++) s += P.slots[k];
-        const int32_t c = P.split_col[sidx];
-        fg[1 + c] = s + l2w * x[c];
+    {
+        // a warp per split column: lane-strided partial sums, then a butterfly (fixed order)
+        const uint32_t lane = threadIdx.x & 31;
+        for (int64_t sidx = tid >> 5; sidx < P.n_split; sidx += nth >> 5) {
+            double s = 0.0;
+            for (int64_t k = P.split_slot_ptr[sidx] + lane; k < P.split_slot_ptr[sidx + 1]; k += 32) s += P.slots[k];
+            s = warp_sum(s);
+            const int32_t c = P.split_col[sidx];
+            if (lane == 0) fg[1 + c] = s + l2w * x[c];
+        }
     }
     if (blockIdx.x != 0) return;
     __shared__ double sh[3][256];
