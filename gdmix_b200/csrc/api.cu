@@ -83,6 +83,11 @@ struct RePlan {
     int fgrid = 1;
     gdmix::FastLayout fL;
     size_t off_defer = 0, off_arena = 0;
+    // entities that cannot be staged at all: X stays in global memory (re_solver_kernel<256, MT, true>)
+    int bgrid = 1;
+    uint32_t bsmem = 0;
+    unsigned long long barena_stride = 0;
+    size_t off_defer_b = 0, off_barena = 0;
     // FULL variance pass (re_variance.cuh)
     int vgrid = 0;
     uint32_t vsmem = 0, vsmem_matrix_doubles = 0;
@@ -142,16 +147,20 @@ int plan_fast(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo 
     const char *env_path = getenv("GDMIX_RE_PATH");
     const char *env_ctas = getenv("GDMIX_FAST_CTAS");
     const char *env_cap = getenv("GDMIX_FAST_CAP_STEPS");  // test hook: shrink the sliced-ELL capacity to force deferrals
-    if (env_path && strcmp(env_path, "generic") == 0) return GDMIX_OK;
+    if (env_path && (strcmp(env_path, "generic") == 0 || strcmp(env_path, "big") == 0)) return GDMIX_OK;
     const uint32_t hi = o->has_intercept ? 1u : 0u;
-    const uint32_t D = (uint32_t)b->max_coef - hi, N = (uint32_t)b->max_rows;
-    if (o->m > gdmix::kFastMT || D > 512 || N > gdmix::kFastMaxRows) return GDMIX_OK;
+    if (o->m > gdmix::kFastMT) return GDMIX_OK;
+    // Planned for the batch's largest entity when that is a shape this kernel takes; else for a clamped shape
+    // (the entities beyond it are deferred one by one, the others keep the fast kernel).
+    const uint32_t D_full = (uint32_t)b->max_coef - hi, N_full = (uint32_t)b->max_rows;
+    const uint32_t D = std::min(D_full, 512u), N = std::min(N_full, 4096u);
+    bool clamped = D < D_full || N < N_full;
     int G;
     if (o->threads_per_entity == 32 || o->threads_per_entity == 64 || o->threads_per_entity == 128 ||
         o->threads_per_entity == 256) {
         G = o->threads_per_entity;
     } else {
-        const uint32_t want = std::max((D + 1) / 2, (N + 1) / 2);
+        const uint32_t want = std::max((D + 1) / 2, (std::min(N, 512u) + 1) / 2);
         G = 32;
         while ((uint32_t)G < want && G < 256) G <<= 1;
     }
@@ -168,23 +177,38 @@ int plan_fast(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo 
     // the sliced index stream holds 16-bit absolute shared addresses into xt[] and r[]
     if (kStaticSmem + fl.r + 8u * N > 65536u) return GDMIX_OK;
     const uint32_t nrslab = (N + 31) / 32, ncslab = (D + 31) / 32;
-    const uint32_t ar = (uint32_t)((b->max_nnz + (int64_t)N - 1) / N), ac = D ? (uint32_t)((b->max_nnz + (int64_t)D - 1) / D) : 0;
+    const uint32_t ar = (uint32_t)((b->max_nnz + (int64_t)N_full - 1) / N_full);
+    const uint32_t ac = D_full ? (uint32_t)((b->max_nnz + (int64_t)D_full - 1) / D_full) : 0;
     const uint32_t est = nrslab * ((ar + 3) / 4 + 1) + ncslab * ((ac + 3) / 4 + 1);
-    int k = env_ctas ? std::max(1, std::min(atoi(env_ctas), k_hw)) : k_hw;
-    for (; k >= 1; k--) {
+    auto cap_for = [&](int k) {
         const int64_t budget = (int64_t)(228 * 1024) / k - 1024 - (int64_t)kStaticSmem - 64;
-        int64_t cap = (std::min<int64_t>(budget, (int64_t)dev.smem_optin - kStaticSmem - 64) - (int64_t)fixed) /
-                            (int64_t)gdmix::kStepBytes;
-        if (cap >= (int64_t)est) {
-            if (env_cap) cap = std::max<int64_t>(1, std::min<int64_t>(cap, atoi(env_cap)));
-            pl.fast = 1;
-            pl.fG = G; pl.fEPT = EPT; pl.fctas_per_sm = k;
-            pl.fL = gdmix::fast_layout(N, D, W, (uint32_t)cap);
-            const int64_t want = (int64_t)dev.sm_count * k;
-            pl.fgrid = (int)std::max<int64_t>(1, std::min<int64_t>(want, b->n_entities));
-            return GDMIX_OK;
+        return (std::min<int64_t>(budget, (int64_t)dev.smem_optin - kStaticSmem - 64) - (int64_t)fixed) /
+               (int64_t)gdmix::kStepBytes;
+    };
+    int k = env_ctas ? std::max(1, std::min(atoi(env_ctas), k_hw)) : k_hw;
+    int64_t cap = 0;
+    bool found = false;
+    if (!clamped) {
+        for (; k >= 1; k--) {
+            cap = cap_for(k);
+            if (cap >= (int64_t)est) { found = true; break; }
+            if (env_ctas) break;
         }
-        if (env_ctas) break;
+    }
+    if (!found) {
+        // the largest entity is not one for this kernel: plan for two CTAs per SM and let the big ones defer
+        k = env_ctas ? std::max(1, std::min(atoi(env_ctas), k_hw)) : std::min(2, k_hw);
+        cap = cap_for(k);
+        found = cap >= 8;
+    }
+    if (found) {
+        if (env_cap) cap = std::max<int64_t>(1, std::min<int64_t>(cap, atoi(env_cap)));
+        pl.fast = 1;
+        pl.fG = G; pl.fEPT = EPT; pl.fctas_per_sm = k;
+        pl.fL = gdmix::fast_layout(N, D, W, (uint32_t)cap);
+        const int64_t want = (int64_t)dev.sm_count * k;
+        pl.fgrid = (int)std::max<int64_t>(1, std::min<int64_t>(want, b->n_entities));
+        return GDMIX_OK;
     }
     if (env_path && strcmp(env_path, "fast") == 0)
         return fail(GDMIX_ERR_TOO_LARGE, "GDMIX_RE_PATH=fast but the batch shape (%u rows, %d nnz, %u features) "
@@ -197,21 +221,27 @@ int plan_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &d
     if (b->max_rows <= 0 || b->max_coef <= 0 || b->max_nnz < 0)
         return fail(GDMIX_ERR_INVALID, "gdmix_re_batch.max_rows/max_nnz/max_coef must be set (got %d/%d/%d)",
                     b->max_rows, b->max_nnz, b->max_coef);
-    if (b->max_rows >= 65535 || b->max_coef >= 65535)
-        return fail(GDMIX_ERR_TOO_LARGE, "an entity has %d rows / %d coefficients; the on-chip index is 16 bit",
-                    b->max_rows, b->max_coef);
     if (o->m < 0 || o->m > GDMIX_MAX_M) return fail(GDMIX_ERR_INVALID, "m = %d outside [0, %d]", o->m, GDMIX_MAX_M);
     const uint32_t hi = o->has_intercept ? 1u : 0u;
     if ((uint32_t)b->max_coef < hi) return fail(GDMIX_ERR_INVALID, "max_coef < has_intercept");
     pl.MT = (o->m <= 10) ? 10 : 32;
-    const gdmix::ReLayout L = gdmix::re_layout((uint32_t)b->max_rows, (uint32_t)b->max_nnz,
-                                               (uint32_t)b->max_coef - hi, (uint32_t)b->max_coef, (uint32_t)o->m,
-                                               (uint32_t)pl.MT);
     const uint32_t budget = (uint32_t)dev.smem_optin - kStaticSmem;
-    if (L.fixed_bytes > budget)
-        return fail(GDMIX_ERR_TOO_LARGE,
-                    "largest entity (%d rows, %d nnz, %d coef) needs %u B of shared memory, device offers %u B",
-                    b->max_rows, b->max_nnz, b->max_coef, L.fixed_bytes, budget);
+    // The staged kernels are planned for the batch's largest entity when that fits on chip.  When it does not
+    // (or its rows / features overflow the 16-bit on-chip indices), they are planned for half an SM's shared
+    // memory and whatever entity does not fit is deferred, one by one, to the kernel that leaves X in global
+    // memory -- one huge entity must not cost the other million their residency.
+    gdmix::ReLayout L = gdmix::re_layout((uint32_t)std::min(b->max_rows, 65534), (uint32_t)b->max_nnz,
+                                         (uint32_t)std::min<int64_t>(b->max_coef - (int)hi, 65534),
+                                         (uint32_t)std::min(b->max_coef, 65534), (uint32_t)o->m, (uint32_t)pl.MT);
+    const bool max_fits = b->max_rows < 65535 && b->max_coef - (int)hi < 65535 && L.fixed_bytes <= budget;
+    if (!max_fits) {
+        L.fixed_bytes = std::min<uint32_t>(budget, (228u * 1024u) / 2 - 1024u - kStaticSmem);
+        L.total_bytes = 0xffffffffu;  // history never on chip in this case
+    }
+    {
+        const char *env_path = getenv("GDMIX_RE_PATH");  // test hook: "big" sends every entity to the global-X kernel
+        if (env_path && strcmp(env_path, "big") == 0) { L.fixed_bytes = 0; L.total_bytes = 0xffffffffu; }
+    }
     pl.G = choose_group(b, o);
     // Where the (S, Y) history lives: on chip when that does not cost residency, else in a per-CTA global
     // arena that stays L2-resident (444 CTAs x 41 KB at the C1 shape).  GDMIX_HIST_GLOBAL=0/1 overrides.
@@ -232,9 +262,20 @@ int plan_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &d
     pl.grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, b->n_entities));
     int rc = plan_fast(b, o, dev, pl);
     if (rc) return rc;
+    const size_t list_bytes = ((size_t)b->n_entities * 4 + 255) & ~(size_t)255;
     pl.off_defer = kQueueBytes;
-    pl.off_arena = pl.off_defer + (pl.fast ? (((size_t)b->n_entities * 4 + 255) & ~(size_t)255) : 0);
-    pl.workspace = pl.off_arena + (size_t)pl.arena_stride * (size_t)want;
+    pl.off_defer_b = pl.off_defer + (pl.fast ? list_bytes : 0);
+    pl.off_arena = pl.off_defer_b + list_bytes;
+    pl.off_barena = pl.off_arena + (size_t)pl.arena_stride * (size_t)want;
+    // global-X kernel: 256 threads, vectors + per-warp gradient copies on chip, history in its own arena
+    {
+        const uint32_t need = gdmix::big_layout_bytes((uint32_t)b->max_coef, (uint32_t)b->max_coef - hi, 8u, (uint32_t)pl.MT);
+        pl.bsmem = std::min(need, budget);   // entities with more coefficients than fit get GDMIX_ERR_TOO_LARGE
+        const int per_sm = std::max(1, std::min(4, (int)((228u * 1024u) / (pl.bsmem + kStaticSmem + 1024u))));
+        pl.bgrid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)dev.sm_count * per_sm, b->n_entities));
+        pl.barena_stride = (unsigned long long)gdmix::align16(16u * (uint32_t)o->m * (uint32_t)b->max_coef);
+    }
+    pl.workspace = pl.off_barena + (size_t)pl.barena_stride * (size_t)pl.bgrid;
     if (o->variance_mode == GDMIX_VARIANCE_FULL) {
         const size_t P = (size_t)b->max_coef;
         const size_t vec_bytes = 2 * 8 * P;
@@ -277,6 +318,21 @@ int launch_fast_t(const gdmix::FastArgs &fa, const RePlan &pl, cudaStream_t st)
         configured.store(1);
     }
     gdmix::re_fast_kernel<G, EPT><<<pl.fgrid, G, pl.fL.total_bytes, st>>>(fa);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
+template <int MT>
+int launch_big_t(const gdmix::ReArgs &args, const RePlan &pl, cudaStream_t st)
+{
+    static std::atomic<int> configured{0};
+    if (!configured.load()) {
+        CUDA_TRY(cudaFuncSetAttribute(gdmix::re_solver_kernel<256, MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024 - (int)kStaticSmem));
+        configured.store(1);
+    }
+    gdmix::re_solver_kernel<256, MT, true><<<pl.bgrid, 256, pl.bsmem, st>>>(args);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return GDMIX_OK;
@@ -351,6 +407,9 @@ int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const d
         a.todo = fa.defer_list;
         a.todo_count = fa.defer_count;
     }
+    // whatever the staged kernels cannot hold goes to list B
+    a.defer_list = (int32_t *)((unsigned char *)workspace + pl.off_defer_b);
+    a.defer_count = (int32_t *)workspace + 5;
     if (pl.MT == 10) {
         switch (pl.G) {
         case 32: rc = launch_re_t<32, 10>(a, pl, st); break;
@@ -365,6 +424,20 @@ int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const d
         case 128: rc = launch_re_t<128, 32>(a, pl, st); break;
         default: rc = launch_re_t<256, 32>(a, pl, st); break;
         }
+    }
+    if (rc) return rc;
+    {
+        // list B: X stays in global memory
+        gdmix::ReArgs g2 = a;
+        g2.queue = (int32_t *)workspace + 4;
+        g2.todo = a.defer_list;
+        g2.todo_count = a.defer_count;
+        g2.defer_list = nullptr; g2.defer_count = nullptr;
+        g2.arena = (unsigned char *)workspace + pl.off_barena;
+        g2.arena_stride = pl.barena_stride;
+        g2.hist_global = 1;
+        g2.smem_bytes = pl.bsmem;
+        rc = (pl.MT == 10) ? launch_big_t<10>(g2, pl, st) : launch_big_t<32>(g2, pl, st);
     }
     if (rc || !full_var) return rc;
     // FULL variance at the un-thresholded optimum, then the threshold (re_variance.cuh)
@@ -703,7 +776,7 @@ int gdmix_re_fit_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const do
             mz = std::max<int64_t>(mz, hb->rowptr[b2] - hb->rowptr[a]);
             mc = std::max<int64_t>(mc, hb->theta_ptr[e + 1] - hb->theta_ptr[e]);
         }
-        if (mr >= 65535 || mc >= 65535 || mz >= (1ll << 30))
+        if (mr >= (1ll << 31) || mc >= (1ll << 31) || mz >= (1ll << 31))
             return fail(GDMIX_ERR_TOO_LARGE, "an entity has %lld rows / %lld nnz / %lld coefficients",
                         (long long)mr, (long long)mz, (long long)mc);
         db.max_rows = (int32_t)mr; db.max_nnz = (int32_t)mz; db.max_coef = (int32_t)mc;

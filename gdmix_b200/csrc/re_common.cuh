@@ -51,6 +51,8 @@ struct ReArgs {
     int32_t *queue;             // work counter, zeroed before launch
     const int32_t *todo;        // optional: solve entities todo[0 .. *todo_count) instead of 0 .. n_entities
     const int32_t *todo_count;
+    int32_t *defer_list;        // optional: entities this kernel cannot hold on chip go here instead of failing
+    int32_t *defer_count;
     unsigned char *arena;       // per-CTA global scratch for history that does not fit on chip
     unsigned long long arena_stride;
     int32_t mode;

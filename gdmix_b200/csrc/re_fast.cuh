@@ -47,6 +47,7 @@ struct FastLayout {
     uint32_t sell_val, sell_idx;
     uint32_t cap_steps;
     uint32_t total_bytes;
+    uint32_t max_n, max_d;   // rows / local features the arrays above are sized for
 };
 
 __host__ __device__ inline uint32_t fast_fixed_bytes(uint32_t N, uint32_t D, uint32_t W, FastLayout *out)
@@ -80,6 +81,7 @@ __host__ __device__ inline uint32_t fast_fixed_bytes(uint32_t N, uint32_t D, uin
     L.cbase = o; o += align16(4 * (D32 / 32 + 2));
     L.sell_val = o;
     L.sell_idx = 0; L.cap_steps = 0; L.total_bytes = o;
+    L.max_n = N; L.max_d = D;
     if (out) *out = L;
     return o;
 }
@@ -522,7 +524,7 @@ __global__ void __launch_bounds__(G, (G <= 128) ? 384 / G : 1) re_fast_kernel(co
                 if (tid == 0 && a.status) a.status[e] = GDMIX_ERR_TOO_LARGE;
                 continue;
             }
-            if (n64 <= (int64_t)kFastMaxRows && (int64_t)E.d <= (int64_t)G * EPT && a.o.m <= MT)
+            if (n64 <= (int64_t)L.max_n && E.d <= L.max_d && (int64_t)E.d <= (int64_t)G * EPT && a.o.m <= MT)
                 st = fast_stage<G>(a, L, smem, r0, q0, E.n, E.d, &s_flag);
         }
         if (st == 1) {

@@ -24,7 +24,10 @@
 
 namespace gdmix {
 
-template <int G, int MT>
+// BIG = false: the entity is staged in shared memory (re_passes.cuh, stage_entity).  BIG = true: the entity
+// does not fit on chip; X stays in global memory and every evaluation sweeps it (evaluate_big), the solver
+// vectors live in shared memory and the (S, Y) history in the per-CTA global arena.  Same solver either way.
+template <int G, int MT, bool BIG = false>
 __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -54,42 +57,82 @@ __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
         const int64_t n64 = r1 - r0, nnz64 = q1 - q0, p64 = a.b.theta_ptr[e + 1] - t0;
         const uint32_t n = (uint32_t)n64, nnz = (uint32_t)nnz64, p = (uint32_t)p64, d = p - hi;
 
-        const ReLayout L = re_layout(n, nnz, d, p, (uint32_t)m, (uint32_t)MT);
-        const bool ok = n64 >= 1 && n64 < 65535 && p64 >= 1 && p64 >= (int64_t)hi && (p64 - hi) < 65535 &&
-                        nnz64 >= 0 && nnz64 < (1ll << 30) && L.fixed_bytes <= a.smem_bytes;
-        if (!ok) {
-            if (tid == 0 && a.status) a.status[e] = GDMIX_ERR_TOO_LARGE;
-            continue;
-        }
-        double *xa = (double *)(smem + L.xa), *xb = (double *)(smem + L.xb);
-        double *ga = (double *)(smem + L.ga), *gb = (double *)(smem + L.gb);
-        double *dv = (double *)(smem + L.dv);
-        double *rres = (double *)(smem + L.r);
-        float *sy = (float *)(smem + L.y), *sw = (float *)(smem + L.w), *soff = (float *)(smem + L.off);
-        uint32_t *rowst = (uint32_t *)(smem + L.rowst), *colst = (uint32_t *)(smem + L.colst);
-        float *csr_val = (float *)(smem + L.csr_val), *csc_val = (float *)(smem + L.csc_val);
-        uint16_t *csr_col = (uint16_t *)(smem + L.csr_col), *csc_row = (uint16_t *)(smem + L.csc_row);
-        double *dense = (double *)(smem + L.dense), *part = (double *)(smem + L.part);
-        double *hist = (L.total_bytes <= a.smem_bytes && !a.hist_global)
-                           ? (double *)(smem + L.hist)
-                           : (double *)(a.arena + (unsigned long long)blockIdx.x * a.arena_stride);
-        double *Sh = hist, *Yh = hist + (size_t)m * p;
-
-        // W*d staging counters alias the solver vectors, which are initialised afterwards
-        if (!stage_entity<G>(a, r0, q0, n, d, sy, sw, soff, rowst, colst, csr_val, csr_col, csc_val, csc_row,
-                             (uint32_t *)xa, (uint32_t *)red, &s_bad)) {
+        const bool shape_ok = n64 >= 1 && p64 >= 1 && p64 >= (int64_t)hi && nnz64 >= 0 && n64 < (1ll << 31) &&
+                              p64 < (1ll << 31);
+        if (!shape_ok) {
             if (tid == 0 && a.status) a.status[e] = GDMIX_ERR_INVALID;
             continue;
         }
-
+        double *xa, *xb, *ga, *gb, *dv, *dense, *part, *Sh, *Yh;
+        double *rres = nullptr;
+        float *sw = nullptr, *soff = nullptr, *csr_val = nullptr, *csc_val = nullptr;
+        uint32_t *rowst = nullptr, *colst = nullptr;
+        uint16_t *csr_col = nullptr, *csc_row = nullptr;
         Staged S;
-        S.n = n; S.d = d; S.p = p; S.nnz = nnz; S.hi = hi;
-        S.trs = team_shift(G, n); S.tr = 1u << S.trs;
-        S.tcs = team_shift(G, d); S.tc = 1u << S.tcs;
-        S.y = sy; S.w = sw; S.off = soff; S.rowst = rowst; S.colst = colst;
-        S.csr_val = (const float2 *)csr_val; S.csc_val = (const float2 *)csc_val;
-        S.csr_col = (const ushort2 *)csr_col; S.csc_row = (const ushort2 *)csc_row;
-        S.r = rres; S.inv_n = 1.0 / (double)n; S.l2 = a.o.l2; S.reg_bias = a.o.regularize_bias;
+        BigEntity B;
+        if constexpr (!BIG) {
+            const ReLayout L = re_layout(n, nnz, d, p, (uint32_t)m, (uint32_t)MT);
+            const bool ok = n64 < 65535 && (p64 - hi) < 65535 && nnz64 < (1ll << 30) && L.fixed_bytes <= a.smem_bytes;
+            if (!ok) {
+                // too large to stage: hand it to the kernel that leaves X in global memory
+                if (tid == 0) {
+                    if (a.defer_list) a.defer_list[atomicAdd(a.defer_count, 1)] = (int32_t)e;
+                    else if (a.status) a.status[e] = GDMIX_ERR_TOO_LARGE;
+                }
+                continue;
+            }
+            xa = (double *)(smem + L.xa); xb = (double *)(smem + L.xb);
+            ga = (double *)(smem + L.ga); gb = (double *)(smem + L.gb);
+            dv = (double *)(smem + L.dv);
+            rres = (double *)(smem + L.r);
+            float *sy = (float *)(smem + L.y);
+            sw = (float *)(smem + L.w); soff = (float *)(smem + L.off);
+            rowst = (uint32_t *)(smem + L.rowst); colst = (uint32_t *)(smem + L.colst);
+            csr_val = (float *)(smem + L.csr_val); csc_val = (float *)(smem + L.csc_val);
+            csr_col = (uint16_t *)(smem + L.csr_col); csc_row = (uint16_t *)(smem + L.csc_row);
+            dense = (double *)(smem + L.dense); part = (double *)(smem + L.part);
+            double *hist = (L.total_bytes <= a.smem_bytes && !a.hist_global)
+                               ? (double *)(smem + L.hist)
+                               : (double *)(a.arena + (unsigned long long)blockIdx.x * a.arena_stride);
+            Sh = hist; Yh = hist + (size_t)m * p;
+
+            // W*d staging counters alias the solver vectors, which are initialised afterwards
+            if (!stage_entity<G>(a, r0, q0, n, d, sy, sw, soff, rowst, colst, csr_val, csr_col, csc_val, csc_row,
+                                 (uint32_t *)xa, (uint32_t *)red, &s_bad)) {
+                if (tid == 0 && a.status) a.status[e] = GDMIX_ERR_INVALID;
+                continue;
+            }
+            S.n = n; S.d = d; S.p = p; S.nnz = nnz; S.hi = hi;
+            S.trs = team_shift(G, n); S.tr = 1u << S.trs;
+            S.tcs = team_shift(G, d); S.tc = 1u << S.tcs;
+            S.y = sy; S.w = sw; S.off = soff; S.rowst = rowst; S.colst = colst;
+            S.csr_val = (const float2 *)csr_val; S.csc_val = (const float2 *)csc_val;
+            S.csr_col = (const ushort2 *)csr_col; S.csc_row = (const ushort2 *)csc_row;
+            S.r = rres; S.inv_n = 1.0 / (double)n; S.l2 = a.o.l2; S.reg_bias = a.o.regularize_bias;
+        } else {
+            constexpr uint32_t W = G / 32;
+            if (big_layout_bytes(p, d, W, (uint32_t)MT) > a.smem_bytes) {
+                if (tid == 0 && a.status) a.status[e] = GDMIX_ERR_TOO_LARGE;  // thousands of local features AND unstageable
+                continue;
+            }
+            uint32_t o = 0;
+            xa = (double *)(smem + o); o += align16(8 * p);
+            xb = (double *)(smem + o); o += align16(8 * p);
+            ga = (double *)(smem + o); o += align16(8 * p);
+            gb = (double *)(smem + o); o += align16(8 * p);
+            dv = (double *)(smem + o); o += align16(8 * p);
+            B.gw = (double *)(smem + o); o += align16(8 * W * d);
+            dense = (double *)(smem + o); o += align16(8 * dense_doubles((uint32_t)MT));
+            part = (double *)(smem + o);
+            double *hist = (double *)(a.arena + (unsigned long long)blockIdx.x * a.arena_stride);
+            Sh = hist; Yh = hist + (size_t)m * p;
+            B.r0 = r0; B.n = n; B.d = d; B.p = p; B.hi = hi;
+            B.inv_n = 1.0 / (double)n; B.l2 = a.o.l2; B.reg_bias = a.o.regularize_bias;
+        }
+        auto eval = [&](const double *xt_, const double *dv_, double *gt_, double &f_, double &gd_, double &gm_) {
+            if constexpr (BIG) evaluate_big<G>(a, B, xt_, dv_, gt_, red, flip, &s_bad, f_, gd_, gm_);
+            else evaluate<G>(S, xt_, dv_, gt_, red, flip, f_, gd_, gm_);
+        };
 
         double *x = xa, *xt = xb, *g = ga, *gt = gb;
         for (uint32_t j = tid; j < p; j += G) {
@@ -101,8 +144,14 @@ __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
         group_sync<G>();
 
         double f, gd, gmax;
-        evaluate<G>(S, x, dv, g, red, flip, f, gd, gmax);
+        eval(x, dv, g, f, gd, gmax);
         int nfev = 1, iter = 0, status = GDMIX_SOLVE_CONVERGED;
+        if constexpr (BIG) {
+            if (s_bad) {  // a column index outside the entity's feature range (found by the first sweep)
+                if (tid == 0 && a.status) a.status[e] = GDMIX_ERR_INVALID;
+                continue;
+            }
+        }
 
         if (a.mode == kModeLossGrad) {
             for (uint32_t j = tid; j < p; j += G) a.g_out[t0 + j] = g[j];
@@ -144,7 +193,7 @@ __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
                 if (iback >= a.o.max_ls) break;
                 for (uint32_t j = tid; j < p; j += G) xt[j] = fma(stp, dv[j], x[j]);
                 group_sync<G>();
-                evaluate<G>(S, xt, dv, gt, red, flip, f, gd, gmax_t);
+                eval(xt, dv, gt, f, gd, gmax_t);
                 nfev++;
             }
             if (info != 0 || iback >= a.o.max_ls) {
@@ -194,7 +243,12 @@ __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
             if (a.nfev) a.nfev[e] = nfev;
             if (a.status) a.status[e] = status;
         }
-        if (a.var_out && a.o.variance_mode == GDMIX_VARIANCE_SIMPLE) {
+        if constexpr (BIG) {
+            if (a.var_out && a.o.variance_mode == GDMIX_VARIANCE_SIMPLE) {
+                group_sync<G>();
+                variance_simple_big<G>(a, B, x, a.var_out + t0, red, flip);
+            }
+        } else if (a.var_out && a.o.variance_mode == GDMIX_VARIANCE_SIMPLE) {
             // var_j = 1 / (sum_i x_ij^2 rho_i (1-rho_i) w_i + l2 [j regularised] + 1e-12)
             // (binary_logistic_regression.py:171-177), evaluated at the un-thresholded optimum
             const double b0 = hi ? x[0] : 0.0;

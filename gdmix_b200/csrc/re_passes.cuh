@@ -309,4 +309,150 @@ __device__ __forceinline__ void evaluate(const Staged &S, const double *xt, cons
     gmax = gmp;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Entities too large to stage: X stays in global memory (L2 / HBM) and is swept twice per evaluation.
+// A warp owns 32 consecutive rows at a time: sweep 1 gives every lane the z of "its" row (lanes walk one row
+// at a time, coalesced), the loss / residual arithmetic then runs lane-parallel, and sweep 2 folds r_i * x_i
+// into the warp's PRIVATE copy of X^T r in shared memory, row after row -- so the sum has a fixed order (only a
+// column repeated inside one row makes two lanes meet, hence the atomic).  The copies are added in warp order.
+// ---------------------------------------------------------------------------------------------------------
+struct BigEntity {
+    int64_t r0;
+    uint32_t n, d, p, hi;
+    double *gw;       // [W][d] per-warp copies of X^T r
+    double inv_n, l2;
+    int reg_bias;
+};
+
+__host__ __device__ inline uint32_t big_layout_bytes(uint32_t p, uint32_t d, uint32_t W, uint32_t mt)
+{
+    return 5u * align16(8 * p) + align16(8 * W * d) + align16(8 * dense_doubles(mt)) +
+           align16(8 * kMaxWarps * (2 * mt + 2));
+}
+
+template <int G>
+__device__ __forceinline__ void evaluate_big(const ReArgs &a, const BigEntity &B, const double *xt, const double *dv,
+                                             double *gt, double *red, int &flip, unsigned *s_bad, double &f,
+                                             double &gd, double &gmax)
+{
+    constexpr uint32_t W = G / 32;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *gw = B.gw + (size_t)warp * B.d;
+    for (uint32_t j = lane; j < B.d; j += 32) gw[j] = 0.0;
+    __syncwarp();
+    const double b0 = B.hi ? xt[0] : 0.0;
+    const double *xf = xt + B.hi;
+    double fs = 0.0, rs = 0.0;
+    unsigned bad = 0;
+    const uint32_t nblk = (B.n + 31u) >> 5;
+    for (uint32_t blk = warp; blk < nblk; blk += W) {
+        const uint32_t base = blk << 5, cnt = min(32u, B.n - base);
+        double myz = 0.0;
+        for (uint32_t s = 0; s < cnt; s++) {
+            const int64_t gi = B.r0 + base + s;
+            const int64_t qs = a.b.rowptr[gi], qe = a.b.rowptr[gi + 1];
+            double z = 0.0;
+            for (int64_t k = qs + lane; k < qe; k += 32) {
+                const uint32_t c = (uint32_t)a.b.col[k];
+                if (c < B.d) z = fma((double)a.b.val[k], xf[c], z); else bad = 1;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(kFull, z, o);
+            if (lane == s) myz = z;
+        }
+        double ri = 0.0;
+        if (lane < cnt) {
+            const int64_t gi = B.r0 + base + lane;
+            const double z = (myz + b0) + (a.b.offset ? (double)a.b.offset[gi] : 0.0);
+            const double yi = (double)a.b.label[gi], wi = a.b.weight ? (double)a.b.weight[gi] : 1.0;
+            const double e = exp(-fabs(z));
+            const double ce = fmax(z, 0.0) - z * yi + log(1.0 + e);
+            fs = fma(wi, ce, fs);
+            const double inv = 1.0 / (1.0 + e);
+            const double sig = (z >= 0.0) ? inv : e * inv;
+            ri = wi * (sig - yi);
+            rs += ri;
+        }
+        for (uint32_t s = 0; s < cnt; s++) {
+            const double rv = __shfl_sync(kFull, ri, s);
+            const int64_t gi = B.r0 + base + s;
+            const int64_t qs = a.b.rowptr[gi], qe = a.b.rowptr[gi + 1];
+            for (int64_t k = qs + lane; k < qe; k += 32) {
+                const uint32_t c = (uint32_t)a.b.col[k];
+                if (c < B.d) atomicAdd(&gw[c], (double)a.b.val[k] * rv);
+            }
+            __syncwarp();
+        }
+    }
+    if (bad) atomicOr(s_bad, 1u);
+    double sq = 0.0;
+    for (uint32_t jj = tid; jj < B.p; jj += G) {
+        if (B.hi && jj == 0 && !B.reg_bias) continue;
+        sq = fma(xt[jj], xt[jj], sq);
+    }
+    double part[3] = {fs, rs, sq};
+    group_sum<G, 3>(part, red, flip);  // its barrier also completes every warp's copy
+    if (G == 32) __syncwarp();
+    f = (part[0] + 0.5 * B.l2 * part[2]) * B.inv_n;
+    double gdp = 0.0, gmp = 0.0;
+    for (uint32_t c = tid; c < B.d; c += G) {
+        double acc = 0.0;
+        for (uint32_t w2 = 0; w2 < W; w2++) acc += B.gw[(size_t)w2 * B.d + c];
+        const uint32_t j = c + B.hi;
+        const double gj = (acc + B.l2 * xt[j]) * B.inv_n;
+        gt[j] = gj;
+        gdp = fma(gj, dv[j], gdp);
+        gmp = fmax(gmp, fabs(gj));
+    }
+    if (B.hi && tid == G - 1) {
+        const double gj = (part[1] + (B.reg_bias ? B.l2 * xt[0] : 0.0)) * B.inv_n;
+        gt[0] = gj;
+        gdp = fma(gj, dv[0], gdp);
+        gmp = fmax(gmp, fabs(gj));
+    }
+    group_sum_max<G>(gdp, gmp, red, flip);
+    gd = gdp;
+    gmax = gmp;
+}
+
+// SIMPLE variance for the same entities: var_j = 1 / (sum_i x_ij^2 rho_i (1 - rho_i) w_i + l2 [j regularised] + 1e-12)
+template <int G>
+__device__ __forceinline__ void variance_simple_big(const ReArgs &a, const BigEntity &B, const double *x,
+                                                    double *var_out, double *red, int &flip)
+{
+    constexpr uint32_t W = G / 32;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *gw = B.gw + (size_t)warp * B.d;
+    for (uint32_t j = lane; j < B.d; j += 32) gw[j] = 0.0;
+    __syncwarp();
+    const double b0 = B.hi ? x[0] : 0.0;
+    const double *xf = x + B.hi;
+    double dsum[1] = {0.0};
+    for (uint32_t i = warp; i < B.n; i += W) {
+        const int64_t gi = B.r0 + i;
+        const int64_t qs = a.b.rowptr[gi], qe = a.b.rowptr[gi + 1];
+        double z = 0.0;
+        for (int64_t k = qs + lane; k < qe; k += 32) z = fma((double)a.b.val[k], xf[a.b.col[k]], z);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(kFull, z, o);
+        z = (z + b0) + (a.b.offset ? (double)a.b.offset[gi] : 0.0);
+        const double rho = 1.0 / (1.0 + exp(-z));
+        const double di = rho * (1.0 - rho) * (a.b.weight ? (double)a.b.weight[gi] : 1.0);
+        for (int64_t k = qs + lane; k < qe; k += 32) {
+            const double v = (double)a.b.val[k];
+            atomicAdd(&gw[a.b.col[k]], v * v * di);
+        }
+        if (lane == 0) dsum[0] += di;
+        __syncwarp();
+    }
+    group_sum<G, 1>(dsum, red, flip);
+    if (G == 32) __syncwarp();
+    for (uint32_t c = tid; c < B.d; c += G) {
+        double h = 0.0;
+        for (uint32_t w2 = 0; w2 < W; w2++) h += B.gw[(size_t)w2 * B.d + c];
+        var_out[B.hi + c] = 1.0 / ((h + B.l2) + 1.0e-12);
+    }
+    if (B.hi && tid == 0) var_out[0] = 1.0 / ((dsum[0] + (B.reg_bias ? B.l2 : 0.0)) + 1.0e-12);
+}
+
 }  // namespace gdmix

@@ -18,12 +18,13 @@ from tests.golden_util import is_pinned, load_re  # noqa: E402
 REL_TOL = 1e-5  # north_star tolerance
 
 
-@pytest.fixture(autouse=True, params=["auto", "generic"])
+@pytest.fixture(autouse=True, params=["auto", "generic", "big"])
 def re_path(request, monkeypatch):
-    """Every test runs twice: through the planner's choice (the sliced-ELL fast kernel when the batch
-    qualifies) and through the general kernel alone."""
-    if request.param == "generic":
-        monkeypatch.setenv("GDMIX_RE_PATH", "generic")
+    """Every test runs three times: through the planner's choice (the sliced-ELL fast kernel when the batch
+    qualifies), through the general staged kernel alone, and through the kernel that leaves X in global memory
+    (the one entities too large for the chip take)."""
+    if request.param != "auto":
+        monkeypatch.setenv("GDMIX_RE_PATH", request.param)
     else:
         monkeypatch.delenv("GDMIX_RE_PATH", raising=False)
     return request.param
@@ -215,7 +216,7 @@ def test_history_sizes_match_oracle(m):
 def test_deferred_entities_take_the_general_kernel(monkeypatch, re_path):
     """Entities whose sliced form does not fit the fast kernel's shared memory are drained by the general
     kernel from the deferral list: same answers either way."""
-    if re_path == "generic":
+    if re_path != "auto":
         pytest.skip("fast path only")
     hb = make_batch(300, 64, 64, 16, seed=31, ragged=True)
     opts = capi.make_opts(l2=1.0)
@@ -283,3 +284,52 @@ def test_golden_variances_match_reference():
                                            ARR[c["key"] + suffix], rtol=2e-6, err_msg=c["name"] + suffix)
                 checked += 1
     assert checked > 50
+
+
+def test_oversized_entities_are_solved_not_rejected(re_path):
+    """One entity with 200k non-zeros (more than the chip holds) and one with 70 000 rows (more than the 16-bit
+    on-chip row index) in a batch of ordinary ones: nobody is rejected, the ordinary ones keep their kernel."""
+    if re_path != "auto":
+        pytest.skip("planner's choice only")
+    small = make_batch(60, 48, 40, 8, seed=41, weights=True)
+    rng = np.random.default_rng(9)
+
+    def entity(n, d, k):
+        col = np.sort(np.stack([rng.choice(d, k, replace=False) for _ in range(n)]), axis=1).astype(np.int32)
+        val = rng.standard_normal((n, k)).astype(np.float32)
+        th = rng.standard_normal(d + 1) * 0.3
+        z = (val * th[1 + col]).sum(1) + th[0]
+        y = (rng.random(n) < 1 / (1 + np.exp(-z))).astype(np.float32)
+        return col.reshape(-1), val.reshape(-1), y, n, k
+
+    parts = [entity(3200, 40, 40 - 1), entity(70000, 40, 3)]
+    ent = small.ent_rowptr.tolist()
+    rowptr = small.rowptr.tolist()
+    cols, vals, ys = [small.col], [small.val], [small.label]
+    ws, offs = [small.weight], [small.offset]
+    tptr = small.theta_ptr.tolist()
+    for col, val, y, n, k in parts:
+        rowptr.extend((rowptr[-1] + k * np.arange(1, n + 1)).tolist())
+        ent.append(ent[-1] + n)
+        cols.append(col); vals.append(val); ys.append(y)
+        ws.append(np.ones(n, np.float32)); offs.append(np.zeros(n, np.float32))
+        tptr.append(tptr[-1] + 41)
+    hb = capi.HostBatch(np.array(ent), np.array(rowptr), np.concatenate(cols), np.concatenate(vals),
+                        np.concatenate(ys), np.concatenate(ws), np.concatenate(offs), np.array(tptr))
+    opts = capi.make_opts(l2=1.0, variance_mode=capi.VARIANCE_SIMPLE)
+    out = capi.re_fit_host(hb, opts, want_variance=True)
+    assert capi.last_plan()["fast"] == 1
+    assert (out["status"] >= 0).all()
+    th_o, f_o, nit_o, nfev_o, st_o = O.re_fit_batch(_oracle_batch(hb), _oracle_opts(opts))
+    rel = _rel_per_entity(out["theta"], th_o, hb.theta_ptr)
+    assert rel.max() <= REL_TOL, rel
+    np.testing.assert_array_equal(out["nit"][:60], nit_o[:60])
+    assert abs(int(out["nit"][60]) - int(nit_o[60])) <= 1 and abs(int(out["nit"][61]) - int(nit_o[61])) <= 1
+    ob, oo = _oracle_batch(hb), _oracle_opts(opts)
+    for e in (60, 61):
+        r0, r1 = hb.ent_rowptr[e], hb.ent_rowptr[e + 1]
+        q0, q1 = hb.rowptr[r0], hb.rowptr[r1]
+        blk = O.EntityBlock(r1 - r0, 40, hb.rowptr[r0:r1 + 1] - q0, hb.col[q0:q1], hb.val[q0:q1], hb.label[r0:r1],
+                            ob["w"][r0:r1], ob["off"][r0:r1])
+        np.testing.assert_allclose(out["variance"][hb.theta_ptr[e]:hb.theta_ptr[e + 1]],
+                                   O.re_variance(blk, oo, th_o[hb.theta_ptr[e]:hb.theta_ptr[e + 1]], "simple"), rtol=1e-6)
