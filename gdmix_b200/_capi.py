@@ -28,7 +28,9 @@ SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_w
            "gdmix_fe_hessian", "gdmix_fe_rows_grid", "gdmix_fe_loss_grad_planned",
            "gdmix_re_fit_host", "gdmix_re_score_host", "gdmix_host_register", "gdmix_host_unregister",
            "gdmix_host_release", "gdmix_partition_ids", "gdmix_lbfgs_create", "gdmix_lbfgs_iterate",
-           "gdmix_lbfgs_info", "gdmix_lbfgs_destroy", "gdmix_launch_count", "gdmix_re_last_plan"]
+           "gdmix_lbfgs_info", "gdmix_lbfgs_destroy", "gdmix_launch_count", "gdmix_re_last_plan",
+           "gdmix_partition_workspace_size", "gdmix_sort_pairs_u64", "gdmix_group_by_key", "gdmix_csr_gather_rows",
+           "gdmix_gather_f32", "gdmix_partition_ids_i64", "gdmix_auc"]
 
 
 class GdmixError(RuntimeError):
@@ -41,7 +43,8 @@ class ReBatch(C.Structure):
     _fields_ = [("n_entities", C.c_int64), ("n_rows", C.c_int64), ("nnz", C.c_int64),
                 ("ent_rowptr", C.c_void_p), ("rowptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p),
                 ("label", C.c_void_p), ("weight", C.c_void_p), ("offset", C.c_void_p), ("theta_ptr", C.c_void_p),
-                ("max_rows", C.c_int32), ("max_nnz", C.c_int32), ("max_coef", C.c_int32), ("reserved", C.c_int32)]
+                ("max_rows", C.c_int32), ("max_nnz", C.c_int32), ("max_coef", C.c_int32), ("reserved", C.c_int32),
+                ("col16", C.c_void_p)]
 
 
 class LrOpts(C.Structure):
@@ -154,10 +157,17 @@ class HostBatch:
         self.max_coef = int(coef.max()) if self.n_entities else 0
         self.n_coef = int(self.theta_ptr[-1])
 
-    def c_struct(self):
+    def c_struct(self, narrow=None):
+        """narrow=True sends the local column indices as uint16 (half the PCIe bytes for them); default: whenever
+        every entity has fewer than 65536 local features."""
+        if narrow is None:
+            narrow = self.max_coef < 65536 and self.nnz > 0
+        if narrow and getattr(self, "_col16", None) is None:
+            self._col16 = self.col.astype(np.uint16)
         return ReBatch(self.n_entities, self.n_rows, self.nnz, _np_ptr(self.ent_rowptr), _np_ptr(self.rowptr),
                        _np_ptr(self.col), _np_ptr(self.val), _np_ptr(self.label), _np_ptr(self.weight),
-                       _np_ptr(self.offset), _np_ptr(self.theta_ptr), self.max_rows, self.max_nnz, self.max_coef, 0)
+                       _np_ptr(self.offset), _np_ptr(self.theta_ptr), self.max_rows, self.max_nnz, self.max_coef, 0,
+                       _np_ptr(self._col16) if narrow else None)
 
     def algorithmic_bytes(self, warm=False):
         """8 B/nnz + 16 B/sample + 8 B/coef out (+8 in when warm) + 4 B/feature index map."""
@@ -230,7 +240,7 @@ class DeviceBatch:
         h = self.host
         return ReBatch(h.n_entities, h.n_rows, h.nnz, _tptr(self.ent_rowptr), _tptr(self.rowptr), _tptr(self.col),
                        _tptr(self.val), _tptr(self.label), _tptr(self.weight), _tptr(self.offset),
-                       _tptr(self.theta_ptr), h.max_rows, h.max_nnz, h.max_coef, 0)
+                       _tptr(self.theta_ptr), h.max_rows, h.max_nnz, h.max_coef, 0, None)
 
 
 def re_workspace_size(cb, opts):

@@ -18,6 +18,7 @@
 #include "re_fast.cuh"
 #include "re_kernel.cuh"
 #include "re_variance.cuh"
+#include "partition.cuh"
 
 namespace {
 
@@ -360,7 +361,7 @@ int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const d
     if (b->n_entities < 0) return fail(GDMIX_ERR_INVALID, "n_entities < 0");
     if (b->n_entities == 0) return GDMIX_OK;
     if (!b->ent_rowptr || !b->rowptr || !b->label || !b->theta_ptr || (b->nnz > 0 && (!b->col || !b->val)))
-        return fail(GDMIX_ERR_INVALID, "null array in gdmix_re_batch");
+        return fail(GDMIX_ERR_INVALID, "null array in gdmix_re_batch (device entry points need the int32 col)");
     DeviceInfo dev;
     int rc = device_info(dev);
     if (rc) return rc;
@@ -471,7 +472,7 @@ struct Slot {
 };
 struct HostCtx {
     std::mutex mu;
-    Slot slot[2];
+    Slot slot[3];
     int device = -1;
 } g_host;
 
@@ -503,14 +504,14 @@ inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // Carves a chunk's device image: inputs first, outputs after.  Returns total bytes.
 struct ChunkImage {
-    size_t ent_rowptr, rowptr, col, val, label, weight, offset, theta_ptr, theta0;  // inputs
+    size_t ent_rowptr, rowptr, col, col16, val, label, weight, offset, theta_ptr, theta0;  // inputs
     size_t in_bytes;
     size_t theta, f, nit, nfev, status, var;  // outputs
     size_t total;
 };
 
 ChunkImage chunk_image(int64_t ne, int64_t nr, int64_t nz, int64_t nt, bool has_w, bool has_off, bool warm,
-                       bool want_var)
+                       bool want_var, bool narrow_col = false)
 {
     ChunkImage c;
     size_t o = 0;
@@ -518,6 +519,7 @@ ChunkImage chunk_image(int64_t ne, int64_t nr, int64_t nz, int64_t nt, bool has_
     c.rowptr = o; o += up256(8 * (nr + 1));
     c.theta_ptr = o; o += up256(8 * (ne + 1));
     c.col = o; o += up256(4 * nz);
+    c.col16 = o; o += narrow_col ? up256(2 * nz) : 0;
     c.val = o; o += up256(4 * nz);
     c.label = o; o += up256(4 * nr);
     c.weight = o; o += has_w ? up256(4 * nr) : 0;
@@ -730,6 +732,8 @@ int gdmix_re_fit_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const do
     if (E <= 0) return GDMIX_OK;
     if (!hb->ent_rowptr || !hb->rowptr || !hb->label || !hb->theta_ptr)
         return fail(GDMIX_ERR_INVALID, "null array in gdmix_re_batch");
+    if (hb->nnz > 0 && !hb->col && !hb->col16) return fail(GDMIX_ERR_INVALID, "gdmix_re_batch needs col or col16");
+    const bool narrow = hb->col16 != nullptr;
     const bool want_var = var_out != nullptr;
     if (want_var && o->variance_mode != GDMIX_VARIANCE_SIMPLE && o->variance_mode != GDMIX_VARIANCE_FULL)
         return fail(GDMIX_ERR_INVALID, "var_out needs variance_mode SIMPLE or FULL");
@@ -738,7 +742,9 @@ int gdmix_re_fit_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const do
     std::lock_guard<std::mutex> lk(g_host.mu);
 
     // chunk boundaries: ~chunk_entities entities, or ~512 MB of input, whichever is smaller
-    if (chunk_entities <= 0) chunk_entities = 16384;
+    // enough chunks to keep three slots busy (H2D of chunk k+1 and D2H of chunk k-1 under the solve of chunk k),
+    // each still large enough to fill the GPU
+    if (chunk_entities <= 0) chunk_entities = std::max<int64_t>(2048, std::min<int64_t>(16384, (E + 11) / 12));
     std::vector<int64_t> cuts;
     cuts.push_back(0);
     {
@@ -761,7 +767,7 @@ int gdmix_re_fit_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const do
     // asynchronous; pageable memory still works, staged by the driver).  The pointer tables keep their
     // absolute values: the device-side array pointers are shifted instead, so nothing is rewritten.
     for (size_t ci = 0; ci < nchunks; ci++) {
-        Slot &s = g_host.slot[ci & 1];
+        Slot &s = g_host.slot[ci % 3];
         if (s.st) CUDA_TRY(cudaStreamSynchronize(s.st));  // the slot's previous chunk is fully drained
         const int64_t e0 = cuts[ci], e1 = cuts[ci + 1], ne = e1 - e0;
         const int64_t r0 = hb->ent_rowptr[e0], r1 = hb->ent_rowptr[e1], nr = r1 - r0;
@@ -784,7 +790,7 @@ int gdmix_re_fit_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const do
         int rc = gdmix_re_workspace_size(&db, o, &ws_bytes);
         if (rc) return rc;
         const ChunkImage img = chunk_image(ne, nr, nz, nt, hb->weight != nullptr, hb->offset != nullptr,
-                                           theta0 != nullptr, want_var);
+                                           theta0 != nullptr, want_var, narrow);
         rc = ensure(s, img.total, 0, ws_bytes);
         if (rc) return rc;
         char *dv = (char *)s.dev;
@@ -793,7 +799,14 @@ int gdmix_re_fit_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const do
         CUDA_TRY(cudaMemcpyAsync(dv + img.rowptr, hb->rowptr + r0, 8 * (nr + 1), H2D, s.st));
         CUDA_TRY(cudaMemcpyAsync(dv + img.theta_ptr, hb->theta_ptr + e0, 8 * (ne + 1), H2D, s.st));
         if (nz) {
-            CUDA_TRY(cudaMemcpyAsync(dv + img.col, hb->col + q0, 4 * nz, H2D, s.st));
+            if (narrow) {
+                CUDA_TRY(cudaMemcpyAsync(dv + img.col16, hb->col16 + q0, 2 * nz, H2D, s.st));
+                gdmix::widen_u16_kernel<<<(int)std::min<int64_t>((nz + 255) / 256, 148 * 8), 256, 0, s.st>>>(
+                    (const uint16_t *)(dv + img.col16), (int32_t *)(dv + img.col), nz);
+                g_launches++;
+            } else {
+                CUDA_TRY(cudaMemcpyAsync(dv + img.col, hb->col + q0, 4 * nz, H2D, s.st));
+            }
             CUDA_TRY(cudaMemcpyAsync(dv + img.val, hb->val + q0, 4 * nz, H2D, s.st));
         }
         CUDA_TRY(cudaMemcpyAsync(dv + img.label, hb->label + r0, 4 * nr, H2D, s.st));
@@ -883,6 +896,192 @@ int gdmix_re_score_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const 
     CUDA_TRY(cudaMemcpyAsync(logit, dv + o_lg, 4 * nr, cudaMemcpyDeviceToHost, s.st));
     CUDA_TRY(cudaMemcpyAsync(logit_pc, dv + o_pc, 4 * nr, cudaMemcpyDeviceToHost, s.st));
     CUDA_TRY(cudaStreamSynchronize(s.st));
+    return GDMIX_OK;
+}
+
+// ---- partitioner / evaluator entry points (partition.cuh) ------------------------------------------------
+namespace {
+inline size_t up256z(size_t x) { return (x + 255) & ~(size_t)255; }
+inline int64_t sort_tiles(int64_t n) { return (n + gdmix::kSortTile - 1) / gdmix::kSortTile; }
+
+struct SortScratch {
+    uint64_t *ktmp; uint32_t *vtmp; uint32_t *hist; uint64_t *digit_total, *digit_base;
+    size_t bytes;
+};
+SortScratch carve_sort(void *ws, int64_t n)
+{
+    SortScratch c;
+    const int64_t nt = sort_tiles(n);
+    size_t o = 0;
+    char *b = (char *)ws;
+    c.ktmp = (uint64_t *)(b + o); o += up256z(8 * (size_t)n);
+    c.vtmp = (uint32_t *)(b + o); o += up256z(4 * (size_t)n);
+    c.hist = (uint32_t *)(b + o); o += up256z(4 * (size_t)nt * gdmix::kRadix);
+    c.digit_total = (uint64_t *)(b + o); o += up256z(8 * gdmix::kRadix);
+    c.digit_base = (uint64_t *)(b + o); o += up256z(8 * gdmix::kRadix);
+    c.bytes = o;
+    return c;
+}
+
+int sort_pairs(const uint64_t *keys_in, const uint32_t *vals_in, int64_t n, int key_bits, uint64_t *keys_out,
+               uint32_t *vals_out, void *ws, cudaStream_t st)
+{
+    const SortScratch c = carve_sort(ws, n);
+    const int passes = std::max(1, (key_bits + 7) / 8);
+    const int grid = (int)sort_tiles(n);
+    const uint64_t *kin = keys_in;
+    const uint32_t *vin = vals_in;
+    for (int p = 0; p < passes; p++) {
+        // the last pass must land in the output pair
+        const bool to_out = ((passes - 1 - p) % 2) == 0;
+        uint64_t *ko = to_out ? keys_out : c.ktmp;
+        uint32_t *vo = to_out ? vals_out : c.vtmp;
+        gdmix::radix_hist_kernel<<<grid, gdmix::kSortThreads, 0, st>>>(kin, n, 8 * p, c.hist);
+        gdmix::radix_scan_tiles_kernel<<<gdmix::kRadix, 256, 0, st>>>(c.hist, grid, c.digit_total);
+        gdmix::radix_scan_digits_kernel<<<1, 32, 0, st>>>(c.digit_total, c.digit_base);
+        gdmix::radix_scatter_kernel<<<grid, gdmix::kSortThreads, 0, st>>>(kin, vin, ko, vo, n, 8 * p, c.hist, c.digit_base);
+        g_launches += 4;
+        kin = ko; vin = vo;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+}  // namespace
+
+int gdmix_partition_workspace_size(int64_t n, size_t *bytes)
+{
+    if (n < 0 || !bytes) return fail(GDMIX_ERR_INVALID, "bad argument");
+    const size_t nt = (size_t)sort_tiles(std::max<int64_t>(n, 1));
+    *bytes = 64 * (size_t)std::max<int64_t>(n, 1) + 16 * nt * gdmix::kRadix + (1u << 16);
+    return GDMIX_OK;
+}
+
+int gdmix_sort_pairs_u64(const uint64_t *keys_in, int64_t n, int32_t key_bits, uint64_t *keys_out, uint32_t *perm_out,
+                         void *ws, size_t ws_bytes, void *stream)
+{
+    if (n < 0 || key_bits < 1 || key_bits > 64 || (n > 0 && (!keys_in || !keys_out || !perm_out || !ws)))
+        return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_sort_pairs_u64");
+    if (n >= (1ll << 32)) return fail(GDMIX_ERR_TOO_LARGE, "at most 2^32 - 1 keys per call");
+    if (n == 0) return GDMIX_OK;
+    size_t need = 0;
+    gdmix_partition_workspace_size(n, &need);
+    if (ws_bytes < need) return fail(GDMIX_ERR_WORKSPACE, "workspace %zu B < required %zu B", ws_bytes, need);
+    return sort_pairs(keys_in, nullptr, n, key_bits, keys_out, perm_out, ws, (cudaStream_t)stream);
+}
+
+int gdmix_group_by_key(const uint64_t *keys, int64_t n, int32_t key_bits, uint64_t *keys_sorted, uint32_t *perm,
+                       int64_t *seg_ptr, uint64_t *seg_key, int64_t *n_groups_dev, void *ws, size_t ws_bytes, void *stream)
+{
+    if (!n_groups_dev || !seg_ptr) return fail(GDMIX_ERR_INVALID, "null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { CUDA_TRY(cudaMemsetAsync(n_groups_dev, 0, 8, st)); CUDA_TRY(cudaMemsetAsync(seg_ptr, 0, 8, st)); return GDMIX_OK; }
+    int rc = gdmix_sort_pairs_u64(keys, n, key_bits, keys_sorted, perm, ws, ws_bytes, stream);
+    if (rc) return rc;
+    // segment heads: scratch after the sort's own
+    const SortScratch c = carve_sort(ws, n);
+    const int64_t nt = sort_tiles(n);
+    uint32_t *tile_count = (uint32_t *)((char *)ws + c.bytes);
+    int64_t *tile_off = (int64_t *)((char *)ws + c.bytes + up256z(4 * (size_t)nt));
+    gdmix::heads_count_kernel<<<(int)nt, gdmix::kSortThreads, 0, st>>>(keys_sorted, n, tile_count);
+    gdmix::tiles_exclusive_scan_kernel<<<1, 256, 0, st>>>(tile_count, nt, tile_off, n_groups_dev);
+    gdmix::heads_write_kernel<<<(int)nt, gdmix::kSortThreads, 0, st>>>(keys_sorted, n, tile_off, seg_ptr, seg_key);
+    g_launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
+int gdmix_csr_gather_rows(const int64_t *rowptr_in, const int32_t *col_in, const float *val_in, const uint32_t *perm,
+                          int64_t n_rows, int64_t *rowptr_out, int32_t *col_out, float *val_out, void *ws,
+                          size_t ws_bytes, void *stream)
+{
+    if (n_rows < 0 || !rowptr_out) return fail(GDMIX_ERR_INVALID, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_rows == 0) { CUDA_TRY(cudaMemsetAsync(rowptr_out, 0, 8, st)); return GDMIX_OK; }
+    if (!rowptr_in || !perm || !ws) return fail(GDMIX_ERR_INVALID, "null argument");
+    size_t need = 0;
+    gdmix_partition_workspace_size(n_rows, &need);
+    if (ws_bytes < need) return fail(GDMIX_ERR_WORKSPACE, "workspace %zu B < required %zu B", ws_bytes, need);
+    const int64_t nt = sort_tiles(n_rows);
+    uint32_t *len = (uint32_t *)ws;
+    uint32_t *tile_sum = (uint32_t *)((char *)ws + up256z(4 * (size_t)n_rows));
+    int64_t *tile_off = (int64_t *)((char *)tile_sum + up256z(4 * (size_t)nt));
+    int64_t *total = tile_off + nt;
+    DeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc) return rc;
+    const int g1 = (int)std::min<int64_t>((n_rows + 255) / 256, (int64_t)dev.sm_count * 8);
+    gdmix::gather_row_len_kernel<<<g1, 256, 0, st>>>(rowptr_in, perm, n_rows, len);
+    gdmix::tile_sum_kernel<<<(int)nt, gdmix::kSortThreads, 0, st>>>(len, n_rows, tile_sum);
+    gdmix::tiles_exclusive_scan_kernel<<<1, 256, 0, st>>>(tile_sum, nt, tile_off, total);
+    gdmix::rowptr_from_len_kernel<<<(int)nt, gdmix::kSortThreads, 0, st>>>(len, n_rows, tile_off, rowptr_out);
+    if (col_in && val_in && col_out && val_out) {
+        const int g2 = (int)std::min<int64_t>((n_rows + 7) / 8, (int64_t)dev.sm_count * 16);
+        gdmix::gather_rows_kernel<<<g2, 256, 0, st>>>(rowptr_in, col_in, val_in, perm, n_rows, rowptr_out, col_out, val_out);
+        g_launches++;
+    }
+    g_launches += 4;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
+int gdmix_gather_f32(const float *in, const uint32_t *perm, int64_t n, float *out, void *stream)
+{
+    if (n < 0 || (n > 0 && (!in || !perm || !out))) return fail(GDMIX_ERR_INVALID, "bad argument");
+    if (n == 0) return GDMIX_OK;
+    gdmix::gather_f32_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(in, perm, n, out);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
+int gdmix_partition_ids_i64(const int64_t *ids, int64_t n, int32_t num_partitions, int32_t *partition_out, void *stream)
+{
+    if (n < 0 || num_partitions <= 0 || (n > 0 && (!ids || !partition_out))) return fail(GDMIX_ERR_INVALID, "bad argument");
+    if (n == 0) return GDMIX_OK;
+    gdmix::partition_i64_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+        ids, n, num_partitions, partition_out);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
+int gdmix_auc(const float *score, const float *label, int64_t n, double *out3, void *ws, size_t ws_bytes, void *stream)
+{
+    if (n <= 0 || !score || !label || !out3 || !ws) return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_auc");
+    if (n >= (1ll << 32)) return fail(GDMIX_ERR_TOO_LARGE, "at most 2^32 - 1 scores per call");
+    size_t need = 0;
+    gdmix_partition_workspace_size(n, &need);
+    if (ws_bytes < need) return fail(GDMIX_ERR_WORKSPACE, "workspace %zu B < required %zu B", ws_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    const SortScratch c = carve_sort(ws, n);
+    const int64_t nt = sort_tiles(n);
+    char *b = (char *)ws + c.bytes;
+    size_t o = 0;
+    uint64_t *keys = (uint64_t *)(b + o); o += up256z(8 * (size_t)n);
+    uint32_t *lab = (uint32_t *)(b + o); o += up256z(4 * (size_t)n);
+    uint64_t *keys_s = (uint64_t *)(b + o); o += up256z(8 * (size_t)n);
+    uint32_t *lab_s = (uint32_t *)(b + o); o += up256z(4 * (size_t)n);
+    int64_t *seg_ptr = (int64_t *)(b + o); o += up256z(8 * (size_t)(n + 1));
+    unsigned long long *gpos = (unsigned long long *)(b + o); o += up256z(8 * (size_t)n);
+    unsigned long long *gneg = (unsigned long long *)(b + o); o += up256z(8 * (size_t)n);
+    uint32_t *tile_count = (uint32_t *)(b + o); o += up256z(4 * (size_t)nt);
+    int64_t *tile_off = (int64_t *)(b + o); o += up256z(8 * (size_t)nt);
+    int64_t *ngroups = (int64_t *)(b + o); o += 256;
+    const int g1 = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    gdmix::auc_keys_kernel<<<g1, 256, 0, st>>>(score, label, n, keys, lab);
+    int rc = sort_pairs(keys, lab, n, 32, keys_s, lab_s, ws, st);
+    if (rc) return rc;
+    gdmix::heads_count_kernel<<<(int)nt, gdmix::kSortThreads, 0, st>>>(keys_s, n, tile_count);
+    gdmix::tiles_exclusive_scan_kernel<<<1, 256, 0, st>>>(tile_count, nt, tile_off, ngroups);
+    gdmix::heads_write_kernel<<<(int)nt, gdmix::kSortThreads, 0, st>>>(keys_s, n, tile_off, seg_ptr, nullptr);
+    // the number of groups is only known on the device: size the group kernels for n, they stop at seg_ptr's end
+    int64_t ng_host = 0;
+    CUDA_TRY(cudaMemcpyAsync(&ng_host, ngroups, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    gdmix::auc_groups_kernel<<<(int)std::min<int64_t>((ng_host + 7) / 8, 148 * 16), 256, 0, st>>>(lab_s, seg_ptr, ng_host, gpos, gneg);
+    gdmix::auc_finish_kernel<<<1, 256, 0, st>>>(gpos, gneg, ng_host, out3);
+    g_launches += 6;
+    CUDA_TRY(cudaGetLastError());
     return GDMIX_OK;
 }
 

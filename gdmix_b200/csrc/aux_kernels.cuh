@@ -43,6 +43,13 @@ __global__ void __launch_bounds__(256) re_score_kernel(const gdmix_re_batch b, c
     }
 }
 
+// 16-bit local column indices (as they crossed PCIe) -> the int32 the kernels index with
+__global__ void __launch_bounds__(256) widen_u16_kernel(const uint16_t *in, int32_t *out, const int64_t n)
+{
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth) out[i] = (int32_t)in[i];
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll

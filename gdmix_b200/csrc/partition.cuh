@@ -1,0 +1,414 @@
+// partition.cuh -- the data movement either side of the hot path, on the device (HBM-bound integer work):
+//
+//   * stable LSD radix sort of (u64 key, u32 payload) pairs, 8 bits per pass, 4096-key tiles;
+//   * group-by-key on top of it: row permutation that brings equal keys together (original order kept inside
+//     a group), segment pointers, the distinct keys -- what Spark's groupBy(entity) does in DataPartitioner
+//     (gdmix-data/src/main/scala/com/linkedin/gdmix/data/DataPartitioner.scala:296-379) without leaving HBM;
+//   * gathering a CSR by a row permutation (the regrouped sample block of a random-effect stage);
+//   * entity -> partition map for integer ids (abs(String.valueOf(id).hashCode) % n, PartitionUtils.scala:31-37);
+//   * area under the ROC curve with ties (Evaluator.scala:29-45 -> MLlib BinaryClassificationMetrics): sort by
+//     score, then a rank-sum over tie groups.
+// Every kernel reads and writes each element once per pass with coalesced accesses; nothing here is a GEMM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gdmix {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per CTA
+constexpr int kRadix = 256;
+
+// ---- radix sort -----------------------------------------------------------------------------------------
+// hist[tile][digit]
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint64_t *keys, const int64_t n, const int shift,
+                                                                  uint32_t *hist)
+{
+    __shared__ uint32_t h[kRadix];
+    const int tid = threadIdx.x;
+    h[tid] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kSortTile;
+#pragma unroll 4
+    for (int i = 0; i < kSortItems; i++) {
+        const int64_t idx = base + (int64_t)i * kSortThreads + tid;
+        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(int64_t)blockIdx.x * kRadix + tid] = h[tid];
+}
+
+// One CTA per digit: exclusive prefix over tiles of hist[.][digit] (in place) and the digit's total.
+__global__ void __launch_bounds__(256) radix_scan_tiles_kernel(uint32_t *hist, const int64_t ntiles, uint64_t *digit_total)
+{
+    __shared__ uint64_t wsum[8];
+    __shared__ uint64_t carry_s;
+    const int d = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t t0 = 0; t0 < ntiles; t0 += 256) {
+        const int64_t t = t0 + tid;
+        const uint64_t mine = (t < ntiles) ? hist[t * kRadix + d] : 0;
+        uint64_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        uint64_t before = carry_s;
+        for (int w = 0; w < warp; w++) before += wsum[w];
+        // 32-bit tile offsets would overflow beyond 4G keys of one digit; keep them relative to the digit's start
+        if (t < ntiles) hist[t * kRadix + d] = (uint32_t)(before + incl - mine);
+        __syncthreads();
+        if (tid == 255) carry_s = before + incl;
+        __syncthreads();
+    }
+    if (tid == 0) digit_total[d] = carry_s;
+}
+
+// exclusive scan of the 256 digit totals (one warp)
+__global__ void radix_scan_digits_kernel(const uint64_t *digit_total, uint64_t *digit_base)
+{
+    const int lane = threadIdx.x;
+    uint64_t carry = 0;
+    for (int c = 0; c < kRadix; c += 32) {
+        const uint64_t mine = digit_total[c + lane];
+        uint64_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        digit_base[c + lane] = carry + incl - mine;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+// Stable scatter of one tile.  A warp owns 512 consecutive keys and walks them 32 at a time, in order; equal
+// digits inside a chunk are ranked by lane (match_any), chunks and warps by running counters.
+__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint64_t *kin, const uint32_t *vin, uint64_t *kout,
+                                                                     uint32_t *vout, const int64_t n, const int shift,
+                                                                     const uint32_t *tile_offs, const uint64_t *digit_base)
+{
+    __shared__ uint64_t wbase[kSortThreads / 32][kRadix];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k < (kSortThreads / 32) * kRadix; k += kSortThreads) (&wbase[0][0])[k] = 0;
+    __syncthreads();
+    const int64_t wbeg = (int64_t)blockIdx.x * kSortTile + (int64_t)warp * (kSortTile / (kSortThreads / 32));
+    constexpr int kChunks = kSortTile / (kSortThreads / 32) / 32;  // 16
+    for (int c = 0; c < kChunks; c++) {
+        const int64_t idx = wbeg + c * 32 + lane;
+        const unsigned d = (idx < n) ? (unsigned)((kin[idx] >> shift) & 255u) : (256u + lane);
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (idx < n && (peers & ((1u << lane) - 1u)) == 0) wbase[warp][d] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        // thread = digit: turn per-warp counts into per-warp global start positions
+        uint64_t run = digit_base[tid] + tile_offs[(int64_t)blockIdx.x * kRadix + tid];
+        for (int w = 0; w < kSortThreads / 32; w++) {
+            const uint64_t cnt = wbase[w][tid];
+            wbase[w][tid] = run;
+            run += cnt;
+        }
+    }
+    __syncthreads();
+    for (int c = 0; c < kChunks; c++) {
+        const int64_t idx = wbeg + c * 32 + lane;
+        const bool act = idx < n;
+        const uint64_t key = act ? kin[idx] : 0;
+        const unsigned d = act ? (unsigned)((key >> shift) & 255u) : (256u + lane);
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+        if (act) {
+            const uint64_t pos = wbase[warp][d] + rank;
+            kout[pos] = key;
+            vout[pos] = vin ? vin[idx] : (uint32_t)idx;
+        }
+        __syncwarp();
+        if (act && rank == 0) wbase[warp][d] += __popc(peers);
+        __syncwarp();
+    }
+}
+
+// ---- segments of a sorted key array ---------------------------------------------------------------------
+// tile_count[tile] = number of group heads in the tile
+__global__ void __launch_bounds__(kSortThreads) heads_count_kernel(const uint64_t *keys, const int64_t n, uint32_t *tile_count)
+{
+    __shared__ uint32_t ws[kSortThreads / 32];
+    const int tid = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * kSortTile;
+    uint32_t c = 0;
+    for (int i = 0; i < kSortItems; i++) {
+        const int64_t idx = base + (int64_t)i * kSortThreads + tid;
+        if (idx < n && (idx == 0 || keys[idx] != keys[idx - 1])) c++;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((tid & 31) == 0) ws[tid >> 5] = c;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < kSortThreads / 32; w++) t += ws[w];
+        tile_count[blockIdx.x] = t;
+    }
+}
+
+// single CTA: exclusive scan of per-tile counts into 64-bit offsets; total to *out_total
+__global__ void __launch_bounds__(256) tiles_exclusive_scan_kernel(const uint32_t *tile_count, const int64_t ntiles,
+                                                                   int64_t *tile_off, int64_t *out_total)
+{
+    __shared__ uint64_t wsum[8];
+    __shared__ uint64_t carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t t0 = 0; t0 < ntiles; t0 += 256) {
+        const int64_t t = t0 + tid;
+        const uint64_t mine = (t < ntiles) ? tile_count[t] : 0;
+        uint64_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        uint64_t before = carry_s;
+        for (int w = 0; w < warp; w++) before += wsum[w];
+        if (t < ntiles) tile_off[t] = (int64_t)(before + incl - mine);
+        __syncthreads();
+        if (tid == 255) carry_s = before + incl;
+        __syncthreads();
+    }
+    if (tid == 0) *out_total = (int64_t)carry_s;
+}
+
+// heads -> seg_ptr[g] = index of the g-th group's first element, seg_key[g] = its key; seg_ptr[G] = n
+__global__ void __launch_bounds__(kSortThreads) heads_write_kernel(const uint64_t *keys, const int64_t n, const int64_t *tile_off,
+                                                                   int64_t *seg_ptr, uint64_t *seg_key)
+{
+    __shared__ uint32_t ws[kSortThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // a thread owns 16 CONSECUTIVE keys here so that heads keep their order
+    const int64_t base = (int64_t)blockIdx.x * kSortTile + (int64_t)tid * kSortItems;
+    uint32_t flags = 0, c = 0;
+    for (int i = 0; i < kSortItems; i++) {
+        const int64_t idx = base + i;
+        if (idx < n && (idx == 0 || keys[idx] != keys[idx - 1])) { flags |= 1u << i; c++; }
+    }
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) ws[warp] = incl;
+    __syncthreads();
+    int64_t g = tile_off[blockIdx.x] + (incl - c);
+    for (int w = 0; w < warp; w++) g += ws[w];
+    for (int i = 0; i < kSortItems; i++) {
+        if ((flags >> i) & 1u) {
+            seg_ptr[g] = base + i;
+            if (seg_key) seg_key[g] = keys[base + i];
+            g++;
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1 && tid == kSortThreads - 1) {
+        // the very last thread knows the total
+        seg_ptr[g] = n;
+    }
+}
+
+// ---- regrouping a CSR by a row permutation ----------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_row_len_kernel(const int64_t *rowptr, const uint32_t *perm, const int64_t n,
+                                                             uint32_t *len_out)
+{
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth) {
+        const uint32_t r = perm[i];
+        len_out[i] = (uint32_t)(rowptr[r + 1] - rowptr[r]);
+    }
+}
+
+// 64-bit exclusive scan of u32 lengths: tile sums, then tiles_exclusive_scan_kernel, then this
+__global__ void __launch_bounds__(kSortThreads) tile_sum_kernel(const uint32_t *len, const int64_t n, uint32_t *tile_sum)
+{
+    __shared__ uint32_t ws[kSortThreads / 32];
+    const int tid = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * kSortTile;
+    uint32_t c = 0;
+    for (int i = 0; i < kSortItems; i++) {
+        const int64_t idx = base + (int64_t)i * kSortThreads + tid;
+        if (idx < n) c += len[idx];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((tid & 31) == 0) ws[tid >> 5] = c;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < kSortThreads / 32; w++) t += ws[w];
+        tile_sum[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads) rowptr_from_len_kernel(const uint32_t *len, const int64_t n,
+                                                                       const int64_t *tile_off, int64_t *rowptr_out)
+{
+    __shared__ uint32_t ws[kSortThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t base = (int64_t)blockIdx.x * kSortTile + (int64_t)tid * kSortItems;
+    uint32_t l[kSortItems], c = 0;
+    for (int i = 0; i < kSortItems; i++) { l[i] = (base + i < n) ? len[base + i] : 0u; c += l[i]; }
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) ws[warp] = incl;
+    __syncthreads();
+    int64_t run = tile_off[blockIdx.x] + (incl - c);
+    for (int w = 0; w < warp; w++) run += ws[w];
+    for (int i = 0; i < kSortItems; i++) {
+        if (base + i < n) rowptr_out[base + i] = run;
+        run += l[i];
+    }
+    if (base <= n - 1 && n - 1 < base + kSortItems) rowptr_out[n] = run;
+}
+
+// a warp copies one row's non-zeros (coalesced on both sides)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const int64_t *rowptr_in, const int32_t *col_in, const float *val_in,
+                                                          const uint32_t *perm, const int64_t n, const int64_t *rowptr_out,
+                                                          int32_t *col_out, float *val_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n; i += nwarps) {
+        const int64_t src = rowptr_in[perm[i]], len = rowptr_in[perm[i] + 1] - src, dst = rowptr_out[i];
+        for (int64_t k = lane; k < len; k += 32) {
+            col_out[dst + k] = col_in[src + k];
+            val_out[dst + k] = val_in[src + k];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_f32_kernel(const float *in, const uint32_t *perm, const int64_t n, float *out)
+{
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth) out[i] = in[perm[i]];
+}
+
+// ---- entity -> partition for integer ids -------------------------------------------------------------------
+__global__ void __launch_bounds__(256) partition_i64_kernel(const int64_t *ids, const int64_t n, const int32_t num_partitions,
+                                                            int32_t *partition_out)
+{
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth) {
+        // String.valueOf(long) then String.hashCode: h = 31 h + char, most significant digit first
+        const int64_t v = ids[i];
+        uint64_t mag = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
+        char digits[20];
+        int nd = 0;
+        do { digits[nd++] = (char)('0' + (int)(mag % 10)); mag /= 10; } while (mag);
+        uint32_t h = 0;
+        if (v < 0) h = (uint32_t)'-';
+        for (int k = nd - 1; k >= 0; k--) h = 31u * h + (uint32_t)digits[k];
+        const int32_t hs = (int32_t)h;
+        const int32_t a = (hs == INT32_MIN) ? hs : (hs < 0 ? -hs : hs);
+        partition_out[i] = a % num_partitions;
+    }
+}
+
+// ---- AUC ------------------------------------------------------------------------------------------------
+// scores -> sortable keys (ascending), payload = label bit
+__global__ void __launch_bounds__(256) auc_keys_kernel(const float *score, const float *label, const int64_t n, uint64_t *keys,
+                                                       uint32_t *payload)
+{
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth) {
+        float s = score[i];
+        if (s == 0.0f) s = 0.0f;  // -0.0 and +0.0 tie
+        uint32_t b = __float_as_uint(s);
+        b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+        keys[i] = b;
+        payload[i] = label[i] > 0.0f ? 1u : 0u;
+    }
+}
+
+// Over the tie groups of the sorted scores: U += pos_g * (neg_below_g + neg_g / 2).  acc[0] = 2U (integer),
+// acc[1] = positives, acc[2] = negatives.  One warp per group run of at most 2^31 elements; groups are found from
+// seg_ptr (heads of equal keys).  neg_below comes from an exclusive scan of per-group negatives done by the caller's
+// second launch: to stay single-pass this kernel does the serial part per CTA-chunk of groups and uses atomics
+// on integers (exact, order-free).
+__global__ void __launch_bounds__(256) auc_groups_kernel(const uint32_t *label_sorted, const int64_t *seg_ptr, const int64_t ngroups,
+                                                         unsigned long long *group_pos, unsigned long long *group_neg)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t g = warp; g < ngroups; g += nwarps) {
+        const int64_t b = seg_ptr[g], e = seg_ptr[g + 1];
+        unsigned long long pos = 0;
+        for (int64_t k = b + lane; k < e; k += 32) pos += label_sorted[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pos += __shfl_xor_sync(0xffffffffu, pos, o);
+        if (lane == 0) { group_pos[g] = pos; group_neg[g] = (unsigned long long)(e - b) - pos; }
+    }
+}
+
+// single CTA: walks the groups in order (chunks of 256 with a block scan of negatives); exact integer arithmetic
+__global__ void __launch_bounds__(256) auc_finish_kernel(const unsigned long long *group_pos, const unsigned long long *group_neg,
+                                                         const int64_t ngroups, double *out /* auc, positives, negatives */)
+{
+    __shared__ unsigned long long wsum[8], carry_s, u2_s[8], pos_s[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    // 2U can exceed 64 bits only beyond ~3e9 x 3e9 pairs; accumulate in double pairs per thread to be safe
+    double u2 = 0.0;
+    unsigned long long pos_total = 0;
+    for (int64_t g0 = 0; g0 < ngroups; g0 += 256) {
+        const int64_t g = g0 + tid;
+        const unsigned long long neg = (g < ngroups) ? group_neg[g] : 0ull, pos = (g < ngroups) ? group_pos[g] : 0ull;
+        unsigned long long incl = neg;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned long long below = carry_s + incl - neg;
+        for (int w = 0; w < warp; w++) below += wsum[w];
+        u2 += (double)pos * (2.0 * (double)below + (double)neg);
+        pos_total += pos;
+        __syncthreads();
+        if (tid == 255) carry_s = below + neg;
+        __syncthreads();
+    }
+    // fixed-order reduction of the per-thread sums
+    __shared__ double ud[256];
+    __shared__ unsigned long long pd[256];
+    ud[tid] = u2; pd[tid] = pos_total;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (tid < s) { ud[tid] += ud[tid + s]; pd[tid] += pd[tid + s]; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const double P = (double)pd[0], N = (double)carry_s;
+        out[0] = (P > 0 && N > 0) ? 0.5 * ud[0] / (P * N) : 0.0;
+        out[1] = P;
+        out[2] = N;
+    }
+    (void)u2_s; (void)pos_s;
+}
+
+}  // namespace gdmix

@@ -1,0 +1,153 @@
+"""Device-side partitioner / evaluator: what gdmix-data's Spark jobs do before and after the hot path, without
+leaving HBM (kernels in csrc/partition.cuh, C ABI in include/gdmix_b200.h).
+
+  group_by_entity   DataPartitioner.boundAndGroupData's groupBy(entity) (DataPartitioner.scala:296-379, bounds aside)
+  regroup_batch     rows in arrival order (+ global feature ids) -> the entity-local CSR batch gdmix_re_fit takes
+                    (prepare_jobs' np.unique per entity, job_consumers.py:243, for the whole dataset at once)
+  partition_ids     PartitionUtils.getPartitionIdUDF for integer entity ids (PartitionUtils.scala:31-37)
+  auc               Evaluator.calculateMetric(..., "auc") (Evaluator.scala:29-45)
+
+torch supplies device memory only; O(nnz) work is done by the library's kernels, O(#entities) glue (a cumsum over
+segment lengths) by torch.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+from ._capi import _stream_ptr, _tptr, check, lib
+
+
+def _ws(n, device):
+    import torch
+    b = C.c_size_t()
+    check(lib.gdmix_partition_workspace_size(C.c_int64(max(int(n), 1)), C.byref(b)))
+    return torch.empty(b.value, dtype=torch.uint8, device=device)
+
+
+def _key_bits(keys):
+    mx = int(keys.max().item()) if keys.numel() else 0
+    return max(1, mx.bit_length())
+
+
+def group_by_entity(keys, key_bits=None, stream=None):
+    """keys: int64 CUDA tensor of non-negative entity keys, one per row.
+    -> (perm int32[n]: rows in grouped order, original order kept inside an entity; seg_ptr int64[G+1];
+        seg_key int64[G]: the entities in ascending key order)"""
+    import torch
+    n = keys.numel()
+    assert keys.dtype == torch.int64 and keys.is_cuda
+    if key_bits is None:
+        key_bits = _key_bits(keys)
+    ws = _ws(n, keys.device)
+    perm = torch.empty(n, dtype=torch.int32, device=keys.device)
+    keys_sorted = torch.empty(n, dtype=torch.int64, device=keys.device)
+    seg_ptr = torch.empty(n + 1, dtype=torch.int64, device=keys.device)
+    seg_key = torch.empty(max(n, 1), dtype=torch.int64, device=keys.device)
+    ng = torch.zeros(1, dtype=torch.int64, device=keys.device)
+    check(lib.gdmix_group_by_key(_tptr(keys), C.c_int64(n), C.c_int32(key_bits), _tptr(keys_sorted), _tptr(perm),
+                                 _tptr(seg_ptr), _tptr(seg_key), _tptr(ng), _tptr(ws), C.c_size_t(ws.numel()),
+                                 _stream_ptr(stream)))
+    g = int(ng.item())
+    return perm, seg_ptr[:g + 1], seg_key[:g]
+
+
+def sort_pairs(keys, key_bits=None, stream=None):
+    """Stable ascending sort of non-negative int64 keys -> (keys_sorted, perm int32)."""
+    import torch
+    n = keys.numel()
+    if key_bits is None:
+        key_bits = _key_bits(keys)
+    ws = _ws(n, keys.device)
+    out = torch.empty_like(keys)
+    perm = torch.empty(n, dtype=torch.int32, device=keys.device)
+    check(lib.gdmix_sort_pairs_u64(_tptr(keys), C.c_int64(n), C.c_int32(key_bits), _tptr(out), _tptr(perm), _tptr(ws),
+                                   C.c_size_t(ws.numel()), _stream_ptr(stream)))
+    return out, perm
+
+
+def gather_rows(rowptr, col, val, perm, stream=None):
+    """CSR rows in the order perm gives -> (rowptr', col', val')."""
+    import torch
+    n = perm.numel()
+    ws = _ws(n, perm.device)
+    rp = torch.empty(n + 1, dtype=torch.int64, device=perm.device)
+    co = torch.empty_like(col)
+    va = torch.empty_like(val)
+    check(lib.gdmix_csr_gather_rows(_tptr(rowptr), _tptr(col), _tptr(val), _tptr(perm), C.c_int64(n), _tptr(rp),
+                                    _tptr(co), _tptr(va), _tptr(ws), C.c_size_t(ws.numel()), _stream_ptr(stream)))
+    return rp, co, va
+
+
+def gather_f32(x, perm, stream=None):
+    import torch
+    out = torch.empty(perm.numel(), dtype=torch.float32, device=perm.device)
+    check(lib.gdmix_gather_f32(_tptr(x), _tptr(perm), C.c_int64(perm.numel()), _tptr(out), _stream_ptr(stream)))
+    return out
+
+
+def partition_ids(ids, num_partitions, stream=None):
+    """abs(str(id).hashCode()) % num_partitions for an int64 CUDA tensor of entity ids -> int32 tensor."""
+    import torch
+    out = torch.empty(ids.numel(), dtype=torch.int32, device=ids.device)
+    check(lib.gdmix_partition_ids_i64(_tptr(ids), C.c_int64(ids.numel()), C.c_int32(num_partitions), _tptr(out),
+                                      _stream_ptr(stream)))
+    return out
+
+
+def auc(score, label, stream=None):
+    """Area under the ROC curve of fp32 CUDA tensors (label > 0 positive), ties counted half."""
+    import torch
+    n = score.numel()
+    ws = _ws(n, score.device)
+    out = torch.zeros(3, dtype=torch.float64, device=score.device)
+    check(lib.gdmix_auc(_tptr(score.contiguous()), _tptr(label.contiguous()), C.c_int64(n), _tptr(out), _tptr(ws),
+                        C.c_size_t(ws.numel()), _stream_ptr(stream)))
+    a, p, q = out.cpu().tolist()
+    return a
+
+
+def regroup_batch(entity, rowptr, gcol, val, label, offset=None, weight=None, has_intercept=True, num_features=None):
+    """Rows in arrival order -> the entity-local CSR batch of a random-effect stage, all on the device.
+
+    entity int64[n] (non-negative ids), rowptr int64[n+1], gcol int32[nnz] GLOBAL feature ids, val fp32[nnz],
+    label / offset / weight fp32[n].  Returns a dict with the gdmix_re_batch arrays (ent_rowptr, rowptr, col =
+    entity-LOCAL feature index, val, label, offset, weight, theta_ptr), the bounds (max_rows, max_nnz, max_coef),
+    `perm` (row i of the batch is input row perm[i]), `entity_ids` and `uniq_ptr` / `uniq_global` (entity e's
+    local feature j is global feature uniq_global[uniq_ptr[e] + j]) -- what prepare_jobs derives per entity
+    (job_consumers.py:243-258), for the whole dataset in a handful of launches."""
+    import torch
+    dev = entity.device
+    n = entity.numel()
+    perm, ent_rowptr, entity_ids = group_by_entity(entity)
+    E = entity_ids.numel()
+    rp, gc, va = gather_rows(rowptr, gcol, val, perm)
+    lab = gather_f32(label, perm)
+    off = gather_f32(offset, perm) if offset is not None else None
+    wt = gather_f32(weight, perm) if weight is not None else None
+    nnz = gc.numel()
+    # entity index of every row / non-zero of the grouped batch (O(n) expansion of O(E) segments)
+    ent_of_row = torch.repeat_interleave(torch.arange(E, device=dev), ent_rowptr[1:] - ent_rowptr[:-1])
+    ent_of_nnz = torch.repeat_interleave(ent_of_row, rp[1:] - rp[:-1])
+    fbits = max(1, int(num_features - 1).bit_length()) if num_features else _key_bits(gc.to(torch.int64))
+    pair = (ent_of_nnz << fbits) | gc.to(torch.int64)
+    pperm, pseg, pkey = group_by_entity(pair, key_bits=fbits + max(1, int(E - 1).bit_length()))
+    # group g = one distinct (entity, feature); groups are ordered by entity, then by feature id
+    uniq_global = (pkey & ((1 << fbits) - 1)).to(torch.int64)
+    ent_of_group = pkey >> fbits
+    d_e = torch.bincount(ent_of_group, minlength=E)
+    uniq_ptr = torch.zeros(E + 1, dtype=torch.int64, device=dev)
+    uniq_ptr[1:] = torch.cumsum(d_e, 0)
+    group_of_sorted = torch.repeat_interleave(torch.arange(pkey.numel(), device=dev), pseg[1:] - pseg[:-1])
+    local = torch.empty(nnz, dtype=torch.int32, device=dev)
+    local[pperm.long()] = (group_of_sorted - uniq_ptr[ent_of_group[group_of_sorted]]).to(torch.int32)
+    hi = 1 if has_intercept else 0
+    theta_ptr = torch.zeros(E + 1, dtype=torch.int64, device=dev)
+    theta_ptr[1:] = torch.cumsum(d_e + hi, 0)
+    rows_e = ent_rowptr[1:] - ent_rowptr[:-1]
+    nnz_e = rp[ent_rowptr[1:]] - rp[ent_rowptr[:-1]]
+    return {"ent_rowptr": ent_rowptr.contiguous(), "rowptr": rp, "col": local, "val": va, "label": lab, "offset": off,
+            "weight": wt, "theta_ptr": theta_ptr, "n_entities": E, "n_rows": n, "nnz": nnz,
+            "max_rows": int(rows_e.max().item()) if E else 0, "max_nnz": int(nnz_e.max().item()) if E else 0,
+            "max_coef": int(d_e.max().item()) + hi if E else hi, "n_coef": int(theta_ptr[-1].item()),
+            "perm": perm, "entity_ids": entity_ids, "uniq_ptr": uniq_ptr, "uniq_global": uniq_global}

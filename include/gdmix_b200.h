@@ -100,6 +100,10 @@ typedef struct gdmix_re_batch {
     int32_t max_nnz;           /* max non-zeros of one entity */
     int32_t max_coef;          /* max coefficients (d_e + has_intercept) of one entity */
     int32_t reserved;
+    /* Optional, *_host entry points only: the same local column indices as 16-bit values (valid when every
+     * entity has fewer than 65536 local features).  When set, `col` may be NULL: 2 instead of 4 bytes per
+     * non-zero cross PCIe and are widened on the device. */
+    const uint16_t *col16;
 } gdmix_re_batch;
 
 /* LRParams / scipy knobs (base_lr_params.py:5-42; scipy defaults for the rest). */
@@ -230,6 +234,37 @@ GDMIX_API void gdmix_host_release(void);
  * code units, entity e owning units[id_ptr[e] .. id_ptr[e+1]).  Host function. */
 GDMIX_API int gdmix_partition_ids(const uint16_t *units, const int64_t *id_ptr, int64_t n_ids,
                                   int32_t num_partitions, int32_t *hash_out, int32_t *partition_out);
+
+/* ---- either side of the path, on the device (the Spark jobs DataPartitioner / Evaluator of gdmix-data) --------
+ * All pointers are device pointers; `ws` is caller-owned scratch of gdmix_partition_workspace_size(n) bytes.
+ *
+ * gdmix_sort_pairs_u64    stable LSD radix sort of n keys (the low key_bits bits are significant); perm_out[i] is
+ *                         the original index of the i-th smallest key.
+ * gdmix_group_by_key      groupBy(entity): sort + segments.  perm brings rows of one entity together (original
+ *                         order kept inside an entity), seg_ptr[g] .. seg_ptr[g+1] are entity g's rows in the
+ *                         permuted order, seg_key[g] its key, *n_groups_dev the number of entities
+ *                         (DataPartitioner.scala:296-379 without the bounds).
+ * gdmix_csr_gather_rows   the sample block in the new row order (rowptr_out[n_rows+1], col_out / val_out[nnz]);
+ *                         gdmix_gather_f32 does the same for labels / offsets / weights.
+ * gdmix_partition_ids_i64 abs(String.valueOf(id).hashCode) % num_partitions for integer entity ids
+ *                         (PartitionUtils.scala:31-37), bit-exact with gdmix_partition_ids on the decimal string.
+ * gdmix_auc               area under the ROC curve with ties counted half (Evaluator.scala:29-45 ->
+ *                         BinaryClassificationMetrics.areaUnderROC); label > 0 is positive.
+ *                         out3 = { auc, positives, negatives }.  Synchronises the stream once. */
+GDMIX_API int gdmix_partition_workspace_size(int64_t n, size_t *bytes);
+GDMIX_API int gdmix_sort_pairs_u64(const uint64_t *keys_in, int64_t n, int32_t key_bits, uint64_t *keys_out,
+                                   uint32_t *perm_out, void *ws, size_t ws_bytes, void *stream);
+GDMIX_API int gdmix_group_by_key(const uint64_t *keys, int64_t n, int32_t key_bits, uint64_t *keys_sorted, uint32_t *perm,
+                                 int64_t *seg_ptr, uint64_t *seg_key, int64_t *n_groups_dev, void *ws, size_t ws_bytes,
+                                 void *stream);
+GDMIX_API int gdmix_csr_gather_rows(const int64_t *rowptr_in, const int32_t *col_in, const float *val_in,
+                                    const uint32_t *perm, int64_t n_rows, int64_t *rowptr_out, int32_t *col_out,
+                                    float *val_out, void *ws, size_t ws_bytes, void *stream);
+GDMIX_API int gdmix_gather_f32(const float *in, const uint32_t *perm, int64_t n, float *out, void *stream);
+GDMIX_API int gdmix_partition_ids_i64(const int64_t *ids, int64_t n, int32_t num_partitions, int32_t *partition_out,
+                                      void *stream);
+GDMIX_API int gdmix_auc(const float *score, const float *label, int64_t n, double *out3, void *ws, size_t ws_bytes,
+                        void *stream);
 
 /* Replicated host-side solver state of the fixed-effect solve: L-BFGS-B without bounds, reverse
  * communication, the role scipy.optimize.fmin_l_bfgs_b plays at fixed_effect_lr_lbfgs_model.py:635-643.
