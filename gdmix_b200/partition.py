@@ -151,3 +151,29 @@ def regroup_batch(entity, rowptr, gcol, val, label, offset=None, weight=None, ha
             "max_rows": int(rows_e.max().item()) if E else 0, "max_nnz": int(nnz_e.max().item()) if E else 0,
             "max_coef": int(d_e.max().item()) + hi if E else hi, "n_coef": int(theta_ptr[-1].item()),
             "perm": perm, "entity_ids": entity_ids, "uniq_ptr": uniq_ptr, "uniq_global": uniq_global}
+
+
+class GroupedBatch:
+    """A regroup_batch() result with the interface capi.re_fit_device / re_score_device expect of a DeviceBatch."""
+
+    def __init__(self, d):
+        from types import SimpleNamespace
+        self.d = d
+        self.ent_rowptr, self.rowptr, self.theta_ptr = d["ent_rowptr"], d["rowptr"], d["theta_ptr"]
+        self.col, self.val, self.label = d["col"], d["val"], d["label"]
+        self.weight, self.offset = d["weight"], d["offset"]
+        self.host = SimpleNamespace(n_entities=d["n_entities"], n_rows=d["n_rows"], nnz=d["nnz"], n_coef=d["n_coef"],
+                                    max_rows=d["max_rows"], max_nnz=d["max_nnz"], max_coef=d["max_coef"])
+
+    def c_struct(self):
+        h = self.host
+        return capi.ReBatch(h.n_entities, h.n_rows, h.nnz, _tptr(self.ent_rowptr), _tptr(self.rowptr), _tptr(self.col),
+                            _tptr(self.val), _tptr(self.label), _tptr(self.weight), _tptr(self.offset),
+                            _tptr(self.theta_ptr), h.max_rows, h.max_nnz, h.max_coef, 0, None)
+
+    def scatter_to_input_order(self, per_row):
+        """per_row[i] belongs to grouped row i = input row perm[i] -> tensor in input row order."""
+        import torch
+        out = torch.empty_like(per_row)
+        out[self.d["perm"].long()] = per_row
+        return out
