@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgdmix_b200.so")
+LIB_PATH = os.environ.get("GDMIX_B200_LIB") or os.path.join(_HERE, "lib", "libgdmix_b200.so")  # override: kernel experiments
 
 GDMIX_OK = 0
 GDMIX_ERR_INVALID = -1
@@ -18,6 +18,7 @@ GDMIX_ERR_WORKSPACE = -3
 GDMIX_ERR_TOO_LARGE = -4
 GDMIX_ERR_NO_DEVICE = -5
 GDMIX_MAX_M = 32
+GDMIX_MAX_SWEEP = 16
 
 VARIANCE_NONE, VARIANCE_SIMPLE, VARIANCE_FULL = 0, 1, 2
 EPS = float(np.finfo(np.float64).eps)
@@ -30,7 +31,8 @@ SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_w
            "gdmix_host_release", "gdmix_partition_ids", "gdmix_lbfgs_create", "gdmix_lbfgs_iterate",
            "gdmix_lbfgs_info", "gdmix_lbfgs_destroy", "gdmix_launch_count", "gdmix_re_last_plan",
            "gdmix_partition_workspace_size", "gdmix_sort_pairs_u64", "gdmix_group_by_key", "gdmix_csr_gather_rows",
-           "gdmix_gather_f32", "gdmix_partition_ids_i64", "gdmix_auc"]
+           "gdmix_gather_f32", "gdmix_partition_ids_i64", "gdmix_auc", "gdmix_re_fit_sweep",
+           "gdmix_re_last_plan_typical"]
 
 
 class GdmixError(RuntimeError):
@@ -78,6 +80,7 @@ def _load():
     lib.gdmix_launch_count.restype = C.c_int64
     lib.gdmix_host_release.restype = None
     lib.gdmix_re_last_plan.restype = None
+    lib.gdmix_re_last_plan_typical.restype = None
     lib.gdmix_lbfgs_create.restype = C.c_void_p
     lib.gdmix_lbfgs_create.argtypes = [C.c_int64, C.c_void_p]
     lib.gdmix_lbfgs_iterate.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
@@ -120,7 +123,11 @@ def last_plan():
     a = (C.c_int32 * 8)()
     lib.gdmix_re_last_plan(a)
     keys = ["fast", "threads", "ept", "ctas_per_sm", "cap_steps", "smem", "grid", "hist_global"]
-    return dict(zip(keys, list(a)))
+    d = dict(zip(keys, list(a)))
+    lib.gdmix_re_last_plan_typical(a)
+    if a[0]:
+        d["typical"] = dict(zip(["threads", "ept", "ctas_per_sm", "cap_steps", "smem", "max_rows"], list(a)[1:7]))
+    return d
 
 
 def launch_count():
@@ -276,6 +283,32 @@ def re_fit_device(dbatch, opts, theta0=None, want_variance=False, workspace=None
                            _tptr(out["nit"]), _tptr(out["nfev"]), _tptr(out["status"]),
                            _tptr(out.get("variance")), _tptr(workspace), C.c_size_t(workspace.numel()),
                            _stream_ptr(stream)))
+    out["workspace"] = workspace
+    return out
+
+
+def re_fit_sweep_device(dbatch, opts, l2_values, theta0=None, workspace=None, stream=None):
+    """gdmix_re_fit_sweep: len(l2_values) models per entity from one staged copy of each entity's block.
+    Returns tensors with a leading axis over l2_values: theta [n_l2, n_coef], f / nit / nfev / status [n_l2, E]."""
+    import torch
+    h = dbatch.host
+    dev = dbatch.val.device
+    cb = dbatch.c_struct()
+    l2 = np.ascontiguousarray(l2_values, dtype=np.float64)
+    n_l2 = int(l2.shape[0])
+    need = re_workspace_size(cb, opts)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+    E = h.n_entities
+    out = {"theta": torch.empty((n_l2, h.n_coef), dtype=torch.float64, device=dev),
+           "f": torch.empty((n_l2, E), dtype=torch.float64, device=dev),
+           "nit": torch.empty((n_l2, E), dtype=torch.int32, device=dev),
+           "nfev": torch.empty((n_l2, E), dtype=torch.int32, device=dev),
+           "status": torch.empty((n_l2, E), dtype=torch.int32, device=dev)}
+    check(lib.gdmix_re_fit_sweep(C.byref(cb), C.byref(opts), _np_ptr(l2), C.c_int32(n_l2), _tptr(theta0),
+                                 _tptr(out["theta"]), C.c_int64(h.n_coef), _tptr(out["f"]), _tptr(out["nit"]),
+                                 _tptr(out["nfev"]), _tptr(out["status"]), _tptr(workspace),
+                                 C.c_size_t(workspace.numel()), _stream_ptr(stream)))
     out["workspace"] = workspace
     return out
 

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "lib", "libgdmix_b200.so")
+LIB = os.environ.get("GDMIX_LIB_OUT") or os.path.join(HERE, "lib", "libgdmix_b200.so")  # GDMIX_LIB_OUT / GDMIX_NVCC_FLAGS: kernel experiments
 SOURCES = ["api.cu"]
 HEADERS = ["re_kernel.cuh", "re_fast.cuh", "re_variance.cuh", "partition.cuh", "host_lbfgs.h", "re_common.cuh", "re_passes.cuh", "re_lbfgs.cuh", "linesearch.cuh", "aux_kernels.cuh", os.path.join("..", "..", "include", "gdmix_b200.h")]
 
@@ -32,7 +32,7 @@ def build(force=False, verbose=False):
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-cudart", "static",
            "-Xptxas", "-v" if verbose else "-warn-spills",
-           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-o", LIB] + os.environ.get("GDMIX_NVCC_FLAGS", "").split() + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

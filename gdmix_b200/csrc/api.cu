@@ -24,7 +24,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
-thread_local int32_t g_last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+thread_local int32_t g_last_plan[16] = {0};
 
 int fail(int code, const char *fmt, ...)
 {
@@ -83,6 +83,12 @@ struct RePlan {
     int fctas_per_sm = 1;
     int fgrid = 1;
     gdmix::FastLayout fL;
+    // ragged batches: a first fast launch planned for the TYPICAL entity (2.5 x the mean sample count) at the
+    // residency that shape allows; what it defers takes the launch above (planned for the largest entity)
+    int fast0 = 0;
+    int f0G = 128, f0EPT = 1, f0ctas_per_sm = 1, f0grid = 1;
+    gdmix::FastLayout f0L;
+    size_t off_defer0 = 0;
     size_t off_defer = 0, off_arena = 0;
     // entities that cannot be staged at all: X stays in global memory (re_solver_kernel<256, MT, true>)
     int bgrid = 1;
@@ -142,18 +148,20 @@ int fast_regs_of(int G, int EPT, int &regs)
 // whatever the chosen residency leaves, so the sliced-ELL capacity (cap_steps) is as large as it can be;
 // residency is the largest for which an entity of the batch's maximal shape with evenly spread non-zeros
 // fits.  Entities that still do not fit are deferred to the general kernel one by one.
-int plan_fast(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &dev, RePlan &pl)
+struct FastShapePlan {
+    int ok = 0, G = 128, EPT = 1, ctas_per_sm = 1, grid = 1;
+    gdmix::FastLayout L;
+};
+
+// Geometry of one re_fast_kernel launch for entities of up to N_full rows / D_full features / nnz_full non-zeros.
+// `must_fit`: give up (ok = 0) unless an entity of that shape with evenly spread non-zeros fits at some residency;
+// otherwise plan for two CTAs per SM and let whatever does not fit defer.
+int plan_fast_shape(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &dev, uint32_t N_full,
+                    uint32_t D_full, int64_t nnz_full, bool typical, FastShapePlan &fp)
 {
-    pl.fast = 0;
-    const char *env_path = getenv("GDMIX_RE_PATH");
+    fp.ok = 0;
     const char *env_ctas = getenv("GDMIX_FAST_CTAS");
     const char *env_cap = getenv("GDMIX_FAST_CAP_STEPS");  // test hook: shrink the sliced-ELL capacity to force deferrals
-    if (env_path && (strcmp(env_path, "generic") == 0 || strcmp(env_path, "big") == 0)) return GDMIX_OK;
-    const uint32_t hi = o->has_intercept ? 1u : 0u;
-    if (o->m > gdmix::kFastMT) return GDMIX_OK;
-    // Planned for the batch's largest entity when that is a shape this kernel takes; else for a clamped shape
-    // (the entities beyond it are deferred one by one, the others keep the fast kernel).
-    const uint32_t D_full = (uint32_t)b->max_coef - hi, N_full = (uint32_t)b->max_rows;
     const uint32_t D = std::min(D_full, 512u), N = std::min(N_full, 4096u);
     bool clamped = D < D_full || N < N_full;
     int G;
@@ -178,9 +186,10 @@ int plan_fast(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo 
     // the sliced index stream holds 16-bit absolute shared addresses into xt[] and r[]
     if (kStaticSmem + fl.r + 8u * N > 65536u) return GDMIX_OK;
     const uint32_t nrslab = (N + 31) / 32, ncslab = (D + 31) / 32;
-    const uint32_t ar = (uint32_t)((b->max_nnz + (int64_t)N_full - 1) / N_full);
-    const uint32_t ac = D_full ? (uint32_t)((b->max_nnz + (int64_t)D_full - 1) / D_full) : 0;
-    const uint32_t est = nrslab * ((ar + 3) / 4 + 1) + ncslab * ((ac + 3) / 4 + 1);
+    const uint32_t ar = (uint32_t)((nnz_full + (int64_t)N_full - 1) / N_full);
+    const uint32_t ac = D_full ? (uint32_t)((nnz_full + (int64_t)D_full - 1) / D_full) : 0;
+    // columns are never evenly filled: one more step per column slab for the typical-shape plan
+    const uint32_t est = nrslab * ((ar + 3) / 4 + 1) + ncslab * ((ac + 3) / 4 + (typical ? 2 : 1));
     auto cap_for = [&](int k) {
         const int64_t budget = (int64_t)(228 * 1024) / k - 1024 - (int64_t)kStaticSmem - 64;
         return (std::min<int64_t>(budget, (int64_t)dev.smem_optin - kStaticSmem - 64) - (int64_t)fixed) /
@@ -196,24 +205,64 @@ int plan_fast(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo 
             if (env_ctas) break;
         }
     }
-    if (!found) {
+    if (!found && !typical) {
         // the largest entity is not one for this kernel: plan for two CTAs per SM and let the big ones defer
         k = env_ctas ? std::max(1, std::min(atoi(env_ctas), k_hw)) : std::min(2, k_hw);
         cap = cap_for(k);
         found = cap >= 8;
     }
-    if (found) {
-        if (env_cap) cap = std::max<int64_t>(1, std::min<int64_t>(cap, atoi(env_cap)));
+    if (!found) return GDMIX_OK;
+    if (env_cap) cap = std::max<int64_t>(1, std::min<int64_t>(cap, atoi(env_cap)));
+    fp.ok = 1;
+    fp.G = G; fp.EPT = EPT; fp.ctas_per_sm = k;
+    fp.L = gdmix::fast_layout(N, D, W, (uint32_t)cap);
+    const int64_t want = (int64_t)dev.sm_count * k;
+    fp.grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, b->n_entities));
+    return GDMIX_OK;
+}
+
+// Decides whether the batch goes through re_fast_kernel and with what geometry.  Shared memory per CTA is
+// whatever the chosen residency leaves, so the sliced-ELL capacity (cap_steps) is as large as it can be;
+// residency is the largest for which an entity of the batch's maximal shape with evenly spread non-zeros
+// fits.  Entities that still do not fit are deferred to the general kernel one by one.
+// A ragged batch (largest entity well above the typical one) gets TWO launches: the first planned for 2.5 x the
+// mean sample count -- the residency the many small entities deserve -- deferring the rest to the second.
+int plan_fast(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &dev, RePlan &pl)
+{
+    pl.fast = 0; pl.fast0 = 0;
+    const char *env_path = getenv("GDMIX_RE_PATH");
+    const char *env_tiers = getenv("GDMIX_FAST_TIERS");    // test hook: "1" disables the typical-shape launch
+    if (env_path && (strcmp(env_path, "generic") == 0 || strcmp(env_path, "big") == 0)) return GDMIX_OK;
+    const uint32_t hi = o->has_intercept ? 1u : 0u;
+    if (o->m > gdmix::kFastMT) return GDMIX_OK;
+    const uint32_t D_full = (uint32_t)b->max_coef - hi, N_full = (uint32_t)b->max_rows;
+    FastShapePlan big;
+    int rc = plan_fast_shape(b, o, dev, N_full, D_full, b->max_nnz, false, big);
+    if (rc) return rc;
+    if (big.ok) {
         pl.fast = 1;
-        pl.fG = G; pl.fEPT = EPT; pl.fctas_per_sm = k;
-        pl.fL = gdmix::fast_layout(N, D, W, (uint32_t)cap);
-        const int64_t want = (int64_t)dev.sm_count * k;
-        pl.fgrid = (int)std::max<int64_t>(1, std::min<int64_t>(want, b->n_entities));
+        pl.fG = big.G; pl.fEPT = big.EPT; pl.fctas_per_sm = big.ctas_per_sm; pl.fgrid = big.grid; pl.fL = big.L;
+        if (b->n_rows > 0 && b->nnz > 0 && b->n_entities > 0 && !(env_tiers && atoi(env_tiers) == 1) &&
+            o->threads_per_entity == 0) {
+            const int64_t mean_rows = (b->n_rows + b->n_entities - 1) / b->n_entities;
+            const uint32_t N_typ = (uint32_t)std::min<int64_t>(N_full, ((5 * mean_rows + 1) / 2 + 31) & ~(int64_t)31);
+            const int64_t nnz_per_row = (b->nnz + b->n_rows - 1) / b->n_rows;
+            if ((int64_t)N_typ * 3 <= (int64_t)N_full * 2) {
+                FastShapePlan typ;
+                rc = plan_fast_shape(b, o, dev, N_typ, D_full, (int64_t)N_typ * nnz_per_row, true, typ);
+                if (rc) return rc;
+                if (typ.ok && typ.ctas_per_sm * typ.G > big.ctas_per_sm * big.G) {
+                    pl.fast0 = 1;
+                    pl.f0G = typ.G; pl.f0EPT = typ.EPT; pl.f0ctas_per_sm = typ.ctas_per_sm; pl.f0grid = typ.grid;
+                    pl.f0L = typ.L;
+                }
+            }
+        }
         return GDMIX_OK;
     }
     if (env_path && strcmp(env_path, "fast") == 0)
         return fail(GDMIX_ERR_TOO_LARGE, "GDMIX_RE_PATH=fast but the batch shape (%u rows, %d nnz, %u features) "
-                    "does not fit the fast kernel", N, b->max_nnz, D);
+                    "does not fit the fast kernel", N_full, b->max_nnz, D_full);
     return GDMIX_OK;
 }
 
@@ -264,7 +313,8 @@ int plan_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &d
     int rc = plan_fast(b, o, dev, pl);
     if (rc) return rc;
     const size_t list_bytes = ((size_t)b->n_entities * 4 + 255) & ~(size_t)255;
-    pl.off_defer = kQueueBytes;
+    pl.off_defer0 = kQueueBytes;
+    pl.off_defer = pl.off_defer0 + (pl.fast ? list_bytes : 0);   // reserved whether or not the typical-shape launch is planned
     pl.off_defer_b = pl.off_defer + (pl.fast ? list_bytes : 0);
     pl.off_arena = pl.off_defer_b + list_bytes;
     pl.off_barena = pl.off_arena + (size_t)pl.arena_stride * (size_t)want;
@@ -310,7 +360,7 @@ int launch_re_t(const gdmix::ReArgs &args, const RePlan &pl, cudaStream_t st)
 
 
 template <int G, int EPT>
-int launch_fast_t(const gdmix::FastArgs &fa, const RePlan &pl, cudaStream_t st)
+int launch_fast_t(const gdmix::FastArgs &fa, int grid, cudaStream_t st)
 {
     static std::atomic<int> configured{0};
     if (!configured.load()) {
@@ -318,7 +368,7 @@ int launch_fast_t(const gdmix::FastArgs &fa, const RePlan &pl, cudaStream_t st)
                                       227 * 1024 - (int)kStaticSmem));
         configured.store(1);
     }
-    gdmix::re_fast_kernel<G, EPT><<<pl.fgrid, G, pl.fL.total_bytes, st>>>(fa);
+    gdmix::re_fast_kernel<G, EPT><<<grid, G, fa.L.total_bytes, st>>>(fa);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return GDMIX_OK;
@@ -339,23 +389,24 @@ int launch_big_t(const gdmix::ReArgs &args, const RePlan &pl, cudaStream_t st)
     return GDMIX_OK;
 }
 
-int launch_fast(const gdmix::FastArgs &fa, const RePlan &pl, cudaStream_t st)
+int launch_fast(const gdmix::FastArgs &fa, int G, int EPT, int grid, cudaStream_t st)
 {
-    switch (pl.fG * 4 + pl.fEPT) {
-    case 32 * 4 + 1: return launch_fast_t<32, 1>(fa, pl, st);
-    case 32 * 4 + 2: return launch_fast_t<32, 2>(fa, pl, st);
-    case 64 * 4 + 1: return launch_fast_t<64, 1>(fa, pl, st);
-    case 64 * 4 + 2: return launch_fast_t<64, 2>(fa, pl, st);
-    case 128 * 4 + 1: return launch_fast_t<128, 1>(fa, pl, st);
-    case 128 * 4 + 2: return launch_fast_t<128, 2>(fa, pl, st);
-    case 256 * 4 + 1: return launch_fast_t<256, 1>(fa, pl, st);
-    default: return launch_fast_t<256, 2>(fa, pl, st);
+    switch (G * 4 + EPT) {
+    case 32 * 4 + 1: return launch_fast_t<32, 1>(fa, grid, st);
+    case 32 * 4 + 2: return launch_fast_t<32, 2>(fa, grid, st);
+    case 64 * 4 + 1: return launch_fast_t<64, 1>(fa, grid, st);
+    case 64 * 4 + 2: return launch_fast_t<64, 2>(fa, grid, st);
+    case 128 * 4 + 1: return launch_fast_t<128, 1>(fa, grid, st);
+    case 128 * 4 + 2: return launch_fast_t<128, 2>(fa, grid, st);
+    case 256 * 4 + 1: return launch_fast_t<256, 1>(fa, grid, st);
+    default: return launch_fast_t<256, 2>(fa, grid, st);
     }
 }
 
 int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const double *theta_in, double *theta_out,
               double *f_out, int32_t *nit, int32_t *nfev, int32_t *status, double *var_out, double *g_out,
-              void *workspace, size_t workspace_bytes, cudaStream_t st)
+              void *workspace, size_t workspace_bytes, cudaStream_t st, const double *l2_values = nullptr,
+              int n_l2 = 0, int64_t coef_stride = 0)
 {
     if (!b || !o) return fail(GDMIX_ERR_INVALID, "null batch/opts");
     if (b->n_entities < 0) return fail(GDMIX_ERR_INVALID, "n_entities < 0");
@@ -387,6 +438,9 @@ int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const d
     a.mode = mode;
     a.hist_global = pl.hist_global;
     a.smem_bytes = pl.smem;
+    a.n_l2 = n_l2;
+    a.sweep_coef_stride = coef_stride;
+    for (int j = 0; j < n_l2; j++) a.l2_sweep[j] = l2_values[j];
     CUDA_TRY(cudaMemsetAsync(workspace, 0, kQueueBytes, st));
     g_last_plan[0] = pl.fast; g_last_plan[1] = pl.fast ? pl.fG : pl.G; g_last_plan[2] = pl.fast ? pl.fEPT : 0;
     g_last_plan[3] = pl.fast ? pl.fctas_per_sm : pl.ctas_per_sm;
@@ -394,15 +448,32 @@ int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const d
     g_last_plan[5] = pl.fast ? (int32_t)pl.fL.total_bytes : (int32_t)pl.smem;
     g_last_plan[6] = pl.fast ? pl.fgrid : pl.grid;
     g_last_plan[7] = pl.hist_global;
+    g_last_plan[8] = pl.fast0; g_last_plan[9] = pl.f0G; g_last_plan[10] = pl.f0EPT; g_last_plan[11] = pl.f0ctas_per_sm;
+    g_last_plan[12] = pl.fast0 ? (int32_t)pl.f0L.cap_steps : 0; g_last_plan[13] = pl.fast0 ? (int32_t)pl.f0L.total_bytes : 0;
+    g_last_plan[14] = pl.fast0 ? (int32_t)pl.f0L.max_n : 0; g_last_plan[15] = 0;
     if (pl.fast) {
         // fast kernel first; what it defers (entities whose sliced form does not fit) is drained by the
-        // general kernel from the list, with its own work counter
+        // general kernel from the list, with its own work counter.  Work counters in the workspace:
+        // [0] first launch, [1] general kernel, [2] list A length, [3] variance, [4] global-X kernel,
+        // [5] list B length, [6] second fast launch, [7] list A0 length.
         gdmix::FastArgs fa;
         fa.a = a;
+        if (pl.fast0) {
+            // ragged batch: typical-shape launch over everything, deferring to list A0 ...
+            fa.L = pl.f0L;
+            fa.defer_list = (int32_t *)((unsigned char *)workspace + pl.off_defer0);
+            fa.defer_count = (int32_t *)workspace + 7;
+            rc = launch_fast(fa, pl.f0G, pl.f0EPT, pl.f0grid, st);
+            if (rc) return rc;
+            // ... which the launch planned for the largest entity drains
+            fa.a.queue = (int32_t *)workspace + 6;
+            fa.a.todo = fa.defer_list;
+            fa.a.todo_count = fa.defer_count;
+        }
         fa.L = pl.fL;
         fa.defer_list = (int32_t *)((unsigned char *)workspace + pl.off_defer);
         fa.defer_count = (int32_t *)workspace + 2;
-        rc = launch_fast(fa, pl, st);
+        rc = launch_fast(fa, pl.fG, pl.fEPT, pl.fgrid, st);
         if (rc) return rc;
         a.queue = (int32_t *)workspace + 1;
         a.todo = fa.defer_list;
@@ -411,6 +482,26 @@ int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const d
     // whatever the staged kernels cannot hold goes to list B
     a.defer_list = (int32_t *)((unsigned char *)workspace + pl.off_defer_b);
     a.defer_count = (int32_t *)workspace + 5;
+    // The general kernels solve one model per launch: a sweep runs them once per weight over the same lists
+    // (only what the fast kernel deferred, when there is one), with their work counters rewound in between.
+    const int n_models = n_l2 > 0 ? n_l2 : 1;
+    const gdmix::ReArgs a_first = a;
+    for (int j = 0; j < n_models; j++) {
+    a = a_first;
+    a.n_l2 = 0;
+    if (n_l2 > 0) {
+        a.o.l2 = l2_values[j];
+        a.theta_out = theta_out + (int64_t)j * coef_stride;
+        if (f_out) a.f_out = f_out + (int64_t)j * b->n_entities;
+        if (nit) a.nit = nit + (int64_t)j * b->n_entities;
+        if (nfev) a.nfev = nfev + (int64_t)j * b->n_entities;
+        if (status) a.status = status + (int64_t)j * b->n_entities;
+        if (j > 0) {
+            // counters: [0] / [1] general queue, [4] list-B queue, [5] list-B length ([2] = fast kernel's list length stays)
+            CUDA_TRY(cudaMemsetAsync((int32_t *)workspace + (pl.fast ? 1 : 0), 0, 4, st));
+            CUDA_TRY(cudaMemsetAsync((int32_t *)workspace + 4, 0, 8, st));
+        }
+    }
     if (pl.MT == 10) {
         switch (pl.G) {
         case 32: rc = launch_re_t<32, 10>(a, pl, st); break;
@@ -440,6 +531,8 @@ int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const d
         g2.smem_bytes = pl.bsmem;
         rc = (pl.MT == 10) ? launch_big_t<10>(g2, pl, st) : launch_big_t<32>(g2, pl, st);
     }
+    if (rc) return rc;
+    }   // models of the sweep
     if (rc || !full_var) return rc;
     // FULL variance at the un-thresholded optimum, then the threshold (re_variance.cuh)
     gdmix::VarArgs v;
@@ -557,7 +650,12 @@ int gdmix_device_info(int32_t *sm_count, int32_t *smem_per_block_optin, int32_t 
 
 void gdmix_re_last_plan(int32_t *out8)
 {
-    if (out8) memcpy(out8, g_last_plan, sizeof(g_last_plan));
+    if (out8) memcpy(out8, g_last_plan, 8 * sizeof(int32_t));
+}
+
+void gdmix_re_last_plan_typical(int32_t *out8)
+{
+    if (out8) memcpy(out8, g_last_plan + 8, 8 * sizeof(int32_t));
 }
 
 int gdmix_re_workspace_size(const gdmix_re_batch *batch, const gdmix_lr_opts *opts, size_t *bytes)
@@ -590,6 +688,20 @@ int gdmix_re_fit(const gdmix_re_batch *batch, const gdmix_lr_opts *opts, const d
         return fail(GDMIX_ERR_INVALID, "var_out given but variance_mode is NONE");
     return launch_re(batch, opts, gdmix::kModeFit, theta0, theta_out, f_out, nit, nfev, status, var_out, nullptr,
                      workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gdmix_re_fit_sweep(const gdmix_re_batch *batch, const gdmix_lr_opts *opts, const double *l2_values, int32_t n_l2,
+                       const double *theta0, double *theta_out, int64_t coef_stride, double *f_out, int32_t *nit,
+                       int32_t *nfev, int32_t *status, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!theta_out || !l2_values) return fail(GDMIX_ERR_INVALID, "null theta_out / l2_values");
+    if (n_l2 < 1 || n_l2 > GDMIX_MAX_SWEEP)
+        return fail(GDMIX_ERR_INVALID, "n_l2 = %d outside [1, %d]", n_l2, GDMIX_MAX_SWEEP);
+    if (coef_stride < 0) return fail(GDMIX_ERR_INVALID, "coef_stride < 0");
+    for (int j = 0; j < n_l2; j++)
+        if (!(l2_values[j] >= 0.0)) return fail(GDMIX_ERR_INVALID, "l2_values[%d] is negative or NaN", j);
+    return launch_re(batch, opts, gdmix::kModeFit, theta0, theta_out, f_out, nit, nfev, status, nullptr, nullptr,
+                     workspace, workspace_bytes, (cudaStream_t)stream, l2_values, n_l2, coef_stride);
 }
 
 int gdmix_re_score(const gdmix_re_batch *b, const gdmix_lr_opts *o, const double *theta, const uint8_t *has_model,

@@ -58,6 +58,12 @@ struct ReArgs {
     int32_t mode;
     int32_t hist_global;        // keep the (S, Y) history in the global arena even if it would fit on chip
     uint32_t smem_bytes;        // dynamic shared memory given to the kernel
+    // L2 sweep (gdmix_re_fit_sweep): n_l2 models per entity from ONE staged copy of its block.  Model j uses
+    // l2_sweep[j] and writes theta_out + j * sweep_coef_stride, {f_out, nit, nfev, status} + j * n_entities.
+    // n_l2 == 0: the single model of o.l2.
+    double l2_sweep[GDMIX_MAX_SWEEP];
+    int32_t n_l2;
+    int64_t sweep_coef_stride;
 };
 
 // Byte layout of one entity's on-chip state.  Host (planning) and device (carving) share it.

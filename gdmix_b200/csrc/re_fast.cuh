@@ -240,27 +240,26 @@ __device__ __forceinline__ double lds_f64(const uint32_t shared_addr)
 // address arithmetic.
 __device__ __forceinline__ double sell_dot(const float4 *pv, const uint2 *pi, const uint32_t nsteps)
 {
+    // Software pipelined: the value / address quads of step k+1 are in flight while step k's four gathers and
+    // FMAs run (index load -> gather -> FMA is a chain of two shared-memory round trips otherwise).
+    // Accumulation order per chain: steps ascending, as the data is laid out.
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    uint32_t k = 0;
-    for (; k + 2 <= nsteps; k += 2) {
-        const float4 va = pv[k * kStepQuads], vb = pv[(k + 1) * kStepQuads];
-        const uint2 ca = pi[k * kStepQuads], cb = pi[(k + 1) * kStepQuads];
+    if (nsteps == 0) return 0.0;
+    float4 va = pv[0];
+    uint2 ca = pi[0];
+#pragma unroll 2
+    for (uint32_t k = 1; k < nsteps; k++) {
+        const float4 vn = pv[k * kStepQuads];
+        const uint2 cn = pi[k * kStepQuads];
         const double x0 = lds_f64(ca.x & 0xffffu), x1 = lds_f64(ca.x >> 16);
         const double x2 = lds_f64(ca.y & 0xffffu), x3 = lds_f64(ca.y >> 16);
-        const double x4 = lds_f64(cb.x & 0xffffu), x5 = lds_f64(cb.x >> 16);
-        const double x6 = lds_f64(cb.y & 0xffffu), x7 = lds_f64(cb.y >> 16);
         s0 = fma((double)va.x, x0, s0);
         s1 = fma((double)va.y, x1, s1);
         s2 = fma((double)va.z, x2, s2);
         s3 = fma((double)va.w, x3, s3);
-        s0 = fma((double)vb.x, x4, s0);
-        s1 = fma((double)vb.y, x5, s1);
-        s2 = fma((double)vb.z, x6, s2);
-        s3 = fma((double)vb.w, x7, s3);
+        va = vn; ca = cn;
     }
-    if (k < nsteps) {
-        const float4 va = pv[k * kStepQuads];
-        const uint2 ca = pi[k * kStepQuads];
+    {
         const double x0 = lds_f64(ca.x & 0xffffu), x1 = lds_f64(ca.x >> 16);
         const double x2 = lds_f64(ca.y & 0xffffu), x3 = lds_f64(ca.y >> 16);
         s0 = fma((double)va.x, x0, s0);
@@ -488,7 +487,10 @@ __device__ __forceinline__ void fast_trial(const FastArgs &fa, unsigned char *sm
 //       next direction d = -gamma g - S u + gamma Y w from registers, next trial point x + d -> B1
 // ---------------------------------------------------------------------------------------------------------
 template <int G, int EPT>
-__global__ void __launch_bounds__(G, (G <= 128) ? 384 / G : 1) re_fast_kernel(const FastArgs fa)
+// Registers: one feature slot per thread keeps 40 history registers and fits 128 per thread (512 threads per SM
+// more than the two-slot variant's 168, which is what lets the typical-shape launch of a ragged batch run four
+// 128-thread CTAs per SM).
+__global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / G : 1)) re_fast_kernel(const FastArgs fa)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double red[2 * kMaxWarps * kRedK];
@@ -506,7 +508,13 @@ __global__ void __launch_bounds__(G, (G <= 128) ? 384 / G : 1) re_fast_kernel(co
 
     for (;;) {
         group_sync<G>();  // previous entity fully emitted before its memory is reused
-        if (tid == 0) { s_entity = atomicAdd(a.queue, 1); s_flag = 0; }
+        if (tid == 0) {
+            // plain launch: entities 0 .. n_entities; second tier: the list the typical-shape launch deferred
+            int idx = atomicAdd(a.queue, 1);
+            if (a.todo) idx = (idx < *a.todo_count) ? a.todo[idx] : 0x7fffffff;
+            s_entity = idx;
+            s_flag = 0;
+        }
         group_sync<G>();
         const int e = s_entity;
         if ((int64_t)e >= a.b.n_entities) break;
@@ -539,6 +547,12 @@ __global__ void __launch_bounds__(G, (G <= 128) ? 384 / G : 1) re_fast_kernel(co
         double *part = (double *)(smem + L.part);
         if (W == 1) prefetch_entity_l2(a.b, (int64_t)e + gridDim.x, lane);
 
+        // One solve per regularisation weight out of the block just staged (gdmix_re_fit_sweep; a plain fit is
+        // the sweep of length one over o.l2).
+        const int n_models = a.n_l2 > 0 ? a.n_l2 : 1;
+        for (int li = 0; li < n_models; li++) {
+        if (li) group_sync<G>();   // the previous model fully emitted before the solve block is rewritten
+
         // ---- solver state: this thread's slots of x, g, direction and of every history vector -----------
         // (the iterate and its gradient live in smem xcur / gold, each thread touching only its own slots;
         //  the intercept's components of the stored pairs in smem icept[], touched by warp 0 only)
@@ -567,7 +581,7 @@ __global__ void __launch_bounds__(G, (G <= 128) ? 384 / G : 1) re_fast_kernel(co
 
         const double epsmch = 2.220446049250313e-16;
         const double ftol = 1e-3, gtol = 0.9, stpmx = 1e10;
-        const double l2 = a.o.l2, inv_n = 1.0 / (double)E.n;
+        const double l2 = a.n_l2 > 0 ? a.l2_sweep[li] : a.o.l2, inv_n = 1.0 / (double)E.n;
         enum { PH_INIT = 0, PH_FIRST = 1, PH_MORE = 2 };
         int phase = PH_INIT, nfev = 0, iter = 0, status = GDMIX_SOLVE_CONVERGED, ifun = 0, ls_slot = 0;
         double f = 0.0, gd = 0.0, fold = 0.0, gdold = 0.0, stp = 0.0;
@@ -892,7 +906,8 @@ __global__ void __launch_bounds__(G, (G <= 128) ? 384 / G : 1) re_fast_kernel(co
         if (emitted) continue;
 
         // ---- emit ---------------------------------------------------------------------------------------
-        const int64_t t0 = a.b.theta_ptr[e];
+        const int64_t t0 = a.b.theta_ptr[e] + (int64_t)li * a.sweep_coef_stride;
+        const int64_t eo = (int64_t)e + (int64_t)li * a.b.n_entities;
         const double thr = a.o.sparsity_threshold;
 #pragma unroll
         for (int k = 0; k < EPT; k++) {
@@ -901,10 +916,10 @@ __global__ void __launch_bounds__(G, (G <= 128) ? 384 / G : 1) re_fast_kernel(co
         }
         if (tid == 0) {
             if (E.hi) a.theta_out[t0] = (thr > 0.0 && fabs(x0) <= thr) ? 0.0 : x0;
-            if (a.f_out) a.f_out[e] = f;
-            if (a.nit) a.nit[e] = iter;
-            if (a.nfev) a.nfev[e] = nfev;
-            if (a.status) a.status[e] = status;
+            if (a.f_out) a.f_out[eo] = f;
+            if (a.nit) a.nit[eo] = iter;
+            if (a.nfev) a.nfev[eo] = nfev;
+            if (a.status) a.status[eo] = status;
         }
         if (a.var_out && a.o.variance_mode == GDMIX_VARIANCE_SIMPLE) {
             // var_j = 1 / (sum_i x_ij^2 rho_i (1-rho_i) w_i + l2 [j regularised] + 1e-12)
@@ -950,11 +965,12 @@ __global__ void __launch_bounds__(G, (G <= 128) ? 384 / G : 1) re_fast_kernel(co
                 }
                 const uint32_t sp = b * 32u + lane;
                 if (sp < E.d)
-                    a.var_out[t0 + E.hi + ((const uint16_t *)(smem + L.colperm))[sp]] = 1.0 / ((h + a.o.l2) + 1.0e-12);
+                    a.var_out[t0 + E.hi + ((const uint16_t *)(smem + L.colperm))[sp]] = 1.0 / ((h + l2) + 1.0e-12);
             }
             if (E.hi && tid == 0)
-                a.var_out[t0] = 1.0 / ((dsum[0] + (a.o.regularize_bias ? a.o.l2 : 0.0)) + 1.0e-12);
+                a.var_out[t0] = 1.0 / ((dsum[0] + (a.o.regularize_bias ? l2 : 0.0)) + 1.0e-12);
         }
+        }   // models of the sweep
     }
 }
 

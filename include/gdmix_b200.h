@@ -65,6 +65,7 @@ typedef enum gdmix_status {
     GDMIX_ERR_NO_DEVICE = -5    /* no sm_100 device */
 } gdmix_status;
 
+#define GDMIX_MAX_SWEEP 16      /* most regularisation weights one gdmix_re_fit_sweep call takes */
 #define GDMIX_MAX_M 32          /* largest supported number of L-BFGS curvature pairs */
 
 /* Per-entity solver status, mirrors scipy's warnflag (fmin_l_bfgs_b). */
@@ -162,6 +163,20 @@ GDMIX_API int gdmix_re_loss_grad(const gdmix_re_batch *batch, const gdmix_lr_opt
 GDMIX_API int gdmix_re_fit(const gdmix_re_batch *batch, const gdmix_lr_opts *opts, const double *theta0,
                            double *theta_out, double *f_out, int32_t *nit, int32_t *nfev, int32_t *status,
                            double *var_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Regularisation sweep (BASELINE.json configs[4]): n_l2 models per entity, model j being exactly what
+ * gdmix_re_fit returns with opts->l2 = l2_values[j] (same theta0 for every j), but each entity's block is read
+ * from HBM and staged on chip ONCE for all of them.  In the reference a sweep over l2_reg_weight is n_l2 separate
+ * training jobs over the same partitions (gdmix-workflow hyper-parameter loop; params l2_reg_weight at
+ * base_lr_params.py:19).  l2_values is a HOST array, 1 <= n_l2 <= GDMIX_MAX_SWEEP.
+ *   theta_out   [n_l2][coef_stride], coef_stride >= theta_ptr[E]; model j of entity e at
+ *               theta_out + j * coef_stride + theta_ptr[e]
+ *   f_out,nit,nfev,status   [n_l2][E], any may be NULL
+ * Workspace: gdmix_re_workspace_size of the same batch / opts. */
+GDMIX_API int gdmix_re_fit_sweep(const gdmix_re_batch *batch, const gdmix_lr_opts *opts, const double *l2_values,
+                                 int32_t n_l2, const double *theta0, double *theta_out, int64_t coef_stride,
+                                 double *f_out, int32_t *nit, int32_t *nfev, int32_t *status, void *workspace,
+                                 size_t workspace_bytes, void *stream);
 
 /* Scoring: logit = x.theta (+ intercept) + offset, per_coordinate = logit - offset, both
  * rounded to fp32 as the reference's Avro `float` fields are.  has_model[e] == 0 (or
@@ -284,6 +299,12 @@ GDMIX_API void gdmix_lbfgs_destroy(gdmix_lbfgs *h);
  * After a fast-path call the number of entities it deferred to the general kernel is the third int32 of the
  * workspace. */
 GDMIX_API void gdmix_re_last_plan(int32_t *out8);
+/* Ragged batches (largest entity well above 2.5 x the mean sample count) get a first fast-kernel launch planned
+ * for the typical entity, ahead of the one gdmix_re_last_plan describes (which then only drains what the first
+ * deferred): out8 = { planned (0/1), threads per entity, features per thread, CTAs per SM, sliced-ELL capacity,
+ * dynamic shared memory per CTA, rows per entity it is planned for, 0 }.  Entities it deferred: eighth int32 of
+ * the workspace. */
+GDMIX_API void gdmix_re_last_plan_typical(int32_t *out8);
 
 /* Number of kernel launches issued by this library since load (for bench accounting). */
 GDMIX_API int64_t gdmix_launch_count(void);

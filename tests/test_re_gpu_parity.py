@@ -333,3 +333,89 @@ def test_oversized_entities_are_solved_not_rejected(re_path):
                             ob["w"][r0:r1], ob["off"][r0:r1])
         np.testing.assert_allclose(out["variance"][hb.theta_ptr[e]:hb.theta_ptr[e + 1]],
                                    O.re_variance(blk, oo, th_o[hb.theta_ptr[e]:hb.theta_ptr[e + 1]], "simple"), rtol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(300, 64, 64, 16), (120, 128, 256, 32)])
+def test_l2_sweep_equals_separate_fits(shape):
+    """BASELINE.json configs[4]: a sweep over l2_reg_weight solved from ONE staged copy of every entity block.
+    Model j must be bit-for-bit what gdmix_re_fit returns with l2 = l2_values[j] (in the reference a sweep is
+    n separate training jobs), and match the oracle run with that weight."""
+    E, n, d, k = shape
+    hb = make_batch(E, n, d, k, seed=77, weights=True)
+    db = capi.DeviceBatch(hb)
+    l2s = [0.1, 1.0, 10.0, 100.0]
+    sw = capi.re_fit_sweep_device(db, capi.make_opts(l2=123.0), l2s)
+    torch.cuda.synchronize()
+    for j, l2 in enumerate(l2s):
+        opts = capi.make_opts(l2=l2)
+        one = capi.re_fit_device(db, opts)
+        torch.cuda.synchronize()
+        for key in ("theta", "f", "nit", "nfev", "status"):
+            assert torch.equal(sw[key][j], one[key]), (key, l2)
+        th_o, f_o, nit_o, nfev_o, st_o = O.re_fit_batch(_oracle_batch(hb), _oracle_opts(opts), e0=0, e1=60)
+        tp = hb.theta_ptr
+        rel = _rel_per_entity(sw["theta"][j].cpu().numpy()[:tp[60]], th_o[:tp[60]], tp[:61])
+        assert rel.max() <= REL_TOL, (l2, rel.max())
+        assert (sw["nit"][j].cpu().numpy()[:60] == nit_o[:60]).all()
+
+
+def test_l2_sweep_with_deferred_entities(monkeypatch, re_path):
+    """Entities the fast kernel defers are swept by the general kernel, one launch per weight, same results."""
+    if re_path == "auto":
+        monkeypatch.setenv("GDMIX_FAST_CAP_STEPS", "30")
+    hb = make_batch(200, 64, 64, 16, seed=78, ragged=True)
+    db = capi.DeviceBatch(hb)
+    l2s = [0.5, 5.0, 50.0]
+    sw = capi.re_fit_sweep_device(db, capi.make_opts(), l2s)
+    for j, l2 in enumerate(l2s):
+        one = capi.re_fit_device(db, capi.make_opts(l2=l2))
+        torch.cuda.synchronize()
+        for key in ("theta", "f", "nit", "nfev", "status"):
+            assert torch.equal(sw[key][j], one[key]), (key, l2)
+
+
+def test_l2_sweep_rejects_bad_arguments():
+    hb = make_batch(8, 16, 24, 4, seed=1)
+    db = capi.DeviceBatch(hb)
+    with pytest.raises(capi.GdmixError):
+        capi.re_fit_sweep_device(db, capi.make_opts(), [1.0] * 17)
+    with pytest.raises(capi.GdmixError):
+        capi.re_fit_sweep_device(db, capi.make_opts(), [1.0, -2.0])
+
+
+def test_ragged_batch_takes_two_fast_tiers(monkeypatch, re_path):
+    """A batch whose largest entity is far above the typical one is planned twice: a first fast launch for
+    2.5 x the mean sample count at high residency, whose deferrals the launch planned for the largest entity
+    drains.  Same answers as the single-tier plan and as the oracle."""
+    if re_path != "auto":
+        pytest.skip("fast path only")
+    small, large = make_batch(380, 40, 64, 16, seed=91, ragged=True), make_batch(20, 600, 64, 16, seed=92)
+    hb = capi.HostBatch(np.concatenate([small.ent_rowptr, large.ent_rowptr[1:] + small.ent_rowptr[-1]]),
+                        np.concatenate([small.rowptr, large.rowptr[1:] + small.rowptr[-1]]),
+                        np.concatenate([small.col, large.col]), np.concatenate([small.val, large.val]),
+                        np.concatenate([small.label, large.label]), None,
+                        np.concatenate([small.offset, large.offset]),
+                        np.concatenate([small.theta_ptr, large.theta_ptr[1:] + small.theta_ptr[-1]]))
+    n_e = np.diff(hb.ent_rowptr)
+    assert n_e.max() > 3 * n_e.mean()
+    opts = capi.make_opts(l2=1.0)
+    db = capi.DeviceBatch(hb)
+    two = capi.re_fit_device(db, opts)
+    torch.cuda.synchronize()
+    plan = capi.last_plan()
+    assert plan["fast"] == 1 and "typical" in plan, plan
+    counters = two["workspace"][:32].view(torch.int32).cpu().numpy()
+    print("plan", plan, "tier-1 deferred", counters[7], "tier-2 deferred", counters[2])
+    assert 0 < counters[7] < hb.n_entities and counters[2] == 0
+    monkeypatch.setenv("GDMIX_FAST_TIERS", "1")
+    one = capi.re_fit_device(db, opts)
+    torch.cuda.synchronize()
+    assert "typical" not in capi.last_plan()
+    for k in ("nit", "nfev", "status"):
+        assert torch.equal(two[k], one[k]), k
+    rel = _rel_per_entity(two["theta"].cpu().numpy(), one["theta"].cpu().numpy(), hb.theta_ptr)
+    assert rel.max() <= 1e-9, rel.max()
+    th_o, f_o, nit_o, nfev_o, st_o = O.re_fit_batch(_oracle_batch(hb), _oracle_opts(opts))
+    rel = _rel_per_entity(two["theta"].cpu().numpy(), th_o, hb.theta_ptr)
+    assert rel.max() <= REL_TOL, rel.max()
+    assert (two["nit"].cpu().numpy() == nit_o).all()
