@@ -277,8 +277,9 @@ def run_ours(args):
         h.copy_(t)
         return h
     h_ent = pinned(data["ent_rowptr"][:Ee + 1]); h_row = pinned(data["rowptr"][:rows_e + 1])
-    # local column indices cross PCIe as uint16 (every entity has 256 local features) and are widened on the device
-    h_col = pinned(data["col"][:nnz_e].to(torch.int16)); h_val = pinned(data["val"][:nnz_e])
+    # local column indices cross PCIe as one byte each (every entity has 256 local features: gdmix_re_batch.col8)
+    # and are widened on the device
+    h_col = pinned(data["col"][:nnz_e].to(torch.uint8)); h_val = pinned(data["val"][:nnz_e])
     h_lab = pinned(data["label"][:rows_e]); h_off = pinned(data["offset"][:rows_e])
     h_tp = pinned(data["theta_ptr"][:Ee + 1])
     h_theta = torch.empty(coef_e, dtype=torch.float64, pin_memory=True)
@@ -288,7 +289,7 @@ def run_ours(args):
     h_st = torch.empty(Ee, dtype=torch.int32, pin_memory=True)
     hcb = capi.ReBatch(Ee, rows_e, nnz_e, h_ent.data_ptr(), h_row.data_ptr(), None, h_val.data_ptr(),
                        h_lab.data_ptr(), None, h_off.data_ptr(), h_tp.data_ptr(), w["n"], w["n"] * w["k"],
-                       w["d"] + 1, 0, h_col.data_ptr())
+                       w["d"] + 1, 0, None, h_col.data_ptr())
 
     def e2e_step():
         capi.check(capi.lib.gdmix_re_fit_host(C.byref(hcb), C.byref(opts), None, C.c_void_p(h_theta.data_ptr()),
@@ -307,11 +308,11 @@ def run_ours(args):
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    h2d = 8 * (Ee + 1) * 2 + 8 * (rows_e + 1) + 6 * nnz_e + 8 * rows_e
+    h2d = 8 * (Ee + 1) * 2 + 8 * (rows_e + 1) + 5 * nnz_e + 8 * rows_e
     d2h = 8 * coef_e + 8 * Ee + 12 * Ee
     e2e = {"value": world * Ee * e2e_steps / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "entities_per_step": Ee, "steps": e2e_steps,
-           "api": "gdmix_re_fit_host (pinned host CSR in -- fp32 values, uint16 local columns -- host coefficients out)",
+           "api": "gdmix_re_fit_host (pinned host CSR in -- fp32 values, uint8 local columns -- host coefficients out)",
            "host_theta_checksum": float(h_theta.sum().item())}
     capi.lib.gdmix_host_release()
 
@@ -342,7 +343,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--entities", type=int, default=1_000_000, help="entities per GPU")
-    ap.add_argument("--e2e-entities", type=int, default=131072)
+    ap.add_argument("--e2e-entities", type=int, default=524288)
     ap.add_argument("--e2e-chunk", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="entities for the cpu_baseline leg (0 = ~15 s of work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

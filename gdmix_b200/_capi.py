@@ -46,7 +46,7 @@ class ReBatch(C.Structure):
                 ("ent_rowptr", C.c_void_p), ("rowptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p),
                 ("label", C.c_void_p), ("weight", C.c_void_p), ("offset", C.c_void_p), ("theta_ptr", C.c_void_p),
                 ("max_rows", C.c_int32), ("max_nnz", C.c_int32), ("max_coef", C.c_int32), ("reserved", C.c_int32),
-                ("col16", C.c_void_p)]
+                ("col16", C.c_void_p), ("col8", C.c_void_p)]
 
 
 class LrOpts(C.Structure):
@@ -169,12 +169,17 @@ class HostBatch:
         every entity has fewer than 65536 local features."""
         if narrow is None:
             narrow = self.max_coef < 65536 and self.nnz > 0
-        if narrow and getattr(self, "_col16", None) is None:
-            self._col16 = self.col.astype(np.uint16)
+        c16 = c8 = None
+        if narrow:
+            if getattr(self, "_col_narrow", None) is None:
+                # one byte per index when every entity has at most 256 local features, else two
+                self._col_narrow = self.col.astype(np.uint8 if int(self.col.max()) < 256 else np.uint16)
+            c8 = self._col_narrow if self._col_narrow.dtype == np.uint8 else None
+            c16 = self._col_narrow if c8 is None else None
         return ReBatch(self.n_entities, self.n_rows, self.nnz, _np_ptr(self.ent_rowptr), _np_ptr(self.rowptr),
                        _np_ptr(self.col), _np_ptr(self.val), _np_ptr(self.label), _np_ptr(self.weight),
                        _np_ptr(self.offset), _np_ptr(self.theta_ptr), self.max_rows, self.max_nnz, self.max_coef, 0,
-                       _np_ptr(self._col16) if narrow else None)
+                       _np_ptr(c16), _np_ptr(c8))
 
     def algorithmic_bytes(self, warm=False):
         """8 B/nnz + 16 B/sample + 8 B/coef out (+8 in when warm) + 4 B/feature index map."""

@@ -604,7 +604,7 @@ struct ChunkImage {
 };
 
 ChunkImage chunk_image(int64_t ne, int64_t nr, int64_t nz, int64_t nt, bool has_w, bool has_off, bool warm,
-                       bool want_var, bool narrow_col = false)
+                       bool want_var, int narrow_col = 0 /* bytes per index crossing PCIe: 0 (= 4), 2 or 1 */)
 {
     ChunkImage c;
     size_t o = 0;
@@ -612,7 +612,7 @@ ChunkImage chunk_image(int64_t ne, int64_t nr, int64_t nz, int64_t nt, bool has_
     c.rowptr = o; o += up256(8 * (nr + 1));
     c.theta_ptr = o; o += up256(8 * (ne + 1));
     c.col = o; o += up256(4 * nz);
-    c.col16 = o; o += narrow_col ? up256(2 * nz) : 0;
+    c.col16 = o; o += narrow_col ? up256(narrow_col * nz) : 0;
     c.val = o; o += up256(4 * nz);
     c.label = o; o += up256(4 * nr);
     c.weight = o; o += has_w ? up256(4 * nr) : 0;
@@ -844,8 +844,9 @@ int gdmix_re_fit_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const do
     if (E <= 0) return GDMIX_OK;
     if (!hb->ent_rowptr || !hb->rowptr || !hb->label || !hb->theta_ptr)
         return fail(GDMIX_ERR_INVALID, "null array in gdmix_re_batch");
-    if (hb->nnz > 0 && !hb->col && !hb->col16) return fail(GDMIX_ERR_INVALID, "gdmix_re_batch needs col or col16");
-    const bool narrow = hb->col16 != nullptr;
+    if (hb->nnz > 0 && !hb->col && !hb->col16 && !hb->col8)
+        return fail(GDMIX_ERR_INVALID, "gdmix_re_batch needs col, col16 or col8");
+    const int narrow = hb->col8 ? 1 : hb->col16 ? 2 : 0;
     const bool want_var = var_out != nullptr;
     if (want_var && o->variance_mode != GDMIX_VARIANCE_SIMPLE && o->variance_mode != GDMIX_VARIANCE_FULL)
         return fail(GDMIX_ERR_INVALID, "var_out needs variance_mode SIMPLE or FULL");
@@ -911,7 +912,12 @@ int gdmix_re_fit_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const do
         CUDA_TRY(cudaMemcpyAsync(dv + img.rowptr, hb->rowptr + r0, 8 * (nr + 1), H2D, s.st));
         CUDA_TRY(cudaMemcpyAsync(dv + img.theta_ptr, hb->theta_ptr + e0, 8 * (ne + 1), H2D, s.st));
         if (nz) {
-            if (narrow) {
+            if (narrow == 1) {
+                CUDA_TRY(cudaMemcpyAsync(dv + img.col16, hb->col8 + q0, nz, H2D, s.st));
+                gdmix::widen_u8_kernel<<<(int)std::min<int64_t>((nz / 16 + 255) / 256 + 1, 148 * 8), 256, 0, s.st>>>(
+                    (const uint8_t *)(dv + img.col16), (int32_t *)(dv + img.col), nz);
+                g_launches++;
+            } else if (narrow == 2) {
                 CUDA_TRY(cudaMemcpyAsync(dv + img.col16, hb->col16 + q0, 2 * nz, H2D, s.st));
                 gdmix::widen_u16_kernel<<<(int)std::min<int64_t>((nz + 255) / 256, 148 * 8), 256, 0, s.st>>>(
                     (const uint16_t *)(dv + img.col16), (int32_t *)(dv + img.col), nz);
@@ -975,6 +981,7 @@ int gdmix_re_score_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const 
     if (E <= 0) return GDMIX_OK;
     std::lock_guard<std::mutex> lk(g_host.mu);
     const int64_t nr = hb->ent_rowptr[E], nz = hb->rowptr[nr], nt = hb->theta_ptr[E];
+    if (nz > 0 && (!hb->col || !hb->val)) return fail(GDMIX_ERR_INVALID, "gdmix_re_score_host needs the int32 col and val");
     size_t o_ent = 0, o_row = up256(8 * (E + 1)), o_tp = o_row + up256(8 * (nr + 1));
     size_t o_col = o_tp + up256(8 * (E + 1)), o_val = o_col + up256(4 * nz), o_off = o_val + up256(4 * nz);
     size_t o_th = o_off + up256(4 * nr), o_hm = o_th + up256(8 * nt), o_in = o_hm + up256(E);

@@ -50,6 +50,22 @@ __global__ void __launch_bounds__(256) widen_u16_kernel(const uint16_t *in, int3
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth) out[i] = (int32_t)in[i];
 }
 
+// 8-bit local column indices (entities with at most 256 local features): 16 per thread and trip
+__global__ void __launch_bounds__(256) widen_u8_kernel(const uint8_t *in, int32_t *out, const int64_t n)
+{
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n16 = n >> 4;   // in / out are 256-byte aligned (chunk_image)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += nth) {
+        const uint4 v = ((const uint4 *)in)[i];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        int4 *o = (int4 *)out + 4 * i;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            o[q] = make_int4(w[q] & 0xffu, (w[q] >> 8) & 0xffu, (w[q] >> 16) & 0xffu, w[q] >> 24);
+    }
+    for (int64_t i = (n16 << 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth) out[i] = (int32_t)in[i];
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll

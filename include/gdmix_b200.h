@@ -105,6 +105,9 @@ typedef struct gdmix_re_batch {
      * entity has fewer than 65536 local features).  When set, `col` may be NULL: 2 instead of 4 bytes per
      * non-zero cross PCIe and are widened on the device. */
     const uint16_t *col16;
+    /* Likewise as 8-bit values (valid when every entity has at most 256 local features -- the C1 shape): one
+     * byte per non-zero crosses PCIe.  Takes precedence over col16. */
+    const uint8_t *col8;
 } gdmix_re_batch;
 
 /* LRParams / scipy knobs (base_lr_params.py:5-42; scipy defaults for the rest). */

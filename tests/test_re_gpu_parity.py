@@ -419,3 +419,27 @@ def test_ragged_batch_takes_two_fast_tiers(monkeypatch, re_path):
     rel = _rel_per_entity(two["theta"].cpu().numpy(), th_o, hb.theta_ptr)
     assert rel.max() <= REL_TOL, rel.max()
     assert (two["nit"].cpu().numpy() == nit_o).all()
+
+
+def test_narrow_column_transfers_are_equivalent():
+    """gdmix_re_batch.col8 / col16 (1 or 2 bytes per local column index across PCIe) give bit-identical fits to
+    the int32 columns; 1003 non-zeros per entity block exercises the 16-at-a-time widening kernel's tail."""
+    import ctypes as C
+    hb = make_batch(37, 17, 59, 3, seed=5)
+    opts = capi.make_opts()
+    outs = []
+    for mode in ("i32", "u16", "u8"):
+        cb = hb.c_struct(narrow=False)
+        keep = None
+        if mode == "u16":
+            keep = hb.col.astype(np.uint16); cb.col16 = keep.ctypes.data; cb.col = None
+        elif mode == "u8":
+            keep = hb.col.astype(np.uint8); cb.col8 = keep.ctypes.data; cb.col = None
+        theta = np.zeros(hb.n_coef); nit = np.zeros(hb.n_entities, np.int32)
+        capi.check(capi.lib.gdmix_re_fit_host(C.byref(cb), C.byref(opts), None, theta.ctypes.data_as(C.c_void_p), None,
+                                              nit.ctypes.data_as(C.c_void_p), None, None, None, C.c_int64(0)))
+        outs.append((theta, nit))
+    for t, n in outs[1:]:
+        np.testing.assert_array_equal(t, outs[0][0])
+        np.testing.assert_array_equal(n, outs[0][1])
+    assert hb.c_struct().col8 is not None and hb.c_struct().col16 is None
