@@ -67,7 +67,7 @@ class FePlanStruct(C.Structure):
                 ("item_col", C.c_void_p), ("item_begin", C.c_void_p), ("item_end", C.c_void_p),
                 ("item_slot", C.c_void_p), ("n_split", C.c_int64), ("split_col", C.c_void_p),
                 ("split_slot_ptr", C.c_void_p), ("n_slots", C.c_int64), ("scratch", C.c_void_p),
-                ("scratch_doubles", C.c_int64)]
+                ("scratch_doubles", C.c_int64), ("n_tiles", C.c_int64), ("tile_item_ptr", C.c_void_p)]
 
 
 def _load():
@@ -363,43 +363,74 @@ class DeviceFeRows:
 
 
 FE_SLICE = 4096  # non-zeros of a column one warp sums; longer columns are sliced
+FE_TILE_ROWS = 4 << 20  # rows per tile of the column-major copy: a tile's dz (32 MB) stays in L2 while it is gathered
 
 
 class DeviceFePlan:
     """Column-major copy of a shard + work items + scratch for gdmix_fe_loss_grad_planned.  Built once per
     training run (the shard does not change between the ~100 evaluations of an L-BFGS run).  The transpose is a
-    stable sort by column done with torch (device memory plumbing, outside any timed region)."""
+    stable sort done with torch (device memory plumbing, outside any timed region).
 
-    def __init__(self, rows, slice_nnz=FE_SLICE):
+    The copy is TILED by rows: non-zeros are ordered by (row tile, column, row) and a work item is a column's
+    run inside one tile (or a slice of at most `slice_nnz` of it).  Items are walked tile after tile, so the dz
+    entries a tile's items gather -- `tile_rows` x 8 bytes -- are L2 hits instead of one 32-byte DRAM sector per
+    non-zero, which is what the gather costs once dz outgrows L2 (a 62 M-row shard has 500 MB of dz).  A column
+    that owns more than one item has its partial sums added in item order by fe_finish_kernel (fixed order)."""
+
+    def __init__(self, rows, slice_nnz=FE_SLICE, tile_rows=FE_TILE_ROWS):
         import torch
         dev = rows.val.device
         D, n = rows.n_features, rows.n_rows
-        col64 = rows.col.to(torch.int64)
-        order = torch.sort(col64, stable=True).indices            # rows ascending inside a column
         row_of_nnz = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int32),
                                              (rows.rowptr[1:] - rows.rowptr[:-1]))
-        self.row = row_of_nnz[order].contiguous()
-        self.val = rows.val[order].contiguous()
-        counts = torch.bincount(col64, minlength=D)
+        key = rows.col.to(torch.int64)
+        counts_col = torch.bincount(key, minlength=D)
+        if n > tile_rows:
+            key += (row_of_nnz // int(tile_rows)).to(torch.int64) * D
+        srt = torch.sort(key, stable=True)                         # rows ascending inside a (tile, column) run
+        del key
+        self.row = row_of_nnz[srt.indices].contiguous()
+        self.val = rows.val[srt.indices].contiguous()
+        del row_of_nnz
+        seg_key, seg_cnt = torch.unique_consecutive(srt.values, return_counts=True)
+        del srt
         self.colptr = torch.zeros(D + 1, dtype=torch.int64, device=dev)
-        self.colptr[1:] = torch.cumsum(counts, 0)
-        del order, row_of_nnz, col64
-        # work items (host side: D is small next to nnz)
-        cp = self.colptr.cpu().numpy()
-        ln = np.diff(cp)
-        pieces = np.maximum(1, -(-ln // slice_nnz)).astype(np.int64)
-        item_col = np.repeat(np.arange(D, dtype=np.int32), pieces)
-        first = np.concatenate([[0], np.cumsum(pieces)[:-1]])
+        self.colptr[1:] = torch.cumsum(counts_col, 0)
+        # work items (host side: segments are few next to nnz)
+        seg_key, seg_cnt = seg_key.cpu().numpy(), seg_cnt.cpu().numpy().astype(np.int64)
+        seg_col = (seg_key % D).astype(np.int32)
+        seg_tile = seg_key // D
+        seg_begin = np.cumsum(seg_cnt) - seg_cnt
+        # inside a tile the long runs go first (they are whole 4096-slices; the short tail fills the launch's end)
+        by_len = np.lexsort((-seg_cnt, seg_tile))
+        seg_col, seg_tile, seg_begin, seg_cnt = seg_col[by_len], seg_tile[by_len], seg_begin[by_len], seg_cnt[by_len]
+        pieces = np.maximum(1, -(-seg_cnt // slice_nnz)).astype(np.int64)
+        item_col = np.repeat(seg_col, pieces)
+        first = np.cumsum(pieces) - pieces
         k = np.arange(item_col.shape[0], dtype=np.int64) - np.repeat(first, pieces)
-        begin = cp[item_col] + k * slice_nnz
-        end = np.minimum(begin + slice_nnz, cp[item_col.astype(np.int64) + 1])
-        split = pieces > 1
-        item_split = np.repeat(split, pieces)
-        slot = np.full(item_col.shape[0], -1, np.int32)
-        slot[item_split] = np.arange(int(item_split.sum()), dtype=np.int32)
-        self.n_items, self.n_slots = int(item_col.shape[0]), int(item_split.sum())
-        split_col = np.flatnonzero(split).astype(np.int32)
-        ssp = np.concatenate([[0], np.cumsum(pieces[split])]).astype(np.int64)
+        begin = np.repeat(seg_begin, pieces) + k * slice_nnz
+        end = np.minimum(begin + slice_nnz, np.repeat(seg_begin + seg_cnt, pieces))
+        self.n_tiles = int(seg_tile.max()) + 1 if seg_tile.shape[0] else 1
+        items_per_tile = np.bincount(np.repeat(seg_tile, pieces), minlength=self.n_tiles).astype(np.int64)
+        # columns without any non-zero still get their L2 term: one empty item each (they ride in the last tile)
+        empty = np.flatnonzero(counts_col.cpu().numpy() == 0).astype(np.int32)
+        items_per_tile[-1] += empty.shape[0]
+        self.tile_item_ptr = np.concatenate([[0], np.cumsum(items_per_tile)]).astype(np.int64)   # host array
+        item_col = np.concatenate([item_col, empty])
+        begin = np.concatenate([begin, np.zeros(empty.shape[0], np.int64)])
+        end = np.concatenate([end, np.zeros(empty.shape[0], np.int64)])
+        # slots: the items of a column that has several, numbered column by column in item order
+        per_col = np.bincount(item_col, minlength=D).astype(np.int64)
+        split_col = np.flatnonzero(per_col > 1).astype(np.int32)
+        ssp = np.concatenate([[0], np.cumsum(per_col[split_col])]).astype(np.int64)
+        slot_base = np.full(D, -1, np.int64)
+        slot_base[split_col] = ssp[:-1]
+        by_col = np.argsort(item_col, kind="stable")
+        first_of_col = np.cumsum(per_col) - per_col
+        rank = np.empty(item_col.shape[0], np.int64)
+        rank[by_col] = np.arange(item_col.shape[0], dtype=np.int64) - first_of_col[item_col[by_col]]
+        slot = np.where(slot_base[item_col] >= 0, slot_base[item_col] + rank, -1).astype(np.int32)
+        self.n_items, self.n_slots = int(item_col.shape[0]), int(ssp[-1])
         to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
         self.item_col, self.item_begin, self.item_end, self.item_slot = to(item_col), to(begin), to(end), to(slot)
         self.n_split = int(split_col.shape[0])
@@ -413,7 +444,7 @@ class DeviceFePlan:
         return FePlanStruct(_tptr(self.colptr), _tptr(self.row), _tptr(self.val), self.n_items, _tptr(self.item_col),
                             _tptr(self.item_begin), _tptr(self.item_end), _tptr(self.item_slot), self.n_split,
                             _tptr(self.split_col), _tptr(self.split_slot_ptr), self.n_slots, _tptr(self.scratch),
-                            self.scratch.numel())
+                            self.scratch.numel(), self.n_tiles, _np_ptr(self.tile_item_ptr))
 
 
 def fe_loss_grad_device(rows, opts, x, fg=None, stream=None, plan=None):

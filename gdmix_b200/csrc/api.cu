@@ -740,11 +740,10 @@ int gdmix_fe_loss_grad(const gdmix_fe_rows *rows, const gdmix_lr_opts *o, const 
 namespace {
 void fe_rows_geometry(const gdmix_fe_rows *rows, const DeviceInfo &dev, int &grid, int &team_shift)
 {
-    const int64_t avg = rows->n_rows > 0 ? (rows->nnz + rows->n_rows - 1) / rows->n_rows : 1;
-    team_shift = 0;
-    while (team_shift < 5 && (1 << team_shift) < avg) team_shift++;
-    // a warp owns 32 rows at a time, 8 warps per CTA
-    grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows->n_rows + 255) / 256, (int64_t)dev.sm_count * 8));
+    team_shift = 0;   // (unused since the rows kernel stages 32 rows per warp in shared memory)
+    // a warp owns 32 rows at a time, 8 warps per CTA, one CTA per SM (x head + stages fill its shared memory)
+    constexpr int T = gdmix::kFeRowsThreads;
+    grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows->n_rows + T - 1) / T, (int64_t)dev.sm_count));
 }
 }  // namespace
 
@@ -784,12 +783,32 @@ int gdmix_fe_loss_grad_planned(const gdmix_fe_rows *rows, const gdmix_fe_plan *p
     P.dz = pl->scratch; P.slots = pl->scratch + rows->n_rows; P.block_part = P.slots + pl->n_slots;
     P.rows_grid = grid; P.team_shift = team_shift;
     cudaStream_t st = (cudaStream_t)stream;
-    gdmix::fe_rows_kernel<<<grid, 256, 0, st>>>(*rows, *o, P, x);
-    const int cgrid = (int)std::max<int64_t>(1, std::min<int64_t>((pl->n_items + 7) / 8, (int64_t)dev.sm_count * 16));
-    gdmix::fe_cols_kernel<<<cgrid, 256, 0, st>>>(*rows, *o, P, x, fg);
+    {
+        // the leading coefficients of x ride in shared memory (aux_kernels.cuh)
+        const uint32_t head = (uint32_t)std::min<int64_t>(rows->n_features, gdmix::kFeHeadMax);
+        const uint32_t smem = gdmix::fe_rows_smem_bytes(head);
+        static std::atomic<int> configured{0};
+        if (!configured.load()) {
+            CUDA_TRY(cudaFuncSetAttribute(gdmix::fe_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)gdmix::fe_rows_smem_bytes(gdmix::kFeHeadMax)));
+            configured.store(1);
+        }
+        gdmix::fe_rows_kernel<<<grid, gdmix::kFeRowsThreads, smem, st>>>(*rows, *o, P, x, head);
+    }
+    // column pass: one launch per row tile (stream order keeps every warp inside the tile whose dz is in L2)
+    const int64_t n_launch = (pl->n_tiles > 1 && pl->tile_item_ptr) ? pl->n_tiles : 1;
+    for (int64_t t = 0; t < n_launch; t++) {
+        const int64_t i0 = n_launch > 1 ? pl->tile_item_ptr[t] : 0;
+        const int64_t i1 = n_launch > 1 ? pl->tile_item_ptr[t + 1] : pl->n_items;
+        if (i1 <= i0) continue;
+        if (i0 < 0 || i1 > pl->n_items) return fail(GDMIX_ERR_INVALID, "tile_item_ptr outside [0, n_items]");
+        const int cgrid = (int)std::max<int64_t>(1, std::min<int64_t>((i1 - i0 + 7) / 8, (int64_t)dev.sm_count * 8));
+        gdmix::fe_cols_kernel<<<cgrid, 256, 0, st>>>(*rows, *o, P, x, fg, i0, i1);
+        g_launches++;
+    }
     const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((pl->n_split + 7) / 8, (int64_t)dev.sm_count * 4));
     gdmix::fe_finish_kernel<<<fgrid, 256, 0, st>>>(*rows, *o, P, x, fg);
-    g_launches += 3;
+    g_launches += 2;
     CUDA_TRY(cudaGetLastError());
     return GDMIX_OK;
 }

@@ -200,35 +200,116 @@ struct FePlan {
     int32_t team_shift;       // log2 lanes per row
 };
 
-__global__ void __launch_bounds__(256) fe_rows_kernel(const gdmix_fe_rows R, const gdmix_lr_opts o, const FePlan P,
-                                                      const double *x)
+constexpr int kFeRowsThreads = 512;         // fe_rows_kernel CTA: sixteen warps, one CTA per SM
+constexpr uint32_t kFeStageCap = 1024;      // non-zeros one warp stages at a time (4 KB values + 4 KB columns)
+constexpr uint32_t kFeHeadMax = 8192;       // leading coefficients of x kept in shared memory (64 KB)
+
+__host__ __device__ inline uint32_t fe_rows_smem_bytes(const uint32_t head)
 {
-    // A warp owns 32 consecutive rows at a time.  Step s: each team of T lanes walks one row (coalesced loads,
-    // x gathered through L2), team sums by butterfly, and the row's z is handed to the lane whose index equals
-    // the row's position in the block -- so the loss / dz arithmetic (one exp, one log1p, one division per row)
-    // then runs on 32 rows in 32 lanes instead of on one lane per team.
+    return 8u * head + (kFeRowsThreads / 32) * kFeStageCap * 8u;
+}
+
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kFeRowsThreads, 1) fe_rows_kernel(const gdmix_fe_rows R, const gdmix_lr_opts o,
+                                                                    const FePlan P, const double *x, const uint32_t head)
+{
+    // A warp owns 32 consecutive rows at a time.  Their non-zeros are one contiguous range of the CSR arrays:
+    // the warp copies it into shared memory asynchronously (cp.async, 16 bytes per lane and instruction when
+    // the range is aligned: the whole 8 KB is in flight at once and no register waits for it), then every LANE
+    // walks its own row out of shared memory -- one FMA per lane and instruction, no cross-lane reduction (a
+    // warp-per-row walk spends ~40 instructions per FMA on butterflies for 32-wide rows).  Each lane starts its
+    // walk `lane` elements into its row and wraps around, which spreads equal-length rows over all banks.
+    // The x gather is what bounds this kernel: 32 lanes x 32 different 128-byte lines cost the L1 one cycle or
+    // two per line.  So the first `head` coefficients of x live in shared memory (the host side numbers features
+    // by falling frequency, so these are the hot ones) and only the tail is gathered through L1 / L2.
+    // The loss / dz arithmetic (one exp, one log1p, one division per row) runs on 32 rows in 32 lanes.  Blocks
+    // with more non-zeros than the stage holds are taken in runs of as many rows as fit; a single row longer
+    // than the stage is summed by the whole warp straight from global memory.  Every sum has a fixed order.
+    extern __shared__ __align__(16) unsigned char fe_smem[];
+    __shared__ double sv[kFeRowsThreads / 32], sd[kFeRowsThreads / 32];
     const int hi = o.has_intercept ? 1 : 0;
     const int64_t D = R.n_features;
-    const uint32_t ts = (uint32_t)P.team_shift, T = 1u << ts, RS = 32u >> ts;   // lanes per row, rows per step
-    const uint32_t lane = threadIdx.x & 31, t = lane & (T - 1), q = lane >> ts;
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *xs = (double *)fe_smem;
+    float *sval = (float *)(fe_smem + 8u * head) + wib * (2u * kFeStageCap);
+    int32_t *scol = (int32_t *)(sval + kFeStageCap);
+    for (uint32_t j = threadIdx.x; j < head; j += kFeRowsThreads) xs[j] = x[j];
+    __syncthreads();
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const double b0 = hi ? x[D] : 0.0;
     double value = 0.0, dz_sum = 0.0;
     const int64_t nblocks = (R.n_rows + 31) >> 5;
+    // row pointers of the warp's NEXT block are fetched while the current one is summed
+    int64_t nqs = 0, nqe = 0;
+    if (warp < nblocks && (warp << 5) + lane < R.n_rows) { nqs = R.rowptr[(warp << 5) + lane]; nqe = R.rowptr[(warp << 5) + lane + 1]; }
     for (int64_t blk = warp; blk < nblocks; blk += nwarps) {
         const int64_t base = blk << 5;
+        const uint32_t nrows = (uint32_t)min((int64_t)32, R.n_rows - base);
+        const int64_t qs = nqs, qe = nqe;
+        {
+            const int64_t nb = (blk + nwarps) << 5;
+            nqs = 0; nqe = 0;
+            if (blk + nwarps < nblocks && nb + lane < R.n_rows) { nqs = R.rowptr[nb + lane]; nqe = R.rowptr[nb + lane + 1]; }
+        }
         double myz = 0.0;
-        for (uint32_t s = 0; s < T; s++) {
-            const int64_t i = base + s * RS + q;
-            double z = 0.0;
-            if (i < R.n_rows) {
-                const int64_t qs = R.rowptr[i], qe = R.rowptr[i + 1];
-                for (int64_t k = qs + t; k < qe; k += T) z = fma((double)R.val[k], x[R.col[k]], z);
+        uint32_t done = 0;
+        while (done < nrows) {
+            const int64_t q0 = __shfl_sync(0xffffffffu, qs, done);
+            const unsigned fit = __ballot_sync(0xffffffffu, lane >= done && lane < nrows && (qe - q0) <= (int64_t)kFeStageCap);
+            const uint32_t nfit = __popc(fit);   // row ends ascend: the rows that fit are done .. done + nfit - 1
+            if (nfit == 0) {
+                const int64_t e0 = __shfl_sync(0xffffffffu, qe, done);
+                double z = 0.0;
+                for (int64_t k = q0 + lane; k < e0; k += 32) z = fma((double)R.val[k], __ldg(x + R.col[k]), z);
+                z = warp_sum(z);
+                if (lane == done) myz = z;
+                done += 1;
+                continue;
             }
-            for (uint32_t m = T >> 1; m > 0; m >>= 1) z += __shfl_xor_sync(0xffffffffu, z, m);
-            const double v = __shfl_sync(0xffffffffu, z, (lane & (RS - 1)) << ts);
-            if ((lane >> (5 - ts)) == s) myz = v;   // lane j takes row j = s * RS + (j mod RS)
+            const uint32_t cnt = (uint32_t)(__shfl_sync(0xffffffffu, qe, done + nfit - 1) - q0);
+            {
+                const float *gv = R.val + q0;
+                const int32_t *gc = R.col + q0;
+                if ((((uintptr_t)gv | (uintptr_t)gc) & 15u) == 0) {   // both ranges start 16-byte aligned
+                    const uint32_t n4 = cnt >> 2;
+                    for (uint32_t f = lane; f < n4; f += 32) {
+                        cp_async16(sval + 4 * f, gv + 4 * f);
+                        cp_async16(scol + 4 * f, gc + 4 * f);
+                    }
+                    for (uint32_t f = (n4 << 2) + lane; f < cnt; f += 32) { cp_async4(sval + f, gv + f); cp_async4(scol + f, gc + f); }
+                } else {
+                    for (uint32_t f = lane; f < cnt; f += 32) { cp_async4(sval + f, gv + f); cp_async4(scol + f, gc + f); }
+                }
+                cp_async_wait_all();
+            }
+            __syncwarp();
+            if (lane >= done && lane < done + nfit) {
+                const uint32_t s0 = (uint32_t)(qs - q0), len = (uint32_t)(qe - qs);
+                uint32_t pos = len ? lane % len : 0u;
+                double z = 0.0;
+#pragma unroll 4
+                for (uint32_t s = 0; s < len; s++) {
+                    const uint32_t c = (uint32_t)scol[s0 + pos];
+                    const double xv = (c < head) ? xs[c] : __ldg(x + c);
+                    z = fma((double)sval[s0 + pos], xv, z);
+                    pos = (pos + 1u == len) ? 0u : pos + 1u;
+                }
+                myz = z;
+            }
+            __syncwarp();
+            done += nfit;
         }
         const int64_t i = base + lane;
         if (i < R.n_rows) {
@@ -252,9 +333,7 @@ __global__ void __launch_bounds__(256) fe_rows_kernel(const gdmix_fe_rows R, con
     }
     value = warp_sum(value);
     dz_sum = warp_sum(dz_sum);
-    __shared__ double sv[8], sd[8];
-    const int wi_ = threadIdx.x >> 5;
-    if (lane == 0) { sv[wi_] = value; sd[wi_] = dz_sum; }
+    if (lane == 0) { sv[wib] = value; sd[wib] = dz_sum; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double v = 0.0, dsum = 0.0;
@@ -265,13 +344,14 @@ __global__ void __launch_bounds__(256) fe_rows_kernel(const gdmix_fe_rows R, con
 }
 
 __global__ void __launch_bounds__(256) fe_cols_kernel(const gdmix_fe_rows R, const gdmix_lr_opts o, const FePlan P,
-                                                      const double *x, double *fg)
+                                                      const double *x, double *fg, const int64_t item0,
+                                                      const int64_t item1)
 {
     const uint32_t lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const double l2w = o.l2 / (double)(R.num_workers > 0 ? R.num_workers : 1);
-    for (int64_t it = warp; it < P.n_items; it += nwarps) {
+    for (int64_t it = item0 + warp; it < item1; it += nwarps) {
         const int64_t b = P.item_begin[it], e = P.item_end[it];
         double s0 = 0.0, s1 = 0.0;
         int64_t q = b + lane;

@@ -216,6 +216,14 @@ typedef struct gdmix_fe_plan {
     int64_t n_slots;
     double *scratch;
     int64_t scratch_doubles;
+    /* Row tiling of the column-major copy (optional; n_tiles <= 1 or tile_item_ptr == NULL: one launch over all
+     * items).  When the copy is ordered by (row tile, column, row), tile t's items are
+     * [tile_item_ptr[t], tile_item_ptr[t+1]) -- a HOST array of n_tiles + 1 entries -- and the column pass runs
+     * tile after tile, so that the dz entries it gathers (tile rows x 8 bytes) stay in L2: on a shard whose dz
+     * outgrows L2 every gathered entry otherwise costs a 32-byte DRAM sector.  A column with items in several
+     * tiles is a split column (its items own slots). */
+    int64_t n_tiles;
+    const int64_t *tile_item_ptr;
 } gdmix_fe_plan;
 GDMIX_API int gdmix_fe_rows_grid(const gdmix_fe_rows *rows, int32_t *grid);
 GDMIX_API int gdmix_fe_loss_grad_planned(const gdmix_fe_rows *rows, const gdmix_fe_plan *plan,

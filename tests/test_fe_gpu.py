@@ -103,8 +103,45 @@ def test_planned_path_matches_atomic_path_and_is_reproducible():
         c = capi.fe_loss_grad_device(rows, opts, x, plan=plan).cpu().numpy()
         np.testing.assert_allclose(b, a, rtol=1e-11, atol=1e-9)
         np.testing.assert_array_equal(b, c)
+        # the same shard with its column-major copy tiled by rows (what a shard larger than L2's worth of dz gets)
+        tiled = capi.DeviceFePlan(rows, slice_nnz=256, tile_rows=7000)
+        assert tiled.n_tiles == 5 and tiled.n_split > plan.n_split
+        t1 = capi.fe_loss_grad_device(rows, opts, x, plan=tiled).cpu().numpy()
+        t2 = capi.fe_loss_grad_device(rows, opts, x, plan=tiled).cpu().numpy()
+        np.testing.assert_array_equal(t1, t2)
+        np.testing.assert_allclose(t1, b, rtol=1e-12, atol=1e-11)
         blk = O.FeBlock(n, D, rowptr, col, val, y, w, off, linear_regression=lin, num_workers=2)
         oo = O.make_opts(l2=0.7, regularize_bias=rb, has_intercept=hi)
         f_o, g_o = O.fe_loss_grad(blk, oo, x.cpu().numpy())
         np.testing.assert_allclose(b[0], f_o, rtol=1e-12)
         np.testing.assert_allclose(b[1:], g_o, rtol=1e-10, atol=1e-10)
+
+
+def test_planned_path_rows_of_every_size():
+    """fe_rows_kernel stages 32 rows per warp in shared memory (1024 non-zeros at a time): blocks that fit, blocks
+    taken in several runs, single rows longer than the stage (summed by the whole warp from global memory), empty
+    rows, a ragged last block -- against the oracle."""
+    rng = np.random.default_rng(17)
+    D = 5000
+    lens = np.concatenate([np.full(64, 32), rng.integers(0, 90, 200), [3000, 0, 1024, 1025, 1, 0, 2047],
+                           rng.integers(20, 60, 37), [1500, 1500], np.zeros(33, np.int64), rng.integers(0, 5, 11)])
+    n = len(lens)
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    nnz = int(rowptr[-1])
+    col = rng.integers(0, D, nnz).astype(np.int32)
+    val = rng.standard_normal(nnz).astype(np.float32)
+    y = (rng.random(n) < 0.5).astype(np.float32)
+    w = rng.uniform(0.5, 2.0, n).astype(np.float32)
+    off = (0.1 * rng.standard_normal(n)).astype(np.float32)
+    x = rng.standard_normal(D + 1) * 0.02
+    rows = capi.DeviceFeRows(rowptr, col, val, y, w, off, D)
+    opts = capi.make_opts(l2=0.3, regularize_bias=False, has_intercept=True)
+    plan = capi.DeviceFePlan(rows)
+    xd = torch.from_numpy(x).cuda()
+    b = capi.fe_loss_grad_device(rows, opts, xd, plan=plan).cpu().numpy()
+    c = capi.fe_loss_grad_device(rows, opts, xd, plan=plan).cpu().numpy()
+    np.testing.assert_array_equal(b, c)
+    blk = O.FeBlock(n, D, rowptr, col, val, y, w, off)
+    f_o, g_o = O.fe_loss_grad(blk, O.make_opts(l2=0.3, regularize_bias=False, has_intercept=True), x)
+    np.testing.assert_allclose(b[0], f_o, rtol=1e-12)
+    np.testing.assert_allclose(b[1:], g_o, rtol=1e-10, atol=1e-10)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Fixed-effect objective/gradient pass (gdmix_fe_loss_grad) on synthetic rows of the C2 shape: rows x 32 nnz over
 D = 100 000 features (Zipf-ish popularity), GB/s against the 8k+16 B/row algorithmic traffic.
-Usage: python tools/fe_bench.py [rows] [D] [k] [iters]"""
+Usage: python tools/fe_bench.py [rows] [D] [k] [iters] [tile_rows]"""
 import json
 import os
 import sys
@@ -49,7 +49,8 @@ ms = ev0.elapsed_time(ev1) / iters
 alg = rows * (8 * k + 16)
 print(json.dumps({"kernel": "fe_loss_grad_kernel", "rows": rows, "D": D, "k": k, "ms": ms,
                   "rows_per_s": rows / ms * 1e3, "algorithmic_GBps": alg / ms / 1e6, "fg0": float(fg[0].item())}))
-plan = capi.DeviceFePlan(r)
+tile_rows = int(sys.argv[5]) if len(sys.argv) > 5 else capi.FE_TILE_ROWS
+plan = capi.DeviceFePlan(r, tile_rows=tile_rows)
 fg2 = torch.empty_like(fg)
 for _ in range(3):
     capi.fe_loss_grad_device(r, opts, x, fg=fg2, plan=plan)
@@ -61,7 +62,7 @@ ev1.record(); torch.cuda.synchronize()
 ms = ev0.elapsed_time(ev1) / iters
 rel = float(((fg2 - fg).abs().max() / fg.abs().max()).item())
 print(json.dumps({"kernel": "fe planned (rows+cols+finish)", "ms": ms, "rows_per_s": rows / ms * 1e3,
-                  "algorithmic_GBps": alg / ms / 1e6, "max_rel_diff_vs_atomic": rel, "items": plan.n_items,
+                  "algorithmic_GBps": alg / ms / 1e6, "max_rel_diff_vs_atomic": rel, "tile_rows": tile_rows, "tiles": plan.n_tiles, "items": plan.n_items,
                   "split_columns": plan.n_split}))
 lg = capi.fe_score_device(r, opts, x)
 torch.cuda.synchronize()
