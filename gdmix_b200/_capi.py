@@ -363,6 +363,7 @@ class DeviceFeRows:
 
 
 FE_SLICE = 4096  # non-zeros of a column one warp sums; longer columns are sliced
+FE_HEAD = 8192   # leading coefficients of x that fe_rows_kernel keeps in shared memory (kFeHeadMax)
 FE_TILE_ROWS = 4 << 20  # rows per tile of the column-major copy: a tile's dz (32 MB) stays in L2 while it is gathered
 
 

@@ -1216,8 +1216,18 @@ int gdmix_auc(const float *score, const float *label, int64_t n, double *out3, v
     int64_t ng_host = 0;
     CUDA_TRY(cudaMemcpyAsync(&ng_host, ngroups, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    gdmix::auc_groups_kernel<<<(int)std::min<int64_t>((ng_host + 7) / 8, 148 * 16), 256, 0, st>>>(lab_s, seg_ptr, ng_host, gpos, gneg);
-    gdmix::auc_finish_kernel<<<1, 256, 0, st>>>(gpos, gneg, ng_host, out3);
+    // negx = exclusive scan of the sorted negative flags (n + 1 entries; spans the two per-group arrays of the
+    // workspace layout, which are contiguous), with the tile arrays reused now that the heads are written
+    int64_t *negx = (int64_t *)gpos;
+    (void)gneg;
+    gdmix::tile_sum_kernel<<<(int)nt, gdmix::kSortThreads, 0, st>>>(lab_s, n, tile_count);
+    gdmix::tiles_exclusive_scan_kernel<<<1, 256, 0, st>>>(tile_count, nt, tile_off, ngroups + 1);
+    gdmix::rowptr_from_len_kernel<<<(int)nt, gdmix::kSortThreads, 0, st>>>(lab_s, n, tile_off, negx);
+    const int n_cta = (int)std::max<int64_t>(1, std::min<int64_t>((ng_host + 255) / 256, 148 * 8));
+    double *cta_u2 = (double *)keys;   // the unsorted keys are dead after the sort
+    gdmix::auc_groups_kernel<<<n_cta, 256, 0, st>>>(seg_ptr, ng_host, negx, cta_u2);
+    gdmix::auc_finish_kernel<<<1, 256, 0, st>>>(cta_u2, n_cta, negx, n, out3);
+    g_launches += 3;
     g_launches += 6;
     CUDA_TRY(cudaGetLastError());
     return GDMIX_OK;

@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(256) partition_i64_kernel(const int64_t *ids, 
 }
 
 // ---- AUC ------------------------------------------------------------------------------------------------
-// scores -> sortable keys (ascending), payload = label bit
+// scores -> sortable keys (ascending), payload = 1 for a NEGATIVE (label <= 0), 0 for a positive
 __global__ void __launch_bounds__(256) auc_keys_kernel(const float *score, const float *label, const int64_t n, uint64_t *keys,
                                                        uint32_t *payload)
 {
@@ -338,77 +338,54 @@ __global__ void __launch_bounds__(256) auc_keys_kernel(const float *score, const
         uint32_t b = __float_as_uint(s);
         b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
         keys[i] = b;
-        payload[i] = label[i] > 0.0f ? 1u : 0u;
+        payload[i] = label[i] > 0.0f ? 0u : 1u;
     }
 }
 
-// Over the tie groups of the sorted scores: U += pos_g * (neg_below_g + neg_g / 2).  acc[0] = 2U (integer),
-// acc[1] = positives, acc[2] = negatives.  One warp per group run of at most 2^31 elements; groups are found from
-// seg_ptr (heads of equal keys).  neg_below comes from an exclusive scan of per-group negatives done by the caller's
-// second launch: to stay single-pass this kernel does the serial part per CTA-chunk of groups and uses atomics
-// on integers (exact, order-free).
-__global__ void __launch_bounds__(256) auc_groups_kernel(const uint32_t *label_sorted, const int64_t *seg_ptr, const int64_t ngroups,
-                                                         unsigned long long *group_pos, unsigned long long *group_neg)
+// Over the tie groups of the sorted scores: 2U = sum_g pos_g * (2 neg_below_g + neg_g) (Evaluator.scala:29-45 counts
+// a tie as half a concordant pair).  With negx[i] = negatives among the first i sorted elements (exclusive scan,
+// negx[n] = all negatives) a group [b, e) has neg_below = negx[b], neg_g = negx[e] - negx[b], so its term is
+// pos_g * (negx[b] + negx[e]) -- one thread per group, no serial walk.  Per-thread sums in double (integers up to
+// 2^53 are exact), CTA partials in a fixed order.
+__global__ void __launch_bounds__(256) auc_groups_kernel(const int64_t *seg_ptr, const int64_t ngroups, const int64_t *negx,
+                                                         double *cta_u2)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t g = warp; g < ngroups; g += nwarps) {
-        const int64_t b = seg_ptr[g], e = seg_ptr[g + 1];
-        unsigned long long pos = 0;
-        for (int64_t k = b + lane; k < e; k += 32) pos += label_sorted[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) pos += __shfl_xor_sync(0xffffffffu, pos, o);
-        if (lane == 0) { group_pos[g] = pos; group_neg[g] = (unsigned long long)(e - b) - pos; }
-    }
-}
-
-// single CTA: walks the groups in order (chunks of 256 with a block scan of negatives); exact integer arithmetic
-__global__ void __launch_bounds__(256) auc_finish_kernel(const unsigned long long *group_pos, const unsigned long long *group_neg,
-                                                         const int64_t ngroups, double *out /* auc, positives, negatives */)
-{
-    __shared__ unsigned long long wsum[8], carry_s, u2_s[8], pos_s[8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
-    // 2U can exceed 64 bits only beyond ~3e9 x 3e9 pairs; accumulate in double pairs per thread to be safe
+    __shared__ double sh[256];
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
     double u2 = 0.0;
-    unsigned long long pos_total = 0;
-    for (int64_t g0 = 0; g0 < ngroups; g0 += 256) {
-        const int64_t g = g0 + tid;
-        const unsigned long long neg = (g < ngroups) ? group_neg[g] : 0ull, pos = (g < ngroups) ? group_pos[g] : 0ull;
-        unsigned long long incl = neg;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += u;
-        }
-        if (lane == 31) wsum[warp] = incl;
-        __syncthreads();
-        unsigned long long below = carry_s + incl - neg;
-        for (int w = 0; w < warp; w++) below += wsum[w];
-        u2 += (double)pos * (2.0 * (double)below + (double)neg);
-        pos_total += pos;
-        __syncthreads();
-        if (tid == 255) carry_s = below + neg;
-        __syncthreads();
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += nth) {
+        const int64_t b = seg_ptr[g], e = seg_ptr[g + 1];
+        const int64_t nb = negx[b], ne = negx[e];
+        const int64_t pos = (e - b) - (ne - nb);
+        u2 += (double)pos * (double)(nb + ne);
     }
-    // fixed-order reduction of the per-thread sums
-    __shared__ double ud[256];
-    __shared__ unsigned long long pd[256];
-    ud[tid] = u2; pd[tid] = pos_total;
+    sh[threadIdx.x] = u2;
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (tid < s) { ud[tid] += ud[tid + s]; pd[tid] += pd[tid + s]; }
+    for (int s2 = 128; s2 > 0; s2 >>= 1) {
+        if ((int)threadIdx.x < s2) sh[threadIdx.x] += sh[threadIdx.x + s2];
         __syncthreads();
     }
-    if (tid == 0) {
-        const double P = (double)pd[0], N = (double)carry_s;
-        out[0] = (P > 0 && N > 0) ? 0.5 * ud[0] / (P * N) : 0.0;
+    if (threadIdx.x == 0) cta_u2[blockIdx.x] = sh[0];
+}
+
+__global__ void __launch_bounds__(256) auc_finish_kernel(const double *cta_u2, const int n_cta, const int64_t *negx,
+                                                         const int64_t n, double *out /* auc, positives, negatives */)
+{
+    __shared__ double sh[256];
+    double u2 = 0.0;
+    for (int i = threadIdx.x; i < n_cta; i += 256) u2 += cta_u2[i];
+    sh[threadIdx.x] = u2;
+    __syncthreads();
+    for (int s2 = 128; s2 > 0; s2 >>= 1) {
+        if ((int)threadIdx.x < s2) sh[threadIdx.x] += sh[threadIdx.x + s2];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double N = (double)negx[n], P = (double)(n - negx[n]);
+        out[0] = (P > 0 && N > 0) ? 0.5 * sh[0] / (P * N) : 0.0;
         out[1] = P;
         out[2] = N;
     }
-    (void)u2_s; (void)pos_s;
 }
 
 }  // namespace gdmix

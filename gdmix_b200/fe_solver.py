@@ -61,6 +61,7 @@ class FixedEffectSolver:
             self._fg_dev = torch.empty(1 + self.n_coef, dtype=torch.float64, device=self.device)
             self._fg_host = torch.empty(1 + self.n_coef, dtype=torch.float64).pin_memory()
             self.plan = None  # column-major copy + work items, built on the first evaluation
+            self._ranked = None  # (rows with columns renumbered by falling frequency, permutation) -- see _prepare
         else:
             self.device = torch.device("cpu") if device is None else device
 
@@ -77,14 +78,48 @@ class FixedEffectSolver:
             return float(fg[0]), fg[1:].copy()
         self._x_dev.copy_(torch.from_numpy(x), non_blocking=False)
         if self.plan is None:
-            self.plan = capi.DeviceFePlan(self.rows)
-        capi.fe_loss_grad_device(self.rows, self.opts, self._x_dev, fg=self._fg_dev, plan=self.plan)
+            self._prepare()
+        if self._ranked is None:
+            capi.fe_loss_grad_device(self.rows, self.opts, self._x_dev, fg=self._fg_dev, plan=self.plan)
+        else:
+            # evaluate in the shard's own frequency order, hand the result back in the caller's feature order
+            # (two D-sized gathers; the all-reduce below needs one common order across ranks)
+            rows_r, perm_x, perm_fg = self._ranked
+            torch.index_select(self._x_dev, 0, perm_x, out=self._x_rank)
+            capi.fe_loss_grad_device(rows_r, self.opts, self._x_rank, fg=self._fg_rank, plan=self.plan)
+            self._fg_dev.index_copy_(0, perm_fg, self._fg_rank)
         if self.dist and self.world > 1:
             self.dist.all_reduce(self._fg_dev, group=self.group)  # value and gradient in one collective
         self._fg_host.copy_(self._fg_dev, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         fg = self._fg_host.numpy()
         return float(fg[0]), fg[1:].copy()
+
+    def _prepare(self):
+        """Once per training run: the column-major copy of the shard (capi.DeviceFePlan) and -- when x is larger
+        than the part of it the rows kernel keeps in shared memory (capi.FE_HEAD, 8192 coefficients) -- this
+        shard's features renumbered by falling frequency, so that the coefficients in shared memory are the ones
+        most non-zeros multiply whatever order the feature file happens to list them in.  The permutation never
+        leaves this object: x comes in and fg goes out in the caller's feature order."""
+        torch = self.torch
+        rows, D = self.rows, self.n_features
+        if D > capi.FE_HEAD and rows.nnz > 0:
+            counts = torch.bincount(rows.col.to(torch.int64), minlength=D)
+            by_freq = torch.sort(counts, descending=True, stable=True).indices      # feature at rank r
+            rank_of = torch.empty(D, dtype=torch.int32, device=self.device)
+            rank_of[by_freq] = torch.arange(D, dtype=torch.int32, device=self.device)
+            ranked = capi.DeviceFeRows.__new__(capi.DeviceFeRows)
+            ranked.__dict__.update(rows.__dict__)
+            ranked.col = rank_of[rows.col.to(torch.int64)].contiguous()
+            tail = torch.arange(D, self.n_coef, dtype=torch.int64, device=self.device)  # the intercept stays last
+            perm_x = torch.cat([by_freq, tail])
+            perm_fg = torch.cat([torch.zeros(1, dtype=torch.int64, device=self.device), 1 + perm_x])
+            self._ranked = (ranked, perm_x, perm_fg)
+            self._x_rank = torch.empty_like(self._x_dev)
+            self._fg_rank = torch.empty_like(self._fg_dev)
+            self.plan = capi.DeviceFePlan(ranked)
+        else:
+            self.plan = capi.DeviceFePlan(rows)
 
     # ---- solve ----------------------------------------------------------------------------------------
     def fit(self, x0=None, threshold=None):

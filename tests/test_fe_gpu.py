@@ -145,3 +145,31 @@ def test_planned_path_rows_of_every_size():
     f_o, g_o = O.fe_loss_grad(blk, O.make_opts(l2=0.3, regularize_bias=False, has_intercept=True), x)
     np.testing.assert_allclose(b[0], f_o, rtol=1e-12)
     np.testing.assert_allclose(b[1:], g_o, rtol=1e-10, atol=1e-10)
+
+
+def test_solver_frequency_ranking_is_invisible_to_the_caller():
+    """With more features than the rows kernel keeps of x in shared memory, FixedEffectSolver renumbers this
+    shard's features by falling frequency internally; value and gradient come back in the caller's order and
+    equal the oracle's, and a short solve equals the un-ranked one."""
+    rng = np.random.default_rng(23)
+    n, D, k = 6000, 20000, 10
+    rowptr = np.arange(n + 1, dtype=np.int64) * k
+    col = (D - 1 - np.minimum((D ** rng.random(n * k) - 1).astype(np.int64), D - 1)).astype(np.int32)  # hot ids HIGH
+    val = rng.standard_normal(n * k).astype(np.float32)
+    y = (rng.random(n) < 0.4).astype(np.float32)
+    rows = capi.DeviceFeRows(rowptr, col, val, y, None, None, D)
+    opts = capi.make_opts(l2=2.0, regularize_bias=True, has_intercept=True, max_iter=8)
+    solver = FixedEffectSolver(rows, opts)
+    x = rng.standard_normal(D + 1) * 0.05
+    f, g = solver.loss_grad(x)
+    assert solver._ranked is not None
+    blk = O.FeBlock(n, D, rowptr, col, val, y, np.ones(n, np.float32), np.zeros(n, np.float32))
+    f_o, g_o = O.fe_loss_grad(blk, O.make_opts(l2=2.0, regularize_bias=True, has_intercept=True), x)
+    np.testing.assert_allclose(f, f_o, rtol=1e-12)
+    np.testing.assert_allclose(g, g_o, rtol=1e-10, atol=1e-10)
+    xa, ia = solver.fit()
+    plain = FixedEffectSolver(rows, opts)
+    plain.plan = capi.DeviceFePlan(rows)      # skips _prepare: no ranking
+    xb, ib = plain.fit()
+    assert (ia["nit"], ia["nfev"]) == (ib["nit"], ib["nfev"])
+    np.testing.assert_allclose(xa, xb, rtol=1e-9, atol=1e-12)
