@@ -832,13 +832,11 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
                             else if (lane == 2u * MT + 1u) tot[lane] = fma(y0, gn0, tot[lane]);
                         }
                         __syncwarp();
-                        double uv, wv;
-                        lbfgs_small_update<MT>(lb, update, newslot, dotmask, stp, dr, gd, dense, uv, wv);
+                        double uv, wv, theta_n, gamma;
+                        lbfgs_small_update<MT>(lb, update, newslot, dotmask, stp, dr, gd, dense, uv, wv, theta_n, gamma);
                         if (update && (int)lane == newslot) { icept[lane] = stp * d0; icept[MT + lane] = y0; }
                         __syncwarp();
                         // intercept component of the next direction
-                        const double theta_n = update ? tot[2 * MT] / dr : lb.theta;
-                        const double gamma = 1.0 / theta_n;
                         double t = (lane < (uint32_t)MT) ? fma(gamma * wv, icept[MT + lane], -uv * icept[lane]) : 0.0;
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
@@ -848,14 +846,14 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
                         prefetch_entity_l2(a.b, (int64_t)e + gridDim.x, lane);
                     }
                     group_sync<G>();                                            // ---- B5
+                    lb.theta = dense[DNF::tot + 2 * MT];   // warp 0 left theta and gamma = 1 / theta there
                     if (update) {
-                        lb.theta = dense[DNF::tot + 2 * MT] / dr;
                         lb.valid |= (1u << newslot);
                         if (lb.col < m) lb.col++; else lb.head = (lb.head + 1) % m;
                     }
                     // H2: d = -gamma g - S u + gamma Y w, the next trial point x + d and the partials of g.d
                     {
-                        const double gamma = 1.0 / lb.theta;
+                        const double gamma = dense[DNF::tot + 2 * MT + 1];
                         double acc[EPT];
 #pragma unroll
                         for (int k = 0; k < EPT; k++) acc[k] = -gamma * gn[k];

@@ -28,13 +28,19 @@ __device__ __forceinline__ void lbfgs_reset(Lbfgs &L, double *dense)
 
 // The warp-sized part of the update, run by ONE full warp after dense[tot..] holds the 2*MT+2 totals
 // [S^T g | Y^T g | y.y | y.g]: appends / replaces the pair, refreshes R^-1, Y^T Y, D and leaves the
-// coefficient vectors u (dense[cu..]) and w (dense[cw..]) of H g = gamma g + S u - gamma Y w.  Lane i < MT
-// returns its u_i, w_i (0 for empty slots).
+// coefficient vectors u (dense[cu..]) and w (dense[cw..]) of H g = gamma g + S u - gamma Y w, and the new
+// scaling theta and gamma = 1 / theta in tot[2 MT], tot[2 MT + 1] (over the two totals it no longer needs) for
+// every thread of the group to pick up.  Lane i < MT returns its u_i, w_i (0 for empty slots).
+//
+// This is the one serial stretch of an iteration (the other warps of the group wait for it), so it is laid out
+// for latency: three dependent m x m products, not four -- the new column of R^-1, -R^-1 (S^T y_new) / dr,
+// and w = R_new^-1 p1 come out of ONE sweep over the old R^-1 (w_i = sum_{j != new} R^-1_ij p1_j + R^-1_i,new
+// p1_new) -- and no division on the dependent chain (1 / dr and gamma are formed beside the first sweep).
 template <int MT>
 __device__ __forceinline__ void lbfgs_small_update(const Lbfgs &L, const bool update, const int newslot,
                                                    const uint32_t dotmask, const double stp, const double dr,
                                                    const double gd_new, double *dense, double &uv_out,
-                                                   double &wv_out)
+                                                   double &wv_out, double &theta_out, double &gamma_out)
 {
     using DN = Dense<MT>;
     const uint32_t lane = threadIdx.x & 31;
@@ -42,55 +48,57 @@ __device__ __forceinline__ void lbfgs_small_update(const Lbfgs &L, const bool up
     const int i = lane;
     const bool in = i < MT;
     const bool old_i = in && ((dotmask >> i) & 1u);
+    const bool new_i = update && i == newslot;
     double p1i = old_i ? tot[i] : 0.0, p2i = old_i ? tot[MT + i] : 0.0;
     const double yyt = tot[2 * MT], ygt = tot[2 * MT + 1];
     double *Rinv = dense + DN::rinv, *YY = dense + DN::yy, *Dg = dense + DN::d;
     double *p1old = dense + DN::p1old, *p2old = dense + DN::p2old;
-    double *ta = dense + DN::ta, *tb = dense + DN::tb;
-    double theta = L.theta;
-    if (update) {
-        theta = yyt / dr;
-        const double rc = old_i ? p1i - p1old[i] : 0.0;  // s_i . y_new
-        const double yc = old_i ? p2i - p2old[i] : 0.0;  // y_i . y_new
-        if (in) ta[i] = rc;
-        __syncwarp();
-        double acc = 0.0;
-        if (in) {
-#pragma unroll
-            for (int j = 0; j < MT; j++) acc = fma(Rinv[i * MT + j], ta[j], acc);
-        }
-        __syncwarp();
-        if (in) {
-            Rinv[i * MT + newslot] = old_i ? -acc / dr : 0.0;
-            YY[i * MT + newslot] = yc;
-        }
-        __syncwarp();
-        if (in) {
-            Rinv[newslot * MT + i] = (i == newslot) ? 1.0 / dr : 0.0;
-            YY[newslot * MT + i] = (i == newslot) ? yyt : yc;
-        }
-        if (i == newslot) { Dg[i] = dr; p1i = stp * gd_new; p2i = ygt; }
-        __syncwarp();
-    }
+    double *ta = dense + DN::ta, *tb = dense + DN::tb, *cwv = dense + DN::cw;
+    const double inv_dr = update ? 1.0 / dr : 0.0;
+    const double theta = update ? yyt * inv_dr : L.theta;
+    const double gamma = 1.0 / theta;
+    const double rc = (update && old_i) ? p1i - p1old[i] : 0.0;  // s_i . y_new
+    const double yc = (update && old_i) ? p2i - p2old[i] : 0.0;  // y_i . y_new
+    const double p1new = stp * gd_new;                           // s_new . g_new
+    if (new_i) { p1i = p1new; p2i = ygt; }
     const uint32_t valid = update ? (L.valid | (1u << newslot)) : L.valid;
     const bool val_i = in && ((valid >> i) & 1u);
-    const double gamma = 1.0 / theta;
-    if (in) { p1old[i] = p1i; p2old[i] = p2i; ta[i] = val_i ? p1i : 0.0; }
+    if (in) {
+        ta[i] = rc;                                   // zero for the new slot and for empty ones
+        tb[i] = (val_i && !new_i) ? p1i : 0.0;
+        p1old[i] = p1i; p2old[i] = p2i;
+    }
     __syncwarp();
-    double wv = 0.0;
+    double acc = 0.0, wvp = 0.0;
     if (in) {
 #pragma unroll
-        for (int j = 0; j < MT; j++) wv = fma(Rinv[i * MT + j], ta[j], wv);
+        for (int j = 0; j < MT; j++) {
+            const double r = Rinv[i * MT + j];
+            acc = fma(r, ta[j], acc);
+            wvp = fma(r, tb[j], wvp);
+        }
     }
-    if (in) tb[i] = wv;
+    double wv = val_i ? wvp : 0.0;
+    __syncwarp();                                     // every lane is done reading the old R^-1
+    if (update) {
+        const double cnew = old_i ? -acc * inv_dr : 0.0;          // new column of R^-1 (old rows)
+        if (in) {
+            wv = new_i ? inv_dr * p1new : (old_i ? fma(cnew, p1new, wvp) : 0.0);
+            Rinv[i * MT + newslot] = new_i ? inv_dr : cnew;
+            Rinv[newslot * MT + i] = new_i ? inv_dr : 0.0;
+            YY[i * MT + newslot] = new_i ? yyt : yc;
+            YY[newslot * MT + i] = new_i ? yyt : yc;
+        }
+        if (new_i) Dg[i] = dr;
+    }
+    if (in) cwv[i] = wv;
     __syncwarp();
     double yw = 0.0;
     if (in) {
 #pragma unroll
-        for (int j = 0; j < MT; j++) yw = fma(YY[i * MT + j], tb[j], yw);
+        for (int j = 0; j < MT; j++) yw = fma(YY[i * MT + j], cwv[j], yw);
     }
     const double tv = val_i ? fma(Dg[i], wv, gamma * (yw - p2i)) : 0.0;
-    __syncwarp();
     if (in) ta[i] = tv;
     __syncwarp();
     double uv = 0.0;
@@ -98,8 +106,9 @@ __device__ __forceinline__ void lbfgs_small_update(const Lbfgs &L, const bool up
 #pragma unroll
         for (int j = 0; j < MT; j++) uv = fma(Rinv[j * MT + i], ta[j], uv);
     }
-    if (in) { dense[DN::cu + i] = uv; dense[DN::cw + i] = wv; }
-    uv_out = uv; wv_out = wv;
+    if (in) dense[DN::cu + i] = uv;
+    if (lane == 0) { tot[2 * MT] = theta; tot[2 * MT + 1] = gamma; }
+    uv_out = uv; wv_out = wv; theta_out = theta; gamma_out = gamma;
 }
 
 // After an accepted step: g = new gradient, gold = previous gradient, dv = the direction just used.
@@ -174,18 +183,18 @@ __device__ __forceinline__ void lbfgs_direction(Lbfgs &L, const int m, const boo
             tot[k] = t;
         }
         __syncwarp();
-        double uv, wv;
-        lbfgs_small_update<MT>(L, update, newslot, dotmask, stp, dr, gd_new, dense, uv, wv);
+        double uv, wv, th, ga;
+        lbfgs_small_update<MT>(L, update, newslot, dotmask, stp, dr, gd_new, dense, uv, wv, th, ga);
     }
     group_sync<G>();
+    L.theta = dense[DN::tot + 2 * MT];
     if (update) {
-        L.theta = dense[DN::tot + 2 * MT] / dr;
         L.valid |= (1u << newslot);
         if (L.col < m) L.col++; else L.head = (L.head + 1) % m;
     }
 
     // ---- pass H2: dv = -gamma g - S u + gamma Y w ------------------------------------------------------
-    const double gamma = 1.0 / L.theta;
+    const double gamma = dense[DN::tot + 2 * MT + 1];
     double cu[MT], cw[MT];
 #pragma unroll
     for (int s = 0; s < MT; s++) { cu[s] = dense[DN::cu + s]; cw[s] = gamma * dense[DN::cw + s]; }
