@@ -822,25 +822,21 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
                             double t = part[src];
 #pragma unroll
                             for (uint32_t w2 = 1; w2 < W; w2++) t += part[w2 * kFastPartK + src];
+                            if (E.hi) {
+                                // the intercept's share: icept[] = [S0 (m) | Y0 (m)], same order as tot[]
+                                if (lane < 2u * MT) t = fma(icept[lane], gn0, t);
+                                else if (lane == 2u * MT) t = fma(y0, y0, t);
+                                else t = fma(y0, gn0, t);
+                            }
                             tot[lane] = t;
-                        }
-                        __syncwarp();
-                        if (E.hi) {
-                            // the intercept's share: icept[] = [S0 (m) | Y0 (m)], same order as tot[]
-                            if (lane < 2u * MT) tot[lane] = fma(icept[lane], gn0, tot[lane]);
-                            else if (lane == 2u * MT) tot[lane] = fma(y0, y0, tot[lane]);
-                            else if (lane == 2u * MT + 1u) tot[lane] = fma(y0, gn0, tot[lane]);
                         }
                         __syncwarp();
                         double uv, wv, theta_n, gamma;
                         lbfgs_small_update<MT>(lb, update, newslot, dotmask, stp, dr, gd, dense, uv, wv, theta_n, gamma);
+                        // the intercept's components of the new pair (its direction component is formed by every
+                        // thread for itself in H2 below: that keeps it off this serial stretch)
                         if (update && (int)lane == newslot) { icept[lane] = stp * d0; icept[MT + lane] = y0; }
-                        __syncwarp();
-                        // intercept component of the next direction
-                        double t = (lane < (uint32_t)MT) ? fma(gamma * wv, icept[MT + lane], -uv * icept[lane]) : 0.0;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
-                        if (lane == 0) dense[DNF::count] = E.hi ? fma(-gamma, gn0, t) : 0.0;
+                        (void)uv; (void)wv; (void)theta_n; (void)gamma;
                     } else if (warp == 1 && iter == 1) {
                         // idle while warp 0 works: pull the entity a grid-width ahead in the queue towards L2
                         prefetch_entity_l2(a.b, (int64_t)e + gridDim.x, lane);
@@ -857,6 +853,7 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
                         double acc[EPT];
 #pragma unroll
                         for (int k = 0; k < EPT; k++) acc[k] = -gamma * gn[k];
+                        double a0 = -gamma * gn0;   // the intercept is one more coordinate: S0 / Y0 come from icept[]
 #pragma unroll
                         for (int s = 0; s < MT; s++) {
                             const double cu = dense[DNF::cu + s], cw = gamma * dense[DNF::cw + s];
@@ -865,8 +862,10 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
                                 acc[k] = fma(-cu, Sh[s][k], acc[k]);
                                 acc[k] = fma(cw, Yh[s][k], acc[k]);
                             }
+                            a0 = fma(-cu, icept[s], a0);
+                            a0 = fma(cw, icept[MT + s], a0);
                         }
-                        d0 = dense[DNF::count];
+                        d0 = E.hi ? a0 : 0.0;
                         double gdp = 0.0;
 #pragma unroll
                         for (int k = 0; k < EPT; k++) {
