@@ -799,7 +799,7 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
                     const int m = a.o.m;
                     const bool update = (m > 0) && !(dr <= epsmch * ddum);
                     int newslot = -1;
-                    if (update) newslot = (lb.col < m) ? (lb.head + lb.col) % m : lb.head;
+                    if (update) { newslot = (lb.col < m) ? lb.head + lb.col : lb.head; if (newslot >= m) newslot -= m; }   // head, col < m
                     const uint32_t dotmask = update ? (lb.valid & ~(1u << newslot)) : lb.valid;
                     // the new pair takes its slot: s = stp d, y = g_new - g_old
                     if (update) {
@@ -845,7 +845,7 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
                     lb.theta = dense[DNF::tot + 2 * MT];   // warp 0 left theta and gamma = 1 / theta there
                     if (update) {
                         lb.valid |= (1u << newslot);
-                        if (lb.col < m) lb.col++; else lb.head = (lb.head + 1) % m;
+                        if (lb.col < m) lb.col++; else lb.head = (lb.head + 1 == m) ? 0 : lb.head + 1;
                     }
                     // H2: d = -gamma g - S u + gamma Y w, the next trial point x + d and the partials of g.d
                     {

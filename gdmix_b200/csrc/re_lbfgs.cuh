@@ -127,7 +127,7 @@ __device__ __forceinline__ void lbfgs_direction(Lbfgs &L, const int m, const boo
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     int newslot = -1;
-    if (update) newslot = (L.col < m) ? (L.head + L.col) % m : L.head;
+    if (update) { newslot = (L.col < m) ? L.head + L.col : L.head; if (newslot >= m) newslot -= m; }   // head, col < m
     const uint32_t dotmask = update ? (L.valid & ~(1u << newslot)) : L.valid;  // surviving old pairs
 
     // ---- pass H1: inner products of every stored pair with g, plus y.y and y.g ------------------------
@@ -190,7 +190,7 @@ __device__ __forceinline__ void lbfgs_direction(Lbfgs &L, const int m, const boo
     L.theta = dense[DN::tot + 2 * MT];
     if (update) {
         L.valid |= (1u << newslot);
-        if (L.col < m) L.col++; else L.head = (L.head + 1) % m;
+        if (L.col < m) L.col++; else L.head = (L.head + 1 == m) ? 0 : L.head + 1;
     }
 
     // ---- pass H2: dv = -gamma g - S u + gamma Y w ------------------------------------------------------
