@@ -251,7 +251,8 @@ int plan_fast(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo 
                 FastShapePlan typ;
                 rc = plan_fast_shape(b, o, dev, N_typ, D_full, (int64_t)N_typ * nnz_per_row, true, typ);
                 if (rc) return rc;
-                if (typ.ok && typ.ctas_per_sm * typ.G > big.ctas_per_sm * big.G) {
+                // worth a launch of its own when it puts more entities on an SM at a time
+                if (typ.ok && typ.ctas_per_sm > big.ctas_per_sm) {
                     pl.fast0 = 1;
                     pl.f0G = typ.G; pl.f0EPT = typ.EPT; pl.f0ctas_per_sm = typ.ctas_per_sm; pl.f0grid = typ.grid;
                     pl.f0L = typ.L;
@@ -320,7 +321,14 @@ int plan_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &d
     pl.off_barena = pl.off_arena + (size_t)pl.arena_stride * (size_t)want;
     // global-X kernel: 256 threads, vectors + per-warp gradient copies on chip, history in its own arena
     {
-        const uint32_t need = gdmix::big_layout_bytes((uint32_t)b->max_coef, (uint32_t)b->max_coef - hi, 8u, (uint32_t)pl.MT);
+        uint32_t need = gdmix::big_layout_bytes((uint32_t)b->max_coef, (uint32_t)b->max_coef - hi, 8u, (uint32_t)pl.MT);
+        // room for several private gradient copies per warp (short rows are walked several to a warp step, one
+        // copy per team of lanes) as long as four CTAs still fit an SM
+        for (uint32_t copies = 32; copies > 1; copies >>= 1) {
+            const uint32_t with = gdmix::big_layout_bytes((uint32_t)b->max_coef, (uint32_t)b->max_coef - hi, 8u,
+                                                          (uint32_t)pl.MT, copies);
+            if (with <= 48u * 1024u) { need = std::max(need, with); break; }
+        }
         pl.bsmem = std::min(need, budget);   // entities with more coefficients than fit get GDMIX_ERR_TOO_LARGE
         const int per_sm = std::max(1, std::min(4, (int)((228u * 1024u) / (pl.bsmem + kStaticSmem + 1024u))));
         pl.bgrid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)dev.sm_count * per_sm, b->n_entities));
@@ -712,8 +720,8 @@ int gdmix_re_score(const gdmix_re_batch *b, const gdmix_lr_opts *o, const double
     DeviceInfo dev;
     int rc = device_info(dev);
     if (rc) return rc;
-    const int64_t warps = b->n_entities;
-    const int grid = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)dev.sm_count * 8);
+    if (b->n_rows <= 0) return GDMIX_OK;
+    const int grid = (int)std::min<int64_t>((b->n_rows + 255) / 256, (int64_t)dev.sm_count * 8);
     gdmix::re_score_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*b, o->has_intercept ? 1 : 0, theta, has_model,
                                                                   logit, logit_pc);
     g_launches++;
@@ -1026,6 +1034,7 @@ int gdmix_re_score_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const 
     db.col = (const int32_t *)(dv + o_col);
     db.val = (const float *)(dv + o_val);
     db.label = nullptr; db.weight = nullptr;
+    db.n_rows = nr; db.nnz = nz;
     db.offset = hb->offset ? (const float *)(dv + o_off) : nullptr;
     rc = gdmix_re_score(&db, o, theta ? (const double *)(dv + o_th) : nullptr,
                         has_model ? (const uint8_t *)(dv + o_hm) : nullptr, (float *)(dv + o_lg),

@@ -14,32 +14,37 @@
 
 namespace gdmix {
 
-// One warp per entity, lanes over the entity's samples.  theta is read through L2 (each entity's
-// coefficients are touched by one warp only), X once from HBM.
+// One thread per sample; the sample's entity is found by bisection of ent_rowptr (L2-resident), so an entity with
+// a million samples is scored by as many threads as one with ten (a warp per entity left the few huge entities of a
+// Zipf-distributed key as the kernel's tail).  theta is read through L1/L2, X once from HBM; per-sample arithmetic
+// and its order are those of the per-entity walk.
 __global__ void __launch_bounds__(256) re_score_kernel(const gdmix_re_batch b, const int hi, const double *theta,
                                                        const uint8_t *has_model, float *logit, float *logit_pc)
 {
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    for (int64_t e = warp; e < b.n_entities; e += nwarps) {
-        const int64_t r0 = b.ent_rowptr[e], r1 = b.ent_rowptr[e + 1];
-        const bool model = theta != nullptr && (has_model == nullptr || has_model[e] != 0);
-        const double *th = model ? theta + b.theta_ptr[e] : nullptr;
-        for (int64_t i = r0 + lane; i < r1; i += 32) {
-            const double offs = b.offset ? (double)b.offset[i] : 0.0;
-            double z;
-            if (model) {
-                z = hi ? th[0] : 0.0;
-                const int64_t qs = b.rowptr[i], qe = b.rowptr[i + 1];
-                for (int64_t q = qs; q < qe; q++) z = fma((double)b.val[q], th[hi + b.col[q]], z);
-                z = z + offs;
-            } else {
-                z = offs;
-            }
-            logit[i] = (float)z;
-            logit_pc[i] = (float)(z - offs);
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    const int64_t first = b.ent_rowptr[0], last = first + b.n_rows;
+    for (int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < last; i += nth) {
+        // e = the entity with ent_rowptr[e] <= i < ent_rowptr[e + 1]
+        int64_t lo = 0, hi_e = b.n_entities;   // invariant: ent_rowptr[lo] <= i < ent_rowptr[hi_e]
+        while (hi_e - lo > 1) {
+            const int64_t mid = (lo + hi_e) >> 1;
+            if (b.ent_rowptr[mid] <= i) lo = mid; else hi_e = mid;
         }
+        const int64_t e = lo;
+        const bool model = theta != nullptr && (has_model == nullptr || has_model[e] != 0);
+        const double offs = b.offset ? (double)b.offset[i] : 0.0;
+        double z;
+        if (model) {
+            const double *th = theta + b.theta_ptr[e];
+            z = hi ? th[0] : 0.0;
+            const int64_t qs = b.rowptr[i], qe = b.rowptr[i + 1];
+            for (int64_t q = qs; q < qe; q++) z = fma((double)b.val[q], th[hi + b.col[q]], z);
+            z = z + offs;
+        } else {
+            z = offs;
+        }
+        logit[i] = (float)z;
+        logit_pc[i] = (float)(z - offs);
     }
 }
 

@@ -121,7 +121,16 @@ __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
             ga = (double *)(smem + o); o += align16(8 * p);
             gb = (double *)(smem + o); o += align16(8 * p);
             dv = (double *)(smem + o); o += align16(8 * p);
-            B.gw = (double *)(smem + o); o += align16(8 * W * d);
+            // lanes per row from the entity's mean row length; as many private gradient copies per warp as the
+            // rows walked per step, if the shared memory given to the kernel holds them (else wider teams)
+            uint32_t ts = 0;
+            {
+                const uint32_t avg = (uint32_t)((nnz64 + n64 - 1) / n64);
+                while (ts < 5u && (1u << ts) < avg) ts++;
+                while (ts < 5u && big_layout_bytes(p, d, W, (uint32_t)MT, 32u >> ts) > a.smem_bytes) ts++;
+            }
+            B.ts = ts;
+            B.gw = (double *)(smem + o); o += align16(8 * W * (32u >> ts) * d);
             dense = (double *)(smem + o); o += align16(8 * dense_doubles((uint32_t)MT));
             part = (double *)(smem + o);
             double *hist = (double *)(a.arena + (unsigned long long)blockIdx.x * a.arena_stride);

@@ -319,14 +319,16 @@ __device__ __forceinline__ void evaluate(const Staged &S, const double *xt, cons
 struct BigEntity {
     int64_t r0;
     uint32_t n, d, p, hi;
-    double *gw;       // [W][d] per-warp copies of X^T r
+    uint32_t ts;      // log2 lanes per row ("team"): 32 >> ts rows are walked per warp step
+    double *gw;       // [W * (32 >> ts)][d] private copies of X^T r, one per team
     double inv_n, l2;
     int reg_bias;
 };
 
-__host__ __device__ inline uint32_t big_layout_bytes(uint32_t p, uint32_t d, uint32_t W, uint32_t mt)
+// `copies` = private gradient copies per warp (1 .. 32): one per team of lanes that walks a row of its own
+__host__ __device__ inline uint32_t big_layout_bytes(uint32_t p, uint32_t d, uint32_t W, uint32_t mt, uint32_t copies = 1)
 {
-    return 5u * align16(8 * p) + align16(8 * W * d) + align16(8 * dense_doubles(mt)) +
+    return 5u * align16(8 * p) + align16(8 * W * copies * d) + align16(8 * dense_doubles(mt)) +
            align16(8 * kMaxWarps * (2 * mt + 2));
 }
 
@@ -335,10 +337,22 @@ __device__ __forceinline__ void evaluate_big(const ReArgs &a, const BigEntity &B
                                              double *gt, double *red, int &flip, unsigned *s_bad, double &f,
                                              double &gd, double &gmax)
 {
+    // A warp owns 32 consecutive rows at a time and walks them 32 >> ts at a step, a team of 1 << ts lanes per
+    // row (ts from the entity's mean non-zeros per row: 8-wide rows go four to a step and a step's loads are one
+    // coalesced line).  Sweep 1: team sums of z by butterfly, handed to the lane whose index equals the row's
+    // position in the block; the loss / residual arithmetic runs on 32 rows in 32 lanes; sweep 2 folds r_i x_i
+    // into the TEAM's private copy of X^T r, row after row, so every copy has a fixed summation order (only a
+    // column repeated inside one row makes two lanes meet, hence the atomic).  The row pointers of a block are
+    // loaded once, one per lane.  Copies are added in (warp, team) order.
     constexpr uint32_t W = G / 32;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double *gw = B.gw + (size_t)warp * B.d;
-    for (uint32_t j = lane; j < B.d; j += 32) gw[j] = 0.0;
+    const uint32_t ts = B.ts, T = 1u << ts, RS = 32u >> ts;
+    const uint32_t t = lane & (T - 1u), q = lane >> ts;
+    {
+        double *mine = B.gw + (size_t)warp * RS * B.d;
+        for (uint32_t j = lane; j < RS * B.d; j += 32) mine[j] = 0.0;
+    }
+    double *gw = B.gw + ((size_t)warp * RS + q) * B.d;
     __syncwarp();
     const double b0 = B.hi ? xt[0] : 0.0;
     const double *xf = xt + B.hi;
@@ -347,18 +361,23 @@ __device__ __forceinline__ void evaluate_big(const ReArgs &a, const BigEntity &B
     const uint32_t nblk = (B.n + 31u) >> 5;
     for (uint32_t blk = warp; blk < nblk; blk += W) {
         const uint32_t base = blk << 5, cnt = min(32u, B.n - base);
+        int64_t rp0 = 0, rp1 = 0;
+        if (lane < cnt) { rp0 = a.b.rowptr[B.r0 + base + lane]; rp1 = a.b.rowptr[B.r0 + base + lane + 1]; }
+        const uint32_t nsteps = (cnt + RS - 1u) >> (5u - ts);
         double myz = 0.0;
-        for (uint32_t s = 0; s < cnt; s++) {
-            const int64_t gi = B.r0 + base + s;
-            const int64_t qs = a.b.rowptr[gi], qe = a.b.rowptr[gi + 1];
+        for (uint32_t s = 0; s < nsteps; s++) {
+            const uint32_t row = s * RS + q;   // position in the block, < 32
+            const int64_t qs = __shfl_sync(kFull, rp0, row), qe = __shfl_sync(kFull, rp1, row);
             double z = 0.0;
-            for (int64_t k = qs + lane; k < qe; k += 32) {
-                const uint32_t c = (uint32_t)a.b.col[k];
-                if (c < B.d) z = fma((double)a.b.val[k], xf[c], z); else bad = 1;
+            if (row < cnt) {
+                for (int64_t k = qs + t; k < qe; k += T) {
+                    const uint32_t c = (uint32_t)a.b.col[k];
+                    if (c < B.d) z = fma((double)a.b.val[k], xf[c], z); else bad = 1;
+                }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(kFull, z, o);
-            if (lane == s) myz = z;
+            for (uint32_t m2 = T >> 1; m2 > 0; m2 >>= 1) z += __shfl_xor_sync(kFull, z, m2);
+            const double v = __shfl_sync(kFull, z, (lane & (RS - 1u)) << ts);
+            if ((lane >> (5u - ts)) == s) myz = v;   // lane j takes row j = s * RS + (j mod RS)
         }
         double ri = 0.0;
         if (lane < cnt) {
@@ -373,13 +392,15 @@ __device__ __forceinline__ void evaluate_big(const ReArgs &a, const BigEntity &B
             ri = wi * (sig - yi);
             rs += ri;
         }
-        for (uint32_t s = 0; s < cnt; s++) {
-            const double rv = __shfl_sync(kFull, ri, s);
-            const int64_t gi = B.r0 + base + s;
-            const int64_t qs = a.b.rowptr[gi], qe = a.b.rowptr[gi + 1];
-            for (int64_t k = qs + lane; k < qe; k += 32) {
-                const uint32_t c = (uint32_t)a.b.col[k];
-                if (c < B.d) atomicAdd(&gw[c], (double)a.b.val[k] * rv);
+        for (uint32_t s = 0; s < nsteps; s++) {
+            const uint32_t row = s * RS + q;
+            const double rv = __shfl_sync(kFull, ri, row);
+            const int64_t qs = __shfl_sync(kFull, rp0, row), qe = __shfl_sync(kFull, rp1, row);
+            if (row < cnt) {
+                for (int64_t k = qs + t; k < qe; k += T) {
+                    const uint32_t c = (uint32_t)a.b.col[k];
+                    if (c < B.d) atomicAdd(&gw[c], (double)a.b.val[k] * rv);
+                }
             }
             __syncwarp();
         }
@@ -391,13 +412,13 @@ __device__ __forceinline__ void evaluate_big(const ReArgs &a, const BigEntity &B
         sq = fma(xt[jj], xt[jj], sq);
     }
     double part[3] = {fs, rs, sq};
-    group_sum<G, 3>(part, red, flip);  // its barrier also completes every warp's copy
+    group_sum<G, 3>(part, red, flip);  // its barrier also completes every team's copy
     if (G == 32) __syncwarp();
     f = (part[0] + 0.5 * B.l2 * part[2]) * B.inv_n;
     double gdp = 0.0, gmp = 0.0;
     for (uint32_t c = tid; c < B.d; c += G) {
         double acc = 0.0;
-        for (uint32_t w2 = 0; w2 < W; w2++) acc += B.gw[(size_t)w2 * B.d + c];
+        for (uint32_t w2 = 0; w2 < W * RS; w2++) acc += B.gw[(size_t)w2 * B.d + c];
         const uint32_t j = c + B.hi;
         const double gj = (acc + B.l2 * xt[j]) * B.inv_n;
         gt[j] = gj;
