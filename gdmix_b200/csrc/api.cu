@@ -95,6 +95,9 @@ struct RePlan {
     uint32_t bsmem = 0;
     unsigned long long barena_stride = 0;
     size_t off_defer_b = 0, off_barena = 0;
+    // ... and the ones with so many samples that one CTA would be the launch's tail: a cluster of kGiantCluster CTAs each
+    int ggrid = 0, giant_rows = 0;
+    size_t off_giant = 0, off_garena = 0;
     // FULL variance pass (re_variance.cuh)
     int vgrid = 0;
     uint32_t vsmem = 0, vsmem_matrix_doubles = 0;
@@ -104,6 +107,8 @@ struct RePlan {
 };
 
 constexpr size_t kQueueBytes = 256;
+constexpr int kGiantCluster = 8;          // CTAs per cluster of the giant-entity launch (portable maximum)
+constexpr int kGiantRowsDefault = 32768;  // samples from which an unstageable entity is solved by a cluster
 constexpr uint32_t kStaticSmem = 1024;  // upper bound on the kernels' static shared memory
 
 int choose_group(const gdmix_re_batch *b, const gdmix_lr_opts *o)
@@ -335,6 +340,15 @@ int plan_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &d
         pl.barena_stride = (unsigned long long)gdmix::align16(16u * (uint32_t)o->m * (uint32_t)b->max_coef);
     }
     pl.workspace = pl.off_barena + (size_t)pl.barena_stride * (size_t)pl.bgrid;
+    {
+        // giant entities: two clusters' worth of CTAs per eight SMs, same shared memory and arena stride
+        const char *env_giant = getenv("GDMIX_GIANT_ROWS");   // test hook: 1 sends every unstageable entity there
+        pl.giant_rows = env_giant ? std::max(1, atoi(env_giant)) : kGiantRowsDefault;
+        pl.ggrid = kGiantCluster * std::max(1, dev.sm_count * 2 / kGiantCluster);
+        pl.off_giant = (pl.workspace + 255) & ~(size_t)255;
+        pl.off_garena = pl.off_giant + list_bytes;
+        pl.workspace = pl.off_garena + (size_t)pl.barena_stride * (size_t)pl.ggrid;
+    }
     if (o->variance_mode == GDMIX_VARIANCE_FULL) {
         const size_t P = (size_t)b->max_coef;
         const size_t vec_bytes = 2 * 8 * P;
@@ -379,6 +393,32 @@ int launch_fast_t(const gdmix::FastArgs &fa, int grid, cudaStream_t st)
     gdmix::re_fast_kernel<G, EPT><<<grid, G, fa.L.total_bytes, st>>>(fa);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
+// The same kernel as a thread-block cluster: kGiantCluster CTAs share one entity (re_kernel.cuh).
+template <int MT>
+int launch_giant_t(const gdmix::ReArgs &args, const RePlan &pl, cudaStream_t st)
+{
+    static std::atomic<int> configured{0};
+    if (!configured.load()) {
+        CUDA_TRY(cudaFuncSetAttribute(gdmix::re_solver_kernel<256, MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024 - (int)kStaticSmem));
+        configured.store(1);
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)pl.ggrid, 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = pl.bsmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kGiantCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, gdmix::re_solver_kernel<256, MT, true>, args));
+    g_launches++;
     return GDMIX_OK;
 }
 
@@ -490,6 +530,10 @@ int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const d
     // whatever the staged kernels cannot hold goes to list B
     a.defer_list = (int32_t *)((unsigned char *)workspace + pl.off_defer_b);
     a.defer_count = (int32_t *)workspace + 5;
+    // ... the ones with very many samples to list C ([8] its queue, [9] its length)
+    a.giant_list = (int32_t *)((unsigned char *)workspace + pl.off_giant);
+    a.giant_count = (int32_t *)workspace + 9;
+    a.giant_rows = pl.giant_rows;
     // The general kernels solve one model per launch: a sweep runs them once per weight over the same lists
     // (only what the fast kernel deferred, when there is one), with their work counters rewound in between.
     const int n_models = n_l2 > 0 ? n_l2 : 1;
@@ -508,6 +552,7 @@ int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const d
             // counters: [0] / [1] general queue, [4] list-B queue, [5] list-B length ([2] = fast kernel's list length stays)
             CUDA_TRY(cudaMemsetAsync((int32_t *)workspace + (pl.fast ? 1 : 0), 0, 4, st));
             CUDA_TRY(cudaMemsetAsync((int32_t *)workspace + 4, 0, 8, st));
+            CUDA_TRY(cudaMemsetAsync((int32_t *)workspace + 8, 0, 8, st));
         }
     }
     if (pl.MT == 10) {
@@ -533,11 +578,20 @@ int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const d
         g2.todo = a.defer_list;
         g2.todo_count = a.defer_count;
         g2.defer_list = nullptr; g2.defer_count = nullptr;
+        g2.giant_list = nullptr; g2.giant_count = nullptr;
         g2.arena = (unsigned char *)workspace + pl.off_barena;
         g2.arena_stride = pl.barena_stride;
         g2.hist_global = 1;
         g2.smem_bytes = pl.bsmem;
         rc = (pl.MT == 10) ? launch_big_t<10>(g2, pl, st) : launch_big_t<32>(g2, pl, st);
+        if (rc) return rc;
+        // list C: a cluster of CTAs per entity
+        gdmix::ReArgs g3 = g2;
+        g3.queue = (int32_t *)workspace + 8;
+        g3.todo = a.giant_list;
+        g3.todo_count = a.giant_count;
+        g3.arena = (unsigned char *)workspace + pl.off_garena;
+        rc = (pl.MT == 10) ? launch_giant_t<10>(g3, pl, st) : launch_giant_t<32>(g3, pl, st);
     }
     if (rc) return rc;
     }   // models of the sweep

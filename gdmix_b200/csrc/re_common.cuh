@@ -53,6 +53,9 @@ struct ReArgs {
     const int32_t *todo_count;
     int32_t *defer_list;        // optional: entities this kernel cannot hold on chip go here instead of failing
     int32_t *defer_count;
+    int32_t *giant_list;        // optional: of those, entities with at least giant_rows samples go here -- they are
+    int32_t *giant_count;       //   solved by a CLUSTER of CTAs that splits the samples (re_kernel.cuh)
+    int32_t giant_rows;
     unsigned char *arena;       // per-CTA global scratch for history that does not fit on chip
     unsigned long long arena_stride;
     int32_t mode;

@@ -34,6 +34,13 @@ __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
     __shared__ double red[2 * kMaxWarps * kRedK];
     __shared__ int s_entity;
     __shared__ unsigned s_bad;
+    __shared__ double cl_part[4];   // BIG, cluster launch: this CTA's loss / residual sums for the other CTAs to read
+
+    // BIG only: launched as a thread-block cluster, all CTAs of a cluster solve ONE entity together -- the samples
+    // are split over them in evaluate_big, everything else is replicated (see there).  C == 1 otherwise.
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t C = BIG ? cluster.num_blocks() : 1u, crank = BIG ? cluster.block_rank() : 0u;
 
     const uint32_t tid = threadIdx.x;
     const uint32_t hi = a.o.has_intercept ? 1u : 0u;
@@ -41,10 +48,22 @@ __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
     int flip = 0;
 
     for (;;) {
-        group_sync<G>();  // previous entity fully emitted before its memory is reused
-        if (tid == 0) { s_entity = atomicAdd(a.queue, 1); s_bad = 0; }
-        group_sync<G>();
-        int64_t e = s_entity;
+        int64_t e;
+        if (BIG && C > 1) {
+            cluster.sync();   // previous entity done in every CTA of the cluster (and its index read by all)
+            if (tid == 0) { if (crank == 0) s_entity = atomicAdd(a.queue, 1); s_bad = 0; }
+            cluster.sync();
+            e = *cluster.map_shared_rank(&s_entity, 0);
+            if (a.todo ? (e >= (int64_t)*a.todo_count) : (e >= a.b.n_entities)) {
+                cluster.sync();   // no CTA leaves while another may still be reading its shared memory
+                break;
+            }
+        } else {
+            group_sync<G>();  // previous entity fully emitted before its memory is reused
+            if (tid == 0) { s_entity = atomicAdd(a.queue, 1); s_bad = 0; }
+            group_sync<G>();
+            e = s_entity;
+        }
         if (a.todo) {
             if (e >= (int64_t)*a.todo_count) break;
             e = a.todo[e];
@@ -76,7 +95,8 @@ __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
             if (!ok) {
                 // too large to stage: hand it to the kernel that leaves X in global memory
                 if (tid == 0) {
-                    if (a.defer_list) a.defer_list[atomicAdd(a.defer_count, 1)] = (int32_t)e;
+                    if (a.giant_list && n64 >= (int64_t)a.giant_rows) a.giant_list[atomicAdd(a.giant_count, 1)] = (int32_t)e;
+                    else if (a.defer_list) a.defer_list[atomicAdd(a.defer_count, 1)] = (int32_t)e;
                     else if (a.status) a.status[e] = GDMIX_ERR_TOO_LARGE;
                 }
                 continue;
@@ -139,7 +159,7 @@ __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
             B.inv_n = 1.0 / (double)n; B.l2 = a.o.l2; B.reg_bias = a.o.regularize_bias;
         }
         auto eval = [&](const double *xt_, const double *dv_, double *gt_, double &f_, double &gd_, double &gm_) {
-            if constexpr (BIG) evaluate_big<G>(a, B, xt_, dv_, gt_, red, flip, &s_bad, f_, gd_, gm_);
+            if constexpr (BIG) evaluate_big<G>(a, B, xt_, dv_, gt_, red, flip, &s_bad, cl_part, f_, gd_, gm_);
             else evaluate<G>(S, xt_, dv_, gt_, red, flip, f_, gd_, gm_);
         };
 
@@ -163,8 +183,10 @@ __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
         }
 
         if (a.mode == kModeLossGrad) {
-            for (uint32_t j = tid; j < p; j += G) a.g_out[t0 + j] = g[j];
-            if (tid == 0) a.f_out[e] = f;
+            if (crank == 0) {
+                for (uint32_t j = tid; j < p; j += G) a.g_out[t0 + j] = g[j];
+                if (tid == 0) a.f_out[e] = f;
+            }
             continue;
         }
 
@@ -241,6 +263,7 @@ __global__ void __launch_bounds__(G) re_solver_kernel(const ReArgs a)
         }
 
         // ---- emit ---------------------------------------------------------------------------------------
+        if (crank != 0) continue;   // every CTA of a cluster holds the same answer: rank 0 writes it
         const double thr = a.o.sparsity_threshold;
         for (uint32_t j = tid; j < p; j += G) {
             const double xj = x[j];

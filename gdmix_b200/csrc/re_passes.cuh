@@ -13,6 +13,7 @@
 // z = X1.theta + offset, the stable cross entropy and the residual follow
 // binary_logistic_regression.py:84-110 (_loss) and :121-131 (_gradient) of the reference.
 #pragma once
+#include <cooperative_groups.h>
 #include "re_common.cuh"
 
 namespace gdmix {
@@ -332,11 +333,19 @@ __host__ __device__ inline uint32_t big_layout_bytes(uint32_t p, uint32_t d, uin
            align16(8 * kMaxWarps * (2 * mt + 2));
 }
 
+// When the kernel runs as a thread-block cluster (entities with hundreds of thousands of samples, see
+// re_solver_kernel), the row blocks are dealt round-robin over the cluster's CTAs: each CTA ends up with ITS
+// part of X^T r and of the loss in its own shared memory, the cluster synchronises, and every CTA adds the C parts
+// in rank order through distributed shared memory -- so all CTAs hold bit-identical f and g and run the same
+// (replicated) solver steps without any further exchange, exactly as the ranks of the fixed-effect solve do.
 template <int G>
 __device__ __forceinline__ void evaluate_big(const ReArgs &a, const BigEntity &B, const double *xt, const double *dv,
-                                             double *gt, double *red, int &flip, unsigned *s_bad, double &f,
-                                             double &gd, double &gmax)
+                                             double *gt, double *red, int &flip, unsigned *s_bad, double *cl_part,
+                                             double &f, double &gd, double &gmax)
 {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t C = cluster.num_blocks(), crank = cluster.block_rank();
     // A warp owns 32 consecutive rows at a time and walks them 32 >> ts at a step, a team of 1 << ts lanes per
     // row (ts from the entity's mean non-zeros per row: 8-wide rows go four to a step and a step's loads are one
     // coalesced line).  Sweep 1: team sums of z by butterfly, handed to the lane whose index equals the row's
@@ -359,7 +368,7 @@ __device__ __forceinline__ void evaluate_big(const ReArgs &a, const BigEntity &B
     double fs = 0.0, rs = 0.0;
     unsigned bad = 0;
     const uint32_t nblk = (B.n + 31u) >> 5;
-    for (uint32_t blk = warp; blk < nblk; blk += W) {
+    for (uint32_t blk = crank * W + warp; blk < nblk; blk += W * C) {
         const uint32_t base = blk << 5, cnt = min(32u, B.n - base);
         int64_t rp0 = 0, rp1 = 0;
         if (lane < cnt) { rp0 = a.b.rowptr[B.r0 + base + lane]; rp1 = a.b.rowptr[B.r0 + base + lane + 1]; }
@@ -414,11 +423,33 @@ __device__ __forceinline__ void evaluate_big(const ReArgs &a, const BigEntity &B
     double part[3] = {fs, rs, sq};
     group_sum<G, 3>(part, red, flip);  // its barrier also completes every team's copy
     if (G == 32) __syncwarp();
+    if (C > 1) {
+        // this CTA's part of X^T r goes where copy 0 was (thread c reads column c of every copy, then writes it),
+        // its loss / residual sums and its bad-column flag beside it
+        for (uint32_t c = tid; c < B.d; c += G) {
+            double acc = 0.0;
+            for (uint32_t w2 = 0; w2 < W * RS; w2++) acc += B.gw[(size_t)w2 * B.d + c];
+            B.gw[c] = acc;
+        }
+        if (tid == 0) { cl_part[0] = part[0]; cl_part[1] = part[1]; cl_part[2] = *s_bad ? 1.0 : 0.0; }
+        cluster.sync();
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        for (uint32_t r = 0; r < C; r++) {
+            const double *q = cluster.map_shared_rank(cl_part, r);
+            t0 += q[0]; t1 += q[1]; t2 += q[2];
+        }
+        part[0] = t0; part[1] = t1;
+        if (t2 != 0.0 && tid == 0) *s_bad = 1u;
+    }
     f = (part[0] + 0.5 * B.l2 * part[2]) * B.inv_n;
     double gdp = 0.0, gmp = 0.0;
     for (uint32_t c = tid; c < B.d; c += G) {
         double acc = 0.0;
-        for (uint32_t w2 = 0; w2 < W * RS; w2++) acc += B.gw[(size_t)w2 * B.d + c];
+        if (C > 1) {
+            for (uint32_t r = 0; r < C; r++) acc += cluster.map_shared_rank(B.gw, r)[c];
+        } else {
+            for (uint32_t w2 = 0; w2 < W * RS; w2++) acc += B.gw[(size_t)w2 * B.d + c];
+        }
         const uint32_t j = c + B.hi;
         const double gj = (acc + B.l2 * xt[j]) * B.inv_n;
         gt[j] = gj;
@@ -434,6 +465,7 @@ __device__ __forceinline__ void evaluate_big(const ReArgs &a, const BigEntity &B
     group_sum_max<G>(gdp, gmp, red, flip);
     gd = gdp;
     gmax = gmp;
+    if (C > 1) cluster.sync();   // nobody rewrites its part while another CTA may still be reading it
 }
 
 // SIMPLE variance for the same entities: var_j = 1 / (sum_i x_ij^2 rho_i (1 - rho_i) w_i + l2 [j regularised] + 1e-12)

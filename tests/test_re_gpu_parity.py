@@ -18,12 +18,17 @@ from tests.golden_util import is_pinned, load_re  # noqa: E402
 REL_TOL = 1e-5  # north_star tolerance
 
 
-@pytest.fixture(autouse=True, params=["auto", "generic", "big"])
+@pytest.fixture(autouse=True, params=["auto", "generic", "big", "giant"])
 def re_path(request, monkeypatch):
-    """Every test runs three times: through the planner's choice (the sliced-ELL fast kernel when the batch
-    qualifies), through the general staged kernel alone, and through the kernel that leaves X in global memory
-    (the one entities too large for the chip take)."""
-    if request.param != "auto":
+    """Every test runs four times: through the planner's choice (the sliced-ELL fast kernel when the batch
+    qualifies), through the general staged kernel alone, through the kernel that leaves X in global memory
+    (the one entities too large for the chip take), and through that kernel launched as thread-block clusters
+    (eight CTAs share an entity's samples -- what entities with tens of thousands of samples take)."""
+    monkeypatch.delenv("GDMIX_GIANT_ROWS", raising=False)
+    if request.param == "giant":
+        monkeypatch.setenv("GDMIX_RE_PATH", "big")
+        monkeypatch.setenv("GDMIX_GIANT_ROWS", "1")
+    elif request.param != "auto":
         monkeypatch.setenv("GDMIX_RE_PATH", request.param)
     else:
         monkeypatch.delenv("GDMIX_RE_PATH", raising=False)
