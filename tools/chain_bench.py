@@ -94,7 +94,7 @@ def re_stage(name, keys, rp, col, val, off, Dn):
     E = st.numel()
     cnt = fit["workspace"][:32].view(torch.int32).cpu().numpy()
     out[name] = {"entities": E, "max_rows": gb.host.max_rows, "group_s": t_group, "fit_s": t_fit, "entities_per_s": E / t_fit,
-                 "rows_per_s": n / t_fit, "score_s": t_score, "converged_frac": float((st == 0).float().mean().item()),
+                 "rows_per_s": n / t_fit, "score_s": t_score, "converged_frac": float((st == 0).double().mean().item()),
                  "rejected": int((st < 0).sum().item()), "mean_nit": float(fit["nit"].float().mean().item()),
                  "plan": plan, "deferred_typical": int(cnt[7]), "deferred_to_general": int(cnt[2]),
                  "deferred_to_global_x": int(cnt[5]), "auc": P.auc(s, y)}
