@@ -271,6 +271,8 @@ def run_ours(args):
     # ---- e2e: host CSR in pinned memory -> gdmix_re_fit_host -> coefficients on the host -------------------
     e2e = None
     Ee = min(args.e2e_entities, E)
+    if world >= 4:
+        Ee = min(Ee, 262144)   # keeps the pinned host staging of an 8-rank run under 50 GB in total
     rows_e, nnz_e, coef_e = Ee * w["n"], Ee * w["n"] * w["k"], Ee * (w["d"] + 1)
 
     def pinned(t):

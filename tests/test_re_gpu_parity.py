@@ -448,3 +448,55 @@ def test_narrow_column_transfers_are_equivalent():
         np.testing.assert_array_equal(t, outs[0][0])
         np.testing.assert_array_equal(n, outs[0][1])
     assert hb.c_struct().col8 is not None and hb.c_struct().col16 is None
+
+
+def test_c1_shape_at_scale_properties():
+    """BASELINE.json configs[1] shape at 100 000 entities generated on the device (the bench's generator): every
+    entity converges, the objective the solver reports equals gdmix_re_loss_grad at the returned coefficients,
+    the gradient there passes scipy's pgtol test or the step was stopped by factr, and a random sample of entities
+    pulled back to the host matches the oracle (coefficients <= 1e-5 relative, identical iteration counts)."""
+    import ctypes as C
+    from gdmix_b200.synthetic import make_device_batch
+    E, n, d, k = 100_000, 128, 256, 32
+    data = make_device_batch(E, n, d, k, seed=424242)
+    cb = capi.ReBatch(E, data["n_rows"], data["nnz"], data["ent_rowptr"].data_ptr(), data["rowptr"].data_ptr(),
+                      data["col"].data_ptr(), data["val"].data_ptr(), data["label"].data_ptr(), None,
+                      data["offset"].data_ptr(), data["theta_ptr"].data_ptr(), data["max_rows"], data["max_nnz"],
+                      data["max_coef"], 0)
+    opts = capi.make_opts(l2=1.0, regularize_bias=False)
+    ws = torch.empty(max(capi.re_workspace_size(cb, opts), 256), dtype=torch.uint8, device="cuda")
+    theta = torch.empty(data["n_coef"], dtype=torch.float64, device="cuda")
+    f = torch.empty(E, dtype=torch.float64, device="cuda")
+    nit = torch.empty(E, dtype=torch.int32, device="cuda")
+    nfev = torch.empty_like(nit)
+    status = torch.empty_like(nit)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    capi.check(capi.lib.gdmix_re_fit(C.byref(cb), C.byref(opts), None, P(theta), P(f), P(nit), P(nfev), P(status), None,
+                                     P(ws), C.c_size_t(ws.numel()), st))
+    f2 = torch.empty_like(f)
+    g2 = torch.empty_like(theta)
+    capi.check(capi.lib.gdmix_re_loss_grad(C.byref(cb), C.byref(opts), P(theta), P(f2), P(g2), P(ws),
+                                           C.c_size_t(ws.numel()), st))
+    torch.cuda.synchronize()
+    assert bool((status == 0).all())
+    assert torch.allclose(f, f2, rtol=1e-13, atol=0.0)
+    gmax = g2.abs().view(E, d + 1).max(1).values
+    small = float((gmax <= 1e-5).double().mean().item())
+    print("max|g| <= pgtol for", small, "of the entities; mean nit", float(nit.float().mean()))
+    assert small > 0.99 and float(gmax.max()) < 1e-3     # any rest stopped on factr, a hair above pgtol
+    # a sample against the oracle
+    rng = np.random.default_rng(0)
+    pick = np.sort(rng.choice(E, 48, replace=False))
+    rows = (pick[:, None] * n + np.arange(n)[None, :]).reshape(-1)
+    nz = (rows[:, None] * k + np.arange(k)[None, :]).reshape(-1)
+    tr = torch.from_numpy(rows).cuda()
+    tz = torch.from_numpy(nz).cuda()
+    hb = capi.HostBatch(np.arange(len(pick) + 1, dtype=np.int64) * n, np.arange(len(rows) + 1, dtype=np.int64) * k,
+                        data["col"][tz].cpu().numpy(), data["val"][tz].cpu().numpy(), data["label"][tr].cpu().numpy(),
+                        None, data["offset"][tr].cpu().numpy(), np.arange(len(pick) + 1, dtype=np.int64) * (d + 1))
+    th_o, f_o, nit_o, nfev_o, st_o = O.re_fit_batch(_oracle_batch(hb), _oracle_opts(opts))
+    th_d = theta.view(E, d + 1)[torch.from_numpy(pick).cuda()].cpu().numpy().reshape(-1)
+    rel = _rel_per_entity(th_d, th_o, hb.theta_ptr)
+    assert rel.max() <= REL_TOL, rel.max()
+    assert (nit.cpu().numpy()[pick] == nit_o).all() and (nfev.cpu().numpy()[pick] == nfev_o).all()
