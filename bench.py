@@ -253,12 +253,12 @@ def run_ours(args):
     kernel = (f"re_fast_kernel<{plan['threads']},{plan['ept']}>" if plan["fast"] else
               f"re_solver_kernel<{plan['threads']}>")
     # DRAM bytes per entity of this kernel on this workload from the committed ncu --set full capture
-    # (profiles/r1_ncu_full_re_fast_v7.txt: dram__bytes_read.sum + dram__bytes_write.sum over 30 000 entities)
-    ncu_dram_bytes_per_entity = (1.045423e9 + 78.837504e6) / 30000.0
+    # (profiles/r1_ncu_full_re_fast_v8.txt: dram__bytes_read.sum + dram__bytes_write.sum over 30 000 entities)
+    ncu_dram_bytes_per_entity = (1.047181e9 + 87.874816e6) / 30000.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_dram_bytes_per_entity * E if w["name"] == "c1" else None,
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per entity "
-                                  "(profiles/r1_ncu_full_re_fast_v7.txt) x entities per launch",
+                                  "(profiles/r1_ncu_full_re_fast_v8.txt) x entities per launch",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel": kernel, "plan": plan,
                 "kernel_ms_per_launch": kern_s * 1e3,

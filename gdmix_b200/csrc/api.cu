@@ -864,7 +864,7 @@ int gdmix_fe_loss_grad_planned(const gdmix_fe_rows *rows, const gdmix_fe_plan *p
         const int64_t i1 = n_launch > 1 ? pl->tile_item_ptr[t + 1] : pl->n_items;
         if (i1 <= i0) continue;
         if (i0 < 0 || i1 > pl->n_items) return fail(GDMIX_ERR_INVALID, "tile_item_ptr outside [0, n_items]");
-        const int cgrid = (int)std::max<int64_t>(1, std::min<int64_t>((i1 - i0 + 7) / 8, (int64_t)dev.sm_count * 8));
+        const int cgrid = (int)std::max<int64_t>(1, std::min<int64_t>((i1 - i0 + 7) / 8, (int64_t)dev.sm_count * 16));
         gdmix::fe_cols_kernel<<<cgrid, 256, 0, st>>>(*rows, *o, P, x, fg, i0, i1);
         g_launches++;
     }
