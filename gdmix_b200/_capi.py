@@ -32,7 +32,7 @@ SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_w
            "gdmix_lbfgs_info", "gdmix_lbfgs_destroy", "gdmix_launch_count", "gdmix_re_last_plan",
            "gdmix_partition_workspace_size", "gdmix_sort_pairs_u64", "gdmix_group_by_key", "gdmix_csr_gather_rows",
            "gdmix_gather_f32", "gdmix_partition_ids_i64", "gdmix_auc", "gdmix_re_fit_sweep",
-           "gdmix_re_last_plan_typical"]
+           "gdmix_re_last_plan_typical", "gdmix_local_index_mark", "gdmix_local_index_apply"]
 
 
 class GdmixError(RuntimeError):

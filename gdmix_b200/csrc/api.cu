@@ -1246,6 +1246,56 @@ int gdmix_partition_ids_i64(const int64_t *ids, int64_t n, int32_t num_partition
     return GDMIX_OK;
 }
 
+int gdmix_local_index_mark(const int64_t *ent_rowptr, int64_t n_entities, const int64_t *rowptr, const int32_t *gcol,
+                           int64_t n_rows, int32_t num_features, uint32_t *bitmap, uint32_t *word_prefix, int64_t *d_e,
+                           void *stream)
+{
+    if (!ent_rowptr || !rowptr || !bitmap || !word_prefix || !d_e || n_entities < 0 || n_rows < 0 || num_features <= 0)
+        return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_local_index_mark");
+    if (n_entities == 0) return GDMIX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int32_t W32 = (num_features + 31) / 32;
+    // the last word of the prefix array doubles as the bad-column flag's home: keep it apart instead
+    unsigned *bad = nullptr;
+    CUDA_TRY(cudaMemsetAsync(bitmap, 0, (size_t)n_entities * W32 * 4, st));
+    CUDA_TRY(cudaMemsetAsync(d_e, 0, 8, st));
+    bad = (unsigned *)d_e;   // d_e[0] is overwritten by the count kernel after the flag has been read back
+    if (n_rows > 0) {
+        const int g = (int)std::min<int64_t>((n_rows + 255) / 256, 148 * 16);
+        gdmix::bitmap_mark_kernel<<<g, 256, 0, st>>>(ent_rowptr, n_entities, rowptr, gcol, n_rows, num_features, W32, bitmap, bad);
+        g_launches++;
+    }
+    unsigned bad_h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bad_h, bad, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (bad_h) return fail(GDMIX_ERR_INVALID, "a feature id is outside [0, num_features)");
+    const int g2 = (int)std::min<int64_t>((n_entities + 255) / 256, 148 * 16);
+    gdmix::bitmap_count_kernel<<<g2, 256, 0, st>>>(bitmap, n_entities, W32, word_prefix, d_e);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
+int gdmix_local_index_apply(const int64_t *ent_rowptr, int64_t n_entities, const int64_t *rowptr, const int32_t *gcol,
+                            int64_t n_rows, int32_t num_features, const uint32_t *bitmap, const uint32_t *word_prefix,
+                            const int64_t *uniq_ptr, int32_t *local_col, int64_t *uniq_global, void *stream)
+{
+    if (!ent_rowptr || !rowptr || !bitmap || !word_prefix || !uniq_ptr || !uniq_global || num_features <= 0)
+        return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_local_index_apply");
+    if (n_entities <= 0) return GDMIX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int32_t W32 = (num_features + 31) / 32;
+    if (n_rows > 0) {
+        const int g = (int)std::min<int64_t>((n_rows + 255) / 256, 148 * 16);
+        gdmix::bitmap_index_kernel<<<g, 256, 0, st>>>(ent_rowptr, n_entities, rowptr, gcol, n_rows, W32, bitmap, word_prefix, local_col);
+    }
+    const int g2 = (int)std::min<int64_t>((n_entities + 255) / 256, 148 * 16);
+    gdmix::bitmap_list_kernel<<<g2, 256, 0, st>>>(bitmap, n_entities, W32, uniq_ptr, uniq_global);
+    g_launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
 int gdmix_auc(const float *score, const float *label, int64_t n, double *out3, void *ws, size_t ws_bytes, void *stream)
 {
     if (n <= 0 || !score || !label || !out3 || !ws) return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_auc");

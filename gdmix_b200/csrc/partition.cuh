@@ -326,6 +326,90 @@ __global__ void __launch_bounds__(256) partition_i64_kernel(const int64_t *ids, 
     }
 }
 
+// ---- entity-local feature indexing by presence bitmaps ------------------------------------------------------------
+// What prepare_jobs derives per entity with np.unique(cols, return_inverse=True) (job_consumers.py:243): the sorted
+// distinct global feature ids of an entity and, for every non-zero, the rank of its feature among them.  With a
+// feature bag of at most a few thousand ids an entity's set is a bitmap of W32 = ceil(D / 32) words:
+//   mark    thread per sample: entity by bisection of ent_rowptr, atomicOr of the sample's feature bits
+//   count   thread per (entity, word): popcount -> prefix inside the entity (a lane walks its entity's words)
+//   index   thread per sample again: local = prefix[word] + popc(bits below), written over the global id
+//   list    thread per entity: its set bits in ascending order -> uniq_global[uniq_ptr[e] ..]
+// Integer work only: the result is the one the (entity, feature) pair sort gives, bit for bit.
+__device__ __forceinline__ int64_t entity_of_row(const int64_t *ent_rowptr, const int64_t n_entities, const int64_t i)
+{
+    int64_t lo = 0, hi = n_entities;   // ent_rowptr[lo] <= i < ent_rowptr[hi]
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (ent_rowptr[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) bitmap_mark_kernel(const int64_t *ent_rowptr, const int64_t n_entities, const int64_t *rowptr,
+                                                          const int32_t *gcol, const int64_t n_rows, const int32_t D, const int32_t W32,
+                                                          uint32_t *bitmap, unsigned *bad)
+{
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += nth) {
+        const int64_t e = entity_of_row(ent_rowptr, n_entities, i);
+        uint32_t *bm = bitmap + e * W32;
+        for (int64_t q = rowptr[i]; q < rowptr[i + 1]; q++) {
+            const uint32_t c = (uint32_t)gcol[q];
+            if (c >= (uint32_t)D) { *bad = 1u; continue; }
+            // look first: an entity with millions of samples would otherwise hammer two words with atomics
+            // (a stale read only costs a redundant atomic)
+            const uint32_t bit = 1u << (c & 31u);
+            if (!(__ldcg(&bm[c >> 5]) & bit)) atomicOr(&bm[c >> 5], bit);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bitmap_count_kernel(const uint32_t *bitmap, const int64_t n_entities, const int32_t W32,
+                                                           uint32_t *word_prefix, int64_t *d_e)
+{
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_entities; e += nth) {
+        uint32_t run = 0;
+        for (int32_t w = 0; w < W32; w++) {
+            word_prefix[e * W32 + w] = run;
+            run += __popc(bitmap[e * W32 + w]);
+        }
+        d_e[e] = run;
+    }
+}
+
+__global__ void __launch_bounds__(256) bitmap_index_kernel(const int64_t *ent_rowptr, const int64_t n_entities, const int64_t *rowptr,
+                                                           const int32_t *gcol, const int64_t n_rows, const int32_t W32,
+                                                           const uint32_t *bitmap, const uint32_t *word_prefix, int32_t *local_col)
+{
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += nth) {
+        const int64_t e = entity_of_row(ent_rowptr, n_entities, i);
+        const uint32_t *bm = bitmap + e * W32, *wp = word_prefix + e * W32;
+        for (int64_t q = rowptr[i]; q < rowptr[i + 1]; q++) {
+            const uint32_t c = (uint32_t)gcol[q], w = c >> 5;
+            local_col[q] = (int32_t)(wp[w] + __popc(bm[w] & ((1u << (c & 31u)) - 1u)));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bitmap_list_kernel(const uint32_t *bitmap, const int64_t n_entities, const int32_t W32,
+                                                          const int64_t *uniq_ptr, int64_t *uniq_global)
+{
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_entities; e += nth) {
+        int64_t at = uniq_ptr[e];
+        for (int32_t w = 0; w < W32; w++) {
+            uint32_t bits = bitmap[e * W32 + w];
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                uniq_global[at++] = (int64_t)w * 32 + b;
+                bits &= bits - 1u;
+            }
+        }
+    }
+}
+
 // ---- AUC ------------------------------------------------------------------------------------------------
 // scores -> sortable keys (ascending), payload = 1 for a NEGATIVE (label <= 0), 0 for a positive
 __global__ void __launch_bounds__(256) auc_keys_kernel(const float *score, const float *label, const int64_t n, uint64_t *keys,

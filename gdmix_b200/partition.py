@@ -126,6 +126,26 @@ def regroup_batch(entity, rowptr, gcol, val, label, offset=None, weight=None, ha
     off = gather_f32(offset, perm) if offset is not None else None
     wt = gather_f32(weight, perm) if weight is not None else None
     nnz = gc.numel()
+    hi = 1 if has_intercept else 0
+    w32 = (int(num_features) + 31) // 32 if num_features else 0
+    if num_features and num_features <= BITMAP_MAX_FEATURES and E * w32 <= (1 << 28) and not FORCE_PAIR_SORT:
+        # small feature bags: per-entity presence bitmaps instead of sorting (entity, feature) pairs
+        ent_rowptr = ent_rowptr.contiguous()
+        bitmap = torch.empty(E * w32, dtype=torch.int32, device=dev)
+        wprefix = torch.empty(E * w32, dtype=torch.int32, device=dev)
+        d_e = torch.empty(E, dtype=torch.int64, device=dev)
+        check(lib.gdmix_local_index_mark(_tptr(ent_rowptr), C.c_int64(E), _tptr(rp), _tptr(gc), C.c_int64(n),
+                                         C.c_int32(int(num_features)), _tptr(bitmap), _tptr(wprefix), _tptr(d_e),
+                                         _stream_ptr(None)))
+        uniq_ptr = torch.zeros(E + 1, dtype=torch.int64, device=dev)
+        uniq_ptr[1:] = torch.cumsum(d_e, 0)
+        uniq_global = torch.empty(int(uniq_ptr[-1].item()), dtype=torch.int64, device=dev)
+        local = torch.empty(nnz, dtype=torch.int32, device=dev)
+        check(lib.gdmix_local_index_apply(_tptr(ent_rowptr), C.c_int64(E), _tptr(rp), _tptr(gc), C.c_int64(n),
+                                          C.c_int32(int(num_features)), _tptr(bitmap), _tptr(wprefix), _tptr(uniq_ptr),
+                                          _tptr(local), _tptr(uniq_global), _stream_ptr(None)))
+        return _finish_regroup(ent_rowptr, rp, local, va, lab, off, wt, d_e, hi, E, n, nnz, perm, entity_ids,
+                               uniq_ptr, uniq_global)
     # entity index of every row / non-zero of the grouped batch (O(n) expansion of O(E) segments)
     ent_of_row = torch.repeat_interleave(torch.arange(E, device=dev), ent_rowptr[1:] - ent_rowptr[:-1])
     ent_of_nnz = torch.repeat_interleave(ent_of_row, rp[1:] - rp[:-1])
@@ -141,7 +161,18 @@ def regroup_batch(entity, rowptr, gcol, val, label, offset=None, weight=None, ha
     group_of_sorted = torch.repeat_interleave(torch.arange(pkey.numel(), device=dev), pseg[1:] - pseg[:-1])
     local = torch.empty(nnz, dtype=torch.int32, device=dev)
     local[pperm.long()] = (group_of_sorted - uniq_ptr[ent_of_group[group_of_sorted]]).to(torch.int32)
-    hi = 1 if has_intercept else 0
+    return _finish_regroup(ent_rowptr, rp, local, va, lab, off, wt, d_e, hi, E, n, nnz, perm, entity_ids, uniq_ptr,
+                           uniq_global)
+
+
+BITMAP_MAX_FEATURES = 2048   # feature bags up to this size are indexed by presence bitmaps (gdmix_local_index_*)
+FORCE_PAIR_SORT = False      # tests: take the (entity, feature) pair sort regardless
+
+
+def _finish_regroup(ent_rowptr, rp, local, va, lab, off, wt, d_e, hi, E, n, nnz, perm, entity_ids, uniq_ptr,
+                    uniq_global):
+    import torch
+    dev = rp.device
     theta_ptr = torch.zeros(E + 1, dtype=torch.int64, device=dev)
     theta_ptr[1:] = torch.cumsum(d_e + hi, 0)
     rows_e = ent_rowptr[1:] - ent_rowptr[:-1]

@@ -291,6 +291,20 @@ GDMIX_API int gdmix_partition_ids_i64(const int64_t *ids, int64_t n, int32_t num
                                       void *stream);
 GDMIX_API int gdmix_auc(const float *score, const float *label, int64_t n, double *out3, void *ws, size_t ws_bytes,
                         void *stream);
+/* Entity-local feature indexing (np.unique(cols, return_inverse=True) per entity, job_consumers.py:243) for feature
+ * bags of at most a few thousand ids, by per-entity presence bitmaps instead of an (entity, feature) pair sort.
+ * The batch is already grouped: entity e owns samples [ent_rowptr[e], ent_rowptr[e+1]).
+ *   mark:   bitmap[E * W32] (W32 = ceil(num_features / 32)), word_prefix[E * W32], d_e[E] = distinct features per entity;
+ *           synchronises the stream once (ids outside [0, num_features) are an error)
+ *   apply:  with uniq_ptr[E+1] = exclusive scan of d_e (the caller's), local_col[nnz] = rank of each non-zero's feature
+ *           among its entity's distinct ids (may alias gcol), uniq_global[uniq_ptr[E]] = those ids, ascending */
+GDMIX_API int gdmix_local_index_mark(const int64_t *ent_rowptr, int64_t n_entities, const int64_t *rowptr,
+                                     const int32_t *gcol, int64_t n_rows, int32_t num_features, uint32_t *bitmap,
+                                     uint32_t *word_prefix, int64_t *d_e, void *stream);
+GDMIX_API int gdmix_local_index_apply(const int64_t *ent_rowptr, int64_t n_entities, const int64_t *rowptr,
+                                      const int32_t *gcol, int64_t n_rows, int32_t num_features, const uint32_t *bitmap,
+                                      const uint32_t *word_prefix, const int64_t *uniq_ptr, int32_t *local_col,
+                                      int64_t *uniq_global, void *stream);
 
 /* Replicated host-side solver state of the fixed-effect solve: L-BFGS-B without bounds, reverse
  * communication, the role scipy.optimize.fmin_l_bfgs_b plays at fixed_effect_lr_lbfgs_model.py:635-643.

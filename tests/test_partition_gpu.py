@@ -126,3 +126,44 @@ def test_regroup_on_device_then_fit_matches_host_grouping():
         got = theta[tp[g]:tp[g + 1]]
         np.testing.assert_allclose(got[0], th_ref[0], rtol=1e-6, atol=1e-9)
         np.testing.assert_allclose(got[1:], th_ref[1 + used], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("D", [20, 64, 100, 2048])
+def test_bitmap_local_indexing_equals_the_pair_sort(D, monkeypatch):
+    """Feature bags of up to 2048 ids are indexed per entity by presence bitmaps (gdmix_local_index_*); the result
+    is the one the (entity, feature) pair sort gives, bit for bit: np.unique(cols, return_inverse=True) per entity
+    (job_consumers.py:243)."""
+    rng = np.random.default_rng(D)
+    n, E = 5000, 300
+    ent = rng.integers(0, E, n).astype(np.int64) * 3 + 1
+    lens = rng.integers(0, 9, n)
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    nnz = int(rowptr[-1])
+    gcol = rng.integers(0, D, nnz).astype(np.int32)            # repeats inside a row included
+    val = rng.standard_normal(nnz).astype(np.float32)
+    y = (rng.random(n) < 0.5).astype(np.float32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    a = P.regroup_batch(t(ent), t(rowptr), t(gcol), t(val), t(y), None, None, num_features=D)
+    monkeypatch.setattr(P, "FORCE_PAIR_SORT", True)
+    b = P.regroup_batch(t(ent), t(rowptr), t(gcol), t(val), t(y), None, None, num_features=D)
+    for k in ("ent_rowptr", "rowptr", "col", "val", "label", "theta_ptr", "perm", "entity_ids", "uniq_ptr", "uniq_global"):
+        assert torch.equal(a[k], b[k]), k
+    for k in ("n_entities", "n_rows", "nnz", "max_rows", "max_nnz", "max_coef", "n_coef"):
+        assert a[k] == b[k], k
+    # and against numpy, entity by entity
+    col, up, ug = a["col"].cpu().numpy(), a["uniq_ptr"].cpu().numpy(), a["uniq_global"].cpu().numpy()
+    er, rp, perm = a["ent_rowptr"].cpu().numpy(), a["rowptr"].cpu().numpy(), a["perm"].cpu().numpy().astype(np.int64)
+    for e in range(0, a["n_entities"], 17):
+        rows = perm[er[e]:er[e + 1]]
+        g = np.concatenate([gcol[rowptr[r]:rowptr[r + 1]] for r in rows]) if len(rows) else np.zeros(0, np.int32)
+        u, inv = np.unique(g, return_inverse=True)
+        np.testing.assert_array_equal(ug[up[e]:up[e + 1]], u)
+        np.testing.assert_array_equal(col[rp[er[e]]:rp[er[e + 1]]], inv)
+
+
+def test_bitmap_local_indexing_rejects_ids_outside_the_bag():
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    with pytest.raises(capi.GdmixError):
+        P.regroup_batch(t(np.array([5, 5, 7], np.int64)), t(np.array([0, 1, 2, 3], np.int64)),
+                        t(np.array([1, 64, 2], np.int32)), t(np.ones(3, np.float32)), t(np.ones(3, np.float32)), None, None,
+                        num_features=64)
