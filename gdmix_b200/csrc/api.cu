@@ -851,11 +851,11 @@ int gdmix_fe_loss_grad_planned(const gdmix_fe_rows *rows, const gdmix_fe_plan *p
         const uint32_t smem = gdmix::fe_rows_smem_bytes(head);
         static std::atomic<int> configured{0};
         if (!configured.load()) {
-            CUDA_TRY(cudaFuncSetAttribute(gdmix::fe_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            CUDA_TRY(cudaFuncSetAttribute(gdmix::fe_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)gdmix::fe_rows_smem_bytes(gdmix::kFeHeadMax)));
             configured.store(1);
         }
-        gdmix::fe_rows_kernel<<<grid, gdmix::kFeRowsThreads, smem, st>>>(*rows, *o, P, x, head);
+        gdmix::fe_rows_kernel<false><<<grid, gdmix::kFeRowsThreads, smem, st>>>(*rows, *o, P, x, head, nullptr, nullptr);
     }
     // column pass: one launch per row tile (stream order keeps every warp inside the tile whose dz is in L2)
     const int64_t n_launch = (pl->n_tiles > 1 && pl->tile_item_ptr) ? pl->n_tiles : 1;
@@ -906,9 +906,20 @@ int gdmix_fe_score(const gdmix_fe_rows *rows, const gdmix_lr_opts *o, const doub
     DeviceInfo dev;
     int rc = device_info(dev);
     if (rc) return rc;
-    const int grid = (int)std::min<int64_t>((rows->n_rows + 255) / 256, (int64_t)dev.sm_count * 8);
-    gdmix::fe_score_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*rows, o->has_intercept ? 1 : 0, x, logit,
-                                                                  logit_pc);
+    // the rows pass of the objective (rows staged per warp, leading coefficients of x in shared memory), writing logits
+    int grid = 1, team_shift = 0;
+    fe_rows_geometry(rows, dev, grid, team_shift);
+    const uint32_t head = (uint32_t)std::min<int64_t>(rows->n_features, gdmix::kFeHeadMax);
+    static std::atomic<int> configured{0};
+    if (!configured.load()) {
+        CUDA_TRY(cudaFuncSetAttribute(gdmix::fe_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)gdmix::fe_rows_smem_bytes(gdmix::kFeHeadMax)));
+        configured.store(1);
+    }
+    gdmix::FePlan P;
+    memset(&P, 0, sizeof(P));
+    gdmix::fe_rows_kernel<true><<<grid, gdmix::kFeRowsThreads, gdmix::fe_rows_smem_bytes(head), (cudaStream_t)stream>>>(
+        *rows, *o, P, x, head, logit, logit_pc);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return GDMIX_OK;

@@ -226,8 +226,12 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// SCORE = false: loss and dz per row (the objective's first pass).  SCORE = true: the same walk, but the row's
+// z goes out as the two fp32 logits of _scoring_fn (fixed_effect_lr_lbfgs_model.py:214-270) and nothing else is kept.
+template <bool SCORE>
 __global__ void __launch_bounds__(kFeRowsThreads, 1) fe_rows_kernel(const gdmix_fe_rows R, const gdmix_lr_opts o,
-                                                                    const FePlan P, const double *x, const uint32_t head)
+                                                                    const FePlan P, const double *x, const uint32_t head,
+                                                                    float *logit, float *logit_pc)
 {
     // A warp owns 32 consecutive rows at a time.  Their non-zeros are one contiguous range of the CSR arrays:
     // the warp copies it into shared memory asynchronously (cp.async, 16 bytes per lane and instruction when
@@ -317,6 +321,14 @@ __global__ void __launch_bounds__(kFeRowsThreads, 1) fe_rows_kernel(const gdmix_
             done += nfit;
         }
         const int64_t i = base + lane;
+        if (SCORE) {
+            if (i < R.n_rows) {
+                const double z = myz + b0, offs = R.offset ? (double)R.offset[i] : 0.0;
+                logit_pc[i] = (float)z;
+                logit[i] = (float)(z + offs);
+            }
+            continue;
+        }
         if (i < R.n_rows) {
             double z = myz + (R.offset ? (double)R.offset[i] : 0.0);
             z += b0;
@@ -336,6 +348,7 @@ __global__ void __launch_bounds__(kFeRowsThreads, 1) fe_rows_kernel(const gdmix_
             dz_sum += dz;
         }
     }
+    if (SCORE) return;
     value = warp_sum(value);
     dz_sum = warp_sum(dz_sum);
     if (lane == 0) { sv[wib] = value; sd[wib] = dz_sum; }
@@ -416,22 +429,6 @@ __global__ void __launch_bounds__(256) fe_finish_kernel(const gdmix_fe_rows R, c
     if (threadIdx.x == 0) {
         fg[0] = sh[0][0] + 0.5 * l2w * sh[2][0];
         if (hi) fg[1 + D] = sh[1][0] + (o.regularize_bias ? l2w * x[D] : 0.0);
-    }
-}
-
-__global__ void __launch_bounds__(256) fe_score_kernel(const gdmix_fe_rows R, const int hi, const double *x,
-                                                       float *logit, float *logit_pc)
-{
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
-    const double b0 = hi ? x[R.n_features] : 0.0;
-    for (int64_t i = tid; i < R.n_rows; i += nth) {
-        double z = 0.0;
-        for (int64_t q = R.rowptr[i]; q < R.rowptr[i + 1]; q++) z = fma((double)R.val[q], x[R.col[q]], z);
-        z += b0;
-        const double offs = R.offset ? (double)R.offset[i] : 0.0;
-        logit_pc[i] = (float)z;
-        logit[i] = (float)(z + offs);
     }
 }
 
