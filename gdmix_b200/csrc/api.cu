@@ -107,7 +107,7 @@ struct RePlan {
 };
 
 constexpr size_t kQueueBytes = 256;
-constexpr int kGiantCluster = 8;          // CTAs per cluster of the giant-entity launch (portable maximum)
+constexpr int kGiantCluster = 8;          // CTAs per cluster of the giant-entity launch (portable maximum); 16 where the device takes it
 constexpr int kGiantRowsDefault = 32768;  // samples from which an unstageable entity is solved by a cluster
 constexpr uint32_t kStaticSmem = 1024;  // upper bound on the kernels' static shared memory
 
@@ -344,7 +344,7 @@ int plan_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &d
         // giant entities: two clusters' worth of CTAs per eight SMs, same shared memory and arena stride
         const char *env_giant = getenv("GDMIX_GIANT_ROWS");   // test hook: 1 sends every unstageable entity there
         pl.giant_rows = env_giant ? std::max(1, atoi(env_giant)) : kGiantRowsDefault;
-        pl.ggrid = kGiantCluster * std::max(1, dev.sm_count * 2 / kGiantCluster);
+        pl.ggrid = 16 * std::max(1, dev.sm_count * 2 / 16);   // a multiple of both cluster sizes
         pl.off_giant = (pl.workspace + 255) & ~(size_t)255;
         pl.off_garena = pl.off_giant + list_bytes;
         pl.workspace = pl.off_garena + (size_t)pl.barena_stride * (size_t)pl.ggrid;
@@ -408,7 +408,7 @@ int launch_giant_t(const gdmix::ReArgs &args, const RePlan &pl, cudaStream_t st)
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)pl.ggrid, 1, 1);
+    cfg.gridDim = dim3((unsigned)pl.ggrid, 1, 1);   // a multiple of 16
     cfg.blockDim = dim3(256, 1, 1);
     cfg.dynamicSmemBytes = pl.bsmem;
     cfg.stream = st;
@@ -417,6 +417,24 @@ int launch_giant_t(const gdmix::ReArgs &args, const RePlan &pl, cudaStream_t st)
     attr[0].val.clusterDim.x = kGiantCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    {
+        // sixteen CTAs per entity (non-portable cluster size) where a GPC holds such a cluster with this much shared memory
+        static std::atomic<int> cluster16{-1};
+        if (cluster16.load() < 0) {
+            int ok16 = 0;
+            if (cudaFuncSetAttribute(gdmix::re_solver_kernel<256, MT, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) ==
+                cudaSuccess) {
+                attr[0].val.clusterDim.x = 16;
+                int nclusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&nclusters, gdmix::re_solver_kernel<256, MT, true>, &cfg) == cudaSuccess &&
+                    nclusters >= 4)
+                    ok16 = 1;
+            }
+            cudaGetLastError();
+            cluster16.store(ok16);
+        }
+        attr[0].val.clusterDim.x = cluster16.load() ? 16 : kGiantCluster;
+    }
     CUDA_TRY(cudaLaunchKernelEx(&cfg, gdmix::re_solver_kernel<256, MT, true>, args));
     g_launches++;
     return GDMIX_OK;

@@ -374,19 +374,35 @@ __device__ __forceinline__ void evaluate_big(const ReArgs &a, const BigEntity &B
         if (lane < cnt) { rp0 = a.b.rowptr[B.r0 + base + lane]; rp1 = a.b.rowptr[B.r0 + base + lane + 1]; }
         const uint32_t nsteps = (cnt + RS - 1u) >> (5u - ts);
         double myz = 0.0;
-        for (uint32_t s = 0; s < nsteps; s++) {
-            const uint32_t row = s * RS + q;   // position in the block, < 32
-            const int64_t qs = __shfl_sync(kFull, rp0, row), qe = __shfl_sync(kFull, rp1, row);
-            double z = 0.0;
-            if (row < cnt) {
-                for (int64_t k = qs + t; k < qe; k += T) {
-                    const uint32_t c = (uint32_t)a.b.col[k];
-                    if (c < B.d) z = fma((double)a.b.val[k], xf[c], z); else bad = 1;
-                }
+        // four steps at a time: their first loads are all in flight before any is consumed (a step is one
+        // dependent global round trip otherwise, and this kernel has few warps to hide it behind)
+        for (uint32_t s0 = 0; s0 < nsteps; s0 += 4) {
+            int64_t kk[4], ee[4];
+            uint32_t cc[4];
+            float vv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t row = ((s0 + u) * RS + q) & 31u;
+                const int64_t qs = __shfl_sync(kFull, rp0, row), qe = __shfl_sync(kFull, rp1, row);
+                const bool on = (s0 + u) < nsteps && (s0 + u) * RS + q < cnt;
+                kk[u] = qs + t; ee[u] = on ? qe : qs;   // off: an empty range
+                cc[u] = 0; vv[u] = 0.0f;
+                if (kk[u] < ee[u]) { cc[u] = (uint32_t)a.b.col[kk[u]]; vv[u] = a.b.val[kk[u]]; }
             }
-            for (uint32_t m2 = T >> 1; m2 > 0; m2 >>= 1) z += __shfl_xor_sync(kFull, z, m2);
-            const double v = __shfl_sync(kFull, z, (lane & (RS - 1u)) << ts);
-            if ((lane >> (5u - ts)) == s) myz = v;   // lane j takes row j = s * RS + (j mod RS)
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                double z = 0.0;
+                if (kk[u] < ee[u]) {
+                    if (cc[u] < B.d) z = (double)vv[u] * xf[cc[u]]; else bad = 1;
+                    for (int64_t k = kk[u] + T; k < ee[u]; k += T) {   // rows longer than the team
+                        const uint32_t c = (uint32_t)a.b.col[k];
+                        if (c < B.d) z = fma((double)a.b.val[k], xf[c], z); else bad = 1;
+                    }
+                }
+                for (uint32_t m2 = T >> 1; m2 > 0; m2 >>= 1) z += __shfl_xor_sync(kFull, z, m2);
+                const double v = __shfl_sync(kFull, z, (lane & (RS - 1u)) << ts);
+                if ((lane >> (5u - ts)) == s0 + u) myz = v;   // lane j takes row j = s * RS + (j mod RS)
+            }
         }
         double ri = 0.0;
         if (lane < cnt) {
@@ -401,17 +417,32 @@ __device__ __forceinline__ void evaluate_big(const ReArgs &a, const BigEntity &B
             ri = wi * (sig - yi);
             rs += ri;
         }
-        for (uint32_t s = 0; s < nsteps; s++) {
-            const uint32_t row = s * RS + q;
-            const double rv = __shfl_sync(kFull, ri, row);
-            const int64_t qs = __shfl_sync(kFull, rp0, row), qe = __shfl_sync(kFull, rp1, row);
-            if (row < cnt) {
-                for (int64_t k = qs + t; k < qe; k += T) {
-                    const uint32_t c = (uint32_t)a.b.col[k];
-                    if (c < B.d) atomicAdd(&gw[c], (double)a.b.val[k] * rv);
-                }
+        for (uint32_t s0 = 0; s0 < nsteps; s0 += 4) {
+            int64_t kk[4], ee[4];
+            uint32_t cc[4];
+            float vv[4];
+            double rr[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t row = ((s0 + u) * RS + q) & 31u;
+                rr[u] = __shfl_sync(kFull, ri, row);
+                const int64_t qs = __shfl_sync(kFull, rp0, row), qe = __shfl_sync(kFull, rp1, row);
+                const bool on = (s0 + u) < nsteps && (s0 + u) * RS + q < cnt;
+                kk[u] = qs + t; ee[u] = on ? qe : qs;
+                cc[u] = 0; vv[u] = 0.0f;
+                if (kk[u] < ee[u]) { cc[u] = (uint32_t)a.b.col[kk[u]]; vv[u] = a.b.val[kk[u]]; }
             }
-            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 4; u++) {   // rows enter the team's copy one after the other: fixed order
+                if (kk[u] < ee[u]) {
+                    if (cc[u] < B.d) atomicAdd(&gw[cc[u]], (double)vv[u] * rr[u]);
+                    for (int64_t k = kk[u] + T; k < ee[u]; k += T) {
+                        const uint32_t c = (uint32_t)a.b.col[k];
+                        if (c < B.d) atomicAdd(&gw[c], (double)a.b.val[k] * rr[u]);
+                    }
+                }
+                __syncwarp();
+            }
         }
     }
     if (bad) atomicOr(s_bad, 1u);
