@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-cudart", "static",
+           "-Xcompiler", "-fPIC,-fvisibility=hidden,-fopenmp", "-shared", "-cudart", "static", "-lgomp",
            "-Xptxas", "-v" if verbose else "-warn-spills",
            "-o", LIB] + os.environ.get("GDMIX_NVCC_FLAGS", "").split() + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)

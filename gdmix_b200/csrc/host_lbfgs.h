@@ -17,6 +17,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
+#include <thread>
 #include <vector>
 
 namespace gdmix_host {
@@ -183,10 +185,44 @@ public:
     const double *grad() const { return g_.data(); }
 
 private:
+    // Long vectors (a 100 000-feature fixed effect streams 32 MB of history through the two-loop recursion per
+    // iteration) are swept by several host threads.  Sums are formed per fixed block of kBlock entries and the block
+    // sums added in block order, so the result does not depend on the number of threads -- every rank, whatever
+    // its core count, keeps bit-identical solver state.  Vectors of at most kBlock entries are summed exactly as
+    // before (one block).
+    static constexpr int64_t kBlock = 4096, kParMin = 32768;
+    static int host_threads()
+    {
+        static const int k = [] {
+            const char *lw = getenv("LOCAL_WORLD_SIZE");
+            const char *cap = getenv("GDMIX_HOST_THREADS");
+            const int ranks = lw ? std::max(1, atoi(lw)) : 1;
+            const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+            const int want = cap ? atoi(cap) : std::min(16, hw / ranks);
+            return std::max(1, want);
+        }();
+        return k;
+    }
     double dot(const double *a, const double *b) const
     {
+        if (n_ <= kBlock) {
+            double s = 0.0;
+            for (int64_t i = 0; i < n_; i++) s += a[i] * b[i];
+            return s;
+        }
+        const int64_t nb = (n_ + kBlock - 1) / kBlock;
+        part_.resize((size_t)nb);
+        double *part = part_.data();
+        const int64_t n = n_;
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (n >= kParMin)
+        for (int64_t blk = 0; blk < nb; blk++) {
+            const int64_t i0 = blk * kBlock, i1 = std::min(n, i0 + kBlock);
+            double s = 0.0;
+            for (int64_t i = i0; i < i1; i++) s += a[i] * b[i];
+            part[blk] = s;
+        }
         double s = 0.0;
-        for (int64_t i = 0; i < n_; i++) s += a[i] * b[i];
+        for (int64_t blk = 0; blk < nb; blk++) s += part[blk];
         return s;
     }
     double gnorm() const
@@ -194,6 +230,13 @@ private:
         double s = 0.0;
         for (int64_t i = 0; i < n_; i++) s = std::fmax(s, std::fabs(g_[i]));
         return s;
+    }
+    // y[i] = y[i] + c * x[i]  (element-wise: any partition over threads gives the same bits)
+    void axpy(double *y, const double c, const double *x) const
+    {
+        const int64_t n = n_;
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (n >= kParMin)
+        for (int64_t i = 0; i < n; i++) y[i] += c * x[i];
     }
     int finish(int status) { status_ = status; state_ = 2; return kDone; }
 
@@ -204,13 +247,13 @@ private:
         for (int k = col_ - 1; k >= 0; k--) {
             const int s = (head_ + k) % m_;
             alpha_[s] = rho_[s] * dot(&S_[(size_t)s * n_], q_.data());
-            for (int64_t i = 0; i < n_; i++) q_[i] -= alpha_[s] * Y_[(size_t)s * n_ + i];
+            axpy(q_.data(), -alpha_[s], &Y_[(size_t)s * n_]);
         }
         for (int64_t i = 0; i < n_; i++) q_[i] = q_[i] / theta_;
         for (int k = 0; k < col_; k++) {
             const int s = (head_ + k) % m_;
             const double beta = rho_[s] * dot(&Y_[(size_t)s * n_], q_.data());
-            for (int64_t i = 0; i < n_; i++) q_[i] += S_[(size_t)s * n_ + i] * (alpha_[s] - beta);
+            axpy(q_.data(), alpha_[s] - beta, &S_[(size_t)s * n_]);
         }
         for (int64_t i = 0; i < n_; i++) d_[i] = -q_[i];
         const double dnorm = std::sqrt(dot(d_.data(), d_.data()));
@@ -288,6 +331,7 @@ private:
     int m_, max_iter_, max_ls_, max_fun_;
     double factr_, pgtol_;
     std::vector<double> g_, d_, t_, r_, q_, S_, Y_, rho_, alpha_;
+    mutable std::vector<double> part_;   // block sums of dot()
     int col_ = 0, head_ = 0, iter_ = 0, nfev_ = 0, state_ = 0, status_ = 0;
     double theta_ = 1.0, f_ = 0.0, stp_ = 0.0, fold_ = 0.0, gd_ = 0.0, gdold_ = 0.0;
     int ifun_ = 0, iback_ = 0, lstask_ = LS_START;
