@@ -1284,11 +1284,9 @@ int gdmix_local_index_mark(const int64_t *ent_rowptr, int64_t n_entities, const 
     if (n_entities == 0) return GDMIX_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int32_t W32 = (num_features + 31) / 32;
-    // the last word of the prefix array doubles as the bad-column flag's home: keep it apart instead
-    unsigned *bad = nullptr;
-    CUDA_TRY(cudaMemsetAsync(bitmap, 0, (size_t)n_entities * W32 * 4, st));
-    CUDA_TRY(cudaMemsetAsync(d_e, 0, 8, st));
-    bad = (unsigned *)d_e;   // d_e[0] is overwritten by the count kernel after the flag has been read back
+    // bitmap has one word more than the entities need: the out-of-range flag
+    unsigned *bad = bitmap + (size_t)n_entities * W32;
+    CUDA_TRY(cudaMemsetAsync(bitmap, 0, ((size_t)n_entities * W32 + 1) * 4, st));
     if (n_rows > 0) {
         const int g = (int)std::min<int64_t>((n_rows + 255) / 256, 148 * 16);
         gdmix::bitmap_mark_kernel<<<g, 256, 0, st>>>(ent_rowptr, n_entities, rowptr, gcol, n_rows, num_features, W32, bitmap, bad);

@@ -131,7 +131,7 @@ def regroup_batch(entity, rowptr, gcol, val, label, offset=None, weight=None, ha
     if num_features and num_features <= BITMAP_MAX_FEATURES and E * w32 <= (1 << 28) and not FORCE_PAIR_SORT:
         # small feature bags: per-entity presence bitmaps instead of sorting (entity, feature) pairs
         ent_rowptr = ent_rowptr.contiguous()
-        bitmap = torch.empty(E * w32, dtype=torch.int32, device=dev)
+        bitmap = torch.empty(E * w32 + 1, dtype=torch.int32, device=dev)   # + the out-of-range flag
         wprefix = torch.empty(E * w32, dtype=torch.int32, device=dev)
         d_e = torch.empty(E, dtype=torch.int64, device=dev)
         check(lib.gdmix_local_index_mark(_tptr(ent_rowptr), C.c_int64(E), _tptr(rp), _tptr(gc), C.c_int64(n),

@@ -294,7 +294,8 @@ GDMIX_API int gdmix_auc(const float *score, const float *label, int64_t n, doubl
 /* Entity-local feature indexing (np.unique(cols, return_inverse=True) per entity, job_consumers.py:243) for feature
  * bags of at most a few thousand ids, by per-entity presence bitmaps instead of an (entity, feature) pair sort.
  * The batch is already grouped: entity e owns samples [ent_rowptr[e], ent_rowptr[e+1]).
- *   mark:   bitmap[E * W32] (W32 = ceil(num_features / 32)), word_prefix[E * W32], d_e[E] = distinct features per entity;
+ *   mark:   bitmap[E * W32 + 1] (W32 = ceil(num_features / 32); the last word is the call's out-of-range flag),
+ *           word_prefix[E * W32], d_e[E] = distinct features per entity;
  *           synchronises the stream once (ids outside [0, num_features) are an error)
  *   apply:  with uniq_ptr[E+1] = exclusive scan of d_e (the caller's), local_col[nnz] = rank of each non-zero's feature
  *           among its entity's distinct ids (may alias gcol), uniq_global[uniq_ptr[E]] = those ids, ascending */

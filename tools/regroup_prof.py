@@ -1,5 +1,7 @@
+#!/usr/bin/env python
+"""Where regroup_batch (group rows by entity + entity-local indexing) spends its time at the C3 per-user shape."""
 import sys, os, time
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gdmix_b200 import partition as P
 dev = torch.device("cuda", 0)
