@@ -173,7 +173,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("GDMIX_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version banner there at any debug level
+        os.environ.pop("NCCL_DEBUG", None)
+        if os.environ.get("GDMIX_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = os.environ["GDMIX_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
