@@ -417,23 +417,27 @@ int launch_giant_t(const gdmix::ReArgs &args, const RePlan &pl, cudaStream_t st)
     attr[0].val.clusterDim.x = kGiantCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    {
-        // sixteen CTAs per entity (non-portable cluster size) where a GPC holds such a cluster with this much shared memory
-        static std::atomic<int> cluster16{-1};
-        if (cluster16.load() < 0) {
-            int ok16 = 0;
-            if (cudaFuncSetAttribute(gdmix::re_solver_kernel<256, MT, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) ==
-                cudaSuccess) {
-                attr[0].val.clusterDim.x = 16;
-                int nclusters = 0;
-                if (cudaOccupancyMaxActiveClusters(&nclusters, gdmix::re_solver_kernel<256, MT, true>, &cfg) == cudaSuccess &&
-                    nclusters >= 4)
-                    ok16 = 1;
-            }
-            cudaGetLastError();
-            cluster16.store(ok16);
+    // sixteen CTAs per entity (non-portable cluster size) where a GPC holds such clusters with this launch's shared
+    // memory; asked per launch, because the shared memory per CTA follows the batch
+    static std::atomic<int> nonportable{-1};
+    if (nonportable.load() < 0) {
+        const bool ok = cudaFuncSetAttribute(gdmix::re_solver_kernel<256, MT, true>,
+                                             cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+        cudaGetLastError();
+        nonportable.store(ok ? 1 : 0);
+    }
+    if (nonportable.load() == 1) {
+        attr[0].val.clusterDim.x = 16;
+        int nclusters = 0;
+        const bool fits = cudaOccupancyMaxActiveClusters(&nclusters, gdmix::re_solver_kernel<256, MT, true>, &cfg) ==
+                              cudaSuccess && nclusters >= 4;
+        cudaGetLastError();
+        if (fits && cudaLaunchKernelEx(&cfg, gdmix::re_solver_kernel<256, MT, true>, args) == cudaSuccess) {
+            g_launches++;
+            return GDMIX_OK;
         }
-        attr[0].val.clusterDim.x = cluster16.load() ? 16 : kGiantCluster;
+        cudaGetLastError();   // fall back to the portable size
+        attr[0].val.clusterDim.x = kGiantCluster;
     }
     CUDA_TRY(cudaLaunchKernelEx(&cfg, gdmix::re_solver_kernel<256, MT, true>, args));
     g_launches++;
