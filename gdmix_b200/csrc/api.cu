@@ -250,7 +250,9 @@ int plan_fast(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo 
         if (b->n_rows > 0 && b->nnz > 0 && b->n_entities > 0 && !(env_tiers && atoi(env_tiers) == 1) &&
             o->threads_per_entity == 0) {
             const int64_t mean_rows = (b->n_rows + b->n_entities - 1) / b->n_entities;
-            const uint32_t N_typ = (uint32_t)std::min<int64_t>(N_full, ((5 * mean_rows + 1) / 2 + 31) & ~(int64_t)31);
+            const char *env_f = getenv("GDMIX_TYPICAL_HALVES");   // tuning hook: typical shape = this many halves of the mean
+            const int64_t halves = env_f ? std::max(2, atoi(env_f)) : 5;
+            const uint32_t N_typ = (uint32_t)std::min<int64_t>(N_full, ((halves * mean_rows + 1) / 2 + 31) & ~(int64_t)31);
             const int64_t nnz_per_row = (b->nnz + b->n_rows - 1) / b->n_rows;
             if ((int64_t)N_typ * 3 <= (int64_t)N_full * 2) {
                 FastShapePlan typ;
