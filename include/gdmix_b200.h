@@ -14,6 +14,8 @@
  *                        -> scipy.optimize.fmin_l_bfgs_b         (L-BFGS-B 3.0, un-vendored dependency)
  *                        + threshold_coefficients                util/model_utils.py:4-12
  *                        + _compute_variance (SIMPLE)            binary_logistic_regression.py:144-189
+ *   gdmix_re_fit_sweep   the same for several l2_reg_weight values at once (one training job per value in the
+ *                        reference: base_lr_params.py:19 via the workflow's hyper-parameter loop)
  *   gdmix_re_loss_grad   _loss / _gradient                       binary_logistic_regression.py:84-131
  *   gdmix_re_score       InferenceJobConsumer.__call__           job_consumers.py:138-152
  *                        -> predict_proba(return_logits=True)    binary_logistic_regression.py:241-262
@@ -21,6 +23,9 @@
  *                        (the all-reduce at :382-390 stays with the caller: NCCL on the same stream)
  *   gdmix_fe_score       _scoring_fn                             fixed_effect_lr_lbfgs_model.py:214-307
  *   gdmix_partition_ids  getPartitionIdUDF                       gdmix-data/.../utils/PartitionUtils.scala:31-37
+ *   gdmix_group_by_key, gdmix_csr_gather_rows, gdmix_local_index_*   groupBy(entity) + per-entity np.unique
+ *                        (DataPartitioner.scala:296-379, job_consumers.py:243) for chained coordinates on the device
+ *   gdmix_auc            Evaluator.calculateMetric("auc")         gdmix-data/.../evaluation/Evaluator.scala:29-45
  *
  * Conventions
  *   - All array pointers in gdmix_re_batch / gdmix_fe_rows are DEVICE pointers owned by
