@@ -81,3 +81,53 @@ def test_random_ragged_batches_match_the_oracle_on_every_path(seed, monkeypatch)
         same = (out["nit"] == nit_o) & (out["nfev"] == nfev_o)
         assert same[pinned].mean() >= 0.99, (path, seed, float(same[pinned].mean()))
         np.testing.assert_allclose(out["f"][pinned], f_o[pinned], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_ragged_batches_warm_start_variance_and_sweep(seed):
+    """The same kind of batch through the planner's cascade with the other outputs of the path: a warm start
+    (prepare_jobs builds theta0 from the previous model, job_consumers.py:262-288) retraces the oracle's warm
+    start; SIMPLE variances equal the oracle's; a regularisation sweep equals separate fits bit for bit."""
+    hb, opts = _random_batch(2000 + seed)
+    th_o, f_o, nit_o, nfev_o, st_o = _oracle(hb, opts)
+    norm = lambda a, b: np.array([np.linalg.norm(a[s:e] - b[s:e]) / max(np.linalg.norm(b[s:e]), 1e-300)
+                                  for s, e in zip(hb.theta_ptr[:-1], hb.theta_ptr[1:])])
+    th_p = _oracle(hb, opts, theta0=1e-13 * np.random.default_rng(seed).standard_normal(th_o.shape[0]))[0]
+    pinned = norm(th_p, th_o) < 1e-7
+    # warm start half way between zero and the optimum
+    theta0 = 0.5 * th_o
+    w_o = _oracle(hb, opts, theta0=theta0)
+    w_p = _oracle(hb, opts, theta0=theta0 * (1 + 1e-13))[0]
+    wpinned = pinned & (norm(w_p, w_o[0]) < 1e-7)
+    w_d = capi.re_fit_host(hb, opts, theta0=theta0)
+    assert (w_d["status"] == w_o[4]).all()
+    assert norm(w_d["theta"], w_o[0])[wpinned].max(initial=0.0) <= 1e-5
+    assert ((w_d["nit"] == w_o[2]) & (w_d["nfev"] == w_o[3]))[wpinned].mean() >= 0.99
+    # SIMPLE variance at the optimum
+    vopts = capi.make_opts(l2=opts.l2, regularize_bias=bool(opts.regularize_bias), has_intercept=bool(opts.has_intercept),
+                           m=opts.m, variance_mode=capi.VARIANCE_SIMPLE)
+    v_d = capi.re_fit_host(hb, vopts, want_variance=True)
+    oo = O.Opts(opts.l2, opts.regularize_bias, opts.has_intercept, opts.m, opts.max_iter, opts.max_ls, opts.max_fun,
+                opts.factr, opts.pgtol)
+    w_all = hb.weight if hb.weight is not None else np.ones(hb.n_rows, np.float32)
+    off_all = hb.offset if hb.offset is not None else np.zeros(hb.n_rows, np.float32)
+    hi = 1 if opts.has_intercept else 0
+    for e in np.flatnonzero(pinned)[::7]:
+        r0, r1 = hb.ent_rowptr[e], hb.ent_rowptr[e + 1]
+        q0, q1 = hb.rowptr[r0], hb.rowptr[r1]
+        t0, t1 = hb.theta_ptr[e], hb.theta_ptr[e + 1]
+        blk = O.EntityBlock(r1 - r0, t1 - t0 - hi, hb.rowptr[r0:r1 + 1] - q0, hb.col[q0:q1], hb.val[q0:q1],
+                            hb.label[r0:r1], w_all[r0:r1], off_all[r0:r1])
+        # (1 / a nearly vanishing sum of rho (1 - rho) when the entity is almost separable: 1e-6, not 1e-9)
+        np.testing.assert_allclose(v_d["variance"][t0:t1], O.re_variance(blk, oo, v_d["theta"][t0:t1], "simple"),
+                                   rtol=1e-6)
+    # sweep == separate fits, bit for bit
+    db = capi.DeviceBatch(hb)
+    l2s = [0.3, 3.0, 30.0]
+    sw = capi.re_fit_sweep_device(db, opts, l2s)
+    for j, l2 in enumerate(l2s):
+        o1 = capi.make_opts(l2=l2, regularize_bias=bool(opts.regularize_bias), has_intercept=bool(opts.has_intercept), m=opts.m)
+        one = capi.re_fit_device(db, o1)
+        torch.cuda.synchronize()
+        for key in ("theta", "f", "nit", "nfev", "status"):
+            assert torch.equal(sw[key][j], one[key]), (key, l2)
