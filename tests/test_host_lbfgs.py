@@ -52,3 +52,37 @@ def test_random_effect_golden_through_host_solver(c):
         assert (info["nit"], info["nfev"], info["status"]) == (c["nit"], c["nfev"], c["warnflag"])
         ref = RE_ARR[k + "_theta"]
         assert np.linalg.norm(x - ref) <= 1e-9 * max(np.linalg.norm(ref), 1e-300)
+
+
+def test_long_vectors_give_the_same_bits_for_any_number_of_host_threads():
+    """Above 32 768 coefficients the solver sweeps its vectors with several host threads; inner products are block
+    sums added in block order, so the trajectory must not depend on the thread count (ranks with different core
+    counts keep bit-identical state).  Each thread count runs in its own process (the count is read once)."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+from gdmix_b200 import _capi as capi
+n = 70001
+rng = np.random.default_rng(0)
+A = np.abs(rng.standard_normal(n)) + 0.5
+b = rng.standard_normal(n)
+h = capi.HostLbfgs(n, capi.make_opts(l2=0.0, max_iter=25))
+x = np.zeros(n)
+fg = lambda x: (0.5 * float((A * x * x).sum() - 2 * (b * x).sum()), A * x - b)
+f, g = fg(x)
+while h.iterate(x, f, g) == capi.HostLbfgs.NEED_FG:
+    f, g = fg(x)
+i = h.info()
+print(i["nit"], i["nfev"], x.tobytes().hex()[:64], repr(float(x.sum())))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for th in ("1", "3", "8"):
+        env = dict(os.environ, GDMIX_HOST_THREADS=th)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr[-500:]
+        outs.append(r.stdout.strip())
+    assert outs[0] == outs[1] == outs[2], outs
+    assert int(outs[0].split()[0]) > 5
