@@ -32,7 +32,17 @@ SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_w
            "gdmix_lbfgs_info", "gdmix_lbfgs_destroy", "gdmix_launch_count", "gdmix_re_last_plan",
            "gdmix_partition_workspace_size", "gdmix_sort_pairs_u64", "gdmix_group_by_key", "gdmix_csr_gather_rows",
            "gdmix_gather_f32", "gdmix_partition_ids_i64", "gdmix_auc", "gdmix_re_fit_sweep",
-           "gdmix_re_last_plan_typical", "gdmix_local_index_mark", "gdmix_local_index_apply"]
+           "gdmix_re_last_plan_typical", "gdmix_local_index_mark", "gdmix_local_index_apply",
+           "gdmix_seqex_count", "gdmix_seqex_fill"]
+
+
+class SeqexSpec(C.Structure):
+    _fields_ = [(n, C.c_char_p) for n in ("entity", "uid", "label", "offset", "weight", "bag_indices", "bag_values")]
+
+
+class SeqexSizes(C.Structure):
+    _fields_ = [("n_entities", C.c_int64), ("n_rows", C.c_int64), ("nnz", C.c_int64), ("id_bytes", C.c_int64),
+                ("all_labelled", C.c_int32), ("saw_weight", C.c_int32)]
 
 
 class GdmixError(RuntimeError):
@@ -517,3 +527,27 @@ class HostLbfgs:
             self.close()
         except Exception:
             pass
+
+
+def parse_entity_grouped(file_image, entity, uid, label, offset, weight, bag_indices, bag_values):
+    """One uncompressed TFRecord file image of entity-grouped SequenceExamples -> dict of flat numpy arrays
+    (gdmix_seqex_count + gdmix_seqex_fill; host code of the library, no device involved)."""
+    enc = lambda x: None if x is None else x.encode("utf-8")
+    spec = SeqexSpec(enc(entity), enc(uid), enc(label), enc(offset), enc(weight), enc(bag_indices), enc(bag_values))
+    buf = np.frombuffer(file_image, dtype=np.uint8)
+    sz = SeqexSizes()
+    check(lib.gdmix_seqex_count(_np_ptr(buf), C.c_int64(buf.size), C.byref(spec), C.byref(sz)))
+    E, N, Z = sz.n_entities, sz.n_rows, sz.nnz
+    out = {"ent_rows": np.zeros(E, np.int64), "row_len": np.zeros(N, np.int64), "gcol": np.zeros(Z, np.int64),
+           "val": np.zeros(Z, np.float32), "uid": np.zeros(N, np.int64), "label": np.zeros(N, np.float32),
+           "offset": np.zeros(N, np.float32), "weight": np.zeros(N, np.float32),
+           "id_chars": np.zeros(max(sz.id_bytes, 1), np.uint8), "id_ptr": np.zeros(E + 1, np.int64)}
+    check(lib.gdmix_seqex_fill(_np_ptr(buf), C.c_int64(buf.size), C.byref(spec), _np_ptr(out["ent_rows"]),
+                               _np_ptr(out["row_len"]), _np_ptr(out["gcol"]), _np_ptr(out["val"]), _np_ptr(out["uid"]),
+                               _np_ptr(out["label"]), _np_ptr(out["offset"]), _np_ptr(out["weight"]),
+                               _np_ptr(out["id_chars"]), _np_ptr(out["id_ptr"])))
+    raw = out["id_chars"].tobytes()
+    ip = out["id_ptr"]
+    out["entity_ids"] = [raw[ip[e]:ip[e + 1]].decode("utf-8") for e in range(E)]
+    out["all_labelled"], out["saw_weight"] = bool(sz.all_labelled), bool(sz.saw_weight)
+    return out

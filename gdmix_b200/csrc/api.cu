@@ -15,6 +15,7 @@
 #include "../../include/gdmix_b200.h"
 #include "aux_kernels.cuh"
 #include "host_lbfgs.h"
+#include "seqex_parser.h"
 #include "re_fast.cuh"
 #include "re_kernel.cuh"
 #include "re_variance.cuh"
@@ -1376,6 +1377,34 @@ int gdmix_auc(const float *score, const float *label, int64_t n, double *out3, v
     g_launches += 3;
     g_launches += 6;
     CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
+int gdmix_seqex_count(const uint8_t *file_image, int64_t len, const gdmix_seqex_spec *spec, gdmix_seqex_sizes *sizes)
+{
+    if (!spec || !sizes || (len > 0 && !file_image) || len < 0 || !spec->entity || !spec->uid || !spec->bag_indices ||
+        !spec->bag_values)
+        return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_seqex_count");
+    std::string err;
+    gdmix_host::SeqexReader r(*spec, err);
+    if (!r.run(file_image, len, *sizes, gdmix_host::SeqexOut())) return fail(GDMIX_ERR_INVALID, "%s", err.c_str());
+    return GDMIX_OK;
+}
+
+int gdmix_seqex_fill(const uint8_t *file_image, int64_t len, const gdmix_seqex_spec *spec, int64_t *ent_rows,
+                     int64_t *row_len, int64_t *gcol, float *val, int64_t *uid, float *label, float *offset,
+                     float *weight, char *id_chars, int64_t *id_ptr)
+{
+    if (!spec || (len > 0 && !file_image) || len < 0 || !ent_rows || !row_len || !gcol || !val || !uid || !label ||
+        !offset || !weight || !id_chars || !id_ptr)
+        return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_seqex_fill");
+    std::string err;
+    gdmix_host::SeqexReader r(*spec, err);
+    gdmix_host::SeqexOut o;
+    o.ent_rows = ent_rows; o.row_len = row_len; o.gcol = gcol; o.val = val; o.uid = uid; o.label = label;
+    o.offset = offset; o.weight = weight; o.id_chars = id_chars; o.id_ptr = id_ptr;
+    gdmix_seqex_sizes sz;
+    if (!r.run(file_image, len, sz, o)) return fail(GDMIX_ERR_INVALID, "%s", err.c_str());
     return GDMIX_OK;
 }
 

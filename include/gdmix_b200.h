@@ -312,6 +312,31 @@ GDMIX_API int gdmix_local_index_apply(const int64_t *ent_rowptr, int64_t n_entit
                                       const uint32_t *word_prefix, const int64_t *uniq_ptr, int32_t *local_col,
                                       int64_t *uniq_global, void *stream);
 
+/* Host-side reader of entity-grouped TFRecord files (no TensorFlow): one uncompressed file image -> the flat arrays
+ * of the random-effect ingest, i.e. what per_entity_grouped_input_fn + prepare_jobs build per entity in the reference
+ * (input_data_pipeline.py:244-273, job_consumers.py:161-258).  One record = one tf.train.SequenceExample = one entity:
+ * context holds the entity id (int64 or bytes, one value) and one list per sample column; feature_lists hold
+ * <bag>_indices (int64 list per sample) and <bag>_values (float list per sample).  Names are NUL-terminated strings;
+ * label / offset / weight may be NULL (column not wanted).  Two calls over the same buffer:
+ *   gdmix_seqex_count  -> sizes (entities, samples, non-zeros, bytes of all entity-id strings, flags)
+ *   gdmix_seqex_fill   -> ent_rows[E] samples per entity, row_len[N], gcol[nnz] GLOBAL feature ids, val[nnz],
+ *                         uid[N], label[N] (meaningful when sizes.all_labelled), offset[N] (0 when the column is
+ *                         absent), weight[N] (1 when absent), id_chars[id_bytes] + id_ptr[E+1] (entity ids as
+ *                         decimal / utf-8 strings, the modelId the trainer writes)
+ * Malformed input is an error (gdmix_last_error), never a silent skip.  Pure host code: no device is touched. */
+typedef struct gdmix_seqex_spec {
+    const char *entity, *uid, *label, *offset, *weight, *bag_indices, *bag_values;
+} gdmix_seqex_spec;
+typedef struct gdmix_seqex_sizes {
+    int64_t n_entities, n_rows, nnz, id_bytes;
+    int32_t all_labelled, saw_weight;
+} gdmix_seqex_sizes;
+GDMIX_API int gdmix_seqex_count(const uint8_t *file_image, int64_t len, const gdmix_seqex_spec *spec,
+                                gdmix_seqex_sizes *sizes);
+GDMIX_API int gdmix_seqex_fill(const uint8_t *file_image, int64_t len, const gdmix_seqex_spec *spec, int64_t *ent_rows,
+                               int64_t *row_len, int64_t *gcol, float *val, int64_t *uid, float *label, float *offset,
+                               float *weight, char *id_chars, int64_t *id_ptr);
+
 /* Replicated host-side solver state of the fixed-effect solve: L-BFGS-B without bounds, reverse
  * communication, the role scipy.optimize.fmin_l_bfgs_b plays at fixed_effect_lr_lbfgs_model.py:635-643.
  *   h = gdmix_lbfgs_create(n, opts)            (uses opts->m, max_iter, max_ls, max_fun, factr, pgtol)

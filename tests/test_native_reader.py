@@ -1,0 +1,164 @@
+"""The library's SequenceExample reader (gdmix_seqex_count / gdmix_seqex_fill, csrc/seqex_parser.h) against the
+pure-Python protobuf walk of gdmix_b200/io/tfrecord.py -- which tests/test_io_formats.py pins to files TensorFlow
+wrote -- on the reference's own fixture and on generated files: int64 / bytes entity ids, int64 / float labels,
+missing optional columns, empty samples, negative and large int64 values, packed and unpacked encodings, gzip."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from gdmix_b200 import _capi as capi, ingest
+from gdmix_b200.io import tfrecord as T
+
+FIX = os.path.join(os.path.dirname(__file__), "golden", "ref_fixtures")
+
+
+def _python_reader(files, **kw):
+    """read_entity_grouped's Python walk, reached by hiding the native path."""
+    saved = ingest._read_entity_grouped_native
+    ingest._read_entity_grouped_native = lambda *a, **k: None
+    try:
+        return ingest.read_entity_grouped(files, **kw)
+    finally:
+        ingest._read_entity_grouped_native = saved
+
+
+def _same(a, b):
+    assert a.entity_ids == b.entity_ids
+    for k in ("ent_rowptr", "rowptr", "gcol", "val", "uid", "offset", "weight"):
+        np.testing.assert_array_equal(getattr(a, k), getattr(b, k), err_msg=k)
+        assert getattr(a, k).dtype == getattr(b, k).dtype, k
+    assert (a.label is None) == (b.label is None)
+    if a.label is not None:
+        np.testing.assert_array_equal(a.label, b.label)
+    assert a.has_weight_column == b.has_weight_column and a.num_features == b.num_features
+
+
+class _Meta:
+    def __init__(self, names):
+        self.names = names
+
+    def get_feature_names(self):
+        return self.names
+
+
+def test_reference_fixture_matches_appendix_d():
+    kw = dict(metadata=_Meta(["memberId"]), entity_name="memberId", feature_bag="per_member", label_column="response",
+              offset_column="offset", weight_column="weight", uid_column="uid", num_features=100)
+    path = os.path.join(FIX, "re_data.tfrecord")
+    nat = ingest.read_entity_grouped(path, **kw)
+    _same(nat, _python_reader(path, **kw))
+    assert nat.entity_ids == ["100034", "100"]
+    np.testing.assert_array_equal(nat.gcol, [0, 7, 60, 80, 95, 34, 57, 10, 11])
+    np.testing.assert_array_equal(nat.uid, [10, 20, 23])
+    np.testing.assert_allclose(nat.val, np.array([1, 2, 3, 5, 6.6, 1, 2, -3.5, 2.3], np.float32))
+
+
+def _write(path, rng, n_ent, bytes_ids=False, float_label=False, with_label=True, with_weight=True, with_offset=True,
+           unpacked=False):
+    with T.TFRecordWriter(path) as w:
+        for e in range(n_ent):
+            n = int(rng.integers(1, 9))
+            ctx = {"ent": [("user-%d-é" % e).encode("utf-8")] if bytes_ids else [int(rng.integers(-5, 10**12))],
+                   "uid": [int(x) for x in rng.integers(-2**62, 2**62, n)]}
+            if with_label:
+                ctx["y"] = [float(x) for x in rng.integers(0, 2, n)] if float_label else [int(x) for x in rng.integers(0, 2, n)]
+            if with_weight:
+                ctx["w"] = [float(x) for x in rng.uniform(0.5, 2, n)]
+            if with_offset:
+                ctx["off"] = [float(x) for x in rng.standard_normal(n)]
+            lens = rng.integers(0, 6, n)
+            fl = {"bag_indices": [[int(x) for x in np.sort(rng.choice(5000, k, replace=False))] for k in lens],
+                  "bag_values": [[float(x) for x in rng.standard_normal(k)] for k in lens],
+                  "other_indices": [[1, 2]] * n}
+            payload = T.encode_sequence_example(ctx, fl)
+            w.write(_unpack(payload) if unpacked else payload)
+
+
+def _unpack(payload):
+    """Re-encodes every packed FloatList / Int64List of a SequenceExample element by element (both are legal)."""
+    def walk(buf, depth):
+        out = bytearray()
+        for fno, wt, v in T._fields(buf, 0, len(buf)):
+            if wt == 2:
+                sub = bytes(buf[v[0]:v[1]])
+                if depth == "feature" and fno in (2, 3):
+                    inner = bytearray()
+                    for f2, w2, v2 in T._fields(sub, 0, len(sub)):
+                        if f2 == 1 and w2 == 2:
+                            body = sub[v2[0]:v2[1]]
+                            if fno == 2:
+                                for i in range(0, len(body), 4):
+                                    inner += T._enc_varint((1 << 3) | 5) + body[i:i + 4]
+                            else:
+                                for x in T._packed_varints(body, 0, len(body)):
+                                    inner += T._enc_varint((1 << 3) | 0) + T._enc_varint(int(x))
+                    sub = bytes(inner)
+                elif depth in ("top", "features", "lists", "entry", "flist"):
+                    nxt = {"top": "features" if fno == 1 else "lists", "features": "entry", "lists": "entry",
+                           "entry": "feature" if fno == 2 else None, "flist": "feature"}[depth]
+                    if depth == "entry" and fno == 2 and _is_feature_list(sub):
+                        nxt = "flist"
+                    if nxt:
+                        sub = walk(sub, nxt)
+                out += T._enc_varint((fno << 3) | 2) + T._enc_varint(len(sub)) + sub
+            elif wt == 0:
+                out += T._enc_varint((fno << 3) | 0) + T._enc_varint(v)
+            elif wt == 5:
+                out += T._enc_varint((fno << 3) | 5) + struct.pack("<I", v)
+        return bytes(out)
+
+    def _is_feature_list(sub):
+        # a FeatureList holds repeated Feature messages in field 1; a Feature holds a list in fields 1..3: tell
+        # them apart by looking one level down (a Feature's payload never starts with another field-1 message
+        # whose own payload parses as a Feature -- good enough for the files this test writes)
+        try:
+            f = list(T._fields(sub, 0, len(sub)))
+            return bool(f) and all(fno == 1 and wt == 2 for fno, wt, _ in f) and \
+                all(k in ("bytes", "float", "int64", None) for k in (T._parse_feature(sub, a, b)[0] for _, _, (a, b) in f))
+        except Exception:
+            return False
+    return walk(payload, "top")
+
+
+@pytest.mark.parametrize("variant", [dict(), dict(bytes_ids=True), dict(float_label=True), dict(with_label=False),
+                                     dict(with_weight=False, with_offset=False), dict(unpacked=True)])
+@pytest.mark.parametrize("suffix", [".tfrecord", ".tfrecord.gz"])
+def test_generated_files_match_the_python_reader(tmp_path, variant, suffix):
+    rng = np.random.default_rng(len(str(variant)))
+    for part in range(2):
+        _write(str(tmp_path / f"part-{part:05d}{suffix}"), rng, 40, **variant)
+    kw = dict(metadata=_Meta(["ent"]), entity_name="ent", feature_bag="bag", label_column="y", offset_column="off",
+              weight_column="w", uid_column="uid", num_features=5000)
+    nat = ingest.read_entity_grouped(str(tmp_path), **kw)
+    assert nat.n_entities == 80
+    _same(nat, _python_reader(str(tmp_path), **kw))
+
+
+def test_malformed_files_raise(tmp_path):
+    rng = np.random.default_rng(1)
+    good = str(tmp_path / "a.tfrecord")
+    _write(good, rng, 5)
+    img = T._read_all(good)
+    spec = ("ent", "uid", "y", "off", "w", "bag_indices", "bag_values")
+    capi.parse_entity_grouped(img, *spec)
+    with pytest.raises(capi.GdmixError):
+        capi.parse_entity_grouped(img[:-7], *spec)                     # truncated last record
+    with pytest.raises(capi.GdmixError):
+        capi.parse_entity_grouped(img, "nope", *spec[1:])              # entity column missing
+    with pytest.raises(capi.GdmixError):
+        capi.parse_entity_grouped(img, "ent", "uid", "y", "off", "w", "bag_indices", "other_indices")   # not floats
+    # a sample column shorter than uid
+    bad = str(tmp_path / "b.tfrecord")
+    with T.TFRecordWriter(bad) as w:
+        w.write(T.encode_sequence_example({"ent": [1], "uid": [1, 2, 3], "off": [0.5]},
+                                          {"bag_indices": [[1], [2], [3]], "bag_values": [[1.0], [2.0], [3.0]]}))
+    with pytest.raises(capi.GdmixError):
+        capi.parse_entity_grouped(T._read_all(bad), *spec)
+    # fewer index lists than samples
+    bad2 = str(tmp_path / "c.tfrecord")
+    with T.TFRecordWriter(bad2) as w:
+        w.write(T.encode_sequence_example({"ent": [1], "uid": [1, 2]}, {"bag_indices": [[1]], "bag_values": [[1.0]]}))
+    with pytest.raises(capi.GdmixError):
+        capi.parse_entity_grouped(T._read_all(bad2), *spec)
