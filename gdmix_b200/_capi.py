@@ -33,7 +33,7 @@ SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_w
            "gdmix_partition_workspace_size", "gdmix_sort_pairs_u64", "gdmix_group_by_key", "gdmix_csr_gather_rows",
            "gdmix_gather_f32", "gdmix_partition_ids_i64", "gdmix_auc", "gdmix_re_fit_sweep",
            "gdmix_re_last_plan_typical", "gdmix_local_index_mark", "gdmix_local_index_apply",
-           "gdmix_seqex_count", "gdmix_seqex_fill"]
+           "gdmix_seqex_count", "gdmix_seqex_fill", "gdmix_example_count", "gdmix_example_fill"]
 
 
 class SeqexSpec(C.Structure):
@@ -550,4 +550,26 @@ def parse_entity_grouped(file_image, entity, uid, label, offset, weight, bag_ind
     ip = out["id_ptr"]
     out["entity_ids"] = [raw[ip[e]:ip[e + 1]].decode("utf-8") for e in range(E)]
     out["all_labelled"], out["saw_weight"] = bool(sz.all_labelled), bool(sz.saw_weight)
+    return out
+
+
+def parse_per_record(file_image, uid, label, offset, weight, bag_indices, bag_values):
+    """One uncompressed TFRecord file image of tf.train.Example rows -> dict of flat numpy arrays
+    (gdmix_example_count + gdmix_example_fill; host code of the library)."""
+    enc = lambda x: None if x is None else x.encode("utf-8")
+    spec = SeqexSpec(None, enc(uid), enc(label), enc(offset), enc(weight), enc(bag_indices), enc(bag_values))
+    buf = np.frombuffer(file_image, dtype=np.uint8)
+    sz = SeqexSizes()
+    check(lib.gdmix_example_count(_np_ptr(buf), C.c_int64(buf.size), C.byref(spec), C.byref(sz)))
+    N, Z = sz.n_rows, sz.nnz
+    out = {"row_len": np.zeros(N, np.int64), "col": np.zeros(max(Z, 1), np.int32)[:Z], "val": np.zeros(max(Z, 1), np.float32)[:Z],
+           "uid": np.zeros(N, np.int64), "label": np.zeros(N, np.float32), "offset": np.zeros(N, np.float32),
+           "weight": np.zeros(N, np.float32)}
+    colbuf, valbuf = np.zeros(max(Z, 1), np.int32), np.zeros(max(Z, 1), np.float32)
+    rl = np.zeros(max(N, 1), np.int64); u = np.zeros(max(N, 1), np.int64)
+    lab, off, w = (np.zeros(max(N, 1), np.float32) for _ in range(3))
+    check(lib.gdmix_example_fill(_np_ptr(buf), C.c_int64(buf.size), C.byref(spec), _np_ptr(rl), _np_ptr(colbuf),
+                                 _np_ptr(valbuf), _np_ptr(u), _np_ptr(lab), _np_ptr(off), _np_ptr(w)))
+    out = {"row_len": rl[:N], "col": colbuf[:Z], "val": valbuf[:Z], "uid": u[:N], "label": lab[:N], "offset": off[:N],
+           "weight": w[:N], "saw_weight": bool(sz.saw_weight)}
     return out

@@ -1408,6 +1408,30 @@ int gdmix_seqex_fill(const uint8_t *file_image, int64_t len, const gdmix_seqex_s
     return GDMIX_OK;
 }
 
+int gdmix_example_count(const uint8_t *file_image, int64_t len, const gdmix_seqex_spec *spec, gdmix_seqex_sizes *sizes)
+{
+    if (!spec || !sizes || (len > 0 && !file_image) || len < 0 || (!spec->bag_indices != !spec->bag_values))
+        return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_example_count");
+    std::string err;
+    gdmix_host::ExampleReader r(*spec, err);
+    if (!r.run(file_image, len, *sizes, gdmix_host::ExampleOut())) return fail(GDMIX_ERR_INVALID, "%s", err.c_str());
+    return GDMIX_OK;
+}
+
+int gdmix_example_fill(const uint8_t *file_image, int64_t len, const gdmix_seqex_spec *spec, int64_t *row_len,
+                       int32_t *col, float *val, int64_t *uid, float *label, float *offset, float *weight)
+{
+    if (!spec || (len > 0 && !file_image) || len < 0 || !row_len || !col || !val || !uid || !label || !offset || !weight)
+        return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_example_fill");
+    std::string err;
+    gdmix_host::ExampleReader r(*spec, err);
+    gdmix_host::ExampleOut o;
+    o.row_len = row_len; o.col = col; o.val = val; o.uid = uid; o.label = label; o.offset = offset; o.weight = weight;
+    gdmix_seqex_sizes sz;
+    if (!r.run(file_image, len, sz, o)) return fail(GDMIX_ERR_INVALID, "%s", err.c_str());
+    return GDMIX_OK;
+}
+
 void gdmix_host_release(void)
 {
     std::lock_guard<std::mutex> lk(g_host.mu);

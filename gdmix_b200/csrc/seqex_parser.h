@@ -322,4 +322,135 @@ private:
     std::string &err_;
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// Fixed-effect input: one tf.train.Example per row (per_record_input_fn, input_data_pipeline.py:223-243): the bag's
+// indices / values as two lists of the features map, and scalar uid / label / offset / weight columns.
+// ---------------------------------------------------------------------------------------------------------
+struct ExampleOut {   // null pointers: counting pass
+    int64_t *row_len = nullptr, *uid = nullptr;
+    int32_t *col = nullptr;
+    float *val = nullptr, *label = nullptr, *offset = nullptr, *weight = nullptr;
+};
+
+class ExampleReader {
+public:
+    ExampleReader(const gdmix_seqex_spec &spec, std::string &err) : spec_(spec), err_(err) {}
+
+    bool run(const uint8_t *buf, int64_t len, gdmix_seqex_sizes &sz, const ExampleOut &o)
+    {
+        memset(&sz, 0, sizeof(sz));
+        sz.all_labelled = 1;
+        const uint8_t *p = buf, *end = buf + len;
+        while (p < end) {
+            if (end - p < 12) return fail("truncated TFRecord header at byte %lld", (long long)(p - buf));
+            uint64_t n; memcpy(&n, p, 8);
+            if (n > (uint64_t)(end - p - 12) || (uint64_t)(end - p - 12) - n < 4)
+                return fail("truncated TFRecord payload at byte %lld", (long long)(p - buf));
+            if (!record(Span{p + 12, p + 12 + n}, sz, o)) return false;
+            p += 12 + n + 4;
+        }
+        return true;
+    }
+
+private:
+    bool fail(const char *fmt, long long a = 0, long long b = 0)
+    {
+        char tmp[256];
+        snprintf(tmp, sizeof(tmp), fmt, a, b);
+        err_ = tmp;
+        return false;
+    }
+    static bool name_is(Span key, const char *name)
+    {
+        if (!name) return false;
+        const size_t n = strlen(name);
+        return (size_t)(key.e - key.p) == n && memcmp(key.p, name, n) == 0;
+    }
+    // first element of a numeric list as double; false when the column is absent or empty
+    static bool first_number(bool present, Span f, double &out, bool &malformed)
+    {
+        if (!present) return false;
+        Kind k; Span l;
+        if (!feature_kind(f, k, l)) { malformed = true; return false; }
+        bool got = false;
+        if (k == kFloat) { if (!each_float(l, [&](float v) { if (!got) { out = (double)v; got = true; } })) malformed = true; }
+        else if (k == kInt64) { if (!each_int64(l, [&](int64_t v) { if (!got) { out = (double)v; got = true; } })) malformed = true; }
+        else if (k == kBytes) malformed = true;
+        return got;
+    }
+
+    bool record(Span rec, gdmix_seqex_sizes &sz, const ExampleOut &o)
+    {
+        const int64_t row = sz.n_rows;
+        Span features{nullptr, nullptr};
+        uint32_t fno, wt; uint64_t sc; Span sub;
+        while (!rec.empty()) {
+            if (!rd_field(rec, fno, wt, sc, sub)) return fail("row %lld: malformed Example", row);
+            if (wt == 2 && fno == 1) { features = sub; break; }
+        }
+        Span f_idx{nullptr, nullptr}, f_val = f_idx, f_uid = f_idx, f_label = f_idx, f_off = f_idx, f_w = f_idx;
+        bool h_idx = false, h_val = false, h_uid = false, h_label = false, h_off = false, h_w = false;
+        Span c = features;
+        while (!c.empty()) {
+            if (!rd_field(c, fno, wt, sc, sub)) return fail("row %lld: malformed features map", row);
+            if (fno != 1 || wt != 2) continue;
+            Span key{nullptr, nullptr}, val{nullptr, nullptr};
+            Span entry = sub;
+            while (!entry.empty()) {
+                uint32_t f2, w2; uint64_t s2; Span sub2;
+                if (!rd_field(entry, f2, w2, s2, sub2)) return fail("row %lld: malformed features entry", row);
+                if (w2 == 2 && f2 == 1) key = sub2;
+                else if (w2 == 2 && f2 == 2) val = sub2;
+            }
+            if (name_is(key, spec_.bag_indices)) { f_idx = val; h_idx = true; }
+            else if (name_is(key, spec_.bag_values)) { f_val = val; h_val = true; }
+            else if (name_is(key, spec_.uid)) { f_uid = val; h_uid = true; }
+            else if (name_is(key, spec_.label)) { f_label = val; h_label = true; }
+            else if (name_is(key, spec_.offset)) { f_off = val; h_off = true; }
+            else if (name_is(key, spec_.weight)) { f_w = val; h_w = true; }
+        }
+        int64_t ni = 0, nv = 0;
+        if (spec_.bag_indices) {
+            Kind ka = kNone, kb = kNone; Span la{nullptr, nullptr}, lb{nullptr, nullptr};
+            if (h_idx && !feature_kind(f_idx, ka, la)) return fail("row %lld: malformed index feature", row);
+            if (h_val && !feature_kind(f_val, kb, lb)) return fail("row %lld: malformed value feature", row);
+            if (ka != kInt64 && ka != kNone) { if (count_elems(ka, la) != 0) return fail("row %lld: feature indices must be an int64 list", row); la = Span{nullptr, nullptr}; }
+            if (kb != kFloat && kb != kNone) { if (count_elems(kb, lb) != 0) return fail("row %lld: feature values must be a float list", row); lb = Span{nullptr, nullptr}; }
+            const int64_t q0 = sz.nnz;
+            bool range_ok = true;
+            if (!each_int64(la, [&](int64_t v) { if (v < 0 || v > 0x7fffffffLL) range_ok = false; if (o.col) o.col[q0 + ni] = (int32_t)v; ni++; }))
+                return fail("row %lld: malformed index list", row);
+            if (!range_ok) return fail("row %lld: feature index outside int32", row);
+            if (!each_float(lb, [&](float v) { if (o.val && nv < ni) o.val[q0 + nv] = v; nv++; }))
+                return fail("row %lld: malformed value list", row);
+            if (ni != nv) return fail("row %lld: indices / values length mismatch (%lld indices)", row, ni);
+            sz.nnz += ni;
+        }
+        if (o.row_len) o.row_len[row] = ni;
+        bool bad = false;
+        double v;
+        const bool g_uid = first_number(h_uid, f_uid, v, bad);
+        if (o.uid) o.uid[row] = g_uid ? (int64_t)v : 0;
+        if (g_uid && o.uid) {   // uids are int64: take the exact value, not its double
+            Kind k; Span l; feature_kind(f_uid, k, l);
+            if (k == kInt64) { bool got = false; each_int64(l, [&](int64_t x) { if (!got) { o.uid[row] = x; got = true; } }); }
+        }
+        const bool g_label = first_number(h_label, f_label, v, bad);
+        if (o.label) { if (g_label) o.label[row] = (float)v; else { const uint32_t nanbits = 0x7fc00000u; memcpy(&o.label[row], &nanbits, 4); } }
+        if (!g_label) sz.all_labelled = 0;
+        const bool g_off = first_number(h_off, f_off, v, bad);
+        if (o.offset) o.offset[row] = g_off ? (float)v : 0.0f;
+        const bool g_w = first_number(h_w, f_w, v, bad);
+        if (o.weight) o.weight[row] = g_w ? (float)v : 1.0f;
+        if (h_w) sz.saw_weight = 1;
+        if (bad) return fail("row %lld: malformed scalar column", row);
+        sz.n_rows++;
+        sz.n_entities = sz.n_rows;
+        return true;
+    }
+
+    const gdmix_seqex_spec &spec_;
+    std::string &err_;
+};
+
 }  // namespace gdmix_host

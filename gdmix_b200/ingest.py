@@ -257,9 +257,36 @@ class RecordData:
         return len(self.rowptr) - 1
 
 
+USE_NATIVE_READER = True   # tests flip it to compare the library's reader with the Python walk below
+
+
+def _read_per_record_native(files, feature_bag, label_column, offset_column, weight_column, uid_column):
+    """The library's tf.train.Example reader (gdmix_example_count / _fill), same arrays as the Python walk."""
+    from . import _capi as capi
+    parts = []
+    for fn in files:
+        try:
+            parts.append(capi.parse_per_record(tfrecord._read_all(fn), uid_column, label_column, offset_column,
+                                               weight_column,
+                                               None if feature_bag is None else feature_bag + INDICES_SUFFIX,
+                                               None if feature_bag is None else feature_bag + VALUES_SUFFIX))
+        except capi.GdmixError as ex:
+            raise ValueError(f"{fn}: {ex}") from None
+    cat = lambda key, dt: (np.concatenate([p[key] for p in parts]).astype(dt) if parts else np.zeros(0, dt))
+    d = RecordData()
+    d.rowptr = np.concatenate([[0], np.cumsum(cat("row_len", np.int64))]).astype(np.int64)
+    d.col, d.val = cat("col", np.int32), cat("val", np.float32)
+    d.uid, d.label = cat("uid", np.int64), cat("label", np.float32)
+    d.offset, d.weight = cat("offset", np.float32), cat("weight", np.float32)
+    d.has_weight_column = any(p["saw_weight"] for p in parts)
+    return d
+
+
 def read_per_record(input_path_or_files, feature_bag, label_column, offset_column, weight_column, uid_column,
                     num_shards=1, shard_index=0):
     files = list_tfrecord_files(input_path_or_files, num_shards, shard_index)
+    if USE_NATIVE_READER:
+        return _read_per_record_native(files, feature_bag, label_column, offset_column, weight_column, uid_column)
     row_len, cols, vals, labels, weights, offsets, uids = [], [], [], [], [], [], []
     saw_weight = False
     for fn in files:

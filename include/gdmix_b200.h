@@ -337,6 +337,15 @@ GDMIX_API int gdmix_seqex_fill(const uint8_t *file_image, int64_t len, const gdm
                                int64_t *row_len, int64_t *gcol, float *val, int64_t *uid, float *label, float *offset,
                                float *weight, char *id_chars, int64_t *id_ptr);
 
+/* The same for the fixed effect's input, one tf.train.Example per row (per_record_input_fn,
+ * input_data_pipeline.py:223-243): spec->bag_indices / bag_values name two lists of the features map (NULL:
+ * intercept-only rows), uid / label / offset / weight scalar columns (first element; absent: 0 / NaN / 0 / 1);
+ * spec->entity is ignored.  sizes.n_rows rows, sizes.nnz non-zeros. */
+GDMIX_API int gdmix_example_count(const uint8_t *file_image, int64_t len, const gdmix_seqex_spec *spec,
+                                  gdmix_seqex_sizes *sizes);
+GDMIX_API int gdmix_example_fill(const uint8_t *file_image, int64_t len, const gdmix_seqex_spec *spec, int64_t *row_len,
+                                 int32_t *col, float *val, int64_t *uid, float *label, float *offset, float *weight);
+
 /* Replicated host-side solver state of the fixed-effect solve: L-BFGS-B without bounds, reverse
  * communication, the role scipy.optimize.fmin_l_bfgs_b plays at fixed_effect_lr_lbfgs_model.py:635-643.
  *   h = gdmix_lbfgs_create(n, opts)            (uses opts->m, max_iter, max_ls, max_fun, factr, pgtol)

@@ -162,3 +162,53 @@ def test_malformed_files_raise(tmp_path):
         w.write(T.encode_sequence_example({"ent": [1], "uid": [1, 2]}, {"bag_indices": [[1]], "bag_values": [[1.0]]}))
     with pytest.raises(capi.GdmixError):
         capi.parse_entity_grouped(T._read_all(bad2), *spec)
+
+
+def _records_equal(a, b):
+    for k in ("rowptr", "col", "val", "uid", "offset", "weight"):
+        np.testing.assert_array_equal(getattr(a, k), getattr(b, k), err_msg=k)
+        assert getattr(a, k).dtype == getattr(b, k).dtype, k
+    np.testing.assert_array_equal(a.label, b.label)        # NaN where a row has no label, in both
+    assert a.has_weight_column == b.has_weight_column
+
+
+def _per_record(files, native, **kw):
+    saved = ingest.USE_NATIVE_READER
+    ingest.USE_NATIVE_READER = native
+    try:
+        return ingest.read_per_record(files, **kw)
+    finally:
+        ingest.USE_NATIVE_READER = saved
+
+
+def test_fixed_effect_fixture_rows_match_the_python_reader():
+    kw = dict(feature_bag="global", label_column="response", offset_column="offset", weight_column="weight",
+              uid_column="uid")
+    path = os.path.join(FIX, "fe_test.tfrecord")
+    nat = _per_record(path, True, **kw)
+    assert nat.n_rows > 0 and nat.col.size > 0
+    _records_equal(nat, _per_record(path, False, **kw))
+
+
+@pytest.mark.parametrize("variant", ["full", "no_bag", "missing_columns", "float_label"])
+def test_generated_example_files_match_the_python_reader(tmp_path, variant):
+    rng = np.random.default_rng(7)
+    path = str(tmp_path / "rows.tfrecord.gz")
+    with T.TFRecordWriter(path) as w:
+        for i in range(300):
+            k = int(rng.integers(0, 7))
+            ex = {"uid": [int(rng.integers(-2**60, 2**60))]}
+            if variant != "no_bag":
+                ex["g_indices"] = [int(x) for x in np.sort(rng.choice(100000, k, replace=False))]
+                ex["g_values"] = [float(x) for x in rng.standard_normal(k)]
+            if not (variant == "missing_columns" and i % 3 == 0):
+                ex["y"] = [float(rng.integers(0, 2))] if variant == "float_label" else [int(rng.integers(0, 2))]
+                ex["w"] = [float(rng.uniform(0.5, 2))]
+            if variant != "missing_columns":
+                ex["off"] = [float(rng.standard_normal())]
+            w.write(T.encode_example(ex))
+    kw = dict(feature_bag=None if variant == "no_bag" else "g", label_column="y", offset_column="off",
+              weight_column="w", uid_column="uid")
+    nat = _per_record(path, True, **kw)
+    assert nat.n_rows == 300
+    _records_equal(nat, _per_record(path, False, **kw))
