@@ -33,7 +33,7 @@ SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_w
            "gdmix_partition_workspace_size", "gdmix_sort_pairs_u64", "gdmix_group_by_key", "gdmix_csr_gather_rows",
            "gdmix_gather_f32", "gdmix_partition_ids_i64", "gdmix_auc", "gdmix_re_fit_sweep",
            "gdmix_re_last_plan_typical", "gdmix_local_index_mark", "gdmix_local_index_apply",
-           "gdmix_seqex_count", "gdmix_seqex_fill", "gdmix_example_count", "gdmix_example_fill"]
+           "gdmix_seqex_count", "gdmix_seqex_fill", "gdmix_example_count", "gdmix_example_fill", "gdmix_avro_score_blocks"]
 
 
 class SeqexSpec(C.Structure):
@@ -573,3 +573,20 @@ def parse_per_record(file_image, uid, label, offset, weight, bag_indices, bag_va
     out = {"row_len": rl[:N], "col": colbuf[:Z], "val": valbuf[:Z], "uid": u[:N], "label": lab[:N], "offset": off[:N],
            "weight": w[:N], "saw_weight": bool(sz.saw_weight)}
     return out
+
+
+def avro_score_blocks(uid, score, label, weight, per_coordinate, sync, records_per_block=1024):
+    """-> bytes: the blocks of an Avro container holding these score records (gdmix_avro_score_blocks)."""
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+    uid = np.ascontiguousarray(uid, dtype=np.int64)
+    score, label, weight, per_coordinate = f32(score), f32(label), f32(weight), f32(per_coordinate)
+    n = int(uid.shape[0])
+    blocks = (n + records_per_block - 1) // records_per_block
+    out = np.empty(max(n * 31 + blocks * 36, 1), np.uint8)
+    written = C.c_int64()
+    sync_arr = np.frombuffer(bytes(sync), dtype=np.uint8)
+    assert sync_arr.size == 16
+    check(lib.gdmix_avro_score_blocks(_np_ptr(uid), _np_ptr(score), _np_ptr(label), _np_ptr(weight),
+                                      _np_ptr(per_coordinate), C.c_int64(n), C.c_int32(records_per_block),
+                                      _np_ptr(sync_arr), _np_ptr(out), C.c_int64(out.size), C.byref(written)))
+    return out[:written.value].tobytes()

@@ -16,6 +16,7 @@
 #include "aux_kernels.cuh"
 #include "host_lbfgs.h"
 #include "seqex_parser.h"
+#include "avro_writer.h"
 #include "re_fast.cuh"
 #include "re_kernel.cuh"
 #include "re_variance.cuh"
@@ -1429,6 +1430,19 @@ int gdmix_example_fill(const uint8_t *file_image, int64_t len, const gdmix_seqex
     o.row_len = row_len; o.col = col; o.val = val; o.uid = uid; o.label = label; o.offset = offset; o.weight = weight;
     gdmix_seqex_sizes sz;
     if (!r.run(file_image, len, sz, o)) return fail(GDMIX_ERR_INVALID, "%s", err.c_str());
+    return GDMIX_OK;
+}
+
+int gdmix_avro_score_blocks(const int64_t *uid, const float *score, const float *label, const float *weight,
+                            const float *per_coordinate, int64_t n, int32_t records_per_block, const uint8_t *sync16,
+                            uint8_t *out, int64_t capacity, int64_t *written)
+{
+    if (n < 0 || records_per_block <= 0 || !sync16 || !written || (n > 0 && (!uid || !score || !out)))
+        return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_avro_score_blocks");
+    if (capacity < gdmix_host::avro_score_blocks_bound(n, records_per_block))
+        return fail(GDMIX_ERR_WORKSPACE, "output buffer %lld B < bound %lld B", (long long)capacity,
+                    (long long)gdmix_host::avro_score_blocks_bound(n, records_per_block));
+    *written = gdmix_host::avro_score_blocks(uid, score, label, weight, per_coordinate, n, records_per_block, sync16, out);
     return GDMIX_OK;
 }
 

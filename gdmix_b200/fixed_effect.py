@@ -203,18 +203,11 @@ class FixedEffectLRModelLBFGS(Model):
         has_label = self._has_label(sp.label_column_name)
         has_weight = self._has_feature(sp.weight_column_name)
 
-        def records():
-            for i in range(data.n_rows):
-                rec = {sp.uid_column_name: int(data.uid[i]), sp.prediction_score_column_name: float(logit[i]),
-                       sp.prediction_score_per_coordinate_column_name: float(per_coordinate[i])}
-                if has_label:
-                    rec[sp.label_column_name] = float(data.label[i])
-                if has_weight:
-                    rec[sp.weight_column_name] = int(data.weight[i])  # the reference truncates here (:426)
-                yield rec
-
         os.makedirs(output_dir, exist_ok=True)
-        model_io.batched_write_avro(records(), os.path.join(output_dir, f"part-{task_index:05d}.avro"), schema)
+        # the reference writes int(weight) here (:426): the truncation is kept
+        model_io.write_scores(os.path.join(output_dir, f"part-{task_index:05d}.avro"), schema, sp, data.uid, logit,
+                              per_coordinate, label=data.label if has_label else None,
+                              weight=np.trunc(data.weight))   # used only if the schema has the field
 
     # ---- model files (:690-750) -----------------------------------------------------------------------------------
     def _save_model(self):

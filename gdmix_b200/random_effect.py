@@ -192,17 +192,8 @@ class RandomEffectLRLBFGSModel(Model):
             logit = per_coordinate = np.zeros(0, np.float32)
         sp = schema_params
 
-        def records():
-            lab = data.label
-            for i in range(data.n_rows):
-                rec = {sp.prediction_score_column_name: float(logit[i]), sp.weight_column_name: float(data.weight[i]),
-                       sp.uid_column_name: int(data.uid[i]),
-                       sp.prediction_score_per_coordinate_column_name: float(per_coordinate[i])}
-                if lab is not None:
-                    rec[sp.label_column_name] = float(lab[i])
-                yield rec
-
-        model_io.batched_write_avro(records(), output_file, schema)
+        model_io.write_scores(output_file, schema, sp, data.uid, logit, per_coordinate, label=data.label,
+                              weight=data.weight)
         logger.info(f"Inference complete: {input_path}.")
 
     # ---- model files (random_effect_lr_lbfgs_model.py:219-309) ---------------------------------------------

@@ -348,6 +348,16 @@ GDMIX_API int gdmix_example_count(const uint8_t *file_image, int64_t len, const 
 GDMIX_API int gdmix_example_fill(const uint8_t *file_image, int64_t len, const gdmix_seqex_spec *spec, int64_t *row_len,
                                  int32_t *col, float *val, int64_t *uid, float *label, float *offset, float *weight);
 
+/* Avro encoding of the score records both trainers write (`validation_result`, util/io_utils.py:367-375, appended in
+ * blocks of 1024 by batched_write_avro :299-334): the BODY of an object-container file -- per block <count> <size>
+ * <records> <sync> -- for n records with fields uid (long), predictionScore (float), label ([null, float]; label ==
+ * NULL writes the null branch), weight (float; NULL: the schema has no such field), predictionScorePerCoordinate
+ * (float; NULL likewise).  The caller writes the container header (magic, schema, codec "null", sync) in front.
+ * capacity >= n * 31 + blocks * 36.  Host code. */
+GDMIX_API int gdmix_avro_score_blocks(const int64_t *uid, const float *score, const float *label, const float *weight,
+                                      const float *per_coordinate, int64_t n, int32_t records_per_block,
+                                      const uint8_t *sync16, uint8_t *out, int64_t capacity, int64_t *written);
+
 /* Replicated host-side solver state of the fixed-effect solve: L-BFGS-B without bounds, reverse
  * communication, the role scipy.optimize.fmin_l_bfgs_b plays at fixed_effect_lr_lbfgs_model.py:635-643.
  *   h = gdmix_lbfgs_create(n, opts)            (uses opts->m, max_iter, max_ls, max_fun, factr, pgtol)

@@ -212,3 +212,49 @@ def test_generated_example_files_match_the_python_reader(tmp_path, variant):
     nat = _per_record(path, True, **kw)
     assert nat.n_rows == 300
     _records_equal(nat, _per_record(path, False, **kw))
+
+
+@pytest.mark.parametrize("with_label", [True, False])
+@pytest.mark.parametrize("with_weight", [True, False])
+@pytest.mark.parametrize("n", [0, 1, 1024, 2500])
+def test_native_score_writer_is_byte_identical_to_the_python_writer(tmp_path, with_label, with_weight, n):
+    """model_io.write_scores (gdmix_avro_score_blocks) against avro.write_records one dict at a time, same sync
+    marker: the files must be equal byte for byte, and decode to the columns that went in."""
+    from types import SimpleNamespace
+    from gdmix_b200.io import avro, model_io
+    sp = SimpleNamespace(uid_column_name="uid", prediction_score_column_name="predictionScore",
+                         label_column_name="label", weight_column_name="weight",
+                         prediction_score_per_coordinate_column_name="predictionScorePerCoordinate")
+    schema = model_io.get_inference_output_avro_schema({}, True, sp, has_weight=with_weight)
+    rng = np.random.default_rng(n + 7)
+    uid = rng.integers(-2**62, 2**62, n).astype(np.int64)
+    if n:
+        uid[0] = 0
+    score, pc = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    label = rng.integers(0, 2, n).astype(np.float32) if with_label else None
+    weight = rng.uniform(0.5, 2, n).astype(np.float32)
+    sync = bytes(range(16))
+    a, b = str(tmp_path / "native.avro"), str(tmp_path / "python.avro")
+    assert model_io.write_scores(a, schema, sp, uid, score, pc, label=label, weight=weight, sync=sync) == n
+
+    def records():
+        for i in range(n):
+            r = {"uid": int(uid[i]), "predictionScore": float(score[i]), "predictionScorePerCoordinate": float(pc[i]),
+                 "weight": float(weight[i])}
+            if with_label:
+                r["label"] = float(label[i])
+            yield r
+    with avro.Writer(b, schema, "null", sync=sync) as w:
+        batch = []
+        for r in records():
+            batch.append(r)
+            if len(batch) == 1024:
+                w.write_block(batch); batch = []
+        w.write_block(batch)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    back = list(avro.read_records(a))
+    assert len(back) == n
+    if n:
+        assert back[0]["uid"] == 0 and back[-1]["uid"] == int(uid[-1])
+        assert (back[5 % n]["label"] is None) == (not with_label)
+        assert ("weight" in back[0]) == with_weight
