@@ -33,7 +33,7 @@ SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_w
            "gdmix_partition_workspace_size", "gdmix_sort_pairs_u64", "gdmix_group_by_key", "gdmix_csr_gather_rows",
            "gdmix_gather_f32", "gdmix_partition_ids_i64", "gdmix_auc", "gdmix_re_fit_sweep",
            "gdmix_re_last_plan_typical", "gdmix_local_index_mark", "gdmix_local_index_apply",
-           "gdmix_seqex_count", "gdmix_seqex_fill", "gdmix_example_count", "gdmix_example_fill", "gdmix_avro_score_blocks"]
+           "gdmix_seqex_count", "gdmix_seqex_fill", "gdmix_example_count", "gdmix_example_fill", "gdmix_avro_score_blocks", "gdmix_avro_model_blocks"]
 
 
 class SeqexSpec(C.Structure):
@@ -43,6 +43,14 @@ class SeqexSpec(C.Structure):
 class SeqexSizes(C.Structure):
     _fields_ = [("n_entities", C.c_int64), ("n_rows", C.c_int64), ("nnz", C.c_int64), ("id_bytes", C.c_int64),
                 ("all_labelled", C.c_int32), ("saw_weight", C.c_int32)]
+
+
+class ModelTable(C.Structure):
+    _fields_ = [("n_models", C.c_int64), ("id_chars", C.c_void_p), ("id_ptr", C.c_void_p), ("model_class", C.c_char_p),
+                ("coef", C.c_void_p), ("var", C.c_void_p), ("coef_ptr", C.c_void_p), ("feat_idx", C.c_void_p),
+                ("has_intercept", C.c_int32), ("reserved", C.c_int32), ("threshold", C.c_double),
+                ("intercept_name", C.c_char_p), ("name_chars", C.c_void_p), ("name_ptr", C.c_void_p),
+                ("term_chars", C.c_void_p), ("term_ptr", C.c_void_p), ("n_features", C.c_int64)]
 
 
 class GdmixError(RuntimeError):
@@ -589,4 +597,42 @@ def avro_score_blocks(uid, score, label, weight, per_coordinate, sync, records_p
     check(lib.gdmix_avro_score_blocks(_np_ptr(uid), _np_ptr(score), _np_ptr(label), _np_ptr(weight),
                                       _np_ptr(per_coordinate), C.c_int64(n), C.c_int32(records_per_block),
                                       _np_ptr(sync_arr), _np_ptr(out), C.c_int64(out.size), C.byref(written)))
+    return out[:written.value].tobytes()
+
+
+def _string_table(strings):
+    """list of str -> (uint8 array of the concatenated utf-8 bytes, int64 offsets [n + 1])"""
+    enc = [x.encode("utf-8") for x in strings]
+    ptr = np.zeros(len(enc) + 1, np.int64)
+    if enc:
+        np.cumsum([len(b) for b in enc], out=ptr[1:])
+    chars = np.frombuffer(b"".join(enc), dtype=np.uint8) if enc and ptr[-1] else np.zeros(1, np.uint8)
+    return np.ascontiguousarray(chars), ptr
+
+
+def avro_model_blocks(model_ids, coef, var, coef_ptr, feat_idx, has_intercept, threshold, feature_names, feature_terms,
+                      model_class, intercept_name, sync, records_per_block=1024):
+    """-> bytes: the blocks of an Avro container holding these BayesianLinearModelAvro records
+    (gdmix_avro_model_blocks; the layout of its arguments is documented in include/gdmix_b200.h)."""
+    idc, idp = _string_table([str(m) for m in model_ids])
+    nc, npt = _string_table(list(feature_names))
+    tc, tpt = _string_table(list(feature_terms))
+    coef = np.ascontiguousarray(coef, dtype=np.float64)
+    var = None if var is None else np.ascontiguousarray(var, dtype=np.float64)
+    coef_ptr = np.ascontiguousarray(coef_ptr, dtype=np.int64)
+    feat_idx = np.ascontiguousarray(feat_idx, dtype=np.int64)
+    if feat_idx.size == 0:
+        feat_idx = np.zeros(1, np.int64)
+    t = ModelTable(len(model_ids), _np_ptr(idc), _np_ptr(idp), model_class.encode("utf-8"), _np_ptr(coef), _np_ptr(var),
+                   _np_ptr(coef_ptr), _np_ptr(feat_idx), 1 if has_intercept else 0, 0, float(threshold),
+                   intercept_name.encode("utf-8"), _np_ptr(nc), _np_ptr(npt), _np_ptr(tc), _np_ptr(tpt), len(feature_names))
+    sync_arr = np.frombuffer(bytes(sync), dtype=np.uint8)
+    assert sync_arr.size == 16
+    need = C.c_int64()
+    check(lib.gdmix_avro_model_blocks(C.byref(t), C.c_int32(records_per_block), _np_ptr(sync_arr), None, C.c_int64(0),
+                                      C.byref(need)))
+    out = np.empty(max(need.value, 1), np.uint8)
+    written = C.c_int64()
+    check(lib.gdmix_avro_model_blocks(C.byref(t), C.c_int32(records_per_block), _np_ptr(sync_arr), _np_ptr(out),
+                                      C.c_int64(out.size), C.byref(written)))
     return out[:written.value].tobytes()

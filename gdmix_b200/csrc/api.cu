@@ -1446,6 +1446,26 @@ int gdmix_avro_score_blocks(const int64_t *uid, const float *score, const float 
     return GDMIX_OK;
 }
 
+int gdmix_avro_model_blocks(const gdmix_model_table *t, int32_t records_per_block, const uint8_t *sync16, uint8_t *out,
+                            int64_t capacity, int64_t *written)
+{
+    if (!t || !written || records_per_block <= 0 || !sync16 || t->n_models < 0 ||
+        (t->n_models > 0 && (!t->id_chars || !t->id_ptr || !t->model_class || !t->coef || !t->coef_ptr || !t->intercept_name)))
+        return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_avro_model_blocks");
+    gdmix_host::ModelTable m;
+    m.n_models = t->n_models; m.id_chars = t->id_chars; m.id_ptr = t->id_ptr; m.model_class = t->model_class;
+    m.coef = t->coef; m.var = t->var; m.coef_ptr = t->coef_ptr; m.feat_idx = t->feat_idx;
+    m.has_intercept = t->has_intercept; m.threshold = t->threshold; m.intercept_name = t->intercept_name;
+    m.name_chars = t->name_chars; m.name_ptr = t->name_ptr; m.term_chars = t->term_chars; m.term_ptr = t->term_ptr;
+    m.n_features = t->n_features;
+    const int64_t need = gdmix_host::avro_model_blocks(m, records_per_block, sync16, nullptr);
+    if (need < 0) return fail(GDMIX_ERR_INVALID, "model table is inconsistent (coefficient slices / feature indices)");
+    if (!out) { *written = need; return GDMIX_OK; }
+    if (capacity < need) return fail(GDMIX_ERR_WORKSPACE, "output buffer %lld B < required %lld B", (long long)capacity, (long long)need);
+    *written = gdmix_host::avro_model_blocks(m, records_per_block, sync16, out);
+    return GDMIX_OK;
+}
+
 void gdmix_host_release(void)
 {
     std::lock_guard<std::mutex> lk(g_host.mu);

@@ -107,6 +107,22 @@ def export_linear_model_to_avro(model_ids, list_of_weight_indices, list_of_weigh
     avro.write_records(output_file, BAYESIAN_LINEAR_MODEL_SCHEMA, gen_records())
 
 
+def export_random_effect_models(model_ids, coef, var, coef_ptr, feat_idx, has_intercept, feature_file, output_file,
+                                model_class=LOGISTIC_MODEL_CLASS, sparsity_threshold=1.0e-4, sync=None):
+    """The same file export_linear_model_to_avro writes for per-entity models, from flat arrays: model m owns
+    coef[coef_ptr[m]:coef_ptr[m+1]] (intercept first when has_intercept; var aligned or None) and feat_idx lists the
+    global feature ids of its other coefficients.  Records are encoded by the library (gdmix_avro_model_blocks)."""
+    from .. import _capi as capi
+    feature_list = read_feature_list(feature_file) if feature_file else []
+    with avro.Writer(output_file, BAYESIAN_LINEAR_MODEL_SCHEMA, "null", sync=sync) as w:
+        body = capi.avro_model_blocks(model_ids, coef, var, coef_ptr, feat_idx, has_intercept, sparsity_threshold,
+                                      [f[0] for f in feature_list], [f[1] for f in feature_list], model_class, INTERCEPT,
+                                      w.sync)
+        w.f.write(body)
+        w.count += len(model_ids)
+        return w.count
+
+
 def load_linear_models_from_avro(model_file, feature_file):
     """Fixed-effect loader: dense coefficient arrays with the intercept moved to the end."""
     feature_map = None if feature_file is None else get_feature_map(feature_file)

@@ -198,25 +198,29 @@ class RandomEffectLRLBFGSModel(Model):
 
     # ---- model files (random_effect_lr_lbfgs_model.py:219-309) ---------------------------------------------
     def _save_model(self, output_file, model_coefficients, num_features, feature_file):
+        """One Photon-ML BayesianLinearModelAvro record per entity (random_effect_lr_lbfgs_model.py:219-260 ->
+        export_linear_model_to_avro): intercept first, features above the sparsity threshold by name / term,
+        variances aligned when a variance mode is set.  The records are encoded by the library from flat arrays."""
         model_ids = list(model_coefficients.keys())
-        biases = [] if self.has_intercept else None
         with_variance = self.model_params.random_effect_variance_mode is not None
+        hi = 1 if self.has_intercept else 0
         if feature_file is None:
-            list_of_weight_indices = list_of_weight_values = None  # intercept-only model
-            assert num_features == 1
-        else:
-            list_of_weight_indices, list_of_weight_values = [], []
+            assert num_features == 1          # intercept-only model: nothing but the bias is written
+        means, variances, indices = [], [], []
         for entity_id, (mean, variance, unique_global_indices) in model_coefficients.items():
-            idx = 0
-            if self.has_intercept:
-                biases.append((mean[idx], variance[idx]) if with_variance else mean[idx])
-                idx = 1
-            if list_of_weight_indices is not None:
-                list_of_weight_values.append((mean[idx:], variance[idx:]) if with_variance else mean[idx:])
-                list_of_weight_indices.append(unique_global_indices)
+            mean = np.asarray(mean, dtype=np.float64).ravel()
+            keep = hi if feature_file is None else mean.shape[0]
+            means.append(mean[:keep])
+            if with_variance:
+                variances.append(np.asarray(variance, dtype=np.float64).ravel()[:keep])
+            if feature_file is not None:
+                indices.append(np.asarray(unique_global_indices, dtype=np.int64).ravel())
+        cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
+        coef_ptr = np.concatenate([[0], np.cumsum([m.shape[0] for m in means])]).astype(np.int64)
         os.makedirs(os.path.dirname(output_file) or ".", exist_ok=True)
-        model_io.export_linear_model_to_avro(model_ids, list_of_weight_indices, list_of_weight_values, biases,
-                                             feature_file, output_file,
+        model_io.export_random_effect_models(model_ids, cat(means, np.float64),
+                                             cat(variances, np.float64) if with_variance else None, coef_ptr,
+                                             cat(indices, np.int64), self.has_intercept, feature_file, output_file,
                                              sparsity_threshold=self.model_params.sparsity_threshold)
 
     def _load_weights(self, model_file, catch_exception=False):

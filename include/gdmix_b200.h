@@ -358,6 +358,28 @@ GDMIX_API int gdmix_avro_score_blocks(const int64_t *uid, const float *score, co
                                       const float *per_coordinate, int64_t n, int32_t records_per_block,
                                       const uint8_t *sync16, uint8_t *out, int64_t capacity, int64_t *written);
 
+/* Avro encoding of model files: Photon-ML BayesianLinearModelAvro records as gen_one_avro_model writes them
+ * (util/io_utils.py:102-160, models/schemas.py:3-51): modelId, modelClass, means = the intercept first (always), then
+ * every feature with |coefficient| > threshold as (name, term, value); variances aligned with means, or null when
+ * var == NULL; lossFunction "".  Model m owns coef[coef_ptr[m] .. coef_ptr[m+1]) (intercept first when has_intercept)
+ * and its non-intercept coefficients' GLOBAL feature ids sit in feat_idx in the same order (intercepts not listed);
+ * names / terms come from the feature file as concatenated utf-8 strings with offset tables.  Blocks of
+ * records_per_block records as in gdmix_avro_score_blocks.  out == NULL: *written = bytes needed. */
+typedef struct gdmix_model_table {
+    int64_t n_models;
+    const char *id_chars; const int64_t *id_ptr;
+    const char *model_class;
+    const double *coef, *var; const int64_t *coef_ptr;
+    const int64_t *feat_idx;
+    int32_t has_intercept; int32_t reserved;
+    double threshold;
+    const char *intercept_name;
+    const char *name_chars; const int64_t *name_ptr; const char *term_chars; const int64_t *term_ptr;
+    int64_t n_features;
+} gdmix_model_table;
+GDMIX_API int gdmix_avro_model_blocks(const gdmix_model_table *table, int32_t records_per_block, const uint8_t *sync16,
+                                      uint8_t *out, int64_t capacity, int64_t *written);
+
 /* Replicated host-side solver state of the fixed-effect solve: L-BFGS-B without bounds, reverse
  * communication, the role scipy.optimize.fmin_l_bfgs_b plays at fixed_effect_lr_lbfgs_model.py:635-643.
  *   h = gdmix_lbfgs_create(n, opts)            (uses opts->m, max_iter, max_ls, max_fun, factr, pgtol)

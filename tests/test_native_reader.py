@@ -258,3 +258,46 @@ def test_native_score_writer_is_byte_identical_to_the_python_writer(tmp_path, wi
         assert back[0]["uid"] == 0 and back[-1]["uid"] == int(uid[-1])
         assert (back[5 % n]["label"] is None) == (not with_label)
         assert ("weight" in back[0]) == with_weight
+
+
+@pytest.mark.parametrize("has_intercept", [True, False])
+@pytest.mark.parametrize("with_variance", [True, False])
+def test_native_model_writer_is_byte_identical_to_the_python_writer(tmp_path, has_intercept, with_variance):
+    """model_io.export_random_effect_models (gdmix_avro_model_blocks) against export_linear_model_to_avro
+    (gen_one_avro_model per entity), same sync marker: equal files, incl. thresholded coefficients, an entity whose
+    every coefficient is thresholded, unicode names / ids, and more models than one block holds."""
+    from gdmix_b200.io import avro, model_io
+    rng = np.random.default_rng(3)
+    D = 50
+    ff = tmp_path / "features.csv"
+    ff.write_text("".join(f"featé{j},term{j % 3 if j % 4 else ''}\n" for j in range(D)), encoding="utf-8")
+    M = 1500
+    ids, idx, vals, vars_, biases = [], [], [], [], []
+    for m in range(M):
+        d = int(rng.integers(0, 9))
+        gi = np.sort(rng.choice(D, d, replace=False)).astype(np.int64)
+        w = rng.standard_normal(d) * rng.choice([1.0, 1e-5], d)        # some fall under the 1e-4 threshold
+        if m == 7:
+            w[:] = 1e-6
+        ids.append(f"user中{m}" if m % 2 else str(m * 97))
+        idx.append(gi); vals.append(w); vars_.append(rng.uniform(0.1, 2, d)); biases.append((float(rng.standard_normal()), float(rng.uniform(0.1, 2))))
+    sync = bytes(range(16, 32))
+    a, b = str(tmp_path / "native.avro"), str(tmp_path / "python.avro")
+    hi = 1 if has_intercept else 0
+    coef = np.concatenate([np.concatenate([[biases[m][0]] if hi else [], vals[m]]) for m in range(M)])
+    var = np.concatenate([np.concatenate([[biases[m][1]] if hi else [], vars_[m]]) for m in range(M)]) if with_variance else None
+    coef_ptr = np.concatenate([[0], np.cumsum([len(v) + hi for v in vals])]).astype(np.int64)
+    model_io.export_random_effect_models(ids, coef, var, coef_ptr, np.concatenate(idx), has_intercept, str(ff), a, sync=sync)
+    # the reference-shaped writer, with the same sync marker
+    feature_list = model_io.read_feature_list(str(ff))
+    recs = [model_io.gen_one_avro_model(ids[m], model_io.LOGISTIC_MODEL_CLASS, idx[m],
+                                        (vals[m], vars_[m]) if with_variance else vals[m],
+                                        (biases[m] if with_variance else biases[m][0]) if hi else None, feature_list, 1e-4)
+            for m in range(M)]
+    with avro.Writer(b, model_io.BAYESIAN_LINEAR_MODEL_SCHEMA, "null", sync=sync) as w:
+        for i in range(0, M, 1024):
+            w.write_block(recs[i:i + 1024])
+    assert open(a, "rb").read() == open(b, "rb").read()
+    back = list(avro.read_records(a))
+    assert len(back) == M and back[1]["modelId"] == ids[1]
+    assert (back[3]["variances"] is None) == (not with_variance)
