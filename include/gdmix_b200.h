@@ -26,6 +26,8 @@
  *   gdmix_group_by_key, gdmix_csr_gather_rows, gdmix_local_index_*   groupBy(entity) + per-entity np.unique
  *                        (DataPartitioner.scala:296-379, job_consumers.py:243) for chained coordinates on the device
  *   gdmix_auc            Evaluator.calculateMetric("auc")         gdmix-data/.../evaluation/Evaluator.scala:29-45
+ *   gdmix_avro_score_blocks, gdmix_avro_model_blocks   batched_write_avro / export_linear_model_to_avro (fastavro)
+ *                                                                util/io_utils.py:102-212, 299-375
  *   gdmix_seqex_*, gdmix_example_*   per_entity_grouped_input_fn / per_record_input_fn (tf.data readers)
  *                                                                io/input_data_pipeline.py:223-273
  *
