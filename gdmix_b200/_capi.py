@@ -33,7 +33,8 @@ SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_w
            "gdmix_partition_workspace_size", "gdmix_sort_pairs_u64", "gdmix_group_by_key", "gdmix_csr_gather_rows",
            "gdmix_gather_f32", "gdmix_partition_ids_i64", "gdmix_auc", "gdmix_re_fit_sweep",
            "gdmix_re_last_plan_typical", "gdmix_local_index_mark", "gdmix_local_index_apply",
-           "gdmix_seqex_count", "gdmix_seqex_fill", "gdmix_example_count", "gdmix_example_fill", "gdmix_avro_score_blocks", "gdmix_avro_model_blocks"]
+           "gdmix_seqex_count", "gdmix_seqex_fill", "gdmix_example_count", "gdmix_example_fill", "gdmix_avro_score_blocks", "gdmix_avro_model_blocks",
+           "gdmix_feature_map_create", "gdmix_feature_map_destroy", "gdmix_avro_model_decode"]
 
 
 class SeqexSpec(C.Structure):
@@ -100,6 +101,9 @@ def _load():
     lib.gdmix_re_last_plan.restype = None
     lib.gdmix_re_last_plan_typical.restype = None
     lib.gdmix_lbfgs_create.restype = C.c_void_p
+    lib.gdmix_feature_map_create.restype = C.c_void_p
+    lib.gdmix_feature_map_destroy.restype = None
+    lib.gdmix_feature_map_destroy.argtypes = [C.c_void_p]
     lib.gdmix_lbfgs_create.argtypes = [C.c_int64, C.c_void_p]
     lib.gdmix_lbfgs_iterate.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
     lib.gdmix_lbfgs_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -636,3 +640,44 @@ def avro_model_blocks(model_ids, coef, var, coef_ptr, feat_idx, has_intercept, t
     check(lib.gdmix_avro_model_blocks(C.byref(t), C.c_int32(records_per_block), _np_ptr(sync_arr), _np_ptr(out),
                                       C.c_int64(out.size), C.byref(written)))
     return out[:written.value].tobytes()
+
+
+class FeatureMap:
+    """(name, term) -> feature-file row, held by the library for gdmix_avro_model_decode."""
+
+    def __init__(self, feature_names, feature_terms, intercept_name):
+        self._keep = (_string_table(list(feature_names)), _string_table(list(feature_terms)))
+        (nc, npt), (tc, tpt) = self._keep
+        self.h = lib.gdmix_feature_map_create(_np_ptr(nc), _np_ptr(npt), _np_ptr(tc), _np_ptr(tpt),
+                                              C.c_int64(len(feature_names)), intercept_name.encode("utf-8"))
+        if not self.h:
+            raise GdmixError(GDMIX_ERR_INVALID, lib.gdmix_last_error().decode())
+
+    def decode_models(self, block, n_records):
+        """One uncompressed container block of BayesianLinearModelAvro records -> flat arrays (dict)."""
+        buf = np.frombuffer(block, dtype=np.uint8)
+        nm, ib = C.c_int64(), C.c_int64()
+        h = C.c_void_p(self.h)
+        check(lib.gdmix_avro_model_decode(h, _np_ptr(buf), C.c_int64(buf.size), C.c_int64(n_records), C.byref(nm),
+                                          C.byref(ib), None, None, None, None, None, None, None))
+        n = int(n_records)
+        out = {"id_chars": np.zeros(max(ib.value, 1), np.uint8), "id_ptr": np.zeros(n + 1, np.int64),
+               "mean_ptr": np.zeros(n + 1, np.int64), "mean_feat": np.zeros(max(nm.value, 1), np.int64),
+               "mean_val": np.zeros(max(nm.value, 1), np.float64), "var_val": np.zeros(max(nm.value, 1), np.float64),
+               "has_var": np.zeros(max(n, 1), np.uint8)}
+        check(lib.gdmix_avro_model_decode(h, _np_ptr(buf), C.c_int64(buf.size), C.c_int64(n_records), C.byref(nm),
+                                          C.byref(ib), _np_ptr(out["id_chars"]), _np_ptr(out["id_ptr"]),
+                                          _np_ptr(out["mean_ptr"]), _np_ptr(out["mean_feat"]), _np_ptr(out["mean_val"]),
+                                          _np_ptr(out["var_val"]), _np_ptr(out["has_var"])))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.gdmix_feature_map_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

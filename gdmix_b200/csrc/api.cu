@@ -1466,6 +1466,51 @@ int gdmix_avro_model_blocks(const gdmix_model_table *t, int32_t records_per_bloc
     return GDMIX_OK;
 }
 
+struct gdmix_feature_map { gdmix_host::FeatureMap fm; };
+
+gdmix_feature_map *gdmix_feature_map_create(const char *name_chars, const int64_t *name_ptr, const char *term_chars,
+                                            const int64_t *term_ptr, int64_t n_features, const char *intercept_name)
+{
+    if (n_features < 0 || !intercept_name || (n_features > 0 && (!name_chars || !name_ptr || !term_chars || !term_ptr))) {
+        fail(GDMIX_ERR_INVALID, "bad argument to gdmix_feature_map_create");
+        return nullptr;
+    }
+    gdmix_feature_map *h = new gdmix_feature_map;
+    h->fm.intercept = intercept_name;
+    h->fm.index.reserve((size_t)n_features * 2);
+    std::string key;
+    for (int64_t g = 0; g < n_features; g++) {
+        key.assign(name_chars + name_ptr[g], (size_t)(name_ptr[g + 1] - name_ptr[g]));
+        key.push_back('\x01');
+        key.append(term_chars + term_ptr[g], (size_t)(term_ptr[g + 1] - term_ptr[g]));
+        h->fm.index[key] = g;   // a repeated (name, term) keeps its LAST row, as the reference's dict does
+    }
+    return h;
+}
+
+void gdmix_feature_map_destroy(gdmix_feature_map *h) { delete h; }
+
+int gdmix_avro_model_decode(const gdmix_feature_map *h, const uint8_t *block, int64_t len, int64_t n_records,
+                            int64_t *n_means, int64_t *id_bytes, char *id_chars, int64_t *id_ptr, int64_t *mean_ptr,
+                            int64_t *mean_feat, double *mean_val, double *var_val, uint8_t *has_var)
+{
+    if (!h || len < 0 || n_records < 0 || (len > 0 && !block) || !n_means || !id_bytes)
+        return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_avro_model_decode");
+    std::string err;
+    gdmix_host::ModelDecoder d(h->fm, err);
+    gdmix_host::ModelDecodeSizes sz;
+    gdmix_host::ModelDecodeOut o;
+    if (id_chars) {
+        if (!id_ptr || !mean_ptr || !mean_feat || !mean_val || !var_val || !has_var)
+            return fail(GDMIX_ERR_INVALID, "gdmix_avro_model_decode: all output arrays or none");
+        o.id_chars = id_chars; o.id_ptr = id_ptr; o.mean_ptr = mean_ptr; o.mean_feat = mean_feat; o.mean_val = mean_val;
+        o.var_val = var_val; o.has_var = has_var;
+    }
+    if (!d.run(block, len, n_records, sz, o)) return fail(GDMIX_ERR_INVALID, "%s", err.c_str());
+    *n_means = sz.n_means; *id_bytes = sz.id_bytes;
+    return GDMIX_OK;
+}
+
 void gdmix_host_release(void)
 {
     std::lock_guard<std::mutex> lk(g_host.mu);

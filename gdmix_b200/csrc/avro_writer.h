@@ -8,6 +8,8 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <string>
+#include <unordered_map>
 
 namespace gdmix_host {
 
@@ -139,5 +141,131 @@ inline int64_t avro_model_blocks(const ModelTable &t, int32_t per_block, const u
     }
     return o.n;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Reading model files back (warm starts, the predict action): the records of one container block of
+// BayesianLinearModelAvro -> flat arrays.  Every (name, term) is looked up in the feature file's table; the
+// intercept is ("(INTERCEPT)", "").  Count pass (null outputs) then fill pass, like the TFRecord readers.
+// ---------------------------------------------------------------------------------------------------------
+struct FeatureMap {
+    std::unordered_map<std::string, int64_t> index;   // key = name + '\x01' + term
+    std::string intercept;
+};
+
+struct ModelDecodeOut {   // null pointers: counting pass
+    char *id_chars = nullptr; int64_t *id_ptr = nullptr;
+    int64_t *mean_ptr = nullptr;      // [n + 1] into mean_feat / mean_val / var_val
+    int64_t *mean_feat = nullptr;     // global feature index, -1 = the intercept
+    double *mean_val = nullptr, *var_val = nullptr;
+    uint8_t *has_var = nullptr;       // [n]
+};
+struct ModelDecodeSizes { int64_t n_models = 0, n_means = 0, id_bytes = 0; };
+
+class ModelDecoder {
+public:
+    ModelDecoder(const FeatureMap &fm, std::string &err) : fm_(fm), err_(err) {}
+
+    bool run(const uint8_t *buf, int64_t len, int64_t n_records, ModelDecodeSizes &sz, const ModelDecodeOut &o)
+    {
+        p_ = buf; e_ = buf + len;
+        for (int64_t r = 0; r < n_records; r++)
+            if (!record(sz, o)) return false;
+        if (p_ != e_) return fail("trailing bytes after the block's records");
+        if (o.id_ptr) o.id_ptr[sz.n_models] = sz.id_bytes;
+        if (o.mean_ptr) o.mean_ptr[sz.n_models] = sz.n_means;
+        return true;
+    }
+
+private:
+    bool fail(const char *msg) { err_ = msg; return false; }
+    bool lng(int64_t &v)
+    {
+        uint64_t z = 0;
+        for (int shift = 0; shift < 70; shift += 7) {
+            if (p_ >= e_) return false;
+            const uint8_t b = *p_++;
+            if (shift < 64) z |= (uint64_t)(b & 0x7f) << shift;
+            if (!(b & 0x80)) { v = (int64_t)(z >> 1) ^ -(int64_t)(z & 1); return true; }
+        }
+        return false;
+    }
+    bool str(const uint8_t *&s, int64_t &n)
+    {
+        if (!lng(n) || n < 0 || n > e_ - p_) return false;
+        s = p_; p_ += n;
+        return true;
+    }
+    bool dbl(double &v) { if (e_ - p_ < 8) return false; memcpy(&v, p_, 8); p_ += 8; return true; }
+    bool opt_string()   // ["null", "string"]
+    {
+        int64_t br; const uint8_t *s; int64_t n;
+        if (!lng(br)) return false;
+        if (br == 0) return true;
+        return br == 1 && str(s, n);
+    }
+    // one array of NameTermValueAvro; which = 0: means (defines the entry list), 1: variances (must align)
+    bool ntv_array(int which, ModelDecodeSizes &sz, const ModelDecodeOut &o, int64_t first, int64_t &count)
+    {
+        count = 0;
+        for (;;) {
+            int64_t n;
+            if (!lng(n)) return fail("malformed array block count");
+            if (n == 0) break;
+            if (n < 0) { int64_t bytes; n = -n; if (!lng(bytes)) return fail("malformed array block size"); }
+            for (int64_t i = 0; i < n; i++) {
+                const uint8_t *nm, *tm; int64_t nl, tl; double v;
+                if (!str(nm, nl) || !str(tm, tl) || !dbl(v)) return fail("malformed name-term-value");
+                int64_t feat;
+                if (tl == 0 && (size_t)nl == fm_.intercept.size() && memcmp(nm, fm_.intercept.data(), nl) == 0) {
+                    feat = -1;
+                } else {
+                    key_.assign((const char *)nm, (size_t)nl); key_.push_back('\x01'); key_.append((const char *)tm, (size_t)tl);
+                    auto it = fm_.index.find(key_);
+                    if (it == fm_.index.end()) { err_ = "feature (" + key_.substr(0, nl) + ", " + std::string((const char *)tm, (size_t)tl) + ") is not in the feature file"; return false; }
+                    feat = it->second;
+                }
+                if (which == 0) {
+                    if (o.mean_feat) { o.mean_feat[first + count] = feat; o.mean_val[first + count] = v; }
+                } else {
+                    if (o.mean_feat) {
+                        if (o.mean_feat[first + count] != feat) return fail("variances are not aligned with means");
+                        o.var_val[first + count] = v;
+                    }
+                }
+                count++;
+            }
+        }
+        return true;
+    }
+    bool record(ModelDecodeSizes &sz, const ModelDecodeOut &o)
+    {
+        const uint8_t *id; int64_t idl;
+        if (!str(id, idl)) return fail("malformed modelId");
+        if (o.id_chars) { o.id_ptr[sz.n_models] = sz.id_bytes; memcpy(o.id_chars + sz.id_bytes, id, (size_t)idl); }
+        if (!opt_string()) return fail("malformed modelClass");
+        const int64_t first = sz.n_means;
+        if (o.mean_ptr) o.mean_ptr[sz.n_models] = first;
+        int64_t nm = 0, nv = 0;
+        if (!ntv_array(0, sz, o, first, nm)) return false;
+        int64_t br;
+        if (!lng(br)) return fail("malformed variances union");
+        if (br == 1) {
+            if (!ntv_array(1, sz, o, first, nv)) return false;
+            if (nv != 0 && nv != nm) return fail("variances and means differ in length");
+        } else if (br != 0) return fail("malformed variances union");
+        if (o.has_var) o.has_var[sz.n_models] = nv ? 1 : 0;
+        if (o.var_val && !nv) for (int64_t i = 0; i < nm; i++) o.var_val[first + i] = 0.0;
+        if (!opt_string()) return fail("malformed lossFunction");
+        sz.id_bytes += idl;
+        sz.n_means += nm;
+        sz.n_models++;
+        return true;
+    }
+
+    const FeatureMap &fm_;
+    std::string &err_;
+    std::string key_;
+    const uint8_t *p_ = nullptr, *e_ = nullptr;
+};
 
 }  // namespace gdmix_host

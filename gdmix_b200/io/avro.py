@@ -342,5 +342,51 @@ def read_container(path_or_bytes):
     return schema.json, records()
 
 
+def read_blocks(path_or_bytes):
+    """-> (schema_json, iterator over (record_count, uncompressed block bytes)) -- for the library's block decoders."""
+    if isinstance(path_or_bytes, (bytes, bytearray)):
+        buf = bytes(path_or_bytes)
+    else:
+        with open(path_or_bytes, "rb") as f:
+            buf = f.read()
+    if buf[:4] != MAGIC:
+        raise ValueError("not an Avro object container file")
+    pos = 4
+    meta = {}
+    while True:
+        n, pos = read_long(buf, pos)
+        if n == 0:
+            break
+        if n < 0:
+            n = -n
+            _, pos = read_long(buf, pos)
+        for _ in range(n):
+            kl, pos = read_long(buf, pos)
+            k = buf[pos:pos + kl].decode(); pos += kl
+            vl, pos = read_long(buf, pos)
+            meta[k] = buf[pos:pos + vl]; pos += vl
+    sync = buf[pos:pos + 16]
+    pos += 16
+    codec = meta.get("avro.codec", b"null").decode()
+
+    def blocks():
+        p = pos
+        while p < len(buf):
+            n, p = read_long(buf, p)
+            size, p = read_long(buf, p)
+            data = buf[p:p + size]
+            p += size
+            if buf[p:p + 16] != sync:
+                raise ValueError("avro sync marker mismatch")
+            p += 16
+            if codec == "deflate":
+                data = zlib.decompress(data, wbits=-15)
+            elif codec != "null":
+                raise ValueError(f"unsupported avro codec {codec!r}")
+            yield n, data
+
+    return json.loads(meta["avro.schema"].decode()), blocks()
+
+
 def read_records(path_or_bytes):
     return list(read_container(path_or_bytes)[1])

@@ -230,11 +230,42 @@ class RandomEffectLRLBFGSModel(Model):
                 logger.info(f"No model found at {model_file}.")
                 return {}
             raise FileNotFoundError(f"Model file {model_file} does not exist")
-        feature2global_id = None if self.feature_file is None else model_io.get_feature_map(self.feature_file)
+        return self._load_weights_native(model_file)
+
+    def _load_weights_native(self, model_file):
+        """entity id -> TrainingResult, decoded block by block by the library (gdmix_avro_model_decode); the same
+        dict _convert_avro_model_record_to_sparse_coefficients builds one Python record at a time."""
         from .io import avro
-        return dict(self._convert_avro_model_record_to_sparse_coefficients(self.has_intercept, record,
-                                                                           feature2global_id)
-                    for record in avro.read_records(model_file))
+        feature_list = model_io.read_feature_list(self.feature_file) if self.feature_file else []
+        fmap = capi.FeatureMap([f[0] for f in feature_list], [f[1] for f in feature_list], constants.INTERCEPT)
+        hi = 1 if self.has_intercept else 0
+        out = {}
+        try:
+            _, blocks = avro.read_blocks(model_file)
+            for n, data in blocks:
+                try:
+                    d = fmap.decode_models(data, n)
+                except capi.GdmixError as ex:
+                    raise KeyError(f"{model_file}: {ex}") from None
+                ids = d["id_chars"].tobytes()
+                ip, mp = d["id_ptr"], d["mean_ptr"]
+                for m in range(n):
+                    a, b = int(mp[m]), int(mp[m + 1])
+                    feat = d["mean_feat"][a:b]
+                    if hi:
+                        assert b > a and feat[0] == -1, "the first mean of a model with intercept is the intercept"
+                    assert not (feat[hi:] < 0).any(), "an intercept among the feature coefficients"
+                    theta, idx = d["mean_val"][a:b].copy(), feat[hi:].copy()
+                    if self.feature_file is None:
+                        # intercept-only model: one dummy feature
+                        assert idx.size == 0
+                        theta, idx = np.append(theta, 0.0), np.zeros(1, np.int64)
+                    var = d["var_val"][a:b].copy() if d["has_var"][m] else None
+                    out[ids[ip[m]:ip[m + 1]].decode("utf-8")] = TrainingResult(theta=theta, variance=var,
+                                                                               unique_global_indices=idx)
+        finally:
+            fmap.close()
+        return out
 
     @staticmethod
     def _convert_avro_model_record_to_sparse_coefficients(has_intercept, model_record, feature2global_id):

@@ -382,6 +382,22 @@ typedef struct gdmix_model_table {
 GDMIX_API int gdmix_avro_model_blocks(const gdmix_model_table *table, int32_t records_per_block, const uint8_t *sync16,
                                       uint8_t *out, int64_t capacity, int64_t *written);
 
+/* Reading model files back (warm starts, the predict action; io_utils.py:163-212 / _load_weights,
+ * random_effect_lr_lbfgs_model.py:262-309): the records of ONE container block (uncompressed) -> flat arrays.
+ * A feature map handle holds the feature file's (name, term) -> row index table.  Call once with id_chars == NULL
+ * for the sizes (*n_means, *id_bytes), then with the arrays: id_chars / id_ptr[n+1] (modelId strings), mean_ptr[n+1],
+ * mean_feat (feature row, -1 = the intercept) / mean_val per entry, var_val aligned (0 where has_var[m] == 0).
+ * A (name, term) missing from the feature file, or variances not aligned with means, is an error. */
+typedef struct gdmix_feature_map gdmix_feature_map;
+GDMIX_API gdmix_feature_map *gdmix_feature_map_create(const char *name_chars, const int64_t *name_ptr,
+                                                      const char *term_chars, const int64_t *term_ptr,
+                                                      int64_t n_features, const char *intercept_name);
+GDMIX_API void gdmix_feature_map_destroy(gdmix_feature_map *map);
+GDMIX_API int gdmix_avro_model_decode(const gdmix_feature_map *map, const uint8_t *block, int64_t len, int64_t n_records,
+                                      int64_t *n_means, int64_t *id_bytes, char *id_chars, int64_t *id_ptr,
+                                      int64_t *mean_ptr, int64_t *mean_feat, double *mean_val, double *var_val,
+                                      uint8_t *has_var);
+
 /* Replicated host-side solver state of the fixed-effect solve: L-BFGS-B without bounds, reverse
  * communication, the role scipy.optimize.fmin_l_bfgs_b plays at fixed_effect_lr_lbfgs_model.py:635-643.
  *   h = gdmix_lbfgs_create(n, opts)            (uses opts->m, max_iter, max_ls, max_fun, factr, pgtol)

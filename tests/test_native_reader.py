@@ -301,3 +301,51 @@ def test_native_model_writer_is_byte_identical_to_the_python_writer(tmp_path, ha
     back = list(avro.read_records(a))
     assert len(back) == M and back[1]["modelId"] == ids[1]
     assert (back[3]["variances"] is None) == (not with_variance)
+
+
+@pytest.mark.parametrize("has_intercept", [True, False])
+@pytest.mark.parametrize("with_variance", [True, False])
+@pytest.mark.parametrize("codec", ["null", "deflate"])
+def test_native_model_reader_matches_the_python_conversion(tmp_path, has_intercept, with_variance, codec):
+    """RandomEffectLRLBFGSModel._load_weights (gdmix_avro_model_decode per container block) against
+    _convert_avro_model_record_to_sparse_coefficients over avro.read_records, on files written by the Python writer
+    (both codecs) -- same entity ids, coefficients, variances, feature indices, dtypes."""
+    from types import SimpleNamespace
+    from gdmix_b200.io import avro, model_io
+    from gdmix_b200.random_effect import RandomEffectLRLBFGSModel as M
+    rng = np.random.default_rng(11)
+    D = 40
+    ff = tmp_path / "features.csv"
+    ff.write_text("".join(f"f{j},{'t' if j % 2 else ''}\n" for j in range(D)), encoding="utf-8")
+    feature_list = model_io.read_feature_list(str(ff))
+    recs = []
+    for m in range(2300):
+        d = int(rng.integers(0, 7))
+        gi = np.sort(rng.choice(D, d, replace=False))
+        w, v = rng.standard_normal(d), rng.uniform(0.1, 2, d)
+        bias = (float(rng.standard_normal()), float(rng.uniform(0.1, 2)))
+        recs.append(model_io.gen_one_avro_model(f"é{m}" if m % 3 else str(m), model_io.LOGISTIC_MODEL_CLASS, gi,
+                                                (w, v) if with_variance else w,
+                                                (bias if with_variance else bias[0]) if has_intercept else None,
+                                                feature_list, 0.0))
+    path = str(tmp_path / "models.avro")
+    avro.write_records(path, model_io.BAYESIAN_LINEAR_MODEL_SCHEMA, recs, codec=codec)
+    fake = SimpleNamespace(feature_file=str(ff), has_intercept=has_intercept)
+    got = M._load_weights_native(fake, path)
+    fmap = model_io.get_feature_map(str(ff))
+    want = dict(M._convert_avro_model_record_to_sparse_coefficients(has_intercept, r, fmap) for r in avro.read_records(path))
+    assert list(got.keys()) == list(want.keys())
+    for k in want:
+        np.testing.assert_array_equal(got[k].theta, want[k].theta)
+        np.testing.assert_array_equal(got[k].unique_global_indices, want[k].unique_global_indices)
+        assert got[k].unique_global_indices.dtype == want[k].unique_global_indices.dtype
+        assert (got[k].variance is None) == (want[k].variance is None)
+        if want[k].variance is not None:
+            np.testing.assert_array_equal(got[k].variance, want[k].variance)
+    # a feature the feature file does not know is an error, as the dict lookup of the reference is
+    bad = dict(recs[0]); bad["means"] = list(bad["means"]) + [{"name": "nope", "term": "", "value": 1.0}]
+    if with_variance:
+        bad["variances"] = list(bad["variances"]) + [{"name": "nope", "term": "", "value": 1.0}]
+    avro.write_records(str(tmp_path / "bad.avro"), model_io.BAYESIAN_LINEAR_MODEL_SCHEMA, [bad])
+    with pytest.raises(KeyError):
+        M._load_weights_native(fake, str(tmp_path / "bad.avro"))
