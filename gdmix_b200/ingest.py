@@ -211,7 +211,45 @@ def to_local_batch(data, has_intercept=True):
 
 def warm_start_theta(hb, uniq_ptr, uniq_global, entity_ids, model_weights, has_intercept=True):
     """theta0 for every entity of the batch plus a has_model flag (job_consumers.py:262-288: the prior's
-    intercept and the prior coefficients of features that occur in the current data; everything else 0)."""
+    intercept and the prior coefficients of features that occur in the current data; everything else 0).
+    One sorted merge over (entity, feature) keys for the whole batch instead of a search per entity."""
+    hi = 1 if has_intercept else 0
+    E = len(entity_ids)
+    theta0 = np.zeros(hb.n_coef, np.float64)
+    has_model = np.zeros(E, np.uint8)
+    if not model_weights:
+        return theta0, has_model
+    ents, idxs, coefs = [], [], []
+    for e, eid in enumerate(entity_ids):
+        prior = model_weights.get(eid)
+        if prior is None:
+            continue
+        has_model[e] = 1
+        ptheta = np.asarray(prior.theta, np.float64)
+        if has_intercept:
+            theta0[hb.theta_ptr[e]] = ptheta[0]
+        pidx = np.asarray(prior.unique_global_indices, np.int64)
+        if pidx.size:
+            ents.append(np.full(pidx.size, e, np.int64)); idxs.append(pidx); coefs.append(ptheta[hi:hi + pidx.size])
+    if not idxs or uniq_global.size == 0:
+        return theta0, has_model
+    p_ent, p_idx, p_coef = np.concatenate(ents), np.concatenate(idxs), np.concatenate(coefs)
+    width = np.int64(max(int(p_idx.max()), int(uniq_global.max())) + 1)
+    p_key = p_ent * width + p_idx
+    order = np.argsort(p_key, kind="stable")            # a repeated prior feature keeps its first occurrence
+    p_key, p_coef = p_key[order], p_coef[order]
+    d_e = np.diff(uniq_ptr)
+    c_ent = np.repeat(np.arange(E, dtype=np.int64), d_e)
+    c_key = c_ent * width + uniq_global
+    pos = np.minimum(np.searchsorted(p_key, c_key), p_key.size - 1)
+    hit = p_key[pos] == c_key
+    k = np.flatnonzero(hit)
+    theta0[hb.theta_ptr[c_ent[k]] + hi + (k - uniq_ptr[c_ent[k]])] = p_coef[pos[k]]
+    return theta0, has_model
+
+
+def _warm_start_theta_per_entity(hb, uniq_ptr, uniq_global, entity_ids, model_weights, has_intercept=True):
+    """The same, one entity at a time (the shape of the reference's loop); kept as the test's cross-check."""
     hi = 1 if has_intercept else 0
     theta0 = np.zeros(hb.n_coef, np.float64)
     has_model = np.zeros(len(entity_ids), np.uint8)

@@ -349,3 +349,35 @@ def test_native_model_reader_matches_the_python_conversion(tmp_path, has_interce
     avro.write_records(str(tmp_path / "bad.avro"), model_io.BAYESIAN_LINEAR_MODEL_SCHEMA, [bad])
     with pytest.raises(KeyError):
         M._load_weights_native(fake, str(tmp_path / "bad.avro"))
+
+
+@pytest.mark.parametrize("has_intercept", [True, False])
+def test_vectorised_warm_start_equals_the_per_entity_loop(has_intercept):
+    """ingest.warm_start_theta (one sorted merge over (entity, feature) keys) against the per-entity search that
+    mirrors job_consumers.py:262-288: prior features absent now are dropped, new features start at 0, entities
+    without a prior keep zeros, unsorted and repeated prior indices included."""
+    from collections import namedtuple
+    from types import SimpleNamespace
+    TR = namedtuple("TR", "theta variance unique_global_indices")
+    rng = np.random.default_rng(5)
+    E, D = 400, 60
+    hi = 1 if has_intercept else 0
+    d_e = rng.integers(0, 12, E)
+    uniq_ptr = np.concatenate([[0], np.cumsum(d_e)]).astype(np.int64)
+    uniq_global = np.concatenate([np.sort(rng.choice(D, d, replace=False)) for d in d_e]).astype(np.int64)
+    theta_ptr = np.concatenate([[0], np.cumsum(d_e + hi)]).astype(np.int64)
+    hb = SimpleNamespace(n_coef=int(theta_ptr[-1]), theta_ptr=theta_ptr)
+    ids = [f"e{e}" for e in range(E)]
+    prior = {}
+    for e in range(0, E, 2):
+        k = int(rng.integers(0, 15))
+        pidx = rng.integers(0, D + 20, k)                      # unsorted, repeats, ids the current data lacks
+        prior[ids[e]] = TR(rng.standard_normal(k + hi), None, pidx.astype(np.int64))
+    prior["someone else"] = TR(rng.standard_normal(3 + hi), None, np.array([1, 2, 3]))
+    a = ingest.warm_start_theta(hb, uniq_ptr, uniq_global, ids, prior, has_intercept)
+    b = ingest._warm_start_theta_per_entity(hb, uniq_ptr, uniq_global, ids, prior, has_intercept)
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
+    assert a[1].sum() == E // 2 and np.count_nonzero(a[0]) > 0
+    z = ingest.warm_start_theta(hb, uniq_ptr, uniq_global, ids, {}, has_intercept)
+    assert not z[0].any() and not z[1].any()
