@@ -34,7 +34,9 @@ SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_w
            "gdmix_gather_f32", "gdmix_partition_ids_i64", "gdmix_auc", "gdmix_re_fit_sweep",
            "gdmix_re_last_plan_typical", "gdmix_local_index_mark", "gdmix_local_index_apply",
            "gdmix_seqex_count", "gdmix_seqex_fill", "gdmix_example_count", "gdmix_example_fill", "gdmix_avro_score_blocks", "gdmix_avro_model_blocks",
-           "gdmix_feature_map_create", "gdmix_feature_map_destroy", "gdmix_avro_model_decode"]
+           "gdmix_feature_map_create", "gdmix_feature_map_destroy", "gdmix_avro_model_decode",
+           "gdmix_fe_lbfgs_create", "gdmix_fe_lbfgs_reset", "gdmix_fe_lbfgs_step", "gdmix_fe_lbfgs_poll",
+           "gdmix_fe_lbfgs_destroy", "gdmix_fe_column_counts", "gdmix_remap_i32"]
 
 
 class SeqexSpec(C.Structure):
@@ -109,6 +111,13 @@ def _load():
     lib.gdmix_lbfgs_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gdmix_lbfgs_destroy.argtypes = [C.c_void_p]
     lib.gdmix_lbfgs_destroy.restype = None
+    lib.gdmix_fe_lbfgs_create.restype = C.c_void_p
+    lib.gdmix_fe_lbfgs_create.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gdmix_fe_lbfgs_reset.argtypes = [C.c_void_p, C.c_void_p]
+    lib.gdmix_fe_lbfgs_step.argtypes = [C.c_void_p, C.c_void_p]
+    lib.gdmix_fe_lbfgs_poll.argtypes = [C.c_void_p] * 7
+    lib.gdmix_fe_lbfgs_destroy.argtypes = [C.c_void_p]
+    lib.gdmix_fe_lbfgs_destroy.restype = None
     for name in SYMBOLS:
         getattr(lib, name)  # AttributeError if the build is stale
     return lib
@@ -470,6 +479,39 @@ class DeviceFePlan:
                             self.scratch.numel(), self.n_tiles, _np_ptr(self.tile_item_ptr))
 
 
+def fe_column_counts(rows, stream=None):
+    """Non-zeros per feature of this rank's shard -> int64 CUDA tensor [D] (gdmix_fe_column_counts)."""
+    import torch
+    counts = torch.empty(rows.n_features, dtype=torch.int64, device=rows.val.device)
+    check(lib.gdmix_fe_column_counts(_tptr(rows.col), C.c_int64(rows.nnz), C.c_int64(rows.n_features), _tptr(counts),
+                                     _stream_ptr(stream)))
+    return counts
+
+
+def rank_by_count(counts, stream=None):
+    """Features by falling count, ties by feature id -> int32 CUDA tensor (the library's stable radix sort)."""
+    import torch
+    n = counts.numel()
+    mx = int(counts.max().item()) if n else 0
+    keys = (mx - counts).contiguous()
+    b = C.c_size_t()
+    check(lib.gdmix_partition_workspace_size(C.c_int64(max(n, 1)), C.byref(b)))
+    ws = torch.empty(b.value, dtype=torch.uint8, device=counts.device)
+    out = torch.empty_like(keys)
+    perm = torch.empty(n, dtype=torch.int32, device=counts.device)
+    check(lib.gdmix_sort_pairs_u64(_tptr(keys), C.c_int64(n), C.c_int32(max(1, mx.bit_length())), _tptr(out), _tptr(perm),
+                                   _tptr(ws), C.c_size_t(ws.numel()), _stream_ptr(stream)))
+    return perm
+
+
+def remap_columns(col, rank_of, stream=None):
+    """rank_of[col] as a new int32 tensor (gdmix_remap_i32)."""
+    import torch
+    out = torch.empty_like(col)
+    check(lib.gdmix_remap_i32(_tptr(col), _tptr(rank_of), C.c_int64(col.numel()), _tptr(out), _stream_ptr(stream)))
+    return out
+
+
 def fe_loss_grad_device(rows, opts, x, fg=None, stream=None, plan=None):
     """-> fg tensor [1 + D + has_intercept]: value then gradient (this rank's partial).  With a DeviceFePlan the
     atomics-free three-kernel path runs; without, the single-pass kernel with fp64 atomics."""
@@ -504,6 +546,46 @@ def fe_score_device(rows, opts, x, stream=None):
     cs = rows.c_struct()
     check(lib.gdmix_fe_score(C.byref(cs), C.byref(opts), _tptr(x), _tptr(logit), _tptr(per), _stream_ptr(stream)))
     return logit, per
+
+
+class DeviceLbfgs:
+    """gdmix_fe_lbfgs_*: the replicated L-BFGS-B state of the fixed-effect solve, resident on the device.  `x` and `fg`
+    are the caller's CUDA tensors (float64, [n] and [1 + n]); step() only enqueues kernels on the stream."""
+
+    DONE, NEED_FG, AGAIN = 0, 1, 2
+
+    def __init__(self, x, fg, opts):
+        n = x.numel()
+        assert fg.numel() == n + 1 and x.is_cuda and fg.is_cuda
+        self._keep = (x, fg)
+        self._h = lib.gdmix_fe_lbfgs_create(C.c_int64(n), C.cast(C.pointer(opts), C.c_void_p), _tptr(x), _tptr(fg))
+        if not self._h:
+            raise GdmixError(GDMIX_ERR_INVALID, lib.gdmix_last_error().decode())
+
+    def reset(self, stream=None):
+        check(lib.gdmix_fe_lbfgs_reset(self._h, _stream_ptr(stream)))
+
+    def step(self, stream=None):
+        check(lib.gdmix_fe_lbfgs_step(self._h, _stream_ptr(stream)))
+
+    def poll(self, stream=None):
+        """Synchronises the stream.  -> dict(task, nit, nfev, status, f)."""
+        task, nit, nfev, status, f = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_double()
+        check(lib.gdmix_fe_lbfgs_poll(self._h, _stream_ptr(stream), C.cast(C.byref(task), C.c_void_p),
+                                      C.cast(C.byref(nit), C.c_void_p), C.cast(C.byref(nfev), C.c_void_p),
+                                      C.cast(C.byref(status), C.c_void_p), C.cast(C.byref(f), C.c_void_p)))
+        return {"task": task.value, "nit": nit.value, "nfev": nfev.value, "status": status.value, "f": f.value}
+
+    def close(self):
+        if self._h:
+            lib.gdmix_fe_lbfgs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class HostLbfgs:
@@ -625,6 +707,15 @@ def avro_model_blocks(model_ids, coef, var, coef_ptr, feat_idx, has_intercept, t
     var = None if var is None else np.ascontiguousarray(var, dtype=np.float64)
     coef_ptr = np.ascontiguousarray(coef_ptr, dtype=np.int64)
     feat_idx = np.ascontiguousarray(feat_idx, dtype=np.int64)
+    hi = 1 if has_intercept else 0
+    n_coef = int(coef_ptr[-1]) if coef_ptr.size else 0
+    # the encoder indexes var and feat_idx with coefficient offsets and checks no lengths itself
+    if coef_ptr.shape[0] != len(model_ids) + 1 or coef.shape[0] < n_coef:
+        raise ValueError("coef / coef_ptr do not describe len(model_ids) models")
+    if var is not None and var.shape[0] != coef.shape[0]:
+        raise ValueError(f"{var.shape[0]} variances for {coef.shape[0]} coefficients")
+    if len(feature_names) and feat_idx.shape[0] != n_coef - hi * len(model_ids):
+        raise ValueError(f"{feat_idx.shape[0]} feature indices for {n_coef - hi * len(model_ids)} feature coefficients")
     if feat_idx.size == 0:
         feat_idx = np.zeros(1, np.int64)
     t = ModelTable(len(model_ids), _np_ptr(idc), _np_ptr(idp), model_class.encode("utf-8"), _np_ptr(coef), _np_ptr(var),

@@ -10,11 +10,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <new>
 #include <vector>
 
 #include "../../include/gdmix_b200.h"
 #include "aux_kernels.cuh"
 #include "host_lbfgs.h"
+#include "fe_lbfgs.cuh"
+#include "fe_plan.cuh"
 #include "seqex_parser.h"
 #include "avro_writer.h"
 #include "re_fast.cuh"
@@ -901,6 +904,44 @@ int gdmix_fe_loss_grad_planned(const gdmix_fe_rows *rows, const gdmix_fe_plan *p
     return GDMIX_OK;
 }
 
+int gdmix_fe_column_counts(const int32_t *col, int64_t nnz, int64_t n_features, int64_t *counts, void *stream)
+{
+    if ((!col && nnz > 0) || !counts || nnz < 0 || n_features <= 0) return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_fe_column_counts");
+    DeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *bad = nullptr;
+    CUDA_TRY(cudaMallocAsync((void **)&bad, 4, st));
+    CUDA_TRY(cudaMemsetAsync(bad, 0, 4, st));
+    CUDA_TRY(cudaMemsetAsync(counts, 0, 8 * (size_t)n_features, st));
+    if (nnz > 0) {
+        const int grid = (int)std::min<int64_t>((nnz + 255) / 256, (int64_t)dev.sm_count * 16);
+        gdmix::fe_count_columns_kernel<<<grid, 256, 0, st>>>(col, nnz, n_features, (unsigned long long *)counts, bad);
+        g_launches++;
+    }
+    int32_t hbad = 0;
+    CUDA_TRY(cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaFreeAsync(bad, st));
+    if (hbad) return fail(GDMIX_ERR_INVALID, "feature index outside [0, %lld)", (long long)n_features);
+    return GDMIX_OK;
+}
+
+int gdmix_remap_i32(const int32_t *in, const int32_t *map, int64_t n, int32_t *out, void *stream)
+{
+    if (n < 0 || (n > 0 && (!in || !map || !out))) return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_remap_i32");
+    if (n == 0) return GDMIX_OK;
+    DeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc) return rc;
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)dev.sm_count * 16);
+    gdmix::remap_i32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, map, n, out);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
 int gdmix_fe_hessian(const gdmix_fe_rows *rows, const gdmix_lr_opts *o, const double *x, int32_t mode, double *h,
                      void *stream)
 {
@@ -1557,6 +1598,103 @@ int gdmix_lbfgs_info(const gdmix_lbfgs *h, int32_t *nit, int32_t *nfev, int32_t 
 }
 
 void gdmix_lbfgs_destroy(gdmix_lbfgs *h) { delete h; }
+
+// ---- device-resident replicated L-BFGS of the fixed-effect solve (fe_lbfgs.cuh) ----------------------------------
+struct gdmix_fe_lbfgs {
+    gdmix::FeLbBuffers B{};
+    gdmix::FeLbState init{};
+    gdmix::FeLbStatus *status_dev = nullptr, *status_host = nullptr;
+    void *arena = nullptr;
+    int64_t n = 0;
+    int m = 0;
+};
+
+gdmix_fe_lbfgs *gdmix_fe_lbfgs_create(int64_t n, const gdmix_lr_opts *o, double *x_dev, double *fg_dev)
+{
+    if (n <= 0 || !o || o->m < 0 || o->m > gdmix::kLbMaxM || !x_dev || !fg_dev) {
+        fail(GDMIX_ERR_INVALID, "bad argument to gdmix_fe_lbfgs_create (n > 0, 0 <= m <= %d, device x and fg)", gdmix::kLbMaxM);
+        return nullptr;
+    }
+    gdmix_fe_lbfgs *h = new (std::nothrow) gdmix_fe_lbfgs();
+    if (!h) { fail(GDMIX_ERR_INVALID, "out of host memory"); return nullptr; }
+    h->n = n; h->m = o->m;
+    const int64_t nb = (n + gdmix::kLbBlock - 1) / gdmix::kLbBlock;
+    const int64_t mm = std::max(o->m, 1);
+    // one arena: state | status | d t r q | S Y | partials
+    const size_t off_state = 0, off_status = 1024, off_vec = 2048;
+    const size_t doubles = (size_t)(4 * n + 2 * mm * n + 4 * nb);
+    const size_t bytes = off_vec + 8 * doubles;
+    if (cudaMalloc(&h->arena, bytes) != cudaSuccess || cudaMallocHost((void **)&h->status_host, sizeof(gdmix::FeLbStatus)) != cudaSuccess) {
+        fail(GDMIX_ERR_CUDA, "gdmix_fe_lbfgs_create: cannot allocate %zu bytes of device memory", bytes);
+        if (h->arena) cudaFree(h->arena);
+        delete h;
+        return nullptr;
+    }
+    char *a = (char *)h->arena;
+    h->B.st = (gdmix::FeLbState *)(a + off_state);
+    h->status_dev = (gdmix::FeLbStatus *)(a + off_status);
+    double *v = (double *)(a + off_vec);
+    h->B.x = x_dev; h->B.fg = fg_dev;
+    h->B.d = v; h->B.t = v + n; h->B.r = v + 2 * n; h->B.q = v + 3 * n;
+    h->B.S = v + 4 * n; h->B.Y = h->B.S + mm * n;
+    h->B.part = h->B.Y + mm * n;
+    h->B.nb = (int32_t)nb;
+    memset(&h->init, 0, sizeof(h->init));
+    h->init.n = n; h->init.m = o->m; h->init.max_iter = o->max_iter; h->init.max_ls = o->max_ls;
+    h->init.max_fun = o->max_fun; h->init.factr = o->factr; h->init.pgtol = o->pgtol; h->init.theta = 1.0;
+    return h;
+}
+
+int gdmix_fe_lbfgs_reset(gdmix_fe_lbfgs *h, void *stream)
+{
+    if (!h) return fail(GDMIX_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaMemcpyAsync(h->B.st, &h->init, sizeof(h->init), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return GDMIX_OK;
+}
+
+int gdmix_fe_lbfgs_step(gdmix_fe_lbfgs *h, void *stream)
+{
+    if (!h) return fail(GDMIX_ERR_INVALID, "null handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = h->B.nb, T = gdmix::kLbThreads;
+    gdmix::lb_dots_kernel<<<nb, T, 0, st>>>(h->B);
+    gdmix::lb_decide1_kernel<<<1, 32, 0, st>>>(h->B);
+    gdmix::lb_pair_kernel<<<nb, T, 0, st>>>(h->B);
+    gdmix::lb_decide2_kernel<<<1, 32, 0, st>>>(h->B);
+    gdmix::lb_store_kernel<<<nb, T, 0, st>>>(h->B);
+    for (int j = 0; j < h->m; j++) gdmix::lb_loop1_kernel<<<nb, T, 0, st>>>(h->B, j);
+    gdmix::lb_scale_kernel<<<nb, T, 0, st>>>(h->B);
+    for (int k = 0; k < h->m; k++) gdmix::lb_loop2_kernel<<<nb, T, 0, st>>>(h->B, k);
+    gdmix::lb_direction_kernel<<<nb, T, 0, st>>>(h->B);
+    gdmix::lb_decide3_kernel<<<1, 32, 0, st>>>(h->B, h->status_dev);
+    gdmix::lb_newx_kernel<<<nb, T, 0, st>>>(h->B);
+    g_launches += 9 + 2 * h->m;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
+int gdmix_fe_lbfgs_poll(gdmix_fe_lbfgs *h, void *stream, int32_t *task, int32_t *nit, int32_t *nfev, int32_t *status,
+                        double *f)
+{
+    if (!h) return fail(GDMIX_ERR_INVALID, "null handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(h->status_host, h->status_dev, sizeof(gdmix::FeLbStatus), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (task) *task = h->status_host->task;
+    if (nit) *nit = h->status_host->nit;
+    if (nfev) *nfev = h->status_host->nfev;
+    if (status) *status = h->status_host->status;
+    if (f) *f = h->status_host->f;
+    return GDMIX_OK;
+}
+
+void gdmix_fe_lbfgs_destroy(gdmix_fe_lbfgs *h)
+{
+    if (!h) return;
+    if (h->arena) cudaFree(h->arena);
+    if (h->status_host) cudaFreeHost(h->status_host);
+    delete h;
+}
 
 int gdmix_partition_ids(const uint16_t *units, const int64_t *id_ptr, int64_t n_ids, int32_t num_partitions,
                         int32_t *hash_out, int32_t *partition_out)

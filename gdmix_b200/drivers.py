@@ -35,6 +35,45 @@ def _cluster_from_env():
     return constants.WORKER, 0, 1, False
 
 
+def torch_env_from_tf_config(env=None):
+    """TF_CONFIG -> the rendezvous variables torch.distributed reads, for jobs launched the reference's way (one
+    process per worker with TF_CONFIG only, fixed_effect_driver.py:24-58): worker 0's "host:port" is the
+    rendezvous address, task.index the rank, the number of workers the world size.  Variables that are already set
+    (torch.distributed.run) win.  -> dict of the values derived (also written into `env`)."""
+    env = os.environ if env is None else env
+    tf_config = env.get(constants.TF_CONFIG)
+    if not tf_config:
+        return {}
+    cfg = json.loads(tf_config)
+    workers = cfg.get("cluster", {}).get(constants.WORKER, [])
+    task = cfg.get("task", {})
+    if not workers or task.get("index") is None:
+        return {}
+    host, _, port = str(workers[0]).rpartition(":")
+    derived = {"MASTER_ADDR": host or str(workers[0]), "MASTER_PORT": port or "29500",
+               "RANK": str(int(task["index"])), "WORLD_SIZE": str(len(workers))}
+    out = {}
+    for k, v in derived.items():
+        if k not in env:
+            env[k] = v
+            out[k] = v
+    return out
+
+
+def select_device(task_index):
+    """One process per GPU: LOCAL_RANK when torch.distributed.run set it, else task index modulo the visible GPUs.
+    Without this every worker of a multi-worker job lands on cuda:0 (NCCL then refuses the duplicate GPU for the fixed
+    effect and the random-effect workers serialise on one device)."""
+    import torch
+    if not torch.cuda.is_available():
+        return None
+    n = torch.cuda.device_count()
+    local = os.environ.get("LOCAL_RANK")
+    idx = int(local) if local is not None else int(task_index or 0) % max(n, 1)
+    torch.cuda.set_device(idx)
+    return idx
+
+
 class Driver(abc.ABC):
     """driver.py:13-216."""
 
@@ -145,6 +184,7 @@ class RandomEffectDriver(Driver):
             if num_workers < 1:
                 raise Exception("No worker found")
             os.environ.pop(constants.TF_CONFIG, None)  # random effect runs in local mode
+        select_device(task_index)
         return {constants.TASK_TYPE: task_type, constants.TASK_INDEX: task_index, constants.CLUSTER_SPEC: None,
                 constants.NUM_WORKERS: num_workers, constants.NUM_SHARDS: 1, constants.SHARD_INDEX: 0,
                 constants.IS_CHIEF: task_index == 0}
@@ -173,6 +213,9 @@ class FixedEffectDriver(Driver):
         task_type, task_index, num_workers, from_tf_config = _cluster_from_env()
         if from_tf_config and (task_type is None or task_index is None):
             raise Exception("No job name found")
+        if from_tf_config and num_workers > 1:
+            torch_env_from_tf_config()     # RANK / WORLD_SIZE / MASTER_* for the NCCL rendezvous of the all-reduce
+        select_device(task_index)
         return {constants.TASK_TYPE: task_type, constants.TASK_INDEX: task_index, constants.CLUSTER_SPEC: None,
                 constants.NUM_WORKERS: num_workers, constants.NUM_SHARDS: num_workers,
                 constants.SHARD_INDEX: task_index, constants.IS_CHIEF: task_index == 0}

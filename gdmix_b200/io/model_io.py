@@ -41,6 +41,32 @@ BAYESIAN_LINEAR_MODEL_SCHEMA = {
 LOGISTIC_MODEL_CLASS = "com.linkedin.photon.ml.supervised.classification.LogisticRegressionModel"
 
 
+def _field_shapes(schema):
+    """(name, type) of every top-level field with named types reduced to their names and docs / defaults dropped."""
+    def shape(t):
+        if isinstance(t, list):
+            return [shape(x) for x in t]
+        if isinstance(t, dict):
+            if t.get("type") == "array":
+                return {"array": shape(t["items"])}
+            if t.get("type") == "record":
+                return {"record": t.get("name"), "fields": [(f["name"], shape(f["type"])) for f in t["fields"]]}
+            return shape(t.get("type"))
+        return str(t).rsplit(".", 1)[-1]
+    return [(f["name"], shape(f["type"])) for f in schema.get("fields", [])]
+
+
+def check_model_schema(writer_schema, where=""):
+    """The library's block decoder (gdmix_avro_model_decode) is laid out for BAYESIAN_LINEAR_MODEL_SCHEMA: a file
+    whose writer schema orders or types its fields differently would decode as garbage, so it is refused.
+    (fastavro in the reference follows the writer schema; files the reference or this package wrote match.)"""
+    if isinstance(writer_schema, (bytes, str)):
+        writer_schema = json.loads(writer_schema)
+    if _field_shapes(writer_schema) != _field_shapes(BAYESIAN_LINEAR_MODEL_SCHEMA):
+        raise ValueError(f"{where}: writer schema is not BayesianLinearModelAvro as Photon-ML / GDMix write it "
+                         f"(fields {[f.get('name') for f in writer_schema.get('fields', [])]})")
+
+
 def read_feature_list(feature_file):
     """CSV rows ``name,term``; the row number is the global feature index (intercept not included)."""
     result = []

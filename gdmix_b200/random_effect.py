@@ -212,7 +212,15 @@ class RandomEffectLRLBFGSModel(Model):
             keep = hi if feature_file is None else mean.shape[0]
             means.append(mean[:keep])
             if with_variance:
-                variances.append(np.asarray(variance, dtype=np.float64).ravel()[:keep])
+                if variance is None:
+                    # a prior-only entity loaded from a model file without variances: the reference fails here too
+                    # (zip(means, None) in gen_one_avro_model, io_utils.py:102-160) -- never write misaligned arrays
+                    raise TypeError(f"model {entity_id!r} has no variances but random_effect_variance_mode="
+                                    f"{self.model_params.random_effect_variance_mode} asks for them")
+                variance = np.asarray(variance, dtype=np.float64).ravel()
+                if variance.shape[0] != mean.shape[0]:
+                    raise ValueError(f"model {entity_id!r}: {variance.shape[0]} variances for {mean.shape[0]} means")
+                variances.append(variance[:keep])
             if feature_file is not None:
                 indices.append(np.asarray(unique_global_indices, dtype=np.int64).ravel())
         cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
@@ -234,14 +242,15 @@ class RandomEffectLRLBFGSModel(Model):
 
     def _load_weights_native(self, model_file):
         """entity id -> TrainingResult, decoded block by block by the library (gdmix_avro_model_decode); the same
-        dict _convert_avro_model_record_to_sparse_coefficients builds one Python record at a time."""
+        dict the reference builds one fastavro record at a time (random_effect_lr_lbfgs_model.py:262-309)."""
         from .io import avro
         feature_list = model_io.read_feature_list(self.feature_file) if self.feature_file else []
         fmap = capi.FeatureMap([f[0] for f in feature_list], [f[1] for f in feature_list], constants.INTERCEPT)
         hi = 1 if self.has_intercept else 0
         out = {}
         try:
-            _, blocks = avro.read_blocks(model_file)
+            schema, blocks = avro.read_blocks(model_file)
+            model_io.check_model_schema(schema, model_file)   # the block decoder is laid out for this schema only
             for n, data in blocks:
                 try:
                     d = fmap.decode_models(data, n)
@@ -252,13 +261,15 @@ class RandomEffectLRLBFGSModel(Model):
                 for m in range(n):
                     a, b = int(mp[m]), int(mp[m + 1])
                     feat = d["mean_feat"][a:b]
-                    if hi:
-                        assert b > a and feat[0] == -1, "the first mean of a model with intercept is the intercept"
-                    assert not (feat[hi:] < 0).any(), "an intercept among the feature coefficients"
+                    if hi and not (b > a and feat[0] == -1):
+                        raise ValueError(f"{model_file}: the first mean of a model with intercept must be the intercept")
+                    if (feat[hi:] < 0).any():
+                        raise ValueError(f"{model_file}: an intercept among the feature coefficients")
                     theta, idx = d["mean_val"][a:b].copy(), feat[hi:].copy()
                     if self.feature_file is None:
                         # intercept-only model: one dummy feature
-                        assert idx.size == 0
+                        if idx.size:
+                            raise ValueError(f"{model_file}: feature coefficients in an intercept-only model")
                         theta, idx = np.append(theta, 0.0), np.zeros(1, np.int64)
                     var = d["var_val"][a:b].copy() if d["has_var"][m] else None
                     out[ids[ip[m]:ip[m + 1]].decode("utf-8")] = TrainingResult(theta=theta, variance=var,
@@ -266,30 +277,3 @@ class RandomEffectLRLBFGSModel(Model):
         finally:
             fmap.close()
         return out
-
-    @staticmethod
-    def _convert_avro_model_record_to_sparse_coefficients(has_intercept, model_record, feature2global_id):
-        model_id = model_record["modelId"]
-        coefficients, unique_global_indices, variances = [], [], []
-        for idx, ntv in enumerate(model_record["means"]):
-            coefficients.append(np.float64(ntv["value"]))
-            if has_intercept and idx == 0:
-                assert ntv["name"] == constants.INTERCEPT and ntv["term"] == ""
-            else:
-                unique_global_indices.append(feature2global_id[(ntv["name"], ntv["term"])])
-        if model_record.get("variances"):
-            for idx, ntv in enumerate(model_record["variances"]):
-                variances.append(np.float64(ntv["value"]))
-                if has_intercept and idx == 0:
-                    assert ntv["name"] == constants.INTERCEPT and ntv["term"] == ""
-                else:
-                    off = 1 if has_intercept else 0
-                    assert unique_global_indices[idx - off] == feature2global_id[(ntv["name"], ntv["term"])]
-        if feature2global_id is None:
-            # intercept-only model: one dummy feature
-            assert len(unique_global_indices) == 0
-            coefficients.append(np.float64(0.0))
-            unique_global_indices.append(0)
-        return model_id, TrainingResult(theta=np.array(coefficients),
-                                        variance=np.array(variances) if variances else None,
-                                        unique_global_indices=np.array(unique_global_indices, dtype=np.int64))

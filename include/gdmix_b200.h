@@ -238,6 +238,12 @@ GDMIX_API int gdmix_fe_rows_grid(const gdmix_fe_rows *rows, int32_t *grid);
 GDMIX_API int gdmix_fe_loss_grad_planned(const gdmix_fe_rows *rows, const gdmix_fe_plan *plan,
                                          const gdmix_lr_opts *opts, const double *x, double *fg, void *stream);
 
+/* Set-up helpers of the planned objective (device pointers; once per training run, the shard does not change between
+ * the evaluations of an L-BFGS run): non-zeros per feature (synchronises the stream; an index outside [0, n_features)
+ * is an error), and out[i] = map[in[i]] (renumbering the shard's columns by falling frequency). */
+GDMIX_API int gdmix_fe_column_counts(const int32_t *col, int64_t nnz, int64_t n_features, int64_t *counts, void *stream);
+GDMIX_API int gdmix_remap_i32(const int32_t *in, const int32_t *map, int64_t n, int32_t *out, void *stream);
+
 /* Hessian of the logistic loss over this rank's rows at x, X1^T diag(w rho (1-rho)) X1 with the intercept column
  * LAST -- the accumulator H of _scoring_fn (fixed_effect_lr_lbfgs_model.py:271-296; the reference keeps it in
  * fp32, here fp64).  mode GDMIX_VARIANCE_SIMPLE: h[D+hi] = diagonal; GDMIX_VARIANCE_FULL: h[(D+hi)^2] row-major.
@@ -409,6 +415,27 @@ GDMIX_API gdmix_lbfgs *gdmix_lbfgs_create(int64_t n, const gdmix_lr_opts *opts);
 GDMIX_API int gdmix_lbfgs_iterate(gdmix_lbfgs *h, double *x, double f, const double *g);
 GDMIX_API int gdmix_lbfgs_info(const gdmix_lbfgs *h, int32_t *nit, int32_t *nfev, int32_t *status, double *f);
 GDMIX_API void gdmix_lbfgs_destroy(gdmix_lbfgs *h);
+
+/* The same replicated solver with its state RESIDENT ON THE DEVICE (x, gradient, direction, previous iterate, the m
+ * curvature pairs): what fixed_effect_lr_lbfgs_model.py:635-643 keeps in every worker's scipy instance.  An
+ * evaluation then never leaves the GPU: gdmix_fe_loss_grad_planned -> all-reduce of fg on the same stream ->
+ * gdmix_fe_lbfgs_step -> next evaluation; only a 24-byte status record crosses to the host (gdmix_fe_lbfgs_poll).
+ *   x_dev[n], fg_dev[1 + n]   caller-owned device arrays: the iterate (start point in, solution out) and the
+ *                             all-reduced [value | gradient] at x_dev
+ *   _reset   (re)starts a solve from the x_dev contents;  enqueue-only
+ *   _step    consumes fg_dev at x_dev and writes the next trial point into x_dev (or finishes); enqueue-only, a fixed
+ *            sequence of 9 + 2m launches whatever the branch taken, so the caller may capture it in a CUDA graph
+ *   _poll    synchronises the stream; *task = 1: evaluate at x_dev and step again, 0: finished, 2: step again without
+ *            evaluating (restart from steepest descent after a failed line search); nit / nfev / status / f as
+ *            gdmix_lbfgs_info
+ * Every inner product has a fixed summation order, so ranks fed the same reduced fg keep bit-identical state. */
+typedef struct gdmix_fe_lbfgs gdmix_fe_lbfgs;
+GDMIX_API gdmix_fe_lbfgs *gdmix_fe_lbfgs_create(int64_t n, const gdmix_lr_opts *opts, double *x_dev, double *fg_dev);
+GDMIX_API int gdmix_fe_lbfgs_reset(gdmix_fe_lbfgs *h, void *stream);
+GDMIX_API int gdmix_fe_lbfgs_step(gdmix_fe_lbfgs *h, void *stream);
+GDMIX_API int gdmix_fe_lbfgs_poll(gdmix_fe_lbfgs *h, void *stream, int32_t *task, int32_t *nit, int32_t *nfev,
+                                  int32_t *status, double *f);
+GDMIX_API void gdmix_fe_lbfgs_destroy(gdmix_fe_lbfgs *h);
 
 /* Launch plan of this thread's most recent gdmix_re_fit / gdmix_re_loss_grad (diagnostics, tests, bench):
  * out8 = { fast kernel used, threads per entity, features per thread (fast) , CTAs per SM,

@@ -100,6 +100,8 @@ def test_random_effect_driver_requires_partition_list_and_job_name(job, monkeypa
 
 
 def test_fixed_effect_driver_context(job, monkeypatch):
+    for k in ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):   # the driver derives these from TF_CONFIG:
+        monkeypatch.setenv(k, "x"); monkeypatch.delenv(k)            # have monkeypatch restore them afterwards
     monkeypatch.setenv(constants.TF_CONFIG, _tf_config(3))
     drv = FixedEffectDriver(_params(job, constants.FIXED_EFFECT), RecordingModel(job))
     ctx = drv.execution_context
@@ -108,7 +110,9 @@ def test_fixed_effect_driver_context(job, monkeypatch):
     assert drv._get_partition_list() == [3]
     assert drv._anchor_directory("/x/y", 3) == "/x/y"
     monkeypatch.delenv(constants.TF_CONFIG)
+    assert os.environ["RANK"] == "3" and os.environ["WORLD_SIZE"] == "5" and os.environ["MASTER_ADDR"] == "node0"
     monkeypatch.delenv("RANK", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
     local = FixedEffectDriver(_params(job, constants.FIXED_EFFECT), RecordingModel(job)).execution_context
     assert (local[constants.TASK_INDEX], local[constants.NUM_WORKERS], local[constants.IS_CHIEF]) == (0, 1, True)
 
@@ -132,3 +136,26 @@ def test_factory_rejects_what_is_out_of_scope(job):
                                         model_type=constants.LINEAR_REGRESSION, partition_list_file="p"), [])
     with pytest.raises(Exception):
         DriverFactory.get_driver(Params(uid_column_name="uid", label_column_name="y", model_type=constants.DETEXT), [])
+
+
+def test_torch_env_is_derived_from_tf_config():
+    """A fixed-effect job launched the reference's way (TF_CONFIG only) gets the rendezvous variables
+    torch.distributed needs; variables torch.distributed.run already set are left alone."""
+    from gdmix_b200.drivers import torch_env_from_tf_config
+    env = {constants.TF_CONFIG: _tf_config(3)}
+    got = torch_env_from_tf_config(env)
+    assert got["RANK"] == "3" and got["WORLD_SIZE"] == "5" and env["MASTER_ADDR"] and int(env["MASTER_PORT"]) > 0
+    env2 = {constants.TF_CONFIG: _tf_config(2), "RANK": "7", "WORLD_SIZE": "9", "MASTER_ADDR": "127.0.0.1",
+            "MASTER_PORT": "1234"}
+    assert torch_env_from_tf_config(env2) == {} and env2["RANK"] == "7"
+    assert torch_env_from_tf_config({}) == {}
+
+
+def test_select_device_without_a_gpu_is_a_no_op(monkeypatch):
+    import torch
+    from gdmix_b200.drivers import select_device
+    if not torch.cuda.is_available():
+        assert select_device(3) is None
+    else:
+        monkeypatch.setenv("LOCAL_RANK", "0")
+        assert select_device(3) == 0

@@ -173,3 +173,57 @@ def test_solver_frequency_ranking_is_invisible_to_the_caller():
     xb, ib = plain.fit()
     assert (ia["nit"], ia["nfev"]) == (ib["nit"], ib["nfev"])
     np.testing.assert_allclose(xa, xb, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("c", FE_CASES, ids=[c["name"] for c in FE_CASES])
+def test_device_lbfgs_retraces_the_host_state_machine(c):
+    """gdmix_fe_lbfgs_* (solver state in HBM) against gdmix_lbfgs_* (the same state machine on the host) on every
+    golden fixed-effect case: same iterations, evaluations, stop status; coefficients to rounding."""
+    dev = FixedEffectSolver(_rows(c), _opts(c, capi), solver="device")
+    host = FixedEffectSolver(_rows(c), _opts(c, capi), solver="host")
+    xd, idv = dev.fit(FE_ARR[c["key"] + "_x0"])
+    xh, ih = host.fit(FE_ARR[c["key"] + "_x0"])
+    assert (idv["nit"], idv["nfev"], idv["status"]) == (ih["nit"], ih["nfev"], ih["status"])
+    np.testing.assert_allclose(xd, xh, rtol=1e-10, atol=1e-12)
+    assert abs(idv["f"] - ih["f"]) <= 1e-12 * abs(ih["f"])
+
+
+def _zipf_shard(rng, n, D, k):
+    rowptr = np.arange(n + 1, dtype=np.int64) * k
+    col = np.minimum((D ** rng.random(n * k) - 1).astype(np.int32), D - 1)
+    val = rng.standard_normal(n * k).astype(np.float32)
+    xs = rng.standard_normal(D + 1) * 0.3
+    z = (val.reshape(n, k) * xs[col.reshape(n, k)]).sum(1) + xs[-1]
+    y = (rng.random(n) < 1 / (1 + np.exp(-z))).astype(np.float32)
+    return rowptr, col, val, y
+
+
+@pytest.mark.parametrize("m,max_iter", [(10, 25), (3, 12), (0, 5)])
+def test_device_lbfgs_on_a_ranked_shard(m, max_iter):
+    """More features than the rows kernel keeps in shared memory (the solver then works in falling-frequency feature
+    order), several blocks of solver vectors, memory wrap-around (m = 3), plain gradient descent (m = 0): device and
+    host solvers agree, bitwise reproducible run to run, coefficients come back in the caller's feature order."""
+    rng = np.random.default_rng(17)
+    n, D, k = 30000, capi.FE_HEAD + 3000, 16
+    rowptr, col, val, y = _zipf_shard(rng, n, D, k)
+    rows = capi.DeviceFeRows(rowptr, col, val, y, None, None, D)
+    opts = capi.make_opts(l2=1.0, regularize_bias=True, has_intercept=True, m=m, max_iter=max_iter)
+    xd, idv = FixedEffectSolver(rows, opts, solver="device").fit()
+    xd2, idv2 = FixedEffectSolver(rows, opts, solver="device").fit()
+    xh, ih = FixedEffectSolver(rows, opts, solver="host").fit()
+    np.testing.assert_array_equal(xd, xd2)
+    assert (idv["nit"], idv["nfev"], idv["status"]) == (ih["nit"], ih["nfev"], ih["status"])
+    np.testing.assert_allclose(xd, xh, rtol=1e-8, atol=1e-11)
+    # the objective at the returned point, recomputed by the oracle in the CALLER's feature order
+    ob = O.FeBlock(n, D, rowptr, col, val, y, np.ones(n, np.float32), np.zeros(n, np.float32))
+    f_o, _ = O.fe_loss_grad(ob, O.make_opts(l2=1.0, regularize_bias=True, has_intercept=True), xd)
+    assert abs(f_o - idv["f"]) <= 1e-10 * abs(f_o)
+
+
+def test_device_lbfgs_stops_at_once_on_a_stationary_start():
+    c = FE_CASES[0]
+    solver = FixedEffectSolver(_rows(c), _opts(c, capi))
+    x, info = solver.fit(FE_ARR[c["key"] + "_theta"])
+    x2, info2 = FixedEffectSolver(_rows(c), _opts(c, capi), solver="host").fit(FE_ARR[c["key"] + "_theta"])
+    assert (info["nit"], info["nfev"], info["status"]) == (info2["nit"], info2["nfev"], info2["status"])
+    np.testing.assert_allclose(x, x2, rtol=1e-10, atol=1e-12)

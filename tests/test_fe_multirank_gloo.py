@@ -47,11 +47,26 @@ def _worker(rank, world, port, out_dir):
               factr=c["factr"])
     oo, po = O.make_opts(**kw), capi.make_opts(**kw)
 
-    def local_eval(x):
-        f, g = O.fe_loss_grad(rows, oo, x)
-        return np.concatenate([[f], g])
+    import torch
 
-    solver = FixedEffectSolver(None, po, n_features=c["D"], local_eval=local_eval)
+    class CpuEvalSolver(FixedEffectSolver):
+        """Test seam: this rank's partial [value | gradient] comes from the CPU oracle instead of the CUDA passes, so
+        that the multi-rank plumbing of the product solver (one all-reduce of fg per evaluation, replicated solver
+        state) runs on gloo without a GPU.  Lives here, not in the package: the product has no CPU path."""
+
+        def _setup(self):
+            pass
+
+        def loss_grad(self, x):
+            self.nfev += 1
+            f, g = O.fe_loss_grad(rows, oo, x)
+            fg = torch.from_numpy(np.concatenate([[f], g]))
+            if self.dist and self.world > 1:
+                self.dist.all_reduce(fg, group=self.group)
+            fg = fg.numpy()
+            return float(fg[0]), fg[1:].copy()
+
+    solver = CpuEvalSolver(None, po, n_features=c["D"], solver="host")
     x, info = solver.fit(arr[k + "_x0"])
     np.save(os.path.join(out_dir, f"x{rank}.npy"), x)
     np.save(os.path.join(out_dir, f"info{rank}.npy"), np.array([info["nit"], info["nfev"], info["status"]]))

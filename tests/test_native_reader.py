@@ -303,12 +303,32 @@ def test_native_model_writer_is_byte_identical_to_the_python_writer(tmp_path, ha
     assert (back[3]["variances"] is None) == (not with_variance)
 
 
+def _record_to_sparse_coefficients(has_intercept, rec, feature2global_id):
+    """CHECKER (test infrastructure): one decoded BayesianLinearModelAvro record -> (modelId, TrainingResult), the
+    per-record conversion the reference's _load_weights does (random_effect_lr_lbfgs_model.py:277-309)."""
+    from gdmix_b200.random_effect import TrainingResult
+    hi = 1 if has_intercept else 0
+    means = rec["means"]
+    if hi:
+        assert (means[0]["name"], means[0]["term"]) == ("(INTERCEPT)", "")
+    theta = [np.float64(m["value"]) for m in means]
+    idx = [feature2global_id[(m["name"], m["term"])] for m in means[hi:]]
+    var = None
+    if rec.get("variances"):
+        var = np.array([np.float64(v["value"]) for v in rec["variances"]])
+        assert [feature2global_id[(v["name"], v["term"])] for v in rec["variances"][hi:]] == idx
+    if feature2global_id is None:   # intercept-only model: one dummy feature
+        assert not idx
+        theta.append(np.float64(0.0)); idx.append(0)
+    return rec["modelId"], TrainingResult(np.array(theta), var, np.array(idx, dtype=np.int64))
+
+
 @pytest.mark.parametrize("has_intercept", [True, False])
 @pytest.mark.parametrize("with_variance", [True, False])
 @pytest.mark.parametrize("codec", ["null", "deflate"])
 def test_native_model_reader_matches_the_python_conversion(tmp_path, has_intercept, with_variance, codec):
     """RandomEffectLRLBFGSModel._load_weights (gdmix_avro_model_decode per container block) against
-    _convert_avro_model_record_to_sparse_coefficients over avro.read_records, on files written by the Python writer
+    a per-record Python conversion (the checker above) over avro.read_records, on files written by the Python writer
     (both codecs) -- same entity ids, coefficients, variances, feature indices, dtypes."""
     from types import SimpleNamespace
     from gdmix_b200.io import avro, model_io
@@ -333,7 +353,7 @@ def test_native_model_reader_matches_the_python_conversion(tmp_path, has_interce
     fake = SimpleNamespace(feature_file=str(ff), has_intercept=has_intercept)
     got = M._load_weights_native(fake, path)
     fmap = model_io.get_feature_map(str(ff))
-    want = dict(M._convert_avro_model_record_to_sparse_coefficients(has_intercept, r, fmap) for r in avro.read_records(path))
+    want = dict(_record_to_sparse_coefficients(has_intercept, r, fmap) for r in avro.read_records(path))
     assert list(got.keys()) == list(want.keys())
     for k in want:
         np.testing.assert_array_equal(got[k].theta, want[k].theta)
@@ -381,3 +401,41 @@ def test_vectorised_warm_start_equals_the_per_entity_loop(has_intercept):
     assert a[1].sum() == E // 2 and np.count_nonzero(a[0]) > 0
     z = ingest.warm_start_theta(hb, uniq_ptr, uniq_global, ids, {}, has_intercept)
     assert not z[0].any() and not z[1].any()
+
+
+def test_model_file_with_another_schema_is_refused(tmp_path):
+    """The block decoder is laid out for BayesianLinearModelAvro as Photon-ML / GDMix write it: a file whose writer
+    schema orders its fields differently must be refused, not decoded as garbage (fastavro would follow the schema)."""
+    import copy
+    from types import SimpleNamespace
+    from gdmix_b200.io import avro, model_io
+    from gdmix_b200.random_effect import RandomEffectLRLBFGSModel as M
+    schema = copy.deepcopy(model_io.BAYESIAN_LINEAR_MODEL_SCHEMA)
+    schema["fields"][0], schema["fields"][1] = schema["fields"][1], schema["fields"][0]
+    rec = {"modelId": "7", "modelClass": None, "means": [{"name": "(INTERCEPT)", "term": "", "value": 1.0}],
+           "variances": None, "lossFunction": None}
+    path = str(tmp_path / "m.avro")
+    avro.write_records(path, schema, [rec])
+    ff = tmp_path / "f.csv"
+    ff.write_text("a,\n", encoding="utf-8")
+    with pytest.raises(ValueError, match="writer schema"):
+        M._load_weights_native(SimpleNamespace(feature_file=str(ff), has_intercept=True), path)
+    model_io.check_model_schema(model_io.BAYESIAN_LINEAR_MODEL_SCHEMA)   # the package's own schema passes
+
+
+def test_saving_a_prior_model_without_variances_under_a_variance_mode_raises(tmp_path):
+    """A model loaded from a file written without variances cannot be re-saved with variances: the reference fails
+    (TypeError) rather than writing misaligned arrays; so does _save_model."""
+    from types import SimpleNamespace
+    from gdmix_b200.random_effect import RandomEffectLRLBFGSModel as M, TrainingResult
+    ff = tmp_path / "f.csv"
+    ff.write_text("a,\nb,\n", encoding="utf-8")
+    fake = SimpleNamespace(model_params=SimpleNamespace(random_effect_variance_mode="SIMPLE", sparsity_threshold=1e-4),
+                           has_intercept=True)
+    coeffs = {"1": TrainingResult(np.array([0.5, 1.0]), np.array([0.1, 0.2]), np.array([0])),
+              "2": TrainingResult(np.array([0.5, 1.0]), None, np.array([1]))}
+    with pytest.raises(TypeError, match="no variances"):
+        M._save_model(fake, str(tmp_path / "out.avro"), coeffs, 2, str(ff))
+    bad = {"1": TrainingResult(np.array([0.5, 1.0]), np.array([0.1]), np.array([0]))}
+    with pytest.raises(ValueError, match="variances for"):
+        M._save_model(fake, str(tmp_path / "out.avro"), bad, 2, str(ff))
