@@ -3,20 +3,29 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--entities E]
 
-Ours: a "step" is one pass of the hot path (gdmix_re_fit: stage + L-BFGS-B solve of every entity) over the
-workload BASELINE.json configs[1] names -- 1M synthetic entities x 128 samples x 256 local features, 32 nnz per
-sample, l2=1, cold start -- resident in HBM (38 GB, far larger than L2).  `value` = entities solved per second
-with device-resident inputs, timed with CUDA events on the launching stream, max over ranks.  `e2e` = the same
-metric through the host-buffer C-ABI call the plugin classes make (gdmix_re_fit_host): pinned host CSR in,
-coefficients out, H2D and D2H inside the timed region.  For N>1 every rank solves its own 1M entities (entities
-shard with no data-path collective: weak scaling); launched by torch.distributed.run, NCCL only for the barrier
-and the max-over-ranks.
+Ours.  Headline (`value`, `roofline`, `e2e`): a "step" is one pass of the hot path (gdmix_re_fit: stage + L-BFGS-B
+solve of every entity) over the workload BASELINE.json configs[1] names -- 1M synthetic entities x 128 samples x 256
+local features, 32 nnz per sample, l2=1, cold start -- resident in HBM (38 GB, far larger than L2).  `value` =
+entities solved per second with device-resident inputs, timed with CUDA events on the launching stream, max over
+ranks.  `e2e` = the same metric through the host-buffer C-ABI call the plugin classes make (gdmix_re_fit_host):
+pinned host CSR in, coefficients out, H2D and D2H inside the timed region, the same number of entities per rank at
+every N.  For N>1 every rank solves its own entities (they shard with no data-path collective: weak scaling);
+launched by torch.distributed.run, NCCL only for the barrier and the max-over-ranks.
 
-Reference arm (--impl reference): the reference's CPU path restated with the same scipy/numpy calls
-(oracle/scipy_port.py; /root/reference cannot travel to the GPU box) on all host cores, on a bounded sample of
-the same workload per step.
+The same line carries, outside the headline's timed region:
+  parity       entities sampled from the TIMED device batch, copied to the host and solved by the CPU oracle
+               (oracle/lr_oracle.c): fraction within 1e-5 relative, max deviation, iteration counts
+  sub          the other configurations of BASELINE.json at one rank's share: `fe` (configs[2]: fixed-effect
+               objective + NCCL all-reduce + device-resident L-BFGS at N ranks), `sweep` (configs[4]), `small`
+               (configs[3] per-user shape), `chain` (configs[3] FE -> per-user -> per-item)
+  cpu_baseline the reference's CPU path on the host cores over the first entities of the timed batch (N=1)
+
+Reference arm (--impl reference): the reference's own BinaryLogisticRegressionTrainer (staged under oracle/_ref by
+oracle/build_ref.py; oracle/scipy_port.py where that is absent) on all host cores, on a bounded sample of the same
+workload per step.  It imports nothing of gdmix_b200.
 """
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
@@ -87,81 +96,246 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def _oracle_batch_dict(hb):
-    return {"ent_rowptr": hb.ent_rowptr, "rowptr": hb.rowptr, "col": hb.col, "val": hb.val, "y": hb.label,
-            "w": hb.weight if hb.weight is not None else np.ones(hb.n_rows, np.float32),
-            "off": hb.offset if hb.offset is not None else np.zeros(hb.n_rows, np.float32), "theta_ptr": hb.theta_ptr}
-
-
-def cpu_baseline(sample_entities):
-    """Reference CPU path (scipy port) on all host cores over a bounded sample of the workload, plus the plain-C
-    oracle port on one core for scale."""
-    from gdmix_b200.synthetic import make_batch
-    from oracle import oracle as O
-    from oracle import scipy_port as SP
-    kw = dict(l2=WORKLOAD["l2"], regularize_bias=False, has_intercept=True)
-    if sample_entities <= 0:
-        # size the sample for ~15 s of CPU work on this box: probe the rate on a small slice first
-        probe = make_batch(64 * (os.cpu_count() or 1), WORKLOAD["n"], WORKLOAD["d"], WORKLOAD["k"],
-                           seed=WORKLOAD["seed"])
-        rate = SP.timed_fit(_oracle_batch_dict(probe), probe.n_entities, **kw)["entities_per_sec"]
-        sample_entities = int(min(max(rate * 15.0, 2048), 400000))
-    hb = make_batch(sample_entities, WORKLOAD["n"], WORKLOAD["d"], WORKLOAD["k"], seed=WORKLOAD["seed"])
-    b = _oracle_batch_dict(hb)
-    r = SP.timed_fit(b, sample_entities, **kw)
-    nc = min(sample_entities, 2000)
-    t0 = time.perf_counter()
-    O.re_fit_batch(b, O.make_opts(l2=WORKLOAD["l2"]), e0=0, e1=nc)
-    c1 = nc / (time.perf_counter() - t0)
-    return {"value": r["entities_per_sec"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-            "sample": f"first {sample_entities} entities of the c1 workload (identical generator/seed), scipy "
-                      f"{__import__('scipy').__version__} fmin_l_bfgs_b + scipy.sparse loss/gradient restated from "
-                      "the reference (oracle/scipy_port.py), multiprocessing over all cores, TF reader / queue / "
-                      "Avro excluded",
-            "seconds": r["seconds"], "mean_nit": r["mean_nit"],
-            "c_oracle_1core_entities_per_sec": c1}
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from gdmix_b200.synthetic import make_batch
-    from oracle import scipy_port as SP
-    cores = os.cpu_count() or 1
-    kw = dict(l2=WORKLOAD["l2"], regularize_bias=False, has_intercept=True)
-    probe = make_batch(64 * cores, WORKLOAD["n"], WORKLOAD["d"], WORKLOAD["k"], seed=WORKLOAD["seed"])
-    rate = SP.timed_fit(_oracle_batch_dict(probe), probe.n_entities, **kw)["entities_per_sec"]
-    per_step = int(min(max(rate * 6.0, 1024), 200000))  # ~6 s of CPU work per step
-    hb = make_batch(per_step, WORKLOAD["n"], WORKLOAD["d"], WORKLOAD["k"], seed=WORKLOAD["seed"])
-    b = _oracle_batch_dict(hb)
-    for _ in range(args.warmup):
-        SP.timed_fit(b, min(per_step, 4 * cores), **kw)
-    secs, done = 0.0, 0
-    for _ in range(args.steps):
-        r = SP.timed_fit(b, per_step, **kw)
-        secs += r["seconds"]; done += r["entities"]
-    v = done / secs
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.entities), "entities_per_gpu": args.entities,
-                       "sample_entities_per_step": per_step,
-                       "note": "each step solves a bounded sample of the same workload (same generator and seed)"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{per_step} c1 entities per step through oracle/scipy_port.py "
-                                       "(reference call sequence on scipy/numpy), all host cores"},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
-
-
 def workload_name(E):
     w = WORKLOAD
     return (f"c1: {E} synthetic entities x {w['n']} samples x {w['d']} local features, {w['k']} nnz/sample, "
             f"l2={w['l2']}, bias unregularised, m=10, tol=1e-12, cold start (BASELINE.json configs[1])")
 
 
+# ---- CPU arm ------------------------------------------------------------------------------------------------------
+def _synth_arrays():
+    """gdmix_b200/synth_arrays.py loaded by path: importing the gdmix_b200 package would load the CUDA library, which
+    the reference arm must not do."""
+    spec = importlib.util.spec_from_file_location("_gdmix_synth_arrays", os.path.join(ROOT, "gdmix_b200",
+                                                                                       "synth_arrays.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def _oracle_dict(a):
+    n_rows = int(a["ent_rowptr"][-1])
+    return {"ent_rowptr": a["ent_rowptr"], "rowptr": a["rowptr"], "col": a["col"], "val": a["val"], "y": a["label"],
+            "w": a["weight"] if a.get("weight") is not None else np.ones(n_rows, np.float32),
+            "off": a["offset"] if a.get("offset") is not None else np.zeros(n_rows, np.float32),
+            "theta_ptr": a["theta_ptr"]}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_arm
+    cores = os.cpu_count() or 1
+    w = WORKLOAD
+    kw = dict(l2=w["l2"], regularize_bias=False, has_intercept=True)
+    gen = _synth_arrays()
+    probe, _ = gen.make_arrays(64 * cores, w["n"], w["d"], w["k"], seed=w["seed"])
+    rate = ref_arm.timed_fit(_oracle_dict(probe), 64 * cores, **kw)["entities_per_sec"]
+    per_step = int(min(max(rate * 6.0, 1024), 200000))  # ~6 s of CPU work per step
+    arrays, _ = gen.make_arrays(per_step, w["n"], w["d"], w["k"], seed=w["seed"])
+    b = _oracle_dict(arrays)
+    for _ in range(args.warmup):
+        ref_arm.timed_fit(b, min(per_step, 4 * cores), **kw)
+    secs, done = 0.0, 0
+    for _ in range(args.steps):
+        r = ref_arm.timed_fit(b, per_step, **kw)
+        secs += r["seconds"]; done += r["entities"]
+    v = done / secs
+    what = ("the reference's own BinaryLogisticRegressionTrainer.fit + threshold_coefficients (oracle/_ref, staged "
+            "unmodified by oracle/build_ref.py)" if ref_arm.kind() == "reference" else
+            "oracle/scipy_port.py (the reference's call sequence restated on scipy/numpy)")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.entities), "entities_per_gpu": args.entities,
+                       "sample_entities_per_step": per_step,
+                       "note": "each step solves a bounded sample of the same workload: same shapes, distributions and "
+                               "solver options; the numpy generator's own draws (the GPU arm generates on the device)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": ref_arm.kind(),
+                             "sample": f"{per_step} c1 entities per step through {what}, scipy "
+                                       f"{__import__('scipy').__version__}, fork pool over all host cores; TF reader / "
+                                       "Manager queue / Avro writer of the reference excluded"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---- GPU arm ------------------------------------------------------------------------------------------------------
+def _slice_entities_to_host(data, e0, e1):
+    """Entities [e0, e1) of the device batch as host numpy arrays, rebased (the oracle's batch dict)."""
+    er = data["ent_rowptr"][e0:e1 + 1].cpu().numpy()
+    r0, r1 = int(er[0]), int(er[-1])
+    rp = data["rowptr"][r0:r1 + 1].cpu().numpy()
+    q0, q1 = int(rp[0]), int(rp[-1])
+    tp = data["theta_ptr"][e0:e1 + 1].cpu().numpy()
+    return {"ent_rowptr": er - r0, "rowptr": rp - q0, "col": data["col"][q0:q1].cpu().numpy(),
+            "val": data["val"][q0:q1].cpu().numpy(), "label": data["label"][r0:r1].cpu().numpy(),
+            "weight": None, "offset": data["offset"][r0:r1].cpu().numpy(), "theta_ptr": tp - tp[0]}, int(tp[0]), int(tp[-1])
+
+
+def parity_sample(data, theta, nit, status, n_sample, runs=16):
+    """Entities of the TIMED device batch (runs of consecutive entities spread over the batch) solved again by the
+    CPU oracle (oracle/lr_oracle.c): per-entity relative L2 deviation of the coefficients, iteration counts."""
+    from oracle import oracle as O
+    E = data["n_entities"]
+    per = max(1, n_sample // runs)
+    starts = np.unique(np.linspace(0, max(E - per, 0), runs).astype(np.int64))
+    oo = O.make_opts(l2=WORKLOAD["l2"], regularize_bias=False, has_intercept=True)
+    rel, nit_eq, st_eq, t_cpu = [], [], [], 0.0
+    for s in starts:
+        e0, e1 = int(s), int(min(E, s + per))
+        a, t0, t1 = _slice_entities_to_host(data, e0, e1)
+        ob = _oracle_dict(a)
+        tt = time.perf_counter()
+        th, f, onit, onfev, ost = O.re_fit_batch(ob, oo)
+        t_cpu += time.perf_counter() - tt
+        g = theta[t0:t1].cpu().numpy()
+        tp = ob["theta_ptr"]
+        for i in range(e1 - e0):
+            a_, b_ = g[tp[i]:tp[i + 1]], th[tp[i]:tp[i + 1]]
+            rel.append(float(np.linalg.norm(a_ - b_) / max(np.linalg.norm(b_), 1e-300)))
+        nit_eq.append(nit[e0:e1].cpu().numpy() == onit)
+        st_eq.append(status[e0:e1].cpu().numpy() == ost)
+    rel = np.array(rel)
+    return {"entities": int(rel.size), "frac_le_1e-5": float((rel <= 1e-5).mean()), "max_rel": float(rel.max()),
+            "median_rel": float(np.median(rel)), "nit_equal_frac": float(np.concatenate(nit_eq).mean()),
+            "status_equal_frac": float(np.concatenate(st_eq).mean()),
+            "oracle": "oracle/lr_oracle.c (pinned to the reference's own outputs by tests/test_oracle.py)",
+            "sample": f"{len(starts)} runs of {per} consecutive entities of the timed device batch",
+            "oracle_seconds": t_cpu}
+
+
+def cpu_baseline_from_batch(data, sample_entities):
+    """The reference's CPU path on all host cores over the FIRST entities of the timed device batch (identical bytes)."""
+    from oracle import oracle as O
+    from oracle import ref_arm
+    w = WORKLOAD
+    kw = dict(l2=w["l2"], regularize_bias=False, has_intercept=True)
+    cores = os.cpu_count() or 1
+    if sample_entities <= 0:
+        a, _, _ = _slice_entities_to_host(data, 0, min(64 * cores, data["n_entities"]))
+        rate = ref_arm.timed_fit(_oracle_dict(a), len(a["ent_rowptr"]) - 1, **kw)["entities_per_sec"]
+        sample_entities = int(min(max(rate * 15.0, 2048), 400000, data["n_entities"]))
+    a, _, _ = _slice_entities_to_host(data, 0, sample_entities)
+    b = _oracle_dict(a)
+    r = ref_arm.timed_fit(b, sample_entities, **kw)
+    nc = min(sample_entities, 2000)
+    t0 = time.perf_counter()
+    O.re_fit_batch(b, O.make_opts(l2=w["l2"]), e0=0, e1=nc)
+    c1 = nc / (time.perf_counter() - t0)
+    return {"value": r["entities_per_sec"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+            "sample": f"first {sample_entities} entities of the timed device batch (identical bytes, copied to the "
+                      f"host) through the reference's per-entity call sequence ({r['kind']}: "
+                      f"{'oracle/_ref BinaryLogisticRegressionTrainer' if r['kind'] == 'reference' else 'oracle/scipy_port.py'}"
+                      f", scipy {__import__('scipy').__version__}), fork pool over all cores; TF reader / queue / "
+                      "Avro excluded",
+            "seconds": r["seconds"], "mean_nit": r["mean_nit"], "c_oracle_1core_entities_per_sec": c1}
+
+
+def probe_traffic(which, timeout=240):
+    """DRAM bytes of our kernels from one ncu pass over a small instance of the workload, run as a subprocess on this
+    box with this build (`bench.py --probe <which>` under ncu --metrics dram__bytes_*).  -> dict or {"error": ...}."""
+    ncu = None
+    for c in ("/usr/local/cuda/bin/ncu", "ncu"):
+        try:
+            subprocess.run([c, "--version"], capture_output=True, timeout=30, check=True)
+            ncu = c
+            break
+        except Exception:
+            continue
+    if ncu is None:
+        return {"error": "ncu not found"}
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--csv",
+           "--print-units", "base", "--profile-from-start", "off", sys.executable, os.path.abspath(__file__),
+           "--probe", which]
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    except Exception as ex:
+        return {"error": f"ncu run failed: {ex}"}
+    marker = None
+    rows = []
+    import csv
+    lines = res.stdout.splitlines()
+    for ln in lines:
+        if ln.startswith("PROBE "):
+            marker = json.loads(ln[6:])
+    try:
+        start = next(i for i, ln in enumerate(lines) if ln.startswith('"ID"'))
+        rows = list(csv.DictReader(lines[start:]))
+    except StopIteration:
+        return {"error": "no ncu csv in output", "tail": (res.stdout + res.stderr)[-400:]}
+    if marker is None:
+        return {"error": "probe did not report its workload", "tail": (res.stdout + res.stderr)[-400:]}
+    per_kernel = {}
+    for r in rows:
+        try:
+            v = float(r["Metric Value"].replace(",", ""))
+        except Exception:
+            continue
+        unit = r.get("Metric Unit", "byte").lower()
+        v *= {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+        name = r["Kernel Name"].split("(")[0]
+        per_kernel.setdefault(name, {"launches": set(), "bytes": 0.0})
+        per_kernel[name]["launches"].add(r["ID"])
+        per_kernel[name]["bytes"] += v
+    # the probe brackets `marker["calls"]` calls with cudaProfilerStart / Stop (after an unprofiled warm-up call)
+    total = sum(k["bytes"] for k in per_kernel.values()) / max(marker["calls"], 1)
+    return {"dram_bytes_per_call": total, "units_per_call": marker["units"], "unit": marker["unit"],
+            "dram_bytes_per_unit": total / marker["units"], "calls_profiled": marker["calls"],
+            "kernels": {k: {"launches": len(v["launches"]), "dram_bytes": v["bytes"]} for k, v in per_kernel.items()},
+            "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over `bench.py --probe "
+                      f"{which}` run by this bench on this box (same build)"}
+
+
+def run_probe(which):
+    """The workload ncu profiles for probe_traffic (small instances of the timed workloads, 2 calls)."""
+    import ctypes as C
+    import torch
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    from gdmix_b200 import _capi as capi
+    if which == "c1":
+        from gdmix_b200.synthetic import make_device_batch
+        from tools import subbench
+        w = WORKLOAD
+        E = 148 * 200
+        data = make_device_batch(E, w["n"], w["d"], w["k"], seed=w["seed"], device=dev)
+        cb = subbench._re_batch(data)
+        opts = capi.make_opts(l2=w["l2"], regularize_bias=False, has_intercept=True)
+        ws = torch.empty(max(capi.re_workspace_size(cb, opts), 256), dtype=torch.uint8, device=dev)
+        theta = torch.empty(data["n_coef"], dtype=torch.float64, device=dev)
+        for i in range(2):
+            if i == 1:
+                torch.cuda.synchronize()
+                torch.cuda.profiler.start()
+            capi.check(capi.lib.gdmix_re_fit(C.byref(cb), C.byref(opts), None, C.c_void_p(theta.data_ptr()), None,
+                                             None, None, None, None, C.c_void_p(ws.data_ptr()),
+                                             C.c_size_t(ws.numel()),
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print("PROBE " + json.dumps({"calls": 1, "units": E, "unit": "entity"}))
+    elif which == "fe":
+        from tools import subbench
+        from gdmix_b200.fe_solver import FixedEffectSolver
+        rows = 8_000_000
+        shard = subbench.zipf_rows(rows, 100_000, 32, 100, dev)
+        solver = FixedEffectSolver(shard, capi.make_opts(l2=1.0, regularize_bias=True), 100_000)
+        solver._prepare()
+        torch.cuda.synchronize()
+        solver._partial()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        solver._partial()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print("PROBE " + json.dumps({"calls": 1, "units": rows, "unit": "row"}))
+    else:
+        raise SystemExit(f"unknown probe {which!r}")
+
+
 def run_ours(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     from gdmix_b200 import _capi as capi
@@ -173,16 +347,26 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at any debug level
-        os.environ.pop("NCCL_DEBUG", None)
-        if os.environ.get("GDMIX_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = os.environ["GDMIX_NCCL_DEBUG"]
+        # NCCL_DEBUG is left as the launcher set it (its lines are how the driver checks the communicator's ranks);
+        # the JSON line is written last, after every rank has torn its communicator down
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def min_over_ranks(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item())
 
     E = args.entities
     w = WORKLOAD
@@ -204,7 +388,6 @@ def run_ours(args):
     nfev = torch.empty(E, dtype=torch.int32, device=dev)
     status = torch.empty(E, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream()
-    import ctypes as C
 
     def step():
         capi.check(capi.lib.gdmix_re_fit(C.byref(cb), C.byref(opts), None, C.c_void_p(theta.data_ptr()),
@@ -230,11 +413,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = capi.launch_count() - launches0
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    total_ms = ev[0].elapsed_time(ev[-1])
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    total_ms_max = max_over_ranks(ev[0].elapsed_time(ev[-1]))
     value = world * E * args.steps / (total_ms_max / 1e3)
 
     # sanity of the solve itself (not timed): all converged, iteration statistics
@@ -242,6 +421,19 @@ def run_ours(args):
     nit_h = nit.cpu().numpy()
     nfev_h = nfev.cpu().numpy()
     converged = float((st == 0).mean())
+
+    # ---- parity of the timed batch against the CPU oracle (every rank checks its own batch) ----------------------
+    parity = None
+    if args.parity_entities > 0:
+        try:
+            parity = parity_sample(data, theta, nit, status, args.parity_entities)
+            parity["frac_le_1e-5_min_over_ranks"] = min_over_ranks(parity["frac_le_1e-5"])
+            parity["max_rel_max_over_ranks"] = max_over_ranks(parity["max_rel"])
+            parity["nit_equal_frac_min_over_ranks"] = min_over_ranks(parity["nit_equal_frac"])
+            parity["ranks"] = world
+        except Exception as ex:  # the headline must still be printed
+            parity = {"error": repr(ex)}
+            min_over_ranks(0.0); max_over_ranks(0.0); min_over_ranks(0.0)
 
     # roofline of the dominant (only) kernel: algorithmic bytes per launch / average launch duration
     alg_bytes = 8 * data["nnz"] + 16 * data["n_rows"] + 8 * data["n_coef"] + 4 * (data["n_coef"] - E)
@@ -255,14 +447,8 @@ def run_ours(args):
     plan = capi.last_plan()
     kernel = (f"re_fast_kernel<{plan['threads']},{plan['ept']}>" if plan["fast"] else
               f"re_solver_kernel<{plan['threads']}>")
-    # DRAM bytes per entity of this kernel on this workload from the committed ncu --set full capture
-    # (profiles/r1_ncu_full_re_fast_v8.txt: dram__bytes_read.sum + dram__bytes_write.sum over 30 000 entities)
-    ncu_dram_bytes_per_entity = (1.047181e9 + 87.874816e6) / 30000.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_dram_bytes_per_entity * E if w["name"] == "c1" else None,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per entity "
-                                  "(profiles/r1_ncu_full_re_fast_v8.txt) x entities per launch",
-                "peak_source": peak_src,
+                "traffic": None, "traffic_source": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel": kernel, "plan": plan,
                 "kernel_ms_per_launch": kern_s * 1e3,
                 "streaming_model_gbs": streaming_bytes / kern_s / 1e9,
@@ -271,11 +457,15 @@ def run_ours(args):
                         "L-BFGS updates out of shared memory and registers), so the kernel is bound by fp64 issue "
                         "latency and the shared-memory pipe, not by HBM (DESIGN.md section 4)"}
 
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline_from_batch(data, args.cpu_sample)
+        except Exception as ex:
+            cpu = {"error": repr(ex)}
+
     # ---- e2e: host CSR in pinned memory -> gdmix_re_fit_host -> coefficients on the host -------------------
-    e2e = None
-    Ee = min(args.e2e_entities, E)
-    if world >= 4:
-        Ee = min(Ee, 262144)   # keeps the pinned host staging of an 8-rank run under 50 GB in total
+    Ee = min(args.e2e_entities, E)     # the same at every N
     rows_e, nnz_e, coef_e = Ee * w["n"], Ee * w["n"] * w["k"], Ee * (w["d"] + 1)
 
     def pinned(t):
@@ -310,20 +500,88 @@ def run_ours(args):
     for _ in range(e2e_steps):
         e2e_step()  # synchronous: returns with the results in host memory
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t1
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = max_over_ranks(time.perf_counter() - t1)
     h2d = 8 * (Ee + 1) * 2 + 8 * (rows_e + 1) + 5 * nnz_e + 8 * rows_e
     d2h = 8 * coef_e + 8 * Ee + 12 * Ee
-    e2e = {"value": world * Ee * e2e_steps / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+    e2e = {"value": world * Ee * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "entities_per_step": Ee, "steps": e2e_steps,
            "api": "gdmix_re_fit_host (pinned host CSR in -- fp32 values, uint8 local columns -- host coefficients out)",
            "host_theta_checksum": float(h_theta.sum().item())}
     capi.lib.gdmix_host_release()
+    # what the box can copy: pinned host -> device, all ranks at once (the ceiling of any host-buffer API on it)
+    try:
+        nbytes = 1 << 30
+        src = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        dst.copy_(src, non_blocking=True)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(4):
+            dst.copy_(src, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        gbs = 4 * nbytes / (c0.elapsed_time(c1) / 1e3) / 1e9
+        gbs_min = min_over_ranks(gbs)
+        e2e["h2d_peak_gbs_per_gpu_at_N"] = gbs_min
+        e2e["h2d_bound_entities_per_s"] = world * gbs_min * 1e9 / (h2d / Ee)
+        e2e["frac_of_h2d_bound"] = e2e["value"] / e2e["h2d_bound_entities_per_s"]
+        e2e["host"] = {"cpus_visible": len(os.sched_getaffinity(0)), "cpu_count": os.cpu_count()}
+        del src, dst
+    except Exception as ex:
+        e2e["h2d_probe_error"] = repr(ex)
+        min_over_ranks(0.0)
 
+    # ---- the other configurations (not part of the headline's timed region) -----------------------------------
+    del data, theta, f, nit, nfev, status, ws, h_ent, h_row, h_col, h_val, h_lab, h_off, h_tp, h_theta
+    torch.cuda.empty_cache()
+    sub = {}
+    if not args.no_sub:
+        from tools import subbench
+        group = dist.group.WORLD if world > 1 else None
+        plan_list = [("small", lambda: subbench.small_entities(dev, rank, world, peak, E=args.small_entities)),
+                     ("sweep", lambda: subbench.l2_sweep(dev, rank, world, peak, E=args.sweep_entities)),
+                     ("fe", lambda: subbench.fixed_effect(dev, rank, world, group, peak, rows=args.fe_rows)),
+                     ("chain", lambda: subbench.chain(dev, rank, world, group, n=args.chain_rows,
+                                                      U=args.chain_rows // 32, I=args.chain_rows // 320))]
+        for name, fn in plan_list:
+            t0 = time.perf_counter()
+            try:
+                sub[name] = fn()
+            except Exception as ex:
+                if world > 1:
+                    raise          # a rank that skips a collective would hang the others
+                sub[name] = {"error": repr(ex)}
+            sub[name]["wall_s"] = time.perf_counter() - t0
+            torch.cuda.empty_cache()
+            barrier()
+
+    # ---- measured DRAM traffic of this build's kernels (ncu over a small instance, N=1 only) -------------------
+    if rank == 0 and world == 1 and not args.no_traffic_probe:
+        tr = probe_traffic("c1")
+        if "error" not in tr:
+            roofline["traffic"] = tr["dram_bytes_per_unit"] * E
+            roofline["traffic_source"] = tr["source"]
+            roofline["traffic_over_algorithmic"] = roofline["traffic"] / alg_bytes
+            roofline["traffic_kernels"] = tr["kernels"]
+        else:
+            roofline["traffic_source"] = tr
+        if "fe" in sub and "roofline" in sub["fe"]:
+            tr = probe_traffic("fe")
+            if "error" not in tr:
+                rf = sub["fe"]["roofline"]
+                rf["traffic"] = tr["dram_bytes_per_unit"] * sub["fe"]["rows_per_gpu"]
+                rf["traffic_over_algorithmic"] = rf["traffic"] / rf["algorithmic_bytes_per_eval"]
+                rf["traffic_source"] = tr["source"]
+                rf["traffic_kernels"] = tr["kernels"]
+            else:
+                sub["fe"]["roofline"]["traffic_source"] = tr
+
+    total_launches = capi.launch_count()
+    if world > 1:
+        barrier()
+        dist.destroy_process_group()
     if rank == 0:
-        cpu = cpu_baseline(args.cpu_sample) if (world == 1 and not args.no_cpu_baseline) else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -334,12 +592,15 @@ def run_ours(args):
                            "generation_seconds": gen_s},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "solve": {"converged_frac": converged, "mean_nit": float(nit_h.mean()),
-                          "mean_nfev": float(nfev_h.mean()), "max_nit": int(nit_h.max())}}
+                          "mean_nfev": float(nfev_h.mean()), "max_nit": int(nit_h.max())},
+                "parity": parity, "sub": sub, "gpu_launches_whole_run": int(total_launches)}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        if world > 1:
+            time.sleep(1.0)      # the other ranks' NCCL teardown lines are out before the one JSON line
+        sys.stdout.flush()
+        sys.stdout.write(json.dumps(line) + "\n")
+        sys.stdout.flush()
 
 
 def main():
@@ -349,13 +610,23 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--entities", type=int, default=1_000_000, help="entities per GPU")
-    ap.add_argument("--e2e-entities", type=int, default=524288)
+    ap.add_argument("--e2e-entities", type=int, default=262144, help="entities per GPU of the e2e leg (same at every N)")
     ap.add_argument("--e2e-chunk", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="entities for the cpu_baseline leg (0 = ~15 s of work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-entities", type=int, default=2048)
+    ap.add_argument("--no-sub", action="store_true", help="skip the fe / sweep / small / chain sub-benchmarks")
+    ap.add_argument("--no-traffic-probe", action="store_true")
+    ap.add_argument("--small-entities", type=int, default=4_000_000)
+    ap.add_argument("--sweep-entities", type=int, default=2_000_000)
+    ap.add_argument("--fe-rows", type=int, default=62_500_000)
+    ap.add_argument("--chain-rows", type=int, default=40_000_000)
     ap.add_argument("--threads-per-entity", type=int, default=0)
+    ap.add_argument("--probe", default=None, help="internal: the workload ncu profiles for roofline.traffic")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.probe:
+        run_probe(args.probe)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -19,38 +19,15 @@ CONFIGS = {
 }
 
 
-def _sample_counts(rng, E, n_mean, ragged, n_min=8, n_max=1024):
-    if not ragged:
-        return np.full(E, n_mean, np.int64)
-    raw = rng.lognormal(mean=0.0, sigma=0.5, size=E)
-    raw *= n_mean / np.exp(0.125)  # E[lognormal(0, .5)] = exp(.125)
-    return np.clip(np.rint(raw), min(n_min, n_mean), n_max).astype(np.int64)
+from .synth_arrays import _sample_counts, make_arrays  # noqa: F401
 
 
 def make_batch(E, n_mean=128, d=256, k=32, seed=20240601, ragged=False, weights=False, has_intercept=True,
                return_truth=False):
     """-> HostBatch (numpy).  Deterministic in (E, shape, seed)."""
-    rng = np.random.default_rng(seed)
-    k = min(k, d)
-    n_e = _sample_counts(rng, E, n_mean, ragged)
-    ent_rowptr = np.zeros(E + 1, np.int64)
-    np.cumsum(n_e, out=ent_rowptr[1:])
-    N = int(ent_rowptr[-1])
-    rowptr = np.arange(N + 1, dtype=np.int64) * k
-    stride = d // k
-    col = (np.arange(k, dtype=np.int32)[None, :] * stride +
-           rng.integers(0, stride, size=(N, k), dtype=np.int32)).reshape(-1)
-    val = rng.standard_normal(N * k, dtype=np.float32)
-    off = rng.standard_normal(N, dtype=np.float32)
-    theta_star = (0.5 * rng.standard_normal((E, d + 1))).astype(np.float64)
-    ent_of_row = np.repeat(np.arange(E), n_e)
-    z = (val.reshape(N, k).astype(np.float64) *
-         theta_star[ent_of_row[:, None], 1 + col.reshape(N, k)]).sum(axis=1) + theta_star[ent_of_row, 0] + off
-    y = (rng.random(N) < 1.0 / (1.0 + np.exp(-z))).astype(np.float32)
-    w = rng.uniform(0.5, 2.0, N).astype(np.float32) if weights else None
-    p = d + (1 if has_intercept else 0)
-    theta_ptr = np.arange(E + 1, dtype=np.int64) * p
-    hb = HostBatch(ent_rowptr, rowptr, col, val, y, w, off, theta_ptr, has_intercept)
+    a, theta_star = make_arrays(E, n_mean, d, k, seed, ragged, weights, has_intercept)
+    hb = HostBatch(a["ent_rowptr"], a["rowptr"], a["col"], a["val"], a["label"], a["weight"], a["offset"],
+                   a["theta_ptr"], has_intercept)
     return (hb, theta_star) if return_truth else hb
 
 

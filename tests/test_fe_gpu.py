@@ -162,7 +162,7 @@ def test_solver_frequency_ranking_is_invisible_to_the_caller():
     solver = FixedEffectSolver(rows, opts)
     x = rng.standard_normal(D + 1) * 0.05
     f, g = solver.loss_grad(x)
-    assert solver._ranked is not None
+    assert solver._perm is not None
     blk = O.FeBlock(n, D, rowptr, col, val, y, np.ones(n, np.float32), np.zeros(n, np.float32))
     f_o, g_o = O.fe_loss_grad(blk, O.make_opts(l2=2.0, regularize_bias=True, has_intercept=True), x)
     np.testing.assert_allclose(f, f_o, rtol=1e-12)

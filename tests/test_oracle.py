@@ -1,6 +1,8 @@
 """CPU oracle (oracle/lr_oracle.c) against the golden vectors produced by the reference itself
 (BinaryLogisticRegressionTrainer + scipy.optimize.fmin_l_bfgs_b, see oracle/gen_golden.py).
 This is the pin that lets the GPU parity tests trust the oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -149,3 +151,34 @@ def test_scipy_port_is_the_reference(c):
     if is_pinned(c):
         assert (nit, nfev, wf) == (c["nit"], c["nfev"], c["warnflag"])
         np.testing.assert_allclose(theta, ARR[k + "_theta"], rtol=1e-12, atol=1e-15)
+
+
+def test_reference_arm_runs_the_staged_reference_class_and_never_loads_the_product():
+    """bench.py --impl reference: oracle/ref_arm.py drives the reference's own BinaryLogisticRegressionTrainer when
+    oracle/_ref is staged (oracle/build_ref.py), reproduces the golden coefficients, and neither it nor the numpy
+    workload generator it uses imports gdmix_b200 (a reference arm must not map the product's library)."""
+    import subprocess
+    import sys
+    from oracle import build_ref, ref_arm
+    cold = [c for c in CASES if not c["warm"] and is_pinned(c) and c["has_intercept"] and c["max_iter"] == 100
+            and c["m"] == 10 and c["tol"] == 1e-12][:6]
+    assert cold
+    for c in cold:
+        k = c["key"]
+        p = c["d"] + 1
+        batch = {"ent_rowptr": np.array([0, c["n"]], np.int64), "rowptr": ARR[k + "_rowptr"], "col": ARR[k + "_col"],
+                 "val": ARR[k + "_val"], "y": ARR[k + "_y"], "w": ARR[k + "_w"], "off": ARR[k + "_off"],
+                 "theta_ptr": np.array([0, p], np.int64)}
+        th = ref_arm.fit_entities(batch, 0, 1, l2=c["l2"], regularize_bias=c["regularize_bias"], has_intercept=True)[0]
+        want = ARR[k + "_theta"].copy()
+        want[np.abs(want) <= 1e-4] = 0.0          # the arm applies threshold_coefficients like TrainingJobConsumer
+        np.testing.assert_allclose(th, want, rtol=1e-12, atol=1e-15)
+    if os.path.isdir(build_ref.REF_SRC):
+        assert build_ref.build() and ref_arm.kind() == "reference"
+    code = ("import sys, bench; g = bench._synth_arrays(); a, _ = g.make_arrays(4, 8, 16, 4); "
+            "from oracle import ref_arm; ref_arm.fit_entities(bench._oracle_dict(a), 0, 2); "
+            "bad = [m for m in sys.modules if m.startswith('gdmix_b200')]; "
+            "maps = open('/proc/self/maps').read(); "
+            "assert not bad and 'libgdmix_b200' not in maps, (bad, 'libgdmix_b200' in maps)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, "-c", code], cwd=root, check=True)
