@@ -26,7 +26,7 @@ EPS = float(np.finfo(np.float64).eps)
 # every symbol include/gdmix_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_workspace_size",
            "gdmix_re_loss_grad", "gdmix_re_fit", "gdmix_re_score", "gdmix_fe_loss_grad", "gdmix_fe_score",
-           "gdmix_fe_hessian", "gdmix_fe_rows_grid", "gdmix_fe_loss_grad_planned",
+           "gdmix_fe_hessian",
            "gdmix_re_fit_host", "gdmix_re_score_host", "gdmix_host_register", "gdmix_host_unregister",
            "gdmix_host_release", "gdmix_partition_ids", "gdmix_lbfgs_create", "gdmix_lbfgs_iterate",
            "gdmix_lbfgs_info", "gdmix_lbfgs_destroy", "gdmix_launch_count", "gdmix_re_last_plan",
@@ -36,7 +36,8 @@ SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_w
            "gdmix_seqex_count", "gdmix_seqex_fill", "gdmix_example_count", "gdmix_example_fill", "gdmix_avro_score_blocks", "gdmix_avro_model_blocks",
            "gdmix_feature_map_create", "gdmix_feature_map_destroy", "gdmix_avro_model_decode",
            "gdmix_fe_lbfgs_create", "gdmix_fe_lbfgs_reset", "gdmix_fe_lbfgs_step", "gdmix_fe_lbfgs_poll",
-           "gdmix_fe_lbfgs_destroy", "gdmix_fe_column_counts", "gdmix_remap_i32"]
+           "gdmix_fe_lbfgs_destroy", "gdmix_fe_column_counts", "gdmix_remap_i32", "gdmix_fe_tile_plan_create",
+           "gdmix_fe_tile_plan_destroy", "gdmix_fe_tile_plan_info", "gdmix_fe_loss_grad_tiled"]
 
 
 class SeqexSpec(C.Structure):
@@ -83,14 +84,6 @@ class FeRows(C.Structure):
                 ("offset", C.c_void_p), ("linear_regression", C.c_int32), ("num_workers", C.c_int32)]
 
 
-class FePlanStruct(C.Structure):
-    _fields_ = [("colptr", C.c_void_p), ("row", C.c_void_p), ("val", C.c_void_p), ("n_items", C.c_int64),
-                ("item_col", C.c_void_p), ("item_begin", C.c_void_p), ("item_end", C.c_void_p),
-                ("item_slot", C.c_void_p), ("n_split", C.c_int64), ("split_col", C.c_void_p),
-                ("split_slot_ptr", C.c_void_p), ("n_slots", C.c_int64), ("scratch", C.c_void_p),
-                ("scratch_doubles", C.c_int64), ("n_tiles", C.c_int64), ("tile_item_ptr", C.c_void_p)]
-
-
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -111,6 +104,12 @@ def _load():
     lib.gdmix_lbfgs_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gdmix_lbfgs_destroy.argtypes = [C.c_void_p]
     lib.gdmix_lbfgs_destroy.restype = None
+    lib.gdmix_fe_tile_plan_create.restype = C.c_void_p
+    lib.gdmix_fe_tile_plan_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]
+    lib.gdmix_fe_tile_plan_destroy.argtypes = [C.c_void_p]
+    lib.gdmix_fe_tile_plan_destroy.restype = None
+    lib.gdmix_fe_tile_plan_info.argtypes = [C.c_void_p, C.c_void_p]
+    lib.gdmix_fe_loss_grad_tiled.argtypes = [C.c_void_p] * 6
     lib.gdmix_fe_lbfgs_create.restype = C.c_void_p
     lib.gdmix_fe_lbfgs_create.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gdmix_fe_lbfgs_reset.argtypes = [C.c_void_p, C.c_void_p]
@@ -393,90 +392,37 @@ class DeviceFeRows:
                       self.num_workers)
 
 
-FE_SLICE = 4096  # non-zeros of a column one warp sums; longer columns are sliced
-FE_HEAD = 8192   # leading coefficients of x that fe_rows_kernel keeps in shared memory (kFeHeadMax)
-FE_TILE_ROWS = 4 << 20  # rows per tile of the column-major copy: a tile's dz (32 MB) stays in L2 while it is gathered
+FE_HEAD = 8192   # above this many features the solver renumbers them by falling frequency (hot ranks first)
 
 
-class DeviceFePlan:
-    """Column-major copy of a shard + work items + scratch for gdmix_fe_loss_grad_planned.  Built once per
-    training run (the shard does not change between the ~100 evaluations of an L-BFGS run).  The transpose is a
-    stable sort done with torch (device memory plumbing, outside any timed region).
+class DeviceFeTilePlan:
+    """gdmix_fe_tile_plan_*: the shard laid out for the tiled objective (row-major hot / cold copy for z = X x,
+    column-major tiled copy for g = X^T dz), built on the device by the library once per training run.
+    hz / hg / tile_rows / l2_tile_rows: 0 = the library's choice (as much of x / of the gradient in shared memory as
+    the kernels hold); the tests pass small values to exercise the cold paths."""
 
-    The copy is TILED by rows: non-zeros are ordered by (row tile, column, row) and a work item is a column's
-    run inside one tile (or a slice of at most `slice_nnz` of it).  Items are walked tile after tile, so the dz
-    entries a tile's items gather -- `tile_rows` x 8 bytes -- are L2 hits instead of one 32-byte DRAM sector per
-    non-zero, which is what the gather costs once dz outgrows L2 (a 62 M-row shard has 500 MB of dz).  A column
-    that owns more than one item has its partial sums added in item order by fe_finish_kernel (fixed order)."""
-
-    def __init__(self, rows, slice_nnz=FE_SLICE, tile_rows=FE_TILE_ROWS):
-        import torch
-        dev = rows.val.device
-        D, n = rows.n_features, rows.n_rows
-        row_of_nnz = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int32),
-                                             (rows.rowptr[1:] - rows.rowptr[:-1]))
-        key = rows.col.to(torch.int64)
-        counts_col = torch.bincount(key, minlength=D)
-        if n > tile_rows:
-            key += (row_of_nnz // int(tile_rows)).to(torch.int64) * D
-        srt = torch.sort(key, stable=True)                         # rows ascending inside a (tile, column) run
-        del key
-        self.row = row_of_nnz[srt.indices].contiguous()
-        self.val = rows.val[srt.indices].contiguous()
-        del row_of_nnz
-        seg_key, seg_cnt = torch.unique_consecutive(srt.values, return_counts=True)
-        del srt
-        self.colptr = torch.zeros(D + 1, dtype=torch.int64, device=dev)
-        self.colptr[1:] = torch.cumsum(counts_col, 0)
-        # work items (host side: segments are few next to nnz)
-        seg_key, seg_cnt = seg_key.cpu().numpy(), seg_cnt.cpu().numpy().astype(np.int64)
-        seg_col = (seg_key % D).astype(np.int32)
-        seg_tile = seg_key // D
-        seg_begin = np.cumsum(seg_cnt) - seg_cnt
-        # inside a tile the long runs go first (they are whole 4096-slices; the short tail fills the launch's end)
-        by_len = np.lexsort((-seg_cnt, seg_tile))
-        seg_col, seg_tile, seg_begin, seg_cnt = seg_col[by_len], seg_tile[by_len], seg_begin[by_len], seg_cnt[by_len]
-        pieces = np.maximum(1, -(-seg_cnt // slice_nnz)).astype(np.int64)
-        item_col = np.repeat(seg_col, pieces)
-        first = np.cumsum(pieces) - pieces
-        k = np.arange(item_col.shape[0], dtype=np.int64) - np.repeat(first, pieces)
-        begin = np.repeat(seg_begin, pieces) + k * slice_nnz
-        end = np.minimum(begin + slice_nnz, np.repeat(seg_begin + seg_cnt, pieces))
-        self.n_tiles = int(seg_tile.max()) + 1 if seg_tile.shape[0] else 1
-        items_per_tile = np.bincount(np.repeat(seg_tile, pieces), minlength=self.n_tiles).astype(np.int64)
-        # columns without any non-zero still get their L2 term: one empty item each (they ride in the last tile)
-        empty = np.flatnonzero(counts_col.cpu().numpy() == 0).astype(np.int32)
-        items_per_tile[-1] += empty.shape[0]
-        self.tile_item_ptr = np.concatenate([[0], np.cumsum(items_per_tile)]).astype(np.int64)   # host array
-        item_col = np.concatenate([item_col, empty])
-        begin = np.concatenate([begin, np.zeros(empty.shape[0], np.int64)])
-        end = np.concatenate([end, np.zeros(empty.shape[0], np.int64)])
-        # slots: the items of a column that has several, numbered column by column in item order
-        per_col = np.bincount(item_col, minlength=D).astype(np.int64)
-        split_col = np.flatnonzero(per_col > 1).astype(np.int32)
-        ssp = np.concatenate([[0], np.cumsum(per_col[split_col])]).astype(np.int64)
-        slot_base = np.full(D, -1, np.int64)
-        slot_base[split_col] = ssp[:-1]
-        by_col = np.argsort(item_col, kind="stable")
-        first_of_col = np.cumsum(per_col) - per_col
-        rank = np.empty(item_col.shape[0], np.int64)
-        rank[by_col] = np.arange(item_col.shape[0], dtype=np.int64) - first_of_col[item_col[by_col]]
-        slot = np.where(slot_base[item_col] >= 0, slot_base[item_col] + rank, -1).astype(np.int32)
-        self.n_items, self.n_slots = int(item_col.shape[0]), int(ssp[-1])
-        to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-        self.item_col, self.item_begin, self.item_end, self.item_slot = to(item_col), to(begin), to(end), to(slot)
-        self.n_split = int(split_col.shape[0])
-        self.split_col, self.split_slot_ptr = to(split_col), to(ssp)
-        g = C.c_int32()
+    def __init__(self, rows, hz=0, hg=0, tile_rows=0, l2_tile_rows=0, stream=None):
         cs = rows.c_struct()
-        check(lib.gdmix_fe_rows_grid(C.byref(cs), C.byref(g)))
-        self.scratch = torch.empty(n + self.n_slots + 2 * g.value, dtype=torch.float64, device=dev)
+        self._rows = rows
+        self._h = lib.gdmix_fe_tile_plan_create(C.cast(C.pointer(cs), C.c_void_p), C.c_int32(hz), C.c_int32(hg),
+                                                C.c_int32(tile_rows), C.c_int64(l2_tile_rows), _stream_ptr(stream))
+        if not self._h:
+            raise GdmixError(GDMIX_ERR_INVALID, lib.gdmix_last_error().decode())
+        a = (C.c_int64 * 8)()
+        check(lib.gdmix_fe_tile_plan_info(self._h, C.cast(a, C.c_void_p)))
+        (self.hz, self.hg, self.tile_rows, self.n_tiles, self.n_cold_z, self.n_cold_g, self.bytes,
+         self.n_l2_tiles) = [int(v) for v in a]
 
-    def c_struct(self):
-        return FePlanStruct(_tptr(self.colptr), _tptr(self.row), _tptr(self.val), self.n_items, _tptr(self.item_col),
-                            _tptr(self.item_begin), _tptr(self.item_end), _tptr(self.item_slot), self.n_split,
-                            _tptr(self.split_col), _tptr(self.split_slot_ptr), self.n_slots, _tptr(self.scratch),
-                            self.scratch.numel(), self.n_tiles, _np_ptr(self.tile_item_ptr))
+    def close(self):
+        if self._h:
+            lib.gdmix_fe_tile_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def fe_column_counts(rows, stream=None):
@@ -513,17 +459,17 @@ def remap_columns(col, rank_of, stream=None):
 
 
 def fe_loss_grad_device(rows, opts, x, fg=None, stream=None, plan=None):
-    """-> fg tensor [1 + D + has_intercept]: value then gradient (this rank's partial).  With a DeviceFePlan the
-    atomics-free three-kernel path runs; without, the single-pass kernel with fp64 atomics."""
+    """-> fg tensor [1 + D + has_intercept]: value then gradient (this rank's partial).  With a DeviceFeTilePlan the
+    atomics-free tiled path runs; without, the single-pass kernel with fp64 atomics (tests, one-off evaluations)."""
     import torch
     n = 1 + rows.n_features + (1 if opts.has_intercept else 0)
     if fg is None:
         fg = torch.empty(n, dtype=torch.float64, device=x.device)
     cs = rows.c_struct()
     if plan is not None:
-        ps = plan.c_struct()
-        check(lib.gdmix_fe_loss_grad_planned(C.byref(cs), C.byref(ps), C.byref(opts), _tptr(x), _tptr(fg),
-                                             _stream_ptr(stream)))
+        check(lib.gdmix_fe_loss_grad_tiled(C.cast(C.pointer(cs), C.c_void_p), plan._h,
+                                           C.cast(C.pointer(opts), C.c_void_p), _tptr(x), _tptr(fg),
+                                           _stream_ptr(stream)))
     else:
         check(lib.gdmix_fe_loss_grad(C.byref(cs), C.byref(opts), _tptr(x), _tptr(fg), _stream_ptr(stream)))
     return fg

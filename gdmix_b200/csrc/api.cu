@@ -18,6 +18,7 @@
 #include "host_lbfgs.h"
 #include "fe_lbfgs.cuh"
 #include "fe_plan.cuh"
+#include "fe_tile.cuh"
 #include "seqex_parser.h"
 #include "avro_writer.h"
 #include "re_fast.cuh"
@@ -838,72 +839,6 @@ void fe_rows_geometry(const gdmix_fe_rows *rows, const DeviceInfo &dev, int &gri
 }
 }  // namespace
 
-int gdmix_fe_rows_grid(const gdmix_fe_rows *rows, int32_t *grid)
-{
-    if (!rows || !grid) return fail(GDMIX_ERR_INVALID, "null argument");
-    DeviceInfo dev;
-    int rc = device_info(dev);
-    if (rc) return rc;
-    int g = 1, ts = 0;
-    fe_rows_geometry(rows, dev, g, ts);
-    *grid = g;
-    return GDMIX_OK;
-}
-
-int gdmix_fe_loss_grad_planned(const gdmix_fe_rows *rows, const gdmix_fe_plan *pl, const gdmix_lr_opts *o,
-                               const double *x, double *fg, void *stream)
-{
-    if (!rows || !pl || !o || !x || !fg) return fail(GDMIX_ERR_INVALID, "null argument");
-    if (!pl->colptr || !pl->item_col || !pl->item_begin || !pl->item_end || !pl->item_slot || !pl->scratch ||
-        (rows->nnz > 0 && (!pl->row || !pl->val)))
-        return fail(GDMIX_ERR_INVALID, "null array in gdmix_fe_plan");
-    DeviceInfo dev;
-    int rc = device_info(dev);
-    if (rc) return rc;
-    int grid = 1, team_shift = 0;
-    fe_rows_geometry(rows, dev, grid, team_shift);
-    const int64_t need = rows->n_rows + pl->n_slots + 2 * (int64_t)grid;
-    if (pl->scratch_doubles < need)
-        return fail(GDMIX_ERR_WORKSPACE, "fe plan scratch %lld doubles < required %lld", (long long)pl->scratch_doubles,
-                    (long long)need);
-    gdmix::FePlan P;
-    P.colptr = pl->colptr; P.row = pl->row; P.val = pl->val;
-    P.n_items = pl->n_items; P.item_col = pl->item_col; P.item_begin = pl->item_begin; P.item_end = pl->item_end;
-    P.item_slot = pl->item_slot; P.n_split = pl->n_split; P.split_col = pl->split_col;
-    P.split_slot_ptr = pl->split_slot_ptr;
-    P.dz = pl->scratch; P.slots = pl->scratch + rows->n_rows; P.block_part = P.slots + pl->n_slots;
-    P.rows_grid = grid; P.team_shift = team_shift;
-    cudaStream_t st = (cudaStream_t)stream;
-    {
-        // the leading coefficients of x ride in shared memory (aux_kernels.cuh)
-        const uint32_t head = (uint32_t)std::min<int64_t>(rows->n_features, gdmix::kFeHeadMax);
-        const uint32_t smem = gdmix::fe_rows_smem_bytes(head);
-        static std::atomic<int> configured{0};
-        if (!configured.load()) {
-            CUDA_TRY(cudaFuncSetAttribute(gdmix::fe_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)gdmix::fe_rows_smem_bytes(gdmix::kFeHeadMax)));
-            configured.store(1);
-        }
-        gdmix::fe_rows_kernel<false><<<grid, gdmix::kFeRowsThreads, smem, st>>>(*rows, *o, P, x, head, nullptr, nullptr);
-    }
-    // column pass: one launch per row tile (stream order keeps every warp inside the tile whose dz is in L2)
-    const int64_t n_launch = (pl->n_tiles > 1 && pl->tile_item_ptr) ? pl->n_tiles : 1;
-    for (int64_t t = 0; t < n_launch; t++) {
-        const int64_t i0 = n_launch > 1 ? pl->tile_item_ptr[t] : 0;
-        const int64_t i1 = n_launch > 1 ? pl->tile_item_ptr[t + 1] : pl->n_items;
-        if (i1 <= i0) continue;
-        if (i0 < 0 || i1 > pl->n_items) return fail(GDMIX_ERR_INVALID, "tile_item_ptr outside [0, n_items]");
-        const int cgrid = (int)std::max<int64_t>(1, std::min<int64_t>((i1 - i0 + 7) / 8, (int64_t)dev.sm_count * 16));
-        gdmix::fe_cols_kernel<<<cgrid, 256, 0, st>>>(*rows, *o, P, x, fg, i0, i1);
-        g_launches++;
-    }
-    const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((pl->n_split + 7) / 8, (int64_t)dev.sm_count * 4));
-    gdmix::fe_finish_kernel<<<fgrid, 256, 0, st>>>(*rows, *o, P, x, fg);
-    g_launches += 2;
-    CUDA_TRY(cudaGetLastError());
-    return GDMIX_OK;
-}
-
 int gdmix_fe_column_counts(const int32_t *col, int64_t nnz, int64_t n_features, int64_t *counts, void *stream)
 {
     if ((!col && nnz > 0) || !counts || nnz < 0 || n_features <= 0) return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_fe_column_counts");
@@ -979,14 +914,12 @@ int gdmix_fe_score(const gdmix_fe_rows *rows, const gdmix_lr_opts *o, const doub
     const uint32_t head = (uint32_t)std::min<int64_t>(rows->n_features, gdmix::kFeHeadMax);
     static std::atomic<int> configured{0};
     if (!configured.load()) {
-        CUDA_TRY(cudaFuncSetAttribute(gdmix::fe_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(gdmix::fe_score_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)gdmix::fe_rows_smem_bytes(gdmix::kFeHeadMax)));
         configured.store(1);
     }
-    gdmix::FePlan P;
-    memset(&P, 0, sizeof(P));
-    gdmix::fe_rows_kernel<true><<<grid, gdmix::kFeRowsThreads, gdmix::fe_rows_smem_bytes(head), (cudaStream_t)stream>>>(
-        *rows, *o, P, x, head, logit, logit_pc);
+    gdmix::fe_score_rows_kernel<<<grid, gdmix::kFeRowsThreads, gdmix::fe_rows_smem_bytes(head), (cudaStream_t)stream>>>(
+        *rows, *o, x, head, logit, logit_pc);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return GDMIX_OK;
@@ -1226,6 +1159,301 @@ int sort_pairs(const uint64_t *keys_in, const uint32_t *vals_in, int64_t n, int 
     return GDMIX_OK;
 }
 }  // namespace
+
+// ---- tiled fixed-effect objective: plan handle (fe_plan.cuh) + evaluation (fe_tile.cuh) ------------------------------
+struct gdmix_fe_tile_plan {
+    gdmix::FeTilePlan P{};
+    std::vector<void *> owned;
+    int64_t nnz = 0, n_hot_z = 0, n_cold_z = 0, n_hot_g = 0, n_cold_g = 0, bytes = 0;
+};
+
+namespace {
+int plan_alloc_bytes(gdmix_fe_tile_plan *h, void **out, size_t bytes, bool keep)
+{
+    void *p = nullptr;
+    bytes = std::max<size_t>(bytes, 256);
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(GDMIX_ERR_CUDA, "fixed-effect plan: cannot allocate %zu bytes of device memory", bytes);
+    }
+    *out = p;
+    if (keep) { h->owned.push_back(p); h->bytes += (int64_t)bytes; }
+    return GDMIX_OK;
+}
+#define plan_alloc(h, out, count, keep) plan_alloc_bytes((h), (void **)(out), sizeof(**(out)) * (size_t)(count), (keep))
+
+// out[0..n] = exclusive scan of len[0..n) (64-bit), ws: >= 4 * tiles + 8 * tiles + 8 bytes
+int exclusive_scan_u32(const uint32_t *len, int64_t n, int64_t *out, void *ws, cudaStream_t st)
+{
+    if (n <= 0) { CUDA_TRY(cudaMemsetAsync(out, 0, 8, st)); return GDMIX_OK; }
+    const int64_t nt = sort_tiles(n);
+    uint32_t *tile_sum = (uint32_t *)ws;
+    int64_t *tile_off = (int64_t *)((char *)ws + up256z(4 * (size_t)nt));
+    int64_t *total = tile_off + nt;
+    gdmix::tile_sum_kernel<<<(int)nt, gdmix::kSortThreads, 0, st>>>(len, n, tile_sum);
+    gdmix::tiles_exclusive_scan_kernel<<<1, 256, 0, st>>>(tile_sum, nt, tile_off, total);
+    gdmix::rowptr_from_len_kernel<<<(int)nt, gdmix::kSortThreads, 0, st>>>(len, n, tile_off, out);
+    g_launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+size_t scan_ws_bytes(int64_t n)
+{
+    const size_t nt = (size_t)sort_tiles(std::max<int64_t>(n, 1));
+    return up256z(4 * nt) + up256z(8 * nt + 8) + 256;
+}
+int bits_for(uint64_t v)
+{
+    int b = 1;
+    while (b < 64 && (v >> b)) b++;
+    return b;
+}
+}  // namespace
+
+void gdmix_fe_tile_plan_destroy(gdmix_fe_tile_plan *h)
+{
+    if (!h) return;
+    for (void *p : h->owned) cudaFree(p);
+    delete h;
+}
+
+gdmix_fe_tile_plan *gdmix_fe_tile_plan_create(const gdmix_fe_rows *rows, int32_t hz, int32_t hg, int32_t tile_rows,
+                                              int64_t l2_tile_rows, void *stream)
+{
+    if (!rows || rows->n_rows < 0 || rows->nnz < 0 || rows->n_features <= 0 || !rows->rowptr ||
+        (rows->nnz > 0 && (!rows->col || !rows->val))) {
+        fail(GDMIX_ERR_INVALID, "bad rows in gdmix_fe_tile_plan_create");
+        return nullptr;
+    }
+    if (rows->nnz >= (1ll << 32) - 4096 || rows->n_rows >= (1ll << 32) - 1) {
+        fail(GDMIX_ERR_TOO_LARGE, "a planned shard holds fewer than 2^32 rows and non-zeros (split the shard)");
+        return nullptr;
+    }
+    DeviceInfo dev;
+    if (device_info(dev)) return nullptr;
+    const int64_t D = rows->n_features, n = rows->n_rows, nnz = rows->nnz;
+    // defaults: as many coefficients / accumulators in shared memory as the two kernels can hold
+    const int64_t smem = dev.smem_optin;
+    const int64_t hz_max = (smem - 1024 - (gdmix::kFeZThreads / 32) * (gdmix::kFeZStage * 6 + gdmix::kFeZColdStage * 8)) / 8;
+    if (tile_rows <= 0) tile_rows = 8192;
+    if (tile_rows > 65536) { fail(GDMIX_ERR_INVALID, "tile_rows must be at most 65536 (16-bit rows inside a tile)"); return nullptr; }
+    const int64_t hg_max = std::min<int64_t>((smem - 4096 - 16 * (int64_t)gdmix::fe_g_tile_doubles((uint32_t)tile_rows)) / 8, 65536);
+    if (hz <= 0) hz = (int32_t)std::min<int64_t>(12288, hz_max);
+    if (hg <= 0) hg = (int32_t)std::min<int64_t>(24064, hg_max);
+    hz = (int32_t)std::min<int64_t>(std::min<int64_t>(hz, D), std::min<int64_t>(hz_max, 65536));
+    hg = (int32_t)std::min<int64_t>(std::min<int64_t>(hg, D), hg_max);
+    if (hz < 0 || hg < 1) {
+        fail(GDMIX_ERR_INVALID, "tile_rows = %d leaves no shared memory for the gradient accumulators (16 bytes per row of a tile, %lld bytes per CTA)",
+             tile_rows, (long long)smem);
+        return nullptr;
+    }
+    if (l2_tile_rows <= 0) l2_tile_rows = 4 << 20;
+    cudaStream_t st = (cudaStream_t)stream;
+    gdmix_fe_tile_plan *h = new (std::nothrow) gdmix_fe_tile_plan();
+    if (!h) { fail(GDMIX_ERR_INVALID, "out of host memory"); return nullptr; }
+    gdmix::FeTilePlan &P = h->P;
+    P.n_rows = n; P.n_features = D; P.hz = hz; P.hg = hg; P.tile_rows = tile_rows; P.l2_tile_rows = l2_tile_rows;
+    P.n_blocks = (n + 31) / 32;
+    P.n_tiles = (n + tile_rows - 1) / tile_rows;
+    P.n_l2_tiles = std::max<int64_t>(1, (n + l2_tile_rows - 1) / l2_tile_rows);
+    P.n_cold = D - hg;
+    P.z_grid = (int32_t)std::max<int64_t>(1, std::min<int64_t>((n + gdmix::kFeZThreads - 1) / gdmix::kFeZThreads, dev.sm_count));
+    P.g_grid = (int32_t)std::min<int64_t>(P.n_tiles, dev.sm_count);
+    h->nnz = nnz;
+    std::vector<void *> temps;
+    auto cleanup = [&](bool ok) {
+        cudaStreamSynchronize(st);
+        for (void *p : temps) cudaFree(p);
+        if (!ok) { gdmix_fe_tile_plan_destroy(h); h = nullptr; }
+    };
+#define PLAN_TRY(expr) do { if ((expr) != GDMIX_OK) { cleanup(false); return nullptr; } } while (0)
+#define PLAN_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { fail(GDMIX_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); cleanup(false); return nullptr; } } while (0)
+    auto temp_bytes = [&](void **out, size_t bytes) {
+        int rc = plan_alloc_bytes(h, out, bytes, false);
+        if (rc == GDMIX_OK) temps.push_back(*out);
+        return rc;
+    };
+#define temp(out, count) temp_bytes((void **)(out), sizeof(**(out)) * (size_t)(count))
+    const int gsm = dev.sm_count * 16;
+    auto grid_for = [&](int64_t items, int per) { return (int)std::max<int64_t>(1, std::min<int64_t>((items + per - 1) / per, gsm)); };
+    // ---- scratch of the evaluation -------------------------------------------------------------------------------
+    double *dz, *block_part, *acc_part, *cold_part;
+    PLAN_TRY(plan_alloc(h, &dz, (size_t)n, true));
+    PLAN_TRY(plan_alloc(h, &block_part, 2 * (size_t)P.z_grid, true));
+    PLAN_TRY(plan_alloc(h, &acc_part, (size_t)std::max(P.g_grid, 1) * hg, true));
+    PLAN_TRY(plan_alloc(h, &cold_part, (size_t)(P.n_l2_tiles * std::max<int64_t>(P.n_cold, 1)), true));
+    P.dz = dz; P.block_part = block_part; P.acc_part = acc_part; P.cold_part = cold_part;
+    // ---- z side ----------------------------------------------------------------------------------------------------
+    uint16_t *zh_len, *zc_len; uint32_t *blk_cnt, *cblk_cnt; int64_t *zh_blk, *zc_blk; int32_t *err; void *scan_ws;
+    PLAN_TRY(plan_alloc(h, &zh_len, (size_t)n, true));
+    PLAN_TRY(plan_alloc(h, &zh_blk, (size_t)P.n_blocks + 1, true));
+    PLAN_TRY(plan_alloc(h, &zc_len, (size_t)n, true));
+    PLAN_TRY(plan_alloc(h, &zc_blk, (size_t)P.n_blocks + 1, true));
+    PLAN_TRY(temp(&blk_cnt, (size_t)P.n_blocks));
+    PLAN_TRY(temp(&cblk_cnt, (size_t)P.n_blocks));
+    PLAN_TRY(temp(&err, 1));
+    { char *w; PLAN_TRY(temp(&w, scan_ws_bytes(std::max<int64_t>(n, P.n_tiles)))); scan_ws = w; }
+    PLAN_CUDA(cudaMemsetAsync(err, 0, 4, st));
+    int64_t tot_hot_z = 0, tot_cold_z = 0;
+    if (n > 0) {
+        gdmix::fe_zcount_kernel<<<grid_for(n, 256), 256, 0, st>>>(rows->rowptr, rows->col, n, hz, zh_len, zc_len, err);
+        gdmix::fe_zblock_kernel<<<grid_for(P.n_blocks, 256), 256, 0, st>>>(zh_len, n, P.n_blocks, 8u, blk_cnt);
+        gdmix::fe_zblock_kernel<<<grid_for(P.n_blocks, 256), 256, 0, st>>>(zc_len, n, P.n_blocks, 4u, cblk_cnt);
+        g_launches += 3;
+    }
+    PLAN_TRY(exclusive_scan_u32(blk_cnt, P.n_blocks, zh_blk, scan_ws, st));
+    PLAN_TRY(exclusive_scan_u32(cblk_cnt, P.n_blocks, zc_blk, scan_ws, st));
+    {
+        int32_t herr = 0;
+        PLAN_CUDA(cudaMemcpyAsync(&tot_hot_z, zh_blk + P.n_blocks, 8, cudaMemcpyDeviceToHost, st));
+        PLAN_CUDA(cudaMemcpyAsync(&tot_cold_z, zc_blk + P.n_blocks, 8, cudaMemcpyDeviceToHost, st));
+        PLAN_CUDA(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, st));
+        PLAN_CUDA(cudaStreamSynchronize(st));
+        if (herr) { fail(GDMIX_ERR_TOO_LARGE, "a row has more than 65535 non-zeros among (or outside) the %d most frequent features", hz); cleanup(false); return nullptr; }
+    }
+    float *zh_val, *zc_val; uint16_t *zh_col; int32_t *zc_col;
+    PLAN_TRY(plan_alloc(h, &zh_val, (size_t)tot_hot_z + 8, true));
+    PLAN_TRY(plan_alloc(h, &zh_col, (size_t)tot_hot_z + 8, true));
+    PLAN_TRY(plan_alloc(h, &zc_val, (size_t)tot_cold_z + 4, true));
+    PLAN_TRY(plan_alloc(h, &zc_col, (size_t)tot_cold_z + 4, true));
+    if (n > 0) {
+        gdmix::fe_zscatter_kernel<<<grid_for(P.n_blocks, 8), 256, 0, st>>>(rows->rowptr, rows->col, rows->val, n, hz, zh_len,
+                                                                          zc_len, zh_blk, zc_blk, zh_val, zh_col, zc_val, zc_col);
+        g_launches++;
+    }
+    P.zh_blk = zh_blk; P.zh_len = zh_len; P.zh_val = zh_val; P.zh_col = zh_col;
+    P.zc_blk = zc_blk; P.zc_len = zc_len; P.zc_val = zc_val; P.zc_col = zc_col;
+    h->n_hot_z = tot_hot_z; h->n_cold_z = tot_cold_z;
+    // ---- g side: one stable sort of all non-zeros by [class | tile | column] -------------------------------------------
+    const uint64_t hot_span = (uint64_t)std::max<int64_t>(P.n_tiles, 1) * (uint64_t)hg;
+    const uint64_t cold_span = (uint64_t)P.n_l2_tiles * (uint64_t)std::max<int64_t>(P.n_cold, 1);
+    const int class_shift = bits_for(std::max(hot_span, cold_span));
+    const uint64_t classbit = 1ull << class_shift;
+    int64_t *tile_begin, *gt_ptr, *gc_run;
+    PLAN_TRY(plan_alloc(h, &gt_ptr, (size_t)P.n_tiles + 1, true));
+    PLAN_TRY(plan_alloc(h, &gc_run, (size_t)(P.n_l2_tiles * P.n_cold) + 1, true));
+    PLAN_TRY(temp(&tile_begin, (size_t)P.n_tiles + 2));
+    int64_t n_hot_g = 0, tot_hot_g = 0;
+    uint32_t *row_of = nullptr, *perm = nullptr; uint64_t *keys = nullptr, *keys_sorted = nullptr;
+    if (nnz > 0) {
+        void *sort_ws;
+        const size_t sort_bytes = carve_sort(nullptr, nnz).bytes + 256;   // exactly what the radix passes use
+        PLAN_TRY(temp(&row_of, (size_t)nnz));
+        PLAN_TRY(temp(&keys, (size_t)nnz));
+        PLAN_TRY(temp(&keys_sorted, (size_t)nnz));
+        PLAN_TRY(temp(&perm, (size_t)nnz));
+        { char *w; PLAN_TRY(temp(&w, sort_bytes)); sort_ws = w; }
+        gdmix::fe_expand_rows_kernel<<<grid_for(n, 256), 256, 0, st>>>(rows->rowptr, n, row_of);
+        gdmix::fe_gkeys_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(rows->col, row_of, nnz, hg, tile_rows, l2_tile_rows,
+                                                                   std::max<int64_t>(P.n_cold, 1), classbit, keys);
+        g_launches += 2;
+        PLAN_TRY(sort_pairs(keys, nullptr, nnz, class_shift + 1, keys_sorted, perm, sort_ws, st));
+    }
+    // tile_begin[t] = first sorted entry of tile t (t = n_tiles: the number of hot entries)
+    gdmix::fe_lower_bound_kernel<<<grid_for(P.n_tiles + 1, 256), 256, 0, st>>>(keys_sorted, nnz, 0, (uint64_t)hg, P.n_tiles + 1, 0,
+                                                                              tile_begin);
+    g_launches++;
+    PLAN_CUDA(cudaMemcpyAsync(&n_hot_g, tile_begin + P.n_tiles, 8, cudaMemcpyDeviceToHost, st));
+    {
+        uint32_t *tcnt;
+        PLAN_TRY(temp(&tcnt, (size_t)std::max<int64_t>(P.n_tiles, 1)));
+        if (P.n_tiles > 0) {
+            gdmix::fe_gtile_count_kernel<<<grid_for(P.n_tiles, 256), 256, 0, st>>>(tile_begin, P.n_tiles, tcnt);
+            g_launches++;
+        }
+        PLAN_TRY(exclusive_scan_u32(tcnt, P.n_tiles, gt_ptr, scan_ws, st));
+        PLAN_CUDA(cudaMemcpyAsync(&tot_hot_g, gt_ptr + P.n_tiles, 8, cudaMemcpyDeviceToHost, st));
+        PLAN_CUDA(cudaStreamSynchronize(st));
+    }
+    const int64_t n_cold_g = nnz - n_hot_g;
+    float *gh_val, *gc_val; uint16_t *gh_row, *gh_col; uint32_t *gc_row;
+    PLAN_TRY(plan_alloc(h, &gh_val, (size_t)tot_hot_g + 8, true));
+    PLAN_TRY(plan_alloc(h, &gh_row, (size_t)tot_hot_g + 8, true));
+    PLAN_TRY(plan_alloc(h, &gh_col, (size_t)tot_hot_g + 8, true));
+    PLAN_TRY(plan_alloc(h, &gc_val, (size_t)n_cold_g + 4, true));
+    PLAN_TRY(plan_alloc(h, &gc_row, (size_t)n_cold_g + 4, true));
+    if (n_hot_g > 0) {
+        gdmix::fe_ghot_gather_kernel<<<grid_for(n_hot_g, 256), 256, 0, st>>>(keys_sorted, perm, n_hot_g, hg, tile_rows, tile_begin,
+                                                                            gt_ptr, rows->val, row_of, gh_val, gh_row, gh_col);
+        gdmix::fe_ghot_pad_kernel<<<grid_for(P.n_tiles, 8), 256, 0, st>>>(P.n_tiles, tile_begin, gt_ptr, gh_val, gh_row, gh_col);
+        g_launches += 2;
+    }
+    if (P.n_cold > 0) {
+        gdmix::fe_lower_bound_kernel<<<grid_for(P.n_l2_tiles * P.n_cold + 1, 256), 256, 0, st>>>(
+            keys_sorted, nnz, classbit, 1, P.n_l2_tiles * P.n_cold + 1, n_hot_g, gc_run);
+        g_launches++;
+        if (n_cold_g > 0) {
+            gdmix::fe_gcold_gather_kernel<<<grid_for(n_cold_g, 256), 256, 0, st>>>(perm + n_hot_g, n_cold_g, rows->val, row_of,
+                                                                                  gc_val, gc_row);
+            g_launches++;
+        }
+    } else {
+        PLAN_CUDA(cudaMemsetAsync(gc_run, 0, 8, st));
+    }
+    P.gt_ptr = gt_ptr; P.gh_val = gh_val; P.gh_row = gh_row; P.gh_col = gh_col;
+    P.gc_run = gc_run; P.gc_val = gc_val; P.gc_row = gc_row;
+    h->n_hot_g = n_hot_g; h->n_cold_g = n_cold_g;
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { fail(GDMIX_ERR_CUDA, "fixed-effect plan kernels: %s", cudaGetErrorString(e)); cleanup(false); return nullptr; }
+    }
+    cleanup(true);
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { fail(GDMIX_ERR_CUDA, "fixed-effect plan: %s", cudaGetErrorString(e)); gdmix_fe_tile_plan_destroy(h); return nullptr; }
+    }
+#undef PLAN_TRY
+#undef PLAN_CUDA
+#undef temp
+    return h;
+}
+
+int gdmix_fe_tile_plan_info(const gdmix_fe_tile_plan *h, int64_t *out8)
+{
+    if (!h || !out8) return fail(GDMIX_ERR_INVALID, "null argument");
+    out8[0] = h->P.hz; out8[1] = h->P.hg; out8[2] = h->P.tile_rows; out8[3] = h->P.n_tiles;
+    out8[4] = h->n_cold_z; out8[5] = h->n_cold_g; out8[6] = h->bytes; out8[7] = h->P.n_l2_tiles;
+    return GDMIX_OK;
+}
+
+int gdmix_fe_loss_grad_tiled(const gdmix_fe_rows *rows, const gdmix_fe_tile_plan *h, const gdmix_lr_opts *o, const double *x,
+                             double *fg, void *stream)
+{
+    if (!rows || !h || !o || !x || !fg) return fail(GDMIX_ERR_INVALID, "null argument");
+    const gdmix::FeTilePlan &P = h->P;
+    if (rows->n_rows != P.n_rows || rows->n_features != P.n_features || rows->nnz != h->nnz)
+        return fail(GDMIX_ERR_INVALID, "the plan was built for another shard");
+    if (P.n_rows > 0 && !rows->label) return fail(GDMIX_ERR_INVALID, "null label");
+    DeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    static std::atomic<int> configured{0};
+    if (!configured.load()) {
+        CUDA_TRY(cudaFuncSetAttribute(gdmix::fe_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin - 1024));
+        CUDA_TRY(cudaFuncSetAttribute(gdmix::fe_g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin - 4096));
+        configured.store(1);
+    }
+    gdmix::fe_z_kernel<<<P.z_grid, gdmix::kFeZThreads, gdmix::fe_z_smem_bytes((uint32_t)P.hz), st>>>(*rows, *o, P, x);
+    g_launches++;
+    if (P.g_grid > 0) {
+        gdmix::fe_g_kernel<<<P.g_grid, gdmix::kFeGThreads, gdmix::fe_g_smem_bytes((uint32_t)P.hg, (uint32_t)P.tile_rows), st>>>(P);
+        g_launches++;
+    }
+    if (P.n_cold > 0) {
+        const int cgrid = (int)std::max<int64_t>(1, std::min<int64_t>((P.n_cold + 7) / 8, (int64_t)dev.sm_count * 16));
+        for (int64_t t = 0; t < P.n_l2_tiles; t++) {
+            gdmix::fe_gcold_kernel<<<cgrid, 256, 0, st>>>(P, t);
+            g_launches++;
+        }
+    }
+    const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((P.n_features + 255) / 256, (int64_t)dev.sm_count * 4));
+    gdmix::fe_finish2_kernel<<<fgrid, 256, 0, st>>>(*rows, *o, P, x, fg);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
 
 int gdmix_partition_workspace_size(int64_t n, size_t *bytes)
 {
@@ -1600,6 +1828,32 @@ int gdmix_lbfgs_info(const gdmix_lbfgs *h, int32_t *nit, int32_t *nfev, int32_t 
 void gdmix_lbfgs_destroy(gdmix_lbfgs *h) { delete h; }
 
 // ---- device-resident replicated L-BFGS of the fixed-effect solve (fe_lbfgs.cuh) ----------------------------------
+namespace {
+// Status records the host polls: one page of pinned memory for the life of the process (cudaFreeHost of a small
+// pinned block costs tens to hundreds of milliseconds next to large pinned staging buffers; a solve must not pay it).
+constexpr int kStatusSlots = 128;
+std::mutex g_status_mu;
+gdmix::FeLbStatus *g_status_page = nullptr;
+bool g_status_used[kStatusSlots] = {false};
+gdmix::FeLbStatus *status_slot_acquire()
+{
+    std::lock_guard<std::mutex> lk(g_status_mu);
+    if (!g_status_page && cudaMallocHost((void **)&g_status_page, sizeof(gdmix::FeLbStatus) * kStatusSlots) != cudaSuccess) {
+        cudaGetLastError();
+        g_status_page = nullptr;
+        return nullptr;
+    }
+    for (int i = 0; i < kStatusSlots; i++)
+        if (!g_status_used[i]) { g_status_used[i] = true; return g_status_page + i; }
+    return nullptr;
+}
+void status_slot_release(gdmix::FeLbStatus *p)
+{
+    std::lock_guard<std::mutex> lk(g_status_mu);
+    if (p && g_status_page && p >= g_status_page && p < g_status_page + kStatusSlots) g_status_used[p - g_status_page] = false;
+}
+}  // namespace
+
 struct gdmix_fe_lbfgs {
     gdmix::FeLbBuffers B{};
     gdmix::FeLbState init{};
@@ -1624,9 +1878,11 @@ gdmix_fe_lbfgs *gdmix_fe_lbfgs_create(int64_t n, const gdmix_lr_opts *o, double 
     const size_t off_state = 0, off_status = 1024, off_vec = 2048;
     const size_t doubles = (size_t)(4 * n + 2 * mm * n + 4 * nb);
     const size_t bytes = off_vec + 8 * doubles;
-    if (cudaMalloc(&h->arena, bytes) != cudaSuccess || cudaMallocHost((void **)&h->status_host, sizeof(gdmix::FeLbStatus)) != cudaSuccess) {
-        fail(GDMIX_ERR_CUDA, "gdmix_fe_lbfgs_create: cannot allocate %zu bytes of device memory", bytes);
-        if (h->arena) cudaFree(h->arena);
+    h->status_host = status_slot_acquire();
+    if (!h->status_host || cudaMalloc(&h->arena, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        fail(GDMIX_ERR_CUDA, "gdmix_fe_lbfgs_create: cannot allocate %zu bytes of device memory (or no status slot)", bytes);
+        status_slot_release(h->status_host);
         delete h;
         return nullptr;
     }
@@ -1692,7 +1948,7 @@ void gdmix_fe_lbfgs_destroy(gdmix_fe_lbfgs *h)
 {
     if (!h) return;
     if (h->arena) cudaFree(h->arena);
-    if (h->status_host) cudaFreeHost(h->status_host);
+    status_slot_release(h->status_host);
     delete h;
 }
 

@@ -175,36 +175,9 @@ __global__ void __launch_bounds__(256) fe_hessian_kernel(const gdmix_fe_rows R, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Fixed-effect objective / gradient without atomics (gdmix_fe_loss_grad_planned).
-//
-//   fe_rows_kernel   a team of T lanes per row (T = 2^k ~ non-zeros per row, so loads coalesce): z, loss,
-//                    dz_i = d loss / d z_i -> dz[] (fp64), per-CTA partial sums of the loss and of dz.
-//   fe_cols_kernel   the gradient X^T dz from the column-major copy of the shard (built once per training by
-//                    the host): one warp per work item = a column, or a slice of at most kFeSlice non-zeros of
-//                    a long column; complete columns are stored straight into fg, slices go to a slot buffer.
-//   fe_finish_kernel sums the slices of every split column and the per-CTA partials in a fixed order, adds
-//                    the L2 term and the intercept's gradient.
-// Every sum has a fixed order: the objective is bitwise reproducible run to run, and popular features (one
-// feature can own 10 % of all non-zeros) cost no more per non-zero than rare ones -- with atomics they serialise.
+// Fixed-effect scoring pass (gdmix_fe_score): the staged row walk.  (The objective / gradient over a planned shard
+// lives in fe_tile.cuh.)
 // ---------------------------------------------------------------------------------------------------------
-struct FePlan {
-    const int64_t *colptr;    // [D+1]
-    const int32_t *row;       // [nnz] ascending inside a column
-    const float *val;         // [nnz]
-    int64_t n_items;
-    const int32_t *item_col;  // [n_items]
-    const int64_t *item_begin, *item_end;
-    const int32_t *item_slot; // [n_items] -1: the item is a whole column
-    int64_t n_split;
-    const int32_t *split_col;       // [n_split]
-    const int64_t *split_slot_ptr;  // [n_split+1]
-    double *dz;               // [n_rows]
-    double *slots;            // [n_slots]
-    double *block_part;       // [2 * rows_grid]
-    int32_t rows_grid;
-    int32_t team_shift;       // log2 lanes per row
-};
-
 constexpr int kFeRowsThreads = 512;         // fe_rows_kernel CTA: sixteen warps, one CTA per SM
 constexpr uint32_t kFeStageCap = 1024;      // non-zeros one warp stages at a time (4 KB values + 4 KB columns)
 constexpr uint32_t kFeHeadMax = 8192;       // leading coefficients of x kept in shared memory (64 KB)
@@ -226,12 +199,10 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// SCORE = false: loss and dz per row (the objective's first pass).  SCORE = true: the same walk, but the row's
-// z goes out as the two fp32 logits of _scoring_fn (fixed_effect_lr_lbfgs_model.py:214-270) and nothing else is kept.
-template <bool SCORE>
-__global__ void __launch_bounds__(kFeRowsThreads, 1) fe_rows_kernel(const gdmix_fe_rows R, const gdmix_lr_opts o,
-                                                                    const FePlan P, const double *x, const uint32_t head,
-                                                                    float *logit, float *logit_pc)
+// The row's z goes out as the two fp32 logits of _scoring_fn (fixed_effect_lr_lbfgs_model.py:214-270).
+__global__ void __launch_bounds__(kFeRowsThreads, 1) fe_score_rows_kernel(const gdmix_fe_rows R, const gdmix_lr_opts o,
+                                                                          const double *x, const uint32_t head,
+                                                                          float *logit, float *logit_pc)
 {
     // A warp owns 32 consecutive rows at a time.  Their non-zeros are one contiguous range of the CSR arrays:
     // the warp copies it into shared memory asynchronously (cp.async, 16 bytes per lane and instruction when
@@ -242,11 +213,9 @@ __global__ void __launch_bounds__(kFeRowsThreads, 1) fe_rows_kernel(const gdmix_
     // The x gather is what bounds this kernel: 32 lanes x 32 different 128-byte lines cost the L1 one cycle or
     // two per line.  So the first `head` coefficients of x live in shared memory (the host side numbers features
     // by falling frequency, so these are the hot ones) and only the tail is gathered through L1 / L2.
-    // The loss / dz arithmetic (one exp, one log1p, one division per row) runs on 32 rows in 32 lanes.  Blocks
-    // with more non-zeros than the stage holds are taken in runs of as many rows as fit; a single row longer
+    // Blocks with more non-zeros than the stage holds are taken in runs of as many rows as fit; a single row longer
     // than the stage is summed by the whole warp straight from global memory.  Every sum has a fixed order.
     extern __shared__ __align__(16) unsigned char fe_smem[];
-    __shared__ double sv[kFeRowsThreads / 32], sd[kFeRowsThreads / 32];
     const int hi = o.has_intercept ? 1 : 0;
     const int64_t D = R.n_features;
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -258,7 +227,6 @@ __global__ void __launch_bounds__(kFeRowsThreads, 1) fe_rows_kernel(const gdmix_
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const double b0 = hi ? x[D] : 0.0;
-    double value = 0.0, dz_sum = 0.0;
     const int64_t nblocks = (R.n_rows + 31) >> 5;
     // row pointers of the warp's NEXT block are fetched while the current one is summed
     int64_t nqs = 0, nqe = 0;
@@ -321,114 +289,11 @@ __global__ void __launch_bounds__(kFeRowsThreads, 1) fe_rows_kernel(const gdmix_
             done += nfit;
         }
         const int64_t i = base + lane;
-        if (SCORE) {
-            if (i < R.n_rows) {
-                const double z = myz + b0, offs = R.offset ? (double)R.offset[i] : 0.0;
-                logit_pc[i] = (float)z;
-                logit[i] = (float)(z + offs);
-            }
-            continue;
-        }
         if (i < R.n_rows) {
-            double z = myz + (R.offset ? (double)R.offset[i] : 0.0);
-            z += b0;
-            const double yi = (double)R.label[i], wi = R.weight ? (double)R.weight[i] : 1.0;
-            double dz;
-            if (R.linear_regression) {
-                const double e = yi - z;
-                value = fma(wi * e, e, value);
-                dz = -2.0 * wi * e;
-            } else {
-                const double ex = exp(-fabs(z));
-                value = fma(wi, fmax(z, 0.0) - z * yi + log1p(ex), value);
-                const double inv = 1.0 / (1.0 + ex);
-                dz = wi * ((z >= 0.0 ? inv : ex * inv) - yi);
-            }
-            P.dz[i] = dz;
-            dz_sum += dz;
+            const double z = myz + b0, offs = R.offset ? (double)R.offset[i] : 0.0;
+            logit_pc[i] = (float)z;
+            logit[i] = (float)(z + offs);
         }
-    }
-    if (SCORE) return;
-    value = warp_sum(value);
-    dz_sum = warp_sum(dz_sum);
-    if (lane == 0) { sv[wib] = value; sd[wib] = dz_sum; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double v = 0.0, dsum = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { v += sv[w]; dsum += sd[w]; }
-        P.block_part[2 * blockIdx.x] = v;
-        P.block_part[2 * blockIdx.x + 1] = dsum;
-    }
-}
-
-__global__ void __launch_bounds__(256) fe_cols_kernel(const gdmix_fe_rows R, const gdmix_lr_opts o, const FePlan P,
-                                                      const double *x, double *fg, const int64_t item0,
-                                                      const int64_t item1)
-{
-    const uint32_t lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const double l2w = o.l2 / (double)(R.num_workers > 0 ? R.num_workers : 1);
-    for (int64_t it = item0 + warp; it < item1; it += nwarps) {
-        const int64_t b = P.item_begin[it], e = P.item_end[it];
-        double s0 = 0.0, s1 = 0.0;
-        int64_t q = b + lane;
-        for (; q + 32 < e; q += 64) {
-            const double a0 = (double)P.val[q] * P.dz[P.row[q]];
-            const double a1 = (double)P.val[q + 32] * P.dz[P.row[q + 32]];
-            s0 += a0; s1 += a1;
-        }
-        if (q < e) s0 = fma((double)P.val[q], P.dz[P.row[q]], s0);
-        const double s = warp_sum(s0 + s1);
-        if (lane == 0) {
-            const int32_t slot = P.item_slot[it];
-            if (slot < 0) {
-                const int32_t c = P.item_col[it];
-                fg[1 + c] = s + l2w * x[c];   // features are always regularised (the intercept is handled apart)
-            } else {
-                P.slots[slot] = s;
-            }
-        }
-    }
-}
-
-// Split columns (slices summed in slice order), then -- CTA 0 -- the objective value and the intercept's gradient
-// from the per-CTA partials of fe_rows_kernel and the L2 term, all in a fixed order.
-__global__ void __launch_bounds__(256) fe_finish_kernel(const gdmix_fe_rows R, const gdmix_lr_opts o, const FePlan P,
-                                                        const double *x, double *fg)
-{
-    const int hi = o.has_intercept ? 1 : 0;
-    const int64_t D = R.n_features;
-    const double l2w = o.l2 / (double)(R.num_workers > 0 ? R.num_workers : 1);
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
-    {
-        // a warp per split column: lane-strided partial sums, then a butterfly (fixed order)
-        const uint32_t lane = threadIdx.x & 31;
-        for (int64_t sidx = tid >> 5; sidx < P.n_split; sidx += nth >> 5) {
-            double s = 0.0;
-            for (int64_t k = P.split_slot_ptr[sidx] + lane; k < P.split_slot_ptr[sidx + 1]; k += 32) s += P.slots[k];
-            s = warp_sum(s);
-            const int32_t c = P.split_col[sidx];
-            if (lane == 0) fg[1 + c] = s + l2w * x[c];
-        }
-    }
-    if (blockIdx.x != 0) return;
-    __shared__ double sh[3][256];
-    double v = 0.0, dsum = 0.0, sq = 0.0;
-    for (int32_t b = threadIdx.x; b < P.rows_grid; b += 256) { v += P.block_part[2 * b]; dsum += P.block_part[2 * b + 1]; }
-    const int64_t preg = (hi && !o.regularize_bias) ? D : D + hi;
-    for (int64_t j = threadIdx.x; j < preg; j += 256) sq = fma(x[j], x[j], sq);
-    sh[0][threadIdx.x] = v; sh[1][threadIdx.x] = dsum; sh[2][threadIdx.x] = sq;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s)
-            for (int k = 0; k < 3; k++) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        fg[0] = sh[0][0] + 0.5 * l2w * sh[2][0];
-        if (hi) fg[1 + D] = sh[1][0] + (o.regularize_bias ? l2w * x[D] : 0.0);
     }
 }
 

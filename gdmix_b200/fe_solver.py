@@ -47,7 +47,7 @@ class FixedEffectSolver:
     profile     record CUDA-event times of the three phases of every evaluation (kernels / all-reduce / step)
     """
 
-    def __init__(self, rows, opts, n_features=None, group=None, solver="device", profile=False):
+    def __init__(self, rows, opts, n_features=None, group=None, solver="device", profile=False, plan_args=None):
         import torch
         self.torch = torch
         self.rows = rows
@@ -55,6 +55,7 @@ class FixedEffectSolver:
         self.group = group
         self.solver = solver
         self.profile = profile
+        self.plan_args = dict(plan_args or {})   # hz / hg / tile_rows / l2_tile_rows of capi.DeviceFeTilePlan (tests)
         self.n_features = int(n_features if n_features is not None else rows.n_features)
         self.hi = 1 if opts.has_intercept else 0
         self.n_coef = self.n_features + self.hi
@@ -80,7 +81,7 @@ class FixedEffectSolver:
 
     def _prepare(self):
         """Once per training run: the feature order of the device (see the module docstring) and the column-major
-        copy of the shard (capi.DeviceFePlan)."""
+        layout of the shard for the tiled objective (capi.DeviceFeTilePlan)."""
         torch = self.torch
         rows, D = self.rows, self.n_features
         if D > capi.FE_HEAD:
@@ -96,7 +97,7 @@ class FixedEffectSolver:
             tail = torch.arange(D, self.n_coef, dtype=torch.int64, device=self.device)  # the intercept stays last
             self._perm = torch.cat([by_freq.to(torch.int64), tail])
             self._rows_eval = ranked
-        self.plan = capi.DeviceFePlan(self._rows_eval)
+        self.plan = capi.DeviceFeTilePlan(self._rows_eval, **self.plan_args)
 
     def _to_device_order(self, x_np):
         x = self.torch.from_numpy(np.ascontiguousarray(x_np, dtype=np.float64)).to(self.device)

@@ -21,6 +21,8 @@
  *                        -> predict_proba(return_logits=True)    binary_logistic_regression.py:241-262
  *   gdmix_fe_loss_grad   _train_model_fn (per-worker partial)    models/custom/fixed_effect_lr_lbfgs_model.py:309-381
  *                        (the all-reduce at :382-390 stays with the caller: NCCL on the same stream)
+ *   gdmix_fe_tile_plan_*, gdmix_fe_loss_grad_tiled   the same partial over a shard laid out once per training run
+ *   gdmix_fe_lbfgs_*     fmin_l_bfgs_b replicated on every worker (:635-643), state resident on the device
  *   gdmix_fe_score       _scoring_fn                             fixed_effect_lr_lbfgs_model.py:214-307
  *   gdmix_partition_ids  getPartitionIdUDF                       gdmix-data/.../utils/PartitionUtils.scala:31-37
  *   gdmix_group_by_key, gdmix_csr_gather_rows, gdmix_local_index_*   groupBy(entity) + per-entity np.unique
@@ -201,42 +203,24 @@ GDMIX_API int gdmix_re_score(const gdmix_re_batch *batch, const gdmix_lr_opts *o
  * all-reduces fg (NCCL, same stream) and feeds it to the replicated L-BFGS step. */
 GDMIX_API int gdmix_fe_loss_grad(const gdmix_fe_rows *rows, const gdmix_lr_opts *opts, const double *x, double *fg,
                                  void *stream);
-/* The same objective / gradient without atomics, for callers that evaluate many times over one shard (every
- * L-BFGS run does): the caller supplies, once, the column-major copy of the shard and a list of work items, and
- * the scratch the passes need.  Three kernels: rows (z, loss, dz), columns (X^T dz by segmented sums), finish.
- * Every sum has a fixed order (bitwise reproducible), and a feature that owns a large share of the non-zeros
- * costs no more per non-zero than a rare one.
- *   colptr[D+1], row[nnz] (ascending inside a column), val[nnz]   the shard sorted by column
- *   items: one per column that has at most `slice` non-zeros (slot = -1), else one per slice of it
- *          (slot = index into the slot buffer); split_col / split_slot_ptr list the sliced columns
- *   scratch: n_rows + n_slots + 2 * rows_grid doubles, rows_grid as returned by gdmix_fe_rows_grid */
-typedef struct gdmix_fe_plan {
-    const int64_t *colptr;
-    const int32_t *row;
-    const float *val;
-    int64_t n_items;
-    const int32_t *item_col;
-    const int64_t *item_begin;
-    const int64_t *item_end;
-    const int32_t *item_slot;
-    int64_t n_split;
-    const int32_t *split_col;
-    const int64_t *split_slot_ptr;
-    int64_t n_slots;
-    double *scratch;
-    int64_t scratch_doubles;
-    /* Row tiling of the column-major copy (optional; n_tiles <= 1 or tile_item_ptr == NULL: one launch over all
-     * items).  When the copy is ordered by (row tile, column, row), tile t's items are
-     * [tile_item_ptr[t], tile_item_ptr[t+1]) -- a HOST array of n_tiles + 1 entries -- and the column pass runs
-     * tile after tile, so that the dz entries it gathers (tile rows x 8 bytes) stay in L2: on a shard whose dz
-     * outgrows L2 every gathered entry otherwise costs a 32-byte DRAM sector.  A column with items in several
-     * tiles is a split column (its items own slots). */
-    int64_t n_tiles;
-    const int64_t *tile_item_ptr;
-} gdmix_fe_plan;
-GDMIX_API int gdmix_fe_rows_grid(const gdmix_fe_rows *rows, int32_t *grid);
-GDMIX_API int gdmix_fe_loss_grad_planned(const gdmix_fe_rows *rows, const gdmix_fe_plan *plan,
-                                         const gdmix_lr_opts *opts, const double *x, double *fg, void *stream);
+/* The objective / gradient over a shard laid out once per training run (the shard does not change between the ~100
+ * evaluations of an L-BFGS run).  The columns of `rows` are expected in falling-frequency order (rank 0 = most frequent
+ * feature; gdmix_fe_column_counts + gdmix_remap_i32 produce that order) -- any order is correct, this one is fast.
+ *   _create   builds, on the device: the row-major copy split into a HOT part (rank < hz, the coefficients the z pass
+ *             keeps in shared memory; fp32 value + 16-bit rank) and a COLD part; the column-major copy of the ranks < hg
+ *             tiled by `tile_rows` rows (fp32 value + 16-bit row + 16-bit rank; the g pass keeps a tile's dz and hg fp64
+ *             accumulators in shared memory) and of the ranks >= hg tiled by `l2_tile_rows` rows (their dz gathers stay in
+ *             L2).  0 for any of hz / hg / tile_rows / l2_tile_rows = choose.  Synchronises the stream; NULL on error.
+ *   gdmix_fe_loss_grad_tiled   fg as gdmix_fe_loss_grad, without atomics: every sum has a fixed order (bitwise
+ *             reproducible); enqueue-only, capturable in a CUDA graph.  `rows` supplies label / weight / offset.
+ *   _info     out8 = { hz, hg, tile_rows, tiles, cold non-zeros of the z side, of the g side, plan bytes, L2 tiles } */
+typedef struct gdmix_fe_tile_plan gdmix_fe_tile_plan;
+GDMIX_API gdmix_fe_tile_plan *gdmix_fe_tile_plan_create(const gdmix_fe_rows *rows, int32_t hz, int32_t hg, int32_t tile_rows,
+                                                        int64_t l2_tile_rows, void *stream);
+GDMIX_API void gdmix_fe_tile_plan_destroy(gdmix_fe_tile_plan *plan);
+GDMIX_API int gdmix_fe_tile_plan_info(const gdmix_fe_tile_plan *plan, int64_t *out8);
+GDMIX_API int gdmix_fe_loss_grad_tiled(const gdmix_fe_rows *rows, const gdmix_fe_tile_plan *plan, const gdmix_lr_opts *opts,
+                                       const double *x, double *fg, void *stream);
 
 /* Set-up helpers of the planned objective (device pointers; once per training run, the shard does not change between
  * the evaluations of an L-BFGS run): non-zeros per feature (synchronises the stream; an index outside [0, n_features)

@@ -78,49 +78,11 @@ def test_fe_score_matches_definition():
     np.testing.assert_allclose(logit, (z + FE_ARR[k + "_off"]).astype(np.float32), rtol=1e-6, atol=1e-6)
 
 
-def test_planned_path_matches_atomic_path_and_is_reproducible():
-    """gdmix_fe_loss_grad_planned (column-major copy, no atomics) vs gdmix_fe_loss_grad on skewed columns, incl.
-    columns long enough to be sliced, empty columns, rows of different lengths, weights/offsets, no intercept."""
-    rng = np.random.default_rng(3)
-    n, D = 30000, 700
-    lens = rng.integers(0, 12, n)
-    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-    nnz = int(rowptr[-1])
-    col = np.minimum((D ** rng.random(nnz) - 1).astype(np.int32), D - 1)
-    col[col == 5] = 6                                   # column 5 stays empty
-    val = rng.standard_normal(nnz).astype(np.float32)
-    y = (rng.random(n) < 0.4).astype(np.float32)
-    w = rng.uniform(0.5, 2.0, n).astype(np.float32)
-    off = rng.standard_normal(n).astype(np.float32)
-    for hi, rb, lin in ((True, True, False), (True, False, False), (False, False, False), (True, True, True)):
-        rows = capi.DeviceFeRows(rowptr, col, val, y, w, off, D, linear_regression=lin, num_workers=2)
-        opts = capi.make_opts(l2=0.7, regularize_bias=rb, has_intercept=hi)
-        x = torch.from_numpy(rng.standard_normal(D + (1 if hi else 0)) * 0.1).cuda()
-        plan = capi.DeviceFePlan(rows, slice_nnz=256)
-        assert plan.n_split > 0
-        a = capi.fe_loss_grad_device(rows, opts, x).cpu().numpy()
-        b = capi.fe_loss_grad_device(rows, opts, x, plan=plan).cpu().numpy()
-        c = capi.fe_loss_grad_device(rows, opts, x, plan=plan).cpu().numpy()
-        np.testing.assert_allclose(b, a, rtol=1e-11, atol=1e-9)
-        np.testing.assert_array_equal(b, c)
-        # the same shard with its column-major copy tiled by rows (what a shard larger than L2's worth of dz gets)
-        tiled = capi.DeviceFePlan(rows, slice_nnz=256, tile_rows=7000)
-        assert tiled.n_tiles == 5 and tiled.n_split > plan.n_split
-        t1 = capi.fe_loss_grad_device(rows, opts, x, plan=tiled).cpu().numpy()
-        t2 = capi.fe_loss_grad_device(rows, opts, x, plan=tiled).cpu().numpy()
-        np.testing.assert_array_equal(t1, t2)
-        np.testing.assert_allclose(t1, b, rtol=1e-12, atol=1e-11)
-        blk = O.FeBlock(n, D, rowptr, col, val, y, w, off, linear_regression=lin, num_workers=2)
-        oo = O.make_opts(l2=0.7, regularize_bias=rb, has_intercept=hi)
-        f_o, g_o = O.fe_loss_grad(blk, oo, x.cpu().numpy())
-        np.testing.assert_allclose(b[0], f_o, rtol=1e-12)
-        np.testing.assert_allclose(b[1:], g_o, rtol=1e-10, atol=1e-10)
-
-
-def test_planned_path_rows_of_every_size():
-    """fe_rows_kernel stages 32 rows per warp in shared memory (1024 non-zeros at a time): blocks that fit, blocks
-    taken in several runs, single rows longer than the stage (summed by the whole warp from global memory), empty
-    rows, a ragged last block -- against the oracle."""
+@pytest.mark.parametrize("pa", [dict(), dict(hz=40, hg=90, tile_rows=50)], ids=["default", "split"])
+def test_tiled_path_rows_of_every_size(pa):
+    """fe_z_kernel stages 32 rows per warp in shared memory (1024 hot / 256 cold entries at a time): blocks that fit,
+    blocks that do not (walked from global memory), single rows longer than the stage, empty rows, a ragged last block
+    -- against the oracle; the scoring walk (gdmix_fe_score) over the same rows against the definition."""
     rng = np.random.default_rng(17)
     D = 5000
     lens = np.concatenate([np.full(64, 32), rng.integers(0, 90, 200), [3000, 0, 1024, 1025, 1, 0, 2047],
@@ -136,7 +98,7 @@ def test_planned_path_rows_of_every_size():
     x = rng.standard_normal(D + 1) * 0.02
     rows = capi.DeviceFeRows(rowptr, col, val, y, w, off, D)
     opts = capi.make_opts(l2=0.3, regularize_bias=False, has_intercept=True)
-    plan = capi.DeviceFePlan(rows)
+    plan = capi.DeviceFeTilePlan(rows, **pa)
     xd = torch.from_numpy(x).cuda()
     b = capi.fe_loss_grad_device(rows, opts, xd, plan=plan).cpu().numpy()
     c = capi.fe_loss_grad_device(rows, opts, xd, plan=plan).cpu().numpy()
@@ -145,6 +107,10 @@ def test_planned_path_rows_of_every_size():
     f_o, g_o = O.fe_loss_grad(blk, O.make_opts(l2=0.3, regularize_bias=False, has_intercept=True), x)
     np.testing.assert_allclose(b[0], f_o, rtol=1e-12)
     np.testing.assert_allclose(b[1:], g_o, rtol=1e-10, atol=1e-10)
+    logit, per = capi.fe_score_device(rows, opts, xd)
+    z = np.array([np.dot(val[rowptr[i]:rowptr[i + 1]].astype(np.float64), x[col[rowptr[i]:rowptr[i + 1]]]) for i in range(n)])
+    np.testing.assert_allclose(per.cpu().numpy(), (z + x[-1]).astype(np.float32), rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(logit.cpu().numpy(), (z + x[-1] + off).astype(np.float32), rtol=2e-6, atol=1e-6)
 
 
 def test_solver_frequency_ranking_is_invisible_to_the_caller():
@@ -169,7 +135,7 @@ def test_solver_frequency_ranking_is_invisible_to_the_caller():
     np.testing.assert_allclose(g, g_o, rtol=1e-10, atol=1e-10)
     xa, ia = solver.fit()
     plain = FixedEffectSolver(rows, opts)
-    plain.plan = capi.DeviceFePlan(rows)      # skips _prepare: no ranking
+    plain.plan = capi.DeviceFeTilePlan(rows)  # skips _prepare: no ranking
     xb, ib = plain.fit()
     assert (ia["nit"], ia["nfev"]) == (ib["nit"], ib["nfev"])
     np.testing.assert_allclose(xa, xb, rtol=1e-9, atol=1e-12)
@@ -227,3 +193,95 @@ def test_device_lbfgs_stops_at_once_on_a_stationary_start():
     x2, info2 = FixedEffectSolver(_rows(c), _opts(c, capi), solver="host").fit(FE_ARR[c["key"] + "_theta"])
     assert (info["nit"], info["nfev"], info["status"]) == (info2["nit"], info2["nfev"], info2["status"])
     np.testing.assert_allclose(x, x2, rtol=1e-10, atol=1e-12)
+
+
+def _ragged_shard(rng, n, D, max_len, long_rows=()):
+    lens = rng.integers(0, max_len + 1, n)
+    for i, L in long_rows:
+        lens[i] = L
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    nnz = int(rowptr[-1])
+    col = np.minimum((D ** rng.random(nnz) - 1).astype(np.int32), D - 1)   # skewed, duplicates inside rows
+    val = rng.standard_normal(nnz).astype(np.float32)
+    y = (rng.random(n) < 0.4).astype(np.float32)
+    w = rng.uniform(0.5, 2.0, n).astype(np.float32)
+    off = rng.standard_normal(n).astype(np.float32)
+    return rowptr, col, val, y, w, off
+
+
+TILE_PARAMS = [dict(), dict(hz=16, hg=32, tile_rows=64, l2_tile_rows=7000), dict(hz=1, hg=1, tile_rows=1, l2_tile_rows=100),
+               dict(hz=700, hg=5, tile_rows=8192), dict(hz=3, hg=699, tile_rows=300, l2_tile_rows=1 << 22)]
+
+
+@pytest.mark.parametrize("pa", TILE_PARAMS, ids=[str(i) for i in range(len(TILE_PARAMS))])
+def test_tiled_objective_matches_atomic_path_and_oracle(pa):
+    """gdmix_fe_loss_grad_tiled (hot / cold split of x and of the gradient, tiles of rows, reduce-by-key) against the
+    single-pass atomic kernel and the oracle: skewed columns with duplicates, empty rows, rows longer than a warp's
+    stage, an empty column, weights / offsets, no intercept, linear regression; every split forced by small hz / hg /
+    tile sizes.  Bitwise reproducible."""
+    rng = np.random.default_rng(31)
+    n, D = 30000, 700
+    rowptr, col, val, y, w, off = _ragged_shard(rng, n, D, 11, long_rows=[(7, 3000), (20001, 1500)])
+    col[col == 5] = 6                                   # column 5 stays empty
+    for hi, rb, lin in ((True, True, False), (True, False, False), (False, False, False), (True, True, True)):
+        rows = capi.DeviceFeRows(rowptr, col, val, y, w, off, D, linear_regression=lin, num_workers=2)
+        opts = capi.make_opts(l2=0.7, regularize_bias=rb, has_intercept=hi)
+        x = torch.from_numpy(rng.standard_normal(D + (1 if hi else 0)) * 0.1).cuda()
+        plan = capi.DeviceFeTilePlan(rows, **pa)
+        a = capi.fe_loss_grad_device(rows, opts, x).cpu().numpy()
+        b = capi.fe_loss_grad_device(rows, opts, x, plan=plan).cpu().numpy()
+        c = capi.fe_loss_grad_device(rows, opts, x, plan=plan).cpu().numpy()
+        np.testing.assert_array_equal(b, c)
+        np.testing.assert_allclose(b, a, rtol=1e-11, atol=1e-9)
+        blk = O.FeBlock(n, D, rowptr, col, val, y, w, off, linear_regression=lin, num_workers=2)
+        f_o, g_o = O.fe_loss_grad(blk, O.make_opts(l2=0.7, regularize_bias=rb, has_intercept=hi), x.cpu().numpy())
+        np.testing.assert_allclose(b[0], f_o, rtol=1e-12)
+        np.testing.assert_allclose(b[1:], g_o, rtol=1e-10, atol=1e-10)
+        plan.close()
+
+
+def test_tiled_objective_edge_shapes():
+    """No rows; no non-zeros; one row; a single column; every row empty but one."""
+    opts = capi.make_opts(l2=0.5, regularize_bias=True, has_intercept=True)
+    oo = O.make_opts(l2=0.5, regularize_bias=True, has_intercept=True)
+    cases = []
+    cases.append((np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(0, np.float32), np.zeros(0, np.float32), 4))
+    cases.append((np.zeros(6, np.int64), np.zeros(0, np.int32), np.zeros(0, np.float32), np.ones(5, np.float32), 4))
+    cases.append((np.array([0, 3], np.int64), np.array([2, 0, 2], np.int32), np.array([1.5, -2, 0.25], np.float32),
+                  np.ones(1, np.float32), 3))
+    cases.append((np.arange(0, 41, dtype=np.int64), np.zeros(40, np.int32), np.linspace(-1, 1, 40).astype(np.float32),
+                  (np.arange(40) % 2).astype(np.float32), 1))
+    rp = np.zeros(101, np.int64); rp[51:] = 7
+    cases.append((rp, np.array([0, 1, 2, 3, 2, 1, 0], np.int32), np.arange(7, dtype=np.float32),
+                  (np.arange(100) % 3 == 0).astype(np.float32), 4))
+    for rowptr, col, val, y, D in cases:
+        n = rowptr.shape[0] - 1
+        rows = capi.DeviceFeRows(rowptr, col, val, y, None, None, D)
+        x = torch.from_numpy(np.linspace(-0.3, 0.4, D + 1)).cuda()
+        for pa in (dict(), dict(hz=1, hg=1, tile_rows=2, l2_tile_rows=3)):
+            plan = capi.DeviceFeTilePlan(rows, **pa)
+            b = capi.fe_loss_grad_device(rows, opts, x, plan=plan).cpu().numpy()
+            blk = O.FeBlock(n, D, rowptr, col, val, y, np.ones(n, np.float32), np.zeros(n, np.float32))
+            f_o, g_o = O.fe_loss_grad(blk, oo, x.cpu().numpy())
+            np.testing.assert_allclose(b[0], f_o, rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(b[1:], g_o, rtol=1e-10, atol=1e-12)
+
+
+def test_tiled_objective_large_zipf_default_split():
+    """The bench's shard shape at test scale with the library's own split (D above hz and hg: both cold paths live),
+    through the solver's frequency ranking."""
+    rng = np.random.default_rng(41)
+    n, D, k = 200_000, 60_000, 32
+    rowptr, col, val, y = _zipf_shard(rng, n, D, k)
+    rows = capi.DeviceFeRows(rowptr, col, val, y, None, None, D)
+    opts = capi.make_opts(l2=1.0, regularize_bias=True, has_intercept=True)
+    solver = FixedEffectSolver(rows, opts)
+    x = rng.standard_normal(D + 1) * 0.05
+    f, g = solver.loss_grad(x)
+    assert solver.plan.n_cold_z > 0 and solver.plan.n_cold_g > 0 and solver.plan.n_tiles > 1
+    blk = O.FeBlock(n, D, rowptr, col, val, y, np.ones(n, np.float32), np.zeros(n, np.float32))
+    f_o, g_o = O.fe_loss_grad(blk, O.make_opts(l2=1.0, regularize_bias=True, has_intercept=True), x)
+    np.testing.assert_allclose(f, f_o, rtol=1e-12)
+    np.testing.assert_allclose(g, g_o, rtol=1e-10, atol=1e-10)
+    f2, g2 = solver.loss_grad(x)
+    assert f2 == f and np.array_equal(g, g2)
