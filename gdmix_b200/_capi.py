@@ -32,7 +32,7 @@ SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_w
            "gdmix_lbfgs_info", "gdmix_lbfgs_destroy", "gdmix_launch_count", "gdmix_re_last_plan",
            "gdmix_partition_workspace_size", "gdmix_sort_pairs_u64", "gdmix_group_by_key", "gdmix_csr_gather_rows",
            "gdmix_gather_f32", "gdmix_partition_ids_i64", "gdmix_auc", "gdmix_re_fit_sweep",
-           "gdmix_re_last_plan_typical", "gdmix_local_index_mark", "gdmix_local_index_apply",
+           "gdmix_re_last_plan_typical", "gdmix_re_last_plan_small", "gdmix_local_index_mark", "gdmix_local_index_apply",
            "gdmix_seqex_count", "gdmix_seqex_fill", "gdmix_example_count", "gdmix_example_fill", "gdmix_avro_score_blocks", "gdmix_avro_model_blocks",
            "gdmix_feature_map_create", "gdmix_feature_map_destroy", "gdmix_avro_model_decode",
            "gdmix_fe_lbfgs_create", "gdmix_fe_lbfgs_reset", "gdmix_fe_lbfgs_step", "gdmix_fe_lbfgs_poll",
@@ -95,6 +95,7 @@ def _load():
     lib.gdmix_host_release.restype = None
     lib.gdmix_re_last_plan.restype = None
     lib.gdmix_re_last_plan_typical.restype = None
+    lib.gdmix_re_last_plan_small.restype = None
     lib.gdmix_lbfgs_create.restype = C.c_void_p
     lib.gdmix_feature_map_create.restype = C.c_void_p
     lib.gdmix_feature_map_destroy.restype = None
@@ -157,6 +158,9 @@ def last_plan():
     lib.gdmix_re_last_plan_typical(a)
     if a[0]:
         d["typical"] = dict(zip(["threads", "ept", "ctas_per_sm", "cap_steps", "smem", "max_rows"], list(a)[1:7]))
+    lib.gdmix_re_last_plan_small(a)
+    if a[0]:
+        d["small"] = dict(zip(["warps_per_cta", "slots", "ctas_per_sm", "cap_rows", "cap_nnz", "smem", "grid"], list(a)[1:8]))
     return d
 
 

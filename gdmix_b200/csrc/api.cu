@@ -23,6 +23,7 @@
 #include "avro_writer.h"
 #include "re_fast.cuh"
 #include "re_kernel.cuh"
+#include "re_small.cuh"
 #include "re_variance.cuh"
 #include "partition.cuh"
 
@@ -31,6 +32,7 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 thread_local int32_t g_last_plan[16] = {0};
+thread_local int32_t g_last_small[8] = {0};
 
 int fail(int code, const char *fmt, ...)
 {
@@ -104,6 +106,11 @@ struct RePlan {
     // ... and the ones with so many samples that one CTA would be the launch's tail: a cluster of kGiantCluster CTAs each
     int ggrid = 0, giant_rows = 0;
     size_t off_giant = 0, off_garena = 0;
+    // small entities: one warp per entity (re_small.cuh), ahead of everything else; what does not fit its slices is
+    // deferred to the launches above through a list
+    int small = 0, sSL = 1, swarps = 8, sctas_per_sm = 1, sgrid = 1;
+    gdmix::SmallShape sS;
+    size_t off_defer_s = 0;
     // FULL variance pass (re_variance.cuh)
     int vgrid = 0;
     uint32_t vsmem = 0, vsmem_matrix_doubles = 0;
@@ -280,6 +287,58 @@ int plan_fast(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo 
     return GDMIX_OK;
 }
 
+template <int SL>
+int small_regs(int &regs)
+{
+    cudaFuncAttributes at;
+    CUDA_TRY(cudaFuncGetAttributes(&at, gdmix::re_small_kernel<SL>));
+    regs = at.numRegs;
+    return GDMIX_OK;
+}
+
+// The warp-per-entity tier (re_small.cuh).  Slices are sized for twice the mean entity (all of it when the batch is
+// uniform); whatever is larger defers to the CTA-per-entity kernels.  MEASURED (B200, per-user shape of configs[3],
+// 32 samples x 64 features x 8 non-zeros, 4 M entities): 11.6 M entities/s against 12.6 M for re_fast_kernel<32,2> --
+// the plain CSR / CSC walk executes 32 K warp instructions per entity and still misses the instruction cache
+// (profiles/r2_ncu_full_re_small_v1.txt), so the planner does NOT pick it; GDMIX_RE_PATH=small selects it (parity
+// tests run through it as a fifth path, and it is the shortest restatement of the solver on the device).
+int plan_small(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &dev, RePlan &pl)
+{
+    pl.small = 0;
+    const char *env_path = getenv("GDMIX_RE_PATH");
+    const bool forced = env_path && strcmp(env_path, "small") == 0;
+    if (!forced) return GDMIX_OK;
+    if (o->m > 10 || b->n_entities <= 0 || b->n_rows <= 0) return GDMIX_OK;
+    const int64_t mean_rows = (b->n_rows + b->n_entities - 1) / b->n_entities;
+    const int64_t mean_nnz = (b->nnz + b->n_entities - 1) / b->n_entities;
+    const uint32_t cap_coef = (uint32_t)std::min(b->max_coef, 96);
+    const uint32_t cap_rows = (uint32_t)std::min<int64_t>(std::min<int64_t>(b->max_rows, 256), std::max<int64_t>(32, 2 * mean_rows));
+    const uint32_t cap_nnz = (uint32_t)std::min<int64_t>(std::min<int64_t>(b->max_nnz, 2048), std::max<int64_t>(128, 2 * mean_nnz));
+    pl.sSL = (int)((cap_coef + 31) / 32);
+    pl.sS = gdmix::small_shape(std::max(cap_rows, 1u), std::max(cap_nnz, 4u), std::max(cap_coef, 1u), (uint32_t)o->m);
+    int regs = 0;
+    int rc = pl.sSL == 1 ? small_regs<1>(regs) : pl.sSL == 2 ? small_regs<2>(regs) : small_regs<3>(regs);
+    if (rc) return rc;
+    const int regs_alloc = (regs + 7) & ~7;
+    const int by_regs = 65536 / (32 * regs_alloc), by_smem = (int)((228u * 1024u - 2048u) / pl.sS.bytes);
+    const int warps_per_sm = std::min({by_regs, by_smem, 48});
+    if (warps_per_sm < 1 || pl.sS.bytes > (uint32_t)dev.smem_optin - 1024u) return GDMIX_OK;
+    int W = 8;
+    while (W > 1 && (warps_per_sm / W < 1 || (size_t)W * pl.sS.bytes + 1024 > (size_t)dev.smem_optin)) W >>= 1;
+    // as many whole CTAs as fit; prefer the CTA size that wastes the fewest warps
+    int best_w = W, best_total = (warps_per_sm / W) * W;
+    for (int w = W; w >= 1; w >>= 1) {
+        const int total = (warps_per_sm / w) * w;
+        if (total > best_total) { best_total = total; best_w = w; }
+    }
+    pl.swarps = best_w;
+    pl.sctas_per_sm = std::max(1, warps_per_sm / best_w);
+    const int64_t want = (int64_t)dev.sm_count * pl.sctas_per_sm;
+    pl.sgrid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (b->n_entities + best_w - 1) / best_w));
+    pl.small = 1;
+    return GDMIX_OK;
+}
+
 int plan_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &dev, RePlan &pl)
 {
     if (b->max_rows <= 0 || b->max_coef <= 0 || b->max_nnz < 0)
@@ -326,8 +385,11 @@ int plan_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, const DeviceInfo &d
     pl.grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, b->n_entities));
     int rc = plan_fast(b, o, dev, pl);
     if (rc) return rc;
+    rc = plan_small(b, o, dev, pl);
+    if (rc) return rc;
     const size_t list_bytes = ((size_t)b->n_entities * 4 + 255) & ~(size_t)255;
-    pl.off_defer0 = kQueueBytes;
+    pl.off_defer_s = kQueueBytes;
+    pl.off_defer0 = pl.off_defer_s + list_bytes;
     pl.off_defer = pl.off_defer0 + (pl.fast ? list_bytes : 0);   // reserved whether or not the typical-shape launch is planned
     pl.off_defer_b = pl.off_defer + (pl.fast ? list_bytes : 0);
     pl.off_arena = pl.off_defer_b + list_bytes;
@@ -481,6 +543,21 @@ int launch_fast(const gdmix::FastArgs &fa, int G, int EPT, int grid, cudaStream_
     }
 }
 
+template <int SL>
+int launch_small_t(const gdmix::SmallArgs &sa, int grid, cudaStream_t st)
+{
+    static std::atomic<int> configured{0};
+    if (!configured.load()) {
+        CUDA_TRY(cudaFuncSetAttribute(gdmix::re_small_kernel<SL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024 - (int)kStaticSmem));
+        configured.store(1);
+    }
+    gdmix::re_small_kernel<SL><<<grid, 32 * sa.warps, (size_t)sa.warps * sa.S.bytes, st>>>(sa);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
 int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const double *theta_in, double *theta_out,
               double *f_out, int32_t *nit, int32_t *nfev, int32_t *status, double *var_out, double *g_out,
               void *workspace, size_t workspace_bytes, cudaStream_t st, const double *l2_values = nullptr,
@@ -529,6 +606,27 @@ int launch_re(const gdmix_re_batch *b, const gdmix_lr_opts *o, int mode, const d
     g_last_plan[8] = pl.fast0; g_last_plan[9] = pl.f0G; g_last_plan[10] = pl.f0EPT; g_last_plan[11] = pl.f0ctas_per_sm;
     g_last_plan[12] = pl.fast0 ? (int32_t)pl.f0L.cap_steps : 0; g_last_plan[13] = pl.fast0 ? (int32_t)pl.f0L.total_bytes : 0;
     g_last_plan[14] = pl.fast0 ? (int32_t)pl.f0L.max_n : 0; g_last_plan[15] = 0;
+    // tier 0: a warp per entity for batches of small entities (fit of one model, no variance output); the entities it
+    // defers are what every later launch works on.  Counters: [10] its work counter, [11] its list's length.
+    const bool use_small = pl.small && mode == gdmix::kModeFit && n_l2 == 0 && !var_out && theta_out;
+    memset(g_last_small, 0, sizeof(g_last_small));
+    if (use_small) {
+        gdmix::SmallArgs sa;
+        sa.a = a;
+        sa.a.queue = (int32_t *)workspace + 10;
+        sa.a.defer_list = (int32_t *)((unsigned char *)workspace + pl.off_defer_s);
+        sa.a.defer_count = (int32_t *)workspace + 11;
+        sa.S = pl.sS;
+        sa.warps = pl.swarps;
+        rc = pl.sSL == 1 ? launch_small_t<1>(sa, pl.sgrid, st) : pl.sSL == 2 ? launch_small_t<2>(sa, pl.sgrid, st)
+                                                                              : launch_small_t<3>(sa, pl.sgrid, st);
+        if (rc) return rc;
+        a.todo = sa.a.defer_list;
+        a.todo_count = sa.a.defer_count;
+        g_last_small[0] = 1; g_last_small[1] = pl.swarps; g_last_small[2] = pl.sSL; g_last_small[3] = pl.sctas_per_sm;
+        g_last_small[4] = (int32_t)pl.sS.cap_rows; g_last_small[5] = (int32_t)pl.sS.cap_nnz;
+        g_last_small[6] = (int32_t)(pl.swarps * pl.sS.bytes); g_last_small[7] = pl.sgrid;
+    }
     if (pl.fast) {
         // fast kernel first; what it defers (entities whose sliced form does not fit) is drained by the
         // general kernel from the list, with its own work counter.  Work counters in the workspace:
@@ -748,6 +846,11 @@ void gdmix_re_last_plan(int32_t *out8)
 void gdmix_re_last_plan_typical(int32_t *out8)
 {
     if (out8) memcpy(out8, g_last_plan + 8, 8 * sizeof(int32_t));
+}
+
+void gdmix_re_last_plan_small(int32_t *out8)
+{
+    if (out8) memcpy(out8, g_last_small, 8 * sizeof(int32_t));
 }
 
 int gdmix_re_workspace_size(const gdmix_re_batch *batch, const gdmix_lr_opts *opts, size_t *bytes)

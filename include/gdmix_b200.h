@@ -433,6 +433,12 @@ GDMIX_API void gdmix_re_last_plan(int32_t *out8);
  * dynamic shared memory per CTA, rows per entity it is planned for, 0 }.  Entities it deferred: eighth int32 of
  * the workspace. */
 GDMIX_API void gdmix_re_last_plan_typical(int32_t *out8);
+/* Batches of small entities (typically a few hundred non-zeros, at most 96 coefficients; fits of one model without
+ * variance output) get a launch of the warp-per-entity kernel ahead of everything else; the launches above then only
+ * drain what it deferred: out8 = { used (0/1), warps per CTA, coefficient slots per lane, CTAs per SM, rows a slice
+ * holds, non-zeros a slice holds, dynamic shared memory per CTA, grid }.  Entities it deferred: twelfth int32 of the
+ * workspace. */
+GDMIX_API void gdmix_re_last_plan_small(int32_t *out8);
 
 /* Number of kernel launches issued by this library since load (for bench accounting). */
 GDMIX_API int64_t gdmix_launch_count(void);

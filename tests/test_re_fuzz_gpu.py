@@ -67,7 +67,7 @@ def test_random_ragged_batches_match_the_oracle_on_every_path(seed, monkeypatch)
     th_p = _oracle(hb, opts, theta0=1e-13 * np.random.default_rng(seed).standard_normal(th_o.shape[0]))[0]
     pinned = norm(th_p, th_o) < 1e-7
     assert pinned.mean() > 0.5
-    for path in ("auto", "generic", "big", "giant"):
+    for path in ("auto", "generic", "big", "giant", "small"):
         monkeypatch.delenv("GDMIX_RE_PATH", raising=False)
         monkeypatch.delenv("GDMIX_GIANT_ROWS", raising=False)
         if path == "giant":

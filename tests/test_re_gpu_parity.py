@@ -18,12 +18,14 @@ from tests.golden_util import is_pinned, load_re  # noqa: E402
 REL_TOL = 1e-5  # north_star tolerance
 
 
-@pytest.fixture(autouse=True, params=["auto", "generic", "big", "giant"])
+@pytest.fixture(autouse=True, params=["auto", "generic", "big", "giant", "small"])
 def re_path(request, monkeypatch):
-    """Every test runs four times: through the planner's choice (the sliced-ELL fast kernel when the batch
-    qualifies), through the general staged kernel alone, through the kernel that leaves X in global memory
-    (the one entities too large for the chip take), and through that kernel launched as thread-block clusters
-    (eight CTAs share an entity's samples -- what entities with tens of thousands of samples take)."""
+    """Every test runs five times: through the planner's choice (the warp-per-entity kernel for batches of small
+    entities, the sliced-ELL fast kernel when the batch qualifies), through the general staged kernel alone, through
+    the kernel that leaves X in global memory (the one entities too large for the chip take), through that kernel
+    launched as thread-block clusters (eight CTAs share an entity's samples -- what entities with tens of thousands of
+    samples take), and with the warp-per-entity kernel forced in front of the cascade (entities above its slices
+    defer to the rest)."""
     monkeypatch.delenv("GDMIX_GIANT_ROWS", raising=False)
     if request.param == "giant":
         monkeypatch.setenv("GDMIX_RE_PATH", "big")
@@ -144,7 +146,8 @@ def test_device_api_matches_host_api(re_path):
     hb = make_batch(300, 64, 64, 16, seed=3)
     opts = capi.make_opts(l2=0.5)
     host = capi.re_fit_host(hb, opts)
-    assert capi.last_plan()["fast"] == (1 if re_path == "auto" else 0)
+    assert capi.last_plan()["fast"] == (1 if re_path in ("auto", "small") else 0)
+    assert ("small" in capi.last_plan()) == (re_path == "small")
     dev = capi.re_fit_device(capi.DeviceBatch(hb), opts)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(dev["theta"].cpu().numpy(), host["theta"])
@@ -160,8 +163,10 @@ def test_run_to_run_bitwise_reproducible():
     np.testing.assert_array_equal(a["f"], b["f"])
 
 
-def test_threshold_and_variance_simple():
+def test_threshold_and_variance_simple(re_path):
     """threshold_coefficients (model_utils.py:4-12) and SIMPLE variance (binary_logistic_regression.py:171-177)."""
+    if re_path == "small":
+        pytest.skip("compares bit for bit runs that the warp-per-entity tier only takes in part (no variance / sweep there)")
     hb = make_batch(64, 40, 24, 6, seed=5, weights=True)
     raw = capi.re_fit_host(hb, capi.make_opts(l2=1.0))
     thr = capi.re_fit_host(hb, capi.make_opts(l2=1.0, sparsity_threshold=1e-4, variance_mode=capi.VARIANCE_SIMPLE),
@@ -248,9 +253,11 @@ def test_deferred_entities_take_the_general_kernel(monkeypatch, re_path):
 
 
 @pytest.mark.parametrize("shape", [(40, 24, 6), (128, 256, 32)])
-def test_variance_full_matches_oracle(shape):
+def test_variance_full_matches_oracle(shape, re_path):
     """FULL variance = diag((X1^T D X1 + (l2 + 1e-12) I - l2 e0 e0^T)^-1) at the un-thresholded optimum
     (binary_logistic_regression.py:178-186); the matrix lives on chip for the small shape, in the workspace for C1."""
+    if re_path == "small":
+        pytest.skip("compares bit for bit runs that the warp-per-entity tier only takes in part (no variance / sweep there)")
     n, d, k = shape
     E = 48
     hb = make_batch(E, n, d, k, seed=15, weights=True)
@@ -341,10 +348,12 @@ def test_oversized_entities_are_solved_not_rejected(re_path):
 
 
 @pytest.mark.parametrize("shape", [(300, 64, 64, 16), (120, 128, 256, 32)])
-def test_l2_sweep_equals_separate_fits(shape):
+def test_l2_sweep_equals_separate_fits(shape, re_path):
     """BASELINE.json configs[4]: a sweep over l2_reg_weight solved from ONE staged copy of every entity block.
     Model j must be bit-for-bit what gdmix_re_fit returns with l2 = l2_values[j] (in the reference a sweep is
     n separate training jobs), and match the oracle run with that weight."""
+    if re_path == "small":
+        pytest.skip("compares bit for bit runs that the warp-per-entity tier only takes in part (no variance / sweep there)")
     E, n, d, k = shape
     hb = make_batch(E, n, d, k, seed=77, weights=True)
     db = capi.DeviceBatch(hb)
@@ -366,6 +375,8 @@ def test_l2_sweep_equals_separate_fits(shape):
 
 def test_l2_sweep_with_deferred_entities(monkeypatch, re_path):
     """Entities the fast kernel defers are swept by the general kernel, one launch per weight, same results."""
+    if re_path == "small":
+        pytest.skip("compares bit for bit runs that the warp-per-entity tier only takes in part (no variance / sweep there)")
     if re_path == "auto":
         monkeypatch.setenv("GDMIX_FAST_CAP_STEPS", "30")
     hb = make_batch(200, 64, 64, 16, seed=78, ragged=True)
@@ -500,3 +511,25 @@ def test_c1_shape_at_scale_properties():
     rel = _rel_per_entity(th_d, th_o, hb.theta_ptr)
     assert rel.max() <= REL_TOL, rel.max()
     assert (nit.cpu().numpy()[pick] == nit_o).all() and (nfev.cpu().numpy()[pick] == nfev_o).all()
+
+
+def test_warp_per_entity_tier_solves_what_fits_and_defers_the_rest(monkeypatch, re_path):
+    """GDMIX_RE_PATH=small: the warp-per-entity kernel (re_small.cuh) takes the entities that fit its slices -- sized
+    for twice the mean entity -- and appends the others to the list the rest of the cascade drains; answers equal the
+    oracle's either way (identical iteration counts), warm starts and weights included."""
+    if re_path != "small":
+        pytest.skip("one configuration is enough")
+    hb = make_batch(600, 24, 40, 6, seed=77, ragged=True, weights=True)     # 8 .. 1024 samples: the long ones defer
+    opts = capi.make_opts(l2=0.3, regularize_bias=True)
+    rng = np.random.default_rng(5)
+    theta0 = 0.1 * rng.standard_normal(hb.n_coef)
+    db = capi.DeviceBatch(hb)
+    out = capi.re_fit_device(db, opts, theta0=torch.from_numpy(theta0).cuda())
+    torch.cuda.synchronize()
+    plan = capi.last_plan()
+    deferred = int(out["workspace"][:64].view(torch.int32)[11].item())
+    assert "small" in plan and 0 < deferred < hb.n_entities
+    th_o, f_o, nit_o, nfev_o, st_o = O.re_fit_batch(_oracle_batch(hb), _oracle_opts(opts), theta0=theta0)
+    rel = _rel_per_entity(out["theta"].cpu().numpy(), th_o, hb.theta_ptr)
+    assert rel.max() <= 1e-9, rel.max()
+    assert (out["nit"].cpu().numpy() == nit_o).all() and (out["status"].cpu().numpy() == st_o).all()
