@@ -36,7 +36,7 @@ SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_w
            "gdmix_seqex_count", "gdmix_seqex_fill", "gdmix_example_count", "gdmix_example_fill", "gdmix_avro_score_blocks", "gdmix_avro_model_blocks",
            "gdmix_feature_map_create", "gdmix_feature_map_destroy", "gdmix_avro_model_decode",
            "gdmix_fe_lbfgs_create", "gdmix_fe_lbfgs_reset", "gdmix_fe_lbfgs_step", "gdmix_fe_lbfgs_poll",
-           "gdmix_fe_lbfgs_destroy", "gdmix_fe_column_counts", "gdmix_remap_i32", "gdmix_fe_tile_plan_create",
+           "gdmix_fe_lbfgs_destroy", "gdmix_fe_column_counts", "gdmix_remap_i32", "gdmix_group_ids", "gdmix_offset_join", "gdmix_seqex_encode", "gdmix_fe_tile_plan_create",
            "gdmix_fe_tile_plan_destroy", "gdmix_fe_tile_plan_info", "gdmix_fe_loss_grad_tiled"]
 
 
@@ -595,6 +595,43 @@ def parse_entity_grouped(file_image, entity, uid, label, offset, weight, bag_ind
     out["entity_ids"] = [raw[ip[e]:ip[e + 1]].decode("utf-8") for e in range(E)]
     out["all_labelled"], out["saw_weight"] = bool(sz.all_labelled), bool(sz.saw_weight)
     return out
+
+
+def encode_entity_grouped(ent_rows, row_len, gcol, val, uid, entity_int=None, entity_str=None, label=None,
+                          label_as_int=True, offset=None, weight=None, entity="entity", uid_name="uid",
+                          label_name="response", offset_name="offset", weight_name="weight", bag=None):
+    """Flat arrays -> the bytes of one uncompressed TFRecord file of entity-grouped SequenceExamples
+    (gdmix_seqex_encode; host code of the library).  Record e = ent_rows[e] consecutive samples; the entity id is
+    entity_int[e] (int64) or entity_str[e].  bag: name of the feature bag (columns <bag>_indices / <bag>_values), None:
+    no features are written."""
+    enc = lambda x: None if x is None else x.encode("utf-8")
+    E = int(len(ent_rows))
+    ent_rows = np.ascontiguousarray(ent_rows, dtype=np.int64)
+    N = int(ent_rows.sum())
+    row_len = None if bag is None else np.ascontiguousarray(row_len, dtype=np.int64)
+    gcol = None if bag is None else np.ascontiguousarray(gcol, dtype=np.int64)
+    val = None if bag is None else np.ascontiguousarray(val, dtype=np.float32)
+    uid = np.ascontiguousarray(uid, dtype=np.int64)
+    assert uid.shape[0] == N and (bag is None or row_len.shape[0] == N)
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+    label, offset, weight = f32(label), f32(offset), f32(weight)
+    ei = idc = idp = None
+    if entity_int is not None:
+        ei = np.ascontiguousarray(entity_int, dtype=np.int64)
+    else:
+        idc, idp = _string_table([str(x) for x in entity_str])
+    spec = SeqexSpec(enc(entity), enc(uid_name), enc(label_name) if label is not None else None,
+                     enc(offset_name) if offset is not None else None, enc(weight_name) if weight is not None else None,
+                     enc(bag + "_indices") if bag else None, enc(bag + "_values") if bag else None)
+    need = C.c_int64()
+    args = [C.byref(spec), C.c_int64(E), _np_ptr(ent_rows), _np_ptr(ei), _np_ptr(idc), _np_ptr(idp), _np_ptr(row_len),
+            _np_ptr(gcol), _np_ptr(val), _np_ptr(uid), _np_ptr(label), C.c_int32(1 if label_as_int else 0), _np_ptr(offset),
+            _np_ptr(weight)]
+    check(lib.gdmix_seqex_encode(*args, None, C.c_int64(0), C.byref(need)))
+    out = np.empty(max(need.value, 1), np.uint8)
+    written = C.c_int64()
+    check(lib.gdmix_seqex_encode(*args, _np_ptr(out), C.c_int64(out.size), C.byref(written)))
+    return out[:written.value]
 
 
 def parse_per_record(file_image, uid, label, offset, weight, bag_indices, bag_values):

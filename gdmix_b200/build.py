@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("GDMIX_LIB_OUT") or os.path.join(HERE, "lib", "libgdmix_b200.so")  # GDMIX_LIB_OUT / GDMIX_NVCC_FLAGS: kernel experiments
 SOURCES = ["api.cu"]
-HEADERS = ["re_kernel.cuh", "re_fast.cuh", "re_small.cuh", "re_variance.cuh", "partition.cuh", "host_lbfgs.h", "fe_lbfgs.cuh", "fe_plan.cuh", "fe_tile.cuh", "seqex_parser.h", "avro_writer.h", "re_common.cuh", "re_passes.cuh", "re_lbfgs.cuh", "linesearch.cuh", "aux_kernels.cuh", os.path.join("..", "..", "include", "gdmix_b200.h")]
+HEADERS = ["re_kernel.cuh", "re_fast.cuh", "re_small.cuh", "re_variance.cuh", "partition.cuh", "host_lbfgs.h", "fe_lbfgs.cuh", "fe_plan.cuh", "fe_tile.cuh", "seqex_parser.h", "seqex_writer.h", "avro_writer.h", "re_common.cuh", "re_passes.cuh", "re_lbfgs.cuh", "linesearch.cuh", "aux_kernels.cuh", os.path.join("..", "..", "include", "gdmix_b200.h")]
 
 
 def _nvcc():

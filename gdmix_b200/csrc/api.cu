@@ -20,6 +20,7 @@
 #include "fe_plan.cuh"
 #include "fe_tile.cuh"
 #include "seqex_parser.h"
+#include "seqex_writer.h"
 #include "avro_writer.h"
 #include "re_fast.cuh"
 #include "re_kernel.cuh"
@@ -1641,6 +1642,65 @@ int gdmix_gather_f32(const float *in, const uint32_t *perm, int64_t n, float *ou
     gdmix::gather_f32_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(in, perm, n, out);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
+int gdmix_group_ids(const int64_t *seg_ptr, int64_t n_groups, const uint32_t *perm, const int64_t *uid, int64_t n,
+                    int32_t lower_bound, int32_t upper_bound, int32_t *group_id, void *stream)
+{
+    if (n < 0 || n_groups < 0 || (n > 0 && (!seg_ptr || !perm || !uid || !group_id || n_groups < 1)))
+        return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_group_ids");
+    if (n == 0) return GDMIX_OK;
+    DeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc) return rc;
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)dev.sm_count * 16);
+    gdmix::group_ids_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seg_ptr, n_groups, perm, uid, n, lower_bound, upper_bound,
+                                                                    group_id);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
+int gdmix_offset_join(const int64_t *uid, int64_t n, const uint64_t *score_uid_sorted, const uint32_t *score_perm, int64_t m,
+                      const float *score, const float *per_coordinate, float *offset_out, uint8_t *matched, void *stream)
+{
+    if (n < 0 || m < 0 || (n > 0 && (!uid || !offset_out || !matched)) || (m > 0 && (!score_uid_sorted || !score_perm || !score)))
+        return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_offset_join");
+    if (n == 0) return GDMIX_OK;
+    DeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc) return rc;
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)dev.sm_count * 16);
+    gdmix::offset_join_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(uid, n, score_uid_sorted, score_perm, m, score,
+                                                                      per_coordinate, offset_out, matched);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
+int gdmix_seqex_encode(const gdmix_seqex_spec *spec, int64_t n_entities, const int64_t *ent_rows, const int64_t *entity_int,
+                       const char *id_chars, const int64_t *id_ptr, const int64_t *row_len, const int64_t *gcol,
+                       const float *val, const int64_t *uid, const float *label, int32_t label_as_int, const float *offset,
+                       const float *weight, uint8_t *out, int64_t capacity, int64_t *written)
+{
+    if (!spec || n_entities < 0 || !written || (n_entities > 0 && !ent_rows))
+        return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_seqex_encode");
+    if (spec->entity && !entity_int && !(id_chars && id_ptr)) return fail(GDMIX_ERR_INVALID, "entity column without ids");
+    if (spec->uid && !uid && n_entities > 0) return fail(GDMIX_ERR_INVALID, "uid column without values");
+    if (spec->bag_indices && n_entities > 0 && (!row_len || (!gcol && !val))) return fail(GDMIX_ERR_INVALID, "feature bag without arrays");
+    gdmix_host::SeqexColumns c;
+    c.entity = spec->entity; c.uid = spec->uid; c.label = spec->label; c.offset = spec->offset; c.weight = spec->weight;
+    c.bag_indices = spec->bag_indices; c.bag_values = spec->bag_values;
+    c.n_entities = n_entities; c.ent_rows = ent_rows; c.entity_int = entity_int; c.id_chars = id_chars; c.id_ptr = id_ptr;
+    c.row_len = row_len; c.gcol = gcol; c.val = val; c.uid_v = uid; c.label_v = label; c.label_as_int = label_as_int;
+    c.offset_v = offset; c.weight_v = weight;
+    try {
+        if (gdmix_host::seqex_encode(c, out, capacity, written) != 0)
+            return fail(GDMIX_ERR_WORKSPACE, "gdmix_seqex_encode: capacity %lld < %lld bytes", (long long)capacity, (long long)*written);
+    } catch (...) {
+        return fail(GDMIX_ERR_INVALID, "out of host memory in gdmix_seqex_encode");
+    }
     return GDMIX_OK;
 }
 

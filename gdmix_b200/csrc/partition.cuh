@@ -472,4 +472,63 @@ __global__ void __launch_bounds__(256) auc_finish_kernel(const double *cta_u2, c
     }
 }
 
+// ---- DataPartitioner's bounds and OffsetUpdater's join ------------------------------------------------------
+// Group id of every row (DataPartitioner.getGroupId, gdmix-data/.../data/DataPartitioner.scala:335-379): rows are
+// given grouped by entity (perm / seg_ptr of gdmix_group_by_key).  count = rows of the entity;
+// groups = upper > 0 ? count / upper + 1 : 1;  id = pmod(uid, groups);  lower > 0 and count < lower: id = -1.
+// 0 = active data, anything else passive.  group_id is written in INPUT row order.
+__global__ void __launch_bounds__(256) group_ids_kernel(const int64_t *seg_ptr, const int64_t n_groups, const uint32_t *perm,
+                                                        const int64_t *uid, const int64_t n, const int32_t lower,
+                                                        const int32_t upper, int32_t *group_id)
+{
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += nth) {
+        int64_t lo = 0, hi = n_groups;   // seg_ptr[lo] <= k < seg_ptr[hi]
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (seg_ptr[mid] <= k) lo = mid; else hi = mid;
+        }
+        const int64_t count = seg_ptr[lo + 1] - seg_ptr[lo];
+        const uint32_t row = perm[k];
+        int32_t id;
+        if (lower > 0 && count < (int64_t)lower) {
+            id = -1;
+        } else {
+            const int64_t groups = upper > 0 ? count / (int64_t)upper + 1 : 1;
+            int64_t r = uid[row] % groups;      // pmod: the sign of the divisor
+            if (r < 0) r += groups;
+            id = (int32_t)r;
+        }
+        group_id[row] = id;
+    }
+}
+
+// Offset of every data row from the previous coordinate's scores, joined by uid (OffsetUpdater.updateOffset,
+// gdmix-data/.../data/OffsetUpdater.scala:105-129): offset = float(predictionScore) [- predictionScorePerCoordinate];
+// matched[i] = 0 marks rows the inner join drops.  The scores' uids come sorted (gdmix_sort_pairs_u64 over the
+// uids reinterpreted as u64) with the permutation that sorted them; of equal uids the first in file order wins.
+__global__ void __launch_bounds__(256) offset_join_kernel(const int64_t *uid, const int64_t n, const uint64_t *skey,
+                                                          const uint32_t *sperm, const int64_t m, const float *score,
+                                                          const float *per_coordinate, float *offset_out, uint8_t *matched)
+{
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth) {
+        const uint64_t want = (uint64_t)uid[i];
+        int64_t lo = 0, hi = m;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (skey[mid] < want) lo = mid + 1; else hi = mid;
+        }
+        const bool hit = lo < m && skey[lo] == want;
+        float o = 0.0f;
+        if (hit) {
+            const uint32_t j = sperm[lo];
+            o = score[j];
+            if (per_coordinate) o = o - per_coordinate[j];
+        }
+        offset_out[i] = o;
+        matched[i] = hit ? 1 : 0;
+    }
+}
+
 }  // namespace gdmix

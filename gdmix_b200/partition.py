@@ -1,7 +1,11 @@
 """Device-side partitioner / evaluator: what gdmix-data's Spark jobs do before and after the hot path, without
 leaving HBM (kernels in csrc/partition.cuh, C ABI in include/gdmix_b200.h).
 
-  group_by_entity   DataPartitioner.boundAndGroupData's groupBy(entity) (DataPartitioner.scala:296-379, bounds aside)
+  group_by_entity   DataPartitioner.boundAndGroupData's groupBy(entity) (DataPartitioner.scala:296-379)
+  group_ids         DataPartitioner.getGroupId: active / passive bounds per entity (DataPartitioner.scala:335-379)
+  join_offsets      OffsetUpdater.updateOffset: the previous coordinate's scores joined by uid (OffsetUpdater.scala:105-129)
+  partition_and_write   groupPartitionAndSaveDataset: the active|passive/partitionId=k TFRecord layout and
+                    partitionList.txt that RandomEffectDriver consumes (DataPartitioner.scala:95-120, 203-280)
   regroup_batch     rows in arrival order (+ global feature ids) -> the entity-local CSR batch gdmix_re_fit takes
                     (prepare_jobs' np.unique per entity, job_consumers.py:243, for the whole dataset at once)
   partition_ids     PartitionUtils.getPartitionIdUDF for integer entity ids (PartitionUtils.scala:31-37)
@@ -208,3 +212,124 @@ class GroupedBatch:
         out = torch.empty_like(per_row)
         out[self.d["perm"].long()] = per_row
         return out
+
+
+# ---- DataPartitioner's bounds, OffsetUpdater's join, and the partitioned files ------------------------------------------
+
+def group_ids(entity, uid, lower_bound=None, upper_bound=None, stream=None):
+    """Group id of every row (DataPartitioner.getGroupId): 0 = active; -1 = the entity has fewer than lower_bound rows;
+    otherwise pmod(uid, rows // upper_bound + 1).  No bounds: all zeros.  int64 CUDA tensors in, int32 tensor out."""
+    import torch
+    n = entity.numel()
+    out = torch.zeros(n, dtype=torch.int32, device=entity.device)
+    if (lower_bound is None and upper_bound is None) or n == 0:
+        return out
+    perm, seg_ptr, _ = group_by_entity(entity, stream=stream)
+    check(lib.gdmix_group_ids(_tptr(seg_ptr.contiguous()), C.c_int64(seg_ptr.numel() - 1), _tptr(perm), _tptr(uid.contiguous()),
+                              C.c_int64(n), C.c_int32(int(lower_bound or 0)), C.c_int32(int(upper_bound or 0)), _tptr(out),
+                              _stream_ptr(stream)))
+    return out
+
+
+def join_offsets(uid, score_uid, score, per_coordinate=None, stream=None):
+    """OffsetUpdater.updateOffset on the device: -> (offset fp32[n], matched bool[n]); a data row without a score row of
+    the same uid is one the reference's inner join drops."""
+    import torch
+    n, m = uid.numel(), score_uid.numel()
+    skey, sperm = sort_pairs(score_uid.contiguous(), key_bits=64, stream=stream)
+    off = torch.empty(n, dtype=torch.float32, device=uid.device)
+    matched = torch.empty(n, dtype=torch.uint8, device=uid.device)
+    check(lib.gdmix_offset_join(_tptr(uid.contiguous()), C.c_int64(n), _tptr(skey), _tptr(sperm), C.c_int64(m),
+                                _tptr(score.contiguous()), _tptr(None if per_coordinate is None else per_coordinate.contiguous()),
+                                _tptr(off), _tptr(matched), _stream_ptr(stream)))
+    return off, matched.bool()
+
+
+def partition_and_write(out_dir, entity, uid, rowptr, gcol, val, label, num_partitions, offset=None, weight=None,
+                        scores=None, lower_bound=None, upper_bound=None, split=True, save_passive=True,
+                        entity_name="entity", uid_name="uid", label_name="response", offset_name="offset",
+                        weight_name="weight", bag="features", label_as_int=True, partition_list_file=None):
+    """DataPartitioner.groupPartitionAndSaveDataset on the device + the files on disk.
+
+    Rows in arrival order (int64 entity ids and uids, CSR feature bag with GLOBAL ids, fp32 label / offset / weight;
+    CUDA tensors) -> `<out_dir>/active/partitionId=k/part-00000.tfrecord` (+ `passive/...` when bounds are given and
+    save_passive; split=False -- validation data -- writes `<out_dir>/partitionId=k/...` without the split), one
+    SequenceExample per (entity, group), and `partition_list_file` with the sorted partition ids that hold a record.
+    scores = (uid, predictionScore[, predictionScorePerCoordinate]) CUDA tensors of the previous coordinate: rows are
+    inner-joined on uid and the joined score becomes the offset column.  The whole regrouping -- join, bounds,
+    (class, partition, entity, group) sort, CSR gather -- runs on the device; the host only encodes and writes the files.
+    Returns a dict with the record counts per file."""
+    import os
+    import torch
+    dev = entity.device
+    n = entity.numel()
+    keep = None
+    if scores is not None:
+        s_uid, s_score = scores[0], scores[1]
+        s_pc = scores[2] if len(scores) > 2 else None
+        offset, matched = join_offsets(uid, s_uid, s_score, s_pc)
+        if not bool(matched.all().item()):
+            # inner join: unmatched rows leave; a stable one-bit sort keeps the others in arrival order
+            _, order = sort_pairs((~matched).to(torch.int64), key_bits=1)
+            keep = order[:int(matched.sum().item())]
+    if keep is not None:
+        rowptr, gcol, val = gather_rows(rowptr, gcol, val, keep)
+        entity, uid = entity[keep.long()], uid[keep.long()]
+        label = gather_f32(label, keep)
+        offset = gather_f32(offset, keep)
+        weight = gather_f32(weight, keep) if weight is not None else None
+        n = entity.numel()
+    if n == 0:
+        raise ValueError("no rows to partition")
+    gid = group_ids(entity, uid, lower_bound, upper_bound)
+    part = partition_ids(entity, num_partitions)
+    if int(part.min().item()) < 0:
+        raise ValueError("negative partition id (an entity whose String.hashCode is Int.MinValue): Spark would write partitionId=-k")
+    _, seg_ptr, ent_ids = group_by_entity(entity)
+    # entity rank of every row: position of its id among the sorted distinct ids
+    rank = torch.searchsorted(ent_ids, entity)
+    gmax = int(gid.max().item()) + 2
+    gb, eb, pb = max(1, (gmax - 1).bit_length()), max(1, int(ent_ids.numel() - 1).bit_length()), max(1, int(num_partitions - 1).bit_length())
+    if gb + eb + pb + 1 > 63:
+        raise ValueError("too many entities x groups x partitions for one 64-bit sort key")
+    passive = (gid != 0).to(torch.int64) if split else torch.zeros(n, dtype=torch.int64, device=dev)
+    key = (passive << (pb + eb + gb)) | (part.to(torch.int64) << (eb + gb)) | (rank << gb) | (gid.to(torch.int64) + 1)
+    perm, rec_ptr, rec_key = group_by_entity(key, key_bits=gb + eb + pb + 1)
+    rp, gc, va = gather_rows(rowptr, gcol, val, perm)
+    cols = {"uid": uid[perm.long()].cpu().numpy(), "label": gather_f32(label, perm).cpu().numpy(),
+            "offset": None if offset is None else gather_f32(offset, perm).cpu().numpy(),
+            "weight": None if weight is None else gather_f32(weight, perm).cpu().numpy()}
+    rp_h, gc_h, va_h = rp.cpu().numpy(), gc.cpu().numpy().astype(np.int64), va.cpu().numpy()
+    rec_ptr_h, rec_key_h = rec_ptr.cpu().numpy(), rec_key.cpu().numpy()
+    ent_h = ent_ids.cpu().numpy()
+    rec_passive = rec_key_h >> (pb + eb + gb)
+    rec_part = (rec_key_h >> (eb + gb)) & ((1 << pb) - 1)
+    rec_ent = ent_h[(rec_key_h >> gb) & ((1 << eb) - 1)]
+    row_len = np.diff(rp_h)
+    written = {}
+    file_key = rec_passive * (1 << pb) + rec_part
+    starts = np.flatnonzero(np.diff(file_key, prepend=-1))
+    ends = np.append(starts[1:], file_key.shape[0])
+    for a, b in zip(starts, ends):
+        pas, k = int(rec_passive[a]), int(rec_part[a])
+        if pas and not (save_passive and (lower_bound is not None or upper_bound is not None)):
+            continue
+        r0, r1 = int(rec_ptr_h[a]), int(rec_ptr_h[b])
+        q0, q1 = int(rp_h[r0]), int(rp_h[r1])
+        sub = os.path.join(out_dir, ("passive" if pas else "active") if split else "", f"partitionId={k}")
+        os.makedirs(sub, exist_ok=True)
+        image = capi.encode_entity_grouped(
+            np.diff(rec_ptr_h[a:b + 1]), row_len[r0:r1], gc_h[q0:q1], va_h[q0:q1], cols["uid"][r0:r1],
+            entity_int=rec_ent[a:b], label=cols["label"][r0:r1], label_as_int=label_as_int,
+            offset=None if cols["offset"] is None else cols["offset"][r0:r1],
+            weight=None if cols["weight"] is None else cols["weight"][r0:r1], entity=entity_name, uid_name=uid_name,
+            label_name=label_name, offset_name=offset_name, weight_name=weight_name, bag=bag)
+        with open(os.path.join(sub, "part-00000.tfrecord"), "wb") as f:
+            f.write(image.tobytes())
+        written[(("passive" if pas else "active") if split else "all", k)] = int(b - a)
+    if partition_list_file:
+        ids = sorted({int(k) for k in np.unique(rec_part)})
+        os.makedirs(os.path.dirname(partition_list_file) or ".", exist_ok=True)
+        with open(partition_list_file, "w") as f:
+            f.write(",".join(str(k) for k in ids))
+    return written

@@ -275,7 +275,19 @@ GDMIX_API int gdmix_partition_ids(const uint16_t *units, const int64_t *id_ptr, 
  *                         (PartitionUtils.scala:31-37), bit-exact with gdmix_partition_ids on the decimal string.
  * gdmix_auc               area under the ROC curve with ties counted half (Evaluator.scala:29-45 ->
  *                         BinaryClassificationMetrics.areaUnderROC); label > 0 is positive.
- *                         out3 = { auc, positives, negatives }.  Synchronises the stream once. */
+ *                         out3 = { auc, positives, negatives }.  Synchronises the stream once.
+ * gdmix_group_ids         DataPartitioner.getGroupId (DataPartitioner.scala:335-379): rows grouped by entity (perm /
+ *                         seg_ptr of gdmix_group_by_key) -> group id per INPUT row: 0 active; -1 the entity has fewer than
+ *                         lower_bound rows; otherwise pmod(uid, rows / upper_bound + 1) (bounds <= 0: absent).
+ * gdmix_offset_join       OffsetUpdater.updateOffset (OffsetUpdater.scala:105-129): offset = float(predictionScore)
+ *                         [- predictionScorePerCoordinate] of the score row with the same uid; matched[i] = 0: no such
+ *                         row (the inner join drops the data row).  score_uid_sorted / score_perm: the scores' uids
+ *                         (as u64) through gdmix_sort_pairs_u64. */
+GDMIX_API int gdmix_group_ids(const int64_t *seg_ptr, int64_t n_groups, const uint32_t *perm, const int64_t *uid, int64_t n,
+                              int32_t lower_bound, int32_t upper_bound, int32_t *group_id, void *stream);
+GDMIX_API int gdmix_offset_join(const int64_t *uid, int64_t n, const uint64_t *score_uid_sorted, const uint32_t *score_perm,
+                                int64_t m, const float *score, const float *per_coordinate, float *offset_out,
+                                uint8_t *matched, void *stream);
 GDMIX_API int gdmix_partition_workspace_size(int64_t n, size_t *bytes);
 GDMIX_API int gdmix_sort_pairs_u64(const uint64_t *keys_in, int64_t n, int32_t key_bits, uint64_t *keys_out,
                                    uint32_t *perm_out, void *ws, size_t ws_bytes, void *stream);
@@ -330,6 +342,17 @@ GDMIX_API int gdmix_seqex_count(const uint8_t *file_image, int64_t len, const gd
 GDMIX_API int gdmix_seqex_fill(const uint8_t *file_image, int64_t len, const gdmix_seqex_spec *spec, int64_t *ent_rows,
                                int64_t *row_len, int64_t *gcol, float *val, int64_t *uid, float *label, float *offset,
                                float *weight, char *id_chars, int64_t *id_ptr);
+
+/* The writer of the same files (what DataPartitioner's Spark job saves, DataPartitioner.scala:203-280 ->
+ * IoUtils.saveDataFrame with recordType SequenceExample): n_entities records, record e = ent_rows[e] consecutive samples;
+ * the entity id is entity_int[e] (int64 list) or the utf-8 string id_chars[id_ptr[e] .. id_ptr[e+1]) (bytes list); spec
+ * names the columns to write (NULL: not written); label_as_int writes the label as an int64 list.  out == NULL:
+ * *written = bytes needed.  TFRecord framing with masked crc32c; all host threads.  Pure host code. */
+GDMIX_API int gdmix_seqex_encode(const gdmix_seqex_spec *spec, int64_t n_entities, const int64_t *ent_rows,
+                                 const int64_t *entity_int, const char *id_chars, const int64_t *id_ptr,
+                                 const int64_t *row_len, const int64_t *gcol, const float *val, const int64_t *uid,
+                                 const float *label, int32_t label_as_int, const float *offset, const float *weight,
+                                 uint8_t *out, int64_t capacity, int64_t *written);
 
 /* The same for the fixed effect's input, one tf.train.Example per row (per_record_input_fn,
  * input_data_pipeline.py:223-243): spec->bag_indices / bag_values name two lists of the features map (NULL:

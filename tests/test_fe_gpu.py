@@ -285,3 +285,46 @@ def test_tiled_objective_large_zipf_default_split():
     np.testing.assert_allclose(g, g_o, rtol=1e-10, atol=1e-10)
     f2, g2 = solver.loss_grad(x)
     assert f2 == f and np.array_equal(g, g2)
+
+
+@pytest.mark.parametrize("hi,rb", [(True, True), (True, False), (False, False)])
+def test_fe_hessian_simple_and_full_match_a_dense_restatement(hi, rb):
+    """gdmix_fe_hessian against the reference's accumulator H = X1^T diag(w rho (1 - rho)) X1 with the intercept column
+    LAST (fixed_effect_lr_lbfgs_model.py:271-296), densified in numpy: SIMPLE = its diagonal, FULL = the matrix; then
+    the variances the model derives from it (:451-463: + l2 on the diagonal except an unregularised intercept, + 1e-12,
+    inverse) against numpy's inverse.  Weights, offsets; feature ids are unique inside a row (tf.sparse.to_dense
+    refuses repeated indices, so the reference has no semantics for them)."""
+    rng = np.random.default_rng(9)
+    n, D, k = 4000, 37, 6
+    rowptr = np.arange(n + 1, dtype=np.int64) * k
+    col = np.stack([rng.permutation(D)[:k] for _ in range(n)]).reshape(-1).astype(np.int32)
+    val = rng.standard_normal(n * k).astype(np.float32)
+    y = (rng.random(n) < 0.5).astype(np.float32)
+    w = rng.uniform(0.5, 2.0, n).astype(np.float32)
+    off = (0.3 * rng.standard_normal(n)).astype(np.float32)
+    P = D + (1 if hi else 0)
+    x = rng.standard_normal(P) * 0.2
+    rows = capi.DeviceFeRows(rowptr, col, val, y, w, off, D)
+    opts = capi.make_opts(l2=0.8, regularize_bias=rb, has_intercept=hi)
+    xd = torch.from_numpy(x).cuda()
+    X1 = np.zeros((n, P))
+    np.add.at(X1, (np.repeat(np.arange(n), k), col), val.astype(np.float64))     # to_dense sums duplicates
+    if hi:
+        X1[:, D] = 1.0
+    rho = 1.0 / (1.0 + np.exp(-(X1 @ x + off)))
+    H = X1.T @ (X1 * (rho * (1 - rho) * w)[:, None])
+    h_simple = capi.fe_hessian_device(rows, opts, xd, capi.VARIANCE_SIMPLE).cpu().numpy()
+    h_full = capi.fe_hessian_device(rows, opts, xd, capi.VARIANCE_FULL).cpu().numpy()
+    np.testing.assert_allclose(h_simple, np.diag(H), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(h_full, H, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(h_full, h_full.T, rtol=0, atol=1e-12)
+    # the variances of the model file
+    l2, eps = 0.8, 1e-12
+    Hs = h_simple + l2
+    Hf = h_full + np.diag([l2 + eps] * P)
+    if hi and not rb:
+        Hs[-1] -= l2
+        Hf[-1, -1] -= l2
+    want_full = np.diagonal(np.linalg.inv(H + np.diag([l2 + eps] * P) - (np.diag([0.0] * (P - 1) + [l2]) if hi and not rb else 0)))
+    np.testing.assert_allclose(np.diagonal(np.linalg.inv(Hf)), want_full, rtol=1e-9)
+    np.testing.assert_allclose(1.0 / (Hs + eps), 1.0 / (np.diag(H) + l2 * (1 - np.eye(P)[-1] * (1 if hi and not rb else 0)) + eps), rtol=1e-10)

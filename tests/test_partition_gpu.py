@@ -167,3 +167,150 @@ def test_bitmap_local_indexing_rejects_ids_outside_the_bag():
         P.regroup_batch(t(np.array([5, 5, 7], np.int64)), t(np.array([0, 1, 2, 3], np.int64)),
                         t(np.array([1, 64, 2], np.int32)), t(np.ones(3, np.float32)), t(np.ones(3, np.float32)), None, None,
                         num_features=64)
+
+
+# ---- DataPartitioner's bounds / OffsetUpdater's join / the partitioned files ------------------------------------------
+# the fixture of gdmix-data/src/test/scala/com/linkedin/gdmix/data/DataPartitionerTest.scala:25-45
+REF_UID = np.arange(10, dtype=np.int64)
+REF_ENTITY = np.array([0, 0, 0, 1, 1, 1, 1, 1, 1, 2], np.int64)
+REF_LABEL = np.array([0, 0, 1, 1, 1, 0, 0, 1, 1, 1], np.float32)
+REF_INDICES = [[0, 1], [0, 1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [3, 4], [5, 9], [0], [0, 2]]
+REF_VALUES = [[0, 1], [0, 1.0, 2.2], [3, 4.1], [5.5, 6.6], [7.7, 8.8], [9.3, 10.12], [0.3, 0.8], [0.8, 1.8], [0.0],
+              [1.0, -2.2]]
+
+
+def _np_group_ids(entity, uid, lower, upper):
+    """numpy restatement of DataPartitioner.getGroupId (DataPartitioner.scala:335-379)."""
+    ids, inv, cnt = np.unique(entity, return_inverse=True, return_counts=True)
+    count = cnt[inv]
+    groups = count // upper + 1 if upper else np.ones_like(count)
+    gid = np.mod(uid, groups)                       # pmod: numpy's mod already has the divisor's sign
+    if lower:
+        gid = np.where(count < lower, -1, gid)
+    return gid.astype(np.int32)
+
+
+def test_group_ids_reference_fixture_and_random():
+    """DataPartitionerTest.testGetGroupId: lowerBound 2, upperBound 4 -- entity 0 (3 rows) all active, entity 1 (6 rows)
+    one or two groups, entity 2 (1 row) passive with id -1; then random ids / uids (negative uids: pmod) against the
+    restatement, every combination of bounds."""
+    from gdmix_b200 import partition as P
+    ent, uid = torch.from_numpy(REF_ENTITY).cuda(), torch.from_numpy(REF_UID).cuda()
+    gid = P.group_ids(ent, uid, 2, 4).cpu().numpy()
+    assert (gid[REF_ENTITY == 0] == 0).all() and (gid[REF_ENTITY == 2] == -1).all()
+    assert 1 <= len(set(gid[REF_ENTITY == 1])) <= 2
+    np.testing.assert_array_equal(gid, _np_group_ids(REF_ENTITY, REF_UID, 2, 4))
+    rng = np.random.default_rng(3)
+    entity = rng.integers(0, 5000, 200_000) ** 2 % 7919
+    uids = rng.integers(-1 << 40, 1 << 40, 200_000)
+    e, u = torch.from_numpy(entity).cuda(), torch.from_numpy(uids).cuda()
+    for lower, upper in ((None, None), (5, None), (None, 7), (3, 20), (40, 10)):
+        got = P.group_ids(e, u, lower, upper).cpu().numpy()
+        np.testing.assert_array_equal(got, _np_group_ids(entity, uids, lower, upper))
+
+
+def test_offset_join_reference_fixture_and_random():
+    """OffsetUpdaterTest.testUpdateOffset (1.0 / 2.0, and 0.9 / 1.8 with the per-coordinate score subtracted in fp32),
+    then a shuffled score file that misses some uids: the inner join's surviving rows and their offsets."""
+    from gdmix_b200 import partition as P
+    uid = torch.tensor([1, 2], dtype=torch.int64).cuda()
+    s_uid = torch.tensor([2, 1], dtype=torch.int64).cuda()
+    score = torch.tensor([2.0, 1.0], dtype=torch.float32).cuda()
+    pc = torch.tensor([0.2, 0.1], dtype=torch.float32).cuda()
+    off, m = P.join_offsets(uid, s_uid, score)
+    assert m.all() and off.cpu().tolist() == [1.0, 2.0]
+    off, m = P.join_offsets(uid, s_uid, score, pc)
+    np.testing.assert_array_equal(off.cpu().numpy(), np.array([1.0, 2.0], np.float32) - np.array([0.1, 0.2], np.float32))
+    rng = np.random.default_rng(8)
+    n = 100_000
+    uids = rng.permutation(1 << 20)[:n].astype(np.int64) - 1000
+    keep = rng.random(n) < 0.9
+    order = rng.permutation(int(keep.sum()))
+    s_uid_h = uids[keep][order]
+    s_h = rng.standard_normal(s_uid_h.shape[0]).astype(np.float32)
+    pc_h = rng.standard_normal(s_uid_h.shape[0]).astype(np.float32)
+    off, m = P.join_offsets(torch.from_numpy(uids).cuda(), torch.from_numpy(s_uid_h).cuda(), torch.from_numpy(s_h).cuda(),
+                            torch.from_numpy(pc_h).cuda())
+    np.testing.assert_array_equal(m.cpu().numpy(), keep)
+    want = dict(zip(s_uid_h.tolist(), (s_h - pc_h).tolist()))
+    got = off.cpu().numpy()
+    np.testing.assert_array_equal(got[keep], np.array([want[u] for u in uids[keep].tolist()], np.float32))
+
+
+def test_partition_and_write_layout_matches_the_spark_job(tmp_path):
+    """groupPartitionAndSaveDataset on the reference's fixture (DataPartitionerTest.scala:25-45, 194-224) and on random
+    data: active|passive/partitionId=k files of one SequenceExample per (entity, group), rows of a record in arrival
+    order, partition = abs(hashCode(str(entity))) % n, partitionList.txt = sorted partitions that hold a record,
+    offsets joined by uid with unmatched rows dropped -- read back with the package's reader and compared with a numpy
+    restatement."""
+    from gdmix_b200 import partition as P
+    from gdmix_b200.io import tfrecord as T
+    from oracle import oracle as O
+
+    def run(entity, uid, lens, cols, vals, label, nparts, lower, upper, scores=None, sub="a"):
+        rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        out = tmp_path / sub
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        sc = None if scores is None else tuple(to(x) for x in scores)
+        plist = out / "partitionList.txt"
+        P.partition_and_write(str(out), to(entity), to(uid), to(rowptr), to(cols.astype(np.int32)), to(vals), to(label), nparts,
+                              scores=sc, lower_bound=lower, upper_bound=upper, entity_name="entityId", bag="global",
+                              label_name="label", partition_list_file=str(plist))
+        # restatement
+        live = np.ones(len(entity), bool)
+        offs = np.zeros(len(entity), np.float32)
+        if scores is not None:
+            lut = {int(u): float(s) for u, s in zip(scores[0][::-1], scores[1][::-1])}
+            live = np.array([int(u) in lut for u in uid])
+            offs = np.array([lut.get(int(u), 0.0) for u in uid], np.float32)
+        gid = np.full(len(entity), 99, np.int32)
+        gid[live] = _np_group_ids(entity[live], uid[live], lower, upper)
+        want = {}
+        for i in np.flatnonzero(live):
+            k = O.partition_id(str(int(entity[i])), nparts)
+            cls = "active" if gid[i] == 0 else "passive"
+            want.setdefault((cls, k), {}).setdefault((int(entity[i]), int(gid[i])), []).append(i)
+        assert sorted(int(x) for x in plist.read_text().split(",")) == sorted({k for (_, k) in want})
+        for (cls, k), recs in want.items():
+            f = out / cls / f"partitionId={k}" / "part-00000.tfrecord"
+            assert f.exists(), (cls, k)
+            d = capi.parse_entity_grouped(f.read_bytes(), "entityId", "uid", "label", "offset", None, "global_indices",
+                                          "global_values")
+            assert sum(1 for _ in T.read_records(str(f), verify_crc=True)) == len(recs)
+            got = {}
+            r = q = 0
+            for e, n in enumerate(d["ent_rows"]):
+                rows = []
+                for i in range(n):
+                    kk = d["row_len"][r + i]
+                    rows.append((int(d["uid"][r + i]), float(d["label"][r + i]), float(d["offset"][r + i]),
+                                 d["gcol"][q:q + kk].tolist(), d["val"][q:q + kk].tolist()))
+                    q += kk
+                r += n
+                got.setdefault(int(d["entity_ids"][e]), []).append(rows)
+            exp = {}
+            for (ent, g), idx in recs.items():
+                exp.setdefault(ent, []).append([(int(uid[i]), float(label[i]), float(offs[i]),
+                                                 cols[rowptr[i]:rowptr[i + 1]].tolist(), vals[rowptr[i]:rowptr[i + 1]].tolist())
+                                                for i in idx])
+            assert {e: sorted(v) for e, v in got.items()} == {e: sorted(v) for e, v in exp.items()}
+        files = {(p.parent.parent.name, int(p.parent.name.split("=")[1])) for p in out.glob("*/partitionId=*/*.tfrecord")}
+        assert files == set(want)
+
+    lens = np.array([len(x) for x in REF_INDICES])
+    cols = np.concatenate(REF_INDICES).astype(np.int64)
+    vals = np.concatenate(REF_VALUES).astype(np.float32)
+    run(REF_ENTITY, REF_UID, lens, cols, vals, REF_LABEL, 3, 2, 4, sub="ref")
+    rng = np.random.default_rng(12)
+    n = 5000
+    entity = (rng.integers(0, 300, n) ** 2 % 401).astype(np.int64)
+    uid = rng.permutation(n).astype(np.int64)
+    lens = rng.integers(0, 6, n)
+    cols = rng.integers(0, 1000, int(lens.sum())).astype(np.int64)
+    vals = rng.standard_normal(int(lens.sum())).astype(np.float32)
+    label = rng.integers(0, 2, n).astype(np.float32)
+    run(entity, uid, lens, cols, vals, label, 7, 4, 9, sub="rnd")
+    keep = rng.random(n) < 0.8
+    s_uid = uid[keep][rng.permutation(int(keep.sum()))]
+    run(entity, uid, lens, cols, vals, label, 5, None, 6, scores=(s_uid, rng.standard_normal(s_uid.shape[0]).astype(np.float32)),
+        sub="joined")
