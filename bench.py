@@ -17,7 +17,8 @@ The same line carries, outside the headline's timed region:
                (oracle/lr_oracle.c): fraction within 1e-5 relative, max deviation, iteration counts
   sub          the other configurations of BASELINE.json at one rank's share: `fe` (configs[2]: fixed-effect
                objective + NCCL all-reduce + device-resident L-BFGS at N ranks), `sweep` (configs[4]), `small`
-               (configs[3] per-user shape), `chain` (configs[3] FE -> per-user -> per-item)
+               (configs[3] per-user shape), `chain` (configs[3] FE -> per-user -> per-item), and (N=1) `e2e_plugin`: a
+               generated C1 TFRecord partition -> RandomEffectLRLBFGSModel.train -> model + score Avro, wall clock
   cpu_baseline the reference's CPU path on the host cores over the first entities of the timed batch (N=1)
 
 Reference arm (--impl reference): the reference's own BinaryLogisticRegressionTrainer (staged under oracle/_ref by
@@ -556,6 +557,17 @@ def run_ours(args):
             torch.cuda.empty_cache()
             barrier()
 
+    # ---- the plugin class end to end: TFRecord partition on disk -> RandomEffectLRLBFGSModel.train -> Avro files (N=1) ----
+    if rank == 0 and world == 1 and not args.no_sub and args.plugin_entities > 0:
+        t0 = time.perf_counter()
+        try:
+            from tools import plugin_bench
+            sub["e2e_plugin"] = plugin_bench.run(E=args.plugin_entities, files=16)
+        except Exception as ex:
+            sub["e2e_plugin"] = {"error": repr(ex)}
+        sub["e2e_plugin"]["wall_s"] = time.perf_counter() - t0
+        torch.cuda.empty_cache()
+
     # ---- measured DRAM traffic of this build's kernels (ncu over a small instance, N=1 only) -------------------
     if rank == 0 and world == 1 and not args.no_traffic_probe:
         tr = probe_traffic("c1")
@@ -621,6 +633,7 @@ def main():
     ap.add_argument("--sweep-entities", type=int, default=2_000_000)
     ap.add_argument("--fe-rows", type=int, default=62_500_000)
     ap.add_argument("--chain-rows", type=int, default=40_000_000)
+    ap.add_argument("--plugin-entities", type=int, default=50_000, help="entities of the generated partition of the e2e_plugin leg (0: skip)")
     ap.add_argument("--threads-per-entity", type=int, default=0)
     ap.add_argument("--probe", default=None, help="internal: the workload ncu profiles for roofline.traffic")
     args = ap.parse_args()

@@ -36,7 +36,7 @@ SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_w
            "gdmix_seqex_count", "gdmix_seqex_fill", "gdmix_example_count", "gdmix_example_fill", "gdmix_avro_score_blocks", "gdmix_avro_model_blocks",
            "gdmix_feature_map_create", "gdmix_feature_map_destroy", "gdmix_avro_model_decode",
            "gdmix_fe_lbfgs_create", "gdmix_fe_lbfgs_reset", "gdmix_fe_lbfgs_step", "gdmix_fe_lbfgs_poll",
-           "gdmix_fe_lbfgs_destroy", "gdmix_fe_column_counts", "gdmix_remap_i32", "gdmix_group_ids", "gdmix_offset_join", "gdmix_seqex_encode", "gdmix_fe_tile_plan_create",
+           "gdmix_fe_lbfgs_destroy", "gdmix_fe_column_counts", "gdmix_remap_i32", "gdmix_group_ids", "gdmix_offset_join", "gdmix_seqex_encode", "gdmix_local_index_host", "gdmix_fe_tile_plan_create",
            "gdmix_fe_tile_plan_destroy", "gdmix_fe_tile_plan_info", "gdmix_fe_loss_grad_tiled"]
 
 
@@ -597,6 +597,28 @@ def parse_entity_grouped(file_image, entity, uid, label, offset, weight, bag_ind
     return out
 
 
+def local_index_host(ent_rowptr, rowptr, gcol):
+    """np.unique per entity over a parsed partition (gdmix_local_index_host, all host threads).
+    -> (local int32[nnz], d_e int64[E], uniq_ptr int64[E+1], uniq_global int64[sum d_e])"""
+    ent_rowptr = np.ascontiguousarray(ent_rowptr, dtype=np.int64)
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    gcol = np.ascontiguousarray(gcol, dtype=np.int64)
+    E = ent_rowptr.shape[0] - 1
+    nnz = int(rowptr[ent_rowptr[-1]]) if E >= 0 else 0
+    local = np.empty(max(nnz, 1), np.int32)
+    d_e = np.zeros(max(E, 1), np.int64)
+    scratch = np.empty(max(nnz, 1), np.int64)
+    check(lib.gdmix_local_index_host(_np_ptr(ent_rowptr), _np_ptr(rowptr), _np_ptr(gcol), C.c_int64(E), _np_ptr(local),
+                                     _np_ptr(d_e), _np_ptr(scratch), None, None))
+    d_e = d_e[:E]
+    uniq_ptr = np.zeros(E + 1, np.int64)
+    np.cumsum(d_e, out=uniq_ptr[1:])
+    uniq_global = np.empty(max(int(uniq_ptr[-1]), 1), np.int64)
+    check(lib.gdmix_local_index_host(_np_ptr(ent_rowptr), _np_ptr(rowptr), _np_ptr(gcol), C.c_int64(E), None,
+                                     _np_ptr(np.ascontiguousarray(d_e)), _np_ptr(scratch), _np_ptr(uniq_ptr), _np_ptr(uniq_global)))
+    return local[:nnz], d_e, uniq_ptr, uniq_global[:int(uniq_ptr[-1])]
+
+
 def encode_entity_grouped(ent_rows, row_len, gcol, val, uid, entity_int=None, entity_str=None, label=None,
                           label_as_int=True, offset=None, weight=None, entity="entity", uid_name="uid",
                           label_name="response", offset_name="offset", weight_name="weight", bag=None):
@@ -632,6 +654,28 @@ def encode_entity_grouped(ent_rows, row_len, gcol, val, uid, entity_int=None, en
     written = C.c_int64()
     check(lib.gdmix_seqex_encode(*args, _np_ptr(out), C.c_int64(out.size), C.byref(written)))
     return out[:written.value]
+
+
+def seqex_spec(entity, uid, label, offset, weight, bag_indices, bag_values):
+    enc = lambda x: None if x is None else x.encode("utf-8")
+    return SeqexSpec(enc(entity), enc(uid), enc(label), enc(offset), enc(weight), enc(bag_indices), enc(bag_values))
+
+
+def seqex_count(buf, spec):
+    """gdmix_seqex_count over a uint8 numpy view of one uncompressed file -> SeqexSizes."""
+    sz = SeqexSizes()
+    check(lib.gdmix_seqex_count(_np_ptr(buf), C.c_int64(buf.size), C.byref(spec), C.byref(sz)))
+    return sz
+
+
+def seqex_fill_into(buf, spec, out, e0, r0, q0, id_chars, id_ptr):
+    """gdmix_seqex_fill of one file straight into the partition-wide arrays `out` at entity e0 / row r0 / non-zero q0;
+    the file's entity-id strings go to its own id_chars / id_ptr (small)."""
+    at = lambda a, i: None if a is None else C.c_void_p(a.ctypes.data + i * a.itemsize)
+    check(lib.gdmix_seqex_fill(_np_ptr(buf), C.c_int64(buf.size), C.byref(spec), at(out["ent_rows"], e0),
+                               at(out["row_len"], r0), at(out["gcol"], q0), at(out["val"], q0), at(out["uid"], r0),
+                               at(out["label"], r0), at(out["offset"], r0), at(out["weight"], r0),
+                               _np_ptr(id_chars), _np_ptr(id_ptr)))
 
 
 def parse_per_record(file_image, uid, label, offset, weight, bag_indices, bag_values):
@@ -683,13 +727,28 @@ def _string_table(strings):
     return np.ascontiguousarray(chars), ptr
 
 
+_FEATURE_TABLES = {}
+
+
+def _feature_tables(feature_names, feature_terms):
+    """String tables of the feature file's names / terms, kept for the last pair of lists seen (same objects)."""
+    key = (id(feature_names), id(feature_terms), len(feature_names))
+    hit = _FEATURE_TABLES.get(key)
+    if hit is not None and hit[0] is feature_names and hit[1] is feature_terms:
+        return hit[2]
+    nc, npt = _string_table(list(feature_names))
+    tc, tpt = _string_table(list(feature_terms))
+    _FEATURE_TABLES.clear()
+    _FEATURE_TABLES[key] = (feature_names, feature_terms, (nc, npt, tc, tpt))
+    return nc, npt, tc, tpt
+
+
 def avro_model_blocks(model_ids, coef, var, coef_ptr, feat_idx, has_intercept, threshold, feature_names, feature_terms,
                       model_class, intercept_name, sync, records_per_block=1024):
     """-> bytes: the blocks of an Avro container holding these BayesianLinearModelAvro records
     (gdmix_avro_model_blocks; the layout of its arguments is documented in include/gdmix_b200.h)."""
     idc, idp = _string_table([str(m) for m in model_ids])
-    nc, npt = _string_table(list(feature_names))
-    tc, tpt = _string_table(list(feature_terms))
+    nc, npt, tc, tpt = _feature_tables(feature_names, feature_terms)
     coef = np.ascontiguousarray(coef, dtype=np.float64)
     var = None if var is None else np.ascontiguousarray(var, dtype=np.float64)
     coef_ptr = np.ascontiguousarray(coef_ptr, dtype=np.int64)

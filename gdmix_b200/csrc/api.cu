@@ -1679,6 +1679,21 @@ int gdmix_offset_join(const int64_t *uid, int64_t n, const uint64_t *score_uid_s
     return GDMIX_OK;
 }
 
+int gdmix_local_index_host(const int64_t *ent_rowptr, const int64_t *rowptr, const int64_t *gcol, int64_t n_entities,
+                           int32_t *local_col, int64_t *d_e, int64_t *scratch, const int64_t *uniq_ptr, int64_t *uniq_global)
+{
+    if (n_entities < 0 || !ent_rowptr || !rowptr || !d_e || !scratch) return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_local_index_host");
+    if (!uniq_global) {
+        if (!local_col && n_entities > 0) return fail(GDMIX_ERR_INVALID, "null local_col");
+        if (gdmix_host::local_index_pass1(ent_rowptr, rowptr, gcol, n_entities, local_col, d_e, scratch) != 0)
+            return fail(GDMIX_ERR_INVALID, "negative feature index");
+        return GDMIX_OK;
+    }
+    if (!uniq_ptr) return fail(GDMIX_ERR_INVALID, "null uniq_ptr");
+    gdmix_host::local_index_pass2(ent_rowptr, rowptr, n_entities, d_e, uniq_ptr, scratch, uniq_global);
+    return GDMIX_OK;
+}
+
 int gdmix_seqex_encode(const gdmix_seqex_spec *spec, int64_t n_entities, const int64_t *ent_rows, const int64_t *entity_int,
                        const char *id_chars, const int64_t *id_ptr, const int64_t *row_len, const int64_t *gcol,
                        const float *val, const int64_t *uid, const float *label, int32_t label_as_int, const float *offset,

@@ -5,6 +5,7 @@
 // <count varint> <size varint> <records> <16-byte sync>, exactly what batched_write_avro (:299-334) appends.
 // The Python writer (gdmix_b200/io/avro.py) produces the same bytes one record at a time at ~120 k records/s.
 #pragma once
+#include <vector>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -126,20 +127,41 @@ inline bool avro_one_model(const ModelTable &t, int64_t m, Sink &o)
 }
 
 // blocks of `per_block` records; out == nullptr: returns the bytes needed.  -1: inconsistent input.
+// Blocks are sized, then written, by all host threads (a block's bytes depend on nothing outside it).
 inline int64_t avro_model_blocks(const ModelTable &t, int32_t per_block, const uint8_t *sync, uint8_t *out)
 {
-    Sink o{out};
-    for (int64_t b0 = 0; b0 < t.n_models; b0 += per_block) {
+    const int64_t nb = (t.n_models + per_block - 1) / per_block;
+    std::vector<int64_t> body((size_t)nb, 0), start((size_t)nb + 1, 0);
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(| : bad)
+    for (int64_t b = 0; b < nb; b++) {
+        const int64_t b0 = b * per_block;
         const int64_t cnt = (t.n_models - b0 < per_block) ? t.n_models - b0 : per_block;
         Sink size_of{nullptr};
         for (int64_t m = b0; m < b0 + cnt; m++)
-            if (!avro_one_model(t, m, size_of)) return -1;
+            if (!avro_one_model(t, m, size_of)) bad |= 1;
+        body[(size_t)b] = size_of.n;
+    }
+    if (bad) return -1;
+    for (int64_t b = 0; b < nb; b++) {
+        const int64_t b0 = b * per_block;
+        const int64_t cnt = (t.n_models - b0 < per_block) ? t.n_models - b0 : per_block;
+        Sink hdr{nullptr};
+        hdr.lng(cnt); hdr.lng(body[(size_t)b]);
+        start[(size_t)b + 1] = start[(size_t)b] + hdr.n + body[(size_t)b] + 16;
+    }
+    if (!out) return start[(size_t)nb];
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t b = 0; b < nb; b++) {
+        const int64_t b0 = b * per_block;
+        const int64_t cnt = (t.n_models - b0 < per_block) ? t.n_models - b0 : per_block;
+        Sink o{out + start[(size_t)b]};
         o.lng(cnt);
-        o.lng(size_of.n);
+        o.lng(body[(size_t)b]);
         for (int64_t m = b0; m < b0 + cnt; m++) avro_one_model(t, m, o);
         o.raw(sync, 16);
     }
-    return o.n;
+    return start[(size_t)nb];
 }
 
 // ---------------------------------------------------------------------------------------------------------

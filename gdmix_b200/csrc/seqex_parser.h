@@ -12,6 +12,8 @@
 // Two passes over the same buffer: count (entities, samples, non-zeros, id characters), then fill caller-allocated
 // arrays.  Anything malformed is an error with a message, never a silent skip.
 #pragma once
+#include <vector>
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -452,5 +454,73 @@ private:
     const gdmix_seqex_spec &spec_;
     std::string &err_;
 };
+
+// ---------------------------------------------------------------------------------------------------------
+// Entity-local feature indexing on the host (np.unique(cols, return_inverse=True) per entity,
+// job_consumers.py:243): entity e owns rows [ent_rowptr[e], ent_rowptr[e+1]) and their non-zeros; its distinct
+// global ids, ascending, become local indices 0 .. d_e - 1.  All host threads, one entity at a time each:
+// an open-addressing table of the entity's ids, the distinct ones sorted, ranks written back.
+//   pass 1 (uniq_global == nullptr): local[nnz], d_e[E], and the distinct ids parked in `scratch` (int64[nnz], entity
+//           e's at its first non-zero's position)
+//   pass 2: uniq_global[uniq_ptr[e] ..] = the parked ids (uniq_ptr = exclusive scan of d_e, the caller's)
+// Returns -1 when an id is negative.
+// ---------------------------------------------------------------------------------------------------------
+inline int local_index_pass1(const int64_t *ent_rowptr, const int64_t *rowptr, const int64_t *gcol, int64_t E, int32_t *local,
+                             int64_t *d_e, int64_t *scratch)
+{
+    int bad = 0;
+#pragma omp parallel reduction(| : bad)
+    {
+        std::vector<int64_t> keys;
+        std::vector<int32_t> slot_rank;
+        std::vector<int64_t> distinct;
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t e = 0; e < E; e++) {
+            const int64_t q0 = rowptr[ent_rowptr[e]], q1 = rowptr[ent_rowptr[e + 1]];
+            const int64_t nz = q1 - q0;
+            if (nz == 0) { d_e[e] = 0; continue; }
+            size_t cap = 16;
+            while (cap < (size_t)(2 * nz)) cap <<= 1;
+            keys.assign(cap, -1);
+            slot_rank.assign(cap, 0);
+            distinct.clear();
+            const size_t mask = cap - 1;
+            for (int64_t q = q0; q < q1; q++) {
+                const int64_t g = gcol[q];
+                if (g < 0) { bad |= 1; continue; }
+                size_t h = (size_t)((uint64_t)g * 0x9E3779B97F4A7C15ull >> 20) & mask;
+                while (keys[h] != -1 && keys[h] != g) h = (h + 1) & mask;
+                if (keys[h] == -1) { keys[h] = g; distinct.push_back(g); }
+            }
+            std::sort(distinct.begin(), distinct.end());
+            for (size_t r = 0; r < distinct.size(); r++) {
+                const int64_t g = distinct[r];
+                size_t h = (size_t)((uint64_t)g * 0x9E3779B97F4A7C15ull >> 20) & mask;
+                while (keys[h] != g) h = (h + 1) & mask;
+                slot_rank[h] = (int32_t)r;
+                scratch[q0 + (int64_t)r] = g;
+            }
+            for (int64_t q = q0; q < q1; q++) {
+                const int64_t g = gcol[q];
+                if (g < 0) { local[q] = 0; continue; }
+                size_t h = (size_t)((uint64_t)g * 0x9E3779B97F4A7C15ull >> 20) & mask;
+                while (keys[h] != g) h = (h + 1) & mask;
+                local[q] = slot_rank[h];
+            }
+            d_e[e] = (int64_t)distinct.size();
+        }
+    }
+    return bad ? -1 : 0;
+}
+
+inline void local_index_pass2(const int64_t *ent_rowptr, const int64_t *rowptr, int64_t E, const int64_t *d_e,
+                              const int64_t *uniq_ptr, const int64_t *scratch, int64_t *uniq_global)
+{
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t e = 0; e < E; e++) {
+        const int64_t q0 = rowptr[ent_rowptr[e]];
+        for (int64_t r = 0; r < d_e[e]; r++) uniq_global[uniq_ptr[e] + r] = scratch[q0 + r];
+    }
+}
 
 }  // namespace gdmix_host

@@ -88,28 +88,78 @@ def _read_entity_grouped_native(files, entity_name, feature_bag, label_column, o
     pure-Python protobuf walk below, same arrays.  Returns None for the one case it leaves to that walk (float
     entity ids); malformed files raise ValueError like the Python reader does."""
     from . import _capi as capi
-    parts = []
-    for fn in files:
+    # Two passes over the partition's files, each file on its own thread (the parser is native code: the calls release
+    # the GIL): count, then fill straight into the partition-wide arrays -- no per-file arrays, no concatenation.
+    # Uncompressed files are memory-mapped; compressed ones are inflated first.
+    import mmap
+    from concurrent.futures import ThreadPoolExecutor
+    spec = capi.seqex_spec(entity_name, uid_column, label_column, offset_column, weight_column,
+                           feature_bag + INDICES_SUFFIX, feature_bag + VALUES_SUFFIX)
+    keep = []
+
+    def image(fn):
+        if tfrecord.compression_of(fn) or os.path.getsize(fn) == 0:
+            return np.frombuffer(tfrecord._read_all(fn), dtype=np.uint8)
+        with open(fn, "rb") as f:
+            mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        keep.append(mm)
+        return np.frombuffer(mm, dtype=np.uint8)
+
+    def count(fn):
+        buf = image(fn)
         try:
-            parts.append(capi.parse_entity_grouped(tfrecord._read_all(fn), entity_name, uid_column, label_column,
-                                                   offset_column, weight_column, feature_bag + INDICES_SUFFIX,
-                                                   feature_bag + VALUES_SUFFIX))
+            return buf, capi.seqex_count(buf, spec)
         except capi.GdmixError as ex:
             if "Python reader" in str(ex):
-                return None
+                return buf, None
             raise ValueError(f"{fn}: {ex}") from None
+
+    workers = max(1, min(len(files), os.cpu_count() or 1))
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        counted = list(pool.map(count, files))
+        if any(sz is None for _, sz in counted):
+            return None
+        E = sum(sz.n_entities for _, sz in counted)
+        N = sum(sz.n_rows for _, sz in counted)
+        Z = sum(sz.nnz for _, sz in counted)
+        out = {"ent_rows": np.empty(E, np.int64), "row_len": np.empty(N, np.int64), "gcol": np.empty(Z, np.int64),
+               "val": np.empty(Z, np.float32), "uid": np.empty(N, np.int64), "label": np.empty(N, np.float32),
+               "offset": np.empty(N, np.float32), "weight": np.empty(N, np.float32)}
+        starts, e0, r0, q0 = [], 0, 0, 0
+        for _, sz in counted:
+            starts.append((e0, r0, q0))
+            e0 += sz.n_entities; r0 += sz.n_rows; q0 += sz.nnz
+
+        def fill(k):
+            buf, sz = counted[k]
+            idc, idp = np.zeros(max(sz.id_bytes, 1), np.uint8), np.zeros(sz.n_entities + 1, np.int64)
+            try:
+                capi.seqex_fill_into(buf, spec, out, *starts[k], idc, idp)
+            except capi.GdmixError as ex:
+                raise ValueError(f"{files[k]}: {ex}") from None
+            raw = idc.tobytes()
+            return [raw[idp[e]:idp[e + 1]].decode("utf-8") for e in range(sz.n_entities)]
+
+        ids = list(pool.map(fill, range(len(files))))
+    all_labelled = all(sz.all_labelled for _, sz in counted)
+    saw_weight = any(sz.saw_weight for _, sz in counted)
+    del counted
     d = EntityGroupedData()
     d.num_features = int(num_features)
-    cat = lambda key, dt: (np.concatenate([p[key] for p in parts]).astype(dt) if parts else np.zeros(0, dt))
-    d.entity_ids = [i for p in parts for i in p["entity_ids"]]
-    d.has_weight_column = any(p["saw_weight"] for p in parts)
-    d.ent_rowptr = np.concatenate([[0], np.cumsum(cat("ent_rows", np.int64))]).astype(np.int64)
-    d.rowptr = np.concatenate([[0], np.cumsum(cat("row_len", np.int64))]).astype(np.int64)
-    d.gcol, d.val = cat("gcol", np.int64), cat("val", np.float32)
-    d.uid, d.offset, d.weight = cat("uid", np.int64), cat("offset", np.float32), cat("weight", np.float32)
-    d.label = cat("label", np.float32) if parts and all(p["all_labelled"] for p in parts) else None
-    if label_column is None:
-        d.label = None
+    d.entity_ids = [i for part in ids for i in part]
+    d.has_weight_column = saw_weight
+    d.ent_rowptr = np.zeros(E + 1, np.int64)
+    np.cumsum(out["ent_rows"], out=d.ent_rowptr[1:])
+    d.rowptr = np.zeros(N + 1, np.int64)
+    np.cumsum(out["row_len"], out=d.rowptr[1:])
+    d.gcol, d.val = out["gcol"], out["val"]
+    d.uid, d.offset, d.weight = out["uid"], out["offset"], out["weight"]
+    d.label = out["label"] if (files and all_labelled and label_column is not None) else None
+    for mm in keep:
+        try:
+            mm.close()
+        except BufferError:      # a numpy view is still alive somewhere: the mapping goes with it
+            pass
     if d.gcol.size and (d.gcol.min() < 0 or d.gcol.max() >= d.num_features):
         raise ValueError(f"feature index outside [0, {d.num_features}) in {input_path}")
     return d
@@ -189,18 +239,10 @@ def read_entity_grouped(input_path, metadata, entity_name, feature_bag, label_co
 
 
 def to_local_batch(data, has_intercept=True):
-    """np.unique per entity, vectorised over the whole partition.
+    """np.unique per entity (job_consumers.py:243) for the whole partition, by the library (all host threads).
     -> (HostBatch with entity-local columns, uniq_ptr int64[E+1], uniq_global int64[sum d_e])"""
-    E = data.n_entities
-    ent_of_row = np.repeat(np.arange(E, dtype=np.int64), np.diff(data.ent_rowptr))
-    ent_of_nnz = np.repeat(ent_of_row, np.diff(data.rowptr))
-    key = ent_of_nnz * np.int64(data.num_features) + data.gcol
-    uk, inv = np.unique(key, return_inverse=True)
-    ent_of_uk = uk // np.int64(data.num_features)
-    d_e = np.bincount(ent_of_uk, minlength=E).astype(np.int64)
-    uniq_ptr = np.concatenate([[0], np.cumsum(d_e)]).astype(np.int64)
-    local = (inv - uniq_ptr[ent_of_nnz]).astype(np.int32)
-    uniq_global = (uk % np.int64(data.num_features)).astype(np.int64)
+    from . import _capi as capi
+    local, d_e, uniq_ptr, uniq_global = capi.local_index_host(data.ent_rowptr, data.rowptr, data.gcol)
     hi = 1 if has_intercept else 0
     theta_ptr = np.concatenate([[0], np.cumsum(d_e + hi)]).astype(np.int64)
     label = data.label if data.label is not None else np.zeros(data.n_rows, np.float32)
@@ -219,6 +261,8 @@ def warm_start_theta(hb, uniq_ptr, uniq_global, entity_ids, model_weights, has_i
     has_model = np.zeros(E, np.uint8)
     if not model_weights:
         return theta0, has_model
+    if hasattr(model_weights, "theta_ptr") and hasattr(model_weights, "index"):
+        return _warm_start_from_flat(hb, uniq_ptr, uniq_global, entity_ids, model_weights, hi, theta0, has_model)
     ents, idxs, coefs = [], [], []
     for e, eid in enumerate(entity_ids):
         prior = model_weights.get(eid)
@@ -244,6 +288,43 @@ def warm_start_theta(hb, uniq_ptr, uniq_global, entity_ids, model_weights, has_i
     pos = np.minimum(np.searchsorted(p_key, c_key), p_key.size - 1)
     hit = p_key[pos] == c_key
     k = np.flatnonzero(hit)
+    theta0[hb.theta_ptr[c_ent[k]] + hi + (k - uniq_ptr[c_ent[k]])] = p_coef[pos[k]]
+    return theta0, has_model
+
+
+def _warm_start_from_flat(hb, uniq_ptr, uniq_global, entity_ids, fm, hi, theta0, has_model):
+    """warm_start_theta when the prior models are a random_effect.FlatModels (the models a train() just produced):
+    the same merge over (entity, feature) keys, with the prior side taken from the flat arrays instead of one
+    TrainingResult per entity."""
+    E = len(entity_ids)
+    index = fm.index
+    src = np.fromiter((index.get(eid, -1) for eid in entity_ids), dtype=np.int64, count=E)   # prior model of entity e
+    hit_e = np.flatnonzero(src >= 0)
+    has_model[hit_e] = 1
+    if hit_e.size == 0:
+        return theta0, has_model
+    ptp, pup = np.asarray(fm.theta_ptr, np.int64), np.asarray(fm.uniq_ptr, np.int64)
+    if hi:
+        theta0[hb.theta_ptr[hit_e]] = fm.theta[ptp[src[hit_e]]]
+    if E == len(fm.entity_ids) and np.array_equal(src, np.arange(E)) and np.array_equal(pup, uniq_ptr) and \
+            np.array_equal(fm.uniq_global, uniq_global):
+        # the very partition the models were trained on (scoring after training): coefficients line up one to one
+        theta0[:] = fm.theta
+        return theta0, has_model
+    d_prior = np.diff(pup)[src[hit_e]]
+    p_ent = np.repeat(hit_e, d_prior)
+    start = np.repeat(pup[src[hit_e]], d_prior)
+    within = np.arange(p_ent.size, dtype=np.int64) - np.repeat(np.cumsum(d_prior) - d_prior, d_prior)
+    p_idx = np.asarray(fm.uniq_global, np.int64)[start + within]
+    p_coef = fm.theta[np.repeat(ptp[src[hit_e]] + hi, d_prior) + within]
+    if p_idx.size == 0 or uniq_global.size == 0:
+        return theta0, has_model
+    width = np.int64(max(int(p_idx.max()), int(uniq_global.max())) + 1)
+    p_key = p_ent * width + p_idx                        # ascending already: entities ascending, features ascending inside
+    c_ent = np.repeat(np.arange(E, dtype=np.int64), np.diff(uniq_ptr))
+    c_key = c_ent * width + uniq_global
+    pos = np.minimum(np.searchsorted(p_key, c_key), p_key.size - 1)
+    k = np.flatnonzero(p_key[pos] == c_key)
     theta0[hb.theta_ptr[c_ent[k]] + hi + (k - uniq_ptr[c_ent[k]])] = p_coef[pos[k]]
     return theta0, has_model
 

@@ -11,6 +11,7 @@ and the schema at models/schemas.py:3-51.
 """
 import csv
 import json
+import os
 
 import numpy as np
 
@@ -67,8 +68,24 @@ def check_model_schema(writer_schema, where=""):
                          f"(fields {[f.get('name') for f in writer_schema.get('fields', [])]})")
 
 
+_FEATURE_LIST_CACHE = {}
+
+
 def read_feature_list(feature_file):
-    """CSV rows ``name,term``; the row number is the global feature index (intercept not included)."""
+    """CSV rows ``name,term``; the row number is the global feature index (intercept not included).  The parsed list is
+    kept per (path, mtime, size): a job reads the same million-row file for every partition's model and score pass."""
+    st = os.stat(feature_file)
+    key = (os.path.abspath(feature_file), st.st_mtime_ns, st.st_size)
+    hit = _FEATURE_LIST_CACHE.get(key)
+    if hit is not None:
+        return hit
+    result = _read_feature_list(feature_file)
+    _FEATURE_LIST_CACHE.clear()
+    _FEATURE_LIST_CACHE[key] = result
+    return result
+
+
+def _read_feature_list(feature_file):
     result = []
     with open(feature_file, newline="") as f:
         for row in csv.reader(f):
@@ -133,17 +150,34 @@ def export_linear_model_to_avro(model_ids, list_of_weight_indices, list_of_weigh
     avro.write_records(output_file, BAYESIAN_LINEAR_MODEL_SCHEMA, gen_records())
 
 
+_FEATURE_COLUMNS = {}
+
+
+def _feature_columns(feature_file):
+    """(names, terms) of the feature file as two lists, the same list objects for the same parsed file (so that the
+    binding's string tables are built once per job, not once per partition)."""
+    if not feature_file:
+        return [], []
+    fl = read_feature_list(feature_file)
+    hit = _FEATURE_COLUMNS.get(id(fl))
+    if hit is not None and hit[0] is fl:
+        return hit[1], hit[2]
+    names, terms = [f[0] for f in fl], [f[1] for f in fl]
+    _FEATURE_COLUMNS.clear()
+    _FEATURE_COLUMNS[id(fl)] = (fl, names, terms)
+    return names, terms
+
+
 def export_random_effect_models(model_ids, coef, var, coef_ptr, feat_idx, has_intercept, feature_file, output_file,
                                 model_class=LOGISTIC_MODEL_CLASS, sparsity_threshold=1.0e-4, sync=None):
     """The same file export_linear_model_to_avro writes for per-entity models, from flat arrays: model m owns
     coef[coef_ptr[m]:coef_ptr[m+1]] (intercept first when has_intercept; var aligned or None) and feat_idx lists the
     global feature ids of its other coefficients.  Records are encoded by the library (gdmix_avro_model_blocks)."""
     from .. import _capi as capi
-    feature_list = read_feature_list(feature_file) if feature_file else []
+    names, terms = _feature_columns(feature_file)
     with avro.Writer(output_file, BAYESIAN_LINEAR_MODEL_SCHEMA, "null", sync=sync) as w:
         body = capi.avro_model_blocks(model_ids, coef, var, coef_ptr, feat_idx, has_intercept, sparsity_threshold,
-                                      [f[0] for f in feature_list], [f[1] for f in feature_list], model_class, INTERCEPT,
-                                      w.sync)
+                                      names, terms, model_class, INTERCEPT, w.sync)
         w.f.write(body)
         w.count += len(model_ids)
         return w.count

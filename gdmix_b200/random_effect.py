@@ -21,6 +21,7 @@ is no queue.  There is no CPU fallback: without the CUDA library the package doe
 """
 import logging
 import os
+import time
 from collections import namedtuple
 
 import numpy as np
@@ -36,6 +37,55 @@ logger = logging.getLogger(__name__)
 
 # job_consumers.py:19
 TrainingResult = namedtuple("TrainingResult", ("theta", "variance", "unique_global_indices"))
+
+
+class FlatModels:
+    """The models of one partition as the solve returned them -- flat arrays -- behind the mapping interface the
+    reference passes around (entity id -> TrainingResult, job_consumers.py:19).  A partition of a million entities
+    then never becomes a million Python tuples: the model writer and the scoring pass take the arrays as they are, and
+    a TrainingResult is only built for an entity somebody asks for."""
+
+    def __init__(self, entity_ids, theta, variance, theta_ptr, uniq_ptr, uniq_global):
+        self.entity_ids = list(entity_ids)
+        self.theta, self.variance = theta, variance
+        self.theta_ptr, self.uniq_ptr, self.uniq_global = theta_ptr, uniq_ptr, uniq_global
+        self._index = None
+
+    @property
+    def index(self):
+        if self._index is None:
+            self._index = {eid: e for e, eid in enumerate(self.entity_ids)}
+        return self._index
+
+    def _result(self, e):
+        a, b = int(self.theta_ptr[e]), int(self.theta_ptr[e + 1])
+        return TrainingResult(theta=self.theta[a:b].copy(), variance=None if self.variance is None else self.variance[a:b].copy(),
+                              unique_global_indices=self.uniq_global[int(self.uniq_ptr[e]):int(self.uniq_ptr[e + 1])].copy())
+
+    def __len__(self):
+        return len(self.entity_ids)
+
+    def __bool__(self):
+        return bool(self.entity_ids)
+
+    def __contains__(self, eid):
+        return eid in self.index
+
+    def __getitem__(self, eid):
+        return self._result(self.index[eid])
+
+    def get(self, eid, default=None):
+        e = self.index.get(eid)
+        return default if e is None else self._result(e)
+
+    def keys(self):
+        return list(self.entity_ids)
+
+    def __iter__(self):
+        return iter(self.entity_ids)
+
+    def items(self):
+        return ((eid, self._result(e)) for e, eid in enumerate(self.entity_ids))
 
 
 class RandomEffectLRLBFGSModel(Model):
@@ -60,6 +110,8 @@ class RandomEffectLRLBFGSModel(Model):
         self.disable_random_effect_scoring_after_training = \
             self.model_params.disable_random_effect_scoring_after_training
         self.last_fit_info = None  # nit / nfev / status arrays of the latest _train (diagnostics, tests)
+        self.last_timing = {}      # seconds per phase of the latest train() (diagnostics, bench)
+        self._parsed = None        # input path -> parsed partition, alive during one _action call
 
     # ---- Model API ------------------------------------------------------------------------------------
     def train(self, training_data_dir, validation_data_dir, metadata_file, checkpoint_path, execution_context,
@@ -85,6 +137,16 @@ class RandomEffectLRLBFGSModel(Model):
     # ---- orchestration (random_effect_lr_lbfgs_model.py:92-138) ------------------------------------------
     def _action(self, action, action_context, metadata_file, checkpoint_path, execution_context, schema_params):
         partition_index = execution_context[constants.PARTITION_INDEX]
+        self._parsed = {}
+        try:
+            return self._action_impl(action, action_context, metadata_file, checkpoint_path, execution_context,
+                                     schema_params, partition_index)
+        finally:
+            self._parsed = None
+            self._join_writer()
+
+    def _action_impl(self, action, action_context, metadata_file, checkpoint_path, execution_context, schema_params,
+                     partition_index):
         metadata = read_json_file(metadata_file)
         tensor_metadata = DatasetMetadata(metadata)
         # an intercept-only model is padded with one dummy (all-zero) feature
@@ -122,6 +184,30 @@ class RandomEffectLRLBFGSModel(Model):
 
     def _read(self, input_path, tensor_metadata, schema_params, num_features, need_label):
         assert self.model_params.data_format == constants.TFRECORD
+        # scoring after training reads the partition the training just parsed: the parsed arrays (and their entity-local
+        # form) are kept for the duration of one train() / predict() call and reused when the same path comes again
+        cached = self._parsed.get(input_path) if self._parsed is not None else None
+        if cached is not None:
+            data = cached["data"]
+            if need_label and data.label is None:
+                raise ValueError(f"label column {schema_params.label_column_name!r} not found in {input_path}")
+            return data
+        data = self._read_uncached(input_path, tensor_metadata, schema_params, num_features, need_label)
+        if self._parsed is not None:
+            self._parsed[input_path] = {"data": data}
+        return data
+
+    def _local(self, input_path, data):
+        """ingest.to_local_batch, once per parsed partition."""
+        slot = self._parsed.get(input_path) if self._parsed is not None else None
+        if slot is not None and "local" in slot and slot["data"] is data:
+            return slot["local"]
+        loc = ingest.to_local_batch(data, self.has_intercept)
+        if slot is not None and slot["data"] is data:
+            slot["local"] = loc
+        return loc
+
+    def _read_uncached(self, input_path, tensor_metadata, schema_params, num_features, need_label):
         data = ingest.read_entity_grouped(
             input_path, tensor_metadata, entity_name=self.model_params.partition_entity,
             feature_bag=self.feature_bag_name, label_column=schema_params.label_column_name,
@@ -144,14 +230,19 @@ class RandomEffectLRLBFGSModel(Model):
                     f"{f'loaded {len(model_weights)} previous models' if model_weights else 'zeros'} "
                     f"as the model initial value.")
         mp = self.model_params
+        tm = self.last_timing = {}
+        t0 = time.perf_counter()
         data = self._read(input_path, tensor_metadata, schema_params, num_features, need_label=True)
+        tm["read_s"] = time.perf_counter() - t0
         if data.n_entities:
             labels = data.label
             if not np.all((labels == 0) | (labels == 1)):
                 raise ValueError("labels must be 0/1 for logistic regression")  # binary_logistic_regression.py:208
-            hb, uniq_ptr, uniq_global = ingest.to_local_batch(data, self.has_intercept)
+            t0 = time.perf_counter()
+            hb, uniq_ptr, uniq_global = self._local(input_path, data)
             theta0, has_model = ingest.warm_start_theta(hb, uniq_ptr, uniq_global, data.entity_ids, model_weights,
                                                         self.has_intercept)
+            tm["local_index_s"] = time.perf_counter() - t0
             mode = mp.random_effect_variance_mode
             if mode == constants.FULL:
                 vmode = capi.VARIANCE_FULL
@@ -160,40 +251,72 @@ class RandomEffectLRLBFGSModel(Model):
             else:
                 vmode = capi.VARIANCE_NONE
             opts = self._opts(sparsity_threshold=mp.sparsity_threshold, variance_mode=vmode)
+            t0 = time.perf_counter()
             out = capi.re_fit_host(hb, opts, theta0=theta0 if has_model.any() else None,
                                    want_variance=vmode != capi.VARIANCE_NONE)
+            tm["fit_s"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
             self.last_fit_info = {k: out[k] for k in ("nit", "nfev", "status", "f")}
-            results = {}
-            tp = hb.theta_ptr
-            for e, eid in enumerate(data.entity_ids):
-                var = out["variance"][tp[e]:tp[e + 1]].copy() if vmode != capi.VARIANCE_NONE else None
-                results[eid] = TrainingResult(theta=out["theta"][tp[e]:tp[e + 1]].copy(), variance=var,
-                                              unique_global_indices=uniq_global[uniq_ptr[e]:uniq_ptr[e + 1]].copy())
-            # prior-only entities survive; prior-only features of a retrained entity do not (:161)
-            model_weights.update(results)
+            results = FlatModels(data.entity_ids, out["theta"], out["variance"] if vmode != capi.VARIANCE_NONE else None,
+                                 hb.theta_ptr, uniq_ptr, uniq_global)
+            if model_weights:
+                # prior-only entities survive; prior-only features of a retrained entity do not (:161)
+                model_weights = dict(model_weights.items())
+                model_weights.update(dict(results.items()))
+            else:
+                model_weights = results
+            tm["results_s"] = time.perf_counter() - t0
         logger.info(f"{len(model_weights)} models in total after training/refreshing.")
-        self._save_model(output_model_file, model_coefficients=model_weights, num_features=num_features,
-                         feature_file=self.feature_file)
+        # the model file is encoded and written (host threads of the library) while the scoring passes that follow use
+        # the GPU; _action joins the writer before it returns, and its exception, if any, is raised there
+        import threading
+
+        def save():
+            t0 = time.perf_counter()
+            try:
+                self._save_model(output_model_file, model_coefficients=model_weights, num_features=num_features,
+                                 feature_file=self.feature_file)
+            except BaseException as ex:      # noqa: BLE001  (re-raised by _join_writer)
+                self._writer_error = ex
+            tm["save_model_s"] = time.perf_counter() - t0
+
+        self._writer_error = None
+        self._writer = threading.Thread(target=save, name="gdmix-model-writer")
+        self._writer.start()
         return model_weights
+
+    def _join_writer(self):
+        w, self._writer = getattr(self, "_writer", None), None
+        if w is not None:
+            w.join()
+            err, self._writer_error = getattr(self, "_writer_error", None), None
+            if err is not None:
+                raise err
 
     # ---- inference (random_effect_lr_lbfgs_model.py:169-190 + job_consumers.py:102-152) --------------------
     def _predict(self, input_path, metadata, tensor_metadata, output_file, schema_params, num_features,
                  model_weights):
         logger.info(f"Start inference for {input_path}.")
+        tm = self.last_timing
+        t0 = time.perf_counter()
         data = self._read(input_path, tensor_metadata, schema_params, num_features, need_label=False)
         has_weight = any(schema_params.weight_column_name == f.name for f in tensor_metadata.get_features())
         schema = model_io.get_inference_output_avro_schema(metadata, True, schema_params, has_weight=has_weight)
         if data.n_entities:
-            hb, uniq_ptr, uniq_global = ingest.to_local_batch(data, self.has_intercept)
+            hb, uniq_ptr, uniq_global = self._local(input_path, data)
             theta, has_model = ingest.warm_start_theta(hb, uniq_ptr, uniq_global, data.entity_ids, model_weights,
                                                        self.has_intercept)
+            tm["predict_prepare_s"] = tm.get("predict_prepare_s", 0.0) + time.perf_counter() - t0
+            t0 = time.perf_counter()
             logit, per_coordinate = capi.re_score_host(hb, self._opts(), theta, has_model)
+            tm["predict_score_s"] = tm.get("predict_score_s", 0.0) + time.perf_counter() - t0
         else:
             logit = per_coordinate = np.zeros(0, np.float32)
         sp = schema_params
-
+        t0 = time.perf_counter()
         model_io.write_scores(output_file, schema, sp, data.uid, logit, per_coordinate, label=data.label,
                               weight=data.weight)
+        tm["predict_write_s"] = tm.get("predict_write_s", 0.0) + time.perf_counter() - t0
         logger.info(f"Inference complete: {input_path}.")
 
     # ---- model files (random_effect_lr_lbfgs_model.py:219-309) ---------------------------------------------
@@ -201,11 +324,19 @@ class RandomEffectLRLBFGSModel(Model):
         """One Photon-ML BayesianLinearModelAvro record per entity (random_effect_lr_lbfgs_model.py:219-260 ->
         export_linear_model_to_avro): intercept first, features above the sparsity threshold by name / term,
         variances aligned when a variance mode is set.  The records are encoded by the library from flat arrays."""
-        model_ids = list(model_coefficients.keys())
         with_variance = self.model_params.random_effect_variance_mode is not None
         hi = 1 if self.has_intercept else 0
         if feature_file is None:
             assert num_features == 1          # intercept-only model: nothing but the bias is written
+        if isinstance(model_coefficients, FlatModels) and feature_file is not None and \
+                (not with_variance or model_coefficients.variance is not None):
+            fm = model_coefficients
+            os.makedirs(os.path.dirname(output_file) or ".", exist_ok=True)
+            model_io.export_random_effect_models(fm.entity_ids, fm.theta, fm.variance if with_variance else None,
+                                                 fm.theta_ptr, fm.uniq_global, self.has_intercept, feature_file,
+                                                 output_file, sparsity_threshold=self.model_params.sparsity_threshold)
+            return
+        model_ids = list(model_coefficients.keys())
         means, variances, indices = [], [], []
         for entity_id, (mean, variance, unique_global_indices) in model_coefficients.items():
             mean = np.asarray(mean, dtype=np.float64).ravel()

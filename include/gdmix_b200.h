@@ -343,6 +343,13 @@ GDMIX_API int gdmix_seqex_fill(const uint8_t *file_image, int64_t len, const gdm
                                int64_t *row_len, int64_t *gcol, float *val, int64_t *uid, float *label, float *offset,
                                float *weight, char *id_chars, int64_t *id_ptr);
 
+/* Entity-local feature indexing of a parsed partition on the host (np.unique(cols, return_inverse=True) per entity,
+ * job_consumers.py:243), all host threads.  Two calls: uniq_global == NULL -> local_col[nnz], d_e[E] and the distinct
+ * ids parked in scratch (int64[nnz]); then, with uniq_ptr[E+1] = exclusive scan of d_e, uniq_global[uniq_ptr[E]]. */
+GDMIX_API int gdmix_local_index_host(const int64_t *ent_rowptr, const int64_t *rowptr, const int64_t *gcol,
+                                     int64_t n_entities, int32_t *local_col, int64_t *d_e, int64_t *scratch,
+                                     const int64_t *uniq_ptr, int64_t *uniq_global);
+
 /* The writer of the same files (what DataPartitioner's Spark job saves, DataPartitioner.scala:203-280 ->
  * IoUtils.saveDataFrame with recordType SequenceExample): n_entities records, record e = ent_rows[e] consecutive samples;
  * the entity id is entity_int[e] (int64 list) or the utf-8 string id_chars[id_ptr[e] .. id_ptr[e+1]) (bytes list); spec
