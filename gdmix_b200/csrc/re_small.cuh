@@ -18,7 +18,7 @@
 //   * coefficient vectors live in registers (feature j in lane j % 32, slot j / 32), the (S, Y) history in shared
 //     memory; inner products are xor-butterflies, so every lane holds identical scalars and the scalar solver logic
 //     (MINPACK-2 dcsrch, stop tests, skip / restart rules) runs replicated without divergence;
-//   * the direction is the textbook two-loop recursion with H0 = I / theta -- exactly the oracle's arithmetic.
+//   * the direction is the textbook two-loop recursion with H0 = I / theta.
 // Entities that do not fit the slice (rows, non-zeros or coefficients above the launch's capacities) are appended to a
 // list that the next kernel of the cascade drains.  fp64 throughout, no atomics on data, bitwise reproducible.
 #pragma once
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) re_small_kernel(const SmallArgs sa)
             return small_max(s0);
         };
 
-        // ---- L-BFGS-B without bounds, as scipy.optimize.fmin_l_bfgs_b runs it (oracle/lr_oracle.c: lbfgsb_minimize) ----
+        // ---- L-BFGS-B without bounds, as scipy.optimize.fmin_l_bfgs_b runs it ----
         double x[SL], g[SL], dd[SL], t[SL], rr_[SL], q[SL];
 #pragma unroll
         for (int s = 0; s < SL; s++) {
