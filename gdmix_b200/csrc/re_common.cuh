@@ -141,7 +141,9 @@ __device__ __forceinline__ void group_sum(double (&v)[K], double *red, int &flip
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(kFull, v[k], o);
     }
-    if (G == 32) return;
+    // the callers use the reduction as the group's barrier as well (shared-memory writes before it are read after it):
+    // with one warp per group the shuffles converge the lanes but order no memory -- __syncwarp does
+    if (G == 32) { __syncwarp(); return; }
     constexpr int W = G / 32;
     double *buf = red + flip * (kMaxWarps * kRedK);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -165,7 +167,7 @@ __device__ __forceinline__ double group_max(double v, double *red, int &flip)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
-    if (G == 32) return v;
+    if (G == 32) { __syncwarp(); return v; }
     constexpr int W = G / 32;
     double *buf = red + flip * (kMaxWarps * kRedK);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -187,7 +189,7 @@ __device__ __forceinline__ void group_sum_max(double &sum, double &mx, double *r
         sum += __shfl_xor_sync(kFull, sum, o);
         mx = fmax(mx, __shfl_xor_sync(kFull, mx, o));
     }
-    if (G == 32) return;
+    if (G == 32) { __syncwarp(); return; }
     constexpr int W = G / 32;
     double *buf = red + flip * (kMaxWarps * kRedK);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
