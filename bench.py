@@ -613,6 +613,10 @@ def run_ours(args):
         sys.stdout.flush()
         sys.stdout.write(json.dumps(line) + "\n")
         sys.stdout.flush()
+        if world > 1:
+            # NCCL (with NCCL_DEBUG set) logs from a destructor at process exit; the JSON line must stay the last line
+            sys.stderr.flush()
+            os._exit(0)
 
 
 def main():
