@@ -1176,42 +1176,74 @@ int gdmix_re_score_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const 
     const int64_t E = hb->n_entities;
     if (E <= 0) return GDMIX_OK;
     std::lock_guard<std::mutex> lk(g_host.mu);
-    const int64_t nr = hb->ent_rowptr[E], nz = hb->rowptr[nr], nt = hb->theta_ptr[E];
-    if (nz > 0 && (!hb->col || !hb->val)) return fail(GDMIX_ERR_INVALID, "gdmix_re_score_host needs the int32 col and val");
-    size_t o_ent = 0, o_row = up256(8 * (E + 1)), o_tp = o_row + up256(8 * (nr + 1));
-    size_t o_col = o_tp + up256(8 * (E + 1)), o_val = o_col + up256(4 * nz), o_off = o_val + up256(4 * nz);
-    size_t o_th = o_off + up256(4 * nr), o_hm = o_th + up256(8 * nt), o_in = o_hm + up256(E);
-    size_t o_lg = o_in, o_pc = o_lg + up256(4 * nr), total = o_pc + up256(4 * nr);
-    Slot &s = g_host.slot[0];
-    int rc = ensure(s, total, 0, 0);
-    if (rc) return rc;
-    char *dv = (char *)s.dev;
-    CUDA_TRY(cudaMemcpyAsync(dv + o_ent, hb->ent_rowptr, 8 * (E + 1), cudaMemcpyHostToDevice, s.st));
-    CUDA_TRY(cudaMemcpyAsync(dv + o_row, hb->rowptr, 8 * (nr + 1), cudaMemcpyHostToDevice, s.st));
-    CUDA_TRY(cudaMemcpyAsync(dv + o_tp, hb->theta_ptr, 8 * (E + 1), cudaMemcpyHostToDevice, s.st));
-    if (nz) {
-        CUDA_TRY(cudaMemcpyAsync(dv + o_col, hb->col, 4 * nz, cudaMemcpyHostToDevice, s.st));
-        CUDA_TRY(cudaMemcpyAsync(dv + o_val, hb->val, 4 * nz, cudaMemcpyHostToDevice, s.st));
+    const int64_t nr_all = hb->ent_rowptr[E], nz_all = hb->rowptr[nr_all];
+    if (nz_all > 0 && (!hb->col || !hb->val)) return fail(GDMIX_ERR_INVALID, "gdmix_re_score_host needs the int32 col and val");
+    // Chunks of about 512 MB of input, alternating between two slots (the upload of a chunk runs under the scoring and
+    // the download of the one before): a partition that trained in chunks scores in chunks.  The kernel indexes with the
+    // batch's absolute row / non-zero / coefficient numbers, so a chunk's device arrays are handed to it shifted back
+    // by the chunk's first row / non-zero / coefficient.
+    const char *env_chunk = getenv("GDMIX_SCORE_CHUNK_BYTES");    // test hook
+    const int64_t budget = env_chunk ? std::max<int64_t>(1, atoll(env_chunk)) : (512ll << 20);
+    int64_t e0 = 0;
+    int k = 0;
+    while (e0 < E) {
+        const int64_t r0 = hb->ent_rowptr[e0], q0 = hb->rowptr[r0], t0 = hb->theta_ptr[e0];
+        int64_t e1 = e0 + 1;
+        {
+            // largest e1 with bytes(e0 .. e1) <= budget (at least one entity): bisection over the cumulative arrays
+            auto bytes_to = [&](int64_t e) {
+                const int64_t r = hb->ent_rowptr[e], q = hb->rowptr[r];
+                return 8 * (q - q0) + 16 * (r - r0) + 8 * (hb->theta_ptr[e] - t0) + 17 * (e - e0);
+            };
+            int64_t lo = e0 + 1, hi2 = E;
+            while (lo < hi2) {
+                const int64_t mid = (lo + hi2 + 1) >> 1;
+                if (bytes_to(mid) <= budget) lo = mid; else hi2 = mid - 1;
+            }
+            e1 = lo;
+        }
+        const int64_t Ec = e1 - e0, r1 = hb->ent_rowptr[e1], q1 = hb->rowptr[r1], t1 = hb->theta_ptr[e1];
+        const int64_t nr = r1 - r0, nz = q1 - q0, nt = t1 - t0;
+        size_t o_ent = 0, o_row = up256(8 * (Ec + 1)), o_tp = o_row + up256(8 * (nr + 1));
+        size_t o_col = o_tp + up256(8 * (Ec + 1)), o_val = o_col + up256(4 * nz), o_off = o_val + up256(4 * nz);
+        size_t o_th = o_off + up256(4 * nr), o_hm = o_th + up256(8 * nt), o_in = o_hm + up256(Ec);
+        size_t o_lg = o_in, o_pc = o_lg + up256(4 * nr), total = o_pc + up256(4 * nr);
+        Slot &s = g_host.slot[k & 1];
+        if (s.st) CUDA_TRY(cudaStreamSynchronize(s.st));     // the chunk that used this slot two turns ago is home
+        int rc = ensure(s, total, 0, 0);
+        if (rc) return rc;
+        char *dv = (char *)s.dev;
+        CUDA_TRY(cudaMemcpyAsync(dv + o_ent, hb->ent_rowptr + e0, 8 * (Ec + 1), cudaMemcpyHostToDevice, s.st));
+        CUDA_TRY(cudaMemcpyAsync(dv + o_row, hb->rowptr + r0, 8 * (nr + 1), cudaMemcpyHostToDevice, s.st));
+        CUDA_TRY(cudaMemcpyAsync(dv + o_tp, hb->theta_ptr + e0, 8 * (Ec + 1), cudaMemcpyHostToDevice, s.st));
+        if (nz) {
+            CUDA_TRY(cudaMemcpyAsync(dv + o_col, hb->col + q0, 4 * nz, cudaMemcpyHostToDevice, s.st));
+            CUDA_TRY(cudaMemcpyAsync(dv + o_val, hb->val + q0, 4 * nz, cudaMemcpyHostToDevice, s.st));
+        }
+        if (hb->offset) CUDA_TRY(cudaMemcpyAsync(dv + o_off, hb->offset + r0, 4 * nr, cudaMemcpyHostToDevice, s.st));
+        if (theta) CUDA_TRY(cudaMemcpyAsync(dv + o_th, theta + t0, 8 * nt, cudaMemcpyHostToDevice, s.st));
+        if (has_model) CUDA_TRY(cudaMemcpyAsync(dv + o_hm, has_model + e0, Ec, cudaMemcpyHostToDevice, s.st));
+        gdmix_re_batch db = *hb;
+        db.n_entities = Ec;
+        db.ent_rowptr = (const int64_t *)(dv + o_ent);
+        db.rowptr = (const int64_t *)(dv + o_row) - r0;
+        db.theta_ptr = (const int64_t *)(dv + o_tp);
+        db.col = (const int32_t *)(dv + o_col) - q0;
+        db.val = (const float *)(dv + o_val) - q0;
+        db.label = nullptr; db.weight = nullptr;
+        db.n_rows = nr; db.nnz = nz;
+        db.offset = hb->offset ? (const float *)(dv + o_off) - r0 : nullptr;
+        rc = gdmix_re_score(&db, o, theta ? (const double *)(dv + o_th) - t0 : nullptr,
+                            has_model ? (const uint8_t *)(dv + o_hm) : nullptr, (float *)(dv + o_lg) - r0,
+                            (float *)(dv + o_pc) - r0, s.st);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(logit + r0, dv + o_lg, 4 * nr, cudaMemcpyDeviceToHost, s.st));
+        CUDA_TRY(cudaMemcpyAsync(logit_pc + r0, dv + o_pc, 4 * nr, cudaMemcpyDeviceToHost, s.st));
+        e0 = e1;
+        k++;
     }
-    if (hb->offset) CUDA_TRY(cudaMemcpyAsync(dv + o_off, hb->offset, 4 * nr, cudaMemcpyHostToDevice, s.st));
-    if (theta) CUDA_TRY(cudaMemcpyAsync(dv + o_th, theta, 8 * nt, cudaMemcpyHostToDevice, s.st));
-    if (has_model) CUDA_TRY(cudaMemcpyAsync(dv + o_hm, has_model, E, cudaMemcpyHostToDevice, s.st));
-    gdmix_re_batch db = *hb;
-    db.ent_rowptr = (const int64_t *)(dv + o_ent);
-    db.rowptr = (const int64_t *)(dv + o_row);
-    db.theta_ptr = (const int64_t *)(dv + o_tp);
-    db.col = (const int32_t *)(dv + o_col);
-    db.val = (const float *)(dv + o_val);
-    db.label = nullptr; db.weight = nullptr;
-    db.n_rows = nr; db.nnz = nz;
-    db.offset = hb->offset ? (const float *)(dv + o_off) : nullptr;
-    rc = gdmix_re_score(&db, o, theta ? (const double *)(dv + o_th) : nullptr,
-                        has_model ? (const uint8_t *)(dv + o_hm) : nullptr, (float *)(dv + o_lg),
-                        (float *)(dv + o_pc), s.st);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(logit, dv + o_lg, 4 * nr, cudaMemcpyDeviceToHost, s.st));
-    CUDA_TRY(cudaMemcpyAsync(logit_pc, dv + o_pc, 4 * nr, cudaMemcpyDeviceToHost, s.st));
-    CUDA_TRY(cudaStreamSynchronize(s.st));
+    for (int j = 0; j < 2; j++)
+        if (g_host.slot[j].st) CUDA_TRY(cudaStreamSynchronize(g_host.slot[j].st));
     return GDMIX_OK;
 }
 
@@ -1401,8 +1433,8 @@ gdmix_fe_tile_plan *gdmix_fe_tile_plan_create(const gdmix_fe_rows *rows, int32_t
     int64_t tot_hot_z = 0, tot_cold_z = 0;
     if (n > 0) {
         gdmix::fe_zcount_kernel<<<grid_for(n, 256), 256, 0, st>>>(rows->rowptr, rows->col, n, hz, zh_len, zc_len, err);
-        gdmix::fe_zblock_kernel<<<grid_for(P.n_blocks, 256), 256, 0, st>>>(zh_len, n, P.n_blocks, 8u, blk_cnt);
-        gdmix::fe_zblock_kernel<<<grid_for(P.n_blocks, 256), 256, 0, st>>>(zc_len, n, P.n_blocks, 4u, cblk_cnt);
+        gdmix::fe_zblock_kernel<<<grid_for(P.n_blocks, 256), 256, 0, st>>>(zh_len, n, P.n_blocks, 4u, 8u, blk_cnt);
+        gdmix::fe_zblock_kernel<<<grid_for(P.n_blocks, 256), 256, 0, st>>>(zc_len, n, P.n_blocks, 1u, 4u, cblk_cnt);
         g_launches += 3;
     }
     PLAN_TRY(exclusive_scan_u32(blk_cnt, P.n_blocks, zh_blk, scan_ws, st));
@@ -1413,7 +1445,7 @@ gdmix_fe_tile_plan *gdmix_fe_tile_plan_create(const gdmix_fe_rows *rows, int32_t
         PLAN_CUDA(cudaMemcpyAsync(&tot_cold_z, zc_blk + P.n_blocks, 8, cudaMemcpyDeviceToHost, st));
         PLAN_CUDA(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, st));
         PLAN_CUDA(cudaStreamSynchronize(st));
-        if (herr) { fail(GDMIX_ERR_TOO_LARGE, "a row has more than 65535 non-zeros among (or outside) the %d most frequent features", hz); cleanup(false); return nullptr; }
+        if (herr) { fail(GDMIX_ERR_TOO_LARGE, "a row has more than 262140 non-zeros among (or 65535 outside) the %d most frequent features", hz); cleanup(false); return nullptr; }
     }
     float *zh_val, *zc_val; uint16_t *zh_col; int32_t *zc_col;
     PLAN_TRY(plan_alloc(h, &zh_val, (size_t)tot_hot_z + 8, true));

@@ -46,7 +46,9 @@ __global__ void __launch_bounds__(256) remap_i32_kernel(const int32_t *in, const
 //   z side (row-major, for z = X x):  every row's non-zeros split, order kept, into a HOT part (rank < hz: the
 //     coefficient sits in shared memory; fp32 value + 16-bit rank = 6 B) and a COLD part (value + 32-bit rank).
 //     Both parts are packed per block of 32 rows, each block padded to a multiple of 8 (hot) / 4 (cold) entries, so
-//     that a warp stages its block with 16-byte copies; zh_len[row] / zc_len[row] are the row's lengths.
+//     that a warp stages its block with 16-byte copies.  A row's hot part is padded with zero entries to whole QUADS
+//     (a lane fetches four values with one 16-byte and four ranks with one 8-byte shared-memory load):
+//     zh_len[row] = its quads, zc_len[row] = its cold entries.
 //   g side (column-major, for g = X^T dz):  non-zeros of rank < hg sorted by (tile of `tile_rows` rows, column, row)
 //     as fp32 value + 16-bit row inside the tile + 16-bit rank (8 B), each tile padded to a multiple of 256 entries
 //     with zeros that extend its last run; the rest sorted by (L2 tile of `l2_tile_rows` rows, column, row) as value +
@@ -74,22 +76,23 @@ __global__ void __launch_bounds__(256) fe_zcount_kernel(const int64_t *rowptr, c
         for (int64_t q = b; q < e; q++) {
             if (col[q] < hz) h++; else c++;
         }
-        if (h > 65535u || c > 65535u) { *err = 1; h = min(h, 65535u); c = min(c, 65535u); }
-        zh_len[i] = (uint16_t)h;
+        const uint32_t hq = (h + 3u) >> 2;        // the hot part is stored in quads (padded with zero entries)
+        if (hq > 65535u || c > 65535u) { *err = 1; c = min(c, 65535u); }
+        zh_len[i] = (uint16_t)min(hq, 65535u);
         zc_len[i] = (uint16_t)c;
     }
 }
 
-// entries of every 32-row block, rounded up to a multiple of `align` (a power of two)
+// entries of every 32-row block (len[row] * unit each), rounded up to a multiple of `align` (a power of two)
 __global__ void __launch_bounds__(256) fe_zblock_kernel(const uint16_t *len, const int64_t n_rows, const int64_t nblocks,
-                                                        const uint32_t align, uint32_t *blk_cnt)
+                                                        const uint32_t unit, const uint32_t align, uint32_t *blk_cnt)
 {
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
     for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nblocks; b += nth) {
         uint32_t s = 0;
         for (int k = 0; k < 32; k++) {
             const int64_t i = b * 32 + k;
-            if (i < n_rows) s += len[i];
+            if (i < n_rows) s += unit * (uint32_t)len[i];
         }
         blk_cnt[b] = (s + align - 1u) & ~(align - 1u);
     }
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(256) fe_zscatter_kernel(const int64_t *rowptr,
     const int64_t nblocks = (n_rows + 31) >> 5;
     for (int64_t blk = warp; blk < nblocks; blk += nwarps) {
         const int64_t i = blk * 32 + lane;
-        const uint32_t len = i < n_rows ? zh_len[i] : 0u, clen = i < n_rows ? zc_len[i] : 0u;
+        const uint32_t len = i < n_rows ? 4u * (uint32_t)zh_len[i] : 0u, clen = i < n_rows ? zc_len[i] : 0u;
         uint32_t incl = len, cincl = clen;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -125,6 +128,7 @@ __global__ void __launch_bounds__(256) fe_zscatter_kernel(const int64_t *rowptr,
                 if (cc < hz) { zh_val[h] = val[q]; zh_col[h] = (uint16_t)cc; h++; }
                 else { zc_val[c] = val[q]; zc_col[c] = cc; c++; }
             }
+            for (const int64_t hend = q0 + incl; h < hend; h++) { zh_val[h] = 0.0f; zh_col[h] = 0; }   // the row's last quad
         }
         if (total + lane < padded) { zh_val[q0 + total + lane] = 0.0f; zh_col[q0 + total + lane] = 0; }
         if (ctotal + lane < cpadded) { zc_val[cq0 + ctotal + lane] = 0.0f; zc_col[cq0 + ctotal + lane] = 0; }

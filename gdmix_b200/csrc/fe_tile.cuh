@@ -32,7 +32,7 @@ struct FeTilePlan {
     // z side
     int64_t n_blocks;
     const int64_t *zh_blk;      // [n_blocks + 1] first hot entry of the 32-row block (multiple of 8)
-    const uint16_t *zh_len;     // [n_rows]
+    const uint16_t *zh_len;     // [n_rows] hot QUADS of the row (entries / 4, zero-padded)
     const float *zh_val;
     const uint16_t *zh_col;
     const int64_t *zc_blk;      // [n_blocks + 1] first cold entry of the 32-row block (multiple of 4)
@@ -200,13 +200,13 @@ __global__ void __launch_bounds__(kFeZThreads, 1) fe_z_kernel(const gdmix_fe_row
         cp_async_commit();
         z_meta(mn, R, P, blk + nwarps, lane);      // the next block's row facts travel under this block's copy
         // this lane's first hot / cold entry inside the block
-        uint32_t incl = m.len, cincl = m.clen;
+        uint32_t incl = 4u * m.len, cincl = m.clen;      // hot lengths are in quads
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) {
             const uint32_t u = __shfl_up_sync(0xffffffffu, incl, s), cu = __shfl_up_sync(0xffffffffu, cincl, s);
             if (lane >= (uint32_t)s) { incl += u; cincl += cu; }
         }
-        const uint32_t s0 = incl - m.len, cs0 = cincl - m.clen, len = m.len, clen = m.clen;
+        const uint32_t nq = m.len, s0 = incl - 4u * nq, cs0 = cincl - m.clen, clen = m.clen;
         cp_async_wait_all();
         __syncwarp();
         // cold coefficients come through L2: the gathers are issued now and used after the hot walk
@@ -220,31 +220,36 @@ __global__ void __launch_bounds__(kFeZThreads, 1) fe_z_kernel(const gdmix_fe_row
                 xc[j] = on ? __ldg(x + ccol[cs0 + j]) : 0.0;
             }
         }
-        double z = 0.0;
-        // hot walk: the lane starts where its entries fall on bank `lane` (when its row reaches that far) and wraps
-        // around, so that lanes of rows of any length read different banks
-        uint32_t pos = (lane - s0) & 31u;
-        if (pos >= len) pos = 0u;
+        double z = 0.0, z1 = 0.0;
+        // hot walk, a quad per step: four values by one 16-byte load, four ranks by one 8-byte load, four gathers of x, two
+        // chains of fused multiply-adds.  The lane starts at the quad that falls on its own 16-byte bank group (when its
+        // row reaches that far) and wraps around, so that lanes of rows of any length read different banks.
+        uint32_t q = (lane - (s0 >> 2)) & 7u;
+        if (q >= nq) q = 0u;
         if (staged) {
-            // two chains of fused multiply-adds (even / odd steps of the walk), eight gathers in flight
-            double z1 = 0.0;
-            uint32_t s = 0;
-#pragma unroll 4
-            for (; s + 2 <= len; s += 2) {
-                const uint32_t p1 = (pos + 1u == len) ? 0u : pos + 1u;
-                z = fma((double)sval[s0 + pos], xs[scol[s0 + pos]], z);
-                z1 = fma((double)sval[s0 + p1], xs[scol[s0 + p1]], z1);
-                pos = (p1 + 1u == len) ? 0u : p1 + 1u;
+#pragma unroll 2
+            for (uint32_t s = 0; s < nq; s++) {
+                const float4 v = *(const float4 *)(sval + s0 + 4u * q);
+                const uint2 c = *(const uint2 *)(scol + s0 + 4u * q);
+                z = fma((double)v.x, xs[c.x & 0xffffu], z);
+                z1 = fma((double)v.y, xs[c.x >> 16], z1);
+                z = fma((double)v.z, xs[c.y & 0xffffu], z);
+                z1 = fma((double)v.w, xs[c.y >> 16], z1);
+                q = (q + 1u == nq) ? 0u : q + 1u;
             }
-            if (s < len) z = fma((double)sval[s0 + pos], xs[scol[s0 + pos]], z);
-            z += z1;
         } else {
             // a block with more hot entries than the stage holds (very long rows): straight from global memory, same order
-            for (uint32_t s = 0; s < len; s++) {
-                z = fma((double)P.zh_val[m.q0 + s0 + pos], xs[P.zh_col[m.q0 + s0 + pos]], z);
-                pos = (pos + 1u == len) ? 0u : pos + 1u;
+            for (uint32_t s = 0; s < nq; s++) {
+                const float4 v = *(const float4 *)(P.zh_val + m.q0 + s0 + 4u * q);
+                const uint2 c = *(const uint2 *)(P.zh_col + m.q0 + s0 + 4u * q);
+                z = fma((double)v.x, xs[c.x & 0xffffu], z);
+                z1 = fma((double)v.y, xs[c.x >> 16], z1);
+                z = fma((double)v.z, xs[c.y & 0xffffu], z);
+                z1 = fma((double)v.w, xs[c.y >> 16], z1);
+                q = (q + 1u == nq) ? 0u : q + 1u;
             }
         }
+        z += z1;
         if (cstaged) {
 #pragma unroll
             for (int j = 0; j < kFeZColdRegs; j++) z = fma((double)vc[j], xc[j], z);

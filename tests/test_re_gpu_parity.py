@@ -204,6 +204,20 @@ def test_scoring_matches_oracle():
         np.testing.assert_allclose(per[r0:r1], po.astype(np.float32), rtol=1e-6, atol=1e-7)
 
 
+def test_scoring_in_chunks_is_the_same(monkeypatch):
+    """gdmix_re_score_host cuts the partition into bounded chunks of entities: any chunking gives the same bits."""
+    hb = make_batch(300, 24, 48, 6, seed=21)
+    opts = capi.make_opts()
+    fit = capi.re_fit_host(hb, opts)
+    has_model = (np.arange(300) % 7 != 0).astype(np.uint8)
+    whole = capi.re_score_host(hb, opts, fit["theta"], has_model)
+    for budget in ("1", "20000", "150000"):     # one entity per chunk, a few entities, a few chunks
+        monkeypatch.setenv("GDMIX_SCORE_CHUNK_BYTES", budget)
+        part = capi.re_score_host(hb, opts, fit["theta"], has_model)
+        np.testing.assert_array_equal(part[0], whole[0])
+        np.testing.assert_array_equal(part[1], whole[1])
+
+
 def test_bad_column_index_is_rejected():
     hb = make_batch(8, 16, 24, 4, seed=1)
     hb.col[5] = 9999
