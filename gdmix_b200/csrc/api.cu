@@ -1247,6 +1247,19 @@ int gdmix_re_score_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const 
     return GDMIX_OK;
 }
 
+#ifdef GDMIX_FAST_TIMING
+GDMIX_API int gdmix_debug_fast_cycles(unsigned long long *out, int reset)
+{
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(out, gdmix::g_fast_cycles, 12 * sizeof(unsigned long long)));
+    if (reset) {
+        unsigned long long z[12] = {0};
+        CUDA_TRY(cudaMemcpyToSymbol(gdmix::g_fast_cycles, z, sizeof(z)));
+    }
+    return GDMIX_OK;
+}
+#endif
+
 // ---- partitioner / evaluator entry points (partition.cuh) ------------------------------------------------
 namespace {
 inline size_t up256z(size_t x) { return (x + 255) & ~(size_t)255; }

@@ -37,6 +37,15 @@ constexpr uint32_t kFastMaxRows = 8191;           // u16 byte offsets into fp64 
 constexpr uint32_t kFastPartK = 24;
 
 using DNF = Dense<kFastMT>;
+
+#ifdef GDMIX_FAST_TIMING
+// kernel experiments only: cycles of thread 0 per phase, summed over entities
+// [0] pop+stage [1] B1->B2 rows [2] B2->B3 cols [3] B3->B4 dots [4] B4->mxm [5] mxm [6] mxm->B5 [7] B5->B1 dir [8] rest [9] iterations
+__device__ unsigned long long g_fast_cycles[12];
+#define FT_MARK(k) do { if (tid == 0) { const long long t_ = clock64(); ft_acc[k] += t_ - ft_acc[11]; ft_acc[11] = t_; } } while (0)
+#else
+#define FT_MARK(k) do { } while (0)
+#endif
 constexpr uint32_t kFastDense = DNF::count + 2;   // + direction / trial value of the intercept
 
 // Byte offsets of one CTA's dynamic shared memory.  N = max rows, D = max local features of the batch.
@@ -232,6 +241,117 @@ __device__ __forceinline__ double lds_f64(const uint32_t shared_addr)
     double v;
     asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(shared_addr));
     return v;
+}
+
+// Shared-state-space accessors for the serial stretch below: one 32-bit base register and immediate offsets instead
+// of a generic pointer whose window base the compiler re-derives (S2UR SR_CgaCtaId ...) in every basic block.
+__device__ __forceinline__ double lds_f64v(const uint32_t a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 lds_v2f64v(const uint32_t a)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64v(const uint32_t a, const double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+// 1 / a as the compiler's own division forms it in the normal range (seed + three fused steps), without its slow
+// path inline: out of range (never on this path in practice) the library division is called instead.
+__device__ __forceinline__ double rcp_f64(const double a)
+{
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    double e = fma(-a, x, 1.0);
+    e = fma(e, e, e);
+    x = fma(x, e, x);
+    e = fma(-a, x, 1.0);
+    x = fma(x, e, x);
+    if (!(fabs(a) > 1e-290 && fabs(a) < 1e290)) x = 1.0 / a;
+    return x;
+}
+
+// lbfgs_small_update (re_lbfgs.cuh: same algebra, same order of every sum) for MT = kFastMT as warp 0 of the fast
+// kernel runs it.  The stretch is serial -- the other warps of the CTA wait at B5 -- and one warp alone is bound by
+// instruction count x latency, so it is written for instruction count: totals arrive in registers (lane l < 2 MT + 2
+// holds entry l of [S^T g | Y^T g | y.y | y.g]) and move by shuffles, lanes >= MT are clones of lane MT - 1 (they
+// compute and store the same values: no `lane < MT` branches), rows are read with 16-byte loads.
+// D = shared address of dense[0].
+__device__ __forceinline__ void fast_small_update(const Lbfgs &L, const bool update, const int newslot,
+                                                  const uint32_t dotmask, const double stp, const double dr,
+                                                  const double gd_new, const double t, const uint32_t D)
+{
+    constexpr int MT = kFastMT;
+    using DN = Dense<MT>;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t i = lane < (uint32_t)MT ? lane : (uint32_t)MT - 1u;
+    double p1i = __shfl_sync(kFull, t, i), p2i = __shfl_sync(kFull, t, MT + i);
+    const double yyt = __shfl_sync(kFull, t, 2 * MT), ygt = __shfl_sync(kFull, t, 2 * MT + 1);
+    const bool old_i = (dotmask >> i) & 1u;
+    const bool new_i = update && (int)i == newslot;
+    const uint32_t valid = update ? (L.valid | (1u << newslot)) : L.valid;
+    const bool val_i = (valid >> i) & 1u;
+    const uint32_t rinv_i = D + 8u * (DN::rinv + i * MT), yy_i = D + 8u * (DN::yy + i * MT), vec_i = D + 8u * i;
+    const double inv_dr = update ? rcp_f64(dr) : 0.0;
+    const double theta = update ? yyt * inv_dr : L.theta;
+    const double gamma = rcp_f64(theta);
+    p1i = old_i ? p1i : 0.0;
+    p2i = old_i ? p2i : 0.0;
+    const double rc = (update && old_i) ? p1i - lds_f64v(vec_i + 8u * DN::p1old) : 0.0;   // s_i . y_new
+    const double yc = (update && old_i) ? p2i - lds_f64v(vec_i + 8u * DN::p2old) : 0.0;   // y_i . y_new
+    const double p1new = stp * gd_new;                                                   // s_new . g_new
+    if (new_i) { p1i = p1new; p2i = ygt; }
+    sts_f64v(vec_i + 8u * DN::ta, rc);
+    sts_f64v(vec_i + 8u * DN::tb, (val_i && !new_i) ? p1i : 0.0);
+    sts_f64v(vec_i + 8u * DN::p1old, p1i);
+    sts_f64v(vec_i + 8u * DN::p2old, p2i);
+    __syncwarp();
+    double acc = 0.0, wvp = 0.0;
+#pragma unroll
+    for (int j = 0; j < MT; j += 2) {
+        const double2 r = lds_v2f64v(rinv_i + 8u * j);
+        const double2 a2 = lds_v2f64v(D + 8u * (DN::ta + j)), b2 = lds_v2f64v(D + 8u * (DN::tb + j));
+        acc = fma(r.x, a2.x, acc); wvp = fma(r.x, b2.x, wvp);
+        acc = fma(r.y, a2.y, acc); wvp = fma(r.y, b2.y, wvp);
+    }
+    double wv = val_i ? wvp : 0.0;
+    __syncwarp();                                     // every lane is done reading the old R^-1
+    if (update) {
+        const double cnew = old_i ? -acc * inv_dr : 0.0;          // new column of R^-1 (old rows)
+        wv = new_i ? inv_dr * p1new : (old_i ? fma(cnew, p1new, wvp) : 0.0);
+        const uint32_t col_new = 8u * (uint32_t)newslot, row_new = 8u * MT * (uint32_t)newslot + 8u * i;
+        sts_f64v(rinv_i + col_new, new_i ? inv_dr : cnew);
+        sts_f64v(D + 8u * DN::rinv + row_new, new_i ? inv_dr : 0.0);
+        sts_f64v(yy_i + col_new, new_i ? yyt : yc);
+        sts_f64v(D + 8u * DN::yy + row_new, new_i ? yyt : yc);
+        if (new_i) sts_f64v(vec_i + 8u * DN::d, dr);
+    }
+    sts_f64v(vec_i + 8u * DN::cw, wv);
+    __syncwarp();
+    double yw = 0.0;
+#pragma unroll
+    for (int j = 0; j < MT; j += 2) {
+        const double2 y2 = lds_v2f64v(yy_i + 8u * j), c2 = lds_v2f64v(D + 8u * (DN::cw + j));
+        yw = fma(y2.x, c2.x, yw);
+        yw = fma(y2.y, c2.y, yw);
+    }
+    const double tv = val_i ? fma(lds_f64v(vec_i + 8u * DN::d), wv, gamma * (yw - p2i)) : 0.0;
+    sts_f64v(vec_i + 8u * DN::ta, tv);
+    __syncwarp();
+    double uv = 0.0;
+#pragma unroll
+    for (int j = 0; j < MT; j += 2) {
+        const double2 a2 = lds_v2f64v(D + 8u * (DN::ta + j));
+        uv = fma(lds_f64v(D + 8u * (DN::rinv + j * MT) + 8u * i), a2.x, uv);
+        uv = fma(lds_f64v(D + 8u * (DN::rinv + (j + 1) * MT) + 8u * i), a2.y, uv);
+    }
+    sts_f64v(vec_i + 8u * DN::cu, uv);
+    if (lane == 0) { sts_f64v(D + 8u * (DN::tot + 2 * MT), theta); sts_f64v(D + 8u * (DN::tot + 2 * MT + 1), gamma); }
 }
 
 // One lane's share of a slab: sum over `nsteps` quads of val * vec[...].  pv / pi point at this lane's quad of
@@ -505,9 +625,14 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
     const FastLayout &L = fa.L;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int flip = 0;
+#ifdef GDMIX_FAST_TIMING
+    __shared__ long long ft_acc[12];     // in shared memory: the kernel has no registers to spare
+    if (tid == 0) { for (int k = 0; k < 11; k++) ft_acc[k] = 0; ft_acc[11] = clock64(); }
+#endif
 
     for (;;) {
         group_sync<G>();  // previous entity fully emitted before its memory is reused
+        FT_MARK(8);
         if (tid == 0) {
             // plain launch: entities 0 .. n_entities; second tier: the list the typical-shape launch deferred
             int idx = atomicAdd(a.queue, 1);
@@ -543,6 +668,7 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
             if (tid == 0) fa.defer_list[atomicAdd(fa.defer_count, 1)] = (int32_t)e;
             continue;
         }
+        FT_MARK(0);
         double *dense = (double *)(smem + L.dense);
         double *part = (double *)(smem + L.part);
         if (W == 1) prefetch_entity_l2(a.b, (int64_t)e + gridDim.x, lane);
@@ -610,6 +736,7 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
 
         for (;;) {
             group_sync<G>();                                                    // ---- B1
+            FT_MARK(7);
             if (gd_pending) {
                 double t = wred[0];
 #pragma unroll
@@ -657,6 +784,7 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
                         }
                     }
                     group_sum<G, 3>(p3, red, flip);                             // ---- B2 (publishes r[])
+                    FT_MARK(1);
                     if (G == 32) __syncwarp();
                     ft = (p3[0] + 0.5 * l2 * p3[2]) * inv_n;
                     gn0 = E.hi ? (p3[1] + (a.o.regularize_bias ? l2 * xt0 : 0.0)) * inv_n : 0.0;
@@ -676,6 +804,7 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
                     }
                 }
                 group_sync<G>();                                                // ---- B3 (publishes g_new)
+                FT_MARK(2);
                 // own slots of g_new; speculative inner products with the stored pairs (12 at a time)
                 double gm = fabs(gn0);
 #pragma unroll
@@ -725,6 +854,7 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
                 for (int o = 16; o > 0; o >>= 1) gm = fmax(gm, __shfl_xor_sync(kFull, gm, o));
                 if (lane == 0) wred[kMaxWarps + warp] = gm;
                 group_sync<G>();                                                // ---- B4
+                FT_MARK(3);
                 gdt = part[2 * MT + 2];
                 gmt = wred[kMaxWarps];
 #pragma unroll
@@ -813,35 +943,39 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
                             }
                         }
                     }
+                    FT_MARK(4);
                     if (warp == 0) {
-                        double *tot = dense + DNF::tot;
                         const double y0 = gn0 - g0;
+                        // part row: [S^T g (10) | y.y | y.g | Y^T g (10) | g.d | -]; lane l < 2 MT + 2 takes entry l of
+                        // [S^T g | Y^T g | y.y | y.g], summed over the warps, plus the intercept's share
+                        double t = 0.0;
                         if (lane < 2 * MT + 2) {
-                            // part row: [S^T g (10) | y.y | y.g | Y^T g (10) | g.d | -]  ->  tot: [S^T g | Y^T g | y.y | y.g]
                             const uint32_t src = (lane < (uint32_t)MT) ? lane : (lane < 2u * MT) ? lane + 2u : lane - MT;
-                            double t = part[src];
+                            t = part[src];
 #pragma unroll
                             for (uint32_t w2 = 1; w2 < W; w2++) t += part[w2 * kFastPartK + src];
                             if (E.hi) {
-                                // the intercept's share: icept[] = [S0 (m) | Y0 (m)], same order as tot[]
+                                // icept[] = [S0 (m) | Y0 (m)], same order as the totals
                                 if (lane < 2u * MT) t = fma(icept[lane], gn0, t);
                                 else if (lane == 2u * MT) t = fma(y0, y0, t);
                                 else t = fma(y0, gn0, t);
                             }
-                            tot[lane] = t;
                         }
-                        __syncwarp();
-                        double uv, wv, theta_n, gamma;
-                        lbfgs_small_update<MT>(lb, update, newslot, dotmask, stp, dr, gd, dense, uv, wv, theta_n, gamma);
+                        fast_small_update(lb, update, newslot, dotmask, stp, dr, gd, t,
+                                          (uint32_t)__cvta_generic_to_shared(dense));
                         // the intercept's components of the new pair (its direction component is formed by every
                         // thread for itself in H2 below: that keeps it off this serial stretch)
                         if (update && (int)lane == newslot) { icept[lane] = stp * d0; icept[MT + lane] = y0; }
-                        (void)uv; (void)wv; (void)theta_n; (void)gamma;
+                        FT_MARK(5);
+#ifdef GDMIX_FAST_TIMING
+                        if (tid == 0) ft_acc[9] += 1;
+#endif
                     } else if (warp == 1 && iter == 1) {
                         // idle while warp 0 works: pull the entity a grid-width ahead in the queue towards L2
                         prefetch_entity_l2(a.b, (int64_t)e + gridDim.x, lane);
                     }
                     group_sync<G>();                                            // ---- B5
+                    FT_MARK(6);
                     lb.theta = dense[DNF::tot + 2 * MT];   // warp 0 left theta and gamma = 1 / theta there
                     if (update) {
                         lb.valid |= (1u << newslot);
@@ -969,6 +1103,10 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
         }
         }   // models of the sweep
     }
+#ifdef GDMIX_FAST_TIMING
+    if (tid == 0)
+        for (int k = 0; k < 11; k++) atomicAdd(&g_fast_cycles[k], (unsigned long long)ft_acc[k]);
+#endif
 }
 
 }  // namespace gdmix
