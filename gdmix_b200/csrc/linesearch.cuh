@@ -12,7 +12,15 @@ struct LineSearch {
 };
 enum { LS_START = 0, LS_FG = 1, LS_CONV = 2, LS_WARN = 3, LS_ERROR = 4 };
 
-__device__ __forceinline__ double max3(double a, double b, double c) { return fmax(fmax(a, b), c); }
+// max of two doubles that are >= 0 (callers pass |x| or constants): their bit patterns order like the numbers, and a
+// 64-bit integer max is 4 instructions where fmax(double, double) is ~10 (its NaN rules); |NaN| is the largest pattern
+// and propagates, as np.max(np.abs(g)) does in the reference's stop test.
+__device__ __forceinline__ double pos_max(const double a, const double b)
+{
+    const long long ia = __double_as_longlong(a), ib = __double_as_longlong(b);
+    return __longlong_as_double(ia > ib ? ia : ib);
+}
+__device__ __forceinline__ double max3(double a, double b, double c) { return pos_max(pos_max(a, b), c); }   // a, b, c >= 0
 
 __device__ inline void dcstep(double &stx, double &fx, double &dx, double &sty, double &fy, double &dy, double &stp,
                               double fp, double dp, int &brackt, double stpmin, double stpmax)

@@ -361,31 +361,37 @@ __device__ __forceinline__ void fast_small_update(const Lbfgs &L, const bool upd
 __device__ __forceinline__ double sell_dot(const float4 *pv, const uint2 *pi, const uint32_t nsteps)
 {
     // Software pipelined: the value / address quads of step k+1 are in flight while step k's four gathers and
-    // FMAs run (index load -> gather -> FMA is a chain of two shared-memory round trips otherwise).
+    // FMAs run (index load -> gather -> FMA is a chain of two shared-memory round trips otherwise); two steps per
+    // trip with the two register sets alternating, so nothing is copied from "next" to "current".
     // Accumulation order per chain: steps ascending, as the data is laid out.
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     if (nsteps == 0) return 0.0;
-    float4 va = pv[0];
-    uint2 ca = pi[0];
-#pragma unroll 2
-    for (uint32_t k = 1; k < nsteps; k++) {
-        const float4 vn = pv[k * kStepQuads];
-        const uint2 cn = pi[k * kStepQuads];
-        const double x0 = lds_f64(ca.x & 0xffffu), x1 = lds_f64(ca.x >> 16);
-        const double x2 = lds_f64(ca.y & 0xffffu), x3 = lds_f64(ca.y >> 16);
-        s0 = fma((double)va.x, x0, s0);
-        s1 = fma((double)va.y, x1, s1);
-        s2 = fma((double)va.z, x2, s2);
-        s3 = fma((double)va.w, x3, s3);
-        va = vn; ca = cn;
+    auto step = [&](const float4 &v, const uint2 &c) {
+        const double x0 = lds_f64(c.x & 0xffffu), x1 = lds_f64(c.x >> 16);
+        const double x2 = lds_f64(c.y & 0xffffu), x3 = lds_f64(c.y >> 16);
+        s0 = fma((double)v.x, x0, s0);
+        s1 = fma((double)v.y, x1, s1);
+        s2 = fma((double)v.z, x2, s2);
+        s3 = fma((double)v.w, x3, s3);
+    };
+    float4 va = pv[0], vb;
+    uint2 ca = pi[0], cb;
+    uint32_t k = 1;
+    for (; k + 1 < nsteps; k += 2) {
+        vb = pv[k * kStepQuads];
+        cb = pi[k * kStepQuads];
+        step(va, ca);
+        va = pv[(k + 1) * kStepQuads];
+        ca = pi[(k + 1) * kStepQuads];
+        step(vb, cb);
     }
-    {
-        const double x0 = lds_f64(ca.x & 0xffffu), x1 = lds_f64(ca.x >> 16);
-        const double x2 = lds_f64(ca.y & 0xffffu), x3 = lds_f64(ca.y >> 16);
-        s0 = fma((double)va.x, x0, s0);
-        s1 = fma((double)va.y, x1, s1);
-        s2 = fma((double)va.z, x2, s2);
-        s3 = fma((double)va.w, x3, s3);
+    if (k < nsteps) {
+        vb = pv[k * kStepQuads];
+        cb = pi[k * kStepQuads];
+        step(va, ca);
+        step(vb, cb);
+    } else {
+        step(va, ca);
     }
     return (s0 + s1) + (s2 + s3);
 }
@@ -811,7 +817,7 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
                 for (int k = 0; k < EPT; k++) {
                     const uint32_t c = tid + (uint32_t)k * G;
                     gn[k] = (c < E.d) ? ((const double *)(smem + L.gnew))[c] : 0.0;
-                    gm = fmax(gm, fabs(gn[k]));
+                    gm = pos_max(gm, fabs(gn[k]));
                 }
                 {
                     double v[12];
@@ -851,7 +857,7 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
                     }
                 }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) gm = fmax(gm, __shfl_xor_sync(kFull, gm, o));
+                for (int o = 16; o > 0; o >>= 1) gm = pos_max(gm, __shfl_xor_sync(kFull, gm, o));
                 if (lane == 0) wred[kMaxWarps + warp] = gm;
                 group_sync<G>();                                                // ---- B4
                 FT_MARK(3);
@@ -860,7 +866,7 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
 #pragma unroll
                 for (uint32_t w2 = 1; w2 < W; w2++) {
                     gdt += part[w2 * kFastPartK + 2 * MT + 2];
-                    gmt = fmax(gmt, wred[kMaxWarps + w2]);
+                    gmt = pos_max(gmt, wred[kMaxWarps + w2]);
                 }
                 nfev++;
                 // ================= what the evaluation was for ===========================================
@@ -932,15 +938,24 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
                     if (update) { newslot = (lb.col < m) ? lb.head + lb.col : lb.head; if (newslot >= m) newslot -= m; }   // head, col < m
                     const uint32_t dotmask = update ? (lb.valid & ~(1u << newslot)) : lb.valid;
                     // the new pair takes its slot: s = stp d, y = g_new - g_old
-                    if (update) {
+                    // (newslot = -1 without an update: no slot matches.  Predicated moves IN PLACE: written as
+                    //  `if (s == newslot) Sh[s][k] = sj` the compiler kept two copies of the history registers and
+                    //  moved one onto the other twice per iteration -- 190 instructions for these 4 EPT stores.)
+                    {
+                        double sj[EPT], yj[EPT];
 #pragma unroll
                         for (int k = 0; k < EPT; k++) {
                             const uint32_t c = tid + (uint32_t)k * G;
-                            const double sj = stp * dd[k], yj = gn[k] - ((c < E.d) ? gold[c] : 0.0);
+                            sj[k] = stp * dd[k];
+                            yj[k] = gn[k] - ((c < E.d) ? gold[c] : 0.0);
+                        }
 #pragma unroll
-                            for (int s = 0; s < MT; s++) {
-                                if (s == newslot) { Sh[s][k] = sj; Yh[s][k] = yj; }
-                            }
+                        for (int s = 0; s < MT; s++) {
+#pragma unroll
+                            for (int k = 0; k < EPT; k++)
+                                asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %4, %5;\n\t@p mov.f64 %0, %2;\n\t@p mov.f64 %1, %3;\n\t}"
+                                    : "+d"(Sh[s][k]), "+d"(Yh[s][k])
+                                    : "d"(sj[k]), "d"(yj[k]), "r"(newslot), "r"(s));
                         }
                     }
                     FT_MARK(4);
