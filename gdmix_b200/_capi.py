@@ -37,7 +37,8 @@ SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_w
            "gdmix_feature_map_create", "gdmix_feature_map_destroy", "gdmix_avro_model_decode",
            "gdmix_fe_lbfgs_create", "gdmix_fe_lbfgs_reset", "gdmix_fe_lbfgs_step", "gdmix_fe_lbfgs_poll",
            "gdmix_fe_lbfgs_destroy", "gdmix_fe_column_counts", "gdmix_remap_i32", "gdmix_group_ids", "gdmix_offset_join", "gdmix_seqex_encode", "gdmix_local_index_host", "gdmix_fe_tile_plan_create",
-           "gdmix_fe_tile_plan_destroy", "gdmix_fe_tile_plan_info", "gdmix_fe_loss_grad_tiled"]
+           "gdmix_fe_tile_plan_destroy", "gdmix_fe_tile_plan_info", "gdmix_fe_loss_grad_tiled",
+           "gdmix_pinned_alloc", "gdmix_pinned_free", "gdmix_narrow_columns"]
 
 
 class SeqexSpec(C.Structure):
@@ -46,7 +47,7 @@ class SeqexSpec(C.Structure):
 
 class SeqexSizes(C.Structure):
     _fields_ = [("n_entities", C.c_int64), ("n_rows", C.c_int64), ("nnz", C.c_int64), ("id_bytes", C.c_int64),
-                ("all_labelled", C.c_int32), ("saw_weight", C.c_int32)]
+                ("all_labelled", C.c_int32), ("saw_weight", C.c_int32), ("min_index", C.c_int64), ("max_index", C.c_int64)]
 
 
 class ModelTable(C.Structure):
@@ -184,6 +185,7 @@ class HostBatch:
         self.label = np.ascontiguousarray(label, dtype=np.float32)
         self.weight = None if weight is None else np.ascontiguousarray(weight, dtype=np.float32)
         self.offset = None if offset is None else np.ascontiguousarray(offset, dtype=np.float32)
+        self.has_intercept = bool(has_intercept)
         self.n_entities = len(self.ent_rowptr) - 1
         self.n_rows = int(self.ent_rowptr[-1]) if self.n_entities >= 0 else 0
         self.nnz = int(self.rowptr[self.n_rows])
@@ -207,7 +209,14 @@ class HostBatch:
         if narrow:
             if getattr(self, "_col_narrow", None) is None:
                 # one byte per index when every entity has at most 256 local features, else two
-                self._col_narrow = self.col.astype(np.uint8 if int(self.col.max()) < 256 else np.uint16)
+                # (an entity's local indices are < its coefficient count minus the intercept)
+                width = 1 if self.max_coef - (1 if self.has_intercept else 0) <= 256 else 2
+                try:
+                    self._col_narrow = narrow_columns(self.col[:self.nnz], width)
+                except GdmixError:
+                    if width == 2:
+                        raise
+                    self._col_narrow = narrow_columns(self.col[:self.nnz], 2)
             c8 = self._col_narrow if self._col_narrow.dtype == np.uint8 else None
             c16 = self._col_narrow if c8 is None else None
         return ReBatch(self.n_entities, self.n_rows, self.nnz, _np_ptr(self.ent_rowptr), _np_ptr(self.rowptr),
@@ -224,12 +233,14 @@ class HostBatch:
 def re_fit_host(batch, opts, theta0=None, want_variance=False, chunk_entities=0):
     """gdmix_re_fit_host: numpy in, numpy out (theta, f, nit, nfev, status[, variance])."""
     E, T = batch.n_entities, batch.n_coef
-    theta = np.zeros(T, np.float64)
+    theta = pinned_empty(T, np.float64); theta.fill(0.0)      # D2H targets: page-locked, from the library's pool
     f = np.zeros(E, np.float64)
     nit = np.zeros(E, np.int32)
     nfev = np.zeros(E, np.int32)
     status = np.zeros(E, np.int32)
-    var = np.zeros(T, np.float64) if want_variance else None
+    var = None
+    if want_variance:
+        var = pinned_empty(T, np.float64); var.fill(0.0)
     t0 = None if theta0 is None else np.ascontiguousarray(theta0, dtype=np.float64)
     cb = batch.c_struct()
     check(lib.gdmix_re_fit_host(C.byref(cb), C.byref(opts), _np_ptr(t0), _np_ptr(theta), _np_ptr(f), _np_ptr(nit),
@@ -241,8 +252,8 @@ def re_fit_host(batch, opts, theta0=None, want_variance=False, chunk_entities=0)
 
 
 def re_score_host(batch, opts, theta, has_model=None):
-    logit = np.zeros(batch.n_rows, np.float32)
-    per = np.zeros(batch.n_rows, np.float32)
+    logit = pinned_empty(batch.n_rows, np.float32); logit.fill(0.0)
+    per = pinned_empty(batch.n_rows, np.float32); per.fill(0.0)
     th = None if theta is None else np.ascontiguousarray(theta, dtype=np.float64)
     hm = None if has_model is None else np.ascontiguousarray(has_model, dtype=np.uint8)
     cb = batch.c_struct()
@@ -597,6 +608,90 @@ def parse_entity_grouped(file_image, entity, uid, label, offset, weight, bag_ind
     return out
 
 
+class _PinnedPool:
+    """Page-locked host blocks (gdmix_pinned_alloc), kept for reuse: a worker trains partition after partition and
+    pinning a few GB costs about as long as copying them.  A block returns here when the last numpy view of it dies."""
+
+    def __init__(self):
+        import threading
+        self.lock = threading.Lock()
+        self.free = []          # (capacity, pointer)
+        self.available = None   # None: not tried yet; False: no CUDA device (host-only use of the readers)
+        self.limit = int(os.environ.get("GDMIX_PINNED_POOL_MB", "24576")) << 20
+
+    def take(self, nbytes):
+        """-> (pointer, capacity) or None when page-locked memory cannot be had."""
+        if self.available is False:
+            return None
+        with self.lock:
+            best = None
+            for k, (cap, _) in enumerate(self.free):
+                if nbytes <= cap <= 2 * nbytes + (1 << 20) and (best is None or cap < self.free[best][0]):
+                    best = k
+            if best is not None:
+                cap, ptr = self.free.pop(best)
+                return ptr, cap
+        cap = (max(int(nbytes), 1) + (1 << 21) - 1) & ~((1 << 21) - 1)
+        out = C.c_void_p()
+        rc = lib.gdmix_pinned_alloc(C.c_size_t(cap), C.byref(out))
+        if rc != 0 or not out.value:
+            if self.available is None:
+                self.available = False
+            return None
+        self.available = True
+        return out.value, cap
+
+    def give(self, ptr, cap):
+        with self.lock:
+            self.free.append((cap, ptr))
+            total = sum(c for c, _ in self.free)
+            while total > self.limit and self.free:
+                c, p = self.free.pop(0)
+                lib.gdmix_pinned_free(C.c_void_p(p))
+                total -= c
+
+    def release(self):
+        with self.lock:
+            for _, p in self.free:
+                lib.gdmix_pinned_free(C.c_void_p(p))
+            self.free = []
+
+
+_pinned_pool = _PinnedPool()
+
+
+class _PinnedBlock:
+    """Owner of one pool block behind a numpy array (array.base): gives the block back when collected."""
+
+    def __init__(self, ptr, cap, n, dtype):
+        self.ptr, self.cap = ptr, cap
+        self.__array_interface__ = {"data": (ptr, False), "shape": (int(n),), "typestr": np.dtype(dtype).str, "version": 3}
+
+    def __del__(self):
+        try:
+            _pinned_pool.give(self.ptr, self.cap)
+        except Exception:      # interpreter shutdown
+            pass
+
+
+def pinned_empty(n, dtype):
+    """np.empty(n, dtype) in page-locked memory of the library's pool (plain np.empty when there is no CUDA device:
+    the readers are host code and are used without one)."""
+    dtype = np.dtype(dtype)
+    got = _pinned_pool.take(int(n) * dtype.itemsize)
+    if got is None:
+        return np.empty(int(n), dtype)
+    return np.asarray(_PinnedBlock(got[0], got[1], n, dtype))
+
+
+def narrow_columns(col, width):
+    """int32 local column indices -> uint8 (width 1) / uint16 (width 2) in pinned memory, all host threads."""
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    out = pinned_empty(col.shape[0], np.uint8 if width == 1 else np.uint16)
+    check(lib.gdmix_narrow_columns(_np_ptr(col), C.c_int64(col.shape[0]), C.c_int32(width), _np_ptr(out)))
+    return out
+
+
 def local_index_host(ent_rowptr, rowptr, gcol):
     """np.unique per entity over a parsed partition (gdmix_local_index_host, all host threads).
     -> (local int32[nnz], d_e int64[E], uniq_ptr int64[E+1], uniq_global int64[sum d_e])"""
@@ -701,7 +796,8 @@ def parse_per_record(file_image, uid, label, offset, weight, bag_indices, bag_va
 
 
 def avro_score_blocks(uid, score, label, weight, per_coordinate, sync, records_per_block=1024):
-    """-> bytes: the blocks of an Avro container holding these score records (gdmix_avro_score_blocks)."""
+    """-> the blocks of an Avro container holding these score records (gdmix_avro_score_blocks), as a bytes-like
+    memoryview."""
     f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
     uid = np.ascontiguousarray(uid, dtype=np.int64)
     score, label, weight, per_coordinate = f32(score), f32(label), f32(weight), f32(per_coordinate)
@@ -714,7 +810,7 @@ def avro_score_blocks(uid, score, label, weight, per_coordinate, sync, records_p
     check(lib.gdmix_avro_score_blocks(_np_ptr(uid), _np_ptr(score), _np_ptr(label), _np_ptr(weight),
                                       _np_ptr(per_coordinate), C.c_int64(n), C.c_int32(records_per_block),
                                       _np_ptr(sync_arr), _np_ptr(out), C.c_int64(out.size), C.byref(written)))
-    return out[:written.value].tobytes()
+    return memoryview(out)[:written.value]      # no copy: the caller writes it to the file
 
 
 def _string_table(strings):
@@ -776,7 +872,7 @@ def avro_model_blocks(model_ids, coef, var, coef_ptr, feat_idx, has_intercept, t
     written = C.c_int64()
     check(lib.gdmix_avro_model_blocks(C.byref(t), C.c_int32(records_per_block), _np_ptr(sync_arr), _np_ptr(out),
                                       C.c_int64(out.size), C.byref(written)))
-    return out[:written.value].tobytes()
+    return memoryview(out)[:written.value]      # no copy: the caller writes it to the file
 
 
 class FeatureMap:

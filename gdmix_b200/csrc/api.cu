@@ -1169,6 +1169,38 @@ int gdmix_host_unregister(void *ptr)
     return GDMIX_OK;
 }
 
+int gdmix_pinned_alloc(size_t bytes, void **out)
+{
+    if (!out || !bytes) return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_pinned_alloc");
+    *out = nullptr;
+    CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return GDMIX_OK;
+}
+
+int gdmix_pinned_free(void *ptr)
+{
+    if (!ptr) return GDMIX_OK;
+    CUDA_TRY(cudaFreeHost(ptr));
+    return GDMIX_OK;
+}
+
+int gdmix_narrow_columns(const int32_t *col, int64_t n, int32_t width, void *out)
+{
+    if (n < 0 || (n > 0 && (!col || !out)) || (width != 1 && width != 2)) return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_narrow_columns");
+    int bad = 0;
+    if (width == 1) {
+        uint8_t *o8 = (uint8_t *)out;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+        for (int64_t i = 0; i < n; i++) { bad |= (col[i] < 0 || col[i] > 255); o8[i] = (uint8_t)col[i]; }
+    } else {
+        uint16_t *o16 = (uint16_t *)out;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+        for (int64_t i = 0; i < n; i++) { bad |= (col[i] < 0 || col[i] > 65535); o16[i] = (uint16_t)col[i]; }
+    }
+    if (bad) return fail(GDMIX_ERR_INVALID, "column index does not fit %d byte(s)", (int)width);
+    return GDMIX_OK;
+}
+
 int gdmix_re_score_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const double *theta,
                         const uint8_t *has_model, float *logit, float *logit_pc)
 {
@@ -1177,7 +1209,9 @@ int gdmix_re_score_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const 
     if (E <= 0) return GDMIX_OK;
     std::lock_guard<std::mutex> lk(g_host.mu);
     const int64_t nr_all = hb->ent_rowptr[E], nz_all = hb->rowptr[nr_all];
-    if (nz_all > 0 && (!hb->col || !hb->val)) return fail(GDMIX_ERR_INVALID, "gdmix_re_score_host needs the int32 col and val");
+    if (nz_all > 0 && ((!hb->col && !hb->col16 && !hb->col8) || !hb->val))
+        return fail(GDMIX_ERR_INVALID, "gdmix_re_score_host needs col, col16 or col8, and val");
+    const int narrow = hb->col8 ? 1 : hb->col16 ? 2 : 0;     // as gdmix_re_fit_host: narrow indices cross PCIe, widened here
     // Chunks of about 512 MB of input, alternating between two slots (the upload of a chunk runs under the scoring and
     // the download of the one before): a partition that trained in chunks scores in chunks.  The kernel indexes with the
     // batch's absolute row / non-zero / coefficient numbers, so a chunk's device arrays are handed to it shifted back
@@ -1207,7 +1241,8 @@ int gdmix_re_score_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const 
         size_t o_ent = 0, o_row = up256(8 * (Ec + 1)), o_tp = o_row + up256(8 * (nr + 1));
         size_t o_col = o_tp + up256(8 * (Ec + 1)), o_val = o_col + up256(4 * nz), o_off = o_val + up256(4 * nz);
         size_t o_th = o_off + up256(4 * nr), o_hm = o_th + up256(8 * nt), o_in = o_hm + up256(Ec);
-        size_t o_lg = o_in, o_pc = o_lg + up256(4 * nr), total = o_pc + up256(4 * nr);
+        size_t o_lg = o_in, o_pc = o_lg + up256(4 * nr), o_nc = o_pc + up256(4 * nr);
+        size_t total = o_nc + (narrow ? up256((size_t)narrow * nz) : 0);
         Slot &s = g_host.slot[k & 1];
         if (s.st) CUDA_TRY(cudaStreamSynchronize(s.st));     // the chunk that used this slot two turns ago is home
         int rc = ensure(s, total, 0, 0);
@@ -1217,7 +1252,19 @@ int gdmix_re_score_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const 
         CUDA_TRY(cudaMemcpyAsync(dv + o_row, hb->rowptr + r0, 8 * (nr + 1), cudaMemcpyHostToDevice, s.st));
         CUDA_TRY(cudaMemcpyAsync(dv + o_tp, hb->theta_ptr + e0, 8 * (Ec + 1), cudaMemcpyHostToDevice, s.st));
         if (nz) {
-            CUDA_TRY(cudaMemcpyAsync(dv + o_col, hb->col + q0, 4 * nz, cudaMemcpyHostToDevice, s.st));
+            if (narrow == 1) {
+                CUDA_TRY(cudaMemcpyAsync(dv + o_nc, hb->col8 + q0, nz, cudaMemcpyHostToDevice, s.st));
+                gdmix::widen_u8_kernel<<<(int)std::min<int64_t>((nz / 16 + 255) / 256 + 1, 148 * 8), 256, 0, s.st>>>(
+                    (const uint8_t *)(dv + o_nc), (int32_t *)(dv + o_col), nz);
+                g_launches++;
+            } else if (narrow == 2) {
+                CUDA_TRY(cudaMemcpyAsync(dv + o_nc, hb->col16 + q0, 2 * nz, cudaMemcpyHostToDevice, s.st));
+                gdmix::widen_u16_kernel<<<(int)std::min<int64_t>((nz + 255) / 256, 148 * 8), 256, 0, s.st>>>(
+                    (const uint16_t *)(dv + o_nc), (int32_t *)(dv + o_col), nz);
+                g_launches++;
+            } else {
+                CUDA_TRY(cudaMemcpyAsync(dv + o_col, hb->col + q0, 4 * nz, cudaMemcpyHostToDevice, s.st));
+            }
             CUDA_TRY(cudaMemcpyAsync(dv + o_val, hb->val + q0, 4 * nz, cudaMemcpyHostToDevice, s.st));
         }
         if (hb->offset) CUDA_TRY(cudaMemcpyAsync(dv + o_off, hb->offset + r0, 4 * nr, cudaMemcpyHostToDevice, s.st));

@@ -30,16 +30,39 @@ inline int64_t avro_score_blocks_bound(int64_t n, int32_t per_block)
     return n * (10 + 4 + 1 + 4 + 4 + 4) + blocks * (10 + 10 + 16);
 }
 
+inline int long_bytes(int64_t v)
+{
+    uint64_t z = ((uint64_t)v << 1) ^ (uint64_t)(v >> 63);
+    int n = 1;
+    while (z >= 0x80) { n++; z >>= 7; }
+    return n;
+}
+
+// Blocks are sized (only the uid varints vary), then written in place by all host threads.
 inline int64_t avro_score_blocks(const int64_t *uid, const float *score, const float *label, const float *weight,
                                  const float *per_coord, int64_t n, int32_t per_block, const uint8_t *sync, uint8_t *out)
 {
-    uint8_t *p = out;
-    uint8_t tmp[24];
-    for (int64_t b0 = 0; b0 < n; b0 += per_block) {
-        const int64_t cnt = (n - b0 < per_block) ? n - b0 : per_block;
-        // records first (into place after a gap for the two varints), then the header is moved in front
-        uint8_t *body = p + 20;
-        uint8_t *q = body;
+    if (n <= 0 || per_block <= 0) return 0;
+    const int64_t nb = (n + per_block - 1) / per_block;
+    const int64_t fixed = 4 + 1 + (label ? 4 : 0) + (weight ? 4 : 0) + (per_coord ? 4 : 0);
+    std::vector<int64_t> start((size_t)nb + 1, 0), body((size_t)nb, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < nb; b++) {
+        const int64_t b0 = b * per_block, cnt = (n - b0 < per_block) ? n - b0 : per_block;
+        int64_t sz = cnt * fixed;
+        for (int64_t i = b0; i < b0 + cnt; i++) sz += long_bytes(uid[i]);
+        body[(size_t)b] = sz;
+    }
+    for (int64_t b = 0; b < nb; b++) {
+        const int64_t b0 = b * per_block, cnt = (n - b0 < per_block) ? n - b0 : per_block;
+        start[(size_t)b + 1] = start[(size_t)b] + long_bytes(cnt) + long_bytes(body[(size_t)b]) + body[(size_t)b] + 16;
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < nb; b++) {
+        const int64_t b0 = b * per_block, cnt = (n - b0 < per_block) ? n - b0 : per_block;
+        uint8_t *q = out + start[(size_t)b];
+        q = put_long(q, cnt);
+        q = put_long(q, body[(size_t)b]);
         for (int64_t i = b0; i < b0 + cnt; i++) {
             q = put_long(q, uid[i]);
             q = put_float(q, score[i]);
@@ -47,17 +70,9 @@ inline int64_t avro_score_blocks(const int64_t *uid, const float *score, const f
             if (weight) q = put_float(q, weight[i]);
             if (per_coord) q = put_float(q, per_coord[i]);
         }
-        const int64_t size = q - body;
-        uint8_t *h = put_long(tmp, cnt);
-        h = put_long(h, size);
-        const int64_t hl = h - tmp;
-        memcpy(p, tmp, hl);
-        memmove(p + hl, body, size);
-        p += hl + size;
-        memcpy(p, sync, 16);
-        p += 16;
+        memcpy(q, sync, 16);
     }
-    return p - out;
+    return start[(size_t)nb];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -111,9 +126,23 @@ inline bool avro_one_model(const ModelTable &t, int64_t m, Sink &o)
         if (kept) {
             o.lng(kept);
             if (hi) { o.str(t.intercept_name, (int64_t)strlen(t.intercept_name)); o.str("", 0); o.dbl(v[c0]); }
+            const int64_t *fi = t.feat_idx + f0 - (c0 + hi);   // fi[j] = global feature of coefficient j
             for (int64_t j = c0 + hi; j < c1; j++) {
+                // the (name, term) of a feature are four dependent cache misses in tables the size of the feature
+                // space: fetch the pointers 16 coefficients ahead and the characters 8 ahead, so the misses overlap
+                if (j + 16 < c1) {
+                    const int64_t g2 = fi[j + 16];
+                    if ((uint64_t)g2 < (uint64_t)t.n_features) { __builtin_prefetch(t.name_ptr + g2); __builtin_prefetch(t.term_ptr + g2); }
+                }
+                if (o.p && j + 8 < c1) {
+                    const int64_t g1 = fi[j + 8];
+                    if ((uint64_t)g1 < (uint64_t)t.n_features) {
+                        __builtin_prefetch(t.name_chars + t.name_ptr[g1]);
+                        __builtin_prefetch(t.term_chars + t.term_ptr[g1]);
+                    }
+                }
                 if (!(fabs(t.coef[j]) > t.threshold)) continue;
-                const int64_t g = t.feat_idx[f0 + (j - c0 - hi)];
+                const int64_t g = fi[j];
                 if (g < 0 || g >= t.n_features) return false;
                 o.str(t.name_chars + t.name_ptr[g], t.name_ptr[g + 1] - t.name_ptr[g]);
                 o.str(t.term_chars + t.term_ptr[g], t.term_ptr[g + 1] - t.term_ptr[g]);

@@ -30,6 +30,15 @@ struct Span {
 
 inline bool rd_varint(Span &s, uint64_t &v)
 {
+    if (s.e - s.p >= 3) {   // one to three bytes (values below 2^21: feature indices, lengths, keys) without the loop
+        const uint8_t *p = s.p;
+        uint64_t b = p[0], r = b & 0x7f;
+        if (!(b & 0x80)) { s.p = p + 1; v = r; return true; }
+        b = p[1]; r |= (b & 0x7f) << 7;
+        if (!(b & 0x80)) { s.p = p + 2; v = r; return true; }
+        b = p[2]; r |= (b & 0x7f) << 14;
+        if (!(b & 0x80)) { s.p = p + 3; v = r; return true; }
+    }
     v = 0;
     for (int shift = 0; shift < 70 && s.p < s.e; shift += 7) {
         const uint8_t b = *s.p++;
@@ -106,6 +115,16 @@ inline bool each_int64(Span list, F &&f)
     return true;
 }
 
+// A FloatList written the usual way -- ONE packed field 1 and nothing else: its payload (copied, not walked)
+inline bool single_packed(Span list, Span &payload)
+{
+    uint32_t fno, wt; uint64_t sc; Span sub;
+    if (list.empty() || !rd_field(list, fno, wt, sc, sub)) return false;
+    if (fno != 1 || wt != 2 || !list.empty()) return false;
+    payload = sub;
+    return true;
+}
+
 // number of elements of a list of the given kind (-1: malformed)
 inline int64_t count_elems(Kind k, Span list)
 {
@@ -137,6 +156,7 @@ public:
     {
         memset(&sz, 0, sizeof(sz));
         sz.all_labelled = 1;
+        sz.min_index = INT64_MAX; sz.max_index = INT64_MIN;
         const uint8_t *p = buf, *end = buf + len;
         int64_t rec = 0;
         while (p < end) {
@@ -305,9 +325,15 @@ private:
             if (kb == kNone) lb = Span{nullptr, nullptr};
             const int64_t q0 = sz.nnz;
             int64_t ni = 0, nv = 0;
-            if (!each_int64(la, [&](int64_t v) { if (o.gcol) o.gcol[q0 + ni] = v; ni++; }))
+            int64_t mn = sz.min_index, mx = sz.max_index;
+            if (!each_int64(la, [&](int64_t v) { if (o.gcol) o.gcol[q0 + ni] = v; mn = v < mn ? v : mn; mx = v > mx ? v : mx; ni++; }))
                 return fail("record %lld: malformed index list", rec_no);
-            if (!each_float(lb, [&](float v) { if (o.val && nv < ni) o.val[q0 + nv] = v; nv++; }))
+            sz.min_index = mn; sz.max_index = mx;
+            Span packed;
+            if (single_packed(lb, packed) && (packed.e - packed.p) % 4 == 0) {
+                nv = (packed.e - packed.p) / 4;
+                if (o.val && nv) memcpy(o.val + q0, packed.p, 4 * (size_t)(nv < ni ? nv : ni));
+            } else if (!each_float(lb, [&](float v) { if (o.val && nv < ni) o.val[q0 + nv] = v; nv++; }))
                 return fail("record %lld: malformed value list", rec_no);
             if (ni != nv) return fail("record %lld: indices / values length mismatch (%lld vs %lld)", rec_no, ni, nv);
             if (si <= n && o.row_len) o.row_len[row0 + si - 1] = ni;

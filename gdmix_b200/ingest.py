@@ -122,9 +122,12 @@ def _read_entity_grouped_native(files, entity_name, feature_bag, label_column, o
         E = sum(sz.n_entities for _, sz in counted)
         N = sum(sz.n_rows for _, sz in counted)
         Z = sum(sz.nnz for _, sz in counted)
+        # what the device calls upload afterwards (values, labels, offsets, weights) is parsed straight into
+        # page-locked memory of the library's pool; the global column ids and uids stay on the host
+        pin = capi.pinned_empty
         out = {"ent_rows": np.empty(E, np.int64), "row_len": np.empty(N, np.int64), "gcol": np.empty(Z, np.int64),
-               "val": np.empty(Z, np.float32), "uid": np.empty(N, np.int64), "label": np.empty(N, np.float32),
-               "offset": np.empty(N, np.float32), "weight": np.empty(N, np.float32)}
+               "val": pin(Z, np.float32), "uid": np.empty(N, np.int64), "label": pin(N, np.float32),
+               "offset": pin(N, np.float32), "weight": pin(N, np.float32)}
         starts, e0, r0, q0 = [], 0, 0, 0
         for _, sz in counted:
             starts.append((e0, r0, q0))
@@ -142,6 +145,8 @@ def _read_entity_grouped_native(files, entity_name, feature_bag, label_column, o
 
         ids = list(pool.map(fill, range(len(files))))
     all_labelled = all(sz.all_labelled for _, sz in counted)
+    index_lo = min((sz.min_index for _, sz in counted if sz.nnz), default=0)
+    index_hi = max((sz.max_index for _, sz in counted if sz.nnz), default=0)
     saw_weight = any(sz.saw_weight for _, sz in counted)
     del counted
     d = EntityGroupedData()
@@ -150,7 +155,8 @@ def _read_entity_grouped_native(files, entity_name, feature_bag, label_column, o
     d.has_weight_column = saw_weight
     d.ent_rowptr = np.zeros(E + 1, np.int64)
     np.cumsum(out["ent_rows"], out=d.ent_rowptr[1:])
-    d.rowptr = np.zeros(N + 1, np.int64)
+    d.rowptr = capi.pinned_empty(N + 1, np.int64)
+    d.rowptr[0] = 0
     np.cumsum(out["row_len"], out=d.rowptr[1:])
     d.gcol, d.val = out["gcol"], out["val"]
     d.uid, d.offset, d.weight = out["uid"], out["offset"], out["weight"]
@@ -160,7 +166,7 @@ def _read_entity_grouped_native(files, entity_name, feature_bag, label_column, o
             mm.close()
         except BufferError:      # a numpy view is still alive somewhere: the mapping goes with it
             pass
-    if d.gcol.size and (d.gcol.min() < 0 or d.gcol.max() >= d.num_features):
+    if d.gcol.size and (index_lo < 0 or index_hi >= d.num_features):      # tracked by the parser's counting pass
         raise ValueError(f"feature index outside [0, {d.num_features}) in {input_path}")
     return d
 
@@ -257,11 +263,17 @@ def warm_start_theta(hb, uniq_ptr, uniq_global, entity_ids, model_weights, has_i
     One sorted merge over (entity, feature) keys for the whole batch instead of a search per entity."""
     hi = 1 if has_intercept else 0
     E = len(entity_ids)
+    flat = bool(model_weights) and hasattr(model_weights, "theta_ptr") and hasattr(model_weights, "index")
+    if flat and getattr(model_weights, "source_ids", None) is entity_ids and model_weights.uniq_global is uniq_global and \
+            model_weights.theta.shape[0] == hb.n_coef:
+        # the very arrays the models were trained from (scoring the partition just trained, parsed once): the
+        # coefficients line up one to one and are handed on as they are (read-only downstream)
+        return model_weights.theta, np.ones(E, np.uint8)
     theta0 = np.zeros(hb.n_coef, np.float64)
     has_model = np.zeros(E, np.uint8)
     if not model_weights:
         return theta0, has_model
-    if hasattr(model_weights, "theta_ptr") and hasattr(model_weights, "index"):
+    if flat:
         return _warm_start_from_flat(hb, uniq_ptr, uniq_global, entity_ids, model_weights, hi, theta0, has_model)
     ents, idxs, coefs = [], [], []
     for e, eid in enumerate(entity_ids):

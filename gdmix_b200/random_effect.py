@@ -47,6 +47,7 @@ class FlatModels:
 
     def __init__(self, entity_ids, theta, variance, theta_ptr, uniq_ptr, uniq_global):
         self.entity_ids = list(entity_ids)
+        self.source_ids = entity_ids      # the parsed partition's own list: identity tells "same partition" in O(1)
         self.theta, self.variance = theta, variance
         self.theta_ptr, self.uniq_ptr, self.uniq_global = theta_ptr, uniq_ptr, uniq_global
         self._index = None

@@ -251,6 +251,14 @@ GDMIX_API int gdmix_re_score_host(const gdmix_re_batch *host_batch, const gdmix_
  * and to it asynchronously.  Optional: pageable buffers work, pinned ones overlap copy and compute. */
 GDMIX_API int gdmix_host_register(void *ptr, size_t bytes);
 GDMIX_API int gdmix_host_unregister(void *ptr);
+/* Page-locked host memory of the library's own (cudaHostAlloc / cudaFreeHost): what the plugin's readers parse a
+ * partition INTO, so that the *_host calls that follow copy at the link's rate instead of through the driver's
+ * pageable staging (the reference has no counterpart: its arrays are numpy's). */
+GDMIX_API int gdmix_pinned_alloc(size_t bytes, void **out);
+GDMIX_API int gdmix_pinned_free(void *ptr);
+/* int32 entity-local column indices -> 1 or 2 bytes each (width = 1 | 2), all host threads; the narrow form is what
+ * gdmix_re_batch.col8 / col16 carry across PCIe. */
+GDMIX_API int gdmix_narrow_columns(const int32_t *col, int64_t n, int32_t width, void *out);
 /* Releases the cached device buffers and streams of the *_host entry points. */
 GDMIX_API void gdmix_host_release(void);
 
@@ -336,6 +344,7 @@ typedef struct gdmix_seqex_spec {
 typedef struct gdmix_seqex_sizes {
     int64_t n_entities, n_rows, nnz, id_bytes;
     int32_t all_labelled, saw_weight;
+    int64_t min_index, max_index;   /* smallest / largest feature index seen (INT64_MAX / INT64_MIN when there is none) */
 } gdmix_seqex_sizes;
 GDMIX_API int gdmix_seqex_count(const uint8_t *file_image, int64_t len, const gdmix_seqex_spec *spec,
                                 gdmix_seqex_sizes *sizes);
