@@ -38,7 +38,7 @@ SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_w
            "gdmix_fe_lbfgs_create", "gdmix_fe_lbfgs_reset", "gdmix_fe_lbfgs_step", "gdmix_fe_lbfgs_poll",
            "gdmix_fe_lbfgs_destroy", "gdmix_fe_column_counts", "gdmix_remap_i32", "gdmix_group_ids", "gdmix_offset_join", "gdmix_seqex_encode", "gdmix_local_index_host", "gdmix_fe_tile_plan_create",
            "gdmix_fe_tile_plan_destroy", "gdmix_fe_tile_plan_info", "gdmix_fe_loss_grad_tiled",
-           "gdmix_pinned_alloc", "gdmix_pinned_free", "gdmix_narrow_columns"]
+           "gdmix_pinned_alloc", "gdmix_pinned_free", "gdmix_narrow_columns", "gdmix_selftest_logistic"]
 
 
 class SeqexSpec(C.Structure):

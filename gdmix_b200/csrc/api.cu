@@ -1169,6 +1169,16 @@ int gdmix_host_unregister(void *ptr)
     return GDMIX_OK;
 }
 
+int gdmix_selftest_logistic(const double *z, int64_t n, double *out, void *stream)
+{
+    if (n < 0 || (n > 0 && (!z || !out))) return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_selftest_logistic");
+    if (n == 0) return GDMIX_OK;
+    gdmix::logistic_selftest_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(z, n, out);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GDMIX_OK;
+}
+
 int gdmix_pinned_alloc(size_t bytes, void **out)
 {
     if (!out || !bytes) return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_pinned_alloc");

@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 #include "../../include/gdmix_b200.h"
+#include "re_common.cuh"
 
 namespace gdmix {
 
@@ -45,6 +46,20 @@ __global__ void __launch_bounds__(256) re_score_kernel(const gdmix_re_batch b, c
         }
         logit[i] = (float)z;
         logit_pc[i] = (float)(z - offs);
+    }
+}
+
+// logistic_terms (re_common.cuh) next to the library functions it replaces in the fast kernel: out[6 i ..] =
+// {t, log1p, inv} of logistic_terms, then exp(-|z|), log(1 + exp(-|z|)), 1 / (1 + exp(-|z|)) by the library
+__global__ void __launch_bounds__(256) logistic_selftest_kernel(const double *z, const int64_t n, double *out)
+{
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth) {
+        double t, l, v;
+        logistic_terms(z[i], t, l, v);
+        const double ez = exp(-fabs(z[i]));
+        out[6 * i] = t; out[6 * i + 1] = l; out[6 * i + 2] = v;
+        out[6 * i + 3] = ez; out[6 * i + 4] = log(1.0 + ez); out[6 * i + 5] = 1.0 / (1.0 + ez);
     }
 }
 

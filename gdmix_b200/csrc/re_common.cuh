@@ -84,6 +84,74 @@ struct ReLayout {
     uint32_t total_bytes;             // fixed + history
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// The three transcendental terms of one logistic sample, t = exp(-|z|), log(1 + t) and 1 / (1 + t), written for the
+// solver's rows pass: one sample per thread, nothing else to overlap with, so what counts is instruction count and
+// the length of the dependent chain -- the library's exp / log / division are ~235 instructions with internal
+// branches; this is ~80, branch-free, with the polynomials in Estrin form and the two reciprocals side by side.
+// Accuracy (tests/test_re_gpu_parity.py::test_logistic_terms_accuracy): t, log(1 + t), 1 / (1 + t) within 2 ulp of
+// the library's results for |z| <= 708; beyond that t is e^-708 (3e-308) instead of a denormal / zero.
+//   exp(-a) = 2^-k e^x, k = rint(a log2 e), x = k ln2 - a in [-ln2/2, ln2/2], e^x = 1 + (x + x^2 R(x)), Taylor to x^13
+//   log(u), u = 1 + t in (1, 2]: m = u or u/2 (above sqrt 2), f = m - 1, s = f / (2 + f),
+//            log m = 2 s + 2 s^3 T(s^2), T = 1/3 + s^2/5 + ... + s^20/23, |s| <= 0.1716
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rcp_newton(const double a)   // a normal and away from the range limits
+{
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    double e = fma(-a, x, 1.0);
+    e = fma(e, e, e);
+    x = fma(x, e, x);
+    e = fma(-a, x, 1.0);
+    return fma(x, e, x);
+}
+
+__device__ __forceinline__ void logistic_terms(const double z, double &t, double &log1pt, double &inv1pt)
+{
+    const double a = fmin(fabs(z), 708.0);
+    const double magic = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to an integer in the low word
+    const double kd = fma(a, 1.4426950408889634074, magic);
+    const int k = __double2loint(kd);
+    const double kf = kd - magic;
+    double x = fma(kf, 6.93147180369123816490e-01, -a);
+    x = fma(kf, 1.90821492927058770002e-10, x);
+    {
+        const double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4;
+        const double p0 = fma(x, 1.0 / 6.0, 0.5);
+        const double p1 = fma(x, 1.0 / 120.0, 1.0 / 24.0);
+        const double p2 = fma(x, 1.0 / 5040.0, 1.0 / 720.0);
+        const double p3 = fma(x, 1.0 / 362880.0, 1.0 / 40320.0);
+        const double p4 = fma(x, 1.0 / 39916800.0, 1.0 / 3628800.0);
+        const double p5 = fma(x, 1.0 / 6227020800.0, 1.0 / 479001600.0);
+        const double q0 = fma(x2, p1, p0), q1 = fma(x2, p3, p2), q2 = fma(x2, p5, p4);
+        const double R = fma(x8, q2, fma(x4, q1, q0));
+        const double ex = 1.0 + fma(x2, R, x);
+        t = ex * __hiloint2double((1023 - k) << 20, 0);
+    }
+    const double u = 1.0 + t;
+    const bool big = u > 1.41421356237309514547;
+    const double m = big ? 0.5 * u : u;
+    const double f = m - 1.0, d = m + 1.0;
+    const double rd = rcp_newton(d);
+    inv1pt = rcp_newton(u);
+    double s = f * rd;
+    s = fma(fma(-d, s, f), rd, s);
+    {
+        const double s2 = s * s, s4 = s2 * s2, s8 = s4 * s4;
+        const double p0 = fma(s2, 1.0 / 5.0, 1.0 / 3.0);
+        const double p1 = fma(s2, 1.0 / 9.0, 1.0 / 7.0);
+        const double p2 = fma(s2, 1.0 / 13.0, 1.0 / 11.0);
+        const double p3 = fma(s2, 1.0 / 17.0, 1.0 / 15.0);
+        const double p4 = fma(s2, 1.0 / 21.0, 1.0 / 19.0);
+        const double q0 = fma(s4, p1, p0), q1 = fma(s4, p3, p2), q2 = fma(s4, 1.0 / 23.0, p4);
+        const double s16 = s8 * s8;
+        const double T = fma(s16, q2, fma(s8, q1, q0));
+        const double two_s = s + s;
+        const double l = fma(two_s * s2, T, two_s);
+        log1pt = big ? l + 6.93147180559945286227e-01 : l;
+    }
+}
+
 // Offsets (in doubles) inside the dense block, MT = compile-time bound on m.
 template <int MT>
 struct Dense {

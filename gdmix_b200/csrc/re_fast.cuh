@@ -779,10 +779,10 @@ __global__ void __launch_bounds__(G, (EPT == 1) ? 512 / G : ((G <= 128) ? 384 / 
                             z = (z + (E.hi ? xt0 : 0.0)) + (double)((const float *)(smem + L.soff))[sp];
                             const double yi = (double)((const float *)(smem + L.sy))[sp];
                             const double wi = (double)((const float *)(smem + L.sw))[sp];
-                            const double ez = exp(-fabs(z));
-                            const double ce = fmax(z, 0.0) - z * yi + log(1.0 + ez);
+                            double ez, l1p, inv;
+                            logistic_terms(z, ez, l1p, inv);     // exp(-|z|), log(1 + ez), 1 / (1 + ez)
+                            const double ce = fmax(z, 0.0) - z * yi + l1p;
                             p3[0] = fma(wi, ce, p3[0]);
-                            const double inv = 1.0 / (1.0 + ez);
                             const double sig = (z >= 0.0) ? inv : ez * inv;
                             const double ri = wi * (sig - yi);
                             ((double *)(smem + L.r))[((const uint16_t *)(smem + L.rowperm))[sp]] = ri;

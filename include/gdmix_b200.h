@@ -251,6 +251,9 @@ GDMIX_API int gdmix_re_score_host(const gdmix_re_batch *host_batch, const gdmix_
  * and to it asynchronously.  Optional: pageable buffers work, pinned ones overlap copy and compute. */
 GDMIX_API int gdmix_host_register(void *ptr, size_t bytes);
 GDMIX_API int gdmix_host_unregister(void *ptr);
+/* Self-test of the solver's own exp(-|z|) / log(1 + t) / 1 / (1 + t) (csrc/re_common.cuh: logistic_terms) against
+ * the CUDA math library on device arrays: out[6 i ..] = the three terms by logistic_terms, then by the library. */
+GDMIX_API int gdmix_selftest_logistic(const double *z, int64_t n, double *out, void *stream);
 /* Page-locked host memory of the library's own (cudaHostAlloc / cudaFreeHost): what the plugin's readers parse a
  * partition INTO, so that the *_host calls that follow copy at the link's rate instead of through the driver's
  * pageable staging (the reference has no counterpart: its arrays are numpy's). */

@@ -218,6 +218,40 @@ def test_scoring_in_chunks_is_the_same(monkeypatch):
         np.testing.assert_array_equal(part[1], whole[1])
 
 
+def test_logistic_terms_accuracy():
+    """The fast kernel's own exp(-|z|), log(1 + t), 1 / (1 + t) (re_common.cuh: logistic_terms) against the CUDA
+    math library: within 2 ulp for |z| <= 708 (and against numpy in higher precision terms: 4e-16 relative)."""
+    import ctypes as C
+    rng = np.random.default_rng(3)
+    z = np.concatenate([rng.uniform(-40, 40, 200000), rng.uniform(-708, 708, 100000), rng.standard_normal(200000) * 1e-3,
+                        rng.standard_normal(100000) * 1e-9, np.array([0.0, -0.0, 1e-300, 708.0, -708.0, 0.34657359, 0.8813736]),
+                        np.linspace(-2, 2, 100001)])
+    zd = torch.from_numpy(z).cuda()
+    out = torch.empty(6 * z.size, dtype=torch.float64, device="cuda")
+    capi.check(capi.lib.gdmix_selftest_logistic(C.c_void_p(zd.data_ptr()), C.c_int64(z.size), C.c_void_p(out.data_ptr()),
+                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    o = out.cpu().numpy().reshape(-1, 6)
+    for k, name in ((0, "exp(-|z|)"), (2, "1/(1+t)")):
+        mine, lib = o[:, k], o[:, 3 + k]
+        ulp = np.abs(mine - lib) / np.spacing(np.abs(lib))
+        assert ulp.max() <= 2.0, (name, ulp.max(), z[ulp.argmax()])
+    # log(1 + t) goes through u = fl(1 + t) in the reference's formula too: one ulp of t can move u by one ulp of 1,
+    # i.e. the value by 2.2e-16 whatever its size -- so: the log of MY u within 2 ulp, and the library's within that + eps
+    u = 1.0 + o[:, 0]
+    ref = np.log(u.astype(np.longdouble))
+    err = np.abs(o[:, 1] - ref)
+    assert np.all(err <= 2.0 * np.spacing(np.abs(o[:, 1])) + 1e-300), (err / np.spacing(np.abs(o[:, 1]))).max()
+    assert np.max(np.abs(o[:, 1] - o[:, 4])) <= 4.5e-16
+    # beyond the clamp: t stays a tiny positive number, the other two terms are exact
+    zd2 = torch.tensor([750.0, -1e6, 1e300], dtype=torch.float64, device="cuda")
+    out2 = torch.empty(18, dtype=torch.float64, device="cuda")
+    capi.check(capi.lib.gdmix_selftest_logistic(C.c_void_p(zd2.data_ptr()), C.c_int64(3), C.c_void_p(out2.data_ptr()),
+                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    o2 = out2.cpu().numpy().reshape(-1, 6)
+    assert (o2[:, 0] > 0).all() and (o2[:, 0] < 1e-307).all() and (o2[:, 2] == 1.0).all() and (o2[:, 1] < 1e-307).all()
+
+
 def test_bad_column_index_is_rejected():
     hb = make_batch(8, 16, 24, 4, seed=1)
     hb.col[5] = 9999
