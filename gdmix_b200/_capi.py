@@ -600,7 +600,7 @@ def parse_entity_grouped(file_image, entity, uid, label, offset, weight, bag_ind
     check(lib.gdmix_seqex_fill(_np_ptr(buf), C.c_int64(buf.size), C.byref(spec), _np_ptr(out["ent_rows"]),
                                _np_ptr(out["row_len"]), _np_ptr(out["gcol"]), _np_ptr(out["val"]), _np_ptr(out["uid"]),
                                _np_ptr(out["label"]), _np_ptr(out["offset"]), _np_ptr(out["weight"]),
-                               _np_ptr(out["id_chars"]), _np_ptr(out["id_ptr"])))
+                               _np_ptr(out["id_chars"]), _np_ptr(out["id_ptr"]), None))
     raw = out["id_chars"].tobytes()
     ip = out["id_ptr"]
     out["entity_ids"] = [raw[ip[e]:ip[e + 1]].decode("utf-8") for e in range(E)]
@@ -767,10 +767,12 @@ def seqex_fill_into(buf, spec, out, e0, r0, q0, id_chars, id_ptr):
     """gdmix_seqex_fill of one file straight into the partition-wide arrays `out` at entity e0 / row r0 / non-zero q0;
     the file's entity-id strings go to its own id_chars / id_ptr (small)."""
     at = lambda a, i: None if a is None else C.c_void_p(a.ctypes.data + i * a.itemsize)
+    rng = (C.c_int64 * 2)()
     check(lib.gdmix_seqex_fill(_np_ptr(buf), C.c_int64(buf.size), C.byref(spec), at(out["ent_rows"], e0),
                                at(out["row_len"], r0), at(out["gcol"], q0), at(out["val"], q0), at(out["uid"], r0),
                                at(out["label"], r0), at(out["offset"], r0), at(out["weight"], r0),
-                               _np_ptr(id_chars), _np_ptr(id_ptr)))
+                               _np_ptr(id_chars), _np_ptr(id_ptr), rng))
+    return int(rng[0]), int(rng[1])      # smallest / largest feature index written
 
 
 def parse_per_record(file_image, uid, label, offset, weight, bag_indices, bag_values):

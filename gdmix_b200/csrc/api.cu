@@ -1943,7 +1943,7 @@ int gdmix_seqex_count(const uint8_t *file_image, int64_t len, const gdmix_seqex_
 
 int gdmix_seqex_fill(const uint8_t *file_image, int64_t len, const gdmix_seqex_spec *spec, int64_t *ent_rows,
                      int64_t *row_len, int64_t *gcol, float *val, int64_t *uid, float *label, float *offset,
-                     float *weight, char *id_chars, int64_t *id_ptr)
+                     float *weight, char *id_chars, int64_t *id_ptr, int64_t *index_range)
 {
     if (!spec || (len > 0 && !file_image) || len < 0 || !ent_rows || !row_len || !gcol || !val || !uid || !label ||
         !offset || !weight || !id_chars || !id_ptr)
@@ -1955,6 +1955,7 @@ int gdmix_seqex_fill(const uint8_t *file_image, int64_t len, const gdmix_seqex_s
     o.offset = offset; o.weight = weight; o.id_chars = id_chars; o.id_ptr = id_ptr;
     gdmix_seqex_sizes sz;
     if (!r.run(file_image, len, sz, o)) return fail(GDMIX_ERR_INVALID, "%s", err.c_str());
+    if (index_range) { index_range[0] = sz.min_index; index_range[1] = sz.max_index; }
     return GDMIX_OK;
 }
 

@@ -115,6 +115,17 @@ inline bool each_int64(Span list, F &&f)
     return true;
 }
 
+// number of varints in a packed payload = bytes without the continuation bit (a loop the compiler vectorises);
+// false when the payload ends inside a varint
+inline bool count_varints(Span sub, int64_t &n)
+{
+    if (sub.empty()) return true;
+    int64_t c = 0;
+    for (const uint8_t *q = sub.p; q < sub.e; q++) c += (*q & 0x80) == 0;
+    n += c;
+    return (sub.e[-1] & 0x80) == 0;
+}
+// An Int64List written the usual way -- ONE packed field 1 and nothing else
 // A FloatList written the usual way -- ONE packed field 1 and nothing else: its payload (copied, not walked)
 inline bool single_packed(Span list, Span &payload)
 {
@@ -325,10 +336,16 @@ private:
             if (kb == kNone) lb = Span{nullptr, nullptr};
             const int64_t q0 = sz.nnz;
             int64_t ni = 0, nv = 0;
-            int64_t mn = sz.min_index, mx = sz.max_index;
-            if (!each_int64(la, [&](int64_t v) { if (o.gcol) o.gcol[q0 + ni] = v; mn = v < mn ? v : mn; mx = v > mx ? v : mx; ni++; }))
-                return fail("record %lld: malformed index list", rec_no);
-            sz.min_index = mn; sz.max_index = mx;
+            Span ipacked;
+            if (!o.gcol && single_packed(la, ipacked)) {
+                // counting pass: the indices are not decoded (their range is tracked by the filling pass)
+                if (!count_varints(ipacked, ni)) return fail("record %lld: malformed index list", rec_no);
+            } else {
+                int64_t mn = sz.min_index, mx = sz.max_index;
+                if (!each_int64(la, [&](int64_t v) { if (o.gcol) o.gcol[q0 + ni] = v; mn = v < mn ? v : mn; mx = v > mx ? v : mx; ni++; }))
+                    return fail("record %lld: malformed index list", rec_no);
+                sz.min_index = mn; sz.max_index = mx;
+            }
             Span packed;
             if (single_packed(lb, packed) && (packed.e - packed.p) % 4 == 0) {
                 nv = (packed.e - packed.p) / 4;

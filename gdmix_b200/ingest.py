@@ -137,16 +137,18 @@ def _read_entity_grouped_native(files, entity_name, feature_bag, label_column, o
             buf, sz = counted[k]
             idc, idp = np.zeros(max(sz.id_bytes, 1), np.uint8), np.zeros(sz.n_entities + 1, np.int64)
             try:
-                capi.seqex_fill_into(buf, spec, out, *starts[k], idc, idp)
+                rng = capi.seqex_fill_into(buf, spec, out, *starts[k], idc, idp)
             except capi.GdmixError as ex:
                 raise ValueError(f"{files[k]}: {ex}") from None
             raw = idc.tobytes()
-            return [raw[idp[e]:idp[e + 1]].decode("utf-8") for e in range(sz.n_entities)]
+            return [raw[idp[e]:idp[e + 1]].decode("utf-8") for e in range(sz.n_entities)], rng
 
-        ids = list(pool.map(fill, range(len(files))))
+        filled = list(pool.map(fill, range(len(files))))
+        ids = [f[0] for f in filled]
+        ranges = [f[1] for f, (_, sz) in zip(filled, counted) if sz.nnz]
     all_labelled = all(sz.all_labelled for _, sz in counted)
-    index_lo = min((sz.min_index for _, sz in counted if sz.nnz), default=0)
-    index_hi = max((sz.max_index for _, sz in counted if sz.nnz), default=0)
+    index_lo = min((r[0] for r in ranges), default=0)      # tracked by the parser's filling pass
+    index_hi = max((r[1] for r in ranges), default=0)
     saw_weight = any(sz.saw_weight for _, sz in counted)
     del counted
     d = EntityGroupedData()
@@ -166,7 +168,7 @@ def _read_entity_grouped_native(files, entity_name, feature_bag, label_column, o
             mm.close()
         except BufferError:      # a numpy view is still alive somewhere: the mapping goes with it
             pass
-    if d.gcol.size and (index_lo < 0 or index_hi >= d.num_features):      # tracked by the parser's counting pass
+    if d.gcol.size and (index_lo < 0 or index_hi >= d.num_features):
         raise ValueError(f"feature index outside [0, {d.num_features}) in {input_path}")
     return d
 

@@ -347,13 +347,15 @@ typedef struct gdmix_seqex_spec {
 typedef struct gdmix_seqex_sizes {
     int64_t n_entities, n_rows, nnz, id_bytes;
     int32_t all_labelled, saw_weight;
-    int64_t min_index, max_index;   /* smallest / largest feature index seen (INT64_MAX / INT64_MIN when there is none) */
+    int64_t min_index, max_index;   /* smallest / largest feature index DECODED (INT64_MAX / INT64_MIN when none was:
+                                     * the counting pass skips over packed index lists; gdmix_seqex_fill reports the
+                                     * range of what it wrote through index_range[2], which may be NULL) */
 } gdmix_seqex_sizes;
 GDMIX_API int gdmix_seqex_count(const uint8_t *file_image, int64_t len, const gdmix_seqex_spec *spec,
                                 gdmix_seqex_sizes *sizes);
 GDMIX_API int gdmix_seqex_fill(const uint8_t *file_image, int64_t len, const gdmix_seqex_spec *spec, int64_t *ent_rows,
                                int64_t *row_len, int64_t *gcol, float *val, int64_t *uid, float *label, float *offset,
-                               float *weight, char *id_chars, int64_t *id_ptr);
+                               float *weight, char *id_chars, int64_t *id_ptr, int64_t *index_range);
 
 /* Entity-local feature indexing of a parsed partition on the host (np.unique(cols, return_inverse=True) per entity,
  * job_consumers.py:243), all host threads.  Two calls: uniq_global == NULL -> local_col[nnz], d_e[E] and the distinct
