@@ -38,7 +38,8 @@ SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_w
            "gdmix_fe_lbfgs_create", "gdmix_fe_lbfgs_reset", "gdmix_fe_lbfgs_step", "gdmix_fe_lbfgs_poll",
            "gdmix_fe_lbfgs_destroy", "gdmix_fe_column_counts", "gdmix_remap_i32", "gdmix_group_ids", "gdmix_offset_join", "gdmix_seqex_encode", "gdmix_local_index_host", "gdmix_fe_tile_plan_create",
            "gdmix_fe_tile_plan_destroy", "gdmix_fe_tile_plan_info", "gdmix_fe_loss_grad_tiled",
-           "gdmix_pinned_alloc", "gdmix_pinned_free", "gdmix_narrow_columns", "gdmix_selftest_logistic"]
+           "gdmix_pinned_alloc", "gdmix_pinned_free", "gdmix_narrow_columns", "gdmix_selftest_logistic",
+           "gdmix_seqex_fill_local"]
 
 
 class SeqexSpec(C.Structure):
@@ -177,10 +178,19 @@ class HostBatch:
     """A batch of entities in host memory (numpy), entity-local CSR -- gdmix_re_batch with host pointers."""
 
     def __init__(self, ent_rowptr, rowptr, col, val, label, weight=None, offset=None, theta_ptr=None,
-                 has_intercept=True):
+                 has_intercept=True, col_narrow=None):
+        """col: int32 entity-local column indices, or None when col_narrow (uint8 / uint16, what crosses PCIe) is
+        given ready-made (the fused reader produces it directly)."""
         self.ent_rowptr = np.ascontiguousarray(ent_rowptr, dtype=np.int64)
         self.rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
-        self.col = np.ascontiguousarray(col, dtype=np.int32)
+        if col is None and col_narrow is None:
+            raise ValueError("HostBatch needs col or col_narrow")
+        self.col = None if col is None else np.ascontiguousarray(col, dtype=np.int32)
+        self._col_narrow = None
+        if col_narrow is not None:
+            if col_narrow.dtype not in (np.uint8, np.uint16):
+                raise ValueError("col_narrow must be uint8 or uint16")
+            self._col_narrow = np.ascontiguousarray(col_narrow)
         self.val = np.ascontiguousarray(val, dtype=np.float32)
         self.label = np.ascontiguousarray(label, dtype=np.float32)
         self.weight = None if weight is None else np.ascontiguousarray(weight, dtype=np.float32)
@@ -189,7 +199,8 @@ class HostBatch:
         self.n_entities = len(self.ent_rowptr) - 1
         self.n_rows = int(self.ent_rowptr[-1]) if self.n_entities >= 0 else 0
         self.nnz = int(self.rowptr[self.n_rows])
-        assert self.rowptr.shape[0] == self.n_rows + 1 and self.col.shape[0] >= self.nnz
+        assert self.rowptr.shape[0] == self.n_rows + 1
+        assert (self.col if self.col is not None else self._col_narrow).shape[0] >= self.nnz
         self.theta_ptr = np.ascontiguousarray(theta_ptr, dtype=np.int64)
         assert self.theta_ptr.shape[0] == self.n_entities + 1
         rows = np.diff(self.ent_rowptr)
@@ -204,7 +215,9 @@ class HostBatch:
         """narrow=True sends the local column indices as uint16 (half the PCIe bytes for them); default: whenever
         every entity has fewer than 65536 local features."""
         if narrow is None:
-            narrow = self.max_coef < 65536 and self.nnz > 0
+            narrow = (self.max_coef < 65536 and self.nnz > 0) or self.col is None
+        if not narrow and self.col is None:
+            raise ValueError("this HostBatch only has narrow column indices")
         c16 = c8 = None
         if narrow:
             if getattr(self, "_col_narrow", None) is None:
@@ -773,6 +786,31 @@ def seqex_fill_into(buf, spec, out, e0, r0, q0, id_chars, id_ptr):
                                at(out["label"], r0), at(out["offset"], r0), at(out["weight"], r0),
                                _np_ptr(id_chars), _np_ptr(id_ptr), rng))
     return int(rng[0]), int(rng[1])      # smallest / largest feature index written
+
+
+def seqex_fill_local_into(buf, spec, out, e0, r0, q0, id_chars, id_ptr):
+    """gdmix_seqex_fill_local of one file into the partition-wide arrays: as seqex_fill_into, with out["local16"],
+    out["d_e"], out["uniq_scratch"] instead of out["gcol"]."""
+    at = lambda a, i: None if a is None else C.c_void_p(a.ctypes.data + i * a.itemsize)
+    rng = (C.c_int64 * 2)()
+    check(lib.gdmix_seqex_fill_local(_np_ptr(buf), C.c_int64(buf.size), C.byref(spec), at(out["ent_rows"], e0),
+                                     at(out["row_len"], r0), at(out["local16"], q0), at(out["d_e"], e0),
+                                     at(out["uniq_scratch"], q0), at(out["val"], q0), at(out["uid"], r0),
+                                     at(out["label"], r0), at(out["offset"], r0), at(out["weight"], r0),
+                                     _np_ptr(id_chars), _np_ptr(id_ptr), rng))
+    return int(rng[0]), int(rng[1])
+
+
+def local_index_gather(ent_rowptr, rowptr, d_e, scratch):
+    """Second call of gdmix_local_index_host: the distinct indices parked in scratch -> (uniq_ptr, uniq_global)."""
+    E = ent_rowptr.shape[0] - 1
+    d_e = np.ascontiguousarray(d_e, dtype=np.int64)
+    uniq_ptr = np.zeros(E + 1, np.int64)
+    np.cumsum(d_e[:E], out=uniq_ptr[1:])
+    uniq_global = np.empty(max(int(uniq_ptr[-1]), 1), np.int64)
+    check(lib.gdmix_local_index_host(_np_ptr(ent_rowptr), _np_ptr(rowptr), None, C.c_int64(E), None, _np_ptr(d_e),
+                                     _np_ptr(scratch), _np_ptr(uniq_ptr), _np_ptr(uniq_global)))
+    return uniq_ptr, uniq_global[:int(uniq_ptr[-1])]
 
 
 def parse_per_record(file_image, uid, label, offset, weight, bag_indices, bag_values):

@@ -1959,6 +1959,27 @@ int gdmix_seqex_fill(const uint8_t *file_image, int64_t len, const gdmix_seqex_s
     return GDMIX_OK;
 }
 
+int gdmix_seqex_fill_local(const uint8_t *file_image, int64_t len, const gdmix_seqex_spec *spec, int64_t *ent_rows,
+                           int64_t *row_len, uint16_t *local16, int64_t *d_e, int64_t *uniq_scratch, float *val,
+                           int64_t *uid, float *label, float *offset, float *weight, char *id_chars, int64_t *id_ptr,
+                           int64_t *index_range)
+{
+    if (!spec || (len > 0 && !file_image) || len < 0 || !ent_rows || !row_len || !local16 || !d_e || !uniq_scratch ||
+        !val || !uid || !label || !offset || !weight || !id_chars || !id_ptr)
+        return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_seqex_fill_local");
+    std::string err;
+    gdmix_host::SeqexReader r(*spec, err);
+    gdmix_host::SeqexOut o;
+    o.ent_rows = ent_rows; o.row_len = row_len; o.val = val; o.uid = uid; o.label = label;
+    o.offset = offset; o.weight = weight; o.id_chars = id_chars; o.id_ptr = id_ptr;
+    o.local16 = local16; o.d_e = d_e; o.uniq_scratch = uniq_scratch;
+    gdmix_seqex_sizes sz;
+    if (!r.run(file_image, len, sz, o))
+        return fail(err.find("65535 distinct") != std::string::npos ? GDMIX_ERR_TOO_LARGE : GDMIX_ERR_INVALID, "%s", err.c_str());
+    if (index_range) { index_range[0] = sz.min_index; index_range[1] = sz.max_index; }
+    return GDMIX_OK;
+}
+
 int gdmix_example_count(const uint8_t *file_image, int64_t len, const gdmix_seqex_spec *spec, gdmix_seqex_sizes *sizes)
 {
     if (!spec || !sizes || (len > 0 && !file_image) || len < 0 || (!spec->bag_indices != !spec->bag_values))

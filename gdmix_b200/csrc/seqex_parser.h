@@ -156,6 +156,10 @@ struct SeqexOut {   // null pointers: counting pass
     int64_t *ent_rows = nullptr, *row_len = nullptr, *gcol = nullptr, *uid = nullptr, *id_ptr = nullptr;
     float *val = nullptr, *label = nullptr, *offset = nullptr, *weight = nullptr;
     char *id_chars = nullptr;
+    // fused entity-local indexing (instead of gcol): local16[nnz] = rank of every index among its entity's distinct
+    // indices, d_e[E] their number, uniq_scratch[nnz] the sorted distinct indices of entity e at its first non-zero
+    uint16_t *local16 = nullptr;
+    int64_t *d_e = nullptr, *uniq_scratch = nullptr;
 };
 
 class SeqexReader {
@@ -291,6 +295,8 @@ private:
         if (!column(f_w, has_w, o.weight, 1.0f, "weight")) return false;
         if (has_w) sz.saw_weight = 1;
         // ---- feature lists: <bag>_indices and <bag>_values, one Feature per sample
+        const int64_t ent_q0 = sz.nnz;
+        ent_g_.clear();
         Span l_idx{nullptr, nullptr}, l_val{nullptr, nullptr};
         bool has_idx = false, has_val = false;
         Span fl = lists;
@@ -337,12 +343,15 @@ private:
             const int64_t q0 = sz.nnz;
             int64_t ni = 0, nv = 0;
             Span ipacked;
-            if (!o.gcol && single_packed(la, ipacked)) {
+            if (!o.gcol && !o.local16 && single_packed(la, ipacked)) {
                 // counting pass: the indices are not decoded (their range is tracked by the filling pass)
                 if (!count_varints(ipacked, ni)) return fail("record %lld: malformed index list", rec_no);
             } else {
                 int64_t mn = sz.min_index, mx = sz.max_index;
-                if (!each_int64(la, [&](int64_t v) { if (o.gcol) o.gcol[q0 + ni] = v; mn = v < mn ? v : mn; mx = v > mx ? v : mx; ni++; }))
+                if (o.local16) {
+                    if (!each_int64(la, [&](int64_t v) { ent_g_.push_back(v); mn = v < mn ? v : mn; mx = v > mx ? v : mx; ni++; }))
+                        return fail("record %lld: malformed index list", rec_no);
+                } else if (!each_int64(la, [&](int64_t v) { if (o.gcol) o.gcol[q0 + ni] = v; mn = v < mn ? v : mn; mx = v > mx ? v : mx; ni++; }))
                     return fail("record %lld: malformed index list", rec_no);
                 sz.min_index = mn; sz.max_index = mx;
             }
@@ -358,13 +367,61 @@ private:
         }
         if (si != n || sv != n)
             return fail("record %lld: %lld index lists / %lld value lists for its samples", rec_no, si, sv);
+        if (o.local16) {
+            if (!local_index(o, ent_q0, sz.n_entities)) return fail("record %lld: more than 65535 distinct features (fused local index)", rec_no);
+        }
         sz.n_rows += n;
         sz.n_entities++;
         return true;
     }
 
+    // np.unique(cols, return_inverse=True) of the entity just parsed (job_consumers.py:243) while its indices are
+    // still in cache: one open-addressing table per reader, two probes per non-zero (local_index_pass1's algorithm).
+    // Negative indices hash like any other (the caller rejects the partition by the index range).
+    bool local_index(const SeqexOut &o, const int64_t q0, const int64_t e)
+    {
+        const size_t nz = ent_g_.size();
+        if (nz == 0) { o.d_e[e] = 0; return true; }
+        size_t cap = 16;
+        while (cap < 2 * nz) cap <<= 1;
+        if (keys_.size() < cap) { keys_.assign(cap, INT64_MIN); slot_rank_.assign(cap, 0); }
+        const size_t mask = keys_.size() - 1;
+        auto hash = [](int64_t g) { return (size_t)((uint64_t)g * 0x9E3779B97F4A7C15ull >> 20); };
+        distinct_.clear();
+        slots_.clear();
+        for (size_t j = 0; j < nz; j++) {
+            const int64_t g = ent_g_[j];
+            size_t h = hash(g) & mask;
+            while (keys_[h] != INT64_MIN && keys_[h] != g) h = (h + 1) & mask;
+            if (keys_[h] == INT64_MIN) { keys_[h] = g; distinct_.push_back(g); slots_.push_back((uint32_t)h); }
+        }
+        bool ok = distinct_.size() <= 65535;
+        if (ok) {
+            std::sort(distinct_.begin(), distinct_.end());
+            for (size_t r = 0; r < distinct_.size(); r++) {
+                const int64_t g = distinct_[r];
+                size_t h = hash(g) & mask;
+                while (keys_[h] != g) h = (h + 1) & mask;
+                slot_rank_[h] = (int32_t)r;
+                o.uniq_scratch[q0 + (int64_t)r] = g;
+            }
+            for (size_t j = 0; j < nz; j++) {
+                const int64_t g = ent_g_[j];
+                size_t h = hash(g) & mask;
+                while (keys_[h] != g) h = (h + 1) & mask;
+                o.local16[q0 + (int64_t)j] = (uint16_t)slot_rank_[h];
+            }
+            o.d_e[e] = (int64_t)distinct_.size();
+        }
+        for (const uint32_t h : slots_) keys_[h] = INT64_MIN;     // reset only what was touched
+        return ok;
+    }
+
     const gdmix_seqex_spec &spec_;
     std::string &err_;
+    std::vector<int64_t> ent_g_, keys_, distinct_;
+    std::vector<int32_t> slot_rank_;
+    std::vector<uint32_t> slots_;
 };
 
 // ---------------------------------------------------------------------------------------------------------

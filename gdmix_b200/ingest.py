@@ -57,7 +57,9 @@ class EntityGroupedData:
         self.entity_ids = []
         self.ent_rowptr = np.zeros(1, np.int64)
         self.rowptr = np.zeros(1, np.int64)
-        self.gcol = np.zeros(0, np.int64)
+        self._gcol = np.zeros(0, np.int64)
+        # the fused reader's output instead of gcol: entity-local indices (uint16), distinct features per entity
+        self.local16 = self.uniq_ptr = self.uniq_global = None
         self.val = np.zeros(0, np.float32)
         self.label = None
         self.weight = None
@@ -65,6 +67,19 @@ class EntityGroupedData:
         self.uid = None
         self.has_weight_column = False
         self.num_features = 1
+
+    @property
+    def gcol(self):
+        """GLOBAL feature id of every non-zero; rebuilt from the local indices when the reader never wrote it."""
+        if self._gcol is None:
+            nnz_e = self.rowptr[self.ent_rowptr[1:]] - self.rowptr[self.ent_rowptr[:-1]]
+            base = np.repeat(self.uniq_ptr[:-1], nnz_e)
+            self._gcol = self.uniq_global[base + self.local16.astype(np.int64)]
+        return self._gcol
+
+    @gcol.setter
+    def gcol(self, value):
+        self._gcol = value
 
     @property
     def n_entities(self):
@@ -83,11 +98,13 @@ def _entity_id_to_str(kind, values):
 
 
 def _read_entity_grouped_native(files, entity_name, feature_bag, label_column, offset_column, weight_column,
-                                uid_column, num_features, input_path):
+                                uid_column, num_features, input_path, fused=None):
     """The library's own SequenceExample reader (csrc/seqex_parser.h through gdmix_seqex_count / _fill): ~50x the
     pure-Python protobuf walk below, same arrays.  Returns None for the one case it leaves to that walk (float
     entity ids); malformed files raise ValueError like the Python reader does."""
     from . import _capi as capi
+    if fused is None:
+        fused = os.environ.get("GDMIX_INGEST_FUSED", "1") != "0"
     # Two passes over the partition's files, each file on its own thread (the parser is native code: the calls release
     # the GIL): count, then fill straight into the partition-wide arrays -- no per-file arrays, no concatenation.
     # Uncompressed files are memory-mapped; compressed ones are inflated first.
@@ -124,10 +141,17 @@ def _read_entity_grouped_native(files, entity_name, feature_bag, label_column, o
         Z = sum(sz.nnz for _, sz in counted)
         # what the device calls upload afterwards (values, labels, offsets, weights) is parsed straight into
         # page-locked memory of the library's pool; the global column ids and uids stay on the host
+        # Fused (default): an entity's indices are ranked among its distinct ones while the reader still has them in
+        # cache (np.unique per entity, job_consumers.py:243) -- the int64 global columns are never written or re-read.
         pin = capi.pinned_empty
-        out = {"ent_rows": np.empty(E, np.int64), "row_len": np.empty(N, np.int64), "gcol": np.empty(Z, np.int64),
+        out = {"ent_rows": np.empty(E, np.int64), "row_len": np.empty(N, np.int64),
                "val": pin(Z, np.float32), "uid": np.empty(N, np.int64), "label": pin(N, np.float32),
                "offset": pin(N, np.float32), "weight": pin(N, np.float32)}
+        if fused:
+            out.update({"local16": pin(Z, np.uint16), "d_e": np.zeros(max(E, 1), np.int64),
+                        "uniq_scratch": np.empty(max(Z, 1), np.int64)})
+        else:
+            out["gcol"] = np.empty(Z, np.int64)
         starts, e0, r0, q0 = [], 0, 0, 0
         for _, sz in counted:
             starts.append((e0, r0, q0))
@@ -137,13 +161,19 @@ def _read_entity_grouped_native(files, entity_name, feature_bag, label_column, o
             buf, sz = counted[k]
             idc, idp = np.zeros(max(sz.id_bytes, 1), np.uint8), np.zeros(sz.n_entities + 1, np.int64)
             try:
-                rng = capi.seqex_fill_into(buf, spec, out, *starts[k], idc, idp)
+                rng = (capi.seqex_fill_local_into if fused else capi.seqex_fill_into)(buf, spec, out, *starts[k], idc, idp)
             except capi.GdmixError as ex:
+                if fused and ex.code == capi.GDMIX_ERR_TOO_LARGE:
+                    return None, None
                 raise ValueError(f"{files[k]}: {ex}") from None
             raw = idc.tobytes()
             return [raw[idp[e]:idp[e + 1]].decode("utf-8") for e in range(sz.n_entities)], rng
 
         filled = list(pool.map(fill, range(len(files))))
+        if any(f[0] is None for f in filled):
+            # an entity with more than 65535 distinct features: the unfused reader + gdmix_local_index_host
+            return _read_entity_grouped_native(files, entity_name, feature_bag, label_column, offset_column,
+                                               weight_column, uid_column, num_features, input_path, fused=False)
         ids = [f[0] for f in filled]
         ranges = [f[1] for f, (_, sz) in zip(filled, counted) if sz.nnz]
     all_labelled = all(sz.all_labelled for _, sz in counted)
@@ -160,7 +190,13 @@ def _read_entity_grouped_native(files, entity_name, feature_bag, label_column, o
     d.rowptr = capi.pinned_empty(N + 1, np.int64)
     d.rowptr[0] = 0
     np.cumsum(out["row_len"], out=d.rowptr[1:])
-    d.gcol, d.val = out["gcol"], out["val"]
+    d.val = out["val"]
+    if fused:
+        d._gcol = None
+        d.local16 = out["local16"]
+        d.uniq_ptr, d.uniq_global = capi.local_index_gather(d.ent_rowptr, d.rowptr, out["d_e"][:E], out["uniq_scratch"])
+    else:
+        d.gcol = out["gcol"]
     d.uid, d.offset, d.weight = out["uid"], out["offset"], out["weight"]
     d.label = out["label"] if (files and all_labelled and label_column is not None) else None
     for mm in keep:
@@ -168,7 +204,7 @@ def _read_entity_grouped_native(files, entity_name, feature_bag, label_column, o
             mm.close()
         except BufferError:      # a numpy view is still alive somewhere: the mapping goes with it
             pass
-    if d.gcol.size and (index_lo < 0 or index_hi >= d.num_features):
+    if Z and (index_lo < 0 or index_hi >= d.num_features):
         raise ValueError(f"feature index outside [0, {d.num_features}) in {input_path}")
     return d
 
@@ -250,10 +286,16 @@ def to_local_batch(data, has_intercept=True):
     """np.unique per entity (job_consumers.py:243) for the whole partition, by the library (all host threads).
     -> (HostBatch with entity-local columns, uniq_ptr int64[E+1], uniq_global int64[sum d_e])"""
     from . import _capi as capi
-    local, d_e, uniq_ptr, uniq_global = capi.local_index_host(data.ent_rowptr, data.rowptr, data.gcol)
     hi = 1 if has_intercept else 0
-    theta_ptr = np.concatenate([[0], np.cumsum(d_e + hi)]).astype(np.int64)
     label = data.label if data.label is not None else np.zeros(data.n_rows, np.float32)
+    if data.local16 is not None:      # the fused reader ranked the indices already
+        uniq_ptr, uniq_global = data.uniq_ptr, data.uniq_global
+        theta_ptr = uniq_ptr + hi * np.arange(uniq_ptr.shape[0], dtype=np.int64)
+        hb = HostBatch(data.ent_rowptr, data.rowptr, None, data.val, label, data.weight, data.offset, theta_ptr,
+                       has_intercept, col_narrow=data.local16)
+        return hb, uniq_ptr, uniq_global
+    local, d_e, uniq_ptr, uniq_global = capi.local_index_host(data.ent_rowptr, data.rowptr, data.gcol)
+    theta_ptr = np.concatenate([[0], np.cumsum(d_e + hi)]).astype(np.int64)
     hb = HostBatch(data.ent_rowptr, data.rowptr, local, data.val, label, data.weight, data.offset, theta_ptr,
                    has_intercept)
     return hb, uniq_ptr, uniq_global

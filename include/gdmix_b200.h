@@ -356,6 +356,15 @@ GDMIX_API int gdmix_seqex_count(const uint8_t *file_image, int64_t len, const gd
 GDMIX_API int gdmix_seqex_fill(const uint8_t *file_image, int64_t len, const gdmix_seqex_spec *spec, int64_t *ent_rows,
                                int64_t *row_len, int64_t *gcol, float *val, int64_t *uid, float *label, float *offset,
                                float *weight, char *id_chars, int64_t *id_ptr, int64_t *index_range);
+/* gdmix_seqex_fill with the entity-local indexing of gdmix_local_index_host fused into it (an entity's indices are
+ * ranked while they are still in cache, and the int64 global columns are never written): local16[nnz] = rank of every
+ * index among its entity's distinct indices, d_e[E] their number, uniq_scratch[nnz] = the sorted distinct indices of
+ * every entity parked at its first non-zero (gather them with gdmix_local_index_host's second call).
+ * GDMIX_ERR_TOO_LARGE when an entity has more than 65535 distinct features: use the two separate calls. */
+GDMIX_API int gdmix_seqex_fill_local(const uint8_t *file_image, int64_t len, const gdmix_seqex_spec *spec,
+                                     int64_t *ent_rows, int64_t *row_len, uint16_t *local16, int64_t *d_e,
+                                     int64_t *uniq_scratch, float *val, int64_t *uid, float *label, float *offset,
+                                     float *weight, char *id_chars, int64_t *id_ptr, int64_t *index_range);
 
 /* Entity-local feature indexing of a parsed partition on the host (np.unique(cols, return_inverse=True) per entity,
  * job_consumers.py:243), all host threads.  Two calls: uniq_global == NULL -> local_col[nnz], d_e[E] and the distinct

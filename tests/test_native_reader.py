@@ -502,3 +502,73 @@ def test_native_partition_writer_matches_the_python_encoder(tmp_path, string_ids
     path = tmp_path / "nobag.tfrecord"
     path.write_bytes(img)
     assert sum(1 for _ in T.read_records(str(path), verify_crc=True)) == E
+
+
+def _partition_file(tmp_path, rng, E, max_rows, max_len, id_range, name="part-00000.tfrecord", wide_entity=None):
+    ent_rows = rng.integers(1, max_rows + 1, E)
+    N = int(ent_rows.sum())
+    row_len = rng.integers(0, max_len + 1, N)
+    if wide_entity is not None:            # (entity, distinct features): that entity gets one long row
+        e, width = wide_entity
+        row_len[int(ent_rows[:e].sum())] = width
+    nnz = int(row_len.sum())
+    gcol = rng.integers(0, id_range, nnz)
+    if wide_entity is not None:
+        r = int(ent_rows[:wide_entity[0]].sum())
+        q = int(row_len[:r].sum())
+        gcol[q:q + wide_entity[1]] = rng.permutation(id_range)[:wide_entity[1]]
+    val = rng.standard_normal(nnz).astype(np.float32)
+    img = capi.encode_entity_grouped(ent_rows, row_len, gcol, val, np.arange(N, dtype=np.int64),
+                                     entity_int=np.arange(E, dtype=np.int64), label=rng.integers(0, 2, N).astype(np.float32),
+                                     offset=rng.standard_normal(N).astype(np.float32), entity="ent", bag="bag",
+                                     label_name="y", offset_name="off")
+    with open(str(tmp_path / name), "wb") as f:
+        f.write(img.tobytes())
+    return ent_rows, row_len, gcol, val
+
+
+@pytest.mark.parametrize("shape", [(200, 6, 12, 50), (60, 40, 30, 5000), (30, 3, 0, 10)])
+def test_fused_reader_equals_reader_plus_local_index(tmp_path, shape):
+    """gdmix_seqex_fill_local (entity-local ranks while parsing) against gdmix_seqex_fill + gdmix_local_index_host and
+    against np.unique per entity (job_consumers.py:243): same local indices, same distinct features, same batch."""
+    E, max_rows, max_len, id_range = shape
+    rng = np.random.default_rng(E)
+    for k in range(3):
+        _partition_file(tmp_path, rng, E, max_rows, max_len, id_range, name=f"part-{k:05d}.tfrecord")
+    files = ingest.list_tfrecord_files(str(tmp_path), 1, 0)
+    args = (files, "ent", "bag", "y", "off", "w", "uid", id_range, str(tmp_path))
+    fused = ingest._read_entity_grouped_native(*args, fused=True)
+    plain = ingest._read_entity_grouped_native(*args, fused=False)
+    assert fused.local16 is not None and plain.local16 is None
+    hb_f, up_f, ug_f = ingest.to_local_batch(fused)
+    hb_p, up_p, ug_p = ingest.to_local_batch(plain)
+    np.testing.assert_array_equal(up_f, up_p)
+    np.testing.assert_array_equal(ug_f, ug_p)
+    np.testing.assert_array_equal(hb_f.theta_ptr, hb_p.theta_ptr)
+    np.testing.assert_array_equal(hb_f._col_narrow.astype(np.int32), hb_p.col[:hb_p.nnz])
+    np.testing.assert_array_equal(fused.gcol, plain.gcol)          # rebuilt from ranks + distinct features
+    for name in ("ent_rowptr", "rowptr", "val", "label", "offset", "weight", "uid"):
+        np.testing.assert_array_equal(getattr(fused, name), getattr(plain, name))
+    assert fused.entity_ids == plain.entity_ids
+    for e in range(0, 3 * E, 7):
+        q0, q1 = plain.rowptr[plain.ent_rowptr[e]], plain.rowptr[plain.ent_rowptr[e + 1]]
+        u, inv = np.unique(plain.gcol[q0:q1], return_inverse=True)
+        np.testing.assert_array_equal(u, ug_f[up_f[e]:up_f[e + 1]])
+        np.testing.assert_array_equal(inv, hb_f._col_narrow[q0:q1])
+    cb = hb_f.c_struct()
+    assert cb.col16 is not None and cb.col is None and cb.col8 is None
+
+
+def test_fused_reader_falls_back_beyond_65535_distinct_features(tmp_path):
+    """An entity with more distinct features than 16-bit local indices can name: the reader goes back to int64
+    columns + gdmix_local_index_host, and an out-of-range index is still refused."""
+    rng = np.random.default_rng(2)
+    _partition_file(tmp_path, rng, 5, 2, 4, 200000, wide_entity=(3, 70000))
+    kw = dict(metadata=_Meta(["ent"]), entity_name="ent", feature_bag="bag", label_column="y", offset_column="off",
+              weight_column="w", uid_column="uid", num_features=200000)
+    d = ingest.read_entity_grouped(str(tmp_path), **kw)
+    assert d.local16 is None and d.n_entities == 5
+    hb, up, ug = ingest.to_local_batch(d)
+    assert int(np.diff(up).max()) >= 70000
+    with pytest.raises(ValueError):
+        ingest.read_entity_grouped(str(tmp_path), **dict(kw, num_features=1000))
