@@ -39,7 +39,7 @@ SYMBOLS = ["gdmix_last_error", "gdmix_version", "gdmix_device_info", "gdmix_re_w
            "gdmix_fe_lbfgs_destroy", "gdmix_fe_column_counts", "gdmix_remap_i32", "gdmix_group_ids", "gdmix_offset_join", "gdmix_seqex_encode", "gdmix_local_index_host", "gdmix_fe_tile_plan_create",
            "gdmix_fe_tile_plan_destroy", "gdmix_fe_tile_plan_info", "gdmix_fe_loss_grad_tiled",
            "gdmix_pinned_alloc", "gdmix_pinned_free", "gdmix_narrow_columns", "gdmix_selftest_logistic",
-           "gdmix_seqex_fill_local"]
+           "gdmix_seqex_fill_local", "gdmix_avro_model_blocks_alloc", "gdmix_buffer_free"]
 
 
 class SeqexSpec(C.Structure):
@@ -687,6 +687,20 @@ class _PinnedBlock:
             pass
 
 
+class _LibBuffer:
+    """Owner of a malloc'ed buffer the library returned (gdmix_buffer_free when collected), as a uint8 array."""
+
+    def __init__(self, ptr, n):
+        self.ptr = ptr
+        self.__array_interface__ = {"data": (ptr, False), "shape": (int(n),), "typestr": "|u1", "version": 3}
+
+    def __del__(self):
+        try:
+            lib.gdmix_buffer_free(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
 def pinned_empty(n, dtype):
     """np.empty(n, dtype) in page-locked memory of the library's pool (plain np.empty when there is no CUDA device:
     the readers are host code and are used without one)."""
@@ -905,14 +919,11 @@ def avro_model_blocks(model_ids, coef, var, coef_ptr, feat_idx, has_intercept, t
                    intercept_name.encode("utf-8"), _np_ptr(nc), _np_ptr(npt), _np_ptr(tc), _np_ptr(tpt), len(feature_names))
     sync_arr = np.frombuffer(bytes(sync), dtype=np.uint8)
     assert sync_arr.size == 16
-    need = C.c_int64()
-    check(lib.gdmix_avro_model_blocks(C.byref(t), C.c_int32(records_per_block), _np_ptr(sync_arr), None, C.c_int64(0),
-                                      C.byref(need)))
-    out = np.empty(max(need.value, 1), np.uint8)
-    written = C.c_int64()
-    check(lib.gdmix_avro_model_blocks(C.byref(t), C.c_int32(records_per_block), _np_ptr(sync_arr), _np_ptr(out),
-                                      C.c_int64(out.size), C.byref(written)))
-    return memoryview(out)[:written.value]      # no copy: the caller writes it to the file
+    ptr, written = C.c_void_p(), C.c_int64()
+    check(lib.gdmix_avro_model_blocks_alloc(C.byref(t), C.c_int32(records_per_block), _np_ptr(sync_arr), C.byref(ptr),
+                                            C.byref(written)))
+    # no copy: a view of the library's buffer (freed when the view's owner is collected); the caller writes it out
+    return memoryview(np.asarray(_LibBuffer(ptr.value, written.value)))
 
 
 class FeatureMap:

@@ -2017,8 +2017,8 @@ int gdmix_avro_score_blocks(const int64_t *uid, const float *score, const float 
     return GDMIX_OK;
 }
 
-int gdmix_avro_model_blocks(const gdmix_model_table *t, int32_t records_per_block, const uint8_t *sync16, uint8_t *out,
-                            int64_t capacity, int64_t *written)
+static int model_blocks_impl(const gdmix_model_table *t, int32_t records_per_block, const uint8_t *sync16, uint8_t *out,
+                             int64_t capacity, int64_t *written, uint8_t **alloc_out)
 {
     if (!t || !written || records_per_block <= 0 || !sync16 || t->n_models < 0 ||
         (t->n_models > 0 && (!t->id_chars || !t->id_ptr || !t->model_class || !t->coef || !t->coef_ptr || !t->intercept_name)))
@@ -2029,13 +2029,40 @@ int gdmix_avro_model_blocks(const gdmix_model_table *t, int32_t records_per_bloc
     m.has_intercept = t->has_intercept; m.threshold = t->threshold; m.intercept_name = t->intercept_name;
     m.name_chars = t->name_chars; m.name_ptr = t->name_ptr; m.term_chars = t->term_chars; m.term_ptr = t->term_ptr;
     m.n_features = t->n_features;
-    const int64_t need = gdmix_host::avro_model_blocks(m, records_per_block, sync16, nullptr);
+    std::vector<int64_t> start, body;
+    const int64_t need = gdmix_host::avro_model_sizes(m, records_per_block, start, body);
     if (need < 0) return fail(GDMIX_ERR_INVALID, "model table is inconsistent (coefficient slices / feature indices)");
+    if (alloc_out) {
+        // one sizing pass, one writing pass, into a buffer of the library's (gdmix_buffer_free)
+        uint8_t *buf = (uint8_t *)malloc((size_t)std::max<int64_t>(need, 1));
+        if (!buf) return fail(GDMIX_ERR_INVALID, "out of host memory for %lld bytes of model records", (long long)need);
+        gdmix_host::avro_model_write(m, records_per_block, sync16, start, body, buf);
+        *alloc_out = buf;
+        *written = need;
+        return GDMIX_OK;
+    }
     if (!out) { *written = need; return GDMIX_OK; }
     if (capacity < need) return fail(GDMIX_ERR_WORKSPACE, "output buffer %lld B < required %lld B", (long long)capacity, (long long)need);
-    *written = gdmix_host::avro_model_blocks(m, records_per_block, sync16, out);
+    gdmix_host::avro_model_write(m, records_per_block, sync16, start, body, out);
+    *written = need;
     return GDMIX_OK;
 }
+
+int gdmix_avro_model_blocks(const gdmix_model_table *t, int32_t records_per_block, const uint8_t *sync16, uint8_t *out,
+                            int64_t capacity, int64_t *written)
+{
+    return model_blocks_impl(t, records_per_block, sync16, out, capacity, written, nullptr);
+}
+
+int gdmix_avro_model_blocks_alloc(const gdmix_model_table *t, int32_t records_per_block, const uint8_t *sync16,
+                                  uint8_t **out, int64_t *written)
+{
+    if (!out) return fail(GDMIX_ERR_INVALID, "bad argument to gdmix_avro_model_blocks_alloc");
+    *out = nullptr;
+    return model_blocks_impl(t, records_per_block, sync16, nullptr, 0, written, out);
+}
+
+void gdmix_buffer_free(void *ptr) { free(ptr); }
 
 struct gdmix_feature_map { gdmix_host::FeatureMap fm; };
 

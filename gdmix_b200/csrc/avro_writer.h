@@ -155,12 +155,14 @@ inline bool avro_one_model(const ModelTable &t, int64_t m, Sink &o)
     return true;
 }
 
-// blocks of `per_block` records; out == nullptr: returns the bytes needed.  -1: inconsistent input.
-// Blocks are sized, then written, by all host threads (a block's bytes depend on nothing outside it).
-inline int64_t avro_model_blocks(const ModelTable &t, int32_t per_block, const uint8_t *sync, uint8_t *out)
+// Blocks of `per_block` records, sized (avro_model_sizes: start[b] = first byte of block b, start[nb] = total; -1:
+// inconsistent input) and then written (avro_model_write) by all host threads -- a block's bytes depend on nothing
+// outside it.
+inline int64_t avro_model_sizes(const ModelTable &t, int32_t per_block, std::vector<int64_t> &start, std::vector<int64_t> &body)
 {
     const int64_t nb = (t.n_models + per_block - 1) / per_block;
-    std::vector<int64_t> body((size_t)nb, 0), start((size_t)nb + 1, 0);
+    body.assign((size_t)nb, 0);
+    start.assign((size_t)nb + 1, 0);
     int bad = 0;
 #pragma omp parallel for schedule(dynamic, 4) reduction(| : bad)
     for (int64_t b = 0; b < nb; b++) {
@@ -179,7 +181,13 @@ inline int64_t avro_model_blocks(const ModelTable &t, int32_t per_block, const u
         hdr.lng(cnt); hdr.lng(body[(size_t)b]);
         start[(size_t)b + 1] = start[(size_t)b] + hdr.n + body[(size_t)b] + 16;
     }
-    if (!out) return start[(size_t)nb];
+    return start[(size_t)nb];
+}
+
+inline void avro_model_write(const ModelTable &t, int32_t per_block, const uint8_t *sync, const std::vector<int64_t> &start,
+                             const std::vector<int64_t> &body, uint8_t *out)
+{
+    const int64_t nb = (int64_t)body.size();
 #pragma omp parallel for schedule(dynamic, 4)
     for (int64_t b = 0; b < nb; b++) {
         const int64_t b0 = b * per_block;
@@ -190,7 +198,6 @@ inline int64_t avro_model_blocks(const ModelTable &t, int32_t per_block, const u
         for (int64_t m = b0; m < b0 + cnt; m++) avro_one_model(t, m, o);
         o.raw(sync, 16);
     }
-    return start[(size_t)nb];
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -424,6 +424,11 @@ typedef struct gdmix_model_table {
 } gdmix_model_table;
 GDMIX_API int gdmix_avro_model_blocks(const gdmix_model_table *table, int32_t records_per_block, const uint8_t *sync16,
                                       uint8_t *out, int64_t capacity, int64_t *written);
+/* The same records into a buffer the library allocates to the exact size (one sizing pass and one writing pass
+ * instead of a sizing call plus a writing call that sizes again): *out is released with gdmix_buffer_free. */
+GDMIX_API int gdmix_avro_model_blocks_alloc(const gdmix_model_table *table, int32_t records_per_block,
+                                            const uint8_t *sync16, uint8_t **out, int64_t *written);
+GDMIX_API void gdmix_buffer_free(void *ptr);
 
 /* Reading model files back (warm starts, the predict action; io_utils.py:163-212 / _load_weights,
  * random_effect_lr_lbfgs_model.py:262-309): the records of ONE container block (uncompressed) -> flat arrays.
