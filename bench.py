@@ -477,7 +477,12 @@ def run_ours(args):
     # local column indices cross PCIe as one byte each (every entity has 256 local features: gdmix_re_batch.col8)
     # and are widened on the device
     h_col = pinned(data["col"][:nnz_e].to(torch.uint8)); h_val = pinned(data["val"][:nnz_e])
-    h_lab = pinned(data["label"][:rows_e]); h_off = pinned(data["offset"][:rows_e])
+    h_off = pinned(data["offset"][:rows_e])
+    # row lengths cross as 16 bits (the row pointers are rebuilt on the device by a scan; the host copy only cuts the
+    # chunks) and the 0/1 labels as bits: gdmix_re_batch.row_len16 / label_bits
+    h_len = pinned((data["rowptr"][1:rows_e + 1] - data["rowptr"][:rows_e]).to(torch.uint16))
+    lab_np = (data["label"][:rows_e] != 0).cpu().numpy()
+    h_bits = pinned(torch.from_numpy(np.concatenate([np.packbits(lab_np, bitorder="little"), np.zeros(1, np.uint8)])))
     h_tp = pinned(data["theta_ptr"][:Ee + 1])
     h_theta = torch.empty(coef_e, dtype=torch.float64, pin_memory=True)
     h_f = torch.empty(Ee, dtype=torch.float64, pin_memory=True)
@@ -485,8 +490,8 @@ def run_ours(args):
     h_nfev = torch.empty(Ee, dtype=torch.int32, pin_memory=True)
     h_st = torch.empty(Ee, dtype=torch.int32, pin_memory=True)
     hcb = capi.ReBatch(Ee, rows_e, nnz_e, h_ent.data_ptr(), h_row.data_ptr(), None, h_val.data_ptr(),
-                       h_lab.data_ptr(), None, h_off.data_ptr(), h_tp.data_ptr(), w["n"], w["n"] * w["k"],
-                       w["d"] + 1, 0, None, h_col.data_ptr())
+                       None, None, h_off.data_ptr(), h_tp.data_ptr(), w["n"], w["n"] * w["k"],
+                       w["d"] + 1, 0, None, h_col.data_ptr(), h_len.data_ptr(), h_bits.data_ptr())
 
     def e2e_step():
         capi.check(capi.lib.gdmix_re_fit_host(C.byref(hcb), C.byref(opts), None, C.c_void_p(h_theta.data_ptr()),
@@ -502,11 +507,12 @@ def run_ours(args):
         e2e_step()  # synchronous: returns with the results in host memory
     torch.cuda.synchronize()
     dt = max_over_ranks(time.perf_counter() - t1)
-    h2d = 8 * (Ee + 1) * 2 + 8 * (rows_e + 1) + 5 * nnz_e + 8 * rows_e
+    h2d = 8 * (Ee + 1) * 2 + 2 * rows_e + 5 * nnz_e + 4 * rows_e + (rows_e + 7) // 8
     d2h = 8 * coef_e + 8 * Ee + 12 * Ee
     e2e = {"value": world * Ee * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "entities_per_step": Ee, "steps": e2e_steps,
-           "api": "gdmix_re_fit_host (pinned host CSR in -- fp32 values, uint8 local columns -- host coefficients out)",
+           "api": "gdmix_re_fit_host (pinned host CSR in -- fp32 values, uint8 local columns, uint16 row lengths, labels as "
+                  "bits -- host coefficients out)",
            "host_theta_checksum": float(h_theta.sum().item())}
     capi.lib.gdmix_host_release()
     # what the box can copy: pinned host -> device, all ranks at once (the ceiling of any host-buffer API on it)
@@ -534,7 +540,7 @@ def run_ours(args):
         min_over_ranks(0.0)
 
     # ---- the other configurations (not part of the headline's timed region) -----------------------------------
-    del data, theta, f, nit, nfev, status, ws, h_ent, h_row, h_col, h_val, h_lab, h_off, h_tp, h_theta
+    del data, theta, f, nit, nfev, status, ws, h_ent, h_row, h_col, h_val, h_len, h_bits, h_off, h_tp, h_theta
     torch.cuda.empty_cache()
     sub = {}
     if not args.no_sub:

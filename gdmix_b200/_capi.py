@@ -70,7 +70,7 @@ class ReBatch(C.Structure):
                 ("ent_rowptr", C.c_void_p), ("rowptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p),
                 ("label", C.c_void_p), ("weight", C.c_void_p), ("offset", C.c_void_p), ("theta_ptr", C.c_void_p),
                 ("max_rows", C.c_int32), ("max_nnz", C.c_int32), ("max_coef", C.c_int32), ("reserved", C.c_int32),
-                ("col16", C.c_void_p), ("col8", C.c_void_p)]
+                ("col16", C.c_void_p), ("col8", C.c_void_p), ("row_len16", C.c_void_p), ("label_bits", C.c_void_p)]
 
 
 class LrOpts(C.Structure):
@@ -232,10 +232,29 @@ class HostBatch:
                     self._col_narrow = narrow_columns(self.col[:self.nnz], 2)
             c8 = self._col_narrow if self._col_narrow.dtype == np.uint8 else None
             c16 = self._col_narrow if c8 is None else None
+        rl16 = bits = None
+        if narrow and self.n_rows > 0:
+            # what else gdmix_re_fit_host can take narrow: 16-bit row lengths instead of the int64 row pointers
+            # (-6 bytes per row on PCIe) and the 0/1 labels as bits (-3.9 bytes per row)
+            if getattr(self, "_rows_narrow", None) is None:
+                lens = np.diff(self.rowptr)
+                r16 = None
+                if lens.size and int(lens.max()) <= 65535:
+                    r16 = pinned_empty(lens.shape[0], np.uint16)
+                    r16[:] = lens
+                lab = self.label
+                b = None
+                if lab is not None and bool(np.all((lab == 0) | (lab == 1))):
+                    packed = np.packbits(lab != 0, bitorder="little")
+                    b = pinned_empty(packed.shape[0] + 1, np.uint8)
+                    b[:packed.shape[0]] = packed
+                    b[packed.shape[0]:] = 0
+                self._rows_narrow = (r16, b)
+            rl16, bits = self._rows_narrow
         return ReBatch(self.n_entities, self.n_rows, self.nnz, _np_ptr(self.ent_rowptr), _np_ptr(self.rowptr),
                        _np_ptr(self.col), _np_ptr(self.val), _np_ptr(self.label), _np_ptr(self.weight),
                        _np_ptr(self.offset), _np_ptr(self.theta_ptr), self.max_rows, self.max_nnz, self.max_coef, 0,
-                       _np_ptr(c16), _np_ptr(c8))
+                       _np_ptr(c16), _np_ptr(c8), _np_ptr(rl16), _np_ptr(bits))
 
     def algorithmic_bytes(self, warm=False):
         """8 B/nnz + 16 B/sample + 8 B/coef out (+8 in when warm) + 4 B/feature index map."""

@@ -789,13 +789,15 @@ inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 // Carves a chunk's device image: inputs first, outputs after.  Returns total bytes.
 struct ChunkImage {
     size_t ent_rowptr, rowptr, col, col16, val, label, weight, offset, theta_ptr, theta0;  // inputs
+    size_t len16, len32, scan_ws, label_bits;   // narrow row lengths / label bits and what rebuilds them
     size_t in_bytes;
     size_t theta, f, nit, nfev, status, var;  // outputs
     size_t total;
 };
 
 ChunkImage chunk_image(int64_t ne, int64_t nr, int64_t nz, int64_t nt, bool has_w, bool has_off, bool warm,
-                       bool want_var, int narrow_col = 0 /* bytes per index crossing PCIe: 0 (= 4), 2 or 1 */)
+                       bool want_var, int narrow_col = 0 /* bytes per index crossing PCIe: 0 (= 4), 2 or 1 */,
+                       bool narrow_rows = false, bool bit_labels = false)
 {
     ChunkImage c;
     size_t o = 0;
@@ -809,6 +811,11 @@ ChunkImage chunk_image(int64_t ne, int64_t nr, int64_t nz, int64_t nt, bool has_
     c.weight = o; o += has_w ? up256(4 * nr) : 0;
     c.offset = o; o += has_off ? up256(4 * nr) : 0;
     c.theta0 = o; o += warm ? up256(8 * nt) : 0;
+    c.len16 = o; o += narrow_rows ? up256(2 * nr) : 0;
+    c.len32 = o; o += narrow_rows ? up256(4 * nr) : 0;
+    // scan workspace: u32 tile sums + int64 tile offsets + total, tiles of 4096 rows
+    c.scan_ws = o; o += narrow_rows ? up256(4 * (nr / 4096 + 2)) + up256(8 * (nr / 4096 + 3)) + 256 : 0;
+    c.label_bits = o; o += bit_labels ? up256(nr / 8 + 2) : 0;
     c.in_bytes = o;
     c.theta = o; o += up256(8 * nt);
     c.f = o; o += up256(8 * ne);
@@ -1030,6 +1037,8 @@ int gdmix_fe_score(const gdmix_fe_rows *rows, const gdmix_lr_opts *o, const doub
 }
 
 // ---- host-buffer entry points --------------------------------------------------------------------
+int exclusive_scan_u32(const uint32_t *len, int64_t n, int64_t *out, void *ws, cudaStream_t st);   // defined below
+
 
 int gdmix_re_fit_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const double *theta0, double *theta_out,
                       double *f_out, int32_t *nit, int32_t *nfev, int32_t *status, double *var_out,
@@ -1038,7 +1047,7 @@ int gdmix_re_fit_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const do
     if (!hb || !o || !theta_out) return fail(GDMIX_ERR_INVALID, "null argument");
     const int64_t E = hb->n_entities;
     if (E <= 0) return GDMIX_OK;
-    if (!hb->ent_rowptr || !hb->rowptr || !hb->label || !hb->theta_ptr)
+    if (!hb->ent_rowptr || !hb->rowptr || (!hb->label && !hb->label_bits) || !hb->theta_ptr)
         return fail(GDMIX_ERR_INVALID, "null array in gdmix_re_batch");
     if (hb->nnz > 0 && !hb->col && !hb->col16 && !hb->col8)
         return fail(GDMIX_ERR_INVALID, "gdmix_re_batch needs col, col16 or col8");
@@ -1098,43 +1107,62 @@ int gdmix_re_fit_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const do
         size_t ws_bytes = 0;
         int rc = gdmix_re_workspace_size(&db, o, &ws_bytes);
         if (rc) return rc;
+        const bool narrow_rows = hb->row_len16 != nullptr, bit_labels = hb->label_bits != nullptr;
         const ChunkImage img = chunk_image(ne, nr, nz, nt, hb->weight != nullptr, hb->offset != nullptr,
-                                           theta0 != nullptr, want_var, narrow);
+                                           theta0 != nullptr, want_var, narrow, narrow_rows, bit_labels);
         rc = ensure(s, img.total, 0, ws_bytes);
         if (rc) return rc;
         char *dv = (char *)s.dev;
         const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
+        // Every copy of the chunk first, then the small kernels that expand what crossed narrow: a kernel in between
+        // would hold the copies behind it on this stream until it finds an SM free of the previous chunk's solve.
         CUDA_TRY(cudaMemcpyAsync(dv + img.ent_rowptr, hb->ent_rowptr + e0, 8 * (ne + 1), H2D, s.st));
-        CUDA_TRY(cudaMemcpyAsync(dv + img.rowptr, hb->rowptr + r0, 8 * (nr + 1), H2D, s.st));
+        if (narrow_rows) CUDA_TRY(cudaMemcpyAsync(dv + img.len16, hb->row_len16 + r0, 2 * nr, H2D, s.st));
+        else CUDA_TRY(cudaMemcpyAsync(dv + img.rowptr, hb->rowptr + r0, 8 * (nr + 1), H2D, s.st));
         CUDA_TRY(cudaMemcpyAsync(dv + img.theta_ptr, hb->theta_ptr + e0, 8 * (ne + 1), H2D, s.st));
         if (nz) {
-            if (narrow == 1) {
-                CUDA_TRY(cudaMemcpyAsync(dv + img.col16, hb->col8 + q0, nz, H2D, s.st));
-                gdmix::widen_u8_kernel<<<(int)std::min<int64_t>((nz / 16 + 255) / 256 + 1, 148 * 8), 256, 0, s.st>>>(
-                    (const uint8_t *)(dv + img.col16), (int32_t *)(dv + img.col), nz);
-                g_launches++;
-            } else if (narrow == 2) {
-                CUDA_TRY(cudaMemcpyAsync(dv + img.col16, hb->col16 + q0, 2 * nz, H2D, s.st));
-                gdmix::widen_u16_kernel<<<(int)std::min<int64_t>((nz + 255) / 256, 148 * 8), 256, 0, s.st>>>(
-                    (const uint16_t *)(dv + img.col16), (int32_t *)(dv + img.col), nz);
-                g_launches++;
-            } else {
-                CUDA_TRY(cudaMemcpyAsync(dv + img.col, hb->col + q0, 4 * nz, H2D, s.st));
-            }
+            if (narrow == 1) CUDA_TRY(cudaMemcpyAsync(dv + img.col16, hb->col8 + q0, nz, H2D, s.st));
+            else if (narrow == 2) CUDA_TRY(cudaMemcpyAsync(dv + img.col16, hb->col16 + q0, 2 * nz, H2D, s.st));
+            else CUDA_TRY(cudaMemcpyAsync(dv + img.col, hb->col + q0, 4 * nz, H2D, s.st));
             CUDA_TRY(cudaMemcpyAsync(dv + img.val, hb->val + q0, 4 * nz, H2D, s.st));
         }
-        CUDA_TRY(cudaMemcpyAsync(dv + img.label, hb->label + r0, 4 * nr, H2D, s.st));
+        const int64_t lb0 = r0 >> 3, lb1 = (r1 + 7) >> 3;
+        if (bit_labels) CUDA_TRY(cudaMemcpyAsync(dv + img.label_bits, hb->label_bits + lb0, (size_t)(lb1 - lb0), H2D, s.st));
+        else CUDA_TRY(cudaMemcpyAsync(dv + img.label, hb->label + r0, 4 * nr, H2D, s.st));
         if (hb->weight) CUDA_TRY(cudaMemcpyAsync(dv + img.weight, hb->weight + r0, 4 * nr, H2D, s.st));
         if (hb->offset) CUDA_TRY(cudaMemcpyAsync(dv + img.offset, hb->offset + r0, 4 * nr, H2D, s.st));
         if (theta0) CUDA_TRY(cudaMemcpyAsync(dv + img.theta0, theta0 + t0, 8 * nt, H2D, s.st));
+        if (narrow_rows) {
+            // 2 bytes per row crossed PCIe; the chunk's row pointers (counted from its own first non-zero) come from a scan
+            gdmix::widen_len16_kernel<<<(int)std::min<int64_t>((nr + 255) / 256, 148 * 8), 256, 0, s.st>>>(
+                (const uint16_t *)(dv + img.len16), (uint32_t *)(dv + img.len32), nr);
+            g_launches++;
+            rc = exclusive_scan_u32((const uint32_t *)(dv + img.len32), nr, (int64_t *)(dv + img.rowptr), dv + img.scan_ws, s.st);
+            if (rc) return rc;
+        }
+        if (nz && narrow == 1) {
+            gdmix::widen_u8_kernel<<<(int)std::min<int64_t>((nz / 16 + 255) / 256 + 1, 148 * 8), 256, 0, s.st>>>(
+                (const uint8_t *)(dv + img.col16), (int32_t *)(dv + img.col), nz);
+            g_launches++;
+        } else if (nz && narrow == 2) {
+            gdmix::widen_u16_kernel<<<(int)std::min<int64_t>((nz + 255) / 256, 148 * 8), 256, 0, s.st>>>(
+                (const uint16_t *)(dv + img.col16), (int32_t *)(dv + img.col), nz);
+            g_launches++;
+        }
+        if (bit_labels) {
+            gdmix::label_from_bits_kernel<<<(int)std::min<int64_t>((nr + 255) / 256, 148 * 8), 256, 0, s.st>>>(
+                (const uint8_t *)(dv + img.label_bits), (int)(r0 & 7), (float *)(dv + img.label), nr);
+            g_launches++;
+        }
         db.ent_rowptr = (const int64_t *)(dv + img.ent_rowptr);            // indexed by local entity
         db.theta_ptr = (const int64_t *)(dv + img.theta_ptr);
         db.rowptr = (const int64_t *)(dv + img.rowptr) - r0;               // indexed by absolute row
         db.label = (const float *)(dv + img.label) - r0;
         db.weight = hb->weight ? (const float *)(dv + img.weight) - r0 : nullptr;
         db.offset = hb->offset ? (const float *)(dv + img.offset) - r0 : nullptr;
-        db.col = (const int32_t *)(dv + img.col) - q0;                     // indexed by absolute non-zero
-        db.val = (const float *)(dv + img.val) - q0;
+        db.col = (const int32_t *)(dv + img.col) - (narrow_rows ? 0 : q0);  // indexed by the row pointers' non-zero numbers:
+        db.val = (const float *)(dv + img.val) - (narrow_rows ? 0 : q0);    // absolute, or the chunk's own after a scan
+        db.row_len16 = nullptr; db.label_bits = nullptr;
         rc = gdmix_re_fit(&db, o, theta0 ? (const double *)(dv + img.theta0) - t0 : nullptr,
                           (double *)(dv + img.theta) - t0, (double *)(dv + img.f), (int32_t *)(dv + img.nit),
                           (int32_t *)(dv + img.nfev), (int32_t *)(dv + img.status),
@@ -1262,24 +1290,23 @@ int gdmix_re_score_host(const gdmix_re_batch *hb, const gdmix_lr_opts *o, const 
         CUDA_TRY(cudaMemcpyAsync(dv + o_row, hb->rowptr + r0, 8 * (nr + 1), cudaMemcpyHostToDevice, s.st));
         CUDA_TRY(cudaMemcpyAsync(dv + o_tp, hb->theta_ptr + e0, 8 * (Ec + 1), cudaMemcpyHostToDevice, s.st));
         if (nz) {
-            if (narrow == 1) {
-                CUDA_TRY(cudaMemcpyAsync(dv + o_nc, hb->col8 + q0, nz, cudaMemcpyHostToDevice, s.st));
-                gdmix::widen_u8_kernel<<<(int)std::min<int64_t>((nz / 16 + 255) / 256 + 1, 148 * 8), 256, 0, s.st>>>(
-                    (const uint8_t *)(dv + o_nc), (int32_t *)(dv + o_col), nz);
-                g_launches++;
-            } else if (narrow == 2) {
-                CUDA_TRY(cudaMemcpyAsync(dv + o_nc, hb->col16 + q0, 2 * nz, cudaMemcpyHostToDevice, s.st));
-                gdmix::widen_u16_kernel<<<(int)std::min<int64_t>((nz + 255) / 256, 148 * 8), 256, 0, s.st>>>(
-                    (const uint16_t *)(dv + o_nc), (int32_t *)(dv + o_col), nz);
-                g_launches++;
-            } else {
-                CUDA_TRY(cudaMemcpyAsync(dv + o_col, hb->col + q0, 4 * nz, cudaMemcpyHostToDevice, s.st));
-            }
+            if (narrow == 1) CUDA_TRY(cudaMemcpyAsync(dv + o_nc, hb->col8 + q0, nz, cudaMemcpyHostToDevice, s.st));
+            else if (narrow == 2) CUDA_TRY(cudaMemcpyAsync(dv + o_nc, hb->col16 + q0, 2 * nz, cudaMemcpyHostToDevice, s.st));
+            else CUDA_TRY(cudaMemcpyAsync(dv + o_col, hb->col + q0, 4 * nz, cudaMemcpyHostToDevice, s.st));
             CUDA_TRY(cudaMemcpyAsync(dv + o_val, hb->val + q0, 4 * nz, cudaMemcpyHostToDevice, s.st));
         }
         if (hb->offset) CUDA_TRY(cudaMemcpyAsync(dv + o_off, hb->offset + r0, 4 * nr, cudaMemcpyHostToDevice, s.st));
         if (theta) CUDA_TRY(cudaMemcpyAsync(dv + o_th, theta + t0, 8 * nt, cudaMemcpyHostToDevice, s.st));
         if (has_model) CUDA_TRY(cudaMemcpyAsync(dv + o_hm, has_model + e0, Ec, cudaMemcpyHostToDevice, s.st));
+        if (nz && narrow == 1) {           // after every copy of the chunk (see gdmix_re_fit_host)
+            gdmix::widen_u8_kernel<<<(int)std::min<int64_t>((nz / 16 + 255) / 256 + 1, 148 * 8), 256, 0, s.st>>>(
+                (const uint8_t *)(dv + o_nc), (int32_t *)(dv + o_col), nz);
+            g_launches++;
+        } else if (nz && narrow == 2) {
+            gdmix::widen_u16_kernel<<<(int)std::min<int64_t>((nz + 255) / 256, 148 * 8), 256, 0, s.st>>>(
+                (const uint16_t *)(dv + o_nc), (int32_t *)(dv + o_col), nz);
+            g_launches++;
+        }
         gdmix_re_batch db = *hb;
         db.n_entities = Ec;
         db.ent_rowptr = (const int64_t *)(dv + o_ent);

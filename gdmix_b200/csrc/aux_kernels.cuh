@@ -70,6 +70,23 @@ __global__ void __launch_bounds__(256) widen_u16_kernel(const uint16_t *in, int3
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth) out[i] = (int32_t)in[i];
 }
 
+// 16-bit row lengths (as they crossed PCIe) -> the u32 the scan kernels take
+__global__ void __launch_bounds__(256) widen_len16_kernel(const uint16_t *in, uint32_t *out, const int64_t n)
+{
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth) out[i] = (uint32_t)in[i];
+}
+
+// labels that crossed PCIe as bits: out[i] = bit (bit0 + i) of `bits`
+__global__ void __launch_bounds__(256) label_from_bits_kernel(const uint8_t *bits, const int bit0, float *out, const int64_t n)
+{
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth) {
+        const int64_t b = (int64_t)bit0 + i;
+        out[i] = (float)((bits[b >> 3] >> (b & 7)) & 1u);
+    }
+}
+
 // 8-bit local column indices (entities with at most 256 local features): 16 per thread and trip
 __global__ void __launch_bounds__(256) widen_u8_kernel(const uint8_t *in, int32_t *out, const int64_t n)
 {

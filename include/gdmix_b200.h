@@ -119,6 +119,13 @@ typedef struct gdmix_re_batch {
     /* Likewise as 8-bit values (valid when every entity has at most 256 local features -- the C1 shape): one
      * byte per non-zero crosses PCIe.  Takes precedence over col16. */
     const uint8_t *col8;
+    /* Optional, gdmix_re_fit_host only: the non-zeros of every row as 16-bit values (valid when no row has more than
+     * 65535).  When set, 2 instead of 8 bytes per row cross PCIe and the row pointers are rebuilt on the device by a
+     * scan; `rowptr` stays required on the host side (the chunks are cut with it). */
+    const uint16_t *row_len16;
+    /* Likewise the 0/1 labels as bits, row i at bit (i & 7) of byte (i >> 3): 1/8 instead of 4 bytes per row.  When
+     * set, `label` may be NULL. */
+    const uint8_t *label_bits;
 } gdmix_re_batch;
 
 /* LRParams / scipy knobs (base_lr_params.py:5-42; scipy defaults for the rest). */

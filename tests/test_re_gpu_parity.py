@@ -252,6 +252,34 @@ def test_logistic_terms_accuracy():
     assert (o2[:, 0] > 0).all() and (o2[:, 0] < 1e-307).all() and (o2[:, 2] == 1.0).all() and (o2[:, 1] < 1e-307).all()
 
 
+def test_narrow_row_lengths_and_label_bits_are_bit_identical(monkeypatch):
+    """gdmix_re_batch.row_len16 / label_bits (2 bytes and 1 bit per row across PCIe instead of 8 + 4 bytes): the row
+    pointers rebuilt on the device by a scan and the labels expanded from bits give the fits the int64 / fp32 arrays
+    give, bit for bit -- with ragged rows, empty rows and chunk boundaries that do not fall on a multiple of 8 rows."""
+    import ctypes as C
+    hb = make_batch(157, 19, 40, 5, seed=13, ragged=True)
+    opts = capi.make_opts()
+    E, T = hb.n_entities, hb.n_coef
+
+    def run(cb, chunk):
+        theta = np.zeros(T); nit = np.zeros(E, np.int32)
+        capi.check(capi.lib.gdmix_re_fit_host(C.byref(cb), C.byref(opts), None, theta.ctypes.data_as(C.c_void_p), None,
+                                              nit.ctypes.data_as(C.c_void_p), None, None, None, C.c_int64(chunk)))
+        return theta, nit
+    wide = hb.c_struct(narrow=False)
+    assert wide.row_len16 is None and wide.label_bits is None
+    narrow = hb.c_struct(narrow=True)
+    assert narrow.row_len16 is not None and narrow.label_bits is not None
+    only_bits = hb.c_struct(narrow=True)      # label bits alone (label pointer NULL)
+    only_bits.label = None
+    for chunk in (0, 37, 1):                  # (the launch plan follows a chunk's shapes: compare like with like)
+        ref = run(wide, chunk)
+        for cb in (narrow, only_bits):
+            got = run(cb, chunk)
+            np.testing.assert_array_equal(got[0], ref[0])
+            np.testing.assert_array_equal(got[1], ref[1])
+
+
 def test_bad_column_index_is_rejected():
     hb = make_batch(8, 16, 24, 4, seed=1)
     hb.col[5] = 9999
