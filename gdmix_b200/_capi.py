@@ -211,9 +211,11 @@ class HostBatch:
         self.max_coef = int(coef.max()) if self.n_entities else 0
         self.n_coef = int(self.theta_ptr[-1])
 
-    def c_struct(self, narrow=None):
+    def c_struct(self, narrow=None, narrow_rows=False):
         """narrow=True sends the local column indices as uint16 (half the PCIe bytes for them); default: whenever
-        every entity has fewer than 65536 local features."""
+        every entity has fewer than 65536 local features.  narrow_rows=True also builds the 16-bit row lengths and
+        the label bits gdmix_re_fit_host can take instead of the int64 row pointers / fp32 labels (-5 % of the bytes:
+        worth it for a caller that keeps the batch, not for one numpy pass per partition)."""
         if narrow is None:
             narrow = (self.max_coef < 65536 and self.nnz > 0) or self.col is None
         if not narrow and self.col is None:
@@ -233,7 +235,7 @@ class HostBatch:
             c8 = self._col_narrow if self._col_narrow.dtype == np.uint8 else None
             c16 = self._col_narrow if c8 is None else None
         rl16 = bits = None
-        if narrow and self.n_rows > 0:
+        if narrow and narrow_rows and self.n_rows > 0:
             # what else gdmix_re_fit_host can take narrow: 16-bit row lengths instead of the int64 row pointers
             # (-6 bytes per row on PCIe) and the 0/1 labels as bits (-3.9 bytes per row)
             if getattr(self, "_rows_narrow", None) is None:

@@ -268,9 +268,10 @@ def test_narrow_row_lengths_and_label_bits_are_bit_identical(monkeypatch):
         return theta, nit
     wide = hb.c_struct(narrow=False)
     assert wide.row_len16 is None and wide.label_bits is None
-    narrow = hb.c_struct(narrow=True)
+    assert hb.c_struct(narrow=True).row_len16 is None
+    narrow = hb.c_struct(narrow=True, narrow_rows=True)
     assert narrow.row_len16 is not None and narrow.label_bits is not None
-    only_bits = hb.c_struct(narrow=True)      # label bits alone (label pointer NULL)
+    only_bits = hb.c_struct(narrow=True, narrow_rows=True)      # label bits alone (label pointer NULL)
     only_bits.label = None
     for chunk in (0, 37, 1):                  # (the launch plan follows a chunk's shapes: compare like with like)
         ref = run(wide, chunk)
