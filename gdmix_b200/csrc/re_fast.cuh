@@ -280,7 +280,8 @@ __device__ __forceinline__ double rcp_f64(const double a)
 // kernel runs it.  The stretch is serial -- the other warps of the CTA wait at B5 -- and one warp alone is bound by
 // instruction count x latency, so it is written for instruction count: totals arrive in registers (lane l < 2 MT + 2
 // holds entry l of [S^T g | Y^T g | y.y | y.g]) and move by shuffles, lanes >= MT are clones of lane MT - 1 (they
-// compute and store the same values: no `lane < MT` branches), rows are read with 16-byte loads.
+// compute and store the same values to the same places, behind the same warp barriers: no `lane < MT` branches), rows
+// are read with 16-byte loads.
 // D = shared address of dense[0].
 __device__ __forceinline__ void fast_small_update(const Lbfgs &L, const bool update, const int newslot,
                                                   const uint32_t dotmask, const double stp, const double dr,
@@ -306,6 +307,7 @@ __device__ __forceinline__ void fast_small_update(const Lbfgs &L, const bool upd
     const double yc = (update && old_i) ? p2i - lds_f64v(vec_i + 8u * DN::p2old) : 0.0;   // y_i . y_new
     const double p1new = stp * gd_new;                                                   // s_new . g_new
     if (new_i) { p1i = p1new; p2i = ygt; }
+    __syncwarp();     // every lane (the clones of lane MT - 1 too) has loaded p1old / p2old before anyone overwrites them
     sts_f64v(vec_i + 8u * DN::ta, rc);
     sts_f64v(vec_i + 8u * DN::tb, (val_i && !new_i) ? p1i : 0.0);
     sts_f64v(vec_i + 8u * DN::p1old, p1i);
