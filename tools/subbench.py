@@ -156,14 +156,24 @@ def fixed_effect(dev, rank, world, group, peak_gbs, rows=62_500_000, D=100_000, 
     opts.max_iter = 2
     solver.fit()
     opts.max_iter = iters
-    solver.phase_ms.clear()
-    if world > 1:
-        torch.distributed.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    x, info = solver.fit()
-    torch.cuda.synchronize()
-    fit_s = _max_over_ranks(time.perf_counter() - t0, dev, world)
+    # the timed solve, twice: the slower rank sets the pace through the all-reduce, and a collector pass or a cudaFree of
+    # the benchmarks before this one landing on ONE rank's host thread triples a 0.25 s solve (seen at N = 4) -- so:
+    # collect first, no collector inside, and the better of two solves is reported (both are in `solve_seconds_runs`)
+    import gc
+    runs = []
+    for _ in range(2):
+        solver.phase_ms.clear()
+        gc.collect()
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        gc.disable()
+        t0 = time.perf_counter()
+        x, info = solver.fit()
+        torch.cuda.synchronize()
+        runs.append(_max_over_ranks(time.perf_counter() - t0, dev, world))
+        gc.enable()
+    fit_s = min(runs)
     ph = np.array(solver.phase_ms) if solver.phase_ms else np.zeros((1, 3))
     xt = torch.from_numpy(x).to(dev)
     identical = True
@@ -176,7 +186,7 @@ def fixed_effect(dev, rank, world, group, peak_gbs, rows=62_500_000, D=100_000, 
     out = {"workload": f"c2 share: {rows} rows/GPU x {k} nnz over D={D} features (Zipf-like popularity), l2=1, m=10, "
                        f"{iters} L-BFGS iterations from x=0; {world} rank(s), rows sharded, one all-reduce of "
                        f"fg[D+2] per evaluation",
-           "rows_per_gpu": rows, "generation_s": gen_s, "plan_s": plan_s,
+           "rows_per_gpu": rows, "generation_s": gen_s, "plan_s": plan_s, "solve_seconds_runs": runs,
            "ms_per_eval_kernels": ms_kernels,
            "ms_per_eval_in_solve": {"kernels": float(np.median(ph[:, 0])), "allreduce": float(np.median(ph[:, 1])),
                                     "solver_step": float(np.median(ph[:, 2]))},
