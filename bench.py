@@ -643,7 +643,7 @@ def main():
     ap.add_argument("--sweep-entities", type=int, default=2_000_000)
     ap.add_argument("--fe-rows", type=int, default=62_500_000)
     ap.add_argument("--chain-rows", type=int, default=40_000_000)
-    ap.add_argument("--plugin-entities", type=int, default=50_000, help="entities of the generated partition of the e2e_plugin leg (0: skip)")
+    ap.add_argument("--plugin-entities", type=int, default=100_000, help="entities of the generated partition of the e2e_plugin leg (0: skip)")
     ap.add_argument("--threads-per-entity", type=int, default=0)
     ap.add_argument("--probe", default=None, help="internal: the workload ncu profiles for roofline.traffic")
     args = ap.parse_args()
