@@ -1,5 +1,8 @@
-import sys, time
-sys.path.insert(0, '/root/repo')
+#!/usr/bin/env python
+"""gdmix_re_fit_host / gdmix_re_score_host on 100 K C1 entities held in page-locked arrays (what the plugin path hands
+them): seconds per call, and the C call alone.  Usage: python tools/score_probe.py"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from gdmix_b200 import _capi as capi
 from gdmix_b200.synth_arrays import make_arrays
