@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Seconds to build the tiled fixed-effect plan of a C2-sized shard, three times in a row (allocation state varies).
 Usage: python tools/plan_probe.py [rows]"""
-import os, sys, time, os
+import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gdmix_b200 import _capi as capi

@@ -13,3 +13,6 @@ run() { local name=$1 tool=$2 lim=$3; shift 3
 }
 run memcheck_re memcheck 900 tests/test_re_gpu_parity.py -k "(test_golden_fit_matches_reference and 0]) or test_golden_variances or test_deferred_entities or test_narrow_row or test_scoring or test_logistic or test_golden_loss_grad"
 run racecheck_re_fast racecheck 900 tests/test_re_gpu_parity.py -k "test_golden_fit_matches_reference and 0] and auto"
+run memcheck_fe memcheck 900 tests/test_fe_gpu.py -k "not large_zipf"
+run racecheck_fe racecheck 900 tests/test_fe_gpu.py -k "reference_restatement or tiled_objective_edge or rows_of_every_size or device_lbfgs_retraces"
+run memcheck_partition memcheck 600 tests/test_partition_gpu.py
