@@ -610,3 +610,28 @@ def test_warp_per_entity_tier_solves_what_fits_and_defers_the_rest(monkeypatch, 
     rel = _rel_per_entity(out["theta"].cpu().numpy(), th_o, hb.theta_ptr)
     assert rel.max() <= 1e-9, rel.max()
     assert (out["nit"].cpu().numpy() == nit_o).all() and (out["status"].cpu().numpy() == st_o).all()
+
+
+def test_pinned_pool_reuses_blocks_and_narrow_columns_checks_its_range():
+    """_capi.pinned_empty: page-locked blocks come back from the pool when the last view of them dies and are handed
+    out again; gdmix_narrow_columns refuses a value that does not fit the width."""
+    import gc
+    a = capi.pinned_empty(1 << 20, np.float32)
+    assert torch.from_numpy(a).is_pinned() or capi._pinned_pool.available   # page-locked (torch sees cudaHostAlloc memory)
+    addr = a.ctypes.data
+    a[:] = 1.0
+    view = a[10:20]
+    del a
+    gc.collect()
+    b = capi.pinned_empty(1 << 20, np.float32)
+    bdata = b.ctypes.data
+    assert bdata != addr                    # the first block is still alive behind `view`
+    del view, b
+    gc.collect()
+    c = capi.pinned_empty(1 << 20, np.float32)
+    assert c.ctypes.data in {addr, bdata}   # ... and now one of the two freed blocks is handed out again
+    col = np.array([0, 5, 255, 256], np.int32)
+    with pytest.raises(capi.GdmixError):
+        capi.narrow_columns(col, 1)
+    np.testing.assert_array_equal(capi.narrow_columns(col, 2), col.astype(np.uint16))
+    np.testing.assert_array_equal(capi.narrow_columns(col[:3], 1), col[:3].astype(np.uint8))
