@@ -267,14 +267,15 @@ class HostBatch:
 def re_fit_host(batch, opts, theta0=None, want_variance=False, chunk_entities=0):
     """gdmix_re_fit_host: numpy in, numpy out (theta, f, nit, nfev, status[, variance])."""
     E, T = batch.n_entities, batch.n_coef
-    theta = pinned_empty(T, np.float64); theta.fill(0.0)      # D2H targets: page-locked, from the library's pool
+    theta = pinned_empty(T, np.float64)      # D2H targets: page-locked, from the library's pool; every coefficient of
+    #                                           every entity is written by the call (or it fails), so no zero fill
     f = np.zeros(E, np.float64)
     nit = np.zeros(E, np.int32)
     nfev = np.zeros(E, np.int32)
     status = np.zeros(E, np.int32)
     var = None
     if want_variance:
-        var = pinned_empty(T, np.float64); var.fill(0.0)
+        var = pinned_empty(T, np.float64)
     t0 = None if theta0 is None else np.ascontiguousarray(theta0, dtype=np.float64)
     cb = batch.c_struct()
     check(lib.gdmix_re_fit_host(C.byref(cb), C.byref(opts), _np_ptr(t0), _np_ptr(theta), _np_ptr(f), _np_ptr(nit),
@@ -286,8 +287,8 @@ def re_fit_host(batch, opts, theta0=None, want_variance=False, chunk_entities=0)
 
 
 def re_score_host(batch, opts, theta, has_model=None):
-    logit = pinned_empty(batch.n_rows, np.float32); logit.fill(0.0)
-    per = pinned_empty(batch.n_rows, np.float32); per.fill(0.0)
+    logit = pinned_empty(batch.n_rows, np.float32)       # every row is written by the call
+    per = pinned_empty(batch.n_rows, np.float32)
     th = None if theta is None else np.ascontiguousarray(theta, dtype=np.float64)
     hm = None if has_model is None else np.ascontiguousarray(has_model, dtype=np.uint8)
     cb = batch.c_struct()
