@@ -916,10 +916,17 @@ def _feature_tables(feature_names, feature_terms):
 
 
 def avro_model_blocks(model_ids, coef, var, coef_ptr, feat_idx, has_intercept, threshold, feature_names, feature_terms,
-                      model_class, intercept_name, sync, records_per_block=1024):
+                      model_class, intercept_name, sync, records_per_block=1024, id_table=None):
     """-> bytes: the blocks of an Avro container holding these BayesianLinearModelAvro records
-    (gdmix_avro_model_blocks; the layout of its arguments is documented in include/gdmix_b200.h)."""
-    idc, idp = _string_table([str(m) for m in model_ids])
+    (gdmix_avro_model_blocks; the layout of its arguments is documented in include/gdmix_b200.h).
+    id_table = (uint8 utf-8 characters, int64 offsets [n + 1]) of the model ids when the caller has them as arrays
+    already (the reader's own table): no per-id Python work."""
+    if id_table is not None and id_table[1].shape[0] == len(model_ids) + 1:
+        idc, idp = np.ascontiguousarray(id_table[0], dtype=np.uint8), np.ascontiguousarray(id_table[1], dtype=np.int64)
+        if idc.size == 0:
+            idc = np.zeros(1, np.uint8)
+    else:
+        idc, idp = _string_table([str(m) for m in model_ids])
     nc, npt, tc, tpt = _feature_tables(feature_names, feature_terms)
     coef = np.ascontiguousarray(coef, dtype=np.float64)
     var = None if var is None else np.ascontiguousarray(var, dtype=np.float64)

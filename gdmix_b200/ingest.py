@@ -164,10 +164,15 @@ def _read_entity_grouped_native(files, entity_name, feature_bag, label_column, o
                 rng = (capi.seqex_fill_local_into if fused else capi.seqex_fill_into)(buf, spec, out, *starts[k], idc, idp)
             except capi.GdmixError as ex:
                 if fused and ex.code == capi.GDMIX_ERR_TOO_LARGE:
-                    return None, None
+                    return None, None, None
                 raise ValueError(f"{files[k]}: {ex}") from None
             raw = idc.tobytes()
-            return [raw[idp[e]:idp[e + 1]].decode("utf-8") for e in range(sz.n_entities)], rng
+            if raw.isascii():      # byte offsets are character offsets: one decode, then slices
+                txt, pl = raw.decode("ascii"), idp.tolist()
+                ids_k = [txt[pl[e]:pl[e + 1]] for e in range(sz.n_entities)]
+            else:
+                ids_k = [raw[idp[e]:idp[e + 1]].decode("utf-8") for e in range(sz.n_entities)]
+            return ids_k, rng, (idc[:sz.id_bytes], idp)
 
         filled = list(pool.map(fill, range(len(files))))
         if any(f[0] is None for f in filled):
@@ -176,6 +181,14 @@ def _read_entity_grouped_native(files, entity_name, feature_bag, label_column, o
                                                weight_column, uid_column, num_features, input_path, fused=False)
         ids = [f[0] for f in filled]
         ranges = [f[1] for f, (_, sz) in zip(filled, counted) if sz.nnz]
+        # the ids once more as one (characters, offsets) table: what the model writer takes without touching a str
+        id_chars = np.concatenate([f[2][0] for f in filled]) if filled else np.zeros(0, np.uint8)
+        id_ptr = np.zeros(E + 1, np.int64)
+        at, base = 0, 0
+        for f, (_, sz) in zip(filled, counted):
+            id_ptr[at:at + sz.n_entities + 1] = f[2][1][:sz.n_entities + 1] + base
+            at += sz.n_entities
+            base += sz.id_bytes
     all_labelled = all(sz.all_labelled for _, sz in counted)
     index_lo = min((r[0] for r in ranges), default=0)      # tracked by the parser's filling pass
     index_hi = max((r[1] for r in ranges), default=0)
@@ -184,6 +197,7 @@ def _read_entity_grouped_native(files, entity_name, feature_bag, label_column, o
     d = EntityGroupedData()
     d.num_features = int(num_features)
     d.entity_ids = [i for part in ids for i in part]
+    d.entity_id_table = (id_chars, id_ptr)
     d.has_weight_column = saw_weight
     d.ent_rowptr = np.zeros(E + 1, np.int64)
     np.cumsum(out["ent_rows"], out=d.ent_rowptr[1:])

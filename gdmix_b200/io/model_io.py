@@ -169,7 +169,7 @@ def _feature_columns(feature_file):
 
 
 def export_random_effect_models(model_ids, coef, var, coef_ptr, feat_idx, has_intercept, feature_file, output_file,
-                                model_class=LOGISTIC_MODEL_CLASS, sparsity_threshold=1.0e-4, sync=None):
+                                model_class=LOGISTIC_MODEL_CLASS, sparsity_threshold=1.0e-4, sync=None, id_table=None):
     """The same file export_linear_model_to_avro writes for per-entity models, from flat arrays: model m owns
     coef[coef_ptr[m]:coef_ptr[m+1]] (intercept first when has_intercept; var aligned or None) and feat_idx lists the
     global feature ids of its other coefficients.  Records are encoded by the library (gdmix_avro_model_blocks)."""
@@ -177,7 +177,7 @@ def export_random_effect_models(model_ids, coef, var, coef_ptr, feat_idx, has_in
     names, terms = _feature_columns(feature_file)
     with avro.Writer(output_file, BAYESIAN_LINEAR_MODEL_SCHEMA, "null", sync=sync) as w:
         body = capi.avro_model_blocks(model_ids, coef, var, coef_ptr, feat_idx, has_intercept, sparsity_threshold,
-                                      names, terms, model_class, INTERCEPT, w.sync)
+                                      names, terms, model_class, INTERCEPT, w.sync, id_table=id_table)
         w.f.write(body)
         w.count += len(model_ids)
         return w.count

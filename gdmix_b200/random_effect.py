@@ -45,9 +45,10 @@ class FlatModels:
     then never becomes a million Python tuples: the model writer and the scoring pass take the arrays as they are, and
     a TrainingResult is only built for an entity somebody asks for."""
 
-    def __init__(self, entity_ids, theta, variance, theta_ptr, uniq_ptr, uniq_global):
+    def __init__(self, entity_ids, theta, variance, theta_ptr, uniq_ptr, uniq_global, id_table=None):
         self.entity_ids = list(entity_ids)
         self.source_ids = entity_ids      # the parsed partition's own list: identity tells "same partition" in O(1)
+        self.id_table = id_table          # (utf-8 characters, offsets) of the ids as the reader left them, or None
         self.theta, self.variance = theta, variance
         self.theta_ptr, self.uniq_ptr, self.uniq_global = theta_ptr, uniq_ptr, uniq_global
         self._index = None
@@ -259,7 +260,7 @@ class RandomEffectLRLBFGSModel(Model):
             t0 = time.perf_counter()
             self.last_fit_info = {k: out[k] for k in ("nit", "nfev", "status", "f")}
             results = FlatModels(data.entity_ids, out["theta"], out["variance"] if vmode != capi.VARIANCE_NONE else None,
-                                 hb.theta_ptr, uniq_ptr, uniq_global)
+                                 hb.theta_ptr, uniq_ptr, uniq_global, id_table=getattr(data, "entity_id_table", None))
             if model_weights:
                 # prior-only entities survive; prior-only features of a retrained entity do not (:161)
                 model_weights = dict(model_weights.items())
@@ -335,7 +336,8 @@ class RandomEffectLRLBFGSModel(Model):
             os.makedirs(os.path.dirname(output_file) or ".", exist_ok=True)
             model_io.export_random_effect_models(fm.entity_ids, fm.theta, fm.variance if with_variance else None,
                                                  fm.theta_ptr, fm.uniq_global, self.has_intercept, feature_file,
-                                                 output_file, sparsity_threshold=self.model_params.sparsity_threshold)
+                                                 output_file, sparsity_threshold=self.model_params.sparsity_threshold,
+                                                 id_table=getattr(fm, "id_table", None))
             return
         model_ids = list(model_coefficients.keys())
         means, variances, indices = [], [], []

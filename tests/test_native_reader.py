@@ -572,3 +572,27 @@ def test_fused_reader_falls_back_beyond_65535_distinct_features(tmp_path):
     assert int(np.diff(up).max()) >= 70000
     with pytest.raises(ValueError):
         ingest.read_entity_grouped(str(tmp_path), **dict(kw, num_features=1000))
+
+
+def test_model_writer_takes_the_readers_id_table(tmp_path):
+    """avro_model_blocks with the ids as a (characters, offsets) table -- what the reader hands on -- writes the bytes
+    it writes from the list of strings; the reader's table matches its own list of ids (ASCII and UTF-8 ids)."""
+    rng = np.random.default_rng(4)
+    for ids in ([str(x) for x in rng.integers(0, 1 << 40, 50)], [f"mémbre-{k}" for k in range(50)]):
+        coef_ptr = np.arange(51, dtype=np.int64) * 4
+        coef = rng.standard_normal(200)
+        feat_idx = rng.integers(0, 30, 150).astype(np.int64)
+        names, terms = [f"f{j}" for j in range(30)], [""] * 30
+        sync = bytes(range(16))
+        a = capi.avro_model_blocks(ids, coef, None, coef_ptr, feat_idx, True, 1e-4, names, terms, "cls", "(INTERCEPT)", sync)
+        table = capi._string_table(ids)
+        b = capi.avro_model_blocks(ids, coef, None, coef_ptr, feat_idx, True, 1e-4, names, terms, "cls", "(INTERCEPT)", sync,
+                                   id_table=table)
+        assert bytes(a) == bytes(b)
+    # the reader's table
+    _partition_file(tmp_path, rng, 40, 3, 5, 100)
+    files = ingest.list_tfrecord_files(str(tmp_path), 1, 0)
+    d = ingest._read_entity_grouped_native(files, "ent", "bag", "y", "off", "w", "uid", 100, str(tmp_path))
+    chars, ptr = d.entity_id_table
+    raw = chars.tobytes()
+    assert [raw[ptr[e]:ptr[e + 1]].decode("utf-8") for e in range(d.n_entities)] == d.entity_ids
